@@ -1,0 +1,83 @@
+"""ctypes binding of ``libsted_b200.so`` (the C ABI declared in ``include/sted_b200.h``).
+
+There is no CPU fallback: importing this module without the built library raises, and every
+compute entry point returns ``STED_ENODEVICE`` (raised here as ``StedError``) without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsted_b200.so")
+
+STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH = 1, 2, 4
+STED_TAB_E, STED_TAB_ET, STED_TAB_CH, STED_TAB_RS, STED_TABLES = 0, 1, 2, 3, 4
+STED_MAX_K = 63
+
+
+def kpitch(K: int) -> int:
+    return ((K + 1) + 3) & ~3
+
+
+class StedError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"sted_b200 error {code}: {message}")
+        self.code = code
+
+
+class StedFluoParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in (
+        "lambda_ex", "lambda_sted", "lambda_fluo", "sigma_abs_ex", "sigma_abs_sted", "sigma_ste", "qy", "tau",
+        "tau_vib", "tau_tri", "k0", "k1", "b", "triplet_dynamics_frac", "sted_tau", "sted_rate")] + [
+        ("anti_stoke", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+
+
+class StedDetectorParams(ctypes.Structure):
+    _fields_ = [("pcef", ctypes.c_double), ("pdef", ctypes.c_double), ("background", ctypes.c_double)]
+
+
+_vp, _i, _u32, _u64, _i64, _d = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64,
+                                 ctypes.c_double)
+
+# name -> (restype, argtypes); every symbol include/sted_b200.h declares
+SIGNATURES = {
+    "sted_version": (ctypes.c_char_p, []),
+    "sted_last_error": (ctypes.c_char_p, []),
+    "sted_device_count": (_i, []),
+    "sted_make_effective": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "sted_acquire": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _u32, ctypes.POINTER(StedDetectorParams), _d, _u64,
+                          _u64, _i64, _vp, _vp, _vp]),
+    "sted_acquire_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _u32,
+                               ctypes.POINTER(StedDetectorParams), _u64, _u64, _i64, _vp, _vp]),
+    "sted_sample_poisson": (_i, [_vp, _i64, _u64, _u64, _vp, _vp]),
+    "sted_sample_binomial": (_i, [_vp, _vp, _i64, _u64, _u64, _vp, _vp]),
+    "sted_philox4x32_10": (None, [ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),
+    "sted_fma_peak": (_i, [ctypes.POINTER(_d), _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (raises ``OSError`` with a build hint when it is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). gym_sted_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise StedError(rc, load().sted_last_error().decode())
+
+
+def device_count() -> int:
+    return load().sted_device_count()

@@ -1,0 +1,260 @@
+"""``pysted.base``-compatible facade over the CUDA hot path (Python level).
+
+Same names, argument meaning and mutation semantics as the pySTED objects gym-sted builds in
+``gym_sted/utils.py:151-182`` and calls at ``gym_sted/envs/mosted_env.py:184,222,227,232``:
+
+* ``Microscope.cache(px)`` -> ``(i_ex, i_sted, psf_det)`` (host set-up, ``physics.py``);
+* ``Microscope.get_effective(px, p_ex, p_sted)`` -> ``(K,K)`` array, formed on the GPU;
+* ``Microscope.get_signal_and_bleach(datamap, pixelsize, pdt, p_ex, p_sted, bleach=True,
+  update=True, seed=None)`` -> ``(photons, {"base": bleached}, intensity)``; with ``bleach`` and
+  ``update`` the datamap is mutated in place like pySTED does;
+* ``Datamap(whole_datamap, datamap_pixelsize)``, ``.set_roi(i_ex, "max")``, ``.roi``,
+  ``.whole_datamap``, ``["base"]``.
+
+Everything numeric goes through ``libsted_b200.so``; there is no numpy fallback for the scan.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib, physics
+
+_PSF_CACHE: dict = {}
+
+
+class GaussianBeam:
+    def __init__(self, lambda_, **kwargs):
+        self.lambda_ = lambda_
+        self.polarization = kwargs.get("polarization", np.pi / 2)
+        self.beta = kwargs.get("beta", np.pi / 4)
+
+    def get_intensity(self, power, f, n, na, transmission, datamap_pixelsize):
+        return physics.gaussian_beam_intensity(self.lambda_, power, n, na, transmission, datamap_pixelsize,
+                                               self.polarization, self.beta)
+
+
+class DonutBeam:
+    def __init__(self, lambda_, **kwargs):
+        self.lambda_ = lambda_
+        self.polarization = kwargs.get("polarization", np.pi / 4)
+        self.beta = kwargs.get("beta", np.pi / 2)
+        self.tau = kwargs.get("tau", 400e-12)
+        self.rate = kwargs.get("rate", 40e6)
+        self.zero_residual = kwargs.get("zero_residual", 0)
+        self.anti_stoke = kwargs.get("anti_stoke", True)
+
+    def get_intensity(self, power, f, n, na, transmission, datamap_pixelsize):
+        return physics.donut_beam_intensity(self.lambda_, power, n, na, transmission, datamap_pixelsize, self.tau,
+                                            self.rate, self.zero_residual, self.polarization, self.beta)
+
+
+class Objective:
+    def __init__(self, f=2e-3, n=1.5, na=1.4, transmission=None):
+        self.f, self.n, self.na = f, n, na
+        self.transmission = dict(transmission or {})
+
+    def get_transmission(self, lambda_):
+        return self.transmission[int(round(lambda_ * 1e9))]
+
+
+class Detector:
+    def __init__(self, **kwargs):
+        self.n_airy = kwargs.get("n_airy", 0.7)
+        self.noise = kwargs.get("noise", False)
+        self.background = kwargs.get("background", 0.0)
+        self.pcef = kwargs.get("pcef", 0.1)
+        self.pdef = kwargs.get("pdef", 0.5)
+
+    def get_detection_psf(self, lambda_, na, transmission, datamap_pixelsize):
+        return physics.detection_psf(lambda_, na, transmission, datamap_pixelsize, self.n_airy)
+
+    def get_signal(self, photons, dwelltime, rate=None, seed=None):
+        """Host twin of the fused detector epilogue, kept for ``FluorescenceOptimizer``
+        (``gym_sted/utils.py:654-657``), which calls it on a scalar."""
+        mean = np.asarray(photons, dtype=np.float64) * self.pcef * self.pdef * dwelltime
+        if not self.noise:
+            return mean + self.background * dwelltime
+        rng = np.random.default_rng(seed)
+        signal = rng.poisson(mean)
+        if self.background > 0:
+            signal = signal + rng.poisson(self.background * dwelltime, np.shape(mean))
+        return signal
+
+    def params(self):
+        return _lib.StedDetectorParams(self.pcef, self.pdef, self.background)
+
+
+class Fluorescence:
+    def __init__(self, lambda_, **kwargs):
+        self.lambda_ = lambda_
+        self.qy = kwargs.get("qy", 0.65)
+        self.sigma_abs = dict(kwargs.get("sigma_abs", {}))
+        self.sigma_ste = dict(kwargs.get("sigma_ste", {}))
+        self.tau = kwargs.get("tau", 3.5e-9)
+        self.tau_vib = kwargs.get("tau_vib", 1e-12)
+        self.tau_tri = kwargs.get("tau_tri", 1.2e-6)
+        self.k0 = kwargs.get("k0", 0)
+        self.k1 = kwargs.get("k1", 2.9e-16)
+        self.b = kwargs.get("b", 1.66)
+        self.triplet_dynamics_frac = kwargs.get("triplet_dynamics_frac", 0)
+
+    def get_sigma_abs(self, lambda_):
+        return self.sigma_abs[int(round(lambda_ * 1e9))]
+
+    def get_sigma_ste(self, lambda_):
+        return self.sigma_ste[int(round(lambda_ * 1e9))]
+
+    def get_photons(self, intensity, lambda_=None):
+        lambda_ = self.lambda_ if lambda_ is None else lambda_
+        return np.asarray(intensity, dtype=np.float64) // (physics.H_PLANCK * physics.C_LIGHT / lambda_)
+
+
+def fluo_struct(fluo: Fluorescence, excitation: GaussianBeam, sted: DonutBeam) -> _lib.StedFluoParams:
+    if fluo.triplet_dynamics_frac:
+        raise NotImplementedError("triplet_dynamics_frac != 0 is outside the modelled path "
+                                  "(every gym-sted parameter set uses 0: defaults.py:41, routines.json)")
+    return _lib.StedFluoParams(
+        excitation.lambda_, sted.lambda_, fluo.lambda_, fluo.get_sigma_abs(excitation.lambda_),
+        fluo.sigma_abs.get(int(round(sted.lambda_ * 1e9)), 0.0), fluo.get_sigma_ste(sted.lambda_), fluo.qy, fluo.tau,
+        fluo.tau_vib, fluo.tau_tri, fluo.k0, fluo.k1, fluo.b, fluo.triplet_dynamics_frac, sted.tau, sted.rate,
+        int(bool(sted.anti_stoke)), 0)
+
+
+class Datamap:
+    """``pysted.base.Datamap``: zero-pads the molecule map by K//2 and remembers the ROI slices."""
+
+    def __init__(self, whole_datamap, datamap_pixelsize):
+        self.whole_datamap = np.array(whole_datamap)
+        self.whole_shape = self.whole_datamap.shape
+        self.pixelsize = datamap_pixelsize
+        self.roi = None
+        self.roi_corners = None
+        self.sub_datamaps_dict = {}
+
+    def set_roi(self, laser, intervals="max"):
+        if intervals != "max":
+            raise NotImplementedError("only the 'max' ROI used by gym-sted (utils.py:180) is supported")
+        p = laser.shape[0] // 2
+        h, w = self.whole_datamap.shape
+        self.whole_datamap = np.pad(self.whole_datamap, p)
+        self.roi = (slice(p, p + h), slice(p, p + w))
+        self.roi_corners = {"tl": (p, p), "tr": (p, p + w - 1), "bl": (p + h - 1, p), "br": (p + h - 1, p + w - 1)}
+        self.sub_datamaps_dict = {"base": self.whole_datamap}
+
+    def __getitem__(self, key):
+        return self.sub_datamaps_dict[key]
+
+
+class Microscope:
+    def __init__(self, excitation, sted, detector, objective, fluo, load_cache=False, verbose=False):
+        self.excitation, self.sted, self.detector, self.objective, self.fluo = excitation, sted, detector, objective, fluo
+        self._acq_counter = 0
+
+    # ---- a1: host set-up ------------------------------------------------------------------
+    def _cache_key(self, px):
+        o, e, s, d = self.objective, self.excitation, self.sted, self.detector
+        return (int(round(px * 1e11)), e.lambda_, e.polarization, e.beta, s.lambda_, s.polarization, s.beta, s.tau,
+                s.rate, s.zero_residual, self.fluo.lambda_, d.n_airy, o.n, o.na,
+                o.get_transmission(e.lambda_), o.get_transmission(s.lambda_), o.get_transmission(self.fluo.lambda_))
+
+    def is_cached(self, datamap_pixelsize):
+        return self._cache_key(datamap_pixelsize) in _PSF_CACHE
+
+    def cache(self, datamap_pixelsize, save_cache=False):
+        key = self._cache_key(datamap_pixelsize)
+        if key not in _PSF_CACHE:
+            o = self.objective
+            i_ex = self.excitation.get_intensity(1, o.f, o.n, o.na, o.get_transmission(self.excitation.lambda_),
+                                                 datamap_pixelsize)
+            i_sted = self.sted.get_intensity(1, o.f, o.n, o.na, o.get_transmission(self.sted.lambda_),
+                                             datamap_pixelsize)
+            psf_det = self.detector.get_detection_psf(self.fluo.lambda_, o.na, o.get_transmission(self.fluo.lambda_),
+                                                      datamap_pixelsize)
+            _PSF_CACHE[key] = physics.resize_common(i_ex, i_sted, psf_det)
+        return _PSF_CACHE[key]
+
+    def clear_cache(self):
+        _PSF_CACHE.clear()
+
+    def _packed_cache(self, px):
+        return np.ascontiguousarray(np.stack(self.cache(px)), dtype=np.float64)
+
+    # ---- a2 / a3 on the device -------------------------------------------------------------
+    def _tables(self, px, p_ex, p_sted, pdt):
+        import torch  # device memory only
+        lib = _lib.load()
+        cache = self._packed_cache(px)
+        K = cache.shape[-1]
+        dev = torch.device("cuda")
+        d_cache = torch.from_numpy(cache).to(dev)
+        fl = fluo_struct(self.fluo, self.excitation, self.sted)
+        d_fluo = torch.frombuffer(bytearray(bytes(fl)), dtype=torch.uint8).to(dev)
+        scal = torch.tensor([[p_ex], [p_sted], [pdt]], dtype=torch.float64, device=dev)
+        tables = torch.empty((1, _lib.STED_TABLES, K, _lib.kpitch(K)), dtype=torch.float32, device=dev)
+        kb = torch.empty((1, K, K), dtype=torch.float64, device=dev)
+        _lib.check(lib.sted_make_effective(d_cache.data_ptr(), d_fluo.data_ptr(), scal[0].data_ptr(),
+                                           scal[1].data_ptr(), scal[2].data_ptr(), 1, K, tables.data_ptr(),
+                                           kb.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return tables[0].cpu().numpy()[:, :, :K].astype(np.float64), kb[0].cpu().numpy()
+
+    def get_effective(self, datamap_pixelsize, p_ex, p_sted):
+        tables, _ = self._tables(datamap_pixelsize, p_ex, p_sted, 0.0)
+        return tables[_lib.STED_TAB_E]
+
+    def get_k_bleach(self, datamap_pixelsize, p_ex, p_sted, pdt):
+        """Bleaching-rate map (1/s): what ``fluo.get_k_bleach`` returns at ``gym_sted/utils.py:627-630``."""
+        return self._tables(datamap_pixelsize, p_ex, p_sted, pdt)[1]
+
+    # ---- a5 --------------------------------------------------------------------------------
+    def get_signal_and_bleach(self, datamap, pixelsize, pdt, p_ex, p_sted, indices=None, acquired_intensity=None,
+                              pixel_list=None, bleach=True, update=True, seed=None, filter_bypass=False,
+                              bleach_func=None, sample_func=None, steps=None, sample_bleach=True):
+        if datamap.roi is None:
+            raise ValueError("Datamap ROI is not set; call datamap.set_roi(i_ex, 'max') first")
+        if np.ndim(pdt) or np.ndim(p_ex) or np.ndim(p_sted):
+            raise NotImplementedError("array-valued pdt/p_ex/p_sted (timed envs) are outside the rebuilt path")
+        if pixel_list is not None or bleach_func is not None or sample_func is not None:
+            raise NotImplementedError("custom pixel lists / bleach functions are outside the rebuilt path")
+        lib = _lib.load()
+        cache = self._packed_cache(pixelsize)
+        K = cache.shape[-1]
+        rs, cs = datamap.roi
+        H, W = rs.stop - rs.start, cs.stop - cs.start
+        whole = datamap.whole_datamap
+        if whole.shape != (H + K - 1, W + K - 1):
+            raise ValueError(f"datamap shape {whole.shape} does not match ROI {H}x{W} padded for K={K}")
+        roi = np.ascontiguousarray(whole[rs, cs], dtype=np.float32).reshape(1, H, W).copy()
+        flags = 0
+        if bleach:
+            flags |= _lib.STED_BLEACH
+            if sample_bleach:
+                flags |= _lib.STED_SAMPLE_BLEACH
+        if self.detector.noise:
+            flags |= _lib.STED_SAMPLE_PHOTONS
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        self._acq_counter += 1
+        fl = fluo_struct(self.fluo, self.excitation, self.sted)
+        det = self.detector.params()
+        scal = np.array([p_ex, p_sted, pdt], dtype=np.float64)
+        intensity = np.empty((1, H, W), dtype=np.float32)
+        signal = np.empty((1, H, W), dtype=np.float32)
+        vp = ctypes.c_void_p
+        _lib.check(lib.sted_acquire_host(
+            roi.ctypes.data_as(vp), cache.ctypes.data_as(vp), ctypes.cast(ctypes.byref(fl), vp),
+            scal[0:1].ctypes.data_as(vp), scal[1:2].ctypes.data_as(vp), scal[2:3].ctypes.data_as(vp),
+            1, H, W, K, flags, ctypes.byref(det), int(seed), self._acq_counter, 0,
+            intensity.ctypes.data_as(vp), signal.ctypes.data_as(vp)))
+        if bleach:
+            out = np.zeros(whole.shape, dtype=np.int64 if sample_bleach else np.float64)
+            out[rs, cs] = np.rint(roi[0]) if sample_bleach else roi[0]
+        else:
+            out = whole.copy()
+        bleached = {"base": out}
+        if bleach and update:
+            datamap.whole_datamap = out
+            datamap.sub_datamaps_dict = {"base": out}
+        photons = np.rint(signal[0]).astype(np.int64) if self.detector.noise else signal[0].astype(np.float64)
+        return photons, bleached, intensity[0].astype(np.float64)

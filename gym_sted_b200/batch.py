@@ -1,0 +1,108 @@
+"""Batched acquisition: B environments per kernel launch (SURVEY.md §8b "batched entry").
+
+``BatchedMicroscope`` owns the device-resident state of B independent environments — padded
+molecule maps (ping-pong pair), per-env fluorophore structs and PSF tables — and exposes the
+same call as the reference, vectorised:
+
+    signal, intensity = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True)
+
+with ``pdt/p_ex/p_sted`` float64 tensors of shape (B,).  PyTorch is used for device memory and
+streams only; all arithmetic runs in ``libsted_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .base import Microscope, fluo_struct
+
+
+class BatchedMicroscope:
+    def __init__(self, microscope: Microscope, B: int, H: int, W: int, pixelsize: float = 20e-9,
+                 device="cuda", fluos=None, env_base: int = 0, seed: int = 0):
+        self.lib = _lib.load()
+        if _lib.device_count() == 0:
+            raise _lib.StedError(-2, "no CUDA device: gym_sted_b200 has no CPU fallback")
+        self.microscope = microscope
+        self.B, self.H, self.W = int(B), int(H), int(W)
+        self.device = torch.device(device)
+        cache = microscope._packed_cache(pixelsize)
+        self.K = K = cache.shape[-1]
+        self.KP = _lib.kpitch(K)
+        self.p = K // 2
+        self.Hp, self.Wp = H + K - 1, W + K - 1
+        self.Wpitch = (self.Wp + 3) & ~3
+        self.env_base, self.seed, self.offset = int(env_base), int(seed), 0
+        self.d_cache = torch.from_numpy(cache).to(self.device)
+        self.set_fluorophores(fluos)
+        self.tables = torch.empty((B, _lib.STED_TABLES, K, self.KP), dtype=torch.float32, device=self.device)
+        self.dmap = torch.zeros((B, self.Hp, self.Wpitch), dtype=torch.float32, device=self.device)
+        self.dmap_alt = torch.zeros_like(self.dmap)
+        self.det = microscope.detector.params()
+        self.lambda_fluo = float(microscope.fluo.lambda_)
+
+    # per-env fluorophores (config 3: one parameter set per environment)
+    def set_fluorophores(self, fluos=None):
+        m = self.microscope
+        if fluos is None:
+            fluos = [m.fluo] * self.B
+        assert len(fluos) == self.B
+        arr = (_lib.StedFluoParams * self.B)(*[fluo_struct(f, m.excitation, m.sted) for f in fluos])
+        self.d_fluo = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+
+    def set_datamaps(self, roi: torch.Tensor):
+        """roi: (B,H,W) molecule counts (any real dtype); pads with the K//2 zero frame."""
+        assert roi.shape == (self.B, self.H, self.W)
+        p = self.p
+        self.dmap.zero_()
+        self.dmap[:, p:p + self.H, p:p + self.W] = roi.to(self.device, torch.float32)
+
+    def datamaps_roi(self) -> torch.Tensor:
+        p = self.p
+        return self.dmap[:, p:p + self.H, p:p + self.W]
+
+    def make_effective(self, p_ex, p_sted, pdt, want_kbleach=False):
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        kb = torch.empty((self.B, self.K, self.K), dtype=torch.float64, device=self.device) if want_kbleach else None
+        _lib.check(self.lib.sted_make_effective(
+            self.d_cache.data_ptr(), self.d_fluo.data_ptr(), p_ex.data_ptr(), p_sted.data_ptr(), pdt.data_ptr(),
+            self.B, self.K, self.tables.data_ptr(), kb.data_ptr() if want_kbleach else None, st))
+        return kb
+
+    def _vec(self, x):
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.broadcast_to(np.asarray(x, dtype=np.float64), (self.B,)).copy())
+        return x.to(self.device, torch.float64).contiguous()
+
+    def get_signal_and_bleach(self, pdt, p_ex, p_sted, bleach=True, update=True, sample_bleach=True,
+                              noise=None, want_intensity=False, seed=None, out_signal=None):
+        """Vectorised ``Microscope.get_signal_and_bleach``; returns ``(signal, intensity|None)`` as
+        (B,H,W) float32 device tensors.  With ``bleach`` and ``update`` the resident maps advance."""
+        pdt, p_ex, p_sted = self._vec(pdt), self._vec(p_ex), self._vec(p_sted)
+        self.make_effective(p_ex, p_sted, pdt)
+        flags = 0
+        if bleach:
+            flags |= _lib.STED_BLEACH | (_lib.STED_SAMPLE_BLEACH if sample_bleach else 0)
+        if self.microscope.detector.noise if noise is None else noise:
+            flags |= _lib.STED_SAMPLE_PHOTONS
+        self.offset += 1
+        signal = out_signal if out_signal is not None else torch.empty((self.B, self.H, self.W), dtype=torch.float32,
+                                                                         device=self.device)
+        intensity = torch.empty_like(signal) if want_intensity else None
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.sted_acquire(
+            self.dmap.data_ptr(), self.dmap_alt.data_ptr() if bleach else None, self.tables.data_ptr(),
+            pdt.data_ptr(), self.B, self.H, self.W, self.K, flags, ctypes.byref(self.det), self.lambda_fluo,
+            self.seed if seed is None else int(seed), self.offset, self.env_base,
+            intensity.data_ptr() if want_intensity else None, signal.data_ptr(), st))
+        if bleach and update:
+            self.dmap, self.dmap_alt = self.dmap_alt, self.dmap
+        return signal, intensity
+
+    def bleached_roi(self) -> torch.Tensor:
+        """ROI of the last bleach output when ``update=False`` was used."""
+        p = self.p
+        return self.dmap_alt[:, p:p + self.H, p:p + self.W]

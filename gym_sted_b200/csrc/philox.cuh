@@ -1,0 +1,172 @@
+// Counter-based Philox4x32-10 (Salmon et al., SC'11) and the exact discrete samplers built on it.
+//
+// pySTED draws bleaching with libc rand() and photons with numpy's global RandomState
+// (SURVEY.md §8b), so draw-for-draw equality with the reference is not defined; what is
+// required is equality in distribution (moments + KS, north_star).  Every draw here is a pure
+// function of (seed, offset, env, pixel, purpose, sub-counter), which makes results independent
+// of the launch geometry and of how environments are sharded over GPUs.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define STED_HD __host__ __device__ __forceinline__
+#else
+#define STED_HD inline
+#endif
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+STED_HD void philox_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+STED_HD Philox4 philox4x32_10(Philox4 c, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        philox_mulhilo(M0, c.x, hi0, lo0);
+        philox_mulhilo(M1, c.z, hi1, lo1);
+        Philox4 n;
+        n.x = hi1 ^ c.y ^ k0;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k1;
+        n.w = lo0;
+        c = n;
+        k0 += W0;
+        k1 += W1;
+    }
+    return c;
+}
+
+// purposes (top 4 bits of counter word 2)
+#define STED_RNG_PHOTON 1u
+#define STED_RNG_BLEACH 2u
+#define STED_RNG_TEST   3u
+
+// Stream of 32-bit words for one (pixel, env, purpose, row) site; refills by bumping a sub-counter.
+struct PhiloxStream {
+    Philox4 ctr, buf;
+    uint32_t k0, k1;
+    int have;
+    STED_HD void init(uint64_t seed, uint32_t offset, uint32_t env, uint32_t site,
+                      uint32_t purpose, uint32_t row) {
+        k0 = (uint32_t)seed;
+        k1 = (uint32_t)(seed >> 32);
+        ctr.x = site;
+        ctr.y = env;
+        ctr.z = (purpose << 28) | ((row & 0xFFFFu) << 12);   // low 12 bits: sub-counter
+        ctr.w = offset;
+        have = 0;
+    }
+    STED_HD uint32_t next() {
+        if (have == 0) {
+            buf = philox4x32_10(ctr, k0, k1);
+            ctr.z += 1u;
+            have = 4;
+        }
+        uint32_t v = (have == 4) ? buf.x : (have == 3) ? buf.y : (have == 2) ? buf.z : buf.w;
+        --have;
+        return v;
+    }
+    // uniform on (0,1): (x + 0.5) * 2^-32 — full relative precision near 0
+    STED_HD float uniform() { return ((float)next() + 0.5f) * 2.3283064365386963e-10f; }
+};
+
+#if defined(__CUDACC__)
+
+// ---------------------------------------------------------------------------------------------
+// Binomial(n, q): number of molecules that bleach out of n, each with probability q.
+// Upper-tail inversion: all compared quantities are small numbers held at full float relative
+// precision, so rare events (n*q ~ 1e-8) keep their probability.  n is split in chunks of 64 so
+// (1-q)^chunk never underflows; q > 1/2 is sampled through the complement.
+// Restates the per-molecule rand() <= prob loop of pySTED's sample_molecules
+// in distribution.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int binomial_chunk(int n, float q, float log1mq, float u) {
+    // q <= 0.5, n <= 64.  p0 = (1-q)^n ; tail_1 = 1 - p0
+    const float p0 = __expf((float)n * log1mq);
+    float tail = -expm1f((float)n * log1mq);          // P(k >= 1)
+    if (u >= tail) return 0;
+    const float odds = q / (1.0f - q);
+    float pmf = p0;
+    int k = 0;
+    while (k < n) {
+        pmf *= odds * (float)(n - k) / (float)(k + 1);   // pmf(k+1)
+        ++k;
+        tail -= pmf;                                     // P(K >= k+1)
+        if (u >= tail) break;
+    }
+    return k;
+}
+
+// hz = per-molecule hazard over the pass (q = 1 - exp(-hz)); returns number of deaths.
+__device__ __forceinline__ int binomial_deaths(int n, float hz, PhiloxStream& rng) {
+    if (n <= 0 || hz <= 0.0f) return 0;
+    // cheap reject: P(any death) = 1 - exp(-n*hz) <= n*hz ; below 2^-33 no uniform can hit it
+    if ((float)n * hz < 1.1e-10f) return 0;
+    float q = -expm1f(-hz);
+    bool flip = q > 0.5f;
+    float log1mq;
+    if (flip) { log1mq = log1pf(-__expf(-hz)); q = __expf(-hz); }   // sample survivors instead
+    else      { log1mq = -hz; }
+    int total = 0, left = n;
+    while (left > 0) {
+        int m = left < 64 ? left : 64;
+        total += binomial_chunk(m, q, log1mq, rng.uniform());
+        left -= m;
+    }
+    return flip ? n - total : total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Poisson(lam): inversion below 12, PTRS (Hörmann 1993, the algorithm numpy's legacy
+// RandomState.poisson uses) above.  Restates Detector.get_signal's numpy.random.poisson draws.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float poisson_sample(float lam, PhiloxStream& rng) {
+    if (!(lam > 0.0f)) return 0.0f;
+    if (lam < 12.0f) {
+        // upper-tail inversion (same scheme as binomial_chunk): K = k iff P(K>=k+1) <= w < P(K>=k)
+        const float w = rng.uniform();
+        float tail = -expm1f(-lam);
+        if (w >= tail) return 0.0f;
+        float pmf = __expf(-lam);
+        int k = 0;
+        while (k < 200) {
+            pmf *= lam / (float)(k + 1);
+            ++k;
+            tail -= pmf;
+            if (w >= tail) break;
+        }
+        return (float)k;
+    }
+    const float slam = sqrtf(lam);
+    const float b = 0.931f + 2.53f * slam;
+    const float a = -0.059f + 0.02483f * b;
+    const float invalpha = 1.1239f + 1.1328f / (b - 3.4f);
+    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+    for (int it = 0; it < 64; ++it) {
+        float U = rng.uniform() - 0.5f;
+        float V = rng.uniform();
+        float us = 0.5f - fabsf(U);
+        float kf = floorf((2.0f * a / us + b) * U + lam + 0.43f);
+        if (us >= 0.07f && V <= vr) return kf;
+        if (kf < 0.0f || (us < 0.013f && V > us)) continue;
+        // rare path: evaluate the acceptance bound in double (k*log(lam) ~ 1e5 for bright pixels)
+        double lhs = log((double)V) + log((double)invalpha) - log((double)a / ((double)us * us) + (double)b);
+        double rhs = -(double)lam + (double)kf * log((double)lam) - lgamma((double)kf + 1.0);
+        if (lhs <= rhs) return kf;
+    }
+    return floorf(lam + 0.5f);
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,777 @@
+// sted_kernels.cu — B200 (sm_100a) kernels + C ABI for the STED acquisition hot path.
+//
+// Path rebuilt here: pysted.base.Microscope.get_effective / fluo.get_k_bleach
+// (a2, a3) -> make_effective_kernel; Microscope.get_signal_and_bleach (a5) ->
+// gather_kernel (bleach=False) and sweep_kernel (bleach=True); Detector.get_signal is fused into
+// both epilogues.  Reference call sites: gym_sted/envs/mosted_env.py:184,222,227,232 and
+// gym_sted/utils.py:616-631,646-657.  See DESIGN.md for the derivations.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build).
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+
+#include "../../include/sted_b200.h"
+#include "philox.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver        \
+                            ? STED_ENODEVICE : STED_ECUDA,                                  \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                        __LINE__);                                                          \
+    } while (0)
+
+constexpr double kPlanck = 6.62607015e-34;
+constexpr double kLight = 299792458.0;
+
+// ------------------------------------------------------------------------------------------
+// K1: effective PSF + bleaching tables, one CTA per environment, one thread per tap row.
+// All physics in float64; tables are rounded to float32 once.
+//   E[u][v]  = sigma_abs*I_ex*qy * eta(I_sted) * psf_det            (Microscope.get_effective)
+//   k_b[u][v]= sigma_abs*phi_ex * tau_sted * (k0*I + k1*I^b),  I = instantaneous STED W/m^2
+//                                                                     (fluo.get_k_bleach)
+//   A = k_b*pdt;  CH[u][v] = sum_{v'>=v} A[u][v'];  ET = E*exp(-CH[u][v+1]);  RS = exp(-CH)
+// ------------------------------------------------------------------------------------------
+__global__ void make_effective_kernel(const double* __restrict__ cache, const StedFluoParams* __restrict__ fluo,
+                                      const double* __restrict__ p_ex, const double* __restrict__ p_sted,
+                                      const double* __restrict__ pdt, int K, int KP,
+                                      float* __restrict__ tables, double* __restrict__ kbleach) {
+    const int b = blockIdx.x;
+    const int u = threadIdx.x;
+    if (u >= K) return;
+    const StedFluoParams f = fluo[b];
+    const double pex = p_ex[b], psted = p_sted[b], dwell = pdt[b];
+    const double* i_ex = cache;
+    const double* i_sted = cache + (size_t)K * K;
+    const double* psf_det = cache + 2 * (size_t)K * K;
+    float* tE = tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP + (size_t)u * KP;
+    float* tET = tables + ((size_t)b * STED_TABLES + STED_TAB_ET) * K * KP + (size_t)u * KP;
+    float* tCH = tables + ((size_t)b * STED_TABLES + STED_TAB_CH) * K * KP + (size_t)u * KP;
+    float* tRS = tables + ((size_t)b * STED_TABLES + STED_TAB_RS) * K * KP + (size_t)u * KP;
+
+    const double e_ex = kPlanck * kLight / f.lambda_ex;
+    const double e_st = kPlanck * kLight / f.lambda_sted;
+    const double k_vib = 1.0 / f.tau_vib, k_s1 = 1.0 / f.tau;
+    const double T = 1.0 / f.sted_rate;
+    const double i_sat = e_st / (f.sigma_ste * f.tau);
+    const double duty = f.sted_tau * f.sted_rate;
+    const double denom = 1.0 - exp(-k_s1 * T);
+
+    for (int v = K; v < KP; ++v) { tE[v] = 0.f; tET[v] = 0.f; tCH[v] = 0.f; tRS[v] = 1.f; }
+    double ch = 0.0;   // suffix hazard, exclusive of the tap being visited on entry
+    for (int v = K - 1; v >= 0; --v) {
+        const int t = u * K + v;
+        const double I_ex = i_ex[t] * pex;
+        const double I_st = i_sted[t] * psted;                 // instantaneous, in-pulse
+        double exc = f.sigma_abs_ex * I_ex * f.qy;
+        if (f.anti_stoke) exc += f.sigma_abs_sted * I_st * f.qy;
+        const double zeta = I_st / i_sat;
+        const double gamma = zeta * k_vib / (zeta * k_s1 + k_vib);
+        const double eta = ((1.0 + gamma * exp(-k_s1 * f.sted_tau * (1.0 + gamma))) / (1.0 + gamma)
+                            - exp(-k_s1 * (gamma * f.sted_tau + T))) / denom;
+        const double E = exc * eta * psf_det[t];
+        // photon fluxes with get_photons' floor division
+        const double phi_ex = floor(I_ex / e_ex);
+        const double phi_st = floor(I_st * duty / e_st);        // time averaged
+        const double I_inst = phi_st * e_st / duty;
+        const double kb = f.sigma_abs_ex * phi_ex * f.sted_tau * (f.k0 * I_inst + f.k1 * pow(I_inst, f.b));
+        if (kbleach) kbleach[(size_t)b * K * K + t] = kb;
+        tE[v] = (float)E;
+        tET[v] = (float)(E * exp(-ch));
+        ch += kb * dwell;
+        tCH[v] = (float)ch;
+        tRS[v] = (float)exp(-ch);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared launch parameters
+// ------------------------------------------------------------------------------------------
+struct AcqParams {
+    const float* din;
+    float* dout;
+    const float* tables;
+    const double* pdt;
+    float* intensity;
+    float* signal;
+    int B, H, W, K, KP, Hp, Wp, Wpitch;
+    uint32_t flags;
+    uint32_t offset;
+    uint64_t seed;
+    uint32_t env_base;
+    float inv_e_photon;   // lambda_fluo/(h c)
+    float det_eff;        // pcef*pdef
+    float background;     // counts per second
+};
+
+// Detector.get_signal fused: photons = floor(I/e_photon); mean = photons*pcef*pdef*pdt + bg*pdt
+__device__ __forceinline__ float detect(const AcqParams& P, float I, float gain, float bg_mean,
+                                        uint32_t env, uint32_t site) {
+    const float mean = floorf(I * P.inv_e_photon) * gain + bg_mean;
+    if (P.flags & STED_SAMPLE_PHOTONS) {
+        PhiloxStream rng;
+        rng.init(P.seed, P.offset, env, site, STED_RNG_PHOTON, 0);
+        return poisson_sample(mean, rng);
+    }
+    return mean;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: dense PSF-window gather, no bleaching.
+//   I[r][c] = sum_{u,v} E[u][v] * D[r+u][c+v]
+// CTA = 64x64 output tile of one environment, 128 threads, thread = 8 rows x 4 columns.
+// smem: datamap tile (64+K-1) x (64+KP) floats + E table.  Per 4 taps and 8 output rows a
+// thread issues 1 LDS.128 of datamap (sliding window) + 8 broadcast LDS.128 of E for 128 FFMA.
+// ------------------------------------------------------------------------------------------
+constexpr int G_TH = 64, G_TW = 64, G_RT = 8, G_THREADS = 128;
+
+template <int KT>
+__global__ void __launch_bounds__(G_THREADS, 3) gather_kernel(const AcqParams P) {
+    const int K = KT ? KT : P.K;
+    const int KP = KT ? STED_KPITCH(KT) : P.KP;
+    const int PITCH = G_TW + KP;
+    const int rows = G_TH + K - 1;
+    extern __shared__ __align__(16) float smem[];
+    float* sD = smem;
+    float* sE = smem + rows * PITCH;
+
+    const int b = blockIdx.z;
+    const int tr0 = blockIdx.y * G_TH, tc0 = blockIdx.x * G_TW;
+    const int tid = threadIdx.x;
+
+    // ---- stage tile + PSF (float4, zero fill outside the padded map)
+    {
+        const float* src = P.din + (size_t)b * P.Hp * P.Wpitch;
+        const int q = PITCH / 4;
+        for (int i = tid; i < rows * q; i += G_THREADS) {
+            const int ry = i / q, cx = (i - ry * q) * 4;
+            const int y = tr0 + ry, x = tc0 + cx;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y < P.Hp && x < P.Wpitch) val = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * P.Wpitch + x));
+            *reinterpret_cast<float4*>(sD + ry * PITCH + cx) = val;
+        }
+        const float4* e4 = reinterpret_cast<const float4*>(P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP);
+        for (int i = tid; i < K * KP / 4; i += G_THREADS) reinterpret_cast<float4*>(sE)[i] = __ldg(e4 + i);
+    }
+    __syncthreads();
+
+    const int lane16 = tid & 15, rg = tid >> 4;
+    const int r0 = rg * G_RT, c0 = lane16 * 4;
+    float acc[G_RT][4];
+#pragma unroll
+    for (int i = 0; i < G_RT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+    const int nchunk = KP / 4;
+    auto band_row = [&](const int yy, const bool check) {
+        const float* drow = sD + (r0 + yy) * PITCH + c0;
+        float4 wa = *reinterpret_cast<const float4*>(drow);
+#pragma unroll 5
+        for (int vc = 0; vc < nchunk; ++vc) {
+            const float4 wb = *reinterpret_cast<const float4*>(drow + 4 * (vc + 1));
+#pragma unroll
+            for (int i = 0; i < G_RT; ++i) {
+                const int u = yy - i;
+                if (!check || (u >= 0 && u < K)) {
+                    const float4 e = *reinterpret_cast<const float4*>(sE + u * KP + 4 * vc);
+                    acc[i][0] = fmaf(e.x, wa.x, acc[i][0]); acc[i][0] = fmaf(e.y, wa.y, acc[i][0]);
+                    acc[i][0] = fmaf(e.z, wa.z, acc[i][0]); acc[i][0] = fmaf(e.w, wa.w, acc[i][0]);
+                    acc[i][1] = fmaf(e.x, wa.y, acc[i][1]); acc[i][1] = fmaf(e.y, wa.z, acc[i][1]);
+                    acc[i][1] = fmaf(e.z, wa.w, acc[i][1]); acc[i][1] = fmaf(e.w, wb.x, acc[i][1]);
+                    acc[i][2] = fmaf(e.x, wa.z, acc[i][2]); acc[i][2] = fmaf(e.y, wa.w, acc[i][2]);
+                    acc[i][2] = fmaf(e.z, wb.x, acc[i][2]); acc[i][2] = fmaf(e.w, wb.y, acc[i][2]);
+                    acc[i][3] = fmaf(e.x, wa.w, acc[i][3]); acc[i][3] = fmaf(e.y, wb.x, acc[i][3]);
+                    acc[i][3] = fmaf(e.z, wb.y, acc[i][3]); acc[i][3] = fmaf(e.w, wb.z, acc[i][3]);
+                }
+            }
+            wa = wb;
+        }
+    };
+    int yy = 0;
+    for (; yy < G_RT - 1 && yy < K; ++yy) band_row(yy, true);       // ramp-up
+    for (; yy < K; ++yy) band_row(yy, false);                       // steady: all 8 rows active
+    for (; yy < G_RT + K - 1; ++yy) band_row(yy, true);             // ramp-down
+
+    // ---- epilogue: detector
+    const float dwell = (float)P.pdt[b];
+    const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
+    const uint32_t env = P.env_base + (uint32_t)b;
+#pragma unroll
+    for (int i = 0; i < G_RT; ++i) {
+        const int r = tr0 + r0 + i;
+        if (r >= P.H) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = tc0 + c0 + j;
+            if (c >= P.W) continue;
+            const size_t o = ((size_t)b * P.H + r) * P.W + c;
+            if (P.intensity) P.intensity[o] = acc[i][j];
+            P.signal[o] = detect(P, acc[i][j], gain, bg_mean, env, (uint32_t)(r * P.W + c));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: raster scan with in-scan bleaching ("row sweep").
+//
+// pySTED visits dwells in row-major order; at each dwell it gathers the window, then thins every
+// molecule of the window with survival exp(-k_b[u][v]*pdt).  Survival factors
+// commute, so within one scan row r the count a dwell sees at tap (u,v) is the count at the start
+// of the row thinned by the taps v' > v of the same tap row, and after the row every pixel of band
+// row u has been thinned by the taps v' in [lo,hi] that exist for its column.
+//   expectation mode : state s = D*exp(CH[u][hi+1]); gather with ET; s *= exp(CHm1 - CH[u][lo])
+//   stochastic mode  : state n integer; deaths ~ Binomial(n, 1-exp(-hz)); each death gets its tap
+//                      by inverting the in-row hazard; taps after the death are subtracted from
+//                      the dense gather of the row.  Identical in distribution to the per-dwell
+//                      chain of binomials.
+// CTA = (environment, tile of TC = 8*CT output columns), 256 threads; scan rows are sequential,
+// the K-row band lives in a shared-memory ring; warp w owns CT columns, lane l the tap rows
+// l and l+32; partial sums meet through a shuffle reduce-scatter.
+// ------------------------------------------------------------------------------------------
+constexpr int S_THREADS = 256;
+
+__host__ __device__ inline int sweep_pitch(int TC, int KP) {
+    int p = TC + KP;
+    while ((p & 31) != 28 && (p & 31) != 4 && (p & 31) != 12 && (p & 31) != 20) p += 4;
+    return p;
+}
+
+template <int CT>
+__device__ __forceinline__ float reduce_scatter(float (&a)[CT], int lane) {
+    // after the loop lane holds the full sum of column (lane >> (5 - log2 CT))
+    int n = CT;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            n >>= 1;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < CT / 2; ++j) {
+                if (j < n) {
+                    const float send = upper ? a[j] : a[j + n];
+                    const float keep = upper ? a[j + n] : a[j];
+                    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+        } else {
+            a[0] += __shfl_xor_sync(0xffffffffu, a[0], off);
+        }
+    }
+    return a[0];
+}
+
+template <int KT, int CT>
+__global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) {
+    constexpr int TC = 8 * CT;
+    const int K = KT ? KT : P.K;
+    const int KP = KT ? STED_KPITCH(KT) : P.KP;
+    const int PR = sweep_pitch(TC, KP);
+    const int span = TC + K - 1;
+    const bool stochastic = (P.flags & STED_SAMPLE_BLEACH) != 0;
+
+    extern __shared__ __align__(16) float smem[];
+    float* ring = smem;                       // [K][PR]
+    float* sWt = ring + K * PR;               // [K][KP] gather weights: E (stochastic) or ET
+    float* sCH = sWt + K * KP;                // [K][KP] suffix hazards
+    float* sRS = sCH + K * KP;                // [K][KP] exp(-CH) (expectation mode)
+    float* sI = sRS + K * KP;                 // [TC] row of intensities
+
+    const int b = blockIdx.y;
+    const int c0 = blockIdx.x * TC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = P.W, H = P.H, Wp = P.Wp;
+    const float* din = P.din + (size_t)b * P.Hp * P.Wpitch;
+    float* dout = P.dout + (size_t)b * P.Hp * P.Wpitch;
+    const uint32_t env = P.env_base + (uint32_t)b;
+
+    {   // tables
+        const size_t tsz = (size_t)K * KP;
+        const float* tb = P.tables + (size_t)b * STED_TABLES * tsz;
+        const float4* w4 = reinterpret_cast<const float4*>(tb + (stochastic ? STED_TAB_E : STED_TAB_ET) * tsz);
+        const float4* c4 = reinterpret_cast<const float4*>(tb + STED_TAB_CH * tsz);
+        const float4* r4 = reinterpret_cast<const float4*>(tb + STED_TAB_RS * tsz);
+        for (int i = tid; i < (int)(tsz / 4); i += S_THREADS) {
+            reinterpret_cast<float4*>(sWt)[i] = __ldg(w4 + i);
+            reinterpret_cast<float4*>(sCH)[i] = __ldg(c4 + i);
+            reinterpret_cast<float4*>(sRS)[i] = __ldg(r4 + i);
+        }
+    }
+    __syncthreads();
+
+    // columns of the molecule map this tile writes back (each column has exactly one owner)
+    const int p = K / 2;
+    const int xs = (c0 == 0) ? 0 : c0 + p;
+    const int xe = (c0 + TC >= W) ? P.Wpitch : c0 + TC + p;
+
+    // load band row y into its ring slot; in expectation mode scale by exp(CH[u_entry][hi+1])
+    auto load_row = [&](const int y, const int u_entry) {
+        float* dst = ring + (y % K) * PR;
+        for (int i = tid; i < PR / 4; i += S_THREADS) {
+            const int xl = 4 * i, x = c0 + xl;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y < P.Hp && x < P.Wpitch) val = __ldg(reinterpret_cast<const float4*>(din + (size_t)y * P.Wpitch + x));
+            if (!stochastic && x < K - 1) {
+                float* pv = reinterpret_cast<float*>(&val);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = x + j;
+                    if (xx < K - 1 && pv[j] != 0.f) pv[j] *= expf(sCH[u_entry * KP + xx + 1]);
+                }
+            }
+            *reinterpret_cast<float4*>(dst + xl) = val;
+        }
+    };
+    // write band row y back (u_scale >= 0: undo the expectation-mode scaling with that tap row)
+    auto store_row = [&](const int y, const int u_scale) {
+        const float* src = ring + (y % K) * PR;
+        for (int x = xs + tid; x < xe; x += S_THREADS) {
+            float val = src[x - c0];
+            if (!stochastic && u_scale >= 0 && x < K - 1 && val != 0.f) val *= expf(-sCH[u_scale * KP + x + 1]);
+            dout[(size_t)y * P.Wpitch + x] = val;
+        }
+    };
+
+    for (int y = 0; y < K; ++y) load_row(y, y);
+    __syncthreads();
+
+    const float dwell = (float)P.pdt[b];
+    const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
+
+    for (int r = 0; r < H; ++r) {
+        // ---------------- phase G: dense gather of scan row r against the row-start state
+        {
+            float acc[CT];
+#pragma unroll
+            for (int j = 0; j < CT; ++j) acc[j] = 0.f;
+            for (int uu = lane; uu < K; uu += 32) {
+                const float* drow = ring + ((r + uu) % K) * PR + CT * warp;
+                const float* erow = sWt + uu * KP;
+                float win[CT + 4];
+#pragma unroll
+                for (int j = 0; j < CT; j += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(drow + j);
+                    win[j] = t.x; win[j + 1] = t.y; win[j + 2] = t.z; win[j + 3] = t.w;
+                }
+                const int nchunk = KP / 4;
+#pragma unroll 5
+                for (int vc = 0; vc < nchunk; ++vc) {
+                    const float4 nw = *reinterpret_cast<const float4*>(drow + CT + 4 * vc);
+                    const float4 e = *reinterpret_cast<const float4*>(erow + 4 * vc);
+                    win[CT] = nw.x; win[CT + 1] = nw.y; win[CT + 2] = nw.z; win[CT + 3] = nw.w;
+#pragma unroll
+                    for (int j = 0; j < CT; ++j) {
+                        acc[j] = fmaf(e.x, win[j], acc[j]);
+                        acc[j] = fmaf(e.y, win[j + 1], acc[j]);
+                        acc[j] = fmaf(e.z, win[j + 2], acc[j]);
+                        acc[j] = fmaf(e.w, win[j + 3], acc[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < CT; ++j) win[j] = win[j + 4];
+                }
+            }
+            const float tot = reduce_scatter<CT>(acc, lane);
+            constexpr int SH = (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
+            if ((lane & ((1 << SH) - 1)) == 0) sI[CT * warp + (lane >> SH)] = tot;
+        }
+        __syncthreads();
+
+        // ---------------- phase S: thin the band with the taps of this scan row
+        for (int u = warp; u < K; u += S_THREADS / 32) {
+            float* row = ring + ((r + u) % K) * PR;
+            const float* ch = sCH + u * KP;
+            const int y = r + u;
+            for (int xl = lane; xl < span; xl += 32) {
+                const float n = row[xl];
+                if (n == 0.f) continue;
+                const int x = c0 + xl;
+                if (x >= Wp) continue;
+                const int lo = max(0, x - W + 1), hi = min(K - 1, x);
+                if (!stochastic) {
+                    float m;
+                    if (hi == K - 1) m = sRS[u * KP + lo];
+                    else m = expf((u > 0 ? sCH[(u - 1) * KP + hi + 1] : 0.f) - ch[lo]);
+                    row[xl] = n * m;
+                    continue;
+                }
+                const float chhi = ch[hi + 1];
+                const float hz = ch[lo] - chhi;
+                PhiloxStream rng;
+                rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, (uint32_t)r);
+                const int dead = binomial_deaths((int)n, hz, rng);
+                if (dead == 0) continue;
+                row[xl] = n - (float)dead;
+                // place each death on the tap where its cumulative in-row hazard is reached
+                const float pd = -expm1f(-hz);
+                for (int d = 0; d < dead; ++d) {
+                    const float t = -log1pf(-rng.uniform() * pd);       // in (0, hz)
+                    const float thr = t + chhi;
+                    int a = lo, z = hi;                                  // largest v in [lo,hi] with ch[v] >= thr
+                    while (a < z) {
+                        const int mid = (a + z + 1) >> 1;
+                        if (ch[mid] >= thr) a = mid; else z = mid - 1;
+                    }
+                    // dwells after the death (taps lo .. a-1) no longer see this molecule
+                    const float* e = sWt + u * KP;
+                    for (int v = lo; v < a; ++v) {
+                        const int cl = x - v - c0;
+                        if (cl >= 0 && cl < TC) atomicAdd(&sI[cl], -e[v]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------- phase O: detector, retire band row y = r, bring in row r + K
+        if (tid < TC && c0 + tid < W) {
+            const float I = fmaxf(sI[tid], 0.f);
+            const size_t o = ((size_t)b * H + r) * W + c0 + tid;
+            if (P.intensity) P.intensity[o] = I;
+            P.signal[o] = detect(P, I, gain, bg_mean, env, (uint32_t)(r * W + c0 + tid));
+        }
+        store_row(r, -1);
+        __syncthreads();
+        if (r + K < P.Hp) load_row(r + K, K - 1);
+        __syncthreads();
+    }
+    // flush the K-1 band rows below the last scan row (tap row they would have had next: y - H)
+    for (int y = H; y < P.Hp; ++y) store_row(y, y - H);
+}
+
+// ------------------------------------------------------------------------------------------
+// sampler test kernels, FMA peak
+// ------------------------------------------------------------------------------------------
+__global__ void poisson_test_kernel(const float* lam, int64_t n, uint64_t seed, uint32_t offset, float* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PhiloxStream rng;
+    rng.init(seed, offset, (uint32_t)(i >> 32), (uint32_t)i, STED_RNG_TEST, 0);
+    out[i] = poisson_sample(lam[i], rng);
+}
+
+__global__ void binomial_test_kernel(const float* nn, const float* q, int64_t n, uint64_t seed, uint32_t offset, float* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PhiloxStream rng;
+    rng.init(seed, offset, (uint32_t)(i >> 32), (uint32_t)i, STED_RNG_TEST, 1);
+    const float hz = -log1pf(-q[i]);
+    out[i] = (float)binomial_deaths((int)nn[i], hz, rng);
+}
+
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters) {
+    float a[16];
+    const float x = 1.0f + 1e-7f * threadIdx.x, y = 1e-9f * blockIdx.x;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (float)j;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += a[j];
+    if (s == 12345.678f) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(STED_ENODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return STED_OK;
+}
+
+int make_params(AcqParams& P, const float* din, float* dout, const float* tables, const double* pdt, int B, int H,
+                int W, int K, uint32_t flags, const StedDetectorParams* det, double lambda_fluo, uint64_t seed,
+                uint64_t offset, int64_t env_base, float* intensity, float* signal) {
+    if (!din || !tables || !pdt || !signal || !det) return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B, H, W must be positive (got %d, %d, %d)", B, H, W);
+    if (K < 1 || (K & 1) == 0) return fail(STED_EINVAL, "K must be odd (got %d)", K);
+    if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
+    if (H > 65535) return fail(STED_EUNSUPPORTED, "H=%d exceeds 65535 scan rows", H);
+    if ((flags & STED_BLEACH) && (!dout || dout == din))
+        return fail(STED_EINVAL, "bleaching needs dmap_out_dev distinct from dmap_in_dev");
+    if (!(lambda_fluo > 0)) return fail(STED_EINVAL, "lambda_fluo must be positive");
+    P.din = din; P.dout = dout; P.tables = tables; P.pdt = pdt; P.intensity = intensity; P.signal = signal;
+    P.B = B; P.H = H; P.W = W; P.K = K; P.KP = STED_KPITCH(K);
+    P.Hp = H + K - 1; P.Wp = W + K - 1; P.Wpitch = (P.Wp + 3) & ~3;
+    P.flags = flags; P.offset = (uint32_t)offset; P.seed = seed ^ (offset >> 32 << 17); P.env_base = (uint32_t)env_base;
+    P.inv_e_photon = (float)(lambda_fluo / (kPlanck * kLight));
+    P.det_eff = (float)(det->pcef * det->pdef);
+    P.background = (float)det->background;
+    return STED_OK;
+}
+
+template <typename Kern>
+int set_smem(Kern kern, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return STED_OK;
+}
+
+int launch_gather(const AcqParams& P, cudaStream_t st) {
+    const size_t smem = ((size_t)(G_TH + P.K - 1) * (G_TW + P.KP) + (size_t)P.K * P.KP) * sizeof(float);
+    dim3 grid((P.W + G_TW - 1) / G_TW, (P.H + G_TH - 1) / G_TH, P.B);
+    int rc;
+    if (P.K == 59) {
+        if ((rc = set_smem(gather_kernel<59>, smem))) return rc;
+        gather_kernel<59><<<grid, G_THREADS, smem, st>>>(P);
+    } else {
+        if ((rc = set_smem(gather_kernel<0>, smem))) return rc;
+        gather_kernel<0><<<grid, G_THREADS, smem, st>>>(P);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+template <int KT, int CT>
+int launch_sweep_t(const AcqParams& P, cudaStream_t st) {
+    constexpr int TC = 8 * CT;
+    const size_t smem = ((size_t)P.K * sweep_pitch(TC, P.KP) + 3 * (size_t)P.K * P.KP + TC) * sizeof(float);
+    dim3 grid((P.W + TC - 1) / TC, P.B);
+    int rc;
+    if ((rc = set_smem(sweep_kernel<KT, CT>, smem))) return rc;
+    sweep_kernel<KT, CT><<<grid, S_THREADS, smem, st>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+int launch_sweep(const AcqParams& P, cudaStream_t st) {
+    const bool wide = P.W > 64;
+    if (P.K == 59) return wide ? launch_sweep_t<59, 16>(P, st) : launch_sweep_t<59, 8>(P, st);
+    return wide ? launch_sweep_t<0, 16>(P, st) : launch_sweep_t<0, 8>(P, st);
+}
+
+// growable device workspace for the *_host entry points
+struct Workspace {
+    std::mutex mu;
+    void* dev[8] = {nullptr};
+    size_t cap[8] = {0};
+    int ensure(int slot, size_t bytes) {
+        if (cap[slot] >= bytes) return STED_OK;
+        if (dev[slot]) cudaFree(dev[slot]);
+        dev[slot] = nullptr; cap[slot] = 0;
+        CUDA_TRY(cudaMalloc(&dev[slot], bytes));
+        cap[slot] = bytes;
+        return STED_OK;
+    }
+};
+Workspace g_ws;
+
+__global__ void pad_kernel(const float* __restrict__ roi, float* __restrict__ padded, int B, int H, int W, int p,
+                           int Hp, int Wpitch) {
+    const size_t n = (size_t)B * Hp * Wpitch;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % Wpitch);
+        const int y = (int)((i / Wpitch) % Hp);
+        const int b = (int)(i / ((size_t)Wpitch * Hp));
+        const int r = y - p, c = x - p;
+        padded[i] = (r >= 0 && r < H && c >= 0 && c < W) ? roi[((size_t)b * H + r) * W + c] : 0.f;
+    }
+}
+
+__global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict__ roi, int B, int H, int W, int p,
+                             int Hp, int Wpitch) {
+    const size_t n = (size_t)B * H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % W);
+        const int r = (int)((i / W) % H);
+        const int b = (int)(i / ((size_t)W * H));
+        roi[i] = padded[((size_t)b * Hp + r + p) * Wpitch + c + p];
+    }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* sted_version(void) { return "sted_b200 0.1 (sm_100a)"; }
+const char* sted_last_error(void) { return g_err; }
+
+int sted_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sted_make_effective(const double* psf_cache_dev, const StedFluoParams* fluo_dev, const double* p_ex_dev,
+                        const double* p_sted_dev, const double* pdt_dev, int B, int K, float* tables_dev,
+                        double* kbleach_dev, void* stream) {
+    if (!psf_cache_dev || !fluo_dev || !p_ex_dev || !p_sted_dev || !pdt_dev || !tables_dev)
+        return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0) return fail(STED_EINVAL, "B must be positive");
+    if (K < 1 || (K & 1) == 0) return fail(STED_EINVAL, "K must be odd (got %d)", K);
+    if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
+    int rc = check_device();
+    if (rc) return rc;
+    make_effective_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(psf_cache_dev, fluo_dev, p_ex_dev, p_sted_dev, pdt_dev,
+                                                               K, STED_KPITCH(K), tables_dev, kbleach_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tables_dev, const double* pdt_dev,
+                 int B, int H, int W, int K, uint32_t flags, const StedDetectorParams* det, double lambda_fluo,
+                 uint64_t seed, uint64_t offset, int64_t env_base, float* intensity_dev, float* signal_dev,
+                 void* stream) {
+    AcqParams P;
+    int rc = make_params(P, dmap_in_dev, dmap_out_dev, tables_dev, pdt_dev, B, H, W, K, flags, det, lambda_fluo, seed,
+                         offset, env_base, intensity_dev, signal_dev);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    // grid.y/z limits: split very large batches
+    const int maxB = 65535;
+    for (int b0 = 0; b0 < B; b0 += maxB) {
+        AcqParams Q = P;
+        Q.B = (B - b0 < maxB) ? B - b0 : maxB;
+        const size_t dm = (size_t)b0 * P.Hp * P.Wpitch, im = (size_t)b0 * H * W;
+        Q.din = P.din + dm;
+        Q.dout = P.dout ? P.dout + dm : nullptr;
+        Q.tables = P.tables + (size_t)b0 * STED_TABLES * K * P.KP;
+        Q.pdt = P.pdt + b0;
+        Q.intensity = P.intensity ? P.intensity + im : nullptr;
+        Q.signal = P.signal + im;
+        Q.env_base = P.env_base + (uint32_t)b0;
+        rc = (flags & STED_BLEACH) ? launch_sweep(Q, (cudaStream_t)stream) : launch_gather(Q, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return STED_OK;
+}
+
+int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const StedFluoParams* fluo_host,
+                      const double* p_ex_host, const double* p_sted_host, const double* pdt_host, int B, int H, int W,
+                      int K, uint32_t flags, const StedDetectorParams* det, uint64_t seed, uint64_t offset,
+                      int64_t env_base, float* intensity_host, float* signal_host) {
+    if (!dmap_host || !psf_cache_host || !fluo_host || !p_ex_host || !p_sted_host || !pdt_host || !signal_host || !det)
+        return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B, H, W must be positive");
+    if (K < 1 || (K & 1) == 0) return fail(STED_EINVAL, "K must be odd (got %d)", K);
+    if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
+    int rc = check_device();
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    const int KP = STED_KPITCH(K), Hp = H + K - 1, Wp = W + K - 1, Wpitch = (Wp + 3) & ~3, p = K / 2;
+    const size_t n_roi = (size_t)B * H * W, n_pad = (size_t)B * Hp * Wpitch;
+    enum { ROI, PADA, PADB, TAB, CACHE, FLUO, SCAL, OUT };
+    if ((rc = g_ws.ensure(ROI, n_roi * 4)) || (rc = g_ws.ensure(PADA, n_pad * 4)) ||
+        (rc = g_ws.ensure(PADB, (flags & STED_BLEACH) ? n_pad * 4 : 16)) ||
+        (rc = g_ws.ensure(TAB, (size_t)B * STED_TABLES * K * KP * 4)) || (rc = g_ws.ensure(CACHE, 3ull * K * K * 8)) ||
+        (rc = g_ws.ensure(FLUO, (size_t)B * sizeof(StedFluoParams))) || (rc = g_ws.ensure(SCAL, 3ull * B * 8)) ||
+        (rc = g_ws.ensure(OUT, 2 * n_roi * 4)))
+        return rc;
+    cudaStream_t st = 0;
+    float* d_roi = (float*)g_ws.dev[ROI];
+    float* d_a = (float*)g_ws.dev[PADA];
+    float* d_b = (float*)g_ws.dev[PADB];
+    float* d_tab = (float*)g_ws.dev[TAB];
+    double* d_cache = (double*)g_ws.dev[CACHE];
+    StedFluoParams* d_fluo = (StedFluoParams*)g_ws.dev[FLUO];
+    double* d_scal = (double*)g_ws.dev[SCAL];
+    float* d_int = (float*)g_ws.dev[OUT];
+    float* d_sig = d_int + n_roi;
+    CUDA_TRY(cudaMemcpyAsync(d_roi, dmap_host, n_roi * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cache, psf_cache_host, 3ull * K * K * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_fluo, fluo_host, (size_t)B * sizeof(StedFluoParams), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_scal, p_ex_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_scal + B, p_sted_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_scal + 2 * B, pdt_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    pad_kernel<<<592, 256, 0, st>>>(d_roi, d_a, B, H, W, p, Hp, Wpitch);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = sted_make_effective(d_cache, d_fluo, d_scal, d_scal + B, d_scal + 2 * B, B, K, d_tab, nullptr, st))) return rc;
+    if ((rc = sted_acquire(d_a, (flags & STED_BLEACH) ? d_b : nullptr, d_tab, d_scal + 2 * B, B, H, W, K, flags, det,
+                           fluo_host[0].lambda_fluo, seed, offset, env_base, intensity_host ? d_int : nullptr, d_sig, st)))
+        return rc;
+    if (flags & STED_BLEACH) {
+        unpad_kernel<<<592, 256, 0, st>>>(d_b, d_roi, B, H, W, p, Hp, Wpitch);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(dmap_host, d_roi, n_roi * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (intensity_host) CUDA_TRY(cudaMemcpyAsync(intensity_host, d_int, n_roi * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(signal_host, d_sig, n_roi * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return STED_OK;
+}
+
+int sted_sample_poisson(const float* lambda_dev, int64_t n, uint64_t seed, uint64_t offset, float* out_dev, void* stream) {
+    if (!lambda_dev || !out_dev || n <= 0) return fail(STED_EINVAL, "bad argument");
+    int rc = check_device();
+    if (rc) return rc;
+    poisson_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lambda_dev, n, seed, (uint32_t)offset, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+int sted_sample_binomial(const float* n_dev, const float* q_dev, int64_t n, uint64_t seed, uint64_t offset,
+                         float* out_dev, void* stream) {
+    if (!n_dev || !q_dev || !out_dev || n <= 0) return fail(STED_EINVAL, "bad argument");
+    int rc = check_device();
+    if (rc) return rc;
+    binomial_test_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n_dev, q_dev, n, seed, (uint32_t)offset, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+void sted_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out_host[4]) {
+    Philox4 c{ctr[0], ctr[1], ctr[2], ctr[3]};
+    Philox4 r = philox4x32_10(c, key[0], key[1]);
+    out_host[0] = r.x; out_host[1] = r.y; out_host[2] = r.z; out_host[3] = r.w;
+}
+
+int sted_fma_peak(double* tflops, void* stream) {
+    if (!tflops) return fail(STED_EINVAL, "null pointer argument");
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 4));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, 0));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    fma_peak_kernel<<<blocks, 256, 0, st>>>(d, 1 << 10);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, st));
+        fma_peak_kernel<<<blocks, 256, 0, st>>>(d, iters);
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 16 * iters * 256.0 * blocks / (ms * 1e-3) * 1e-12;
+        if (fl > best) best = fl;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return STED_OK;
+}
+
+}  // extern "C"

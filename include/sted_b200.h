@@ -1,0 +1,160 @@
+/*
+ * sted_b200.h — C ABI of the B200-native STED acquisition hot path.
+ *
+ * Drop-in boundary for the path gym-sted reaches through
+ *   pysted.base.Microscope.get_signal_and_bleach   (reference call sites:
+ *       gym_sted/envs/mosted_env.py:184,222,227,232)
+ *   pysted.base.Microscope.get_effective / fluo.get_k_bleach / detector.get_signal
+ *       (gym_sted/utils.py:616-631,646-657)
+ *   gym_sted.utils.get_foreground + rewards.objectives.{Signal_Ratio,Bleach,Resolution,
+ *       NumberNanodomains}                        (gym_sted/utils.py:16-24,
+ *       gym_sted/rewards/objectives.py:57-430)
+ *
+ * The reference has no FFI layer of its own (pure Python calling pySTED's Cython); these
+ * entry points are what a ctypes stub on the reference side binds — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `*_dev` pointer is DEVICE memory owned by the
+ *     caller, every `*_host` pointer is HOST memory owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); device entry points
+ *     are stream-ordered and never synchronise; `*_host` entry points synchronise before
+ *     returning (their outputs are host memory);
+ *   - return 0 on success, a negative STED_E* code otherwise; sted_last_error() gives text;
+ *   - outputs are fully overwritten; no allocation crosses the ABI (the `*_host` calls keep a
+ *     private, growable device workspace per process);
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     STED_ENODEVICE.
+ *
+ * Device datamap layout ("molecule map"): float32 [B][Hp][Wpitch], Hp = H + K - 1,
+ *   Wp = W + K - 1, Wpitch = Wp rounded up to a multiple of 4 (16-byte rows for TMA / float4).
+ *   Counts are integer-valued floats (< 2^24) in stochastic mode, expected counts otherwise.
+ *   The K/2-pixel frame around the H x W region of interest is the zero padding
+ *   pysted.base.Datamap.set_roi(i_ex, "max") adds (gym_sted/utils.py:179-180).
+ */
+#ifndef STED_B200_H
+#define STED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STED_OK            0
+#define STED_EINVAL       -1   /* bad argument (shape, alignment, null pointer, aliasing)   */
+#define STED_ENODEVICE    -2   /* no usable CUDA device / driver                            */
+#define STED_ECUDA        -3   /* a CUDA runtime call or kernel launch failed                */
+#define STED_EUNSUPPORTED -4   /* shape outside the compiled limits (K > STED_MAX_K, ...)    */
+
+#define STED_MAX_K        63   /* largest PSF side (odd)                                     */
+#define STED_KPITCH(K)    ((((K) + 1) + 3) & ~3)   /* row pitch of the per-env K x K tables  */
+
+/* flags of sted_acquire* */
+#define STED_BLEACH         1u  /* apply in-scan photobleaching (pySTED bleach=True)          */
+#define STED_SAMPLE_PHOTONS 2u  /* detector noise: Poisson photon counts (Detector.noise)     */
+#define STED_SAMPLE_BLEACH  4u  /* binomial molecule thinning; otherwise expected counts      */
+
+/* Fluorophore + STED-pulse parameters of one environment.
+ * Mirrors pysted.base.Fluorescence(**defaults.FLUO) (gym_sted/defaults.py:25-42) and the
+ * lambda_/tau/rate attributes gym-sted reads from microscope.excitation / microscope.sted
+ * (gym_sted/utils.py:620-623). */
+typedef struct StedFluoParams {
+    double lambda_ex;        /* excitation wavelength (m)                  */
+    double lambda_sted;      /* depletion wavelength (m)                   */
+    double lambda_fluo;      /* emission wavelength (m)                    */
+    double sigma_abs_ex;     /* absorption cross-section at lambda_ex (m2) */
+    double sigma_abs_sted;   /* ... at lambda_sted (anti-Stokes excitation) */
+    double sigma_ste;        /* stimulated-emission cross-section (m2)     */
+    double qy;               /* quantum yield                              */
+    double tau;              /* fluorescence lifetime (s)                  */
+    double tau_vib;          /* vibrational relaxation (s)                 */
+    double tau_tri;          /* triplet lifetime (s)                       */
+    double k0, k1, b;        /* bleaching law k0*I + k1*I^b                */
+    double triplet_dynamics_frac;
+    double sted_tau;         /* STED pulse width (s)                       */
+    double sted_rate;        /* laser repetition rate (Hz)                 */
+    int32_t anti_stoke;      /* DonutBeam.anti_stoke                       */
+    int32_t _pad;
+} StedFluoParams;
+
+/* Detector parameters (pysted.base.Detector; gym_sted/defaults.py:21). */
+typedef struct StedDetectorParams {
+    double pcef;             /* photon collection efficiency  */
+    double pdef;             /* photon detection efficiency   */
+    double background;       /* background counts per second  */
+} StedDetectorParams;
+
+/* Per-env tables produced by sted_make_effective, consumed by sted_acquire*.
+ * float32 [B][STED_TABLES][K][KP], KP = STED_KPITCH(K); columns >= K are zero. */
+#define STED_TAB_E   0   /* effective PSF E[u][v] (W per molecule) — Microscope.get_effective */
+#define STED_TAB_ET  1   /* E[u][v]*exp(-sum_{v'>v} A[u][v']): in-row expected-survival weights */
+#define STED_TAB_CH  2   /* suffix hazard CH[u][v] = sum_{v'>=v} A[u][v'], A = k_bleach*pdt    */
+#define STED_TAB_RS  3   /* exp(-CH[u][v]): survival of a whole in-row pass starting at tap v     */
+#define STED_TABLES  4
+
+const char* sted_version(void);
+const char* sted_last_error(void);
+/* Number of visible CUDA devices (0 when none); never fails. */
+int sted_device_count(void);
+
+/* get_effective + get_k_bleach for B environments at once.
+ *   psf_cache_dev : float64 [3][K][K]  = Microscope.cache(px): i_ex, i_sted (instantaneous,
+ *                   per watt of average power), psf_det
+ *   fluo_dev      : StedFluoParams [B]
+ *   p_ex/p_sted/pdt_dev : float64 [B]  imaging parameters of each environment
+ *   tables_dev    : float32 [B][STED_TABLES][K][KP]  (output)
+ *   kbleach_dev   : float64 [B][K][K] bleaching-rate map k_b (1/s), or NULL (output)
+ */
+int sted_make_effective(const double* psf_cache_dev, const StedFluoParams* fluo_dev,
+                        const double* p_ex_dev, const double* p_sted_dev, const double* pdt_dev,
+                        int B, int K, float* tables_dev, double* kbleach_dev, void* stream);
+
+/* One raster-scan acquisition for B environments (Microscope.get_signal_and_bleach).
+ *   dmap_in_dev   : float32 [B][Hp][Wpitch] molecule maps
+ *   dmap_out_dev  : float32 [B][Hp][Wpitch] bleached maps (required, and != dmap_in_dev, when
+ *                   STED_BLEACH is set; ignored otherwise)
+ *   tables_dev    : from sted_make_effective
+ *   pdt_dev       : float64 [B] pixel dwell times
+ *   det           : detector parameters (host struct, read during the call)
+ *   lambda_fluo   : emission wavelength for the photon conversion (m)
+ *   seed, offset  : Philox key / acquisition counter; (seed, offset, env, pixel) fixes every draw,
+ *                   env ids are env_base .. env_base+B-1 so results do not depend on sharding
+ *   intensity_dev : float32 [B][H][W] detected power per pixel (W), or NULL
+ *   signal_dev    : float32 [B][H][W] photon counts (integer-valued when STED_SAMPLE_PHOTONS)
+ */
+int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tables_dev,
+                 const double* pdt_dev, int B, int H, int W, int K, uint32_t flags,
+                 const StedDetectorParams* det, double lambda_fluo,
+                 uint64_t seed, uint64_t offset, int64_t env_base,
+                 float* intensity_dev, float* signal_dev, void* stream);
+
+/* Same, from HOST buffers: pads, uploads, runs sted_make_effective + sted_acquire, downloads.
+ *   dmap_host     : float32 [B][H][W] molecule maps of the region of interest (un-padded);
+ *                   overwritten with the bleached maps when STED_BLEACH is set
+ *   psf_cache_host: float64 [3][K][K]
+ *   fluo_host     : StedFluoParams [B];  p_ex/p_sted/pdt_host : float64 [B]
+ *   intensity_host, signal_host : float32 [B][H][W] (intensity_host may be NULL)
+ */
+int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
+                      const StedFluoParams* fluo_host, const double* p_ex_host,
+                      const double* p_sted_host, const double* pdt_host,
+                      int B, int H, int W, int K, uint32_t flags,
+                      const StedDetectorParams* det, uint64_t seed, uint64_t offset,
+                      int64_t env_base, float* intensity_host, float* signal_host);
+
+/* Samplers exposed for the statistical tests (same device functions the kernels use).
+ *   out_dev[i] ~ Poisson(lambda_dev[i]) / Binomial(n_dev[i], q_dev[i]); counter = i. */
+int sted_sample_poisson(const float* lambda_dev, int64_t n, uint64_t seed, uint64_t offset,
+                        float* out_dev, void* stream);
+int sted_sample_binomial(const float* n_dev, const float* q_dev, int64_t n, uint64_t seed,
+                         uint64_t offset, float* out_dev, void* stream);
+/* Raw Philox4x32-10 block for known-answer tests: out_host[4]. Host-side, no device needed. */
+void sted_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out_host[4]);
+
+/* FP32-FMA peak microbenchmark (roofline denominator): returns achieved TFLOP/s in *tflops. */
+int sted_fma_peak(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STED_B200_H */

@@ -1,0 +1,56 @@
+"""Shared builders for the test-suite (oracle + product objects on identical parameters)."""
+import functools
+import os
+
+import numpy as np
+
+from gym_sted_b200 import base, defaults
+from oracle import pysted_oracle as po
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PX = defaults.PIXELSIZE
+
+
+def _det(noise=False, background=0.0):
+    return {"noise": noise, "background": background}
+
+
+@functools.lru_cache(maxsize=None)
+def oracle_psf_cache():
+    """(i_ex, i_sted, psf_det) from the oracle's scipy.integrate.quad beams; memoised on disk under
+    tests/golden/ (regenerate with tests/golden/make_golden.py)."""
+    path = os.path.join(GOLDEN, "oracle_psf_cache.npz")
+    if os.path.exists(path):
+        z = np.load(path)
+        return z["i_ex"], z["i_sted"], z["psf_det"]
+    m = po.default_microscope(defaults.FLUO, _det(), defaults.LASER_EX, defaults.LASER_STED, defaults.OBJECTIVE)
+    return m.cache(PX)
+
+
+def oracle_microscope(fluo=None, noise=False, background=0.0):
+    m = po.default_microscope(fluo or defaults.FLUO, _det(noise, background), defaults.LASER_EX, defaults.LASER_STED,
+                              defaults.OBJECTIVE)
+    m._cache[int(round(PX * 1e9))] = oracle_psf_cache()
+    return m
+
+
+def product_microscope(fluo=None, noise=False, background=0.0):
+    return base.Microscope(base.GaussianBeam(**defaults.LASER_EX), base.DonutBeam(**defaults.LASER_STED),
+                           base.Detector(**_det(noise, background)), base.Objective(**defaults.OBJECTIVE),
+                           base.Fluorescence(**(fluo or defaults.FLUO)), load_cache=True)
+
+
+def synthetic_datamap(rng, H, W, density=0.14, molecules=5, n_domains=6, domain=(100, 175)):
+    """Sparse spine-like molecule map: a band of `molecules` per pixel plus single-pixel nanodomains."""
+    d = np.zeros((H, W), dtype=np.int64)
+    yy, xx = np.mgrid[:H, :W]
+    cy, cx = H / 2 + rng.uniform(-H / 8, H / 8), W / 2 + rng.uniform(-W / 8, W / 8)
+    ry, rx = H * rng.uniform(0.2, 0.35), W * rng.uniform(0.2, 0.35)
+    rr = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2
+    band = (rr < 1.0) & (rr > 0.45)
+    d[band] = molecules
+    ys, xs = np.nonzero(band)
+    if len(ys):
+        for i in rng.choice(len(ys), size=min(n_domains, len(ys)), replace=False):
+            d[ys[i], xs[i]] = rng.integers(domain[0], domain[1] + 1)
+    return d

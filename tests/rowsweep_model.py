@@ -1,0 +1,73 @@
+"""float64 numpy model of the row-sweep schedule used by ``sweep_kernel`` (csrc/sted_kernels.cu).
+
+Test-side only.  It lets the CPU suite check the *derivation*  against the
+sequential oracle without a GPU: per scan row, gather against the row-start state with in-row
+survival folded into the weights, then thin the K-row band once.
+"""
+import numpy as np
+
+
+def tables(E, A):
+    """E, A=(k_b*pdt): (K,K).  Returns ET, CH (K,K+1), as sted_make_effective builds them."""
+    K = E.shape[0]
+    CH = np.zeros((K, K + 1))
+    CH[:, :K] = np.cumsum(A[:, ::-1], axis=1)[:, ::-1]      # CH[u][v] = sum_{v'>=v} A[u][v']
+    ET = E * np.exp(-CH[:, 1:])
+    return ET, CH
+
+
+def sweep_expectation(D, H, W, E, A):
+    """D: (Hp,Wp) float64, returns (intensity (H,W), bleached D)."""
+    K = E.shape[0]
+    ET, CH = tables(E, A)
+    Wp = W + K - 1
+    D = D.copy()
+    out = np.zeros((H, W))
+    x = np.arange(Wp)
+    lo = np.maximum(0, x - W + 1)
+    hi = np.minimum(K - 1, x)
+    for r in range(H):
+        band = D[r:r + K]                                   # view, band[u] = row r+u
+        # in-row clip: pixel (u,x) was only thinned by taps v' <= hi(x)
+        scaled = band * np.exp(CH[:, hi + 1])               # (K,Wp) * (K,Wp)
+        for c in range(W):
+            out[r, c] = (ET * scaled[:, c:c + K]).sum()
+        band *= np.exp(-(CH[np.arange(K)[:, None], lo[None, :]] - CH[np.arange(K)[:, None], hi[None, :] + 1]))
+    return out, D
+
+
+def sweep_stochastic(D, H, W, E, A, rng):
+    """Integer thinning with one binomial per (pixel, scan row) + hazard-inverted death taps."""
+    K = E.shape[0]
+    _, CH = tables(E, A)
+    Wp = W + K - 1
+    D = D.astype(np.int64).copy()
+    out = np.zeros((H, W))
+    for r in range(H):
+        band = D[r:r + K]
+        row = np.zeros(W)
+        for c in range(W):
+            row[c] = (E * band[:, c:c + K]).sum()
+        ys, xs = np.nonzero(band)
+        for u, x in zip(ys, xs):
+            lo, hi = max(0, x - W + 1), min(K - 1, x)
+            hz = CH[u, lo] - CH[u, hi + 1]
+            if hz <= 0:
+                continue
+            n = band[u, x]
+            dead = rng.binomial(n, -np.expm1(-hz))
+            if dead == 0:
+                continue
+            band[u, x] = n - dead
+            pd = -np.expm1(-hz)
+            for _ in range(dead):
+                t = -np.log1p(-rng.random() * pd)
+                thr = t + CH[u, hi + 1]
+                cand = np.nonzero(CH[u, lo:hi + 1] >= thr)[0]
+                a = lo + cand.max()                          # largest v with CH[u][v] >= thr
+                for v in range(lo, a):
+                    c = x - v
+                    if 0 <= c < W:
+                        row[c] -= E[u, v]
+        out[r] = row
+    return out, D
