@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — STED acquisitions/sec on the ContextualMOSTED acquisition schedule.
+
+One *step* = the four acquisitions a ContextualMOSTED ``env.step`` performs for every environment of
+the batch (gym_sted/envs/mosted_env.py:222-234 + :184): confocal, STED with in-scan bleaching
+(stochastic, detector noise on), confocal on the bleached map, confocal on a fresh datamap.
+Workload at N=1: BASELINE.json configs[1], ContextualMOSTED-easy-hslb-v0, 256 envs, 256x256 px,
+K=59 PSF, actions uniform in the action box.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU restatement of pySTED's loop
+(oracle/raster_oracle.c, kind "port": pySTED itself is not installable here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ACQ_PER_STEP = 4
+K = 59
+
+
+def algorithmic_flops(H, W, bleach):
+    n = H * W * K * K
+    return (3 if bleach else 2) * n
+
+
+def algorithmic_bytes(H, W, bleach):
+    hp, wp = H + K - 1, W + K - 1
+    return 4 * hp * wp + 4 * H * W + (4 * hp * wp if bleach else 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C dwell loop on host threads (ctypes releases the GIL)
+# ------------------------------------------------------------------------------------------------
+def cpu_env_steps(n_envs, H, W, threads, seed=1234):
+    """Runs `n_envs` full env-steps (4 acquisitions each) of the workload on `threads` host threads.
+    Returns (seconds, acquisitions)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from gym_sted_b200 import defaults, synapse
+    from oracle import pysted_oracle as po
+    from tests import helpers
+
+    om = helpers.oracle_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
+                                   background=defaults.DETECTOR["background"])
+    po.raster_lib()
+    rng = np.random.default_rng(seed)
+    lo = np.array([defaults.action_spaces[k]["low"] for k in ("p_sted", "p_ex", "pdt")])
+    hi = np.array([defaults.action_spaces[k]["high"] for k in ("p_sted", "p_ex", "pdt")])
+    actions = rng.uniform(lo, hi, (n_envs, 3))
+    maps, _ = synapse.generate_batch(2 * n_envs, H, W, seed=seed)
+    i_ex = om.cache(helpers.PX)[0]
+
+    def one(i):
+        dm = po.Datamap(maps[i], helpers.PX); dm.set_roi(i_ex, "max")
+        conf = dict(pdt=defaults.PDT, p_ex=defaults.P_EX, p_sted=0.0)
+        om.get_signal_and_bleach(dm, helpers.PX, **conf, bleach=False)
+        om.get_signal_and_bleach(dm, helpers.PX, pdt=actions[i, 2], p_ex=actions[i, 1], p_sted=actions[i, 0],
+                                 bleach=True, seed=i + 1)
+        om.get_signal_and_bleach(dm, helpers.PX, **conf, bleach=False)
+        dm2 = po.Datamap(maps[n_envs + i], helpers.PX); dm2.set_roi(i_ex, "max")
+        om.get_signal_and_bleach(dm2, helpers.PX, **conf, bleach=False)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(n_envs)))
+    return time.perf_counter() - t0, n_envs * ACQ_PER_STEP
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    H = W = args.size
+    cores = os.cpu_count() or 1
+    n_envs = max(cores, 8) if args.cpu_envs is None else args.cpu_envs
+    for _ in range(min(args.warmup, 1)):
+        cpu_env_steps(min(cores, n_envs), H, W, cores)
+    times, acqs = [], 0
+    for _ in range(args.steps):
+        t, a = cpu_env_steps(n_envs, H, W, cores)
+        times.append(t); acqs += a
+    total = sum(times)
+    value = acqs / total
+    sample = f"{n_envs} envs x 4 acquisitions per step ({H}x{W} px, K=59), {args.steps} steps, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "STED acquisitions/sec", "value": value, "unit": "acquisitions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_envs, 1),
+        "cpu_baseline": {"value": value, "unit": "acquisitions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "acquisitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, envs_per_gpu, world):
+    return {"workload": f"ContextualMOSTED-easy-hslb-v0 acquisition schedule (conf, STED+bleach, conf, conf-on-new-map), "
+                        f"{envs_per_gpu} envs/GPU, {args.size}x{args.size} px, K=59, stochastic bleaching + Poisson detection",
+            "envs_per_gpu": envs_per_gpu, "global_envs": envs_per_gpu * world, "image": [args.size, args.size],
+            "psf": [K, K], "fluorophore": "high-signal_low-bleach", "actions": "uniform in action box",
+            "l2": "inputs larger than L2: molecule maps + images of one step exceed 126 MB",
+            "parallelism": f"env-parallel x{world}, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.barrier()
+    from gym_sted_b200 import _lib, defaults, synapse
+    from gym_sted_b200.batch import BatchedMicroscope
+    from tests import helpers  # builders only (no oracle use on this path except cpu_baseline below)
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    H = W = args.size
+    B = args.envs
+    env_base = rank * B
+    micro = helpers.product_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
+                                       background=defaults.DETECTOR["background"])
+    bm = BatchedMicroscope(micro, B, H, W, device=dev, env_base=env_base, seed=1234)
+
+    # synthetic inputs: two pools of B maps (current / fresh), resident in HBM and in pinned host memory
+    n_unique = min(B, 32)
+    maps_np, _ = synapse.generate_batch(2 * n_unique, H, W, seed=1234, env_base=env_base)
+    reps = (B + n_unique - 1) // n_unique
+    pool = [torch.from_numpy(np.tile(maps_np[i * n_unique:(i + 1) * n_unique], (reps, 1, 1))[:B]).to(torch.float32)
+            for i in range(2)]
+    pool_dev = [p.to(dev) for p in pool]
+    pool_pin = [p.pin_memory() for p in pool]
+    g = torch.Generator().manual_seed(1234 + rank)
+    lo = torch.tensor([defaults.action_spaces[k]["low"] for k in ("p_sted", "p_ex", "pdt")], dtype=torch.float64)
+    hi = torch.tensor([defaults.action_spaces[k]["high"] for k in ("p_sted", "p_ex", "pdt")], dtype=torch.float64)
+    n_act = args.steps + args.warmup + 2
+    actions = (lo + (hi - lo) * torch.rand((n_act, B, 3), generator=g, dtype=torch.float64))
+    actions_dev = actions.to(dev)
+    conf = [torch.full((B,), v, dtype=torch.float64, device=dev) for v in (defaults.PDT, defaults.P_EX, 0.0)]
+    sig = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(4)]
+    launches = [0]
+    kern_ev = []
+
+    def step(i, timed):
+        a = actions_dev[i]
+        bm.set_datamaps(pool_dev[0])
+        ev = None
+        if timed:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        bm.make_effective(conf[1], conf[2], conf[0])
+        if ev: ev[0].record()
+        _gather_only(bm, conf[0], sig[0])
+        if ev: ev[1].record(); kern_ev.append(ev)
+        bm.get_signal_and_bleach(a[:, 2].contiguous(), a[:, 1].contiguous(), a[:, 0].contiguous(), bleach=True,
+                                 out_signal=sig[1])
+        bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[2])
+        bm.set_datamaps(pool_dev[1])
+        bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
+        launches[0] += 8
+
+    def _gather_only(bm, pdt, out):
+        import ctypes
+        bm.offset += 1
+        flags = _lib.STED_SAMPLE_PHOTONS
+        _lib.check(bm.lib.sted_acquire(bm.dmap.data_ptr(), None, bm.tables.data_ptr(), pdt.data_ptr(), bm.B, bm.H,
+                                       bm.W, bm.K, flags, ctypes.byref(bm.det), bm.lambda_fluo, bm.seed, bm.offset,
+                                       bm.env_base, None, out.data_ptr(),
+                                       torch.cuda.current_stream(dev).cuda_stream))
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i, False)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i, True)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    gather_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
+    n_launch = launches[0]
+
+    # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region
+    import ctypes
+    lib = bm.lib
+    cache = micro._packed_cache(helpers.PX)
+    from gym_sted_b200.base import fluo_struct
+    fl = (_lib.StedFluoParams * B)(*[fluo_struct(micro.fluo, micro.excitation, micro.sted)] * B)
+    det = micro.detector.params()
+    h_map = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    h_sig = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    conf_np = [np.full(B, v) for v in (defaults.P_EX, 0.0, defaults.PDT)]
+    vp = ctypes.c_void_p
+
+    def host_acquire(p_ex, p_sted, pdt, flags, off):
+        _lib.check(lib.sted_acquire_host(h_map.data_ptr(), cache.ctypes.data_as(vp), ctypes.cast(fl, vp),
+                                         p_ex.ctypes.data_as(vp), p_sted.ctypes.data_as(vp), pdt.ctypes.data_as(vp),
+                                         B, H, W, K, flags, ctypes.byref(det), 1234, off, env_base, None,
+                                         h_sig.data_ptr()))
+
+    def e2e_step(i):
+        a = actions[i].numpy()
+        h_map.copy_(pool_pin[0])
+        host_acquire(*conf_np, _lib.STED_SAMPLE_PHOTONS, 4 * i + 1)
+        host_acquire(np.ascontiguousarray(a[:, 1]), np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 2]),
+                     _lib.STED_BLEACH | _lib.STED_SAMPLE_BLEACH | _lib.STED_SAMPLE_PHOTONS, 4 * i + 2)
+        host_acquire(*conf_np, _lib.STED_SAMPLE_PHOTONS, 4 * i + 3)
+        h_map.copy_(pool_pin[1])
+        host_acquire(*conf_np, _lib.STED_SAMPLE_PHOTONS, 4 * i + 4)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step(0)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i + 1)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    img_bytes = B * H * W * 4
+    h2d = 4 * img_bytes + 4 * (3 * K * K * 8 + B * (136 + 24))
+    d2h = 4 * img_bytes + img_bytes
+
+    # ---- max over ranks
+    t = torch.tensor([ms, e2e_s, gather_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s, gather_ms = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        acq = ACQ_PER_STEP * B * world * args.steps
+        value = acq / (ms * 1e-3)
+        e2e_value = ACQ_PER_STEP * B * world * e2e_steps / e2e_s
+        # roofline of the dominant kernel (gather_kernel<59>: 3 of 4 acquisitions)
+        peak = [0.0]
+        pk = ctypes.c_double()
+        _lib.check(lib.sted_fma_peak(ctypes.byref(pk), None))
+        fl_launch = algorithmic_flops(H, W, False) * B
+        achieved = fl_launch / (gather_ms * 1e-3) * 1e-12
+        by_launch = algorithmic_bytes(H, W, False) * B
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        roofline = {"bound": "fp32", "kernel": "gather_kernel<59>", "achieved": achieved, "peak": pk.value,
+                    "unit": "TFLOP/s", "frac": achieved / pk.value if pk.value else None, "traffic": None,
+                    "peak_source": "FP32 FFMA micro-benchmark run in this process (sted_fma_peak); "
+                                   "MEASURED_PEAKS.json has no FP32 entry",
+                    "algorithmic_flops_per_launch": fl_launch, "launch_ms": gather_ms,
+                    "hbm": {"achieved": by_launch / (gather_ms * 1e-3) * 1e-9, "peak": peaks.get("hbm_gbs", 6650.0),
+                            "unit": "GB/s", "peak_source": "measured" if peaks else "fallback"}}
+        cpu = None
+        if not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n_envs = args.cpu_envs or max(cores, 8)
+            tcpu, a = cpu_env_steps(n_envs, H, W, cores)
+            cpu = {"value": a / tcpu, "unit": "acquisitions/s", "cores": cores, "kind": "port",
+                   "sample": f"{n_envs} envs x 4 acquisitions of the same workload ({H}x{W}, K=59) on {cores} host "
+                             f"threads, {tcpu:.1f} s; C restatement of pySTED's dwell loop (oracle/raster_oracle.c), not pySTED"}
+        line = {
+            "metric": "STED acquisitions/sec", "value": value, "unit": "acquisitions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B, world), "env_steps_per_s": value / ACQ_PER_STEP,
+            "e2e": {"value": e2e_value, "unit": "acquisitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "sted_acquire_host (C ABI, pinned host buffers)"},
+            "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=256, help="environments per GPU")
+    ap.add_argument("--size", type=int, default=256, help="image side in pixels")
+    ap.add_argument("--cpu-envs", type=int, default=None, help="env-steps in the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,392 @@
+"""GPU parity tests of the acquisition path — CUDA kernels (through the C ABI) vs the CPU oracle.
+
+Tolerances: floating-point fields (effective PSF, expected photons, expected bleached maps) within
+1e-5 relative as north_star states; stochastic mode by per-pixel moments and KS tests.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from gym_sted_b200 import _lib, base, defaults  # noqa: E402
+from oracle import pysted_oracle as po  # noqa: E402
+from tests import helpers, rowsweep_model as rm  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+PX = helpers.PX
+RTOL = 1e-5
+
+
+def _require_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("these tests need a CUDA device (no CPU fallback exists)")
+
+
+@pytest.fixture(scope="module")
+def micro():
+    _require_gpu()
+    return helpers.product_microscope()
+
+
+@pytest.fixture(scope="module")
+def omicro():
+    return helpers.oracle_microscope()
+
+
+def batched(micro, B, H, W, **kw):
+    from gym_sted_b200.batch import BatchedMicroscope
+    return BatchedMicroscope(micro, B, H, W, device="cuda:0", **kw)
+
+
+def oracle_acquire(om, roi, pdt, p_ex, p_sted, mode, seed=0):
+    """(intensity, bleached padded map) from the sequential float64 oracle."""
+    dm = po.Datamap(roi, PX)
+    dm.set_roi(om.cache(PX)[0], "max")
+    E = om.get_effective(PX, p_ex, p_sted)
+    S = np.exp(-om.get_k_bleach_map(PX, p_ex, p_sted, pdt) * pdt)
+    work = dm.whole_datamap.astype(np.float64).copy()
+    inten = po.raster(work, roi.shape[0], roi.shape[1], E, S, mode, seed)
+    return inten, work[dm.roi]
+
+
+ACTIONS = [(10e-6, 10e-6, 0.0), (30e-6, 10e-6, 0.15), (100e-6, 20e-6, 0.35), (1e-6, 2e-6, 0.05)]  # pdt, p_ex, p_sted
+
+
+# ------------------------------------------------------------------ K1: get_effective / get_k_bleach
+def test_make_effective_tables_match_oracle(micro, omicro):
+    B = len(ACTIONS)
+    bm = batched(micro, B, 8, 8)
+    pdt, p_ex, p_sted = (torch.tensor([a[i] for a in ACTIONS], dtype=torch.float64, device="cuda") for i in range(3))
+    kb = bm.make_effective(p_ex, p_sted, pdt, want_kbleach=True).cpu().numpy()
+    tab = bm.tables.cpu().numpy()
+    K = bm.K
+    assert tab.shape == (B, 4, K, 60) and np.all(tab[:, :3, :, K:] == 0)
+    for b, (dt, pe, ps) in enumerate(ACTIONS):
+        E = omicro.get_effective(PX, pe, ps)
+        kref = omicro.get_k_bleach_map(PX, pe, ps, dt)
+        np.testing.assert_allclose(tab[b, _lib.STED_TAB_E, :, :K], E, rtol=2e-7, atol=0)
+        np.testing.assert_allclose(kb[b], kref, rtol=1e-11, atol=0)
+        ET, CH = rm.tables(E, kref * dt)
+        np.testing.assert_allclose(tab[b, _lib.STED_TAB_ET, :, :K], ET, rtol=3e-7)
+        np.testing.assert_allclose(tab[b, _lib.STED_TAB_CH, :, :K], CH[:, :K], rtol=3e-7)
+        np.testing.assert_allclose(tab[b, _lib.STED_TAB_RS, :, :K], np.exp(-CH[:, :K]), rtol=3e-7)
+
+
+def test_get_effective_facade(micro, omicro):
+    got = micro.get_effective(PX, 10e-6, 0.1)
+    np.testing.assert_allclose(got, omicro.get_effective(PX, 10e-6, 0.1), rtol=2e-7)
+    np.testing.assert_allclose(micro.get_k_bleach(PX, 10e-6, 0.1, 20e-6),
+                               omicro.get_k_bleach_map(PX, 10e-6, 0.1, 20e-6), rtol=1e-11)
+
+
+# ------------------------------------------------------------------ K2: gather (bleach=False)
+@pytest.mark.parametrize("H,W", [(64, 64), (80, 72), (33, 130), (1, 1)])
+def test_gather_matches_oracle(micro, omicro, H, W):
+    rng = np.random.default_rng(H * 1000 + W)
+    B = 3
+    rois = np.stack([helpers.synthetic_datamap(rng, H, W) if min(H, W) > 8 else rng.integers(0, 9, (H, W))
+                     for _ in range(B)])
+    rois[1] = rng.integers(0, 200, (H, W))          # dense map
+    bm = batched(micro, B, H, W)
+    bm.set_datamaps(torch.from_numpy(rois))
+    acts = ACTIONS[:B]
+    pdt, p_ex, p_sted = (torch.tensor([a[i] for a in acts], dtype=torch.float64) for i in range(3))
+    sig, inten = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=False, want_intensity=True, noise=False)
+    sig, inten = sig.cpu().numpy(), inten.cpu().numpy()
+    det = micro.detector
+    for b, (dt, pe, ps) in enumerate(acts):
+        ref, _ = oracle_acquire(omicro, rois[b], dt, pe, ps, 0)
+        np.testing.assert_allclose(inten[b], ref, rtol=RTOL, atol=1e-7 * ref.max())
+        mean = omicro.fluo.get_photons(ref) * det.pcef * det.pdef * dt + det.background * dt
+        np.testing.assert_allclose(sig[b], mean, rtol=RTOL, atol=1e-6 * max(mean.max(), 1e-30))
+    assert torch.equal(bm.datamaps_roi().cpu(), torch.from_numpy(rois).float())   # untouched
+
+
+def test_gather_generic_psf_size(micro):
+    """K != 59 goes through the runtime-K instantiation; random dense data, random tables."""
+    _require_gpu()
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for K, H, W in [(7, 20, 31), (11, 70, 66), (3, 5, 4)]:
+        KP = _lib.kpitch(K)
+        B = 2
+        Hp, Wp = H + K - 1, W + K - 1
+        Wpitch = (Wp + 3) & ~3
+        E = rng.random((B, K, K))
+        D = np.zeros((B, Hp, Wpitch), dtype=np.float32)
+        D[:, :, :Wp] = rng.integers(0, 50, (B, Hp, Wp))
+        tab = np.zeros((B, 4, K, KP), dtype=np.float32)
+        tab[:, 0, :, :K] = E
+        d_D, d_tab = torch.from_numpy(D).cuda(), torch.from_numpy(tab).cuda()
+        d_pdt = torch.full((B,), 1e-5, dtype=torch.float64, device="cuda")
+        d_int = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
+        d_sig = torch.empty_like(d_int)
+        det = _lib.StedDetectorParams(0.1, 0.5, 0.0)
+        _lib.check(lib.sted_acquire(d_D.data_ptr(), None, d_tab.data_ptr(), d_pdt.data_ptr(), B, H, W, K, 0,
+                                    ctypes.byref(det), 690e-9, 1, 1, 0, d_int.data_ptr(), d_sig.data_ptr(), None))
+        got = d_int.cpu().numpy()
+        for b in range(B):
+            work = D[b, :, :Wp].astype(np.float64).copy()
+            ref = po.raster(work, H, W, tab[b, 0, :, :K].astype(np.float64), np.ones((K, K)), 0)
+            np.testing.assert_allclose(got[b], ref, rtol=RTOL)
+
+
+# ------------------------------------------------------------------ K3: scan with bleaching, expectation mode
+@pytest.mark.parametrize("H,W", [(64, 64), (40, 96), (48, 160), (70, 30)])
+def test_sweep_expectation_matches_oracle(micro, omicro, H, W):
+    rng = np.random.default_rng(H * 7 + W)
+    acts = ACTIONS[1:4]
+    B = len(acts)
+    rois = np.stack([helpers.synthetic_datamap(rng, H, W) for _ in range(B)])
+    rois[2] = rng.integers(0, 60, (H, W))
+    bm = batched(micro, B, H, W)
+    bm.set_datamaps(torch.from_numpy(rois))
+    pdt, p_ex, p_sted = (torch.tensor([a[i] for a in acts], dtype=torch.float64) for i in range(3))
+    _, inten = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True, sample_bleach=False, want_intensity=True,
+                                        noise=False)
+    inten = inten.cpu().numpy()
+    bleached = bm.datamaps_roi().cpu().numpy()
+    whole = bm.dmap.cpu().numpy()
+    for b, (dt, pe, ps) in enumerate(acts):
+        ref_i, ref_d = oracle_acquire(omicro, rois[b], dt, pe, ps, 1)
+        np.testing.assert_allclose(inten[b], ref_i, rtol=RTOL, atol=1e-7 * ref_i.max())
+        np.testing.assert_allclose(bleached[b], ref_d, rtol=RTOL, atol=1e-6)
+        assert ref_d.sum() < rois[b].sum() * 0.999            # the case does bleach
+    p = bm.p
+    frame = whole.copy()
+    frame[:, p:p + H, p:p + W] = 0
+    assert not frame.any()                                     # zero frame preserved
+
+
+def test_sweep_generic_psf_edge_shapes(micro):
+    """Runtime-K sweep on shapes smaller than the PSF, one-pixel scans, ragged widths."""
+    _require_gpu()
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    for K, H, W in [(7, 9, 11), (7, 6, 4), (7, 3, 3), (5, 1, 1), (9, 20, 17), (11, 16, 70), (3, 1, 9)]:
+        KP = _lib.kpitch(K)
+        B = 2
+        Hp, Wp = H + K - 1, W + K - 1
+        Wpitch = (Wp + 3) & ~3
+        p = K // 2
+        D = np.zeros((B, Hp, Wpitch), dtype=np.float32)
+        D[:, p:p + H, p:p + W] = rng.integers(0, 9, (B, H, W)) * (rng.random((B, H, W)) < 0.6)
+        tab = np.zeros((B, 4, K, KP), dtype=np.float32)
+        tab[:, 3] = 1.0
+        Es, As = rng.random((B, K, K)), rng.random((B, K, K)) * 0.3
+        for b in range(B):
+            ET, CH = rm.tables(Es[b], As[b])
+            tab[b, 0, :, :K], tab[b, 1, :, :K] = Es[b], ET
+            tab[b, 2, :, :K], tab[b, 3, :, :K] = CH[:, :K], np.exp(-CH[:, :K])
+        d_D, d_tab = torch.from_numpy(D).cuda(), torch.from_numpy(tab).cuda()
+        d_out = torch.full_like(d_D, -1.0)
+        d_pdt = torch.full((B,), 1e-5, dtype=torch.float64, device="cuda")
+        d_int = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
+        d_sig = torch.empty_like(d_int)
+        det = _lib.StedDetectorParams(0.1, 0.5, 0.0)
+        _lib.check(lib.sted_acquire(d_D.data_ptr(), d_out.data_ptr(), d_tab.data_ptr(), d_pdt.data_ptr(), B, H, W, K,
+                                    _lib.STED_BLEACH, ctypes.byref(det), 690e-9, 1, 1, 0, d_int.data_ptr(),
+                                    d_sig.data_ptr(), None))
+        got_i, got_d = d_int.cpu().numpy(), d_out.cpu().numpy()
+        for b in range(B):
+            work = D[b, :, :Wp].astype(np.float64).copy()
+            ref = po.raster(work, H, W, Es[b], np.exp(-As[b]), 1)
+            np.testing.assert_allclose(got_i[b], ref, rtol=2e-5, atol=1e-6, err_msg=f"K={K} H={H} W={W}")
+            np.testing.assert_allclose(got_d[b, :, :Wp], work, rtol=2e-5, atol=1e-6, err_msg=f"K={K} H={H} W={W}")
+
+
+# ------------------------------------------------------------------ stochastic mode
+def test_sweep_stochastic_moments_and_ks(micro, omicro):
+    """256 replicas of one environment: per-pixel mean equals the exact mean field, spread and
+    distributions match the reference-order per-molecule thinning (oracle mode 2)."""
+    from scipy import stats
+    H = W = 24
+    rng = np.random.default_rng(2)
+    roi = helpers.synthetic_datamap(rng, H, W, n_domains=4)
+    R = 256
+    dt, pe, ps = 60e-6, 10e-6, 0.2
+    bm = batched(micro, R, H, W, seed=99)
+    bm.set_datamaps(torch.from_numpy(np.broadcast_to(roi, (R, H, W)).copy()))
+    _, inten = bm.get_signal_and_bleach(dt, pe, ps, bleach=True, sample_bleach=True, want_intensity=True, noise=False)
+    gi = inten.cpu().numpy().astype(np.float64)
+    gd = bm.datamaps_roi().cpu().numpy().astype(np.float64)
+    assert np.all(gd == np.rint(gd)) and np.all(gd <= roi) and np.all(gd >= 0)
+    exp_i, exp_d = oracle_acquire(omicro, roi, dt, pe, ps, 1)
+    oi = np.zeros((R, H, W)); od = np.zeros((R, H, W))
+    for r in range(R):
+        oi[r], od[r] = oracle_acquire(omicro, roi, dt, pe, ps, 2, seed=1000 + r)
+    assert 0.2 < exp_d.sum() / roi.sum() < 0.95               # substantial but partial bleaching
+    # means against the exact expectation (standard error of the mean from the oracle's spread)
+    se_i = oi.std(0) / np.sqrt(R) + 1e-9 * exp_i.max()
+    assert np.all(np.abs(gi.mean(0) - exp_i) < 5 * se_i + 1e-5 * exp_i)
+    se_d = od.std(0) / np.sqrt(R) + 1e-9
+    assert np.all(np.abs(gd.mean(0) - exp_d) < 5 * se_d + 1e-5 * exp_d + 1e-6)
+    # spreads
+    bright = exp_i > 0.2 * exp_i.max()
+    np.testing.assert_allclose(gi.std(0)[bright], oi.std(0)[bright], rtol=0.25)
+    occupied = roi > 0
+    np.testing.assert_allclose(gd.std(0)[occupied], od.std(0)[occupied], rtol=0.3, atol=0.15)
+    # KS on the brightest image pixel, on the total surviving molecules and on every nanodomain pixel
+    y, x = np.unravel_index(exp_i.argmax(), exp_i.shape)
+    assert stats.ks_2samp(gi[:, y, x], oi[:, y, x]).pvalue > 1e-3
+    assert stats.ks_2samp(gd.sum((1, 2)), od.sum((1, 2))).pvalue > 1e-3
+    for (yy, xx) in zip(*np.nonzero(roi > 50)):
+        assert stats.ks_2samp(gd[:, yy, xx], od[:, yy, xx]).pvalue > 1e-3
+
+
+def test_stochastic_results_do_not_depend_on_sharding(micro):
+    """Draws are keyed by (seed, offset, global env id, pixel): B=8 in one launch == two launches of 4."""
+    H = W = 40
+    rng = np.random.default_rng(4)
+    rois = np.stack([helpers.synthetic_datamap(rng, H, W) for _ in range(8)])
+    m = helpers.product_microscope(noise=True, background=defaults.DETECTOR["background"])
+    full = batched(m, 8, H, W, seed=7)
+    full.set_datamaps(torch.from_numpy(rois))
+    s_full, _ = full.get_signal_and_bleach(40e-6, 10e-6, 0.2, bleach=True)
+    d_full = full.datamaps_roi().clone()
+    for half in range(2):
+        part = batched(m, 4, H, W, seed=7, env_base=4 * half)
+        part.set_datamaps(torch.from_numpy(rois[4 * half:4 * half + 4]))
+        s, _ = part.get_signal_and_bleach(40e-6, 10e-6, 0.2, bleach=True)
+        assert torch.equal(s, s_full[4 * half:4 * half + 4])
+        assert torch.equal(part.datamaps_roi(), d_full[4 * half:4 * half + 4])
+    assert (d_full.sum() < torch.from_numpy(rois).sum())
+
+
+# ------------------------------------------------------------------ samplers
+@pytest.mark.parametrize("lam", [0.05, 0.9, 3.0, 11.9, 12.1, 47.0, 1.0e3, 2.5e5])
+def test_poisson_sampler_distribution(lam):
+    from scipy import stats
+    _require_gpu()
+    n = 400_000
+    lib = _lib.load()
+    d_lam = torch.full((n,), lam, dtype=torch.float32, device="cuda")
+    d_out = torch.empty_like(d_lam)
+    _lib.check(lib.sted_sample_poisson(d_lam.data_ptr(), n, 12345, 3, d_out.data_ptr(), None))
+    x = d_out.cpu().numpy().astype(np.float64)
+    assert np.all(x == np.rint(x)) and x.min() >= 0
+    assert abs(x.mean() - lam) < 5 * np.sqrt(lam / n)
+    assert abs(x.var() - lam) < 6 * lam * np.sqrt(2.0 / n) + 6 * np.sqrt(lam / n)
+    if lam < 100:
+        ks = np.arange(0, int(lam + 12 * np.sqrt(lam) + 12))
+        obs = np.bincount(x.astype(np.int64), minlength=len(ks) + 1)
+        expc = stats.poisson.pmf(ks, lam) * n
+        keep = expc > 5
+        chi2 = ((obs[:len(ks)][keep] - expc[keep]) ** 2 / expc[keep]).sum()
+        assert chi2 < stats.chi2.ppf(1 - 1e-6, keep.sum())
+    else:
+        assert stats.kstest(x + np.random.default_rng(0).uniform(-0.5, 0.5, n), stats.norm(lam, np.sqrt(lam)).cdf).statistic < 0.01
+
+
+@pytest.mark.parametrize("nmol,q", [(5, 1e-4), (5, 0.02), (150, 0.03), (150, 0.7), (1000, 0.5), (3, 0.999), (64, 0.25),
+                                    (65, 0.25), (1, 0.5)])
+def test_binomial_sampler_distribution(nmol, q):
+    from scipy import stats
+    _require_gpu()
+    n = 400_000
+    lib = _lib.load()
+    d_n = torch.full((n,), float(nmol), dtype=torch.float32, device="cuda")
+    d_q = torch.full((n,), q, dtype=torch.float32, device="cuda")
+    d_out = torch.empty_like(d_n)
+    _lib.check(lib.sted_sample_binomial(d_n.data_ptr(), d_q.data_ptr(), n, 777, 1, d_out.data_ptr(), None))
+    x = d_out.cpu().numpy().astype(np.int64)
+    assert x.min() >= 0 and x.max() <= nmol
+    ks = np.arange(nmol + 1)
+    expc = stats.binom.pmf(ks, nmol, float(np.float32(q))) * n
+    obs = np.bincount(x, minlength=nmol + 1)
+    keep = expc > 5
+    chi2 = ((obs[keep] - expc[keep]) ** 2 / expc[keep]).sum()
+    assert chi2 < stats.chi2.ppf(1 - 1e-6, max(keep.sum(), 1))
+    assert abs(x.mean() - nmol * q) < 5 * np.sqrt(nmol * q * (1 - q) / n) + 1e-7 * nmol
+
+
+def test_detector_noise_moments(micro):
+    """Poisson detection: per-pixel mean/variance over replicas equal the noise-free signal (+ background)."""
+    m = helpers.product_microscope(noise=True, background=defaults.DETECTOR["background"])
+    H = W = 32
+    rng = np.random.default_rng(8)
+    roi = helpers.synthetic_datamap(rng, H, W)
+    R = 512
+    bm = batched(m, R, H, W, seed=5)
+    bm.set_datamaps(torch.from_numpy(np.broadcast_to(roi, (R, H, W)).copy()))
+    noisy, _ = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)
+    clean, _ = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False, noise=False)
+    noisy, clean = noisy.cpu().numpy().astype(np.float64), clean.cpu().numpy().astype(np.float64)[0]
+    assert np.all(noisy == np.rint(noisy))
+    assert clean.min() == pytest.approx(0.5 / 3, rel=1e-4)     # background 0.5/(3*PDT) * PDT
+    assert np.all(np.abs(noisy.mean(0) - clean) < 5.5 * np.sqrt(clean / R))
+    ratio = noisy.var(0) / clean
+    assert abs(ratio.mean() - 1) < 0.02 and ratio.min() > 0.6 and ratio.max() < 1.5
+
+
+# ------------------------------------------------------------------ reference-facing call (host buffers)
+def test_microscope_facade_matches_oracle_and_mutates_datamap(omicro):
+    _require_gpu()
+    m = helpers.product_microscope()
+    rng = np.random.default_rng(12)
+    roi = helpers.synthetic_datamap(rng, 64, 64)
+    dm = base.Datamap(roi, PX)
+    dm.set_roi(m.cache(PX)[0], "max")
+    odm = po.Datamap(roi, PX)
+    odm.set_roi(omicro.cache(PX)[0], "max")
+    conf = dict(pdt=10e-6, p_ex=10e-6, p_sted=0.0)
+    c1, bl, i1 = m.get_signal_and_bleach(dm, PX, **conf, bleach=False)
+    oc1, _, oi1 = omicro.get_signal_and_bleach(odm, PX, **conf, bleach=False)
+    np.testing.assert_allclose(i1, oi1, rtol=RTOL, atol=1e-7 * oi1.max())
+    np.testing.assert_allclose(c1, oc1, rtol=RTOL, atol=1e-6)
+    assert bl["base"].shape == (122, 122) and np.array_equal(bl["base"], dm.whole_datamap)
+    sted = dict(pdt=30e-6, p_ex=10e-6, p_sted=0.15)
+    s, bl, i2 = m.get_signal_and_bleach(dm, PX, **sted, bleach=True, sample_bleach=False)
+    os_, obl, oi2 = omicro.get_signal_and_bleach(odm, PX, **sted, bleach=True, sample_bleach=False)
+    np.testing.assert_allclose(i2, oi2, rtol=RTOL, atol=1e-7 * oi2.max())
+    np.testing.assert_allclose(bl["base"], obl["base"], rtol=RTOL, atol=1e-6)
+    assert bl["base"] is dm.whole_datamap                      # mutated in place like pySTED (update=True)
+    c2, _, i3 = m.get_signal_and_bleach(dm, PX, **conf, bleach=False)
+    _, _, oi3 = omicro.get_signal_and_bleach(odm, PX, **conf, bleach=False)
+    np.testing.assert_allclose(i3, oi3, rtol=2 * RTOL, atol=1e-7 * oi3.max())
+    assert i3.sum() < i1.sum()
+    # stochastic call: integer outputs, fewer molecules, update=False leaves the datamap alone
+    before = dm.whole_datamap.copy()
+    m2 = helpers.product_microscope(noise=True, background=defaults.DETECTOR["background"])
+    dm2 = base.Datamap(roi, PX)
+    dm2.set_roi(m2.cache(PX)[0], "max")
+    ph, bl2, _ = m2.get_signal_and_bleach(dm2, PX, **sted, bleach=True, update=False, seed=3)
+    assert ph.dtype == np.int64 and bl2["base"].dtype == np.int64
+    assert bl2["base"].sum() < roi.sum() and np.array_equal(dm2.whole_datamap[dm2.roi], roi)
+    assert np.array_equal(dm.whole_datamap, before)
+    with pytest.raises(ValueError):
+        m.get_signal_and_bleach(base.Datamap(roi, PX), PX, **conf)
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE sizes)
+def test_full_size_properties(micro):
+    """256x256, K=59: linearity of the gather, monotone bleaching, integer thinning — properties that
+    need no CPU oracle at this size."""
+    H = W = 256
+    B = 4
+    from gym_sted_b200 import synapse
+    maps, _ = synapse.generate_batch(2 * B, H, W, seed=3)
+    bm = batched(micro, B, H, W, seed=1)
+    a, b = torch.from_numpy(maps[:B]).float(), torch.from_numpy(maps[B:]).float()
+    out = []
+    for roi in (a, b, a + b):
+        bm.set_datamaps(roi)
+        _, i = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False, want_intensity=True, noise=False)
+        out.append(i.clone())
+    torch.testing.assert_close(out[0] + out[1], out[2], rtol=1e-5, atol=1e-7 * float(out[2].max()))
+    bm.set_datamaps(a)
+    _, i_exp = bm.get_signal_and_bleach(50e-6, 10e-6, 0.25, bleach=True, sample_bleach=False, want_intensity=True,
+                                        noise=False)
+    d_exp = bm.datamaps_roi().clone()
+    assert torch.all(d_exp <= a.cuda() + 1e-4) and d_exp.sum() < 0.9 * a.sum()
+    bm.set_datamaps(a)
+    _, i_st = bm.get_signal_and_bleach(50e-6, 10e-6, 0.25, bleach=True, sample_bleach=True, want_intensity=True,
+                                       noise=False)
+    d_st = bm.datamaps_roi()
+    assert torch.all(d_st == torch.round(d_st)) and torch.all(d_st <= a.cuda()) and torch.all(d_st >= 0)
+    # totals agree with the mean field within a few sigma of binomial noise
+    tot_exp, tot_st = float(d_exp.sum()), float(d_st.sum())
+    assert abs(tot_exp - tot_st) < 6 * np.sqrt(float(a.sum()))
+    assert abs(float(i_st.sum()) / float(i_exp.sum()) - 1) < 0.01
