@@ -212,22 +212,26 @@ __global__ void __launch_bounds__(G_THREADS, 3) gather_kernel(const AcqParams P)
     for (; yy < K; ++yy) band_row(yy, false);                       // steady: all 8 rows active
     for (; yy < G_RT + K - 1; ++yy) band_row(yy, true);             // ramp-down
 
-    // ---- epilogue: detector
+    // ---- epilogue: stage the tile in shared memory (the datamap tile is dead), then run the detector
+    // in a compact, non-unrolled loop with coalesced stores.  (Unrolling the Poisson sampler over the
+    // 32 register accumulators made the kernel instruction-fetch bound: ncu stall_no_instruction.)
+    __syncthreads();
+    float* sOut = sD;
+#pragma unroll
+    for (int i = 0; i < G_RT; ++i)
+        *reinterpret_cast<float4*>(sOut + (r0 + i) * G_TW + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
     const float dwell = (float)P.pdt[b];
     const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
     const uint32_t env = P.env_base + (uint32_t)b;
-#pragma unroll
-    for (int i = 0; i < G_RT; ++i) {
-        const int r = tr0 + r0 + i;
-        if (r >= P.H) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = tc0 + c0 + j;
-            if (c >= P.W) continue;
-            const size_t o = ((size_t)b * P.H + r) * P.W + c;
-            if (P.intensity) P.intensity[o] = acc[i][j];
-            P.signal[o] = detect(P, acc[i][j], gain, bg_mean, env, (uint32_t)(r * P.W + c));
-        }
+#pragma unroll 1
+    for (int idx = tid; idx < G_TH * G_TW; idx += G_THREADS) {
+        const int r = tr0 + (idx / G_TW), c = tc0 + (idx % G_TW);
+        if (r >= P.H || c >= P.W) continue;
+        const float I = sOut[idx];
+        const size_t o = ((size_t)b * P.H + r) * P.W + c;
+        if (P.intensity) P.intensity[o] = I;
+        P.signal[o] = detect(P, I, gain, bg_mean, env, (uint32_t)(r * P.W + c));
     }
 }
 
@@ -280,21 +284,23 @@ __device__ __forceinline__ float reduce_scatter(float (&a)[CT], int lane) {
     return a[0];
 }
 
-template <int KT, int CT>
+template <int KT, int CT, bool STOCH>
 __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) {
     constexpr int TC = 8 * CT;
     const int K = KT ? KT : P.K;
     const int KP = KT ? STED_KPITCH(KT) : P.KP;
     const int PR = sweep_pitch(TC, KP);
     const int span = TC + K - 1;
-    const bool stochastic = (P.flags & STED_SAMPLE_BLEACH) != 0;
 
     extern __shared__ __align__(16) float smem[];
-    float* ring = smem;                       // [K][PR]
-    float* sWt = ring + K * PR;               // [K][KP] gather weights: E (stochastic) or ET
-    float* sCH = sWt + K * KP;                // [K][KP] suffix hazards
-    float* sRS = sCH + K * KP;                // [K][KP] exp(-CH) (expectation mode)
-    float* sI = sRS + K * KP;                 // [TC] row of intensities
+    float* ring = smem;                       // [K][PR]  band of the molecule map (counts / scaled expectations)
+    float* sWt = ring + K * PR;               // [K][KP]  gather weights: E (stochastic) or ET (expectation)
+    float* sCH = sWt + K * KP;                // [K][KP]  suffix hazards
+    float* sAux = sCH + K * KP;               // expectation: RS [K][KP]; stochastic: Q[K+1] + next-death ring
+    float* sRS = sAux;
+    float* sQ = sAux;                         // Q[u] = sum_{u'>=u} CH[u'][0], Q[K] = 0
+    uint8_t* ndr = reinterpret_cast<uint8_t*>(sAux + ((K + 1 + 3) & ~3));   // [K][PR] next-death pass per pixel
+    float* sI = sAux + (STOCH ? ((K + 1 + 3) & ~3) + (K * PR + 3) / 4 : K * KP);   // [TC]
 
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * TC;
@@ -307,14 +313,20 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
     {   // tables
         const size_t tsz = (size_t)K * KP;
         const float* tb = P.tables + (size_t)b * STED_TABLES * tsz;
-        const float4* w4 = reinterpret_cast<const float4*>(tb + (stochastic ? STED_TAB_E : STED_TAB_ET) * tsz);
+        const float4* w4 = reinterpret_cast<const float4*>(tb + (STOCH ? STED_TAB_E : STED_TAB_ET) * tsz);
         const float4* c4 = reinterpret_cast<const float4*>(tb + STED_TAB_CH * tsz);
         const float4* r4 = reinterpret_cast<const float4*>(tb + STED_TAB_RS * tsz);
         for (int i = tid; i < (int)(tsz / 4); i += S_THREADS) {
             reinterpret_cast<float4*>(sWt)[i] = __ldg(w4 + i);
             reinterpret_cast<float4*>(sCH)[i] = __ldg(c4 + i);
-            reinterpret_cast<float4*>(sRS)[i] = __ldg(r4 + i);
+            if (!STOCH) reinterpret_cast<float4*>(sRS)[i] = __ldg(r4 + i);
         }
+    }
+    __syncthreads();
+    if (STOCH && tid == 0) {
+        float q = 0.f;
+        sQ[K] = 0.f;
+        for (int u = K - 1; u >= 0; --u) { q += sCH[u * KP]; sQ[u] = q; }
     }
     __syncthreads();
 
@@ -323,35 +335,81 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
     const int xs = (c0 == 0) ? 0 : c0 + p;
     const int xe = (c0 + TC >= W) ? P.Wpitch : c0 + TC + p;
 
-    // load band row y into its ring slot; in expectation mode scale by exp(CH[u_entry][hi+1])
-    auto load_row = [&](const int y, const int u_entry) {
-        float* dst = ring + (y % K) * PR;
+    // per-molecule hazard of one whole pass of tap row u over pixel column x
+    auto pass_hazard = [&](const int u, const int lo, const int hi) -> float {
+        return sCH[u * KP + lo] - sCH[u * KP + hi + 1];
+    };
+    // Pass (<= u_from) in which a per-molecule hazard budget `tau`, counted from the START of pass u_from,
+    // runs out; 255 when it outlasts the remaining passes.
+    auto find_pass = [&](const int u_from, const float tau, const int lo, const int hi) -> int {
+        if (u_from < 0) return 255;
+        if (lo == 0 && hi == K - 1) {
+            const float thr = tau + sQ[u_from + 1];
+            if (sQ[0] < thr) return 255;
+            int a = 0, z = u_from;                      // largest u in [0,u_from] with Q[u] >= thr
+            while (a < z) {
+                const int mid = (a + z + 1) >> 1;
+                if (sQ[mid] >= thr) a = mid; else z = mid - 1;
+            }
+            return a;
+        }
+        float cum = 0.f;
+        for (int u = u_from; u >= 0; --u) {
+            cum += pass_hazard(u, lo, hi);
+            if (cum >= tau) return u;
+        }
+        return 255;
+    };
+
+    // Band row y replaces the retired row in its ring slot.  The thread that owns a group of four
+    // columns first writes the old values back (store), then loads the new ones, so no barrier is needed
+    // in between.  Expectation mode keeps s = D*exp(CH[u][hi+1]) for the left-clipped columns.
+    auto cycle_row = [&](const int y_old, const int u_scale_old, const int y_new, const int u_entry) {
         for (int i = tid; i < PR / 4; i += S_THREADS) {
             const int xl = 4 * i, x = c0 + xl;
-            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y < P.Hp && x < P.Wpitch) val = __ldg(reinterpret_cast<const float4*>(din + (size_t)y * P.Wpitch + x));
-            if (!stochastic && x < K - 1) {
-                float* pv = reinterpret_cast<float*>(&val);
+            if (y_old >= 0) {
+                const float4 old = *reinterpret_cast<const float4*>(ring + (y_old % K) * PR + xl);
+                const float* po_ = reinterpret_cast<const float*>(&old);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int xx = x + j;
-                    if (xx < K - 1 && pv[j] != 0.f) pv[j] *= expf(sCH[u_entry * KP + xx + 1]);
+                    if (xx >= xs && xx < xe) {
+                        float val = po_[j];
+                        if (!STOCH && u_scale_old >= 0 && xx < K - 1 && val != 0.f)
+                            val *= expf(-sCH[u_scale_old * KP + xx + 1]);
+                        dout[(size_t)y_old * P.Wpitch + xx] = val;
+                    }
                 }
             }
-            *reinterpret_cast<float4*>(dst + xl) = val;
-        }
-    };
-    // write band row y back (u_scale >= 0: undo the expectation-mode scaling with that tap row)
-    auto store_row = [&](const int y, const int u_scale) {
-        const float* src = ring + (y % K) * PR;
-        for (int x = xs + tid; x < xe; x += S_THREADS) {
-            float val = src[x - c0];
-            if (!stochastic && u_scale >= 0 && x < K - 1 && val != 0.f) val *= expf(-sCH[u_scale * KP + x + 1]);
-            dout[(size_t)y * P.Wpitch + x] = val;
+            if (y_new >= 0) {
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (y_new < P.Hp && x < P.Wpitch)
+                    val = __ldg(reinterpret_cast<const float4*>(din + (size_t)y_new * P.Wpitch + x));
+                float* pv = reinterpret_cast<float*>(&val);
+                uint32_t nd4 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = x + j;
+                    if (pv[j] == 0.f || xx >= Wp) continue;
+                    if (!STOCH) {
+                        if (xx < K - 1) pv[j] *= expf(sCH[u_entry * KP + xx + 1]);
+                    } else {
+                        // first death among n molecules: hazard budget Exp(1)/n from the start of pass u_entry
+                        const int lo = max(0, xx - W + 1), hi = min(K - 1, xx);
+                        PhiloxStream rng;
+                        rng.init(P.seed, P.offset, env, (uint32_t)(y_new * Wp + xx), STED_RNG_BLEACH, 0xFFFFu);
+                        const float tau = -__logf(rng.uniform()) / pv[j];
+                        const int nd = find_pass(u_entry, tau, lo, hi);
+                        nd4 = (nd4 & ~(0xFFu << (8 * j))) | ((uint32_t)nd << (8 * j));
+                    }
+                }
+                *reinterpret_cast<float4*>(ring + (y_new % K) * PR + xl) = val;
+                if (STOCH) *reinterpret_cast<uint32_t*>(ndr + (y_new % K) * PR + xl) = nd4;
+            }
         }
     };
 
-    for (int y = 0; y < K; ++y) load_row(y, y);
+    for (int y = 0; y < K; ++y) cycle_row(-1, -1, y, y);
     __syncthreads();
 
     const float dwell = (float)P.pdt[b];
@@ -390,51 +448,74 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
                 }
             }
             const float tot = reduce_scatter<CT>(acc, lane);
-            constexpr int SH = (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
+            constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
             if ((lane & ((1 << SH) - 1)) == 0) sI[CT * warp + (lane >> SH)] = tot;
         }
         __syncthreads();
 
         // ---------------- phase S: thin the band with the taps of this scan row
-        for (int u = warp; u < K; u += S_THREADS / 32) {
-            float* row = ring + ((r + u) % K) * PR;
-            const float* ch = sCH + u * KP;
-            const int y = r + u;
-            for (int xl = lane; xl < span; xl += 32) {
-                const float n = row[xl];
-                if (n == 0.f) continue;
-                const int x = c0 + xl;
-                if (x >= Wp) continue;
-                const int lo = max(0, x - W + 1), hi = min(K - 1, x);
-                if (!stochastic) {
+        if (!STOCH) {
+            for (int u = warp; u < K; u += S_THREADS / 32) {
+                float* row = ring + ((r + u) % K) * PR;
+                for (int xl = lane; xl < span; xl += 32) {
+                    const float n = row[xl];
+                    if (n == 0.f) continue;
+                    const int x = c0 + xl;
+                    if (x >= Wp) continue;
+                    const int lo = max(0, x - W + 1), hi = min(K - 1, x);
                     float m;
                     if (hi == K - 1) m = sRS[u * KP + lo];
-                    else m = expf((u > 0 ? sCH[(u - 1) * KP + hi + 1] : 0.f) - ch[lo]);
+                    else m = expf((u > 0 ? sCH[(u - 1) * KP + hi + 1] : 0.f) - sCH[u * KP + lo]);
                     row[xl] = n * m;
-                    continue;
                 }
-                const float chhi = ch[hi + 1];
-                const float hz = ch[lo] - chhi;
-                PhiloxStream rng;
-                rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, (uint32_t)r);
-                const int dead = binomial_deaths((int)n, hz, rng);
-                if (dead == 0) continue;
-                row[xl] = n - (float)dead;
-                // place each death on the tap where its cumulative in-row hazard is reached
-                const float pd = -expm1f(-hz);
-                for (int d = 0; d < dead; ++d) {
-                    const float t = -log1pf(-rng.uniform() * pd);       // in (0, hz)
-                    const float thr = t + chhi;
-                    int a = lo, z = hi;                                  // largest v in [lo,hi] with ch[v] >= thr
-                    while (a < z) {
-                        const int mid = (a + z + 1) >> 1;
-                        if (ch[mid] >= thr) a = mid; else z = mid - 1;
-                    }
-                    // dwells after the death (taps lo .. a-1) no longer see this molecule
-                    const float* e = sWt + u * KP;
-                    for (int v = lo; v < a; ++v) {
-                        const int cl = x - v - c0;
-                        if (cl >= 0 && cl < TC) atomicAdd(&sI[cl], -e[v]);
+            }
+        } else {
+            // only pixels whose scheduled next death falls in this pass do any work
+            for (int u = warp; u < K; u += S_THREADS / 32) {
+                const int slot = (r + u) % K;
+                const uint32_t* nrow = reinterpret_cast<const uint32_t*>(ndr + slot * PR);
+                const uint32_t pat = 0x01010101u * (uint32_t)u;
+                for (int g4 = lane; g4 < PR / 4; g4 += 32) {
+                    const uint32_t diff = nrow[g4] ^ pat;
+                    // any zero byte?  (classic haszero test)
+                    if (((diff - 0x01010101u) & ~diff & 0x80808080u) == 0u) continue;
+#pragma unroll 1
+                    for (int j = 0; j < 4; ++j) {
+                        if (((diff >> (8 * j)) & 0xFFu) != 0u) continue;
+                        const int xl = 4 * g4 + j, x = c0 + xl, y = r + u;
+                        const int lo = max(0, x - W + 1), hi = min(K - 1, x);
+                        const float* ch = sCH + u * KP;
+                        const float chhi = ch[hi + 1];
+                        const float hzp = ch[lo] - chhi;
+                        float n = ring[slot * PR + xl];
+                        PhiloxStream rng;
+                        rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, (uint32_t)r);
+                        // a death is known to fall in this pass: truncated Exp(n) on (0, hzp)
+                        float pos = -log1pf(-rng.uniform() * (-expm1f(-n * hzp))) / n;
+                        int nd = 255;
+                        while (true) {
+                            pos = fminf(pos, hzp);
+                            const float thr = pos + chhi;
+                            int a = lo, z = hi;                      // largest v in [lo,hi] with ch[v] >= thr
+                            while (a < z) {
+                                const int mid = (a + z + 1) >> 1;
+                                if (ch[mid] >= thr) a = mid; else z = mid - 1;
+                            }
+                            // dwells after the death (taps lo .. a-1) no longer see this molecule
+                            const float* e = sWt + u * KP;
+                            for (int v = lo; v < a; ++v) {
+                                const int cl = x - v - c0;
+                                if (cl >= 0 && cl < TC) atomicAdd(&sI[cl], -e[v]);
+                            }
+                            n -= 1.f;
+                            if (n <= 0.f) break;
+                            const float tau = -__logf(rng.uniform()) / n;
+                            if (tau < hzp - pos) { pos += tau; continue; }      // another death in this pass
+                            nd = find_pass(u - 1, tau - (hzp - pos), lo, hi);
+                            break;
+                        }
+                        ring[slot * PR + xl] = n;
+                        ndr[slot * PR + xl] = (uint8_t)nd;
                     }
                 }
             }
@@ -448,13 +529,11 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
             if (P.intensity) P.intensity[o] = I;
             P.signal[o] = detect(P, I, gain, bg_mean, env, (uint32_t)(r * W + c0 + tid));
         }
-        store_row(r, -1);
-        __syncthreads();
-        if (r + K < P.Hp) load_row(r + K, K - 1);
+        cycle_row(r, -1, (r + K < P.Hp) ? r + K : -1, K - 1);
         __syncthreads();
     }
     // flush the K-1 band rows below the last scan row (tap row they would have had next: y - H)
-    for (int y = H; y < P.Hp; ++y) store_row(y, y - H);
+    for (int y = H; y < P.Hp; ++y) cycle_row(y, y - H, -1, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -548,22 +627,31 @@ int launch_gather(const AcqParams& P, cudaStream_t st) {
     return STED_OK;
 }
 
-template <int KT, int CT>
+template <int KT, int CT, bool STOCH>
 int launch_sweep_t(const AcqParams& P, cudaStream_t st) {
     constexpr int TC = 8 * CT;
-    const size_t smem = ((size_t)P.K * sweep_pitch(TC, P.KP) + 3 * (size_t)P.K * P.KP + TC) * sizeof(float);
+    const int PR = sweep_pitch(TC, P.KP);
+    size_t words = (size_t)P.K * PR + 2 * (size_t)P.K * P.KP + TC;
+    if (STOCH) words += ((P.K + 1 + 3) & ~3) + ((size_t)P.K * PR + 3) / 4;
+    else words += (size_t)P.K * P.KP;
+    const size_t smem = words * sizeof(float);
     dim3 grid((P.W + TC - 1) / TC, P.B);
     int rc;
-    if ((rc = set_smem(sweep_kernel<KT, CT>, smem))) return rc;
-    sweep_kernel<KT, CT><<<grid, S_THREADS, smem, st>>>(P);
+    if ((rc = set_smem(sweep_kernel<KT, CT, STOCH>, smem))) return rc;
+    sweep_kernel<KT, CT, STOCH><<<grid, S_THREADS, smem, st>>>(P);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }
 
-int launch_sweep(const AcqParams& P, cudaStream_t st) {
+template <bool STOCH>
+int launch_sweep_m(const AcqParams& P, cudaStream_t st) {
     const bool wide = P.W > 64;
-    if (P.K == 59) return wide ? launch_sweep_t<59, 16>(P, st) : launch_sweep_t<59, 8>(P, st);
-    return wide ? launch_sweep_t<0, 16>(P, st) : launch_sweep_t<0, 8>(P, st);
+    if (P.K == 59) return wide ? launch_sweep_t<59, 16, STOCH>(P, st) : launch_sweep_t<59, 8, STOCH>(P, st);
+    return wide ? launch_sweep_t<0, 16, STOCH>(P, st) : launch_sweep_t<0, 8, STOCH>(P, st);
+}
+
+int launch_sweep(const AcqParams& P, cudaStream_t st) {
+    return (P.flags & STED_SAMPLE_BLEACH) ? launch_sweep_m<true>(P, st) : launch_sweep_m<false>(P, st);
 }
 
 // growable device workspace for the *_host entry points

@@ -71,3 +71,71 @@ def sweep_stochastic(D, H, W, E, A, rng):
                         row[c] -= E[u, v]
         out[r] = row
     return out, D
+
+
+def sweep_stochastic_scheduled(D, H, W, E, A, rng):
+    """Twin of sweep_kernel<STOCH=true>: instead of one binomial per (pixel, pass), every pixel carries
+    the pass of its next death.  The first death among n molecules needs a per-molecule hazard budget
+    Exp(1)/n; by memorylessness the budget is re-drawn (truncated to the pass) when the pass arrives."""
+    K = E.shape[0]
+    _, CH = tables(E, A)
+    D = D.astype(np.int64).copy()
+    Hp, Wp = D.shape
+    out = np.zeros((H, W))
+    nd = np.full((Hp, Wp), 255, dtype=np.int64)
+
+    def clip(x):
+        return max(0, x - W + 1), min(K - 1, x)
+
+    def hz(u, lo, hi):
+        return CH[u, lo] - CH[u, hi + 1]
+
+    def find_pass(u_from, tau, lo, hi):
+        cum = 0.0
+        for u in range(u_from, -1, -1):
+            cum += hz(u, lo, hi)
+            if cum >= tau:
+                return u
+        return 255
+
+    def enter(y, u_entry):
+        for x in range(Wp):
+            if D[y, x] > 0:
+                lo, hi = clip(x)
+                nd[y, x] = find_pass(u_entry, rng.exponential() / D[y, x], lo, hi)
+
+    for y in range(K):
+        enter(y, y)
+    for r in range(H):
+        band = D[r:r + K]
+        row = np.array([(E * band[:, c:c + K]).sum() for c in range(W)])
+        for u in range(K):
+            y = r + u
+            for x in np.nonzero(nd[y] == u)[0]:
+                lo, hi = clip(x)
+                hzp = hz(u, lo, hi)
+                n = D[y, x]
+                pos = -np.log1p(-rng.random() * -np.expm1(-n * hzp)) / n
+                nxt = 255
+                while True:
+                    cand = np.nonzero(CH[u, lo:hi + 1] >= pos + CH[u, hi + 1])[0]
+                    a = lo + (cand.max() if len(cand) else 0)
+                    for v in range(lo, a):
+                        c = x - v
+                        if 0 <= c < W:
+                            row[c] -= E[u, v]
+                    n -= 1
+                    if n == 0:
+                        break
+                    tau = rng.exponential() / n
+                    if tau < hzp - pos:
+                        pos += tau
+                        continue
+                    nxt = find_pass(u - 1, tau - (hzp - pos), lo, hi)
+                    break
+                D[y, x] = n
+                nd[y, x] = nxt
+        out[r] = row
+        if r + K < Hp:
+            enter(r + K, K - 1)
+    return out, D

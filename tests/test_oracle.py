@@ -115,15 +115,17 @@ def test_rowsweep_expectation_equals_sequential_scan(H, W, K):
     np.testing.assert_allclose(Db, ref_D, rtol=1e-12, atol=1e-13)
 
 
-def test_rowsweep_stochastic_matches_sequential_moments():
-    """One binomial per (pixel, scan row) + hazard-inverted death taps has the same image / datamap
-    moments as the reference's per-dwell per-molecule thinning."""
+@pytest.mark.parametrize("variant", ["binomial_per_pass", "scheduled_deaths"])
+def test_rowsweep_stochastic_matches_sequential_moments(variant):
+    """Both row-sweep samplers — one binomial per (pixel, scan row), and the next-death schedule the CUDA
+    kernel uses — have the same image / datamap moments as the reference's per-dwell per-molecule thinning."""
     rng = np.random.default_rng(7)
     H, W, K = 6, 7, 5
     E, A = rng.random((K, K)), rng.random((K, K)) * 0.2
     p = K // 2
     D = np.zeros((H + K - 1, W + K - 1))
     D[p:p + H, p:p + W] = rng.integers(0, 30, (H, W)) * (rng.random((H, W)) < 0.6)
+    fn = rm.sweep_stochastic if variant == "binomial_per_pass" else rm.sweep_stochastic_scheduled
     N = 1500
     a = np.zeros((N, H, W)); b = np.zeros((N, H, W))
     da = np.zeros((N,) + D.shape); db = np.zeros((N,) + D.shape)
@@ -131,7 +133,7 @@ def test_rowsweep_stochastic_matches_sequential_moments():
         d1 = D.copy()
         a[i] = po.raster(d1, H, W, E, np.exp(-A), 2, seed=i + 1)
         da[i] = d1
-        b[i], db[i] = rm.sweep_stochastic(D, H, W, E, A, rng)
+        b[i], db[i] = fn(D, H, W, E, A, rng)
     # mean field is exact for both
     exp_D = D.copy()
     exp_I = po.raster(exp_D, H, W, E, np.exp(-A), 1)
@@ -141,6 +143,10 @@ def test_rowsweep_stochastic_matches_sequential_moments():
     sa, sb = a.std(0), b.std(0)
     np.testing.assert_allclose(sb, sa, rtol=0.12, atol=1e-6 * sa.max())
     np.testing.assert_allclose(db.std(0), da.std(0), atol=0.25)
+    # image / datamap covariance (the thinning trajectory couples them)
+    ca = ((a[:, 3, 3] - a[:, 3, 3].mean()) * (da.sum((1, 2)) - da.sum((1, 2)).mean())).mean()
+    cb = ((b[:, 3, 3] - b[:, 3, 3].mean()) * (db.sum((1, 2)) - db.sum((1, 2)).mean())).mean()
+    assert cb == pytest.approx(ca, rel=0.25)
 
 
 def test_oracle_microscope_mutates_datamap_like_pysted():
