@@ -132,6 +132,9 @@ __device__ __forceinline__ int binomial_deaths(int n, float hz, PhiloxStream& rn
 // Poisson(lam): inversion below 12, PTRS (Hörmann 1993, the algorithm numpy's legacy
 // RandomState.poisson uses) above.  Restates Detector.get_signal's numpy.random.poisson draws.
 // ---------------------------------------------------------------------------------------------
+static __constant__ float STED_LOGFACT[10] = {0.f, 0.f, 0.6931471806f, 1.7917594692f, 3.1780538303f, 4.7874917428f,
+                                              6.5792512120f, 8.5251613611f, 10.6046029027f, 12.8018274801f};
+
 __device__ __forceinline__ float poisson_sample(float lam, PhiloxStream& rng) {
     if (!(lam > 0.0f)) return 0.0f;
     if (lam < 12.0f) {
@@ -161,9 +164,20 @@ __device__ __forceinline__ float poisson_sample(float lam, PhiloxStream& rng) {
         float kf = floorf((2.0f * a / us + b) * U + lam + 0.43f);
         if (us >= 0.07f && V <= vr) return kf;
         if (kf < 0.0f || (us < 0.013f && V > us)) continue;
-        // rare path: evaluate the acceptance bound in double (k*log(lam) ~ 1e5 for bright pixels)
-        double lhs = log((double)V) + log((double)invalpha) - log((double)a / ((double)us * us) + (double)b);
-        double rhs = -(double)lam + (double)kf * log((double)lam) - lgamma((double)kf + 1.0);
+        // acceptance bound log(V*invalpha/(a/us^2+b)) <= -lam + k*log(lam) - lgamma(k+1), all in float:
+        // for k >= 10 the right side is rewritten with Stirling's series around k = lam + delta,
+        //   -lam*((1+x)*log1p(x) - x) - 0.5*log(2*pi*k) - 1/(12k) + 1/(360k^3),  x = delta/lam,
+        // which has no large cancelling terms (absolute error ~1e-4 at lam = 1e6).
+        const float lhs = __logf(V * invalpha / (a / (us * us) + b));
+        float rhs;
+        if (kf < 10.0f) {
+            rhs = -lam + kf * logf(lam) - STED_LOGFACT[(int)kf];
+        } else {
+            const float x = (kf - lam) / lam;
+            const float g = (1.0f + x) * log1pf(x) - x;
+            const float ik = 1.0f / kf;
+            rhs = -lam * g - 0.5f * logf(6.2831853072f * kf) - ik * (0.0833333333f - 0.0027777778f * ik * ik);
+        }
         if (lhs <= rhs) return kf;
     }
     return floorf(lam + 0.5f);

@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gather_kernel(const AcqParams P)
 // l and l+32; partial sums meet through a shuffle reduce-scatter.
 // ------------------------------------------------------------------------------------------
 constexpr int S_THREADS = 256;
+constexpr int S_EVCAP = 2048, S_JOBCAP = 2048;   // per scan row and tile; overflow falls back to inline work
 
 __host__ __device__ inline int sweep_pitch(int TC, int KP) {
     int p = TC + KP;
@@ -300,7 +301,12 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
     float* sRS = sAux;
     float* sQ = sAux;                         // Q[u] = sum_{u'>=u} CH[u'][0], Q[K] = 0
     uint8_t* ndr = reinterpret_cast<uint8_t*>(sAux + ((K + 1 + 3) & ~3));   // [K][PR] next-death pass per pixel
-    float* sI = sAux + (STOCH ? ((K + 1 + 3) & ~3) + (K * PR + 3) / 4 : K * KP);   // [TC]
+    float* sI = sAux + (STOCH ? ((K + 1 + 3) & ~3) + (K * PR + 3) / 4 : K * KP);   // [TC] dense row intensities
+    float* sScale = sI + TC;                  // [TC] 2^30 / sI  (fixed-point scale of the corrections)
+    int* sCorr = reinterpret_cast<int*>(sScale + TC);        // [TC] sum of removed taps, fixed point
+    int* sCnt = sCorr + TC;                   // [4]  job / event counters
+    uint32_t* evq = reinterpret_cast<uint32_t*>(sCnt + 4);   // [S_EVCAP] death events  xl | u<<8 | a<<14 | lo<<20
+    uint16_t* jobq = reinterpret_cast<uint16_t*>(evq + S_EVCAP);   // [S_JOBCAP] pixel passes xl | u<<8
 
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * TC;
@@ -409,6 +415,54 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         }
     };
 
+    // One pixel whose scheduled death falls in pass u of scan row r: draw where in the pass each death
+    // happens (and whether more follow), emit an event per death, re-schedule the survivors.
+    auto process_job = [&](const int r, const int xl, const int u) {
+        const int slot = (r + u) % K;
+        const int x = c0 + xl, y = r + u;
+        const int lo = max(0, x - W + 1), hi = min(K - 1, x);
+        const float* ch = sCH + u * KP;
+        const float chhi = ch[hi + 1];
+        const float hzp = ch[lo] - chhi;
+        float n = ring[slot * PR + xl];
+        PhiloxStream rng;
+        rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, (uint32_t)r);
+        // a death is known to fall in this pass: truncated Exp(n) on (0, hzp)
+        float pos = -log1pf(-rng.uniform() * (-expm1f(-n * hzp))) / n;
+        int nd = 255;
+        while (true) {
+            pos = fminf(pos, hzp);
+            const float thr = pos + chhi;
+            int a = lo, z = hi;                          // largest v in [lo,hi] with ch[v] >= thr
+            while (a < z) {
+                const int mid = (a + z + 1) >> 1;
+                if (ch[mid] >= thr) a = mid; else z = mid - 1;
+            }
+            if (a > lo) {                                // dwells at taps lo .. a-1 no longer see this molecule
+                const int q = atomicAdd(&sCnt[1], 1);
+                if (q < S_EVCAP) {
+                    evq[q] = (uint32_t)xl | ((uint32_t)u << 8) | ((uint32_t)a << 14) | ((uint32_t)lo << 20);
+                } else {
+                    const float* e = sWt + u * KP;
+                    for (int v = lo; v < a; ++v) {
+                        const int cl = xl - v;
+                        if (cl >= 0 && cl < TC) atomicAdd(&sCorr[cl], __float2int_rn(e[v] * sScale[cl]));
+                    }
+                }
+            }
+            n -= 1.f;
+            if (n <= 0.f) break;
+            const float tau = -__logf(rng.uniform()) / n;
+            if (tau < hzp - pos) { pos += tau; continue; }       // another death in this pass
+            nd = find_pass(u - 1, tau - (hzp - pos), lo, hi);
+            break;
+        }
+        ring[slot * PR + xl] = n;
+        ndr[slot * PR + xl] = (uint8_t)nd;
+    };
+
+    if (STOCH && tid < TC) sCorr[tid] = 0;
+    if (STOCH && tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
     for (int y = 0; y < K; ++y) cycle_row(-1, -1, y, y);
     __syncthreads();
 
@@ -449,7 +503,10 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
             }
             const float tot = reduce_scatter<CT>(acc, lane);
             constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
-            if ((lane & ((1 << SH) - 1)) == 0) sI[CT * warp + (lane >> SH)] = tot;
+            if ((lane & ((1 << SH) - 1)) == 0) {
+                sI[CT * warp + (lane >> SH)] = tot;
+                if (STOCH) sScale[CT * warp + (lane >> SH)] = 1073741824.0f / fmaxf(tot, 1e-30f);
+            }
         }
         __syncthreads();
 
@@ -470,52 +527,40 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
                 }
             }
         } else {
-            // only pixels whose scheduled next death falls in this pass do any work
+            // (S1) scan the next-death ring: pixels whose scheduled death falls in this pass become jobs
             for (int u = warp; u < K; u += S_THREADS / 32) {
                 const int slot = (r + u) % K;
                 const uint32_t* nrow = reinterpret_cast<const uint32_t*>(ndr + slot * PR);
                 const uint32_t pat = 0x01010101u * (uint32_t)u;
                 for (int g4 = lane; g4 < PR / 4; g4 += 32) {
                     const uint32_t diff = nrow[g4] ^ pat;
-                    // any zero byte?  (classic haszero test)
-                    if (((diff - 0x01010101u) & ~diff & 0x80808080u) == 0u) continue;
+                    if (((diff - 0x01010101u) & ~diff & 0x80808080u) == 0u) continue;   // no byte equals u
 #pragma unroll 1
                     for (int j = 0; j < 4; ++j) {
                         if (((diff >> (8 * j)) & 0xFFu) != 0u) continue;
-                        const int xl = 4 * g4 + j, x = c0 + xl, y = r + u;
-                        const int lo = max(0, x - W + 1), hi = min(K - 1, x);
-                        const float* ch = sCH + u * KP;
-                        const float chhi = ch[hi + 1];
-                        const float hzp = ch[lo] - chhi;
-                        float n = ring[slot * PR + xl];
-                        PhiloxStream rng;
-                        rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, (uint32_t)r);
-                        // a death is known to fall in this pass: truncated Exp(n) on (0, hzp)
-                        float pos = -log1pf(-rng.uniform() * (-expm1f(-n * hzp))) / n;
-                        int nd = 255;
-                        while (true) {
-                            pos = fminf(pos, hzp);
-                            const float thr = pos + chhi;
-                            int a = lo, z = hi;                      // largest v in [lo,hi] with ch[v] >= thr
-                            while (a < z) {
-                                const int mid = (a + z + 1) >> 1;
-                                if (ch[mid] >= thr) a = mid; else z = mid - 1;
-                            }
-                            // dwells after the death (taps lo .. a-1) no longer see this molecule
-                            const float* e = sWt + u * KP;
-                            for (int v = lo; v < a; ++v) {
-                                const int cl = x - v - c0;
-                                if (cl >= 0 && cl < TC) atomicAdd(&sI[cl], -e[v]);
-                            }
-                            n -= 1.f;
-                            if (n <= 0.f) break;
-                            const float tau = -__logf(rng.uniform()) / n;
-                            if (tau < hzp - pos) { pos += tau; continue; }      // another death in this pass
-                            nd = find_pass(u - 1, tau - (hzp - pos), lo, hi);
-                            break;
-                        }
-                        ring[slot * PR + xl] = n;
-                        ndr[slot * PR + xl] = (uint8_t)nd;
+                        const int q = atomicAdd(&sCnt[0], 1);
+                        if (q < S_JOBCAP) jobq[q] = (uint16_t)((4 * g4 + j) | (u << 8));
+                        else process_job(r, 4 * g4 + j, u);
+                    }
+                }
+            }
+            __syncthreads();
+            // (S2) one job per thread: draw the deaths of that pixel in this pass, emit one event per death
+            {
+                const int njobs = min(sCnt[0], S_JOBCAP);
+                for (int q = tid; q < njobs; q += S_THREADS) process_job(r, jobq[q] & 0xFF, jobq[q] >> 8);
+            }
+            __syncthreads();
+            // (S3) a warp per event: the taps after the death leave the row's intensities
+            {
+                const int nev = min(sCnt[1], S_EVCAP);
+                for (int q = warp; q < nev; q += S_THREADS / 32) {
+                    const uint32_t ev = evq[q];
+                    const int xl = ev & 0xFF, u = (ev >> 8) & 0x3F, a = (ev >> 14) & 0x3F, lo = (ev >> 20) & 0x3F;
+                    const float* e = sWt + u * KP;
+                    for (int v = lo + lane; v < a; v += 32) {
+                        const int cl = xl - v;
+                        if (cl >= 0 && cl < TC) atomicAdd(&sCorr[cl], __float2int_rn(e[v] * sScale[cl]));
                     }
                 }
             }
@@ -523,8 +568,13 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         __syncthreads();
 
         // ---------------- phase O: detector, retire band row y = r, bring in row r + K
+        if (STOCH && tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
         if (tid < TC && c0 + tid < W) {
-            const float I = fmaxf(sI[tid], 0.f);
+            float I = sI[tid];
+            if (STOCH) {
+                I = fmaxf(I * (1.0f - (float)sCorr[tid] * 9.313225746154785e-10f), 0.f);
+                sCorr[tid] = 0;
+            }
             const size_t o = ((size_t)b * H + r) * W + c0 + tid;
             if (P.intensity) P.intensity[o] = I;
             P.signal[o] = detect(P, I, gain, bg_mean, env, (uint32_t)(r * W + c0 + tid));
@@ -632,7 +682,7 @@ int launch_sweep_t(const AcqParams& P, cudaStream_t st) {
     constexpr int TC = 8 * CT;
     const int PR = sweep_pitch(TC, P.KP);
     size_t words = (size_t)P.K * PR + 2 * (size_t)P.K * P.KP + TC;
-    if (STOCH) words += ((P.K + 1 + 3) & ~3) + ((size_t)P.K * PR + 3) / 4;
+    if (STOCH) words += ((P.K + 1 + 3) & ~3) + ((size_t)P.K * PR + 3) / 4 + 2 * TC + 4 + S_EVCAP + S_JOBCAP / 2;
     else words += (size_t)P.K * P.KP;
     const size_t smem = words * sizeof(float);
     dim3 grid((P.W + TC - 1) / TC, P.B);
