@@ -214,24 +214,26 @@ def run_ours(args, rank, local_rank, world):
         if timed:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         bm.make_effective(conf[1], conf[2], conf[0])
-        if ev: ev[0].record()
-        _gather_only(bm, conf[0], sig[0])
-        if ev: ev[1].record(); kern_ev.append(ev)
+        _gather_only(bm, conf[0], sig[0], ev)
         bm.get_signal_and_bleach(a[:, 2].contiguous(), a[:, 1].contiguous(), a[:, 0].contiguous(), bleach=True,
                                  out_signal=sig[1])
         bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[2])
         bm.set_datamaps(pool_dev[1])
         bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
-        launches[0] += 8
+        launches[0] += 12     # per acquisition: make_effective, gather|sweep, detect
 
-    def _gather_only(bm, pdt, out):
+    def _gather_only(bm, pdt, out, ev):
         import ctypes
         bm.offset += 1
+        st = torch.cuda.current_stream(dev).cuda_stream
         flags = _lib.STED_SAMPLE_PHOTONS
+        if ev: ev[0].record()
         _lib.check(bm.lib.sted_acquire(bm.dmap.data_ptr(), None, bm.tables.data_ptr(), pdt.data_ptr(), bm.B, bm.H,
-                                       bm.W, bm.K, flags, ctypes.byref(bm.det), bm.lambda_fluo, bm.seed, bm.offset,
-                                       bm.env_base, None, out.data_ptr(),
-                                       torch.cuda.current_stream(dev).cuda_stream))
+                                       bm.W, bm.K, flags | _lib.STED_NO_DETECT, ctypes.byref(bm.det), bm.lambda_fluo,
+                                       bm.seed, bm.offset, bm.env_base, None, out.data_ptr(), st))
+        if ev: ev[1].record(); kern_ev.append(ev)
+        _lib.check(bm.lib.sted_detect(out.data_ptr(), pdt.data_ptr(), bm.B, bm.H, bm.W, flags, ctypes.byref(bm.det),
+                                      bm.lambda_fluo, bm.seed, bm.offset, bm.env_base, st))
 
     def sync_all():
         torch.cuda.synchronize(dev)

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsted_b200.so")
 
-STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH = 1, 2, 4
+STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH, STED_NO_DETECT = 1, 2, 4, 8
 STED_TAB_E, STED_TAB_ET, STED_TAB_CH, STED_TAB_RS, STED_TABLES = 0, 1, 2, 3, 4
 STED_MAX_K = 63
 
@@ -48,6 +48,7 @@ SIGNATURES = {
     "sted_make_effective": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sted_acquire": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _u32, ctypes.POINTER(StedDetectorParams), _d, _u64,
                           _u64, _i64, _vp, _vp, _vp]),
+    "sted_detect": (_i, [_vp, _vp, _i, _i, _i, _u32, ctypes.POINTER(StedDetectorParams), _d, _u64, _u64, _i64, _vp]),
     "sted_acquire_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _u32,
                                ctypes.POINTER(StedDetectorParams), _u64, _u64, _i64, _vp, _vp]),
     "sted_sample_poisson": (_i, [_vp, _i64, _u64, _u64, _vp, _vp]),

@@ -52,6 +52,7 @@ STED_HD Philox4 philox4x32_10(Philox4 c, uint32_t k0, uint32_t k1) {
 #define STED_RNG_PHOTON 1u
 #define STED_RNG_BLEACH 2u
 #define STED_RNG_TEST   3u
+#define STED_RNG_BLEACH2 4u
 
 // Stream of 32-bit words for one (pixel, env, purpose, row) site; refills by bumping a sub-counter.
 struct PhiloxStream {

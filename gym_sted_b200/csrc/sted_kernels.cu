@@ -221,17 +221,27 @@ __global__ void __launch_bounds__(G_THREADS, 3) gather_kernel(const AcqParams P)
     for (int i = 0; i < G_RT; ++i)
         *reinterpret_cast<float4*>(sOut + (r0 + i) * G_TW + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     __syncthreads();
-    const float dwell = (float)P.pdt[b];
-    const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
-    const uint32_t env = P.env_base + (uint32_t)b;
-#pragma unroll 1
+    // detected power goes to `signal`; detect_kernel turns it into photon counts in place
     for (int idx = tid; idx < G_TH * G_TW; idx += G_THREADS) {
         const int r = tr0 + (idx / G_TW), c = tc0 + (idx % G_TW);
         if (r >= P.H || c >= P.W) continue;
         const float I = sOut[idx];
         const size_t o = ((size_t)b * P.H + r) * P.W + c;
         if (P.intensity) P.intensity[o] = I;
-        P.signal[o] = detect(P, I, gain, bg_mean, env, (uint32_t)(r * P.W + c));
+        P.signal[o] = I;
+    }
+}
+
+// Detector.get_signal for every pixel of the batch, in place on `signal` (power -> photon counts).
+// A separate, light kernel: the Poisson sampler is latency bound and runs at full occupancy here
+// instead of at the 12 warps/SM of the gather kernel.
+__global__ void __launch_bounds__(256) detect_kernel(const AcqParams P) {
+    const size_t hw = (size_t)P.H * P.W, n = hw * P.B;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(o / hw);
+        const float dwell = (float)P.pdt[b];
+        P.signal[o] = detect(P, P.signal[o], P.det_eff * dwell, P.background * dwell, P.env_base + (uint32_t)b,
+                             (uint32_t)(o - (size_t)b * hw));
     }
 }
 
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gather_kernel(const AcqParams P)
 // l and l+32; partial sums meet through a shuffle reduce-scatter.
 // ------------------------------------------------------------------------------------------
 constexpr int S_THREADS = 256;
-constexpr int S_EVCAP = 2048, S_JOBCAP = 2048;   // per scan row and tile; overflow falls back to inline work
+constexpr int S_EVCAP = 3072, S_JOBCAP = 1536;   // per scan row and tile; overflow falls back to inline work
 
 __host__ __device__ inline int sweep_pitch(int TC, int KP) {
     int p = TC + KP;
@@ -305,8 +315,9 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
     float* sScale = sI + TC;                  // [TC] 2^30 / sI  (fixed-point scale of the corrections)
     int* sCorr = reinterpret_cast<int*>(sScale + TC);        // [TC] sum of removed taps, fixed point
     int* sCnt = sCorr + TC;                   // [4]  job / event counters
-    uint32_t* evq = reinterpret_cast<uint32_t*>(sCnt + 4);   // [S_EVCAP] death events  xl | u<<8 | a<<14 | lo<<20
-    uint16_t* jobq = reinterpret_cast<uint16_t*>(evq + S_EVCAP);   // [S_JOBCAP] pixel passes xl | u<<8
+    uint32_t* evq = reinterpret_cast<uint32_t*>(sCnt + 4);   // [S_EVCAP] death tasks job | idx<<11, then events xl | u<<8 | a<<14
+    float* jobpos = reinterpret_cast<float*>(evq + S_EVCAP);       // [S_JOBCAP] first-death position of the job
+    uint16_t* jobq = reinterpret_cast<uint16_t*>(jobpos + S_JOBCAP);   // [S_JOBCAP] pixel passes xl | u<<8
 
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * TC;
@@ -415,59 +426,65 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         }
     };
 
-    // One pixel whose scheduled death falls in pass u of scan row r: draw where in the pass each death
-    // happens (and whether more follow), emit an event per death, re-schedule the survivors.
-    auto process_job = [&](const int r, const int xl, const int u) {
+    // Tap at which a death at in-pass hazard position `pos` happens: largest v in [lo,hi] whose suffix
+    // hazard still covers pos (the scan visits the taps of a row from hi down to lo).
+    auto tap_of = [&](const float* ch, const float pos, const int lo, const int hi) -> int {
+        const float thr = pos + ch[hi + 1];
+        int a = lo, z = hi;
+        while (a < z) {
+            const int mid = (a + z + 1) >> 1;
+            if (ch[mid] >= thr) a = mid; else z = mid - 1;
+        }
+        return a;
+    };
+    // Position of death number idx > 0 of a pixel-pass whose first death sits at pos1: the other dying
+    // molecules survived up to pos1, then are i.i.d. truncated Exp(1) on the rest of the pass.
+    auto later_death_pos = [&](const uint32_t site, const int r, const int idx, const float pos1, const float hzp) -> float {
+        PhiloxStream rng;
+        rng.init(P.seed, P.offset, env, site, STED_RNG_BLEACH2, (uint32_t)r);
+        rng.ctr.z += (uint32_t)idx;
+        return fminf(pos1 - log1pf(-rng.uniform() * (-expm1f(-(hzp - pos1)))), hzp);
+    };
+    auto remove_taps = [&](const int xl, const int u, const int lo, const int a) {
+        const float* e = sWt + u * KP;                   // dwells at taps lo .. a-1 no longer see the molecule
+        for (int v = lo; v < a; ++v) {
+            const int cl = xl - v;
+            if (cl >= 0 && cl < TC) atomicAdd(&sCorr[cl], __float2int_rn(e[v] * sScale[cl]));
+        }
+    };
+    // One pixel whose scheduled death falls in pass u of scan row r: place the first death (truncated
+    // Exp(n) on the pass), count the further deaths of the pass (binomial over the n-1 others), queue one
+    // task per death and re-schedule the survivors (memoryless: fresh Exp(1)/n_left from the next pass on).
+    auto process_job = [&](const int r, const int jq, const int xl, const int u) {
         const int slot = (r + u) % K;
-        const int x = c0 + xl, y = r + u;
+        const int x = c0 + xl;
         const int lo = max(0, x - W + 1), hi = min(K - 1, x);
         const float* ch = sCH + u * KP;
-        const float chhi = ch[hi + 1];
-        const float hzp = ch[lo] - chhi;
-        float n = ring[slot * PR + xl];
+        const float hzp = ch[lo] - ch[hi + 1];
+        const float n = ring[slot * PR + xl];
+        const uint32_t site = (uint32_t)((r + u) * Wp + x);
         PhiloxStream rng;
-        rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, (uint32_t)r);
-        // a death is known to fall in this pass: truncated Exp(n) on (0, hzp)
-        float pos = -log1pf(-rng.uniform() * (-expm1f(-n * hzp))) / n;
+        rng.init(P.seed, P.offset, env, site, STED_RNG_BLEACH, (uint32_t)r);
+        const float pos1 = fminf(-log1pf(-rng.uniform() * (-expm1f(-n * hzp))) / n, hzp);
+        const int kd = 1 + binomial_deaths((int)n - 1, hzp - pos1, rng);
+        const float left = n - (float)kd;
         int nd = 255;
-        while (true) {
-            pos = fminf(pos, hzp);
-            const float thr = pos + chhi;
-            int a = lo, z = hi;                          // largest v in [lo,hi] with ch[v] >= thr
-            while (a < z) {
-                const int mid = (a + z + 1) >> 1;
-                if (ch[mid] >= thr) a = mid; else z = mid - 1;
-            }
-            if (a > lo) {                                // dwells at taps lo .. a-1 no longer see this molecule
-                const int q = atomicAdd(&sCnt[1], 1);
-                if (q < S_EVCAP) {
-                    evq[q] = (uint32_t)xl | ((uint32_t)u << 8) | ((uint32_t)a << 14) | ((uint32_t)lo << 20);
-                } else {
-                    const float* e = sWt + u * KP;
-                    for (int v = lo; v < a; ++v) {
-                        const int cl = xl - v;
-                        if (cl >= 0 && cl < TC) atomicAdd(&sCorr[cl], __float2int_rn(e[v] * sScale[cl]));
-                    }
-                }
-            }
-            n -= 1.f;
-            if (n <= 0.f) break;
-            const float tau = -__logf(rng.uniform()) / n;
-            if (tau < hzp - pos) { pos += tau; continue; }       // another death in this pass
-            nd = find_pass(u - 1, tau - (hzp - pos), lo, hi);
-            break;
-        }
-        ring[slot * PR + xl] = n;
+        if (left > 0.f) nd = find_pass(u - 1, -__logf(rng.uniform()) / left, lo, hi);
+        ring[slot * PR + xl] = left;
         ndr[slot * PR + xl] = (uint8_t)nd;
+        int q = S_EVCAP;
+        if (jq >= 0) { jobpos[jq] = pos1; q = atomicAdd(&sCnt[1], kd); }
+        for (int i = 0; i < kd; ++i) {
+            const int idx = min(i, 4095);
+            if (q + i < S_EVCAP) evq[q + i] = (uint32_t)jq | ((uint32_t)idx << 11);
+            else remove_taps(xl, u, lo, tap_of(ch, i ? later_death_pos(site, r, idx, pos1, hzp) : pos1, lo, hi));
+        }
     };
 
     if (STOCH && tid < TC) sCorr[tid] = 0;
     if (STOCH && tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
     for (int y = 0; y < K; ++y) cycle_row(-1, -1, y, y);
     __syncthreads();
-
-    const float dwell = (float)P.pdt[b];
-    const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
 
     for (int r = 0; r < H; ++r) {
         // ---------------- phase G: dense gather of scan row r against the row-start state
@@ -540,28 +557,40 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
                         if (((diff >> (8 * j)) & 0xFFu) != 0u) continue;
                         const int q = atomicAdd(&sCnt[0], 1);
                         if (q < S_JOBCAP) jobq[q] = (uint16_t)((4 * g4 + j) | (u << 8));
-                        else process_job(r, 4 * g4 + j, u);
+                        else process_job(r, -1, 4 * g4 + j, u);          // queue full: whole job inline
                     }
                 }
             }
             __syncthreads();
-            // (S2) one job per thread: draw the deaths of that pixel in this pass, emit one event per death
+            // (S2) one job per thread: count the deaths of that pixel-pass, queue a task per death
             {
                 const int njobs = min(sCnt[0], S_JOBCAP);
-                for (int q = tid; q < njobs; q += S_THREADS) process_job(r, jobq[q] & 0xFF, jobq[q] >> 8);
+                for (int q = tid; q < njobs; q += S_THREADS) process_job(r, q, jobq[q] & 0xFF, jobq[q] >> 8);
             }
             __syncthreads();
-            // (S3) a warp per event: the taps after the death leave the row's intensities
-            {
-                const int nev = min(sCnt[1], S_EVCAP);
-                for (int q = warp; q < nev; q += S_THREADS / 32) {
-                    const uint32_t ev = evq[q];
-                    const int xl = ev & 0xFF, u = (ev >> 8) & 0x3F, a = (ev >> 14) & 0x3F, lo = (ev >> 20) & 0x3F;
-                    const float* e = sWt + u * KP;
-                    for (int v = lo + lane; v < a; v += 32) {
-                        const int cl = xl - v;
-                        if (cl >= 0 && cl < TC) atomicAdd(&sCorr[cl], __float2int_rn(e[v] * sScale[cl]));
-                    }
+            // (S3) one task per thread: place the death on its tap; the task slot becomes the event
+            const int nev = min(sCnt[1], S_EVCAP);
+            for (int q = tid; q < nev; q += S_THREADS) {
+                const uint32_t t = evq[q];
+                const int jq = t & 0x7FF, idx = t >> 11;
+                const int xl = jobq[jq] & 0xFF, u = jobq[jq] >> 8;
+                const int x = c0 + xl;
+                const int lo = max(0, x - W + 1), hi = min(K - 1, x);
+                const float* ch = sCH + u * KP;
+                const float pos1 = jobpos[jq];
+                const float pos = idx ? later_death_pos((uint32_t)((r + u) * Wp + x), r, idx, pos1, ch[lo] - ch[hi + 1]) : pos1;
+                evq[q] = (uint32_t)xl | ((uint32_t)u << 8) | ((uint32_t)tap_of(ch, pos, lo, hi) << 14);
+            }
+            __syncthreads();
+            // (S4) a warp per event: the taps after the death leave the row's intensities
+            for (int q = warp; q < nev; q += S_THREADS / 32) {
+                const uint32_t ev = evq[q];
+                const int xl = ev & 0xFF, u = (ev >> 8) & 0x3F, a = (ev >> 14) & 0x3F;
+                const int lo = max(0, c0 + xl - W + 1);
+                const float* e = sWt + u * KP;
+                for (int v = lo + lane; v < a; v += 32) {
+                    const int cl = xl - v;
+                    if (cl >= 0 && cl < TC) atomicAdd(&sCorr[cl], __float2int_rn(e[v] * sScale[cl]));
                 }
             }
         }
@@ -577,7 +606,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
             }
             const size_t o = ((size_t)b * H + r) * W + c0 + tid;
             if (P.intensity) P.intensity[o] = I;
-            P.signal[o] = detect(P, I, gain, bg_mean, env, (uint32_t)(r * W + c0 + tid));
+            P.signal[o] = I;                              // detect_kernel converts to photon counts
         }
         cycle_row(r, -1, (r + K < P.Hp) ? r + K : -1, K - 1);
         __syncthreads();
@@ -682,7 +711,7 @@ int launch_sweep_t(const AcqParams& P, cudaStream_t st) {
     constexpr int TC = 8 * CT;
     const int PR = sweep_pitch(TC, P.KP);
     size_t words = (size_t)P.K * PR + 2 * (size_t)P.K * P.KP + TC;
-    if (STOCH) words += ((P.K + 1 + 3) & ~3) + ((size_t)P.K * PR + 3) / 4 + 2 * TC + 4 + S_EVCAP + S_JOBCAP / 2;
+    if (STOCH) words += ((P.K + 1 + 3) & ~3) + ((size_t)P.K * PR + 3) / 4 + 2 * TC + 4 + S_EVCAP + S_JOBCAP + S_JOBCAP / 2;
     else words += (size_t)P.K * P.KP;
     const size_t smem = words * sizeof(float);
     dim3 grid((P.W + TC - 1) / TC, P.B);
@@ -702,6 +731,15 @@ int launch_sweep_m(const AcqParams& P, cudaStream_t st) {
 
 int launch_sweep(const AcqParams& P, cudaStream_t st) {
     return (P.flags & STED_SAMPLE_BLEACH) ? launch_sweep_m<true>(P, st) : launch_sweep_m<false>(P, st);
+}
+
+int launch_detect(const AcqParams& P, cudaStream_t st) {
+    const size_t npx = (size_t)P.B * P.H * P.W;
+    const size_t want = (npx + 255) / 256;
+    const unsigned blocks = (unsigned)(want < 148u * 32u ? want : 148u * 32u);
+    detect_kernel<<<blocks, 256, 0, st>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
 }
 
 // growable device workspace for the *_host entry points
@@ -799,8 +837,26 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
         Q.env_base = P.env_base + (uint32_t)b0;
         rc = (flags & STED_BLEACH) ? launch_sweep(Q, (cudaStream_t)stream) : launch_gather(Q, (cudaStream_t)stream);
         if (rc) return rc;
+        if (!(flags & STED_NO_DETECT) && (rc = launch_detect(Q, (cudaStream_t)stream))) return rc;
     }
     return STED_OK;
+}
+
+int sted_detect(float* signal_dev, const double* pdt_dev, int B, int H, int W, uint32_t flags,
+                const StedDetectorParams* det, double lambda_fluo, uint64_t seed, uint64_t offset, int64_t env_base,
+                void* stream) {
+    if (!signal_dev || !pdt_dev || !det) return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B, H, W must be positive");
+    if (!(lambda_fluo > 0)) return fail(STED_EINVAL, "lambda_fluo must be positive");
+    int rc = check_device();
+    if (rc) return rc;
+    AcqParams P{};
+    P.signal = signal_dev; P.pdt = pdt_dev; P.B = B; P.H = H; P.W = W;
+    P.flags = flags; P.offset = (uint32_t)offset; P.seed = seed ^ (offset >> 32 << 17); P.env_base = (uint32_t)env_base;
+    P.inv_e_photon = (float)(lambda_fluo / (kPlanck * kLight));
+    P.det_eff = (float)(det->pcef * det->pdef);
+    P.background = (float)det->background;
+    return launch_detect(P, (cudaStream_t)stream);
 }
 
 int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const StedFluoParams* fluo_host,

@@ -53,6 +53,8 @@ extern "C" {
 #define STED_BLEACH         1u  /* apply in-scan photobleaching (pySTED bleach=True)          */
 #define STED_SAMPLE_PHOTONS 2u  /* detector noise: Poisson photon counts (Detector.noise)     */
 #define STED_SAMPLE_BLEACH  4u  /* binomial molecule thinning; otherwise expected counts      */
+#define STED_NO_DETECT      8u  /* sted_acquire leaves the detected power (W) in signal_dev; the
+                                   detector is applied later by sted_detect                   */
 
 /* Fluorophore + STED-pulse parameters of one environment.
  * Mirrors pysted.base.Fluorescence(**defaults.FLUO) (gym_sted/defaults.py:25-42) and the
@@ -127,6 +129,14 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
                  const StedDetectorParams* det, double lambda_fluo,
                  uint64_t seed, uint64_t offset, int64_t env_base,
                  float* intensity_dev, float* signal_dev, void* stream);
+
+/* Detector.get_signal on its own (gym_sted/utils.py:654-657): converts detected power (W), as left
+ * in signal_dev by sted_acquire(..., STED_NO_DETECT), to photon counts in place:
+ *   mean = floor(I / (h c / lambda_fluo)) * pcef * pdef * pdt + background * pdt,
+ *   Poisson(mean) when STED_SAMPLE_PHOTONS is set.  Same (seed, offset, env, pixel) keying. */
+int sted_detect(float* signal_dev, const double* pdt_dev, int B, int H, int W, uint32_t flags,
+                const StedDetectorParams* det, double lambda_fluo, uint64_t seed, uint64_t offset,
+                int64_t env_base, void* stream);
 
 /* Same, from HOST buffers: pads, uploads, runs sted_make_effective + sted_acquire, downloads.
  *   dmap_host     : float32 [B][H][W] molecule maps of the region of interest (un-padded);
