@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsted_b200.so")
+LIB_PATH = os.environ.get("STED_B200_LIB", os.path.join(_HERE, "libsted_b200.so"))
 
 STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH, STED_NO_DETECT = 1, 2, 4, 8
 STED_TAB_E, STED_TAB_ET, STED_TAB_CH, STED_TAB_RS, STED_TABLES = 0, 1, 2, 3, 4
@@ -54,6 +54,7 @@ SIGNATURES = {
     "sted_sample_poisson": (_i, [_vp, _i64, _u64, _u64, _vp, _vp]),
     "sted_sample_binomial": (_i, [_vp, _vp, _i64, _u64, _u64, _vp, _vp]),
     "sted_philox4x32_10": (None, [ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),
+    "sted_debug_phase_cycles": (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     "sted_fma_peak": (_i, [ctypes.POINTER(_d), _vp]),
 }
 

@@ -263,7 +263,11 @@ __global__ void __launch_bounds__(256) detect_kernel(const AcqParams P) {
 // l and l+32; partial sums meet through a shuffle reduce-scatter.
 // ------------------------------------------------------------------------------------------
 constexpr int S_THREADS = 256;
-constexpr int S_EVCAP = 3072, S_JOBCAP = 1536;   // per scan row and tile; overflow falls back to inline work
+__device__ unsigned long long g_phase_cycles[8];   // SWEEP_PROBE==2: per-phase cycle sums of sweep_kernel (thread 0 of each CTA)
+#ifndef SWEEP_PROBE
+#define SWEEP_PROBE 0   // 1: skip job scan + entry scheduling (timing experiments only)
+#endif
+constexpr int S_EVCAP = 2560, S_JOBCAP = 1024;   // per scan row and tile; overflow falls back to inline work
 
 __host__ __device__ inline int sweep_pitch(int TC, int KP) {
     int p = TC + KP;
@@ -311,13 +315,13 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
     float* sRS = sAux;
     float* sQ = sAux;                         // Q[u] = sum_{u'>=u} CH[u'][0], Q[K] = 0
     uint8_t* ndr = reinterpret_cast<uint8_t*>(sAux + ((K + 1 + 3) & ~3));   // [K][PR] next-death pass per pixel
-    float* sI = sAux + (STOCH ? ((K + 1 + 3) & ~3) + (K * PR + 3) / 4 : K * KP);   // [TC] dense row intensities
-    float* sScale = sI + TC;                  // [TC] 2^30 / sI  (fixed-point scale of the corrections)
-    int* sCorr = reinterpret_cast<int*>(sScale + TC);        // [TC] sum of removed taps, fixed point
-    int* sCnt = sCorr + TC;                   // [4]  job / event counters
-    uint32_t* evq = reinterpret_cast<uint32_t*>(sCnt + 4);   // [S_EVCAP] death tasks job | idx<<11, then events xl | u<<8 | a<<14
-    float* jobpos = reinterpret_cast<float*>(evq + S_EVCAP);       // [S_JOBCAP] first-death position of the job
-    uint16_t* jobq = reinterpret_cast<uint16_t*>(jobpos + S_JOBCAP);   // [S_JOBCAP] pixel passes xl | u<<8
+    float* sI = sAux + (STOCH ? ((K + 1 + 3) & ~3) + (K * PR + 3) / 4 : K * KP);   // [2][TC] dense row intensities
+    float* sScale = sI + 2 * TC;              // [2][TC] 2^30 / sI  (fixed-point scale of the corrections)
+    int* sCorr = reinterpret_cast<int*>(sScale + 2 * TC);    // [2][TC] sum of removed taps, fixed point
+    int* sCnt = sCorr + 2 * TC;               // [4]  jobs of even / odd scan rows, events, unused
+    uint32_t* evq = reinterpret_cast<uint32_t*>(sCnt + 4);   // [S_EVCAP] events xl | u<<8 | a<<14, or tasks 1<<31 | job | idx<<11
+    float* jobpos = reinterpret_cast<float*>(evq + S_EVCAP);       // [2][S_JOBCAP] first-death position of the job
+    uint16_t* jobq = reinterpret_cast<uint16_t*>(jobpos + 2 * S_JOBCAP);   // [2][S_JOBCAP] pixel passes xl | u<<8
 
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * TC;
@@ -345,14 +349,15 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         sQ[K] = 0.f;
         for (int u = K - 1; u >= 0; --u) { q += sCH[u * KP]; sQ[u] = q; }
     }
-    __syncthreads();
+    if (STOCH && tid < 2 * TC) sCorr[tid] = 0;
+    if (STOCH && tid < 4) sCnt[tid] = 0;
 
     // columns of the molecule map this tile writes back (each column has exactly one owner)
     const int p = K / 2;
     const int xs = (c0 == 0) ? 0 : c0 + p;
     const int xe = (c0 + TC >= W) ? P.Wpitch : c0 + TC + p;
 
-    // per-molecule hazard of one whole pass of tap row u over pixel column x
+    // per-molecule hazard of one whole pass of tap row u over a pixel whose taps are clipped to [lo,hi]
     auto pass_hazard = [&](const int u, const int lo, const int hi) -> float {
         return sCH[u * KP + lo] - sCH[u * KP + hi + 1];
     };
@@ -377,55 +382,6 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         }
         return 255;
     };
-
-    // Band row y replaces the retired row in its ring slot.  The thread that owns a group of four
-    // columns first writes the old values back (store), then loads the new ones, so no barrier is needed
-    // in between.  Expectation mode keeps s = D*exp(CH[u][hi+1]) for the left-clipped columns.
-    auto cycle_row = [&](const int y_old, const int u_scale_old, const int y_new, const int u_entry) {
-        for (int i = tid; i < PR / 4; i += S_THREADS) {
-            const int xl = 4 * i, x = c0 + xl;
-            if (y_old >= 0) {
-                const float4 old = *reinterpret_cast<const float4*>(ring + (y_old % K) * PR + xl);
-                const float* po_ = reinterpret_cast<const float*>(&old);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int xx = x + j;
-                    if (xx >= xs && xx < xe) {
-                        float val = po_[j];
-                        if (!STOCH && u_scale_old >= 0 && xx < K - 1 && val != 0.f)
-                            val *= expf(-sCH[u_scale_old * KP + xx + 1]);
-                        dout[(size_t)y_old * P.Wpitch + xx] = val;
-                    }
-                }
-            }
-            if (y_new >= 0) {
-                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (y_new < P.Hp && x < P.Wpitch)
-                    val = __ldg(reinterpret_cast<const float4*>(din + (size_t)y_new * P.Wpitch + x));
-                float* pv = reinterpret_cast<float*>(&val);
-                uint32_t nd4 = 0xFFFFFFFFu;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int xx = x + j;
-                    if (pv[j] == 0.f || xx >= Wp) continue;
-                    if (!STOCH) {
-                        if (xx < K - 1) pv[j] *= expf(sCH[u_entry * KP + xx + 1]);
-                    } else {
-                        // first death among n molecules: hazard budget Exp(1)/n from the start of pass u_entry
-                        const int lo = max(0, xx - W + 1), hi = min(K - 1, xx);
-                        PhiloxStream rng;
-                        rng.init(P.seed, P.offset, env, (uint32_t)(y_new * Wp + xx), STED_RNG_BLEACH, 0xFFFFu);
-                        const float tau = -__logf(rng.uniform()) / pv[j];
-                        const int nd = find_pass(u_entry, tau, lo, hi);
-                        nd4 = (nd4 & ~(0xFFu << (8 * j))) | ((uint32_t)nd << (8 * j));
-                    }
-                }
-                *reinterpret_cast<float4*>(ring + (y_new % K) * PR + xl) = val;
-                if (STOCH) *reinterpret_cast<uint32_t*>(ndr + (y_new % K) * PR + xl) = nd4;
-            }
-        }
-    };
-
     // Tap at which a death at in-pass hazard position `pos` happens: largest v in [lo,hi] whose suffix
     // hazard still covers pos (the scan visits the taps of a row from hi down to lo).
     auto tap_of = [&](const float* ch, const float pos, const int lo, const int hi) -> int {
@@ -445,17 +401,33 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         rng.ctr.z += (uint32_t)idx;
         return fminf(pos1 - log1pf(-rng.uniform() * (-expm1f(-(hzp - pos1)))), hzp);
     };
-    auto remove_taps = [&](const int xl, const int u, const int lo, const int a) {
+    auto remove_taps = [&](const int par, const int xl, const int u, const int lo, const int a) {
         const float* e = sWt + u * KP;                   // dwells at taps lo .. a-1 no longer see the molecule
         for (int v = lo; v < a; ++v) {
             const int cl = xl - v;
-            if (cl >= 0 && cl < TC) atomicAdd(&sCorr[cl], __float2int_rn(e[v] * sScale[cl]));
+            if (cl >= 0 && cl < TC) atomicAdd(&sCorr[par * TC + cl], __float2int_rn(e[v] * sScale[par * TC + cl]));
         }
     };
+    auto push_event = [&](const int par, const int xl, const int u, const int lo, const int a) {
+        if (a <= lo) return;
+        const int q = atomicAdd(&sCnt[2], 1);
+        if (q < S_EVCAP) evq[q] = (uint32_t)xl | ((uint32_t)u << 8) | ((uint32_t)a << 14);
+        else remove_taps(par, xl, u, lo, a);
+    };
+    // First death among the n molecules of a pixel that enters the band with tap row u_entry: hazard budget
+    // Exp(1)/n from the start of that pass.  One draw per (pixel, acquisition).
+    auto schedule_entry = [&](const int y, const int x, const float n, const int u_entry) -> int {
+        const int lo = max(0, x - W + 1), hi = min(K - 1, x);
+        PhiloxStream rng;
+        rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, 0xFFFFu);
+        return find_pass(u_entry, -__logf(rng.uniform()) / n, lo, hi);
+    };
     // One pixel whose scheduled death falls in pass u of scan row r: place the first death (truncated
-    // Exp(n) on the pass), count the further deaths of the pass (binomial over the n-1 others), queue one
-    // task per death and re-schedule the survivors (memoryless: fresh Exp(1)/n_left from the next pass on).
+    // Exp(n) on the pass) and emit its event, count the further deaths of the pass (binomial over the n-1
+    // others; each becomes a task), re-schedule the survivors (memoryless: fresh Exp(1)/n_left from the
+    // next pass on).
     auto process_job = [&](const int r, const int jq, const int xl, const int u) {
+        const int par = r & 1;
         const int slot = (r + u) % K;
         const int x = c0 + xl;
         const int lo = max(0, x - W + 1), hi = min(K - 1, x);
@@ -466,28 +438,182 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         PhiloxStream rng;
         rng.init(P.seed, P.offset, env, site, STED_RNG_BLEACH, (uint32_t)r);
         const float pos1 = fminf(-log1pf(-rng.uniform() * (-expm1f(-n * hzp))) / n, hzp);
-        const int kd = 1 + binomial_deaths((int)n - 1, hzp - pos1, rng);
-        const float left = n - (float)kd;
+        const int extra = binomial_deaths((int)n - 1, hzp - pos1, rng);
+        const float left = n - (float)(1 + extra);
         int nd = 255;
         if (left > 0.f) nd = find_pass(u - 1, -__logf(rng.uniform()) / left, lo, hi);
         ring[slot * PR + xl] = left;
         ndr[slot * PR + xl] = (uint8_t)nd;
-        int q = S_EVCAP;
-        if (jq >= 0) { jobpos[jq] = pos1; q = atomicAdd(&sCnt[1], kd); }
-        for (int i = 0; i < kd; ++i) {
-            const int idx = min(i, 4095);
-            if (q + i < S_EVCAP) evq[q + i] = (uint32_t)jq | ((uint32_t)idx << 11);
-            else remove_taps(xl, u, lo, tap_of(ch, i ? later_death_pos(site, r, idx, pos1, hzp) : pos1, lo, hi));
+        push_event(par, xl, u, lo, tap_of(ch, pos1, lo, hi));
+        if (extra > 0) {
+            // a couple of further deaths are placed right here; long runs (nanodomain pixels) become tasks
+            const int inline_n = (jq >= 0 && extra > 2) ? 0 : extra;
+            for (int i = 0; i < inline_n; ++i)
+                push_event(par, xl, u, lo, tap_of(ch, later_death_pos(site, r, min(i + 1, 4095), pos1, hzp), lo, hi));
+            if (inline_n == 0) {
+                jobpos[par * S_JOBCAP + jq] = pos1;
+                const int q = atomicAdd(&sCnt[2], extra);
+                sCnt[3] = 1;
+                for (int i = 0; i < extra; ++i) {
+                    const int idx = min(i + 1, 4095);
+                    if (q + i < S_EVCAP) evq[q + i] = 0x80000000u | (uint32_t)jq | ((uint32_t)idx << 11);
+                    else remove_taps(par, xl, u, lo, tap_of(ch, later_death_pos(site, r, idx, pos1, hzp), lo, hi));
+                }
+            }
+        }
+    };
+    // Queue pixel (xl, tap row u) as a job of scan row r; a queued pixel is marked 254 in the next-death ring.
+    // When the queue is full the pixel keeps its mark u and is picked up by the rescan in phase B.
+    auto add_job = [&](const int r, const int xl, const int u) {
+        const int par = r & 1;
+        const int q = atomicAdd(&sCnt[par], 1);
+        if (q < S_JOBCAP) {
+            jobq[par * S_JOBCAP + q] = (uint16_t)(xl | (u << 8));
+            ndr[((r + u) % K) * PR + xl] = 254;
+        }
+    };
+    // Scan the next-death ring for pixels whose death falls in scan row r (band rows first_u..K-1 relative to r).
+    auto scan_jobs = [&](const int r, const int u_count) {
+        for (int u = warp; u < u_count; u += S_THREADS / 32) {
+            const uint32_t* nrow = reinterpret_cast<const uint32_t*>(ndr + ((r + u) % K) * PR);
+            const uint32_t pat = 0x01010101u * (uint32_t)u;
+            for (int g4 = lane; g4 < PR / 4; g4 += 32) {
+                const uint32_t diff = nrow[g4] ^ pat;
+                if (((diff - 0x01010101u) & ~diff & 0x80808080u) == 0u) continue;   // no byte equals u
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j)
+                    if (((diff >> (8 * j)) & 0xFFu) == 0u) add_job(r, 4 * g4 + j, u);
+            }
         }
     };
 
-    if (STOCH && tid < TC) sCorr[tid] = 0;
-    if (STOCH && tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
-    for (int y = 0; y < K; ++y) cycle_row(-1, -1, y, y);
-    __syncthreads();
+    // Retire band row y_old to global memory (expectation mode undoes the s = D*exp(CH[u][hi+1]) scaling of
+    // the left-clipped columns) and install the prefetched row y_new in the same ring slot.  The same
+    // thread owns a group of four columns in both halves, so no barrier is needed in between.
+    auto cycle_row = [&](const int y_old, const int u_scale_old, const int y_new, const int u_entry, const float4 pre,
+                         const bool sched_jobs) {
+        if (tid < PR / 4) {
+            const int xl = 4 * tid, x = c0 + xl;
+            if (y_old >= 0) {
+                const float4 old = *reinterpret_cast<const float4*>(ring + (y_old % K) * PR + xl);
+                const float* po_ = reinterpret_cast<const float*>(&old);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = x + j;
+                    if (xx >= xs && xx < xe) {
+                        float val = po_[j];
+                        if (!STOCH && u_scale_old >= 0 && xx < K - 1 && val != 0.f)
+                            val *= expf(-sCH[u_scale_old * KP + xx + 1]);
+                        dout[(size_t)y_old * P.Wpitch + xx] = val;
+                    }
+                }
+            }
+            if (y_new >= 0) {
+                float4 val = pre;
+                if (!STOCH) {
+                    float* pv = reinterpret_cast<float*>(&val);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x + j < K - 1 && pv[j] != 0.f) pv[j] *= expf(sCH[u_entry * KP + x + j + 1]);
+                }
+                *reinterpret_cast<float4*>(ring + (y_new % K) * PR + xl) = val;
+                if (STOCH && SWEEP_PROBE == 1) *reinterpret_cast<uint32_t*>(ndr + (y_new % K) * PR + xl) = 0xFFFFFFFFu;
+                if (STOCH && SWEEP_PROBE != 1) {
+                    // schedule the first death of each occupied pixel; deaths due in the very next scan row
+                    // (tap row u_entry) are queued for it right away
+                    uint32_t nd4 = 0xFFFFFFFFu;
+                    const float* pv = reinterpret_cast<const float*>(&val);
+                    const int r_next = y_new - u_entry;
+#pragma unroll 1
+                    for (int j = 0; j < 4; ++j) {
+                        if (pv[j] <= 0.f || x + j >= Wp) continue;
+                        const int nd = schedule_entry(y_new, x + j, pv[j], u_entry);
+                        nd4 = (nd4 & ~(0xFFu << (8 * j))) | ((uint32_t)nd << (8 * j));
+                    }
+                    *reinterpret_cast<uint32_t*>(ndr + (y_new % K) * PR + xl) = nd4;
+                    if (sched_jobs) {
+#pragma unroll 1
+                        for (int j = 0; j < 4; ++j)
+                            if (((nd4 >> (8 * j)) & 0xFFu) == (uint32_t)u_entry) add_job(r_next, xl + j, u_entry);
+                    }
+                }
+            }
+        }
+    };
+    // Stochastic mode handles the band rows one pixel per thread (thread t owns ring column t).
+    auto fetch_px = [&](const int y) -> float {
+        const int x = c0 + tid;
+        return (tid < PR && y >= 0 && y < P.Hp && x < P.Wpitch) ? __ldg(din + (size_t)y * P.Wpitch + x) : 0.f;
+    };
+    auto entry_nd = [&](const int y, const float n, const int u_entry) -> int {
+        const int x = c0 + tid;
+        return (tid < PR && n > 0.f && x < Wp && SWEEP_PROBE != 1) ? schedule_entry(y, x, n, u_entry) : 255;
+    };
+    auto cycle_px = [&](const int y_old, const int y_new, const float n_new, const int nd_new, const int u_entry,
+                        const bool sched_jobs) {
+        if (tid < PR) {
+            const int x = c0 + tid;
+            if (y_old >= 0 && x >= xs && x < xe) dout[(size_t)y_old * P.Wpitch + x] = ring[(y_old % K) * PR + tid];
+            if (y_new >= 0) {
+                ring[(y_new % K) * PR + tid] = n_new;
+                ndr[(y_new % K) * PR + tid] = (uint8_t)nd_new;
+                if (sched_jobs && nd_new == u_entry) add_job(y_new - u_entry, tid, u_entry);
+            }
+        }
+    };
+    auto fetch_row = [&](const int y) -> float4 {
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int x = c0 + 4 * tid;
+        if (tid < PR / 4 && y >= 0 && y < P.Hp && x < P.Wpitch)
+            val = __ldg(reinterpret_cast<const float4*>(din + (size_t)y * P.Wpitch + x));
+        return val;
+    };
 
+    if (STOCH) {
+        for (int y = 0; y < K; ++y) {
+            const float n = fetch_px(y);
+            cycle_px(-1, y, n, entry_nd(y, n, y), y, false);
+        }
+    } else {
+        for (int y = 0; y < K; ++y) cycle_row(-1, -1, y, y, fetch_row(y), false);
+    }
+    __syncthreads();
+    if (STOCH) {   // jobs of scan row 0
+        scan_jobs(0, K);
+        __syncthreads();
+    }
+
+    // writes scan row r (dense gather minus the taps removed by the deaths of that row)
+    auto write_row = [&](const int r) {
+        if (tid < TC && c0 + tid < W) {
+            const int par = r & 1;
+            float I = sI[par * TC + tid];
+            if (STOCH) {
+                I = fmaxf(I * (1.0f - (float)sCorr[par * TC + tid] * 9.313225746154785e-10f), 0.f);
+                sCorr[par * TC + tid] = 0;
+            }
+            const size_t o = ((size_t)b * H + r) * W + c0 + tid;
+            if (P.intensity) P.intensity[o] = I;
+            P.signal[o] = I;                              // detect_kernel converts to photon counts
+        }
+    };
+
+#if SWEEP_PROBE == 2
+    long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = clock64();
+#define PHASE_MARK(i) do { const long long t_now = clock64(); t_ph[i] += t_now - t_last; t_last = t_now; } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
     for (int r = 0; r < H; ++r) {
-        // ---------------- phase G: dense gather of scan row r against the row-start state
+        const int par = r & 1;
+        const int y_in = r + K < P.Hp ? r + K : -1;                    // band row that enters after this scan row
+        const float4 pre = STOCH ? make_float4(0.f, 0.f, 0.f, 0.f) : fetch_row(y_in);   // lands while the row is gathered
+        const float pre_px = STOCH ? fetch_px(y_in) : 0.f;
+        // ---------------- phase A: write the previous row; dense gather of scan row r against the row-start state
+        if (STOCH) {
+            if (r > 0) write_row(r - 1);
+            if (tid == 0) sCnt[2] = 0;
+        }
         {
             float acc[CT];
 #pragma unroll
@@ -521,14 +647,16 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
             const float tot = reduce_scatter<CT>(acc, lane);
             constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
             if ((lane & ((1 << SH) - 1)) == 0) {
-                sI[CT * warp + (lane >> SH)] = tot;
-                if (STOCH) sScale[CT * warp + (lane >> SH)] = 1073741824.0f / fmaxf(tot, 1e-30f);
+                sI[par * TC + CT * warp + (lane >> SH)] = tot;
+                if (STOCH) sScale[par * TC + CT * warp + (lane >> SH)] = 1073741824.0f / fmaxf(tot, 1e-30f);
             }
         }
+        PHASE_MARK(0);
         __syncthreads();
+        PHASE_MARK(1);
 
-        // ---------------- phase S: thin the band with the taps of this scan row
         if (!STOCH) {
+            // ---------------- expectation mode: thin the band with the taps of this scan row
             for (int u = warp; u < K; u += S_THREADS / 32) {
                 float* row = ring + ((r + u) % K) * PR;
                 for (int xl = lane; xl < span; xl += 32) {
@@ -543,76 +671,76 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
                     row[xl] = n * m;
                 }
             }
-        } else {
-            // (S1) scan the next-death ring: pixels whose scheduled death falls in this pass become jobs
-            for (int u = warp; u < K; u += S_THREADS / 32) {
-                const int slot = (r + u) % K;
-                const uint32_t* nrow = reinterpret_cast<const uint32_t*>(ndr + slot * PR);
-                const uint32_t pat = 0x01010101u * (uint32_t)u;
-                for (int g4 = lane; g4 < PR / 4; g4 += 32) {
-                    const uint32_t diff = nrow[g4] ^ pat;
-                    if (((diff - 0x01010101u) & ~diff & 0x80808080u) == 0u) continue;   // no byte equals u
-#pragma unroll 1
-                    for (int j = 0; j < 4; ++j) {
-                        if (((diff >> (8 * j)) & 0xFFu) != 0u) continue;
-                        const int q = atomicAdd(&sCnt[0], 1);
-                        if (q < S_JOBCAP) jobq[q] = (uint16_t)((4 * g4 + j) | (u << 8));
-                        else process_job(r, -1, 4 * g4 + j, u);          // queue full: whole job inline
-                    }
+            __syncthreads();
+            write_row(r);
+            cycle_row(r, -1, (r + K < P.Hp) ? r + K : -1, K - 1, pre, false);
+            __syncthreads();
+            continue;
+        }
+
+        // ---------------- phase B: one job per thread (deaths of the pixel-passes due in this scan row)
+        const int nd_in = entry_nd(y_in, pre_px, K - 1);   // ... the low ones schedule the pixels of the entering row
+        {
+            const int total = sCnt[par];
+            const int njobs = min(total, S_JOBCAP);
+            for (int q = S_THREADS - 1 - tid; q < njobs; q += S_THREADS)      // jobs start at the high thread ids ...
+                process_job(r, q, jobq[par * S_JOBCAP + q] & 0xFF, jobq[par * S_JOBCAP + q] >> 8);
+            if (total > S_JOBCAP) {          // queue overflowed: the unqueued pixels still carry their tap row
+                for (int idx = tid; idx < K * PR; idx += S_THREADS) {
+                    const int u = idx / PR, xl = idx - u * PR;
+                    if (ndr[((r + u) % K) * PR + xl] == (uint8_t)u) process_job(r, -1, xl, u);
                 }
             }
-            __syncthreads();
-            // (S2) one job per thread: count the deaths of that pixel-pass, queue a task per death
-            {
-                const int njobs = min(sCnt[0], S_JOBCAP);
-                for (int q = tid; q < njobs; q += S_THREADS) process_job(r, q, jobq[q] & 0xFF, jobq[q] >> 8);
-            }
-            __syncthreads();
-            // (S3) one task per thread: place the death on its tap; the task slot becomes the event
-            const int nev = min(sCnt[1], S_EVCAP);
+        }
+        __syncthreads();
+        PHASE_MARK(2);
+
+        // ---------------- phase C: corrections of row r; retire row r / install row r+K; find the jobs of row r+1
+        const int nev = min(sCnt[2], S_EVCAP);
+        if (sCnt[3]) {                       // some queue entries are still tasks: give them their tap first
             for (int q = tid; q < nev; q += S_THREADS) {
-                const uint32_t t = evq[q];
-                const int jq = t & 0x7FF, idx = t >> 11;
-                const int xl = jobq[jq] & 0xFF, u = jobq[jq] >> 8;
+                const uint32_t ev = evq[q];
+                if (!(ev & 0x80000000u)) continue;
+                const int jq = ev & 0x7FF, idx = (ev >> 11) & 0xFFF;
+                const uint32_t jb = jobq[par * S_JOBCAP + jq];
+                const int xl = jb & 0xFF, u = jb >> 8;
                 const int x = c0 + xl;
                 const int lo = max(0, x - W + 1), hi = min(K - 1, x);
                 const float* ch = sCH + u * KP;
-                const float pos1 = jobpos[jq];
-                const float pos = idx ? later_death_pos((uint32_t)((r + u) * Wp + x), r, idx, pos1, ch[lo] - ch[hi + 1]) : pos1;
-                evq[q] = (uint32_t)xl | ((uint32_t)u << 8) | ((uint32_t)tap_of(ch, pos, lo, hi) << 14);
+                const int a = tap_of(ch, later_death_pos((uint32_t)((r + u) * Wp + x), r, idx, jobpos[par * S_JOBCAP + jq],
+                                                         ch[lo] - ch[hi + 1]), lo, hi);
+                evq[q] = (a > lo) ? ((uint32_t)xl | ((uint32_t)u << 8) | ((uint32_t)a << 14)) : 0u;
             }
             __syncthreads();
-            // (S4) a warp per event: the taps after the death leave the row's intensities
-            for (int q = warp; q < nev; q += S_THREADS / 32) {
-                const uint32_t ev = evq[q];
-                const int xl = ev & 0xFF, u = (ev >> 8) & 0x3F, a = (ev >> 14) & 0x3F;
-                const int lo = max(0, c0 + xl - W + 1);
-                const float* e = sWt + u * KP;
-                for (int v = lo + lane; v < a; v += 32) {
-                    const int cl = xl - v;
-                    if (cl >= 0 && cl < TC) atomicAdd(&sCorr[cl], __float2int_rn(e[v] * sScale[cl]));
-                }
-            }
         }
-        __syncthreads();
-
-        // ---------------- phase O: detector, retire band row y = r, bring in row r + K
-        if (STOCH && tid == 0) { sCnt[0] = 0; sCnt[1] = 0; }
-        if (tid < TC && c0 + tid < W) {
-            float I = sI[tid];
-            if (STOCH) {
-                I = fmaxf(I * (1.0f - (float)sCorr[tid] * 9.313225746154785e-10f), 0.f);
-                sCorr[tid] = 0;
-            }
-            const size_t o = ((size_t)b * H + r) * W + c0 + tid;
-            if (P.intensity) P.intensity[o] = I;
-            P.signal[o] = I;                              // detect_kernel converts to photon counts
+        if (tid == 0) { sCnt[par] = 0; sCnt[3] = 0; }
+        PHASE_MARK(3);
+        // one event per thread: the taps after the death (lo .. a-1 of tap row u) leave the row's intensities.
+        // Fixed-point integer atomics: native in shared memory, and the sum does not depend on the order.
+        for (int q = tid; q < nev; q += S_THREADS) {
+            const uint32_t ev = evq[q];
+            const int xl = ev & 0xFF, u = (ev >> 8) & 0x3F, a = (ev >> 14) & 0x3F;
+            const float* e = sWt + u * KP;
+            const float* sc = sScale + par * TC;
+            int* corr = sCorr + par * TC;
+            const int v0 = max(max(0, c0 + xl - W + 1), xl - (TC - 1)), v1 = min(a, xl + 1);   // keeps 0 <= xl - v < TC
+#pragma unroll 4
+            for (int v = v0; v < v1; ++v) atomicAdd(&corr[xl - v], __float2int_rn(e[v] * sc[xl - v]));
         }
-        cycle_row(r, -1, (r + K < P.Hp) ? r + K : -1, K - 1);
+        PHASE_MARK(4);
+        cycle_px(r, y_in, pre_px, nd_in, K - 1, true);
+        PHASE_MARK(5);
+        if (r + 1 < H && SWEEP_PROBE != 1) scan_jobs(r + 1, K - 1);          // rows r+1 .. r+K-1; row r+K is queued by cycle_row
+        PHASE_MARK(6);
         __syncthreads();
+        PHASE_MARK(7);
     }
+#if SWEEP_PROBE == 2
+    if (tid == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)t_ph[i]);
+#endif
+    if (STOCH) write_row(H - 1);
     // flush the K-1 band rows below the last scan row (tap row they would have had next: y - H)
-    for (int y = H; y < P.Hp; ++y) cycle_row(y, y - H, -1, 0);
+    for (int y = H; y < P.Hp; ++y) cycle_row(y, y - H, -1, 0, make_float4(0.f, 0.f, 0.f, 0.f), false);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -710,8 +838,8 @@ template <int KT, int CT, bool STOCH>
 int launch_sweep_t(const AcqParams& P, cudaStream_t st) {
     constexpr int TC = 8 * CT;
     const int PR = sweep_pitch(TC, P.KP);
-    size_t words = (size_t)P.K * PR + 2 * (size_t)P.K * P.KP + TC;
-    if (STOCH) words += ((P.K + 1 + 3) & ~3) + ((size_t)P.K * PR + 3) / 4 + 2 * TC + 4 + S_EVCAP + S_JOBCAP + S_JOBCAP / 2;
+    size_t words = (size_t)P.K * PR + 2 * (size_t)P.K * P.KP + 2 * TC;
+    if (STOCH) words += ((P.K + 1 + 3) & ~3) + ((size_t)P.K * PR + 3) / 4 + 6 * TC + 4 + S_EVCAP + 2 * S_JOBCAP + S_JOBCAP;
     else words += (size_t)P.K * P.KP;
     const size_t smem = words * sizeof(float);
     dim3 grid((P.W + TC - 1) / TC, P.B);
@@ -936,6 +1064,14 @@ void sted_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
     Philox4 c{ctr[0], ctr[1], ctr[2], ctr[3]};
     Philox4 r = philox4x32_10(c, key[0], key[1]);
     out_host[0] = r.x; out_host[1] = r.y; out_host[2] = r.z; out_host[3] = r.w;
+}
+
+int sted_debug_phase_cycles(unsigned long long out_host[8], int reset) {
+    int rc = check_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyFromSymbol(out_host, g_phase_cycles, sizeof(unsigned long long) * 8));
+    if (reset) { unsigned long long z[8] = {0}; CUDA_TRY(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z))); }
+    return STED_OK;
 }
 
 int sted_fma_peak(double* tflops, void* stream) {

@@ -161,6 +161,9 @@ int sted_sample_binomial(const float* n_dev, const float* q_dev, int64_t n, uint
 /* Raw Philox4x32-10 block for known-answer tests: out_host[4]. Host-side, no device needed. */
 void sted_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out_host[4]);
 
+/* Debug: per-phase cycle sums of the scan kernel (non-zero only in SWEEP_PROBE=2 builds). */
+int sted_debug_phase_cycles(unsigned long long out_host[8], int reset);
+
 /* FP32-FMA peak microbenchmark (roofline denominator): returns achieved TFLOP/s in *tflops. */
 int sted_fma_peak(double* tflops, void* stream);
 
