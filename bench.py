@@ -195,6 +195,7 @@ def run_ours(args, rank, local_rank, world):
     pool = [torch.from_numpy(np.tile(maps_np[i * n_unique:(i + 1) * n_unique], (reps, 1, 1))[:B]).to(torch.float32)
             for i in range(2)]
     pool_dev = [p.to(dev) for p in pool]
+    pool_tot = [int(p.sum().item()) for p in pool]
     pool_pin = [p.pin_memory() for p in pool]
     g = torch.Generator().manual_seed(1234 + rank)
     lo = torch.tensor([defaults.action_spaces[k]["low"] for k in ("p_sted", "p_ex", "pdt")], dtype=torch.float64)
@@ -209,7 +210,7 @@ def run_ours(args, rank, local_rank, world):
 
     def step(i, timed):
         a = actions_dev[i]
-        bm.set_datamaps(pool_dev[0])
+        bm.set_datamaps(pool_dev[0], max_molecules=pool_tot[0])
         ev = None
         if timed:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -218,7 +219,7 @@ def run_ours(args, rank, local_rank, world):
         bm.get_signal_and_bleach(a[:, 2].contiguous(), a[:, 1].contiguous(), a[:, 0].contiguous(), bleach=True,
                                  out_signal=sig[1])
         bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[2])
-        bm.set_datamaps(pool_dev[1])
+        bm.set_datamaps(pool_dev[1], max_molecules=pool_tot[1])
         bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
         launches[0] += 12     # per acquisition: make_effective, gather|sweep, detect
 
@@ -230,7 +231,7 @@ def run_ours(args, rank, local_rank, world):
         if ev: ev[0].record()
         _lib.check(bm.lib.sted_acquire(bm.dmap.data_ptr(), None, bm.tables.data_ptr(), pdt.data_ptr(), bm.B, bm.H,
                                        bm.W, bm.K, flags | _lib.STED_NO_DETECT, ctypes.byref(bm.det), bm.lambda_fluo,
-                                       bm.seed, bm.offset, bm.env_base, None, out.data_ptr(), st))
+                                       bm.seed, bm.offset, bm.env_base, None, out.data_ptr(), None, 0, st))
         if ev: ev[1].record(); kern_ev.append(ev)
         _lib.check(bm.lib.sted_detect(out.data_ptr(), pdt.data_ptr(), bm.B, bm.H, bm.W, flags, ctypes.byref(bm.det),
                                       bm.lambda_fluo, bm.seed, bm.offset, bm.env_base, st))

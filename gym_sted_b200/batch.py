@@ -43,6 +43,7 @@ class BatchedMicroscope:
         self.dmap_alt = torch.zeros_like(self.dmap)
         self.det = microscope.detector.params()
         self.lambda_fluo = float(microscope.fluo.lambda_)
+        self.workspace, self.workspace_bytes = None, 0
 
     # per-env fluorophores (config 3: one parameter set per environment)
     def set_fluorophores(self, fluos=None):
@@ -53,12 +54,31 @@ class BatchedMicroscope:
         arr = (_lib.StedFluoParams * self.B)(*[fluo_struct(f, m.excitation, m.sted) for f in fluos])
         self.d_fluo = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
 
-    def set_datamaps(self, roi: torch.Tensor):
-        """roi: (B,H,W) molecule counts (any real dtype); pads with the K//2 zero frame."""
+    def set_datamaps(self, roi: torch.Tensor, max_molecules=None):
+        """roi: (B,H,W) molecule counts (any real dtype); pads with the K//2 zero frame.
+
+        ``max_molecules`` bounds the total number of molecules of the batch (it sizes the scratch of the
+        stochastic scan); when omitted it is read back from the device once (one synchronisation)."""
         assert roi.shape == (self.B, self.H, self.W)
         p = self.p
         self.dmap.zero_()
         self.dmap[:, p:p + self.H, p:p + self.W] = roi.to(self.device, torch.float32)
+        if max_molecules is None:
+            max_molecules = int(torch.clamp(roi, min=0).sum().item())
+        self._reserve(int(max_molecules) + 16)
+
+    def _reserve(self, max_events: int):
+        need = int(self.lib.sted_bleach_workspace_bytes(self.B, self.H, max_events))
+        if self.workspace is None or self.workspace.numel() < need:
+            self.workspace = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        self.workspace_bytes = need
+
+    def dropped_events(self) -> int:
+        """Deaths the last stochastic scan could not store (0 unless ``max_molecules`` was too small)."""
+        out = ctypes.c_int(0)
+        _lib.check(self.lib.sted_bleach_dropped_events(self.workspace.data_ptr(), ctypes.byref(out),
+                                                       torch.cuda.current_stream(self.device).cuda_stream))
+        return out.value
 
     def datamaps_roi(self) -> torch.Tensor:
         p = self.p
@@ -97,7 +117,8 @@ class BatchedMicroscope:
             self.dmap.data_ptr(), self.dmap_alt.data_ptr() if bleach else None, self.tables.data_ptr(),
             pdt.data_ptr(), self.B, self.H, self.W, self.K, flags, ctypes.byref(self.det), self.lambda_fluo,
             self.seed if seed is None else int(seed), self.offset, self.env_base,
-            intensity.data_ptr() if want_intensity else None, signal.data_ptr(), st))
+            intensity.data_ptr() if want_intensity else None, signal.data_ptr(),
+            self.workspace.data_ptr() if self.workspace is not None else None, self.workspace_bytes, st))
         if bleach and update:
             self.dmap, self.dmap_alt = self.dmap_alt, self.dmap
         return signal, intensity

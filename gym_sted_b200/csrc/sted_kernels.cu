@@ -246,28 +246,33 @@ __global__ void __launch_bounds__(256) detect_kernel(const AcqParams P) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K3: raster scan with in-scan bleaching ("row sweep").
+// K3: raster scan with in-scan bleaching.
 //
 // pySTED visits dwells in row-major order; at each dwell it gathers the window, then thins every
-// molecule of the window with survival exp(-k_b[u][v]*pdt).  Survival factors
-// commute, so within one scan row r the count a dwell sees at tap (u,v) is the count at the start
-// of the row thinned by the taps v' > v of the same tap row, and after the row every pixel of band
-// row u has been thinned by the taps v' in [lo,hi] that exist for its column.
+// molecule of the window with survival exp(-k_b[u][v]*pdt).  Two facts make this
+// parallel:
+//  (1) survival factors commute, so within scan row r the count a dwell sees at tap (u,v) is the count
+//      at the start of the row thinned by the taps v' > v of the same tap row ("row sweep");
+//  (2) the thinning of a pixel depends only on its own count and on the hazard tables, never on the
+//      image, so in stochastic mode every death can be drawn BEFORE the scan: each molecule lives an
+//      Exp(1) amount of cumulative hazard along the (pass, tap) sequence that visits its pixel.
+//
 //   expectation mode : state s = D*exp(CH[u][hi+1]); gather with ET; s *= exp(CHm1 - CH[u][lo])
-//   stochastic mode  : state n integer; deaths ~ Binomial(n, 1-exp(-hz)); each death gets its tap
-//                      by inverting the in-row hazard; taps after the death are subtracted from
-//                      the dense gather of the row.  Identical in distribution to the per-dwell
-//                      chain of binomials.
-// CTA = (environment, tile of TC = 8*CT output columns), 256 threads; scan rows are sequential,
-// the K-row band lives in a shared-memory ring; warp w owns CT columns, lane l the tap rows
+//   stochastic mode  : presample_kernel draws, per occupied pixel, Binomial(n, 1-exp(-H_tot)) deaths and
+//                      places each one on its (scan row, tap) by inverting the cumulative hazard; a
+//                      count / prefix-sum / fill pass buckets the events by scan row; sweep_kernel
+//                      replays them: after the dense gather of row r, every event of row r decrements its
+//                      pixel and removes the taps the dead molecule no longer contributes to.
+//                      Identical in distribution to the per-dwell chain of binomials.
+// sweep_kernel: CTA = (environment, tile of TC = 8*CT output columns), 256 threads; scan rows are
+// sequential, the K-row band lives in a shared-memory ring; warp w owns CT columns, lane l the tap rows
 // l and l+32; partial sums meet through a shuffle reduce-scatter.
 // ------------------------------------------------------------------------------------------
 constexpr int S_THREADS = 256;
-__device__ unsigned long long g_phase_cycles[8];   // SWEEP_PROBE==2: per-phase cycle sums of sweep_kernel (thread 0 of each CTA)
 #ifndef SWEEP_PROBE
-#define SWEEP_PROBE 0   // 1: skip job scan + entry scheduling (timing experiments only)
+#define SWEEP_PROBE 0   // 2: per-phase cycle counters (timing experiments only)
 #endif
-constexpr int S_EVCAP = 2560, S_JOBCAP = 1024;   // per scan row and tile; overflow falls back to inline work
+__device__ unsigned long long g_phase_cycles[8];   // SWEEP_PROBE==2: per-phase cycle sums of sweep_kernel
 
 __host__ __device__ inline int sweep_pitch(int TC, int KP) {
     int p = TC + KP;
@@ -299,8 +304,131 @@ __device__ __forceinline__ float reduce_scatter(float (&a)[CT], int lane) {
     return a[0];
 }
 
+// workspace of the stochastic scan: [4 ints status][B*H ints cursor][B*H+1 ints offsets][cap events]
+struct BleachWs {
+    int* status;         // [0] = events dropped because the workspace was too small
+    int* cnt;            // [B*H] events per (env, scan row); reused as fill cursor
+    int* off;            // [B*H + 1] exclusive prefix sums
+    uint32_t* ev;        // [cap] events  x | u<<12 | a<<18
+    unsigned long long cap;
+};
+
+// Death schedule of every occupied pixel (one thread per pixel of the padded map).
+//   FILL = false: count the events of each (env, scan row);  FILL = true: regenerate them (same Philox
+//   stream, same arithmetic) and store them in their row bucket.
+template <bool FILL>
+__global__ void __launch_bounds__(256) presample_kernel(const AcqParams P, const BleachWs ws) {
+    const int K = P.K, KP = P.KP, H = P.H, W = P.W, Wp = P.Wp;
+    extern __shared__ __align__(16) float smem[];
+    float* sCH = smem;                 // [K][KP]
+    float* sQ = sCH + K * KP;          // [K+1]  Q[u] = sum_{u'>=u} CH[u'][0]
+    const int b = blockIdx.y;
+    {
+        const float4* c4 = reinterpret_cast<const float4*>(P.tables + ((size_t)b * STED_TABLES + STED_TAB_CH) * K * KP);
+        for (int i = threadIdx.x; i < K * KP / 4; i += blockDim.x) reinterpret_cast<float4*>(sCH)[i] = __ldg(c4 + i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float q = 0.f;
+        sQ[K] = 0.f;
+        for (int u = K - 1; u >= 0; --u) { q += sCH[u * KP]; sQ[u] = q; }
+    }
+    __syncthreads();
+    if (sQ[0] <= 0.f) return;          // no bleaching at all for this environment
+    const int p = K / 2;
+    const float* din = P.din + (size_t)b * P.Hp * P.Wpitch;
+    const uint32_t env = P.env_base + (uint32_t)b;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < H * W; idx += gridDim.x * blockDim.x) {
+        const int y = p + idx / W, x = p + idx % W;             // molecules only live inside the ROI
+        const int n = (int)din[(size_t)y * P.Wpitch + x];
+        if (n <= 0) continue;
+        const int lo = max(0, x - W + 1), hi = min(K - 1, x);    // taps that ever visit this column
+        const int u_hi = min(K - 1, y), u_lo = max(0, y - (H - 1));   // passes, visited from u_hi down to u_lo
+        const bool interior = (lo == 0 && hi == K - 1);
+        float htot;
+        if (interior) htot = sQ[u_lo] - sQ[u_hi + 1];
+        else { htot = 0.f; for (int u = u_lo; u <= u_hi; ++u) htot += sCH[u * KP + lo] - sCH[u * KP + hi + 1]; }
+        PhiloxStream rng;
+        rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, 0);
+        const int dead = binomial_deaths(n, htot, rng);
+        const float pd = -expm1f(-htot);
+        for (int d = 0; d < dead; ++d) {
+            // hazard this molecule had consumed when it died: truncated Exp(1) on (0, htot)
+            const float t = fminf(-log1pf(-rng.uniform() * pd), htot);
+            int u;
+            float before;                                        // hazard of the passes visited before pass u
+            if (interior) {
+                const float thr = t + sQ[u_hi + 1];
+                int a = u_lo, z = u_hi;                          // largest u in [u_lo,u_hi] with Q[u] >= thr
+                while (a < z) {
+                    const int mid = (a + z + 1) >> 1;
+                    if (sQ[mid] >= thr) a = mid; else z = mid - 1;
+                }
+                u = a;
+                before = sQ[u + 1] - sQ[u_hi + 1];
+            } else {
+                float cum = 0.f;
+                u = u_lo; before = 0.f;
+                for (int uu = u_hi; uu >= u_lo; --uu) {
+                    const float hz = sCH[uu * KP + lo] - sCH[uu * KP + hi + 1];
+                    if (cum + hz >= t || uu == u_lo) { u = uu; before = cum; break; }
+                    cum += hz;
+                }
+            }
+            const int r = y - u;
+            if (!FILL) {
+                atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
+            } else {
+                // tap: largest v in [lo,hi] whose suffix hazard still covers the in-pass position
+                const float* ch = sCH + u * KP;
+                const float thr = fmaxf(t - before, 0.f) + ch[hi + 1];
+                int a = lo, z = hi;
+                while (a < z) {
+                    const int mid = (a + z + 1) >> 1;
+                    if (ch[mid] >= thr) a = mid; else z = mid - 1;
+                }
+                const unsigned long long slot = (unsigned long long)ws.off[(size_t)b * H + r] +
+                                                (unsigned long long)atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
+                if (slot < ws.cap) ws.ev[slot] = (uint32_t)x | ((uint32_t)u << 12) | ((uint32_t)a << 18);
+                else atomicAdd(&ws.status[0], 1);
+            }
+        }
+    }
+}
+
+// exclusive prefix sum of cnt[n] into off[n+1] (single CTA), then cnt is cleared to serve as fill cursor
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const BleachWs ws, const int n) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? ws.cnt[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) warp_tot[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const int excl = carry + (warp ? warp_tot[warp - 1] : 0) + s - v;
+        if (i < n) { ws.off[i] = excl; ws.cnt[i] = 0; }
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) ws.off[n] = carry;
+}
+
 template <int KT, int CT, bool STOCH>
-__global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) {
+__global__ void __launch_bounds__(S_THREADS, STOCH ? 3 : 2) sweep_kernel(const AcqParams P, const BleachWs ws) {
     constexpr int TC = 8 * CT;
     const int K = KT ? KT : P.K;
     const int KP = KT ? STED_KPITCH(KT) : P.KP;
@@ -310,18 +438,11 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;                       // [K][PR]  band of the molecule map (counts / scaled expectations)
     float* sWt = ring + K * PR;               // [K][KP]  gather weights: E (stochastic) or ET (expectation)
-    float* sCH = sWt + K * KP;                // [K][KP]  suffix hazards
-    float* sAux = sCH + K * KP;               // expectation: RS [K][KP]; stochastic: Q[K+1] + next-death ring
-    float* sRS = sAux;
-    float* sQ = sAux;                         // Q[u] = sum_{u'>=u} CH[u'][0], Q[K] = 0
-    uint8_t* ndr = reinterpret_cast<uint8_t*>(sAux + ((K + 1 + 3) & ~3));   // [K][PR] next-death pass per pixel
-    float* sI = sAux + (STOCH ? ((K + 1 + 3) & ~3) + (K * PR + 3) / 4 : K * KP);   // [2][TC] dense row intensities
-    float* sScale = sI + 2 * TC;              // [2][TC] 2^30 / sI  (fixed-point scale of the corrections)
+    float* sI = sWt + K * KP;                 // [2][TC]  dense row intensities (even / odd scan rows)
+    float* sScale = sI + 2 * TC;              // [2][TC]  2^30 / sI  (fixed-point scale of the corrections)
     int* sCorr = reinterpret_cast<int*>(sScale + 2 * TC);    // [2][TC] sum of removed taps, fixed point
-    int* sCnt = sCorr + 2 * TC;               // [4]  jobs of even / odd scan rows, events, unused
-    uint32_t* evq = reinterpret_cast<uint32_t*>(sCnt + 4);   // [S_EVCAP] events xl | u<<8 | a<<14, or tasks 1<<31 | job | idx<<11
-    float* jobpos = reinterpret_cast<float*>(evq + S_EVCAP);       // [2][S_JOBCAP] first-death position of the job
-    uint16_t* jobq = reinterpret_cast<uint16_t*>(jobpos + 2 * S_JOBCAP);   // [2][S_JOBCAP] pixel passes xl | u<<8
+    float* sCH = reinterpret_cast<float*>(sCorr + 2 * TC);   // [K][KP]  suffix hazards     (expectation mode only)
+    float* sRS = sCH + K * KP;                // [K][KP]  exp(-CH)                           (expectation mode only)
 
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * TC;
@@ -329,7 +450,6 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
     const int W = P.W, H = P.H, Wp = P.Wp;
     const float* din = P.din + (size_t)b * P.Hp * P.Wpitch;
     float* dout = P.dout + (size_t)b * P.Hp * P.Wpitch;
-    const uint32_t env = P.env_base + (uint32_t)b;
 
     {   // tables
         const size_t tsz = (size_t)K * KP;
@@ -339,159 +459,24 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         const float4* r4 = reinterpret_cast<const float4*>(tb + STED_TAB_RS * tsz);
         for (int i = tid; i < (int)(tsz / 4); i += S_THREADS) {
             reinterpret_cast<float4*>(sWt)[i] = __ldg(w4 + i);
-            reinterpret_cast<float4*>(sCH)[i] = __ldg(c4 + i);
-            if (!STOCH) reinterpret_cast<float4*>(sRS)[i] = __ldg(r4 + i);
+            if (!STOCH) {
+                reinterpret_cast<float4*>(sCH)[i] = __ldg(c4 + i);
+                reinterpret_cast<float4*>(sRS)[i] = __ldg(r4 + i);
+            }
         }
     }
+    if (tid < 2 * TC) sCorr[tid] = 0;
     __syncthreads();
-    if (STOCH && tid == 0) {
-        float q = 0.f;
-        sQ[K] = 0.f;
-        for (int u = K - 1; u >= 0; --u) { q += sCH[u * KP]; sQ[u] = q; }
-    }
-    if (STOCH && tid < 2 * TC) sCorr[tid] = 0;
-    if (STOCH && tid < 4) sCnt[tid] = 0;
 
     // columns of the molecule map this tile writes back (each column has exactly one owner)
     const int p = K / 2;
     const int xs = (c0 == 0) ? 0 : c0 + p;
     const int xe = (c0 + TC >= W) ? P.Wpitch : c0 + TC + p;
 
-    // per-molecule hazard of one whole pass of tap row u over a pixel whose taps are clipped to [lo,hi]
-    auto pass_hazard = [&](const int u, const int lo, const int hi) -> float {
-        return sCH[u * KP + lo] - sCH[u * KP + hi + 1];
-    };
-    // Pass (<= u_from) in which a per-molecule hazard budget `tau`, counted from the START of pass u_from,
-    // runs out; 255 when it outlasts the remaining passes.
-    auto find_pass = [&](const int u_from, const float tau, const int lo, const int hi) -> int {
-        if (u_from < 0) return 255;
-        if (lo == 0 && hi == K - 1) {
-            const float thr = tau + sQ[u_from + 1];
-            if (sQ[0] < thr) return 255;
-            int a = 0, z = u_from;                      // largest u in [0,u_from] with Q[u] >= thr
-            while (a < z) {
-                const int mid = (a + z + 1) >> 1;
-                if (sQ[mid] >= thr) a = mid; else z = mid - 1;
-            }
-            return a;
-        }
-        float cum = 0.f;
-        for (int u = u_from; u >= 0; --u) {
-            cum += pass_hazard(u, lo, hi);
-            if (cum >= tau) return u;
-        }
-        return 255;
-    };
-    // Tap at which a death at in-pass hazard position `pos` happens: largest v in [lo,hi] whose suffix
-    // hazard still covers pos (the scan visits the taps of a row from hi down to lo).
-    auto tap_of = [&](const float* ch, const float pos, const int lo, const int hi) -> int {
-        const float thr = pos + ch[hi + 1];
-        int a = lo, z = hi;
-        while (a < z) {
-            const int mid = (a + z + 1) >> 1;
-            if (ch[mid] >= thr) a = mid; else z = mid - 1;
-        }
-        return a;
-    };
-    // Position of death number idx > 0 of a pixel-pass whose first death sits at pos1: the other dying
-    // molecules survived up to pos1, then are i.i.d. truncated Exp(1) on the rest of the pass.
-    auto later_death_pos = [&](const uint32_t site, const int r, const int idx, const float pos1, const float hzp) -> float {
-        PhiloxStream rng;
-        rng.init(P.seed, P.offset, env, site, STED_RNG_BLEACH2, (uint32_t)r);
-        rng.ctr.z += (uint32_t)idx;
-        return fminf(pos1 - log1pf(-rng.uniform() * (-expm1f(-(hzp - pos1)))), hzp);
-    };
-    auto remove_taps = [&](const int par, const int xl, const int u, const int lo, const int a) {
-        const float* e = sWt + u * KP;                   // dwells at taps lo .. a-1 no longer see the molecule
-        for (int v = lo; v < a; ++v) {
-            const int cl = xl - v;
-            if (cl >= 0 && cl < TC) atomicAdd(&sCorr[par * TC + cl], __float2int_rn(e[v] * sScale[par * TC + cl]));
-        }
-    };
-    auto push_event = [&](const int par, const int xl, const int u, const int lo, const int a) {
-        if (a <= lo) return;
-        const int q = atomicAdd(&sCnt[2], 1);
-        if (q < S_EVCAP) evq[q] = (uint32_t)xl | ((uint32_t)u << 8) | ((uint32_t)a << 14);
-        else remove_taps(par, xl, u, lo, a);
-    };
-    // First death among the n molecules of a pixel that enters the band with tap row u_entry: hazard budget
-    // Exp(1)/n from the start of that pass.  One draw per (pixel, acquisition).
-    auto schedule_entry = [&](const int y, const int x, const float n, const int u_entry) -> int {
-        const int lo = max(0, x - W + 1), hi = min(K - 1, x);
-        PhiloxStream rng;
-        rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, 0xFFFFu);
-        return find_pass(u_entry, -__logf(rng.uniform()) / n, lo, hi);
-    };
-    // One pixel whose scheduled death falls in pass u of scan row r: place the first death (truncated
-    // Exp(n) on the pass) and emit its event, count the further deaths of the pass (binomial over the n-1
-    // others; each becomes a task), re-schedule the survivors (memoryless: fresh Exp(1)/n_left from the
-    // next pass on).
-    auto process_job = [&](const int r, const int jq, const int xl, const int u) {
-        const int par = r & 1;
-        const int slot = (r + u) % K;
-        const int x = c0 + xl;
-        const int lo = max(0, x - W + 1), hi = min(K - 1, x);
-        const float* ch = sCH + u * KP;
-        const float hzp = ch[lo] - ch[hi + 1];
-        const float n = ring[slot * PR + xl];
-        const uint32_t site = (uint32_t)((r + u) * Wp + x);
-        PhiloxStream rng;
-        rng.init(P.seed, P.offset, env, site, STED_RNG_BLEACH, (uint32_t)r);
-        const float pos1 = fminf(-log1pf(-rng.uniform() * (-expm1f(-n * hzp))) / n, hzp);
-        const int extra = binomial_deaths((int)n - 1, hzp - pos1, rng);
-        const float left = n - (float)(1 + extra);
-        int nd = 255;
-        if (left > 0.f) nd = find_pass(u - 1, -__logf(rng.uniform()) / left, lo, hi);
-        ring[slot * PR + xl] = left;
-        ndr[slot * PR + xl] = (uint8_t)nd;
-        push_event(par, xl, u, lo, tap_of(ch, pos1, lo, hi));
-        if (extra > 0) {
-            // a couple of further deaths are placed right here; long runs (nanodomain pixels) become tasks
-            const int inline_n = (jq >= 0 && extra > 2) ? 0 : extra;
-            for (int i = 0; i < inline_n; ++i)
-                push_event(par, xl, u, lo, tap_of(ch, later_death_pos(site, r, min(i + 1, 4095), pos1, hzp), lo, hi));
-            if (inline_n == 0) {
-                jobpos[par * S_JOBCAP + jq] = pos1;
-                const int q = atomicAdd(&sCnt[2], extra);
-                sCnt[3] = 1;
-                for (int i = 0; i < extra; ++i) {
-                    const int idx = min(i + 1, 4095);
-                    if (q + i < S_EVCAP) evq[q + i] = 0x80000000u | (uint32_t)jq | ((uint32_t)idx << 11);
-                    else remove_taps(par, xl, u, lo, tap_of(ch, later_death_pos(site, r, idx, pos1, hzp), lo, hi));
-                }
-            }
-        }
-    };
-    // Queue pixel (xl, tap row u) as a job of scan row r; a queued pixel is marked 254 in the next-death ring.
-    // When the queue is full the pixel keeps its mark u and is picked up by the rescan in phase B.
-    auto add_job = [&](const int r, const int xl, const int u) {
-        const int par = r & 1;
-        const int q = atomicAdd(&sCnt[par], 1);
-        if (q < S_JOBCAP) {
-            jobq[par * S_JOBCAP + q] = (uint16_t)(xl | (u << 8));
-            ndr[((r + u) % K) * PR + xl] = 254;
-        }
-    };
-    // Scan the next-death ring for pixels whose death falls in scan row r (band rows first_u..K-1 relative to r).
-    auto scan_jobs = [&](const int r, const int u_count) {
-        for (int u = warp; u < u_count; u += S_THREADS / 32) {
-            const uint32_t* nrow = reinterpret_cast<const uint32_t*>(ndr + ((r + u) % K) * PR);
-            const uint32_t pat = 0x01010101u * (uint32_t)u;
-            for (int g4 = lane; g4 < PR / 4; g4 += 32) {
-                const uint32_t diff = nrow[g4] ^ pat;
-                if (((diff - 0x01010101u) & ~diff & 0x80808080u) == 0u) continue;   // no byte equals u
-#pragma unroll 1
-                for (int j = 0; j < 4; ++j)
-                    if (((diff >> (8 * j)) & 0xFFu) == 0u) add_job(r, 4 * g4 + j, u);
-            }
-        }
-    };
-
     // Retire band row y_old to global memory (expectation mode undoes the s = D*exp(CH[u][hi+1]) scaling of
     // the left-clipped columns) and install the prefetched row y_new in the same ring slot.  The same
     // thread owns a group of four columns in both halves, so no barrier is needed in between.
-    auto cycle_row = [&](const int y_old, const int u_scale_old, const int y_new, const int u_entry, const float4 pre,
-                         const bool sched_jobs) {
+    auto cycle_row = [&](const int y_old, const int u_scale_old, const int y_new, const int u_entry, const float4 pre) {
         if (tid < PR / 4) {
             const int xl = 4 * tid, x = c0 + xl;
             if (y_old >= 0) {
@@ -517,47 +502,6 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
                         if (x + j < K - 1 && pv[j] != 0.f) pv[j] *= expf(sCH[u_entry * KP + x + j + 1]);
                 }
                 *reinterpret_cast<float4*>(ring + (y_new % K) * PR + xl) = val;
-                if (STOCH && SWEEP_PROBE == 1) *reinterpret_cast<uint32_t*>(ndr + (y_new % K) * PR + xl) = 0xFFFFFFFFu;
-                if (STOCH && SWEEP_PROBE != 1) {
-                    // schedule the first death of each occupied pixel; deaths due in the very next scan row
-                    // (tap row u_entry) are queued for it right away
-                    uint32_t nd4 = 0xFFFFFFFFu;
-                    const float* pv = reinterpret_cast<const float*>(&val);
-                    const int r_next = y_new - u_entry;
-#pragma unroll 1
-                    for (int j = 0; j < 4; ++j) {
-                        if (pv[j] <= 0.f || x + j >= Wp) continue;
-                        const int nd = schedule_entry(y_new, x + j, pv[j], u_entry);
-                        nd4 = (nd4 & ~(0xFFu << (8 * j))) | ((uint32_t)nd << (8 * j));
-                    }
-                    *reinterpret_cast<uint32_t*>(ndr + (y_new % K) * PR + xl) = nd4;
-                    if (sched_jobs) {
-#pragma unroll 1
-                        for (int j = 0; j < 4; ++j)
-                            if (((nd4 >> (8 * j)) & 0xFFu) == (uint32_t)u_entry) add_job(r_next, xl + j, u_entry);
-                    }
-                }
-            }
-        }
-    };
-    // Stochastic mode handles the band rows one pixel per thread (thread t owns ring column t).
-    auto fetch_px = [&](const int y) -> float {
-        const int x = c0 + tid;
-        return (tid < PR && y >= 0 && y < P.Hp && x < P.Wpitch) ? __ldg(din + (size_t)y * P.Wpitch + x) : 0.f;
-    };
-    auto entry_nd = [&](const int y, const float n, const int u_entry) -> int {
-        const int x = c0 + tid;
-        return (tid < PR && n > 0.f && x < Wp && SWEEP_PROBE != 1) ? schedule_entry(y, x, n, u_entry) : 255;
-    };
-    auto cycle_px = [&](const int y_old, const int y_new, const float n_new, const int nd_new, const int u_entry,
-                        const bool sched_jobs) {
-        if (tid < PR) {
-            const int x = c0 + tid;
-            if (y_old >= 0 && x >= xs && x < xe) dout[(size_t)y_old * P.Wpitch + x] = ring[(y_old % K) * PR + tid];
-            if (y_new >= 0) {
-                ring[(y_new % K) * PR + tid] = n_new;
-                ndr[(y_new % K) * PR + tid] = (uint8_t)nd_new;
-                if (sched_jobs && nd_new == u_entry) add_job(y_new - u_entry, tid, u_entry);
             }
         }
     };
@@ -568,21 +512,6 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
             val = __ldg(reinterpret_cast<const float4*>(din + (size_t)y * P.Wpitch + x));
         return val;
     };
-
-    if (STOCH) {
-        for (int y = 0; y < K; ++y) {
-            const float n = fetch_px(y);
-            cycle_px(-1, y, n, entry_nd(y, n, y), y, false);
-        }
-    } else {
-        for (int y = 0; y < K; ++y) cycle_row(-1, -1, y, y, fetch_row(y), false);
-    }
-    __syncthreads();
-    if (STOCH) {   // jobs of scan row 0
-        scan_jobs(0, K);
-        __syncthreads();
-    }
-
     // writes scan row r (dense gather minus the taps removed by the deaths of that row)
     auto write_row = [&](const int r) {
         if (tid < TC && c0 + tid < W) {
@@ -598,22 +527,34 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         }
     };
 
+    for (int y = 0; y < K; ++y) cycle_row(-1, -1, y, y, fetch_row(y));
+    __syncthreads();
+
 #if SWEEP_PROBE == 2
     long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_last = clock64();
 #define PHASE_MARK(i) do { const long long t_now = clock64(); t_ph[i] += t_now - t_last; t_last = t_now; } while (0)
 #else
 #define PHASE_MARK(i) do { } while (0)
 #endif
+    const int* row_off = STOCH ? ws.off + (size_t)b * H : nullptr;
     for (int r = 0; r < H; ++r) {
         const int par = r & 1;
-        const int y_in = r + K < P.Hp ? r + K : -1;                    // band row that enters after this scan row
-        const float4 pre = STOCH ? make_float4(0.f, 0.f, 0.f, 0.f) : fetch_row(y_in);   // lands while the row is gathered
-        const float pre_px = STOCH ? fetch_px(y_in) : 0.f;
-        // ---------------- phase A: write the previous row; dense gather of scan row r against the row-start state
+        const float4 pre = fetch_row(r + K < P.Hp ? r + K : -1);      // lands while the row is gathered
+        // events of this scan row: the first one of each thread is prefetched too
+        constexpr int EV_LANES = 4, EV_SLOTS = S_THREADS / EV_LANES, EV_PRE = 4;
+        int ev_lo = 0, ev_hi = 0;
+        uint32_t evp[EV_PRE] = {0u, 0u, 0u, 0u};
         if (STOCH) {
+            ev_lo = __ldg(row_off + r); ev_hi = __ldg(row_off + r + 1);
+            if ((unsigned long long)ev_hi > ws.cap) ev_hi = (int)ws.cap;
+#pragma unroll
+            for (int i = 0; i < EV_PRE; ++i) {
+                const int q = ev_lo + tid / EV_LANES + i * EV_SLOTS;
+                if (q < ev_hi) evp[i] = __ldg(ws.ev + q);
+            }
             if (r > 0) write_row(r - 1);
-            if (tid == 0) sCnt[2] = 0;
         }
+        // ---------------- phase A: dense gather of scan row r against the row-start state
         {
             float acc[CT];
 #pragma unroll
@@ -655,8 +596,8 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
         __syncthreads();
         PHASE_MARK(1);
 
+        // ---------------- phase B: thin the band with the taps of this scan row
         if (!STOCH) {
-            // ---------------- expectation mode: thin the band with the taps of this scan row
             for (int u = warp; u < K; u += S_THREADS / 32) {
                 float* row = ring + ((r + u) % K) * PR;
                 for (int xl = lane; xl < span; xl += 32) {
@@ -673,74 +614,42 @@ __global__ void __launch_bounds__(S_THREADS, 2) sweep_kernel(const AcqParams P) 
             }
             __syncthreads();
             write_row(r);
-            cycle_row(r, -1, (r + K < P.Hp) ? r + K : -1, K - 1, pre, false);
-            __syncthreads();
-            continue;
-        }
-
-        // ---------------- phase B: one job per thread (deaths of the pixel-passes due in this scan row)
-        const int nd_in = entry_nd(y_in, pre_px, K - 1);   // ... the low ones schedule the pixels of the entering row
-        {
-            const int total = sCnt[par];
-            const int njobs = min(total, S_JOBCAP);
-            for (int q = S_THREADS - 1 - tid; q < njobs; q += S_THREADS)      // jobs start at the high thread ids ...
-                process_job(r, q, jobq[par * S_JOBCAP + q] & 0xFF, jobq[par * S_JOBCAP + q] >> 8);
-            if (total > S_JOBCAP) {          // queue overflowed: the unqueued pixels still carry their tap row
-                for (int idx = tid; idx < K * PR; idx += S_THREADS) {
-                    const int u = idx / PR, xl = idx - u * PR;
-                    if (ndr[((r + u) % K) * PR + xl] == (uint8_t)u) process_job(r, -1, xl, u);
-                }
-            }
-        }
-        __syncthreads();
-        PHASE_MARK(2);
-
-        // ---------------- phase C: corrections of row r; retire row r / install row r+K; find the jobs of row r+1
-        const int nev = min(sCnt[2], S_EVCAP);
-        if (sCnt[3]) {                       // some queue entries are still tasks: give them their tap first
-            for (int q = tid; q < nev; q += S_THREADS) {
-                const uint32_t ev = evq[q];
-                if (!(ev & 0x80000000u)) continue;
-                const int jq = ev & 0x7FF, idx = (ev >> 11) & 0xFFF;
-                const uint32_t jb = jobq[par * S_JOBCAP + jq];
-                const int xl = jb & 0xFF, u = jb >> 8;
-                const int x = c0 + xl;
-                const int lo = max(0, x - W + 1), hi = min(K - 1, x);
-                const float* ch = sCH + u * KP;
-                const int a = tap_of(ch, later_death_pos((uint32_t)((r + u) * Wp + x), r, idx, jobpos[par * S_JOBCAP + jq],
-                                                         ch[lo] - ch[hi + 1]), lo, hi);
-                evq[q] = (a > lo) ? ((uint32_t)xl | ((uint32_t)u << 8) | ((uint32_t)a << 14)) : 0u;
-            }
-            __syncthreads();
-        }
-        if (tid == 0) { sCnt[par] = 0; sCnt[3] = 0; }
-        PHASE_MARK(3);
-        // one event per thread: the taps after the death (lo .. a-1 of tap row u) leave the row's intensities.
-        // Fixed-point integer atomics: native in shared memory, and the sum does not depend on the order.
-        for (int q = tid; q < nev; q += S_THREADS) {
-            const uint32_t ev = evq[q];
-            const int xl = ev & 0xFF, u = (ev >> 8) & 0x3F, a = (ev >> 14) & 0x3F;
-            const float* e = sWt + u * KP;
+        } else {
+            // replay the pre-drawn deaths of this scan row, one event per thread: the pixel loses a molecule
+            // and the dwells at taps lo .. a-1 of tap row u no longer see it.  Corrections are fixed-point
+            // integer atomics (native in shared memory; the sum does not depend on the order).
+            // Four lanes share an event and split its taps.
             const float* sc = sScale + par * TC;
             int* corr = sCorr + par * TC;
-            const int v0 = max(max(0, c0 + xl - W + 1), xl - (TC - 1)), v1 = min(a, xl + 1);   // keeps 0 <= xl - v < TC
+            const int sub = tid % EV_LANES;
+            int it = 0;
+            for (int q = ev_lo + tid / EV_LANES; q < ev_hi; q += EV_SLOTS, ++it) {
+                uint32_t ev;
+                if (it == 0) ev = evp[0]; else if (it == 1) ev = evp[1]; else if (it == 2) ev = evp[2];
+                else if (it == 3) ev = evp[3]; else ev = __ldg(ws.ev + q);
+                const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F, a = (ev >> 18) & 0x3F;
+                if (xl < 0 || xl >= span) continue;                       // another tile's pixel
+                if (sub == 0) atomicAdd(&ring[((r + u) % K) * PR + xl], -1.0f);
+                const float* e = sWt + u * KP;
+                const int v0 = max(max(0, c0 + xl - W + 1), xl - (TC - 1)), v1 = min(a, xl + 1);   // 0 <= xl - v < TC
 #pragma unroll 4
-            for (int v = v0; v < v1; ++v) atomicAdd(&corr[xl - v], __float2int_rn(e[v] * sc[xl - v]));
+                for (int v = v0 + sub; v < v1; v += EV_LANES) atomicAdd(&corr[xl - v], __float2int_rn(e[v] * sc[xl - v]));
+            }
+            PHASE_MARK(2);
+            __syncthreads();
         }
-        PHASE_MARK(4);
-        cycle_px(r, y_in, pre_px, nd_in, K - 1, true);
-        PHASE_MARK(5);
-        if (r + 1 < H && SWEEP_PROBE != 1) scan_jobs(r + 1, K - 1);          // rows r+1 .. r+K-1; row r+K is queued by cycle_row
-        PHASE_MARK(6);
+        PHASE_MARK(3);
+        // ---------------- retire band row y = r, install row r + K
+        cycle_row(r, -1, (r + K < P.Hp) ? r + K : -1, K - 1, pre);
         __syncthreads();
-        PHASE_MARK(7);
+        PHASE_MARK(4);
     }
 #if SWEEP_PROBE == 2
     if (tid == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)t_ph[i]);
 #endif
     if (STOCH) write_row(H - 1);
     // flush the K-1 band rows below the last scan row (tap row they would have had next: y - H)
-    for (int y = H; y < P.Hp; ++y) cycle_row(y, y - H, -1, 0, make_float4(0.f, 0.f, 0.f, 0.f), false);
+    for (int y = H; y < P.Hp; ++y) cycle_row(y, y - H, -1, 0, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -800,6 +709,7 @@ int make_params(AcqParams& P, const float* din, float* dout, const float* tables
     if (K < 1 || (K & 1) == 0) return fail(STED_EINVAL, "K must be odd (got %d)", K);
     if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
     if (H > 65535) return fail(STED_EUNSUPPORTED, "H=%d exceeds 65535 scan rows", H);
+    if (W + K - 1 > 4095) return fail(STED_EUNSUPPORTED, "W=%d exceeds the 4095-column limit of the event encoding", W);
     if ((flags & STED_BLEACH) && (!dout || dout == din))
         return fail(STED_EINVAL, "bleaching needs dmap_out_dev distinct from dmap_in_dev");
     if (!(lambda_fluo > 0)) return fail(STED_EINVAL, "lambda_fluo must be positive");
@@ -835,30 +745,56 @@ int launch_gather(const AcqParams& P, cudaStream_t st) {
 }
 
 template <int KT, int CT, bool STOCH>
-int launch_sweep_t(const AcqParams& P, cudaStream_t st) {
+int launch_sweep_t(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     constexpr int TC = 8 * CT;
     const int PR = sweep_pitch(TC, P.KP);
-    size_t words = (size_t)P.K * PR + 2 * (size_t)P.K * P.KP + 2 * TC;
-    if (STOCH) words += ((P.K + 1 + 3) & ~3) + ((size_t)P.K * PR + 3) / 4 + 6 * TC + 4 + S_EVCAP + 2 * S_JOBCAP + S_JOBCAP;
-    else words += (size_t)P.K * P.KP;
+    size_t words = (size_t)P.K * PR + (size_t)P.K * P.KP + 6 * TC;
+    if (!STOCH) words += 2 * (size_t)P.K * P.KP;
     const size_t smem = words * sizeof(float);
     dim3 grid((P.W + TC - 1) / TC, P.B);
     int rc;
     if ((rc = set_smem(sweep_kernel<KT, CT, STOCH>, smem))) return rc;
-    sweep_kernel<KT, CT, STOCH><<<grid, S_THREADS, smem, st>>>(P);
+    sweep_kernel<KT, CT, STOCH><<<grid, S_THREADS, smem, st>>>(P, ws);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }
 
 template <bool STOCH>
-int launch_sweep_m(const AcqParams& P, cudaStream_t st) {
+int launch_sweep_m(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     const bool wide = P.W > 64;
-    if (P.K == 59) return wide ? launch_sweep_t<59, 16, STOCH>(P, st) : launch_sweep_t<59, 8, STOCH>(P, st);
-    return wide ? launch_sweep_t<0, 16, STOCH>(P, st) : launch_sweep_t<0, 8, STOCH>(P, st);
+    if (P.K == 59) return wide ? launch_sweep_t<59, 16, STOCH>(P, ws, st) : launch_sweep_t<59, 8, STOCH>(P, ws, st);
+    return wide ? launch_sweep_t<0, 16, STOCH>(P, ws, st) : launch_sweep_t<0, 8, STOCH>(P, ws, st);
 }
 
-int launch_sweep(const AcqParams& P, cudaStream_t st) {
-    return (P.flags & STED_SAMPLE_BLEACH) ? launch_sweep_m<true>(P, st) : launch_sweep_m<false>(P, st);
+// bytes of workspace the stochastic scan needs for B environments of H rows and at most max_events deaths
+size_t bleach_ws_bytes(int B, int H, unsigned long long max_events) {
+    return 16 + ((size_t)B * H * 2 + 4) * sizeof(int) + (size_t)max_events * sizeof(uint32_t);
+}
+
+int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    BleachWs ws{};
+    if (!(P.flags & STED_SAMPLE_BLEACH)) return launch_sweep_m<false>(P, ws, st);
+    const size_t fixed = bleach_ws_bytes(P.B, P.H, 0);
+    if (!workspace || workspace_bytes < fixed + 4)
+        return fail(STED_EINVAL, "stochastic bleaching needs a workspace of at least %zu bytes (see sted_bleach_workspace_bytes)",
+                    fixed + 4);
+    const int n = P.B * P.H;
+    ws.status = reinterpret_cast<int*>(workspace);
+    ws.cnt = ws.status + 4;
+    ws.off = ws.cnt + n;
+    ws.ev = reinterpret_cast<uint32_t*>(ws.off + n + 4);
+    ws.cap = (workspace_bytes - fixed) / sizeof(uint32_t);
+    if (ws.cap > 0x7FFFFFFFull) ws.cap = 0x7FFFFFFFull;
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, 16 + (size_t)n * sizeof(int), st));
+    const size_t psmem = ((size_t)P.K * P.KP + P.K + 4) * sizeof(float);
+    dim3 pgrid((unsigned)((P.H * P.W + 255) / 256 < 128 ? (P.H * P.W + 255) / 256 : 128), P.B);
+    presample_kernel<false><<<pgrid, 256, psmem, st>>>(P, ws);
+    CUDA_TRY(cudaGetLastError());
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(ws, n);
+    CUDA_TRY(cudaGetLastError());
+    presample_kernel<true><<<pgrid, 256, psmem, st>>>(P, ws);
+    CUDA_TRY(cudaGetLastError());
+    return launch_sweep_m<true>(P, ws, st);
 }
 
 int launch_detect(const AcqParams& P, cudaStream_t st) {
@@ -873,8 +809,8 @@ int launch_detect(const AcqParams& P, cudaStream_t st) {
 // growable device workspace for the *_host entry points
 struct Workspace {
     std::mutex mu;
-    void* dev[8] = {nullptr};
-    size_t cap[8] = {0};
+    void* dev[9] = {nullptr};
+    size_t cap[9] = {0};
     int ensure(int slot, size_t bytes) {
         if (cap[slot] >= bytes) return STED_OK;
         if (dev[slot]) cudaFree(dev[slot]);
@@ -944,7 +880,7 @@ int sted_make_effective(const double* psf_cache_dev, const StedFluoParams* fluo_
 int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tables_dev, const double* pdt_dev,
                  int B, int H, int W, int K, uint32_t flags, const StedDetectorParams* det, double lambda_fluo,
                  uint64_t seed, uint64_t offset, int64_t env_base, float* intensity_dev, float* signal_dev,
-                 void* stream) {
+                 void* workspace_dev, uint64_t workspace_bytes, void* stream) {
     AcqParams P;
     int rc = make_params(P, dmap_in_dev, dmap_out_dev, tables_dev, pdt_dev, B, H, W, K, flags, det, lambda_fluo, seed,
                          offset, env_base, intensity_dev, signal_dev);
@@ -963,10 +899,24 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
         Q.intensity = P.intensity ? P.intensity + im : nullptr;
         Q.signal = P.signal + im;
         Q.env_base = P.env_base + (uint32_t)b0;
-        rc = (flags & STED_BLEACH) ? launch_sweep(Q, (cudaStream_t)stream) : launch_gather(Q, (cudaStream_t)stream);
+        rc = (flags & STED_BLEACH) ? launch_sweep(Q, workspace_dev, (size_t)workspace_bytes, (cudaStream_t)stream)
+                                   : launch_gather(Q, (cudaStream_t)stream);
         if (rc) return rc;
         if (!(flags & STED_NO_DETECT) && (rc = launch_detect(Q, (cudaStream_t)stream))) return rc;
     }
+    return STED_OK;
+}
+
+uint64_t sted_bleach_workspace_bytes(int B, int H, uint64_t max_events) {
+    return (uint64_t)bleach_ws_bytes(B, H, max_events);
+}
+
+int sted_bleach_dropped_events(const void* workspace_dev, int* dropped_host, void* stream) {
+    if (!workspace_dev || !dropped_host) return fail(STED_EINVAL, "null pointer argument");
+    int rc = check_device();
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dropped_host, workspace_dev, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return STED_OK;
 }
 
@@ -1001,7 +951,11 @@ int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const Sted
     std::lock_guard<std::mutex> lock(g_ws.mu);
     const int KP = STED_KPITCH(K), Hp = H + K - 1, Wp = W + K - 1, Wpitch = (Wp + 3) & ~3, p = K / 2;
     const size_t n_roi = (size_t)B * H * W, n_pad = (size_t)B * Hp * Wpitch;
-    enum { ROI, PADA, PADB, TAB, CACHE, FLUO, SCAL, OUT };
+    enum { ROI, PADA, PADB, TAB, CACHE, FLUO, SCAL, OUT, WS };
+    const bool stoch = (flags & STED_BLEACH) && (flags & STED_SAMPLE_BLEACH);
+    // scratch of the stochastic scan: starts at 4 deaths per pixel and grows when a scan reports dropped events
+    static unsigned long long s_max_events = 0;
+    if (stoch && s_max_events < 4ull * n_roi) s_max_events = 4ull * n_roi;
     if ((rc = g_ws.ensure(ROI, n_roi * 4)) || (rc = g_ws.ensure(PADA, n_pad * 4)) ||
         (rc = g_ws.ensure(PADB, (flags & STED_BLEACH) ? n_pad * 4 : 16)) ||
         (rc = g_ws.ensure(TAB, (size_t)B * STED_TABLES * K * KP * 4)) || (rc = g_ws.ensure(CACHE, 3ull * K * K * 8)) ||
@@ -1027,9 +981,23 @@ int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const Sted
     pad_kernel<<<592, 256, 0, st>>>(d_roi, d_a, B, H, W, p, Hp, Wpitch);
     CUDA_TRY(cudaGetLastError());
     if ((rc = sted_make_effective(d_cache, d_fluo, d_scal, d_scal + B, d_scal + 2 * B, B, K, d_tab, nullptr, st))) return rc;
-    if ((rc = sted_acquire(d_a, (flags & STED_BLEACH) ? d_b : nullptr, d_tab, d_scal + 2 * B, B, H, W, K, flags, det,
-                           fluo_host[0].lambda_fluo, seed, offset, env_base, intensity_host ? d_int : nullptr, d_sig, st)))
-        return rc;
+    for (int attempt = 0;; ++attempt) {
+        size_t ws_bytes = 0;
+        if (stoch) {
+            ws_bytes = bleach_ws_bytes(B, H, s_max_events);
+            if ((rc = g_ws.ensure(WS, ws_bytes))) return rc;
+        }
+        if ((rc = sted_acquire(d_a, (flags & STED_BLEACH) ? d_b : nullptr, d_tab, d_scal + 2 * B, B, H, W, K, flags, det,
+                               fluo_host[0].lambda_fluo, seed, offset, env_base, intensity_host ? d_int : nullptr, d_sig,
+                               stoch ? g_ws.dev[WS] : nullptr, ws_bytes, st)))
+            return rc;
+        if (!stoch) break;
+        int dropped = 0;
+        if ((rc = sted_bleach_dropped_events(g_ws.dev[WS], &dropped, st))) return rc;
+        if (dropped == 0) break;
+        if (attempt >= 8) return fail(STED_ECUDA, "stochastic scan kept overflowing its event scratch");
+        s_max_events = s_max_events * 2 + (unsigned long long)dropped;     // same seed => same deaths on the re-run
+    }
     if (flags & STED_BLEACH) {
         unpad_kernel<<<592, 256, 0, st>>>(d_b, d_roi, B, H, W, p, Hp, Wpitch);
         CUDA_TRY(cudaGetLastError());

@@ -128,7 +128,16 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
                  const double* pdt_dev, int B, int H, int W, int K, uint32_t flags,
                  const StedDetectorParams* det, double lambda_fluo,
                  uint64_t seed, uint64_t offset, int64_t env_base,
-                 float* intensity_dev, float* signal_dev, void* stream);
+                 float* intensity_dev, float* signal_dev,
+                 void* workspace_dev, uint64_t workspace_bytes, void* stream);
+
+/* Scratch for STED_BLEACH|STED_SAMPLE_BLEACH: the deaths of the whole scan are drawn before it and
+ * bucketed by scan row.  max_events bounds the number of molecules that can bleach (the total
+ * molecule count of the B maps is always enough).  Other modes accept workspace_dev = NULL. */
+uint64_t sted_bleach_workspace_bytes(int B, int H, uint64_t max_events);
+/* Number of deaths the last stochastic scan could not store (0 unless max_events was too small;
+ * a non-zero value means that scan's outputs are invalid).  Synchronises `stream`. */
+int sted_bleach_dropped_events(const void* workspace_dev, int* dropped_host, void* stream);
 
 /* Detector.get_signal on its own (gym_sted/utils.py:654-657): converts detected power (W), as left
  * in signal_dev by sted_acquire(..., STED_NO_DETECT), to photon counts in place:

@@ -35,7 +35,7 @@ def timeit(name, fn, n=5):
     extra = ""
     if sum(ph):
         tot = sum(ph)
-        extra = "  G/wait/B/place/corr/cycle/scan/wait %: " + " ".join(f"{100 * x / tot:.0f}" for x in list(ph)[:8]) + f"  cyc/row/cta {tot / (n + 2) / B / max(1, (W + 127) // 128) / H:.0f}"
+        extra = "  G/wait/replay/wait/cycle %: " + " ".join(f"{100 * x / tot:.0f}" for x in list(ph)[:8]) + f"  cyc/row/cta {tot / (n + 2) / B / max(1, (W + 127) // 128) / H:.0f}"
     print(f"{name:48s} {np.median(ts):8.3f} ms{extra}", flush=True)
 
 

@@ -139,3 +139,58 @@ def sweep_stochastic_scheduled(D, H, W, E, A, rng):
         if r + K < Hp:
             enter(r + K, K - 1)
     return out, D
+
+
+def presample_events(D, H, W, A, rng):
+    """Twin of presample_kernel: for every occupied pixel draw Binomial(n, 1-exp(-H_tot)) deaths and place
+    each on its (scan row, tap) by inverting the cumulative hazard along the passes (tap rows u from
+    min(K-1,y) down to max(0,y-H+1)) and, inside the pass, along the taps hi..lo.  Returns a list of
+    (r, y, x, u, a): the molecule of pixel (y,x) dies at tap a of tap row u during scan row r."""
+    K = A.shape[0]
+    CH = np.zeros((K, K + 1))
+    CH[:, :K] = np.cumsum(A[:, ::-1], axis=1)[:, ::-1]
+    events = []
+    ys, xs = np.nonzero(D)
+    for y, x in zip(ys, xs):
+        n = int(D[y, x])
+        lo, hi = max(0, x - W + 1), min(K - 1, x)
+        u_hi, u_lo = min(K - 1, y), max(0, y - (H - 1))
+        if lo > hi or u_lo > u_hi:
+            continue
+        hz = np.array([CH[u, lo] - CH[u, hi + 1] for u in range(u_hi, u_lo - 1, -1)])   # in visiting order
+        htot = hz.sum()
+        if htot <= 0:
+            continue
+        dead = rng.binomial(n, -np.expm1(-htot))
+        cum = np.cumsum(hz)
+        for _ in range(dead):
+            t = -np.log1p(-rng.random() * -np.expm1(-htot))
+            k = min(int(np.searchsorted(cum, t)), len(hz) - 1)
+            u = u_hi - k
+            pos = t - (cum[k] - hz[k])
+            cand = np.nonzero(CH[u, lo:hi + 1] >= pos + CH[u, hi + 1])[0]
+            a = lo + (cand.max() if len(cand) else 0)
+            events.append((y - u, y, x, u, a))
+    return events
+
+
+def sweep_stochastic_presampled(D, H, W, E, A, rng):
+    """Twin of the stochastic sweep_kernel: dense gather of each scan row against the row-start counts, then
+    replay of that row's pre-drawn deaths (count decrement + removal of the taps lo..a-1)."""
+    K = E.shape[0]
+    D = D.astype(np.int64).copy()
+    by_row = [[] for _ in range(H)]
+    for ev in presample_events(D, H, W, A, rng):
+        by_row[ev[0]].append(ev)
+    out = np.zeros((H, W))
+    for r in range(H):
+        band = D[r:r + K]
+        row = np.array([(E * band[:, c:c + K]).sum() for c in range(W)])
+        for (_, y, x, u, a) in by_row[r]:
+            D[y, x] -= 1
+            for v in range(max(0, x - W + 1), a):
+                c = x - v
+                if 0 <= c < W:
+                    row[c] -= E[u, v]
+        out[r] = row
+    return out, D

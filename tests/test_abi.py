@@ -58,9 +58,9 @@ def test_argument_validation_happens_before_device_use():
     buf = np.zeros(16, dtype=np.float32)
     p = buf.ctypes.data
     # even K is rejected as EINVAL, K > STED_MAX_K as EUNSUPPORTED, in-place bleaching as EINVAL
-    assert lib.sted_acquire(p, p, p, p, 1, 4, 4, 4, 0, ctypes.byref(det), 690e-9, 0, 0, 0, None, p, None) == -1
-    assert lib.sted_acquire(p, p, p, p, 1, 4, 4, 65, 0, ctypes.byref(det), 690e-9, 0, 0, 0, None, p, None) == -4
-    assert lib.sted_acquire(p, p, p, p, 1, 4, 4, 5, 1, ctypes.byref(det), 690e-9, 0, 0, 0, None, p, None) == -1
+    assert lib.sted_acquire(p, p, p, p, 1, 4, 4, 4, 0, ctypes.byref(det), 690e-9, 0, 0, 0, None, p, None, 0, None) == -1
+    assert lib.sted_acquire(p, p, p, p, 1, 4, 4, 65, 0, ctypes.byref(det), 690e-9, 0, 0, 0, None, p, None, 0, None) == -4
+    assert lib.sted_acquire(p, p, p, p, 1, 4, 4, 5, 1, ctypes.byref(det), 690e-9, 0, 0, 0, None, p, None, 0, None) == -1
     assert b"distinct" in lib.sted_last_error()
     assert lib.sted_make_effective(None, p, p, p, p, 1, 5, p, None, None) == -1
 
@@ -72,7 +72,7 @@ def test_no_cpu_fallback_without_device():
     det = _lib.StedDetectorParams(0.1, 0.5, 0.0)
     buf = np.zeros(4096, dtype=np.float32)
     p = buf.ctypes.data
-    rc = lib.sted_acquire(p, None, p, p, 1, 4, 4, 5, 0, ctypes.byref(det), 690e-9, 0, 0, 0, None, p, None)
+    rc = lib.sted_acquire(p, None, p, p, 1, 4, 4, 5, 0, ctypes.byref(det), 690e-9, 0, 0, 0, None, p, None, 0, None)
     assert rc == -2 and b"no CPU fallback" in lib.sted_last_error()
     with pytest.raises(_lib.StedError):
         _lib.check(rc)

@@ -125,7 +125,7 @@ def test_gather_generic_psf_size(micro):
         d_sig = torch.empty_like(d_int)
         det = _lib.StedDetectorParams(0.1, 0.5, 0.0)
         _lib.check(lib.sted_acquire(d_D.data_ptr(), None, d_tab.data_ptr(), d_pdt.data_ptr(), B, H, W, K, 0,
-                                    ctypes.byref(det), 690e-9, 1, 1, 0, d_int.data_ptr(), d_sig.data_ptr(), None))
+                                    ctypes.byref(det), 690e-9, 1, 1, 0, d_int.data_ptr(), d_sig.data_ptr(), None, 0, None))
         got = d_int.cpu().numpy()
         for b in range(B):
             work = D[b, :, :Wp].astype(np.float64).copy()
@@ -189,7 +189,7 @@ def test_sweep_generic_psf_edge_shapes(micro):
         det = _lib.StedDetectorParams(0.1, 0.5, 0.0)
         _lib.check(lib.sted_acquire(d_D.data_ptr(), d_out.data_ptr(), d_tab.data_ptr(), d_pdt.data_ptr(), B, H, W, K,
                                     _lib.STED_BLEACH, ctypes.byref(det), 690e-9, 1, 1, 0, d_int.data_ptr(),
-                                    d_sig.data_ptr(), None))
+                                    d_sig.data_ptr(), None, 0, None))
         got_i, got_d = d_int.cpu().numpy(), d_out.cpu().numpy()
         for b in range(B):
             work = D[b, :, :Wp].astype(np.float64).copy()

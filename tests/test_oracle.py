@@ -115,17 +115,19 @@ def test_rowsweep_expectation_equals_sequential_scan(H, W, K):
     np.testing.assert_allclose(Db, ref_D, rtol=1e-12, atol=1e-13)
 
 
-@pytest.mark.parametrize("variant", ["binomial_per_pass", "scheduled_deaths"])
+@pytest.mark.parametrize("variant", ["binomial_per_pass", "scheduled_deaths", "presampled"])
 def test_rowsweep_stochastic_matches_sequential_moments(variant):
-    """Both row-sweep samplers — one binomial per (pixel, scan row), and the next-death schedule the CUDA
-    kernel uses — have the same image / datamap moments as the reference's per-dwell per-molecule thinning."""
+    """Three exact re-orderings of the reference's per-dwell per-molecule thinning — one binomial per (pixel,
+    scan row); a next-death schedule; and the one the CUDA kernels use, all deaths drawn before the scan and
+    replayed row by row — give the same image / datamap moments as the sequential oracle."""
     rng = np.random.default_rng(7)
     H, W, K = 6, 7, 5
     E, A = rng.random((K, K)), rng.random((K, K)) * 0.2
     p = K // 2
     D = np.zeros((H + K - 1, W + K - 1))
     D[p:p + H, p:p + W] = rng.integers(0, 30, (H, W)) * (rng.random((H, W)) < 0.6)
-    fn = rm.sweep_stochastic if variant == "binomial_per_pass" else rm.sweep_stochastic_scheduled
+    fn = {"binomial_per_pass": rm.sweep_stochastic, "scheduled_deaths": rm.sweep_stochastic_scheduled,
+          "presampled": rm.sweep_stochastic_presampled}[variant]
     N = 1500
     a = np.zeros((N, H, W)); b = np.zeros((N, H, W))
     da = np.zeros((N,) + D.shape); db = np.zeros((N,) + D.shape)
