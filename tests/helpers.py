@@ -54,3 +54,12 @@ def synthetic_datamap(rng, H, W, density=0.14, molecules=5, n_domains=6, domain=
         for i in rng.choice(len(ys), size=min(n_domains, len(ys)), replace=False):
             d[ys[i], xs[i]] = rng.integers(domain[0], domain[1] + 1)
     return d
+
+
+def load_demonstrations():
+    """The reference's recorded episodes (tests/golden/make_golden.py): dict of arrays, 50 records."""
+    z = np.load(os.path.join(GOLDEN, "demonstrations.npz"))
+    out = {k: z[k] for k in z.files}
+    out["fg_c"] = np.unpackbits(out["fg_c"], axis=-1).astype(bool)
+    out["fg_s"] = np.unpackbits(out["fg_s"], axis=-1).astype(bool)
+    return out
