@@ -17,30 +17,11 @@
 #include "../../include/sted_b200.h"
 #include "philox.cuh"
 
+#include "common.cuh"
+
+thread_local char sted_err_buf[512] = "";
+
 namespace {
-
-// ------------------------------------------------------------------------------------------
-// error plumbing
-// ------------------------------------------------------------------------------------------
-thread_local char g_err[512] = "";
-
-int fail(int code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-#define CUDA_TRY(expr)                                                                      \
-    do {                                                                                    \
-        cudaError_t _e = (expr);                                                            \
-        if (_e != cudaSuccess)                                                              \
-            return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver        \
-                            ? STED_ENODEVICE : STED_ECUDA,                                  \
-                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
-                        __LINE__);                                                          \
-    } while (0)
 
 constexpr double kPlanck = 6.62607015e-34;
 constexpr double kLight = 299792458.0;
@@ -690,17 +671,6 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-int check_device() {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        cudaGetLastError();
-        return fail(STED_ENODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
-                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    }
-    return STED_OK;
-}
-
 int make_params(AcqParams& P, const float* din, float* dout, const float* tables, const double* pdt, int B, int H,
                 int W, int K, uint32_t flags, const StedDetectorParams* det, double lambda_fluo, uint64_t seed,
                 uint64_t offset, int64_t env_base, float* intensity, float* signal) {
@@ -853,7 +823,7 @@ __global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict
 extern "C" {
 
 const char* sted_version(void) { return "sted_b200 0.1 (sm_100a)"; }
-const char* sted_last_error(void) { return g_err; }
+const char* sted_last_error(void) { return sted_err_buf; }
 
 int sted_device_count(void) {
     int n = 0;

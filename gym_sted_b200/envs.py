@@ -1,0 +1,311 @@
+"""ContextualMOSTED environments on the batched CUDA path.
+
+``VectorContextualMOSTED`` steps B independent environments per call with the acquisition schedule of
+``ContextualSTEDMultiObjectivesEnv.step`` (``gym_sted/envs/contextual_sted_env.py:49-93`` +
+``mosted_env.py:168-246``): conf1 -> STED (+bleach, datamap mutated) -> conf2 -> foregrounds ->
+[Resolution, Bleach, SNR] -> nanodomain F1 reward -> observation packing -> fresh datamap + confocal.
+``ContextualSTEDMultiObjectivesEnv`` is the single-environment (B = 1) gym-API view of it and ``make``
+resolves the reference's ids (``gym_sted/__init__.py:587-610,665-674``); ``gym`` itself is not installed in
+this image, so ``Box``/``Tuple`` below are minimal stand-ins for ``gym.spaces``.
+
+Deviations, all because of un-vendored dependencies of the reference: synapses come from
+``synapse.generate`` (stand-in for ``pysted.exp_data_gen.Synapse``); ``bleach_sampling`` "uniform"/"choice"
+draw the targets of ``defaults.fluorescence_criterions`` but solve ``sigma_abs`` and ``k1`` in closed form
+with ``b`` fixed (the reference's 25x L-BFGS-B ``FluorescenceOptimizer`` is a "next" row).
+"""
+from __future__ import annotations
+
+import random
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import base, defaults, rewards, synapse
+from .batch import BatchedMicroscope
+
+OBJ_NAMES = ["Resolution", "Bleach", "SNR"]
+
+
+class Box:
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.low = np.broadcast_to(np.asarray(low, dtype=dtype), shape if shape is not None else np.shape(low)).copy()
+        self.high = np.broadcast_to(np.asarray(high, dtype=dtype), self.low.shape).copy()
+        self.shape, self.dtype = self.low.shape, np.dtype(dtype)
+
+    def sample(self, rng=None):
+        rng = rng or np.random.default_rng()
+        return rng.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+
+class Tuple(tuple):
+    def __new__(cls, spaces):
+        return super().__new__(cls, spaces)
+
+
+class Normalizer:
+    """``gym_sted/utils.py:414-440``: (x - low) / (high - low), un-clipped."""
+
+    def __init__(self, names, scales):
+        self.low = np.array([scales[n]["low"] for n in names], dtype=np.float64)
+        self.span = np.array([scales[n]["high"] - scales[n]["low"] for n in names], dtype=np.float64)
+
+    def __call__(self, x):
+        return (np.asarray(x, dtype=np.float64) - self.low) / self.span
+
+
+def make_microscope(fluo=None, detector=None):
+    """``MicroscopeGenerator.generate_microscope`` (``gym_sted/utils.py:151-166``)."""
+    return base.Microscope(base.GaussianBeam(**defaults.LASER_EX), base.DonutBeam(**defaults.LASER_STED),
+                           base.Detector(**(detector or defaults.DETECTOR)), base.Objective(**defaults.OBJECTIVE),
+                           base.Fluorescence(**(fluo or defaults.FLUO)), load_cache=True)
+
+
+class BleachSampler:
+    """``gym_sted/utils.py:271-376`` (modes constant / uniform / choice; see the module docstring)."""
+
+    def __init__(self, mode, value=None, routine=None, seed=None, criterions=None):
+        self.rng = random.Random(seed)
+        self.mode, self.value = mode, value
+        if isinstance(routine, str):
+            self.value = defaults.load_routine(routine)
+        self.criterions = criterions or defaults.fluorescence_criterions
+        if mode not in ("constant", "uniform", "choice"):
+            raise ValueError(f"unknown bleach sampling mode {mode!r}")
+        self._anchor = None
+
+    def _draw(self, v):
+        if isinstance(v, (list, tuple)):
+            if self.mode == "choice":
+                return float(self.rng.choice(list(np.linspace(*v, 5))))
+            return self.rng.uniform(*v)
+        return v
+
+    def sample(self, microscope=None):
+        if self.mode == "constant":
+            return self.value or defaults.FLUO
+        crit = {k: {kk: self._draw(vv) for kk, vv in v.items()} for k, v in self.criterions.items()}
+        fluo = {k: (dict(v) if isinstance(v, dict) else v) for k, v in defaults.FLUO.items()}
+        if self._anchor is None:
+            self._anchor = _ClosedForms(microscope or make_microscope())
+        s, bl = crit["signal"], crit["bleach"]
+        fluo["sigma_abs"][635] = self._anchor.sigma_abs_for(s["p_ex"], s["pdt"], s["target"])
+        fluo["k1"] = self._anchor.k1_for(fluo["sigma_abs"][635], bl["p_ex"], bl["p_sted"], bl["pdt"], bl["target"])
+        return fluo
+
+
+class _ClosedForms:
+    """The reference's own closed forms (``gym_sted/utils.py:599-661``) are linear in ``sigma_abs`` (signal)
+    and in ``k1`` (bleach hazard) once ``b`` is fixed, so both are solved directly from one evaluation."""
+
+    def __init__(self, microscope, factor=2.25, scale=40.0):
+        import scipy.ndimage as ndi
+        self.m = microscope
+        K = microscope.cache(defaults.PIXELSIZE)[0].shape[0]
+        blob = np.zeros((K, K))
+        blob[K // 2, K // 2] = 1
+        blob = ndi.gaussian_filter(blob, factor, mode="nearest", truncate=4.0)
+        self.blob = blob / blob.max() * scale
+
+    def sigma_abs_for(self, p_ex, pdt, target):
+        m = self.m
+        E = m.get_effective(defaults.PIXELSIZE, p_ex, 0.0)
+        photons = float((E * self.blob).sum()) / (6.62607015e-34 * 299792458.0 / m.fluo.lambda_)
+        signal = photons * m.detector.pcef * m.detector.pdef * pdt
+        return m.fluo.get_sigma_abs(m.excitation.lambda_) * target / signal
+
+    def k1_for(self, sigma_abs, p_ex, p_sted, pdt, target):
+        m = self.m
+        kb = m.get_k_bleach(defaults.PIXELSIZE, p_ex, p_sted, pdt)
+        hazard = float(kb.sum()) * pdt * sigma_abs / m.fluo.get_sigma_abs(m.excitation.lambda_)
+        return m.fluo.k1 * (-np.log(1.0 - target)) / hazard
+
+
+class VectorContextualMOSTED:
+    """B ContextualMOSTED environments stepped together on one GPU."""
+
+    obj_names = OBJ_NAMES
+
+    def __init__(self, num_envs=1, bleach_sampling="constant", actions=("p_sted", "p_ex", "pdt"), max_episode_steps=10,
+                 scale_nanodomain_reward=1.0, normalize_observations=True, image_size=64, device="cuda", seed=None,
+                 env_base=0, compute_f1=True):
+        self.B, self.H, self.W = int(num_envs), int(image_size), int(image_size)
+        self.actions = list(actions)
+        self.max_episode_steps = int(max_episode_steps)
+        self.scale_nanodomain_reward = scale_nanodomain_reward
+        self.normalize_observations = normalize_observations
+        self.compute_f1 = compute_f1
+        self.device = torch.device(device)
+        self.env_base = int(env_base)
+        self.np_rng = np.random.default_rng(seed)
+        low = np.array([defaults.action_spaces[n]["low"] for n in self.actions], dtype=np.float32)
+        high = np.array([defaults.action_spaces[n]["high"] for n in self.actions], dtype=np.float32)
+        self.action_space = Box(low, high, dtype=np.float32)
+        vec = (len(OBJ_NAMES) + len(self.actions)) * self.max_episode_steps
+        self.observation_space = Tuple((Box(0, 2 ** 16, shape=(self.H, self.W, 3), dtype=np.uint16),
+                                        Box(0, 1024, shape=(vec,), dtype=np.float32)))
+        self.action_normalizer = Normalizer(self.actions, defaults.action_spaces)
+        self.obj_normalizer = Normalizer(OBJ_NAMES, defaults.scales_dict)
+        self.microscope = make_microscope()
+        if isinstance(bleach_sampling, dict):
+            self.bleach_sampler = BleachSampler(**bleach_sampling)
+        else:
+            self.bleach_sampler = BleachSampler(mode=bleach_sampling)
+        self.bm = BatchedMicroscope(self.microscope, self.B, self.H, self.W, defaults.PIXELSIZE, device=self.device,
+                                    env_base=self.env_base, seed=int(self.np_rng.integers(0, 2 ** 31 - 1)))
+        self.conf = (defaults.PDT, defaults.P_EX, 0.0)            # generate_params(): pdt, p_ex, p_sted
+        self.current_step = 0
+        self.synapses = None
+        self.state = None
+        self.episode_memory = {"actions": [], "mo_objs": [], "reward": []}
+
+    # ------------------------------------------------------------------ helpers
+    def _new_datamaps(self):
+        """``_update_datamap`` (mosted_env.py:168-187): new synapse, new datamap, confocal image of it."""
+        self.synapses = [synapse.generate(self.H, self.W, seed=int(self.np_rng.integers(0, 2 ** 63 - 1)))
+                         for _ in range(self.B)]
+        frames = np.stack([s.frame for s in self.synapses])
+        self.bm.set_datamaps(torch.from_numpy(frames), max_molecules=int(frames.sum()))
+        state, _ = self.bm.get_signal_and_bleach(*self.conf, bleach=False)
+        return state
+
+    def _full_action(self, action):
+        cols = {n: action[:, self.actions.index(n)] if n in self.actions else
+                np.full(self.B, getattr(defaults, n.upper())) for n in ("pdt", "p_ex", "p_sted")}
+        return cols["pdt"].astype(np.float64), cols["p_ex"].astype(np.float64), cols["p_sted"].astype(np.float64)
+
+    @staticmethod
+    def _u16(x: torch.Tensor) -> torch.Tensor:
+        # numpy's int64 -> uint16 cast wraps modulo 2^16 (contextual_sted_env.py:93)
+        return (x.to(torch.int64) & 0xFFFF).to(torch.int32)
+
+    # ------------------------------------------------------------------ gym API
+    def reset(self, seed=None, options=None):
+        if seed is not None:
+            self.np_rng = np.random.default_rng(seed)
+        fluos = [base.Fluorescence(**self.bleach_sampler.sample(self.microscope)) for _ in range(self.B)] \
+            if self.bleach_sampler.mode != "constant" else None
+        if fluos is None:
+            self.microscope = make_microscope(self.bleach_sampler.sample())
+            self.bm.microscope = self.microscope
+        self.bm.set_fluorophores(fluos)
+        self.current_step = 0
+        self.episode_memory = {"actions": [], "mo_objs": [], "reward": []}
+        state = self._new_datamaps()
+        zeros = torch.zeros_like(state)
+        self.state = torch.stack((state, zeros, zeros), dim=-1)
+        img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+        vec = np.zeros((self.B, self.observation_space[1].shape[0]), dtype=np.float32)
+        return (img, vec), {}
+
+    def step(self, action):
+        action = np.clip(np.asarray(action, dtype=np.float32).reshape(self.B, len(self.actions)),
+                         self.action_space.low, self.action_space.high)
+        pdt, p_ex, p_sted = self._full_action(action)
+        bm = self.bm
+        conf1, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)
+        sted, _ = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True)
+        conf2, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)
+        bleached = bm.datamaps_roi().clone()
+        fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
+        res = rewards.resolution(sted)
+        sted_np = sted.cpu().numpy()
+        mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)      # (B,3)
+        if self.compute_f1:
+            f1 = np.array([rewards.nanodomain_f1(np.rint(sted_np[b]).astype(np.int64), self.synapses[b].nanodomains_coords)
+                           for b in range(self.B)])
+        else:
+            f1 = np.zeros(self.B)
+        reward = f1 * self.scale_nanodomain_reward
+
+        done = self.current_step >= self.max_episode_steps - 1
+        self.current_step += 1
+        self.episode_memory["mo_objs"].append(mo_objs)
+        self.episode_memory["actions"].append(action)
+        self.episode_memory["reward"].append(reward)
+        info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,
+                "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "f1-score": f1,
+                "nanodomains-coords": [s.nanodomains_coords for s in self.synapses]}
+
+        obs = []
+        for a, mo in zip(self.episode_memory["actions"], self.episode_memory["mo_objs"]):
+            if np.isnan(mo).any() and self.normalize_observations:
+                # the reference's Normalizer raises TypeError on a None objective (SURVEY App. C "edge cases")
+                raise TypeError("unsupported operand type(s) for -: 'NoneType' and 'int' (SNR objective is None)")
+            obs.append(self.action_normalizer(a) if self.normalize_observations else a)
+            obs.append(self.obj_normalizer(mo) if self.normalize_observations else mo)
+        obs = np.concatenate(obs, axis=1)
+        obs = np.pad(obs, ((0, 0), (0, self.observation_space[1].shape[0] - obs.shape[1])))
+
+        state = self._new_datamaps()
+        self.state = torch.stack((state, conf1, sted), dim=-1)
+        img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+        return (img, obs.astype(np.float32)), reward, np.full(self.B, done), np.zeros(self.B, dtype=bool), info
+
+    def close(self):
+        return None
+
+
+class ContextualSTEDMultiObjectivesEnv:
+    """Single-environment gym-API view (reset -> (obs, info); step -> (obs, reward, done, False, info))."""
+
+    metadata = {"render.modes": ["human"]}
+    obj_names = OBJ_NAMES
+
+    def __init__(self, bleach_sampling="constant", actions=("p_sted",), max_episode_steps=10, scale_nanodomain_reward=1.0,
+                 normalize_observations=True, **kwargs):
+        self.vec = VectorContextualMOSTED(1, bleach_sampling, actions, max_episode_steps, scale_nanodomain_reward,
+                                          normalize_observations, **kwargs)
+        self.action_space, self.observation_space = self.vec.action_space, self.vec.observation_space
+        self.actions = self.vec.actions
+        self.spec = SimpleNamespace(id=None, max_episode_steps=max_episode_steps)
+
+    @property
+    def microscope(self):
+        return self.vec.microscope
+
+    def reset(self, seed=None, options=None):
+        (img, vec), info = self.vec.reset(seed=seed, options=options)
+        return (img[0], vec[0]), info
+
+    def step(self, action):
+        self.vec.max_episode_steps = self.spec.max_episode_steps
+        (img, vec), reward, done, trunc, info = self.vec.step(np.asarray(action)[None])
+        one = {k: (v[0] if isinstance(v, (np.ndarray, list)) else v[0].cpu().numpy()) for k, v in info.items()}
+        return (img[0], vec[0]), float(reward[0]), bool(done[0]), False, one
+
+    def close(self):
+        return None
+
+
+# ids and kwargs of gym_sted/__init__.py:587-610,665-674 (Appendix C)
+REGISTRY = {
+    "ContextualMOSTED-easy-v0": dict(max_episode_steps=10, kwargs=dict(
+        actions=["p_sted", "p_ex", "pdt"], bleach_sampling="constant", scale_nanodomain_reward=1.0)),
+    "ContextualMOSTED-easy-hslb-v0": dict(max_episode_steps=10, kwargs=dict(
+        actions=["p_sted", "p_ex", "pdt"], bleach_sampling={"mode": "constant", "routine": "high-signal_low-bleach"},
+        scale_nanodomain_reward=1.0)),
+    "ContextualMOSTED-hard-v0": dict(max_episode_steps=10, kwargs=dict(
+        actions=["p_sted", "p_ex", "pdt"], bleach_sampling="uniform", scale_nanodomain_reward=1.0)),
+}
+
+
+def make(env_id: str, **overrides):
+    """``gym.make`` for the registered ids (accepts the ``gym_sted:`` prefix)."""
+    key = env_id.split(":")[-1]
+    if key not in REGISTRY:
+        raise KeyError(f"unknown environment id {env_id!r}; known: {sorted(REGISTRY)}")
+    entry = REGISTRY[key]
+    env = ContextualSTEDMultiObjectivesEnv(max_episode_steps=entry["max_episode_steps"], **{**entry["kwargs"], **overrides})
+    env.spec = SimpleNamespace(id=key, max_episode_steps=entry["max_episode_steps"])
+    return env
+
+
+def make_vec(env_id: str, num_envs: int, **overrides):
+    key = env_id.split(":")[-1]
+    entry = REGISTRY[key]
+    return VectorContextualMOSTED(num_envs, max_episode_steps=entry["max_episode_steps"], **{**entry["kwargs"], **overrides})

@@ -1,0 +1,300 @@
+"""Per-step foregrounds, objectives and rewards for batches of environments (SURVEY.md §8a rows a6–a10).
+
+* ``foreground_objectives``  Otsu foregrounds + Bleach + SNR: one CUDA kernel (``rewards_kernels.cu``),
+  bit-identical to ``gym_sted/utils.py:16-24``, ``mosted_env.py:237-244``, ``objectives.py:91-111``.
+* ``resolution``             image-decorrelation resolution (``objectives.py:121-291``): apodisation,
+  FFT, high-pass sweeps and ring sums run batched on the GPU in float64 (torch tensors; the ring sums are
+  prefix sums in radius-sorted pixel order); only the 50-point peak searches run on the host.
+* ``nanodomain_f1``          detection + F1 (``objectives.py:404-430``, ``rewards/utils.py:6-49``):
+  **host side in this round** (scipy.ndimage + MINPACK ``leastsq`` + Hungarian matching, per
+  environment) — the device version is the next item of this row.
+* ``PrefNet`` / ``PreferenceArticulator``  the 3-10-10-1 ReLU MLP of ``gym_sted/prefnet`` on the device.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+RES_CAP = 300.0          # gym_sted/defaults.py:117
+PIXELSIZE = 20e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# a6 + a7
+# ------------------------------------------------------------------------------------------------
+def foreground_objectives(conf1: torch.Tensor, sted: torch.Tensor, conf2: torch.Tensor):
+    """(B,H,W) float32 photon counts -> fg_s, fg_c (bool), bleach, snr (float64, NaN where the reference
+    returns None), flags (int32)."""
+    lib = _lib.load()
+    B, H, W = conf1.shape
+    dev = conf1.device
+    conf1, sted, conf2 = (t.contiguous().to(torch.float32) for t in (conf1, sted, conf2))
+    fg_c = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    fg_s = torch.empty_like(fg_c)
+    objs = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    flags = torch.empty((B,), dtype=torch.int32, device=dev)
+    scratch = None
+    if float(torch.maximum(conf1.amax(), sted.amax())) >= 8192:
+        scratch = torch.empty((B, 2, 65536), dtype=torch.int32, device=dev)
+    _lib.check(lib.sted_foreground_objectives(conf1.data_ptr(), sted.data_ptr(), conf2.data_ptr(), B, H, W,
+                                              fg_c.data_ptr(), fg_s.data_ptr(), objs.data_ptr(), flags.data_ptr(),
+                                              scratch.data_ptr() if scratch is not None else None,
+                                              torch.cuda.current_stream(dev).cuda_stream))
+    snr = torch.where((flags & 1) != 0, torch.full_like(objs[:, 1], float("nan")), objs[:, 1])
+    return fg_s.bool(), fg_c.bool(), objs[:, 0], snr, flags
+
+
+# ------------------------------------------------------------------------------------------------
+# a8: resolution
+# ------------------------------------------------------------------------------------------------
+def _decorr_peak(d: np.ndarray, tol: float):
+    idx = int(np.argmax(d))
+    A = d[idx]
+    while len(d) > 1:
+        if (A - np.min(d[idx:])) >= tol or idx == 0:
+            break
+        d = d[:-1]
+        idx = int(np.argmax(d))
+        A = d[idx]
+    return idx, A
+
+
+class _Decorrelator:
+    """Geometry shared by every image of one shape: apodisation window, radius map, radius-sorted order."""
+
+    def __init__(self, H, W, device, w=20):
+        edge = (np.sin(np.linspace(-np.pi / 2, np.pi / 2, w)) + 1) / 2
+        wins = [np.concatenate([edge, np.ones(l - 2 * w), edge[::-1]]) for l in (H, W)]
+        self.window = torch.from_numpy(wins[0][:, None] * wins[1][None, :]).to(device)
+        self.Hc, self.Wc = H - 1 + H % 2, W - 1 + W % 2
+        ys = np.linspace(-1, 1, self.Hc)[:, None]
+        xs = np.linspace(-1, 1, self.Wc)[None, :]
+        R = np.sqrt(xs ** 2 + ys ** 2).ravel()
+        order = np.argsort(R, kind="stable")
+        self.R_sorted_np = R[order]
+        self.order = torch.from_numpy(order).to(device)
+        self.R_sorted = torch.from_numpy(self.R_sorted_np).to(device)
+        self.inside = self.R_sorted < 1
+
+
+def _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, bounds, sigmas=None):
+    """Ik, Ikn_conj: (B,N) complex in radius-sorted order; cum_abs2: (B,N+1) prefix sums of |Ikn|^2;
+    bounds: (B,Nr) int64 = number of pixels with R < r_i; sigmas: (B,) or None.  Returns d (B,Nr) float64."""
+    if sigmas is not None:
+        Ik = Ik * (1 - torch.exp(-2 * sigmas[:, None] ** 2 * R2[None, :]))
+    num = torch.real(Ik * Ikn_conj)
+    cum = torch.zeros((Ik.shape[0], Ik.shape[1] + 1), dtype=torch.float64, device=Ik.device)
+    torch.cumsum(num, dim=1, out=cum[:, 1:])
+    nom = torch.gather(cum, 1, bounds)
+    denom1 = torch.gather(cum_abs2, 1, bounds)
+    denom2 = torch.sum(Ik.real ** 2 + Ik.imag ** 2, dim=1, keepdim=True)
+    d = nom / torch.sqrt(denom1 * denom2)
+    d = torch.floor(1000 * d) / 1000
+    return torch.nan_to_num(d, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+
+
+_DECORR_CACHE: dict = {}
+
+
+def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, Ng=10, tol=0.0005) -> np.ndarray:
+    """(B,H,W) photon counts on the GPU -> (B,) float64 numpy array of resolutions in nm (capped)."""
+    B, H, W = sted.shape
+    dev = sted.device
+    key = (H, W, str(dev))
+    if key not in _DECORR_CACHE:
+        _DECORR_CACHE[key] = _Decorrelator(H, W, dev)
+    geo = _DECORR_CACHE[key]
+    img = sted.to(torch.float64)
+    mean = img.mean(dim=(1, 2), keepdim=True)
+    img = (geo.window * (img - mean) + mean).to(torch.float32).to(torch.float64)[:, :geo.Hc, :geo.Wc]
+    Ik = torch.fft.fftshift(torch.fft.fftn(torch.fft.fftshift(img, dim=(1, 2)), dim=(1, 2)), dim=(1, 2))
+    Ik = Ik.reshape(B, -1)[:, geo.order]
+    Ik = Ik * geo.inside
+    mag = torch.abs(Ik)
+    Ikn = torch.where(mag > 0, Ik / mag, torch.zeros_like(Ik))
+    Ikn = torch.where(torch.isfinite(Ikn.real) & torch.isfinite(Ikn.imag), Ikn, torch.zeros_like(Ikn))
+    Ikn_conj = torch.conj(Ikn)
+    cum_abs2 = torch.zeros((B, Ik.shape[1] + 1), dtype=torch.float64, device=dev)
+    torch.cumsum(Ikn.real ** 2 + Ikn.imag ** 2, dim=1, out=cum_abs2[:, 1:])
+    R2 = geo.R_sorted ** 2
+
+    def bounds_for(radii_np):          # (B,Nr) radii -> number of pixels with R < r
+        return torch.from_numpy(np.searchsorted(geo.R_sorted_np, radii_np, side="left")).to(dev)
+
+    r = np.linspace(0, 1, Nr)
+    b_shared = bounds_for(np.broadcast_to(r, (B, Nr)))
+    d0 = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_shared).cpu().numpy()
+    first = [_decorr_peak(d0[b], tol) for b in range(B)]
+    r0 = np.array([r[i] for i, _ in first])
+    A0 = np.array([a for _, a in first])
+    with np.errstate(divide="ignore"):
+        g_max = 2 / r0
+    g_max[np.isinf(g_max)] = max(geo.Hc, geo.Wc) / 2
+    sigmas = np.concatenate([np.full((B, 1), geo.Hc / 4),
+                             np.exp(np.linspace(np.log(g_max), np.log(0.15), Ng, axis=1))], axis=1)      # (B, Ng+1)
+    As = [A0]
+    rs = [r0]
+    for j in range(Ng + 1):
+        d = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_shared, torch.from_numpy(sigmas[:, j]).to(dev)).cpu().numpy()
+        pk = [_decorr_peak(d[b], tol) for b in range(B)]
+        rs.append(np.array([r[i] for i, _ in pk]))
+        As.append(np.array([a for _, a in pk]))
+    rs_a = np.stack(rs, axis=1)            # (B, Ng+2)
+    As_a = np.stack(As, axis=1)
+    kmax = np.array([int(np.where(row == row.max())[0][-1]) for row in rs_a])
+    ind1 = np.where(kmax == 0, 0, np.where(kmax >= Ng, kmax - 2, kmax - 1))
+    peak_r = rs_a[np.arange(B), kmax]
+    r_fine = np.linspace(peak_r - (r[1] - r[0]), np.minimum(peak_r + 0.4, r[-1]), Nr, axis=1)
+    sig_fine = np.exp(np.linspace(np.log(sigmas[np.arange(B), ind1]), np.log(sigmas[np.arange(B), ind1 + 1]), Ng, axis=1))
+    b_fine = bounds_for(r_fine)
+    rs_l = [rs_a[:, :-1]]
+    As_l = [As_a[:, :-1]]
+    for j in range(Ng):
+        d = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_fine, torch.from_numpy(sig_fine[:, j]).to(dev)).cpu().numpy()
+        pk = [_decorr_peak(d[b], tol) for b in range(B)]
+        rs_l.append(np.array([r_fine[b, i] for b, (i, _) in enumerate(pk)])[:, None])
+        As_l.append(np.array([a for _, a in pk])[:, None])
+    rs_l.append(r0[:, None])
+    As_l.append(A0[:, None])
+    rs_f = np.concatenate(rs_l, axis=1)
+    As_f = np.concatenate(As_l, axis=1)
+    rs_f[As_f < 0.05] = 0
+    with np.errstate(divide="ignore"):
+        res = 2 / rs_f.max(axis=1) * pixelsize / 1e-9
+    return np.minimum(res, res_cap)
+
+
+# ------------------------------------------------------------------------------------------------
+# a9: nanodomain detection + F1 (host side in this round)
+# ------------------------------------------------------------------------------------------------
+def _ensure_spacing(coords, spacing):
+    keep = []
+    for i, c in enumerate(coords):
+        if all(np.max(np.abs(c - coords[k])) >= spacing for k in keep):
+            keep.append(i)
+    return coords[keep]
+
+
+def detect_nanodomains(sted: np.ndarray, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
+    """``NumberNanodomains`` detector: gaussian(0.5) -> q99 mask -> drop objects < 4 px (8-conn.) -> label ->
+    per-label local maxima (5x5, Chebyshev spacing 2) -> 7x7 Gaussian-fit validation (40 nm <= FWHM <= 200 nm)."""
+    import scipy.ndimage as ndi
+    import scipy.optimize
+
+    sted = np.asarray(sted)
+    filtered = ndi.gaussian_filter(sted.astype(np.float64), 0.5, mode="nearest", truncate=4.0)
+    mask = filtered > np.quantile(filtered, 0.99)
+    eight = np.ones((3, 3), dtype=bool)
+    lab, n = ndi.label(mask, structure=eight)
+    if n:
+        sizes = np.bincount(lab.ravel())
+        small = sizes < 4
+        small[0] = False
+        mask &= ~small[lab]
+    labels, _ = ndi.label(mask, structure=eight)
+    lowest = filtered.min()
+    peaks = []
+    for li, roi in enumerate(ndi.find_objects(labels)):
+        if roi is None:
+            continue
+        inside = labels[roi] == li + 1
+        obj = np.where(inside, filtered[roi], np.finfo(np.float64).min)
+        if obj.size == 1:
+            pm = obj > lowest
+        else:
+            pm = obj == ndi.maximum_filter(obj, size=2 * threshold + 1, mode="nearest")
+            if np.all(pm[inside]):
+                pm[:] = False
+                pm[np.logical_xor(inside, ndi.binary_opening(inside))] = True
+            pm &= obj > lowest
+        cc = np.transpose(np.nonzero(pm))
+        cc = cc[np.argsort(-obj[tuple(cc.T)], kind="stable")]
+        cc = _ensure_spacing(cc, threshold)
+        peaks.append(cc + np.array([s.start for s in roi]))
+    guess = np.vstack(peaks) if peaks else np.zeros((0, 2), dtype=np.int64)
+    padded = np.pad(sted, 3, constant_values=0)
+    X, Y = np.indices((7, 7)) - 3.0
+    valid = []
+    for row, col in guess:
+        data = padded[row:row + 7, col:col + 7]
+
+        def err(p):
+            wx, wy = float(p[3]) + 1e-3, float(p[4]) + 1e-3
+            return np.ravel(p[0] * np.exp(-(((p[1] - X) ** 2.0 / (2 * wx ** 2.0)) + ((p[2] - Y) ** 2.0 / (2 * wy ** 2.0)))) - data)
+
+        p, _ = scipy.optimize.leastsq(err, [data.max(), 0, 0, 1, 1], ftol=1e-3)
+        fx, fy = 2.355 * p[3] * pixelsize, 2.355 * p[4] * pixelsize
+        if not (fx > 200e-9 or fx < 40e-9 or fy > 200e-9 or fy < 40e-9):
+            valid.append((row, col))
+    return np.asarray(valid, dtype=np.int64).reshape(-1, 2)
+
+
+def match_counts(truth, guess, threshold=2):
+    """(TP, FP, FN): Hungarian matching on Euclidean distances, pairs at distance >= threshold forbidden
+    (``metrics.CentroidDetectionError(gt, guess, 2, algorithm="hungarian")``)."""
+    import scipy.optimize
+    import scipy.spatial
+
+    truth = np.asarray(truth, dtype=np.float64).reshape(-1, 2)
+    guess = np.asarray(guess, dtype=np.float64).reshape(-1, 2)
+    if len(truth) == 0 or len(guess) == 0:
+        return 0, len(guess), len(truth)
+    cost = scipy.spatial.distance.cdist(truth, guess)
+    masked = np.where(cost < threshold, cost, 1e6)
+    ri, ci = scipy.optimize.linear_sum_assignment(masked)
+    tp = int(np.sum(masked[ri, ci] < 1e6))
+    return tp, len(guess) - tp, len(truth) - tp
+
+
+def f1_from_counts(tp, fp, fn):
+    prec = tp / (tp + fp + 1e-6)
+    rec = tp / (tp + fn + 1e-6)
+    return 2 * prec * rec / (prec + rec + 1e-6)
+
+
+def nanodomain_f1(sted: np.ndarray, truth_coords, pixelsize=PIXELSIZE, threshold=2):
+    return f1_from_counts(*match_counts(truth_coords, detect_nanodomains(sted, pixelsize, threshold), threshold))
+
+
+# ------------------------------------------------------------------------------------------------
+# a10: preference network
+# ------------------------------------------------------------------------------------------------
+class PrefNet(torch.nn.Module):
+    """``gym_sted/prefnet/prefNet.py:11-31``: Linear(nb_obj,10)-ReLU-Linear(10,10)-ReLU-Linear(10,1)."""
+
+    def __init__(self, nb_obj=3, middle_size=10):
+        super().__init__()
+        self.f1 = torch.nn.Linear(nb_obj, middle_size)
+        self.f2 = torch.nn.Linear(middle_size, middle_size)
+        self.out = torch.nn.Linear(middle_size, 1)
+
+    def forward(self, X):
+        return self.out(torch.relu(self.f2(torch.relu(self.f1(X)))))
+
+
+class PreferenceArticulator:
+    """``gym_sted/prefnet/articulation.py:36-75`` with the weights of model ``2021-07-12-06-40-29_ResolutionBleachSNR``."""
+
+    def __init__(self, nb_obj=3, model_name="2021-07-12-06-40-29_ResolutionBleachSNR", device="cpu"):
+        path = os.path.join(_DATA, "prefnet_" + model_name)
+        self.model = PrefNet(nb_obj=nb_obj)
+        self.model.load_state_dict(torch.load(os.path.join(path, "weights.t7"), map_location="cpu"))
+        self.model.eval().to(device)
+        self.device = torch.device(device)
+        with open(os.path.join(path, "config.json")) as fh:
+            self.config = json.load(fh)
+
+    def articulate(self, thetas, use_sigmoid=False):
+        thetas = (np.array(thetas) - self.config["train_mean"]) / self.config["train_std"]
+        with torch.no_grad():
+            scores = self.model(torch.from_numpy(thetas).float().to(self.device)).cpu().numpy()
+        if use_sigmoid:
+            scores = torch.sigmoid(torch.tensor(scores)).numpy()
+        order = np.argsort(scores.ravel())
+        return scores, order[-1], order

@@ -170,6 +170,21 @@ int sted_sample_binomial(const float* n_dev, const float* q_dev, int64_t n, uint
 /* Raw Philox4x32-10 block for known-answer tests: out_host[4]. Host-side, no device needed. */
 void sted_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out_host[4]);
 
+/* Foreground masks and the Bleach / SNR objectives of B acquisitions, bit-identical to
+ *   get_foreground (skimage Otsu on integer images)        gym_sted/utils.py:16-24
+ *   fg_s = otsu(sted) if any(sted) else ones; fg_s *= fg_c gym_sted/envs/mosted_env.py:237-244
+ *   Bleach.evaluate, Signal_Ratio(75).evaluate             gym_sted/rewards/objectives.py:91-111
+ *   conf1/sted/conf2_dev : float32 [B][H][W] photon counts (integer valued)
+ *   fg_c/fg_s_dev        : uint8   [B][H][W] masks (output)
+ *   objs_dev             : float64 [B][2] = {Bleach, SNR}   (SNR is 0 without STED foreground)
+ *   flags_dev            : int32   [B]  bit 0: SNR < 0 (the reference returns None), bit 1: value range too
+ *                          large for the histograms (outputs NaN)
+ *   hist_scratch_dev     : int32 [B][2][65536] or NULL; only needed when an image spans > 8192 values */
+int sted_foreground_objectives(const float* conf1_dev, const float* sted_dev, const float* conf2_dev,
+                               int B, int H, int W, uint8_t* fg_c_dev, uint8_t* fg_s_dev,
+                               double* objs_dev, int32_t* flags_dev, int32_t* hist_scratch_dev,
+                               void* stream);
+
 /* Debug: per-phase cycle sums of the scan kernel (non-zero only in SWEEP_PROBE=2 builds). */
 int sted_debug_phase_cycles(unsigned long long out_host[8], int reset);
 

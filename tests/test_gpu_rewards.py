@@ -1,0 +1,134 @@
+"""GPU parity of the reward side (Otsu foregrounds, Bleach, SNR, Resolution) and env API conformance."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from gym_sted_b200 import defaults, envs, rewards  # noqa: E402
+from oracle import rewards_oracle as ro  # noqa: E402
+from tests import helpers  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("these tests need a CUDA device (no CPU fallback exists)")
+
+
+def _check_against_oracle(conf1, sted, conf2):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().cuda()
+    fg_s, fg_c, bl, snr, flags = rewards.foreground_objectives(t(conf1), t(sted), t(conf2))
+    fg_s, fg_c, bl, snr = fg_s.cpu().numpy(), fg_c.cpu().numpy(), bl.cpu().numpy(), snr.cpu().numpy()
+    for i in range(len(conf1)):
+        rs, rc = ro.foregrounds(conf1[i], sted[i])
+        assert np.array_equal(fg_c[i], rc), i
+        assert np.array_equal(fg_s[i], rs), i
+        assert bl[i] == ro.bleach(conf1[i], conf2[i], rc), i                      # bit-exact float64
+        ref = ro.signal_ratio(sted[i], conf1[i], rs, rc)
+        if ref is None:
+            assert np.isnan(snr[i]) and int(flags[i]) & 1
+        else:
+            assert snr[i] == ref, (i, snr[i], ref)
+
+
+def test_foregrounds_and_objectives_reproduce_recorded_episodes():
+    """Integer outputs (masks) bit-exact; Bleach/SNR bit-exact in float64 against the reference's records."""
+    _gpu()
+    demo = helpers.load_demonstrations()
+    _check_against_oracle(demo["conf1"], demo["sted_image"], demo["conf2"])
+    t = lambda a: torch.from_numpy(a).float().cuda()
+    fg_s, fg_c, bl, snr, _ = rewards.foreground_objectives(t(demo["conf1"]), t(demo["sted_image"]), t(demo["conf2"]))
+    assert np.array_equal(fg_c.cpu().numpy(), demo["fg_c"]) and np.array_equal(fg_s.cpu().numpy(), demo["fg_s"])
+    assert np.array_equal(bl.cpu().numpy(), demo["mo_objs"][:, 1])
+    assert np.array_equal(snr.cpu().numpy(), demo["mo_objs"][:, 2])
+    res = rewards.resolution(t(demo["sted_image"]))
+    assert np.array_equal(res, demo["mo_objs"][:, 0])
+
+
+def test_foregrounds_edge_cases():
+    _gpu()
+    rng = np.random.default_rng(0)
+    H = W = 48
+    conf1 = rng.poisson(3.0, (6, H, W)) + (rng.random((6, H, W)) < 0.1) * rng.poisson(60, (6, H, W))
+    sted = rng.poisson(1.0, (6, H, W)) + (rng.random((6, H, W)) < 0.05) * rng.poisson(25, (6, H, W))
+    conf2 = rng.poisson(2.0, (6, H, W))
+    sted[1] = 0                                   # empty STED image -> fg_s = fg_c, SNR from the ones-mask branch
+    sted[2] = rng.poisson(0.02, (H, W))           # nearly empty
+    conf1[3] = rng.integers(0, 20000, (H, W))     # wide value range -> global histogram path
+    sted[4] = rng.poisson(40.0, (H, W)) * (conf1[4] <= np.median(conf1[4]))      # bright background -> SNR < 0 -> None
+    conf1[5, :, : W // 2] = 7; conf1[5, :, W // 2:] = 9                           # two-valued image
+    _check_against_oracle(conf1.astype(np.int64), sted.astype(np.int64), conf2.astype(np.int64))
+
+
+def test_objectives_on_simulated_acquisitions():
+    _gpu()
+    from gym_sted_b200.batch import BatchedMicroscope
+    from gym_sted_b200 import synapse
+    m = helpers.product_microscope(noise=True, background=defaults.DETECTOR["background"])
+    B = 8
+    maps, _ = synapse.generate_batch(B, 64, 64, seed=9)
+    bm = BatchedMicroscope(m, B, 64, 64, seed=3)
+    bm.set_datamaps(torch.from_numpy(maps))
+    conf1, _ = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)
+    sted, _ = bm.get_signal_and_bleach(20e-6, 10e-6, 0.1, bleach=True)
+    conf2, _ = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)
+    assert bm.dropped_events() == 0
+    c1, s, c2 = (np.rint(x.cpu().numpy()).astype(np.int64) for x in (conf1, sted, conf2))
+    _check_against_oracle(c1, s, c2)
+    res = rewards.resolution(sted)
+    ref = np.array([ro.resolution(s[b]) for b in range(B)])
+    np.testing.assert_allclose(res, ref, rtol=1e-12)
+    assert np.all(res < 250) and np.all(res > 30)             # STED at 100 mW resolves well below the confocal limit
+
+
+def test_env_api_conformance_single():
+    """Spaces, dtypes, info keys, episode length and observation layout of SURVEY Appendix C."""
+    _gpu()
+    env = envs.make("gym_sted:ContextualMOSTED-easy-v0")
+    assert env.spec.max_episode_steps == 10
+    np.testing.assert_allclose(env.action_space.low, [0, 0, 1e-6])
+    np.testing.assert_allclose(env.action_space.high, np.array([0.35, 20e-6, 100e-6], dtype=np.float32))
+    assert env.observation_space[0].shape == (64, 64, 3) and env.observation_space[0].dtype == np.uint16
+    assert env.observation_space[1].shape == (60,) and env.observation_space[1].dtype == np.float32
+    (img, vec), info = env.reset(seed=0)
+    assert img.shape == (64, 64, 3) and img.dtype == np.uint16 and vec.shape == (60,) and vec.dtype == np.float32
+    assert img[..., 0].any() and not img[..., 1:].any() and not vec.any() and info == {}
+    for t in range(10):
+        action = np.array([0.1, 12e-6, 20e-6], dtype=np.float32) * (1 + 0.05 * t)
+        (img, vec), reward, done, truncated, info = env.step(action)
+        assert set(info) == {"action", "bleached", "sted_image", "conf1", "conf2", "fg_c", "fg_s", "mo_objs", "reward",
+                             "f1-score", "nanodomains-coords"}
+        assert truncated is False and done == (t == 9) and 0.0 <= reward <= 1.0 and reward == info["f1-score"]
+        assert img.dtype == np.uint16 and np.array_equal(img[..., 1], info["conf1"].astype(np.uint16))
+        assert np.array_equal(img[..., 2], info["sted_image"].astype(np.uint16))
+        mo = info["mo_objs"]
+        assert 0 < mo[0] <= 300 and mo[1] < 1
+        exp = np.concatenate([(np.clip(action, env.action_space.low, env.action_space.high) - [0, 0, 1e-6])
+                              / [0.35, 20e-6, 99e-6], [(mo[0] - 40) / 140, mo[1], mo[2]]])
+        np.testing.assert_allclose(vec[6 * t:6 * t + 6], exp.astype(np.float32), rtol=1e-5, atol=1e-6)
+        assert not vec[6 * (t + 1):].any()
+        assert info["bleached"].shape == (64, 64) and info["fg_s"].dtype == bool
+    # out-of-range actions are clipped, not rejected
+    env.reset()
+    _, _, _, _, info = env.step(np.array([5.0, 1.0, 1.0], dtype=np.float32))
+    np.testing.assert_allclose(info["action"], env.action_space.high)
+
+
+def test_vector_env_routine_and_per_env_fluorophores():
+    _gpu()
+    vec = envs.make_vec("ContextualMOSTED-easy-hslb-v0", 6, compute_f1=False)
+    assert vec.bleach_sampler.sample()["k1"] == pytest.approx(3.626623963067252e-16)
+    (img, v), _ = vec.reset(seed=1)
+    assert img.shape == (6, 64, 64, 3) and v.shape == (6, 60)
+    acts = np.tile(np.array([[0.15, 10e-6, 30e-6]], dtype=np.float32), (6, 1))
+    (img, v), reward, done, trunc, info = vec.step(acts)
+    assert reward.shape == (6,) and done.shape == (6,) and info["mo_objs"].shape == (6, 3)
+    assert float(info["bleached"].sum()) < sum(s.frame.sum() for s in vec.synapses) * 2       # molecules were lost
+    hard = envs.make_vec("ContextualMOSTED-hard-v0", 4, compute_f1=False, seed=3)
+    (img, v), _ = hard.reset(seed=3)
+    (img, v), reward, done, trunc, info = hard.step(acts[:4])
+    assert np.isfinite(info["mo_objs"][:, :2]).all()
+    # closed-form sampler: sigma_abs and k1 inside the ranges spanned by the reference's fitted routines x the criteria
+    f = hard.bleach_sampler.sample(hard.microscope)
+    assert 1e-23 < f["sigma_abs"][635] < 2e-20 and 1e-18 < f["k1"] < 1e-13

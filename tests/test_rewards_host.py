@@ -1,0 +1,88 @@
+"""CPU suite for the reward/observation host logic of the product package (no GPU needed)."""
+import numpy as np
+import pytest
+import torch
+
+from gym_sted_b200 import defaults, rewards
+from oracle import rewards_oracle as ro
+from tests import helpers
+
+
+def test_resolution_reproduces_recorded_values_exactly():
+    """Batched decorrelation (torch, here on the CPU device) against the reference's recorded objectives."""
+    demo = helpers.load_demonstrations()
+    res = rewards.resolution(torch.from_numpy(demo["sted_image"]).to(torch.float32))
+    assert np.array_equal(res, demo["mo_objs"][:, 0])
+
+
+def test_resolution_matches_oracle_on_other_sizes():
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[:96, :96]
+    imgs = []
+    for s in (1.5, 3.0, 6.0):
+        img = np.zeros((96, 96))
+        for _ in range(25):
+            y, x = rng.uniform(10, 86, 2)
+            img += 80 * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * s ** 2))
+        imgs.append(rng.poisson(img + 0.2))
+    got = rewards.resolution(torch.from_numpy(np.stack(imgs)).to(torch.float32))
+    ref = np.array([ro.resolution(i) for i in imgs])
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    assert got[0] < got[1] < got[2] <= 300
+
+
+def test_detection_and_f1_match_oracle():
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[:64, :64]
+    for trial in range(4):
+        img = rng.poisson(0.3, (64, 64)).astype(np.int64)
+        truth = rng.integers(6, 58, (6, 2))
+        for (y, x) in truth:
+            img += rng.poisson(90 * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * 1.8 ** 2)))
+        a = rewards.detect_nanodomains(img)
+        b = ro.detect_nanodomains(img)
+        assert np.array_equal(a, b)
+        assert rewards.match_counts(truth, a) == ro.match_counts(truth, b)
+        assert rewards.nanodomain_f1(img, truth) == ro.nanodomain_f1(img, truth)
+
+
+def test_prefnet_known_answer():
+    """SURVEY App. B probe: model 2021-07-12 scores mo_objs = [80, 0.2, 0.9] at 0.9572."""
+    art = rewards.PreferenceArticulator()
+    scores, best, order = art.articulate([[80, 0.2, 0.9], [200, 0.9, 0.1]])
+    assert scores.shape == (2, 1) and scores[0, 0] == pytest.approx(0.9572, abs=5e-4)
+    assert best == 0 and list(order) == [1, 0]
+
+
+def test_registry_and_spaces_without_gpu():
+    from gym_sted_b200 import envs
+    assert set(envs.REGISTRY) == {"ContextualMOSTED-easy-v0", "ContextualMOSTED-easy-hslb-v0", "ContextualMOSTED-hard-v0"}
+    for entry in envs.REGISTRY.values():
+        assert entry["max_episode_steps"] == 10 and entry["kwargs"]["actions"] == ["p_sted", "p_ex", "pdt"]
+    box = envs.Box(np.array([0, 0, 1e-6], dtype=np.float32), np.array([0.35, 20e-6, 100e-6], dtype=np.float32))
+    assert box.shape == (3,) and box.contains(box.sample(np.random.default_rng(0)))
+    norm = envs.Normalizer(["p_sted", "p_ex", "pdt"], defaults.action_spaces)
+    np.testing.assert_allclose(norm([0.35, 10e-6, 1e-6]), [1.0, 0.5, 0.0])
+    norm = envs.Normalizer(envs.OBJ_NAMES, defaults.scales_dict)
+    np.testing.assert_allclose(norm([110, 0.5, 0.25]), [0.5, 0.5, 0.25])
+    s = envs.BleachSampler("constant", routine="high-signal_low-bleach").sample()
+    assert s["k1"] == pytest.approx(3.626623963067252e-16) and s["sigma_abs"][635] == pytest.approx(3.2482521692221336e-21)
+    assert envs.BleachSampler("constant").sample() is defaults.FLUO
+    with pytest.raises(KeyError):
+        envs.make("NoSuchEnv-v0")
+
+
+def test_synthetic_synapse_generator():
+    from gym_sted_b200 import synapse
+    s = synapse.generate(64, 64, seed=5)
+    assert s.frame.shape == (64, 64) and s.datamap_pixelsize_nm == 20
+    n = len(s.nanodomains_coords)
+    assert 3 <= n <= 15
+    vals = s.frame[tuple(s.nanodomains_coords.T)]
+    assert vals.min() >= 100 and vals.max() <= 175
+    d = np.linalg.norm(s.nanodomains_coords[:, None] - s.nanodomains_coords[None], axis=-1)
+    assert d[np.triu_indices(n, 1)].min() >= 5
+    assert set(np.unique(s.frame)) - set(vals.tolist()) <= {0, 5}
+    big, coords = synapse.generate_batch(2, 256, 256, seed=1)
+    assert big.shape == (2, 256, 256) and 0.05 < (big > 0).mean() < 0.3
+    assert np.array_equal(synapse.generate_batch(2, 256, 256, seed=1)[0], big)
