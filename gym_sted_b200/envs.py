@@ -29,6 +29,9 @@ OBJ_NAMES = ["Resolution", "Bleach", "SNR"]
 
 class Box:
     def __init__(self, low, high, shape=None, dtype=np.float32):
+        if np.issubdtype(np.dtype(dtype), np.integer):      # e.g. Box(0, 2**16, dtype=uint16): clip to the dtype
+            info = np.iinfo(dtype)
+            low, high = np.clip(low, info.min, info.max), np.clip(high, info.min, info.max)
         self.low = np.broadcast_to(np.asarray(low, dtype=dtype), shape if shape is not None else np.shape(low)).copy()
         self.high = np.broadcast_to(np.asarray(high, dtype=dtype), self.low.shape).copy()
         self.shape, self.dtype = self.low.shape, np.dtype(dtype)
