@@ -294,86 +294,126 @@ struct BleachWs {
     unsigned long long cap;
 };
 
-// Death schedule of every occupied pixel (one thread per pixel of the padded map).
+// Death schedule of every occupied pixel.
 //   FILL = false: count the events of each (env, scan row);  FILL = true: regenerate them (same Philox
-//   stream, same arithmetic) and store them in their row bucket.
+//   streams, same arithmetic) and store them in their row bucket.
+// A CTA takes a chunk of PS_CHUNK pixels of one environment, compacts the occupied ones into work items of
+// at most 8 molecules (independent sub-binomials add up to the pixel's binomial; a 150-molecule nanodomain
+// becomes 19 items) and then gives one item to each thread, so lanes stay busy and evenly loaded.
+// Cumulative pass hazards come from QQ[v][u] = sum_{u'>=u} CH[u'][v]: for a pixel whose taps are clipped to
+// [lo,hi] the hazard of the passes u..u_hi is G(u) - G(u_hi+1) with G(u) = QQ[lo][u] - QQ[hi+1][u].
+constexpr int PS_THREADS = 256, PS_CHUNK = 4096, PS_ITEMS = 2048, PS_PER = PS_CHUNK / PS_THREADS;
+
 template <bool FILL>
-__global__ void __launch_bounds__(256) presample_kernel(const AcqParams P, const BleachWs ws) {
+__global__ void __launch_bounds__(PS_THREADS) presample_kernel(const AcqParams P, const BleachWs ws) {
     const int K = P.K, KP = P.KP, H = P.H, W = P.W, Wp = P.Wp;
     extern __shared__ __align__(16) float smem[];
-    float* sCH = smem;                 // [K][KP]
-    float* sQ = sCH + K * KP;          // [K+1]  Q[u] = sum_{u'>=u} CH[u'][0]
-    const int b = blockIdx.y;
+    float* sCH = smem;                                   // [K][KP]
+    float* sQQ = sCH + K * KP;                           // [K+1][KP]
+    uint32_t* items = reinterpret_cast<uint32_t*>(sQQ + (K + 1) * KP);      // [PS_ITEMS] pixel | sub<<12 | m<<24
+    __shared__ int s_warp[PS_THREADS / 32];
+    __shared__ int s_total;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const float4* c4 = reinterpret_cast<const float4*>(P.tables + ((size_t)b * STED_TABLES + STED_TAB_CH) * K * KP);
-        for (int i = threadIdx.x; i < K * KP / 4; i += blockDim.x) reinterpret_cast<float4*>(sCH)[i] = __ldg(c4 + i);
+        for (int i = tid; i < K * KP / 4; i += PS_THREADS) reinterpret_cast<float4*>(sCH)[i] = __ldg(c4 + i);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid <= K) {                                      // column v = tid of CH, suffix-summed over tap rows
         float q = 0.f;
-        sQ[K] = 0.f;
-        for (int u = K - 1; u >= 0; --u) { q += sCH[u * KP]; sQ[u] = q; }
+        sQQ[tid * KP + K] = 0.f;
+        for (int u = K - 1; u >= 0; --u) { q += (tid < K) ? sCH[u * KP + tid] : 0.f; sQQ[tid * KP + u] = q; }
     }
     __syncthreads();
-    if (sQ[0] <= 0.f) return;          // no bleaching at all for this environment
+    if (sQQ[0] <= 0.f) return;                           // no bleaching at all for this environment
     const int p = K / 2;
     const float* din = P.din + (size_t)b * P.Hp * P.Wpitch;
     const uint32_t env = P.env_base + (uint32_t)b;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < H * W; idx += gridDim.x * blockDim.x) {
-        const int y = p + idx / W, x = p + idx % W;             // molecules only live inside the ROI
-        const int n = (int)din[(size_t)y * P.Wpitch + x];
-        if (n <= 0) continue;
-        const int lo = max(0, x - W + 1), hi = min(K - 1, x);    // taps that ever visit this column
-        const int u_hi = min(K - 1, y), u_lo = max(0, y - (H - 1));   // passes, visited from u_hi down to u_lo
-        const bool interior = (lo == 0 && hi == K - 1);
-        float htot;
-        if (interior) htot = sQ[u_lo] - sQ[u_hi + 1];
-        else { htot = 0.f; for (int u = u_lo; u <= u_hi; ++u) htot += sCH[u * KP + lo] - sCH[u * KP + hi + 1]; }
-        PhiloxStream rng;
-        rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, 0);
-        const int dead = binomial_deaths(n, htot, rng);
-        const float pd = -expm1f(-htot);
-        for (int d = 0; d < dead; ++d) {
-            // hazard this molecule had consumed when it died: truncated Exp(1) on (0, htot)
-            const float t = fminf(-log1pf(-rng.uniform() * pd), htot);
-            int u;
-            float before;                                        // hazard of the passes visited before pass u
-            if (interior) {
-                const float thr = t + sQ[u_hi + 1];
-                int a = u_lo, z = u_hi;                          // largest u in [u_lo,u_hi] with Q[u] >= thr
-                while (a < z) {
-                    const int mid = (a + z + 1) >> 1;
-                    if (sQ[mid] >= thr) a = mid; else z = mid - 1;
+    const int base = blockIdx.x * PS_CHUNK;
+
+    int cnt[PS_PER];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < PS_PER; ++j) {
+        const int idx = base + j * PS_THREADS + tid;
+        int n = 0;
+        if (idx < H * W) n = (int)__ldg(din + (size_t)(p + idx / W) * P.Wpitch + p + idx % W);
+        cnt[j] = n > 0 ? n : 0;
+        mine += (cnt[j] + 7) >> 3;
+    }
+    // exclusive scan of the per-thread item counts over the CTA
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < PS_THREADS / 32; ++w) { const int t = s_warp[w]; s_warp[w] = run; run += t; }
+        s_total = run;
+    }
+    __syncthreads();
+    const int first = s_warp[warp] + incl - mine;        // index of this thread's first item
+    const int total = s_total;
+
+    for (int win = 0; win < total; win += PS_ITEMS) {    // rounds of at most PS_ITEMS items
+        int g = first;
+#pragma unroll
+        for (int j = 0; j < PS_PER; ++j) {
+            const int subs = (cnt[j] + 7) >> 3;
+            for (int s = 0; s < subs; ++s, ++g) {
+                if (g >= win && g < win + PS_ITEMS) {
+                    const int m = min(8, cnt[j] - 8 * s);
+                    items[g - win] = (uint32_t)(j * PS_THREADS + tid) | ((uint32_t)min(s, 4095) << 12) | ((uint32_t)m << 24);
                 }
-                u = a;
-                before = sQ[u + 1] - sQ[u_hi + 1];
-            } else {
-                float cum = 0.f;
-                u = u_lo; before = 0.f;
-                for (int uu = u_hi; uu >= u_lo; --uu) {
-                    const float hz = sCH[uu * KP + lo] - sCH[uu * KP + hi + 1];
-                    if (cum + hz >= t || uu == u_lo) { u = uu; before = cum; break; }
-                    cum += hz;
-                }
-            }
-            const int r = y - u;
-            if (!FILL) {
-                atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
-            } else {
-                // tap: largest v in [lo,hi] whose suffix hazard still covers the in-pass position
-                const float* ch = sCH + u * KP;
-                const float thr = fmaxf(t - before, 0.f) + ch[hi + 1];
-                int a = lo, z = hi;
-                while (a < z) {
-                    const int mid = (a + z + 1) >> 1;
-                    if (ch[mid] >= thr) a = mid; else z = mid - 1;
-                }
-                const unsigned long long slot = (unsigned long long)ws.off[(size_t)b * H + r] +
-                                                (unsigned long long)atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
-                if (slot < ws.cap) ws.ev[slot] = (uint32_t)x | ((uint32_t)u << 12) | ((uint32_t)a << 18);
-                else atomicAdd(&ws.status[0], 1);
             }
         }
+        __syncthreads();
+        const int n_items = min(PS_ITEMS, total - win);
+        for (int q = tid; q < n_items; q += PS_THREADS) {
+            const uint32_t it = items[q];
+            const int idx = base + (int)(it & 0xFFFu), sub = (it >> 12) & 0xFFF, m = it >> 24;
+            const int y = p + idx / W, x = p + idx % W;
+            const int lo = max(0, x - W + 1), hi = min(K - 1, x);        // taps that ever visit this column
+            const int u_hi = min(K - 1, y), u_lo = max(0, y - (H - 1));   // passes, visited from u_hi down to u_lo
+            const float* qa = sQQ + lo * KP;
+            const float* qb = sQQ + (hi + 1) * KP;
+            const float g_end = qa[u_hi + 1] - qb[u_hi + 1];
+            const float htot = (qa[u_lo] - qb[u_lo]) - g_end;
+            PhiloxStream rng;
+            rng.init(P.seed, P.offset, env, (uint32_t)(y * Wp + x), STED_RNG_BLEACH, (uint32_t)sub);
+            const int dead = binomial_deaths(m, htot, rng);
+            const float pd = -expm1f(-htot);
+            for (int d = 0; d < dead; ++d) {
+                // hazard this molecule had consumed when it died: truncated Exp(1) on (0, htot)
+                const float t = fminf(-log1pf(-rng.uniform() * pd), htot);
+                const float thr = t + g_end;
+                int a = u_lo, z = u_hi;                  // largest u in [u_lo,u_hi] with G(u) >= thr
+                while (a < z) {
+                    const int mid = (a + z + 1) >> 1;
+                    if (qa[mid] - qb[mid] >= thr) a = mid; else z = mid - 1;
+                }
+                const int u = a, r = y - u;
+                if (!FILL) {
+                    atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
+                } else {
+                    // tap: largest v in [lo,hi] whose suffix hazard still covers the in-pass position
+                    const float before = (qa[u + 1] - qb[u + 1]) - g_end;
+                    const float* ch = sCH + u * KP;
+                    const float thr2 = fmaxf(t - before, 0.f) + ch[hi + 1];
+                    int a2 = lo, z2 = hi;
+                    while (a2 < z2) {
+                        const int mid = (a2 + z2 + 1) >> 1;
+                        if (ch[mid] >= thr2) a2 = mid; else z2 = mid - 1;
+                    }
+                    const unsigned long long slot = (unsigned long long)ws.off[(size_t)b * H + r] +
+                                                    (unsigned long long)atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
+                    if (slot < ws.cap) ws.ev[slot] = (uint32_t)x | ((uint32_t)u << 12) | ((uint32_t)a2 << 18);
+                    else atomicAdd(&ws.status[0], 1);
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -756,13 +796,13 @@ int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cu
     ws.cap = (workspace_bytes - fixed) / sizeof(uint32_t);
     if (ws.cap > 0x7FFFFFFFull) ws.cap = 0x7FFFFFFFull;
     CUDA_TRY(cudaMemsetAsync(workspace, 0, 16 + (size_t)n * sizeof(int), st));
-    const size_t psmem = ((size_t)P.K * P.KP + P.K + 4) * sizeof(float);
-    dim3 pgrid((unsigned)((P.H * P.W + 255) / 256 < 128 ? (P.H * P.W + 255) / 256 : 128), P.B);
-    presample_kernel<false><<<pgrid, 256, psmem, st>>>(P, ws);
+    const size_t psmem = ((size_t)(2 * P.K + 1) * P.KP + PS_ITEMS) * sizeof(float);
+    dim3 pgrid((unsigned)((P.H * P.W + PS_CHUNK - 1) / PS_CHUNK), P.B);
+    presample_kernel<false><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
     CUDA_TRY(cudaGetLastError());
     bucket_scan_kernel<<<1, 1024, 0, st>>>(ws, n);
     CUDA_TRY(cudaGetLastError());
-    presample_kernel<true><<<pgrid, 256, psmem, st>>>(P, ws);
+    presample_kernel<true><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
     CUDA_TRY(cudaGetLastError());
     return launch_sweep_m<true>(P, ws, st);
 }
