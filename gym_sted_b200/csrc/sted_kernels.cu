@@ -7,6 +7,7 @@
 // gym_sted/utils.py:616-631,646-657.  See DESIGN.md for the derivations.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
@@ -125,22 +126,64 @@ __device__ __forceinline__ float detect(const AcqParams& P, float I, float gain,
 // smem: datamap tile (64+K-1) x (64+KP) floats + E table.  Per 4 taps and 8 output rows a
 // thread issues 1 LDS.128 of datamap (sliding window) + 8 broadcast LDS.128 of E for 128 FFMA.
 // ------------------------------------------------------------------------------------------
-constexpr int G_TH = 64, G_TW = 64, G_RT = 8, G_THREADS = 128;
+#ifndef G_UNROLL
+#define G_UNROLL 5   // tap chunks (of 4) unrolled per iteration of the gather's inner loop
+#endif
+#ifndef G_TILE_H
+#define G_TILE_H 64
+#endif
+constexpr int G_TH = G_TILE_H, G_TW = 64, G_RT = 8, G_THREADS = 2 * G_TILE_H, kGatherUnroll = G_UNROLL;
+constexpr int G_MINB = G_TILE_H == 64 ? 3 : 2;
+
+#ifndef GATHER_TMA
+#define GATHER_TMA 1   // 0: stage the tile with coalesced float4 loads instead of TMA (A/B timing only)
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (long long spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1ll << 28)) __trap();           // a lost TMA must not hang the GPU
+    }
+}
 
 template <int KT>
-__global__ void __launch_bounds__(G_THREADS, 3) gather_kernel(const AcqParams P) {
+__global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqParams P, const __grid_constant__ CUtensorMap tmap) {
     const int K = KT ? KT : P.K;
     const int KP = KT ? STED_KPITCH(KT) : P.KP;
     const int PITCH = G_TW + KP;
     const int rows = G_TH + K - 1;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* sD = smem;
     float* sE = smem + rows * PITCH;
+    __shared__ __align__(8) unsigned long long mbar;
 
     const int b = blockIdx.z;
     const int tr0 = blockIdx.y * G_TH, tc0 = blockIdx.x * G_TW;
     const int tid = threadIdx.x;
 
+#if GATHER_TMA
+    // ---- stage tile + PSF with TMA: one 3-D tensor box (zero filled outside the padded map) and one bulk copy,
+    // both completing on the same mbarrier
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes_d = (uint32_t)(rows * PITCH * sizeof(float)), bytes_e = (uint32_t)(K * KP * sizeof(float));
+        const float* gE = P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(bytes_d + bytes_e) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     :: "r"(smem_u32(sD)), "l"(&tmap), "r"(tc0), "r"(tr0), "r"(b), "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(sE)), "l"(gE), "r"(bytes_e), "r"(smem_u32(&mbar)) : "memory");
+    }
+    mbar_wait(smem_u32(&mbar), 0);
+#else
     // ---- stage tile + PSF (float4, zero fill outside the padded map)
     {
         const float* src = P.din + (size_t)b * P.Hp * P.Wpitch;
@@ -156,6 +199,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gather_kernel(const AcqParams P)
         for (int i = tid; i < K * KP / 4; i += G_THREADS) reinterpret_cast<float4*>(sE)[i] = __ldg(e4 + i);
     }
     __syncthreads();
+#endif
 
     const int lane16 = tid & 15, rg = tid >> 4;
     const int r0 = rg * G_RT, c0 = lane16 * 4;
@@ -167,7 +211,7 @@ __global__ void __launch_bounds__(G_THREADS, 3) gather_kernel(const AcqParams P)
     auto band_row = [&](const int yy, const bool check) {
         const float* drow = sD + (r0 + yy) * PITCH + c0;
         float4 wa = *reinterpret_cast<const float4*>(drow);
-#pragma unroll 5
+#pragma unroll kGatherUnroll
         for (int vc = 0; vc < nchunk; ++vc) {
             const float4 wb = *reinterpret_cast<const float4*>(drow + 4 * (vc + 1));
 #pragma unroll
@@ -307,7 +351,7 @@ constexpr int PS_THREADS = 256, PS_CHUNK = 4096, PS_ITEMS = 2048, PS_PER = PS_CH
 template <bool FILL>
 __global__ void __launch_bounds__(PS_THREADS) presample_kernel(const AcqParams P, const BleachWs ws) {
     const int K = P.K, KP = P.KP, H = P.H, W = P.W, Wp = P.Wp;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* sCH = smem;                                   // [K][KP]
     float* sQQ = sCH + K * KP;                           // [K+1][KP]
     uint32_t* items = reinterpret_cast<uint32_t*>(sQQ + (K + 1) * KP);      // [PS_ITEMS] pixel | sub<<12 | m<<24
@@ -456,7 +500,7 @@ __global__ void __launch_bounds__(S_THREADS, STOCH ? 3 : 2) sweep_kernel(const A
     const int PR = sweep_pitch(TC, KP);
     const int span = TC + K - 1;
 
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* ring = smem;                       // [K][PR]  band of the molecule map (counts / scaled expectations)
     float* sWt = ring + K * PR;               // [K][KP]  gather weights: E (stochastic) or ET (expectation)
     float* sI = sWt + K * KP;                 // [2][TC]  dense row intensities (even / odd scan rows)
@@ -739,16 +783,45 @@ int set_smem(Kern kern, size_t bytes) {
     return STED_OK;
 }
 
+// 3-D tensor map of the padded molecule maps [B][Hp][Wpitch] with a (tile + halo) box; elements outside the
+// map read as zero, so edge tiles need no special case.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tile_map(const AcqParams& P, CUtensorMap* map) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(STED_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)P.Wpitch, (cuuint64_t)P.Hp, (cuuint64_t)P.B};
+    const cuuint64_t strides[2] = {(cuuint64_t)P.Wpitch * sizeof(float), (cuuint64_t)P.Hp * P.Wpitch * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)(G_TW + P.KP), (cuuint32_t)(G_TH + P.K - 1), 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (((uintptr_t)P.din & 15u) != 0) return fail(STED_EINVAL, "dmap_in_dev must be 16-byte aligned");
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(P.din), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(STED_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return STED_OK;
+}
+
 int launch_gather(const AcqParams& P, cudaStream_t st) {
     const size_t smem = ((size_t)(G_TH + P.K - 1) * (G_TW + P.KP) + (size_t)P.K * P.KP) * sizeof(float);
     dim3 grid((P.W + G_TW - 1) / G_TW, (P.H + G_TH - 1) / G_TH, P.B);
+    CUtensorMap map;
     int rc;
+    if ((rc = make_tile_map(P, &map))) return rc;
     if (P.K == 59) {
         if ((rc = set_smem(gather_kernel<59>, smem))) return rc;
-        gather_kernel<59><<<grid, G_THREADS, smem, st>>>(P);
+        gather_kernel<59><<<grid, G_THREADS, smem, st>>>(P, map);
     } else {
         if ((rc = set_smem(gather_kernel<0>, smem))) return rc;
-        gather_kernel<0><<<grid, G_THREADS, smem, st>>>(P);
+        gather_kernel<0><<<grid, G_THREADS, smem, st>>>(P, map);
     }
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
@@ -947,10 +1020,39 @@ int sted_detect(float* signal_dev, const double* pdt_dev, int B, int H, int W, u
     return launch_detect(P, (cudaStream_t)stream);
 }
 
-int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const StedFluoParams* fluo_host,
-                      const double* p_ex_host, const double* p_sted_host, const double* pdt_host, int B, int H, int W,
-                      int K, uint32_t flags, const StedDetectorParams* det, uint64_t seed, uint64_t offset,
-                      int64_t env_base, float* intensity_host, float* signal_host) {
+}  // extern "C" (re-opened below)
+
+namespace {
+
+// Streams / events of the host-buffer entry point: upload, compute and download of different chunks overlap.
+struct HostPipe {
+    static constexpr int MAXC = 8;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[MAXC], e_comp[MAXC];
+    int* h_drop = nullptr;               // pinned: dropped-event counter of each chunk
+    bool ready = false;
+    int init() {
+        if (ready) return STED_OK;
+        CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < MAXC; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&e_comp[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaMallocHost(&h_drop, MAXC * sizeof(int)));
+        ready = true;
+        return STED_OK;
+    }
+};
+HostPipe g_pipe;
+
+}  // namespace
+
+extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const StedFluoParams* fluo_host,
+                                 const double* p_ex_host, const double* p_sted_host, const double* pdt_host, int B, int H,
+                                 int W, int K, uint32_t flags, const StedDetectorParams* det, uint64_t seed, uint64_t offset,
+                                 int64_t env_base, float* intensity_host, float* signal_host) {
     if (!dmap_host || !psf_cache_host || !fluo_host || !p_ex_host || !p_sted_host || !pdt_host || !signal_host || !det)
         return fail(STED_EINVAL, "null pointer argument");
     if (B <= 0 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B, H, W must be positive");
@@ -959,20 +1061,25 @@ int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const Sted
     int rc = check_device();
     if (rc) return rc;
     std::lock_guard<std::mutex> lock(g_ws.mu);
+    if ((rc = g_pipe.init())) return rc;
     const int KP = STED_KPITCH(K), Hp = H + K - 1, Wp = W + K - 1, Wpitch = (Wp + 3) & ~3, p = K / 2;
-    const size_t n_roi = (size_t)B * H * W, n_pad = (size_t)B * Hp * Wpitch;
+    const size_t px_roi = (size_t)H * W, px_pad = (size_t)Hp * Wpitch;
+    const size_t n_roi = (size_t)B * px_roi, n_pad = (size_t)B * px_pad;
     enum { ROI, PADA, PADB, TAB, CACHE, FLUO, SCAL, OUT, WS };
-    const bool stoch = (flags & STED_BLEACH) && (flags & STED_SAMPLE_BLEACH);
+    const bool bleach = (flags & STED_BLEACH) != 0;
+    const bool stoch = bleach && (flags & STED_SAMPLE_BLEACH);
+    // chunks: upload of chunk i+1, compute of chunk i and download of chunk i-1 run concurrently
+    const int nch = B >= 32 ? 4 : (B >= 8 ? 2 : 1);
+    const int cb = (B + nch - 1) / nch;
     // scratch of the stochastic scan: starts at 4 deaths per pixel and grows when a scan reports dropped events
     static unsigned long long s_max_events = 0;
-    if (stoch && s_max_events < 4ull * n_roi) s_max_events = 4ull * n_roi;
+    if (stoch && s_max_events < 4ull * cb * px_roi) s_max_events = 4ull * cb * px_roi;
     if ((rc = g_ws.ensure(ROI, n_roi * 4)) || (rc = g_ws.ensure(PADA, n_pad * 4)) ||
-        (rc = g_ws.ensure(PADB, (flags & STED_BLEACH) ? n_pad * 4 : 16)) ||
+        (rc = g_ws.ensure(PADB, bleach ? n_pad * 4 : 16)) ||
         (rc = g_ws.ensure(TAB, (size_t)B * STED_TABLES * K * KP * 4)) || (rc = g_ws.ensure(CACHE, 3ull * K * K * 8)) ||
         (rc = g_ws.ensure(FLUO, (size_t)B * sizeof(StedFluoParams))) || (rc = g_ws.ensure(SCAL, 3ull * B * 8)) ||
         (rc = g_ws.ensure(OUT, 2 * n_roi * 4)))
         return rc;
-    cudaStream_t st = 0;
     float* d_roi = (float*)g_ws.dev[ROI];
     float* d_a = (float*)g_ws.dev[PADA];
     float* d_b = (float*)g_ws.dev[PADB];
@@ -982,42 +1089,66 @@ int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const Sted
     double* d_scal = (double*)g_ws.dev[SCAL];
     float* d_int = (float*)g_ws.dev[OUT];
     float* d_sig = d_int + n_roi;
-    CUDA_TRY(cudaMemcpyAsync(d_roi, dmap_host, n_roi * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_cache, psf_cache_host, 3ull * K * K * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_fluo, fluo_host, (size_t)B * sizeof(StedFluoParams), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_scal, p_ex_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_scal + B, p_sted_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_scal + 2 * B, pdt_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-    pad_kernel<<<592, 256, 0, st>>>(d_roi, d_a, B, H, W, p, Hp, Wpitch);
-    CUDA_TRY(cudaGetLastError());
-    if ((rc = sted_make_effective(d_cache, d_fluo, d_scal, d_scal + B, d_scal + 2 * B, B, K, d_tab, nullptr, st))) return rc;
+    cudaStream_t s_in = g_pipe.s_in, s_comp = g_pipe.s_comp, s_out = g_pipe.s_out;
+
+    CUDA_TRY(cudaMemcpyAsync(d_cache, psf_cache_host, 3ull * K * K * 8, cudaMemcpyHostToDevice, s_in));
+    CUDA_TRY(cudaMemcpyAsync(d_fluo, fluo_host, (size_t)B * sizeof(StedFluoParams), cudaMemcpyHostToDevice, s_in));
+    CUDA_TRY(cudaMemcpyAsync(d_scal, p_ex_host, (size_t)B * 8, cudaMemcpyHostToDevice, s_in));
+    CUDA_TRY(cudaMemcpyAsync(d_scal + B, p_sted_host, (size_t)B * 8, cudaMemcpyHostToDevice, s_in));
+    CUDA_TRY(cudaMemcpyAsync(d_scal + 2 * B, pdt_host, (size_t)B * 8, cudaMemcpyHostToDevice, s_in));
+
+    bool uploaded = false;
     for (int attempt = 0;; ++attempt) {
         size_t ws_bytes = 0;
         if (stoch) {
-            ws_bytes = bleach_ws_bytes(B, H, s_max_events);
+            ws_bytes = bleach_ws_bytes(cb, H, s_max_events);
             if ((rc = g_ws.ensure(WS, ws_bytes))) return rc;
         }
-        if ((rc = sted_acquire(d_a, (flags & STED_BLEACH) ? d_b : nullptr, d_tab, d_scal + 2 * B, B, H, W, K, flags, det,
-                               fluo_host[0].lambda_fluo, seed, offset, env_base, intensity_host ? d_int : nullptr, d_sig,
-                               stoch ? g_ws.dev[WS] : nullptr, ws_bytes, st)))
-            return rc;
-        if (!stoch) break;
-        int dropped = 0;
-        if ((rc = sted_bleach_dropped_events(g_ws.dev[WS], &dropped, st))) return rc;
-        if (dropped == 0) break;
+        for (int c = 0; c < nch; ++c) {
+            const int b0 = c * cb, nb = (B - b0 < cb) ? B - b0 : cb;
+            if (nb <= 0) break;
+            const size_t o_roi = (size_t)b0 * px_roi, o_pad = (size_t)b0 * px_pad;
+            if (!uploaded) {
+                CUDA_TRY(cudaMemcpyAsync(d_roi + o_roi, dmap_host + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyHostToDevice, s_in));
+                CUDA_TRY(cudaEventRecord(g_pipe.e_in[c], s_in));
+                CUDA_TRY(cudaStreamWaitEvent(s_comp, g_pipe.e_in[c], 0));
+                pad_kernel<<<296, 256, 0, s_comp>>>(d_roi + o_roi, d_a + o_pad, nb, H, W, p, Hp, Wpitch);
+                CUDA_TRY(cudaGetLastError());
+                if ((rc = sted_make_effective(d_cache, d_fluo + b0, d_scal + b0, d_scal + B + b0, d_scal + 2 * B + b0, nb, K,
+                                              d_tab + (size_t)b0 * STED_TABLES * K * KP, nullptr, s_comp)))
+                    return rc;
+            }
+            if ((rc = sted_acquire(d_a + o_pad, bleach ? d_b + o_pad : nullptr, d_tab + (size_t)b0 * STED_TABLES * K * KP,
+                                   d_scal + 2 * B + b0, nb, H, W, K, flags, det, fluo_host[0].lambda_fluo, seed, offset,
+                                   env_base + b0, intensity_host ? d_int + o_roi : nullptr, d_sig + o_roi,
+                                   stoch ? g_ws.dev[WS] : nullptr, ws_bytes, s_comp)))
+                return rc;
+            g_pipe.h_drop[c] = 0;
+            if (stoch) CUDA_TRY(cudaMemcpyAsync(&g_pipe.h_drop[c], g_ws.dev[WS], sizeof(int), cudaMemcpyDeviceToHost, s_comp));
+            if (bleach) {
+                unpad_kernel<<<296, 256, 0, s_comp>>>(d_b + o_pad, d_roi + o_roi, nb, H, W, p, Hp, Wpitch);
+                CUDA_TRY(cudaGetLastError());
+            }
+            CUDA_TRY(cudaEventRecord(g_pipe.e_comp[c], s_comp));
+            CUDA_TRY(cudaStreamWaitEvent(s_out, g_pipe.e_comp[c], 0));
+            if (bleach) CUDA_TRY(cudaMemcpyAsync(dmap_host + o_roi, d_roi + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
+            if (intensity_host)
+                CUDA_TRY(cudaMemcpyAsync(intensity_host + o_roi, d_int + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
+            CUDA_TRY(cudaMemcpyAsync(signal_host + o_roi, d_sig + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
+        }
+        CUDA_TRY(cudaStreamSynchronize(s_comp));
+        CUDA_TRY(cudaStreamSynchronize(s_out));
+        uploaded = true;                 // the padded inputs stay on the device: a re-run needs no new upload
+        long long dropped = 0;
+        for (int c = 0; c < nch; ++c) dropped += g_pipe.h_drop[c];
+        if (!stoch || dropped == 0) break;
         if (attempt >= 8) return fail(STED_ECUDA, "stochastic scan kept overflowing its event scratch");
         s_max_events = s_max_events * 2 + (unsigned long long)dropped;     // same seed => same deaths on the re-run
     }
-    if (flags & STED_BLEACH) {
-        unpad_kernel<<<592, 256, 0, st>>>(d_b, d_roi, B, H, W, p, Hp, Wpitch);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(dmap_host, d_roi, n_roi * 4, cudaMemcpyDeviceToHost, st));
-    }
-    if (intensity_host) CUDA_TRY(cudaMemcpyAsync(intensity_host, d_int, n_roi * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(signal_host, d_sig, n_roi * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     return STED_OK;
 }
+
+extern "C" {
 
 int sted_sample_poisson(const float* lambda_dev, int64_t n, uint64_t seed, uint64_t offset, float* out_dev, void* stream) {
     if (!lambda_dev || !out_dev || n <= 0) return fail(STED_EINVAL, "bad argument");
