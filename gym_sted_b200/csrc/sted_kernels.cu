@@ -1027,16 +1027,16 @@ namespace {
 // Streams / events of the host-buffer entry point: upload, compute and download of different chunks overlap.
 struct HostPipe {
     static constexpr int MAXC = 8;
-    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[MAXC];   // one compute stream per chunk: their kernels co-run
     cudaEvent_t e_in[MAXC], e_comp[MAXC];
     int* h_drop = nullptr;               // pinned: dropped-event counter of each chunk
     bool ready = false;
     int init() {
         if (ready) return STED_OK;
         CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
         for (int i = 0; i < MAXC; ++i) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s_comp[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&e_comp[i], cudaEventDisableTiming));
         }
@@ -1089,7 +1089,7 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
     double* d_scal = (double*)g_ws.dev[SCAL];
     float* d_int = (float*)g_ws.dev[OUT];
     float* d_sig = d_int + n_roi;
-    cudaStream_t s_in = g_pipe.s_in, s_comp = g_pipe.s_comp, s_out = g_pipe.s_out;
+    cudaStream_t s_in = g_pipe.s_in, s_out = g_pipe.s_out;
 
     CUDA_TRY(cudaMemcpyAsync(d_cache, psf_cache_host, 3ull * K * K * 8, cudaMemcpyHostToDevice, s_in));
     CUDA_TRY(cudaMemcpyAsync(d_fluo, fluo_host, (size_t)B * sizeof(StedFluoParams), cudaMemcpyHostToDevice, s_in));
@@ -1101,13 +1101,15 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
     for (int attempt = 0;; ++attempt) {
         size_t ws_bytes = 0;
         if (stoch) {
-            ws_bytes = bleach_ws_bytes(cb, H, s_max_events);
-            if ((rc = g_ws.ensure(WS, ws_bytes))) return rc;
+            ws_bytes = (bleach_ws_bytes(cb, H, s_max_events) + 255) & ~(size_t)255;      // one scratch per chunk
+            if ((rc = g_ws.ensure(WS, ws_bytes * nch))) return rc;
         }
         for (int c = 0; c < nch; ++c) {
             const int b0 = c * cb, nb = (B - b0 < cb) ? B - b0 : cb;
             if (nb <= 0) break;
             const size_t o_roi = (size_t)b0 * px_roi, o_pad = (size_t)b0 * px_pad;
+            cudaStream_t s_comp = g_pipe.s_comp[c];
+            char* ws_c = stoch ? (char*)g_ws.dev[WS] + (size_t)c * ws_bytes : nullptr;
             if (!uploaded) {
                 CUDA_TRY(cudaMemcpyAsync(d_roi + o_roi, dmap_host + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyHostToDevice, s_in));
                 CUDA_TRY(cudaEventRecord(g_pipe.e_in[c], s_in));
@@ -1121,10 +1123,10 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
             if ((rc = sted_acquire(d_a + o_pad, bleach ? d_b + o_pad : nullptr, d_tab + (size_t)b0 * STED_TABLES * K * KP,
                                    d_scal + 2 * B + b0, nb, H, W, K, flags, det, fluo_host[0].lambda_fluo, seed, offset,
                                    env_base + b0, intensity_host ? d_int + o_roi : nullptr, d_sig + o_roi,
-                                   stoch ? g_ws.dev[WS] : nullptr, ws_bytes, s_comp)))
+                                   ws_c, ws_bytes, s_comp)))
                 return rc;
             g_pipe.h_drop[c] = 0;
-            if (stoch) CUDA_TRY(cudaMemcpyAsync(&g_pipe.h_drop[c], g_ws.dev[WS], sizeof(int), cudaMemcpyDeviceToHost, s_comp));
+            if (stoch) CUDA_TRY(cudaMemcpyAsync(&g_pipe.h_drop[c], ws_c, sizeof(int), cudaMemcpyDeviceToHost, s_comp));
             if (bleach) {
                 unpad_kernel<<<296, 256, 0, s_comp>>>(d_b + o_pad, d_roi + o_roi, nb, H, W, p, Hp, Wpitch);
                 CUDA_TRY(cudaGetLastError());
@@ -1136,7 +1138,7 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
                 CUDA_TRY(cudaMemcpyAsync(intensity_host + o_roi, d_int + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
             CUDA_TRY(cudaMemcpyAsync(signal_host + o_roi, d_sig + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
         }
-        CUDA_TRY(cudaStreamSynchronize(s_comp));
+        for (int c = 0; c < nch; ++c) CUDA_TRY(cudaStreamSynchronize(g_pipe.s_comp[c]));
         CUDA_TRY(cudaStreamSynchronize(s_out));
         uploaded = true;                 // the padded inputs stay on the device: a re-run needs no new upload
         long long dropped = 0;
