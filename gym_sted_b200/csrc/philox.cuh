@@ -53,6 +53,7 @@ STED_HD Philox4 philox4x32_10(Philox4 c, uint32_t k0, uint32_t k1) {
 #define STED_RNG_BLEACH 2u
 #define STED_RNG_TEST   3u
 #define STED_RNG_BLEACH2 4u
+#define STED_RNG_PHOTON2 5u
 
 // Stream of 32-bit words for one (pixel, env, purpose, row) site; refills by bumping a sub-counter.
 struct PhiloxStream {
@@ -68,6 +69,14 @@ struct PhiloxStream {
         ctr.z = (purpose << 28) | ((row & 0xFFFFu) << 12);   // low 12 bits: sub-counter
         ctr.w = offset;
         have = 0;
+    }
+    // stream whose first word is given (drawn elsewhere, e.g. one Philox block shared by four pixels); the
+    // following words come from this site's own counter
+    STED_HD void init_with_first(uint32_t first, uint64_t seed, uint32_t offset, uint32_t env, uint32_t site,
+                                 uint32_t purpose, uint32_t row) {
+        init(seed, offset, env, site, purpose, row);
+        buf.w = first;
+        have = 1;
     }
     STED_HD uint32_t next() {
         if (have == 0) {

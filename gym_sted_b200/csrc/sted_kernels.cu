@@ -35,22 +35,19 @@ constexpr double kLight = 299792458.0;
 //                                                                     (fluo.get_k_bleach)
 //   A = k_b*pdt;  CH[u][v] = sum_{v'>=v} A[u][v'];  ET = E*exp(-CH[u][v+1]);  RS = exp(-CH)
 // ------------------------------------------------------------------------------------------
-__global__ void make_effective_kernel(const double* __restrict__ cache, const StedFluoParams* __restrict__ fluo,
+__global__ void __launch_bounds__(256) make_effective_kernel(const double* __restrict__ cache, const StedFluoParams* __restrict__ fluo,
                                       const double* __restrict__ p_ex, const double* __restrict__ p_sted,
                                       const double* __restrict__ pdt, int K, int KP,
                                       float* __restrict__ tables, double* __restrict__ kbleach) {
+    extern __shared__ double sm_d[];                     // [K*K] E, then [K*K] A = k_b * pdt
+    double* sE = sm_d;
+    double* sA = sm_d + K * K;
     const int b = blockIdx.x;
-    const int u = threadIdx.x;
-    if (u >= K) return;
     const StedFluoParams f = fluo[b];
     const double pex = p_ex[b], psted = p_sted[b], dwell = pdt[b];
     const double* i_ex = cache;
     const double* i_sted = cache + (size_t)K * K;
     const double* psf_det = cache + 2 * (size_t)K * K;
-    float* tE = tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP + (size_t)u * KP;
-    float* tET = tables + ((size_t)b * STED_TABLES + STED_TAB_ET) * K * KP + (size_t)u * KP;
-    float* tCH = tables + ((size_t)b * STED_TABLES + STED_TAB_CH) * K * KP + (size_t)u * KP;
-    float* tRS = tables + ((size_t)b * STED_TABLES + STED_TAB_RS) * K * KP + (size_t)u * KP;
 
     const double e_ex = kPlanck * kLight / f.lambda_ex;
     const double e_st = kPlanck * kLight / f.lambda_sted;
@@ -60,10 +57,8 @@ __global__ void make_effective_kernel(const double* __restrict__ cache, const St
     const double duty = f.sted_tau * f.sted_rate;
     const double denom = 1.0 - exp(-k_s1 * T);
 
-    for (int v = K; v < KP; ++v) { tE[v] = 0.f; tET[v] = 0.f; tCH[v] = 0.f; tRS[v] = 1.f; }
-    double ch = 0.0;   // suffix hazard, exclusive of the tap being visited on entry
-    for (int v = K - 1; v >= 0; --v) {
-        const int t = u * K + v;
+    // every tap independently (all threads), then one thread per tap row for the suffix sums
+    for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
         const double I_ex = i_ex[t] * pex;
         const double I_st = i_sted[t] * psted;                 // instantaneous, in-pulse
         double exc = f.sigma_abs_ex * I_ex * f.qy;
@@ -72,16 +67,29 @@ __global__ void make_effective_kernel(const double* __restrict__ cache, const St
         const double gamma = zeta * k_vib / (zeta * k_s1 + k_vib);
         const double eta = ((1.0 + gamma * exp(-k_s1 * f.sted_tau * (1.0 + gamma))) / (1.0 + gamma)
                             - exp(-k_s1 * (gamma * f.sted_tau + T))) / denom;
-        const double E = exc * eta * psf_det[t];
         // photon fluxes with get_photons' floor division
         const double phi_ex = floor(I_ex / e_ex);
         const double phi_st = floor(I_st * duty / e_st);        // time averaged
         const double I_inst = phi_st * e_st / duty;
         const double kb = f.sigma_abs_ex * phi_ex * f.sted_tau * (f.k0 * I_inst + f.k1 * pow(I_inst, f.b));
         if (kbleach) kbleach[(size_t)b * K * K + t] = kb;
+        sE[t] = exc * eta * psf_det[t];
+        sA[t] = kb * dwell;
+    }
+    __syncthreads();
+    const int u = threadIdx.x;
+    if (u >= K) return;
+    float* tE = tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP + (size_t)u * KP;
+    float* tET = tables + ((size_t)b * STED_TABLES + STED_TAB_ET) * K * KP + (size_t)u * KP;
+    float* tCH = tables + ((size_t)b * STED_TABLES + STED_TAB_CH) * K * KP + (size_t)u * KP;
+    float* tRS = tables + ((size_t)b * STED_TABLES + STED_TAB_RS) * K * KP + (size_t)u * KP;
+    for (int v = K; v < KP; ++v) { tE[v] = 0.f; tET[v] = 0.f; tCH[v] = 0.f; tRS[v] = 1.f; }
+    double ch = 0.0;   // suffix hazard, exclusive of the tap being visited on entry
+    for (int v = K - 1; v >= 0; --v) {
+        const double E = sE[u * K + v];
         tE[v] = (float)E;
         tET[v] = (float)(E * exp(-ch));
-        ch += kb * dwell;
+        ch += sA[u * K + v];
         tCH[v] = (float)ch;
         tRS[v] = (float)exp(-ch);
     }
@@ -107,13 +115,14 @@ struct AcqParams {
     float background;     // counts per second
 };
 
-// Detector.get_signal fused: photons = floor(I/e_photon); mean = photons*pcef*pdef*pdt + bg*pdt
+// Detector.get_signal: photons = floor(I/e_photon); mean = photons*pcef*pdef*pdt + bg*pdt; Poisson when noisy.
+// `first` is this pixel's first random word (one Philox block serves four neighbouring pixels).
 __device__ __forceinline__ float detect(const AcqParams& P, float I, float gain, float bg_mean,
-                                        uint32_t env, uint32_t site) {
+                                        uint32_t env, uint32_t site, uint32_t first) {
     const float mean = floorf(I * P.inv_e_photon) * gain + bg_mean;
     if (P.flags & STED_SAMPLE_PHOTONS) {
         PhiloxStream rng;
-        rng.init(P.seed, P.offset, env, site, STED_RNG_PHOTON, 0);
+        rng.init_with_first(first, P.seed, P.offset, env, site, STED_RNG_PHOTON2, 0);
         return poisson_sample(mean, rng);
     }
     return mean;
@@ -122,17 +131,21 @@ __device__ __forceinline__ float detect(const AcqParams& P, float I, float gain,
 // ------------------------------------------------------------------------------------------
 // K2: dense PSF-window gather, no bleaching.
 //   I[r][c] = sum_{u,v} E[u][v] * D[r+u][c+v]
-// CTA = 64x64 output tile of one environment, 128 threads, thread = 8 rows x 4 columns.
-// smem: datamap tile (64+K-1) x (64+KP) floats + E table.  Per 4 taps and 8 output rows a
-// thread issues 1 LDS.128 of datamap (sliding window) + 8 broadcast LDS.128 of E for 128 FFMA.
+// CTA = 64x64 output tile of one environment, 256 threads, thread = 4 rows x 4 columns, 3 CTAs (24 warps) per SM.
+// smem: datamap tile (64+K-1) x (64+KP) floats + E table, both staged by TMA.  Per 4 taps and 4 output rows a
+// thread issues 1 LDS.128 of datamap (sliding window) + 4 broadcast LDS.128 of E for 64 FFMA.
 // ------------------------------------------------------------------------------------------
 #ifndef G_UNROLL
-#define G_UNROLL 5   // tap chunks (of 4) unrolled per iteration of the gather's inner loop
+#define G_UNROLL 15  // tap chunks (of 4) unrolled per iteration of the gather's inner loop (15 = the whole tap row)
 #endif
 #ifndef G_TILE_H
 #define G_TILE_H 64
 #endif
-constexpr int G_TH = G_TILE_H, G_TW = 64, G_RT = 8, G_THREADS = 2 * G_TILE_H, kGatherUnroll = G_UNROLL;
+#ifndef G_ROWS_PER_THREAD
+#define G_ROWS_PER_THREAD 4   // measured on B200: 8 -> 2.46 ms, 4 -> 2.0 ms, 2 -> 2.05 ms per 256x256^2 launch
+#endif
+constexpr int G_TH = G_TILE_H, G_TW = 64, G_RT = G_ROWS_PER_THREAD, G_THREADS = (G_TILE_H / G_ROWS_PER_THREAD) * 16,
+              kGatherUnroll = G_UNROLL;
 constexpr int G_MINB = G_TILE_H == 64 ? 3 : 2;
 
 #ifndef GATHER_TMA
@@ -261,12 +274,34 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
 // A separate, light kernel: the Poisson sampler is latency bound and runs at full occupancy here
 // instead of at the 12 warps/SM of the gather kernel.
 __global__ void __launch_bounds__(256) detect_kernel(const AcqParams P) {
-    const size_t hw = (size_t)P.H * P.W, n = hw * P.B;
-    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(o / hw);
+    const size_t hw = (size_t)P.H * P.W;
+    const size_t groups_per_env = (hw + 3) / 4, n_groups = groups_per_env * P.B;
+    const bool vec = (hw & 3) == 0;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(g / groups_per_env);
+        const uint32_t grp = (uint32_t)(g - (size_t)b * groups_per_env);
+        const uint32_t env = P.env_base + (uint32_t)b;
         const float dwell = (float)P.pdt[b];
-        P.signal[o] = detect(P, P.signal[o], P.det_eff * dwell, P.background * dwell, P.env_base + (uint32_t)b,
-                             (uint32_t)(o - (size_t)b * hw));
+        const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
+        Philox4 r4 = {0u, 0u, 0u, 0u};
+        if (P.flags & STED_SAMPLE_PHOTONS) {
+            Philox4 c;
+            c.x = grp; c.y = env; c.z = STED_RNG_PHOTON << 28; c.w = P.offset;
+            r4 = philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+        }
+        float* px = P.signal + (size_t)b * hw + 4 * (size_t)grp;
+        const uint32_t site = 4u * grp;
+        if (vec) {
+            float4 v = *reinterpret_cast<float4*>(px);
+            v.x = detect(P, v.x, gain, bg_mean, env, site, r4.x);
+            v.y = detect(P, v.y, gain, bg_mean, env, site + 1, r4.y);
+            v.z = detect(P, v.z, gain, bg_mean, env, site + 2, r4.z);
+            v.w = detect(P, v.w, gain, bg_mean, env, site + 3, r4.w);
+            *reinterpret_cast<float4*>(px) = v;
+        } else {
+            const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+            for (int j = 0; j < 4 && site + j < hw; ++j) px[j] = detect(P, px[j], gain, bg_mean, env, site + j, w4[j]);
+        }
     }
 }
 
@@ -881,7 +916,7 @@ int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cu
 }
 
 int launch_detect(const AcqParams& P, cudaStream_t st) {
-    const size_t npx = (size_t)P.B * P.H * P.W;
+    const size_t npx = (((size_t)P.H * P.W + 3) / 4) * P.B;      // one thread per group of four pixels
     const size_t want = (npx + 255) / 256;
     const unsigned blocks = (unsigned)(want < 148u * 32u ? want : 148u * 32u);
     detect_kernel<<<blocks, 256, 0, st>>>(P);
@@ -954,8 +989,10 @@ int sted_make_effective(const double* psf_cache_dev, const StedFluoParams* fluo_
     if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
     int rc = check_device();
     if (rc) return rc;
-    make_effective_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(psf_cache_dev, fluo_dev, p_ex_dev, p_sted_dev, pdt_dev,
-                                                               K, STED_KPITCH(K), tables_dev, kbleach_dev);
+    const size_t me_smem = 2 * (size_t)K * K * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(make_effective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)me_smem));
+    make_effective_kernel<<<B, 256, me_smem, (cudaStream_t)stream>>>(psf_cache_dev, fluo_dev, p_ex_dev, p_sted_dev, pdt_dev,
+                                                                      K, STED_KPITCH(K), tables_dev, kbleach_dev);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }
