@@ -285,6 +285,155 @@ class ContextualSTEDMultiObjectivesEnv:
         return None
 
 
+class SyntheticDatamapGenerator:
+    """Stand-in for ``gym_sted/datamaps/datamap.py`` (``DatamapGenerator``): the reference crops 96x96 windows
+    out of U-Net-predicted structure maps under ``./data/datamap/<group>`` which are not shipped
+    (``defaults.py:6-13``).  Here every group gets a procedural structure map in [0, 1] — filaments for
+    actin / tubulin / lifeact, clusters for psd95 / camkii / PSD95-Bassoon — scaled by ``int(N(40, 4))``
+    molecules (``datamap.py:68-85``) and augmented with the same flips / rot90."""
+
+    GROUPS = ["actin", "psd95", "lifeact", "PSD95-Bassoon", "tubulin", "camkii"]
+
+    def __init__(self, shape=(96, 96), molecules=40, molecules_scale=0.1, seed=None):
+        self.shape, self.molecules, self.molecules_scale = shape, molecules, molecules_scale
+        self.rng = np.random.default_rng(seed)
+
+    def sample_group(self):
+        return str(self.rng.choice(self.GROUPS))
+
+    def __call__(self, group):
+        H, W = self.shape
+        yy, xx = np.mgrid[:H, :W].astype(np.float64)
+        img = np.zeros((H, W))
+        if group in ("actin", "tubulin", "lifeact"):
+            width = {"actin": 1.2, "tubulin": 1.0, "lifeact": 1.6}[group]
+            for _ in range(int(self.rng.integers(3, 8))):
+                th = self.rng.uniform(0, np.pi)
+                off = self.rng.uniform(0.1, 0.9) * (H * abs(np.sin(th)) + W * abs(np.cos(th)))
+                d = np.abs(xx * np.cos(th) + yy * np.sin(th) - off + 3 * np.sin(0.08 * (yy * np.cos(th) - xx * np.sin(th))))
+                img = np.maximum(img, np.exp(-0.5 * (d / width) ** 2))
+        else:
+            for _ in range(int(self.rng.integers(8, 25))):
+                cy, cx = self.rng.uniform(4, H - 4), self.rng.uniform(4, W - 4)
+                sig = self.rng.uniform(1.0, 2.5)
+                img = np.maximum(img, np.exp(-0.5 * ((yy - cy) ** 2 + (xx - cx) ** 2) / sig ** 2))
+        img[img < 0.5] = 0.0
+        scale = self.rng.normal(self.molecules, self.molecules_scale * self.molecules)
+        while scale < 1 or scale > self.molecules:
+            scale = self.rng.normal(self.molecules, self.molecules_scale * self.molecules)
+        img = np.floor(img * int(scale))
+        if self.rng.random() < 0.5:
+            img = np.rot90(img, int(self.rng.integers(1, 4)))
+        if self.rng.random() < 0.5:
+            img = np.flip(img, axis=0)
+        if self.rng.random() < 0.5:
+            img = np.flip(img, axis=1)
+        return np.ascontiguousarray(img)
+
+
+FACTORS = {"synthetic": 1.0, "clusters": 2.25, "camkii": 2.25, "psd95": 2.25, "PSD95-Bassoon": 2.25, "actin": 3.0,
+           "tubulin": 3.75, "lifeact": 3.75}          # gym_sted/utils.py:447-456
+
+
+class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
+    """B ``PreferenceCountRateScaleSTEDMultiObjectivesEnv`` environments
+    (``gym_sted/envs/preference_sted_env.py:205-323``): 96x96 structure-map crops, confocal power lowered by
+    x0.75 until the count rate is <= 20 MHz, reward = raw PrefNet score of [Resolution, Bleach, SNR], replaced
+    by -10 when the STED image exceeds the count-rate limit; the observation vector starts with
+    ``conf_params["p_ex"] / P_EX``."""
+
+    def __init__(self, num_envs=1, bleach_sampling="constant", actions=("p_sted", "p_ex", "pdt"), max_episode_steps=30,
+                 max_count_rate=20e6, negative_reward=-10.0, image_size=96, **kw):
+        super().__init__(num_envs, bleach_sampling, actions, max_episode_steps, image_size=image_size, compute_f1=False, **kw)
+        vec = 1 + (len(OBJ_NAMES) + len(self.actions)) * self.max_episode_steps
+        self.observation_space = Tuple((Box(0, 2 ** 16, shape=(self.H, self.W, 3), dtype=np.uint16),
+                                        Box(0, 1, shape=(vec,), dtype=np.float32)))
+        self.max_count_rate, self.negative_reward = max_count_rate, negative_reward
+        self.datamap_generator = SyntheticDatamapGenerator((self.H, self.W), seed=int(self.np_rng.integers(0, 2 ** 31)))
+        self.articulator = rewards.PreferenceArticulator(device="cpu")
+        self.groups = None
+        self.conf_p_ex = None
+
+    def reset(self, seed=None, options=None):
+        if seed is not None:
+            self.np_rng = np.random.default_rng(seed)
+            self.datamap_generator.rng = np.random.default_rng(seed + 1)
+        self.groups = [self.datamap_generator.sample_group() for _ in range(self.B)]
+        self.conf_p_ex = None
+        if self.bleach_sampler.mode != "constant":
+            fluos = []
+            for g in self.groups:
+                self.bleach_sampler._anchor = _ClosedForms(self.microscope, factor=FACTORS[g])
+                fluos.append(base.Fluorescence(**self.bleach_sampler.sample(self.microscope)))
+            self.bm.set_fluorophores(fluos)
+        else:
+            self.microscope = make_microscope(self.bleach_sampler.sample())
+            self.bm.microscope = self.microscope
+            self.bm.set_fluorophores(None)
+        self.current_step = 0
+        self.episode_memory = {"actions": [], "mo_objs": [], "reward": []}
+        state = self._new_datamaps()
+        zeros = torch.zeros_like(state)
+        self.state = torch.stack((state, zeros, zeros), dim=-1)
+        img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+        return (img, np.zeros((self.B, self.observation_space[1].shape[0]), dtype=np.float32)), {}
+
+    def _new_datamaps(self):
+        """``_update_datamap`` (preference_sted_env.py:173-203) with the per-env count-rate loop."""
+        frames = np.stack([self.datamap_generator(g) for g in self.groups])
+        self.bm.set_datamaps(torch.from_numpy(frames), max_molecules=int(frames.sum()))
+        pdt = defaults.PDT
+        if self.conf_p_ex is None:
+            p_ex = np.full(self.B, defaults.P_EX)
+            for _ in range(64):
+                state, _ = self.bm.get_signal_and_bleach(pdt, p_ex, 0.0, bleach=False)
+                hot = (state.amax(dim=(1, 2)) / pdt > self.max_count_rate).cpu().numpy()
+                if not hot.any():
+                    break
+                p_ex = np.where(hot, p_ex * 0.75, p_ex)
+            self.conf_p_ex = p_ex
+        state, _ = self.bm.get_signal_and_bleach(pdt, self.conf_p_ex, 0.0, bleach=False)
+        return state
+
+    def step(self, action):
+        action = np.clip(np.asarray(action, dtype=np.float32).reshape(self.B, len(self.actions)),
+                         self.action_space.low, self.action_space.high)
+        pdt, p_ex, p_sted = self._full_action(action)
+        bm = self.bm
+        conf1, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)           # _acquire uses the DEFAULT confocal params
+        sted, _ = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True)
+        conf2, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)
+        bleached = bm.datamaps_roi().clone()
+        fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
+        res = rewards.resolution(sted)
+        mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)
+        if np.isnan(mo_objs).any():
+            raise TypeError("SNR objective is None (negative signal ratio): the reference fails here as well")
+        scores, _, _ = self.articulator.articulate(mo_objs, use_sigmoid=False)
+        reward = scores.ravel().astype(np.float64)
+        count_rate = sted.amax(dim=(1, 2)).cpu().numpy() / pdt
+        reward = np.where(count_rate > self.max_count_rate, self.negative_reward, reward)
+
+        done = self.current_step >= self.max_episode_steps - 1
+        self.current_step += 1
+        self.episode_memory["mo_objs"].append(mo_objs)
+        self.episode_memory["actions"].append(action)
+        self.episode_memory["reward"].append(reward)
+        info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,
+                "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "sample": list(self.groups),
+                "conf_params": [{"pdt": defaults.PDT, "p_ex": float(p), "p_sted": 0.0} for p in self.conf_p_ex]}
+        obs = [(self.conf_p_ex / defaults.P_EX)[:, None]]
+        for a, mo in zip(self.episode_memory["actions"], self.episode_memory["mo_objs"]):
+            obs.append(self.action_normalizer(a) if self.normalize_observations else a)
+            obs.append(self.obj_normalizer(mo) if self.normalize_observations else mo)
+        obs = np.concatenate(obs, axis=1)
+        obs = np.pad(obs, ((0, 0), (0, self.observation_space[1].shape[0] - obs.shape[1])))
+        state = self._new_datamaps()
+        self.state = torch.stack((state, conf1, sted), dim=-1)
+        img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+        return (img, obs.astype(np.float32)), reward, np.full(self.B, done), np.zeros(self.B, dtype=bool), info
+
+
 # ids and kwargs of gym_sted/__init__.py:587-610,665-674 (Appendix C)
 REGISTRY = {
     "ContextualMOSTED-easy-v0": dict(max_episode_steps=10, kwargs=dict(
@@ -294,6 +443,9 @@ REGISTRY = {
         scale_nanodomain_reward=1.0)),
     "ContextualMOSTED-hard-v0": dict(max_episode_steps=10, kwargs=dict(
         actions=["p_sted", "p_ex", "pdt"], bleach_sampling="uniform", scale_nanodomain_reward=1.0)),
+    # gym_sted/__init__.py:522-531
+    "PreferenceCountRateMOSTED-hard-v0": dict(max_episode_steps=30, cls="preference", kwargs=dict(
+        actions=["p_sted", "p_ex", "pdt"], bleach_sampling="uniform", max_episode_steps=30)),
 }
 
 
@@ -303,6 +455,8 @@ def make(env_id: str, **overrides):
     if key not in REGISTRY:
         raise KeyError(f"unknown environment id {env_id!r}; known: {sorted(REGISTRY)}")
     entry = REGISTRY[key]
+    if entry.get("cls") == "preference":
+        raise NotImplementedError("PreferenceCountRateMOSTED is provided as a vector env: use make_vec(id, num_envs)")
     env = ContextualSTEDMultiObjectivesEnv(max_episode_steps=entry["max_episode_steps"], **{**entry["kwargs"], **overrides})
     env.spec = SimpleNamespace(id=key, max_episode_steps=entry["max_episode_steps"])
     return env
@@ -311,4 +465,6 @@ def make(env_id: str, **overrides):
 def make_vec(env_id: str, num_envs: int, **overrides):
     key = env_id.split(":")[-1]
     entry = REGISTRY[key]
-    return VectorContextualMOSTED(num_envs, max_episode_steps=entry["max_episode_steps"], **{**entry["kwargs"], **overrides})
+    kwargs = {"max_episode_steps": entry["max_episode_steps"], **entry["kwargs"], **overrides}
+    cls = VectorPreferenceCountRateMOSTED if entry.get("cls") == "preference" else VectorContextualMOSTED
+    return cls(num_envs, **kwargs)

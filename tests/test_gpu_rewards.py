@@ -132,3 +132,26 @@ def test_vector_env_routine_and_per_env_fluorophores():
     # closed-form sampler: sigma_abs and k1 inside the ranges spanned by the reference's fitted routines x the criteria
     f = hard.bleach_sampler.sample(hard.microscope)
     assert 1e-23 < f["sigma_abs"][635] < 2e-20 and 1e-18 < f["k1"] < 1e-13
+
+
+def test_preference_count_rate_env():
+    """Config 4: 96x96 crops, count-rate loop on the confocal power, PrefNet reward with the -10 penalty."""
+    _gpu()
+    vec = envs.make_vec("PreferenceCountRateMOSTED-hard-v0", 4, seed=2)
+    assert vec.observation_space[0].shape == (96, 96, 3) and vec.observation_space[1].shape == (1 + 6 * 30,)
+    (img, v), _ = vec.reset(seed=2)
+    assert img.shape == (4, 96, 96, 3) and v.shape == (4, 181) and not v.any()
+    assert np.all(vec.conf_p_ex <= defaults.P_EX) and np.all(vec.conf_p_ex > 0)
+    assert np.all(img[..., 0].reshape(4, -1).max(1) / defaults.PDT <= 20e6)      # the loop enforced the count rate
+    acts = np.tile(np.array([[0.08, 5e-6, 15e-6]], dtype=np.float32), (4, 1))
+    acts[3] = [0.0, 20e-6, 100e-6]                                                # confocal at full power, long dwell
+    (img, v), reward, done, trunc, info = vec.step(acts)
+    assert set(info) == {"action", "bleached", "sted_image", "conf1", "conf2", "fg_c", "fg_s", "mo_objs", "reward", "sample",
+                         "conf_params"}
+    np.testing.assert_allclose(v[:, 0], vec.conf_p_ex / defaults.P_EX, rtol=1e-6)
+    rate = info["sted_image"].amax(dim=(1, 2)).cpu().numpy() / acts[:, 2]
+    assert np.array_equal(reward == -10.0, rate > 20e6)
+    ok = reward != -10.0
+    art = rewards.PreferenceArticulator()
+    np.testing.assert_allclose(reward[ok], art.articulate(info["mo_objs"][ok])[0].ravel(), rtol=1e-6)
+    assert not done.any() and vec.max_episode_steps == 30

@@ -56,9 +56,15 @@ def test_prefnet_known_answer():
 
 def test_registry_and_spaces_without_gpu():
     from gym_sted_b200 import envs
-    assert set(envs.REGISTRY) == {"ContextualMOSTED-easy-v0", "ContextualMOSTED-easy-hslb-v0", "ContextualMOSTED-hard-v0"}
-    for entry in envs.REGISTRY.values():
-        assert entry["max_episode_steps"] == 10 and entry["kwargs"]["actions"] == ["p_sted", "p_ex", "pdt"]
+    assert set(envs.REGISTRY) == {"ContextualMOSTED-easy-v0", "ContextualMOSTED-easy-hslb-v0", "ContextualMOSTED-hard-v0",
+                                  "PreferenceCountRateMOSTED-hard-v0"}
+    for key, entry in envs.REGISTRY.items():
+        assert entry["max_episode_steps"] == (30 if key.startswith("Preference") else 10)
+        assert entry["kwargs"]["actions"] == ["p_sted", "p_ex", "pdt"]
+    gen = envs.SyntheticDatamapGenerator(seed=0)
+    for g in gen.GROUPS:
+        d = gen(g)
+        assert d.shape == (96, 96) and d.min() == 0 and 15 <= d.max() <= 40 and np.array_equal(d, np.floor(d))
     box = envs.Box(np.array([0, 0, 1e-6], dtype=np.float32), np.array([0.35, 20e-6, 100e-6], dtype=np.float32))
     assert box.shape == (3,) and box.contains(box.sample(np.random.default_rng(0)))
     norm = envs.Normalizer(["p_sted", "p_ex", "pdt"], defaults.action_spaces)
