@@ -222,3 +222,243 @@ extern "C" int sted_foreground_objectives(const float* conf1_dev, const float* s
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }
+
+// =============================================================================================================
+// Nanodomain candidate detection (the integer part of NumberNanodomains.evaluate,
+// gym_sted/rewards/objectives.py:416-422):
+//     filtered = skimage.filters.gaussian(sted, sigma=0.5)      (scipy.ndimage.gaussian_filter, mode nearest, truncate 4)
+//     mask     = filtered > numpy.quantile(filtered, 0.99)
+//     mask     = remove_small_objects(mask, min_size=4, connectivity=2);  labels = measure.label(mask)
+//     peaks    = peak_local_max(filtered, min_distance=2, labels=labels, exclude_border=False)
+// Everything is float64 in the reference; the float operations are replayed in the same order with explicitly
+// rounded multiplies/adds (no FMA contraction), so the filtered image, the quantile and therefore the integer
+// outputs (mask, labels, peak coordinates) are bit-identical.  One CTA per image; the mask holds at most 1 % of
+// the pixels, so labelling and peak picking run on a short list.
+// =============================================================================================================
+namespace {
+
+constexpr int D_THREADS = 256;
+constexpr int D_MAXFG = 4096;        // foreground pixels per image (1 % of up to 640 x 640)
+constexpr int D_MAXPEAKS = 256;
+
+__device__ __forceinline__ double gauss5(const double w0, const double w1, const double w2, const double xm2, const double xm1,
+                                         const double x0, const double xp1, const double xp2) {
+    // NI_Correlate1D, symmetric branch: tmp = x0*fw[0]; tmp += fw[-2]*(x[-2]+x[2]); tmp += fw[-1]*(x[-1]+x[1])
+    double t = __dmul_rn(x0, w0);
+    t = __dadd_rn(t, __dmul_rn(w2, __dadd_rn(xm2, xp2)));
+    t = __dadd_rn(t, __dmul_rn(w1, __dadd_rn(xm1, xp1)));
+    return t;
+}
+
+__global__ void __launch_bounds__(D_THREADS) nanodomain_kernel(const float* __restrict__ sted, int H, int W, double w0, double w1,
+                                                             double w2, long long k0, double gamma, double* __restrict__ tmp,
+                                                             double* __restrict__ filt, int* __restrict__ peaks,
+                                                             int* __restrict__ npeaks, int* __restrict__ flags) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix, s_v0, s_v1;
+    __shared__ long long s_rank;
+    __shared__ int s_count, s_warp_off[D_THREADS / 32 + 1];
+    __shared__ double s_min[D_THREADS / 32];
+    __shared__ int fg_idx[D_MAXFG];           // raster-ordered pixel indices of the mask
+    __shared__ short lab[D_MAXFG];            // component label of each mask pixel
+    __shared__ int s_nfg;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = H * W;
+    const float* img = sted + (size_t)b * N;
+    double* t1 = tmp + (size_t)b * N;
+    double* f = filt + (size_t)b * N;
+
+    // ---- gaussian along axis 0, then along axis 1 (scipy's order), edges replicated
+    for (int i = tid; i < N; i += D_THREADS) {
+        const int y = i / W, x = i - y * W;
+        // skimage.filters.gaussian first maps the int64 image through img_as_float: x -> ((x + 0.5) * 2) / 2^64; the
+        // power of two commutes with every rounding, so filtering 2x + 1 gives the same bits up to that factor
+        auto at = [&](int yy) { return 2.0 * (double)img[min(max(yy, 0), H - 1) * W + x] + 1.0; };
+        t1[i] = gauss5(w0, w1, w2, at(y - 2), at(y - 1), at(y), at(y + 1), at(y + 2));
+    }
+    __syncthreads();
+    double vmin = 1.0e300;
+    for (int i = tid; i < N; i += D_THREADS) {
+        const int y = i / W, x = i - y * W;
+        auto at = [&](int xx) { return t1[y * W + min(max(xx, 0), W - 1)]; };
+        const double v = gauss5(w0, w1, w2, at(x - 2), at(x - 1), at(x), at(x + 1), at(x + 2));
+        f[i] = v;
+        vmin = fmin(vmin, v);
+    }
+    for (int o = 16; o; o >>= 1) vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    if (lane == 0) s_min[warp] = vmin;
+    __syncthreads();
+    vmin = s_min[0];
+    for (int i = 1; i < D_THREADS / 32; ++i) vmin = fmin(vmin, s_min[i]);
+
+    // ---- order statistic k0 by MSB-first radix select on the (non-negative) doubles' bit patterns
+    if (tid == 0) { s_prefix = 0ull; s_rank = k0; }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
+        for (int i = tid; i < N; i += D_THREADS) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(f[i]);
+            if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            long long r = s_rank;
+            int bin = 0;
+            for (; bin < 256; ++bin) { if (r < (long long)hist[bin]) break; r -= hist[bin]; }
+            s_prefix = prefix | ((unsigned long long)bin << shift);
+            s_rank = r;
+        }
+        __syncthreads();
+    }
+    // next order statistic: v0 again if enough copies of it, else the smallest value above it
+    {
+        const unsigned long long v0 = s_prefix;
+        unsigned long long above = ~0ull;
+        int le = 0;
+        for (int i = tid; i < N; i += D_THREADS) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(f[i]);
+            if (key <= v0) ++le; else above = min(above, key);
+        }
+        for (int o = 16; o; o >>= 1) { le += __shfl_xor_sync(0xffffffffu, le, o); above = min(above, __shfl_xor_sync(0xffffffffu, above, o)); }
+        if (tid == 0) { s_count = 0; s_v1 = ~0ull; }
+        __syncthreads();
+        if (lane == 0) { atomicAdd(&s_count, le); atomicMin(&s_v1, above); }
+        __syncthreads();
+        if (tid == 0) { s_v0 = v0; if ((long long)s_count > k0 + 1 || k0 + 1 > N - 1) s_v1 = v0; }
+        __syncthreads();
+    }
+    const double a = __longlong_as_double((long long)s_v0), bq = __longlong_as_double((long long)s_v1);
+    const double diff = __dadd_rn(bq, -a);
+    double thr = __dadd_rn(a, __dmul_rn(diff, gamma));                       // numpy _lerp
+    if (gamma >= 0.5) thr = __dadd_rn(bq, -__dmul_rn(diff, __dadd_rn(1.0, -gamma)));
+
+    // ---- mask pixels in raster order
+    if (tid == 0) s_nfg = 0;
+    __syncthreads();
+    for (int base = 0; base < N; base += D_THREADS) {
+        const int i = base + tid;
+        const bool on = (i < N) && (f[i] > thr);
+        const unsigned int bal = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) s_warp_off[warp] = __popc(bal);
+        __syncthreads();
+        if (tid == 0) {
+            int run = s_nfg;
+            for (int w = 0; w < D_THREADS / 32; ++w) { const int c = s_warp_off[w]; s_warp_off[w] = run; run += c; }
+            s_nfg = run;
+        }
+        __syncthreads();
+        if (on) {
+            const int pos = s_warp_off[warp] + __popc(bal & ((1u << lane) - 1u));
+            if (pos < D_MAXFG) fg_idx[pos] = i;
+        }
+        __syncthreads();
+    }
+    if (tid != 0) return;
+
+    // ---- the rest is a short list: one thread
+    int flag = 0;
+    int n = s_nfg;
+    if (n > D_MAXFG) { n = D_MAXFG; flag |= 1; }
+    auto find = [&](int pix) {                 // position of pixel in the sorted list, -1 if absent
+        int lo = 0, hi = n - 1;
+        while (lo <= hi) { const int mid = (lo + hi) >> 1; if (fg_idx[mid] == pix) return mid; if (fg_idx[mid] < pix) lo = mid + 1; else hi = mid - 1; }
+        return -1;
+    };
+    // 8-connected components: union-find through the backward neighbours (W, NW, N, NE)
+    for (int i = 0; i < n; ++i) lab[i] = (short)i;
+    auto root = [&](int i) { while (lab[i] != i) { lab[i] = lab[lab[i]]; i = lab[i]; } return i; };
+    for (int i = 0; i < n; ++i) {
+        const int y = fg_idx[i] / W, x = fg_idx[i] - y * W;
+        const int nb[4][2] = {{0, -1}, {-1, -1}, {-1, 0}, {-1, 1}};
+        for (int k = 0; k < 4; ++k) {
+            const int yy = y + nb[k][0], xx = x + nb[k][1];
+            if (yy < 0 || xx < 0 || xx >= W) continue;
+            const int j = find(yy * W + xx);
+            if (j < 0) continue;
+            const int ri = root(i), rj = root(j);
+            if (ri != rj) { if (ri < rj) lab[rj] = (short)ri; else lab[ri] = (short)rj; }
+        }
+    }
+    for (int i = 0; i < n; ++i) lab[i] = (short)root(i);        // root = first (raster) pixel of the component
+    // remove_small_objects(min_size=4): mark pixels of small components with -1
+    for (int i = 0; i < n; ++i) {
+        if (lab[i] != i) continue;
+        int size = 0;
+        for (int j = i; j < n; ++j) size += (lab[j] == i);
+        if (size < 4) for (int j = i; j < n; ++j) if (lab[j] == i) lab[j] = -1;
+    }
+    // per component (in order of first pixel = measure.label numbering): local maxima, spacing, output
+    int np_out = 0;
+    int* out = peaks + (size_t)b * D_MAXPEAKS * 2;
+    for (int c = 0; c < n; ++c) {
+        if (lab[c] != c) continue;
+        // candidates: value equals the 5x5 maximum over the component (other pixels are -DBL_MAX) and exceeds the image minimum
+        int cand[64], nc = 0, size = 0, npk = 0;
+        for (int i = c; i < n; ++i) {
+            if (lab[i] != c) continue;
+            ++size;
+            const int y = fg_idx[i] / W, x = fg_idx[i] - y * W;
+            const double v = f[fg_idx[i]];
+            bool is_max = true;
+            for (int j = c; j < n && is_max; ++j) {
+                if (lab[j] != c) continue;
+                const int yj = fg_idx[j] / W, xj = fg_idx[j] - yj * W;
+                if (abs(yj - y) <= 2 && abs(xj - x) <= 2 && f[fg_idx[j]] > v) is_max = false;
+            }
+            if (is_max) { ++npk; if (v > vmin) { if (nc < 64) cand[nc++] = i; else flag |= 2; } }
+        }
+        if (npk == size && size > 1) {
+            // "trivial image": every pixel of the component is a maximum (all values equal).  skimage then keeps
+            // only isolated pixels (mask xor its binary opening); flagged, handled on the host.
+            flag |= 4;
+            continue;
+        }
+        // sort by value, descending, stable in raster order (insertion sort on a handful of entries)
+        for (int i = 1; i < nc; ++i) {
+            const int ci = cand[i];
+            const double vi = f[fg_idx[ci]];
+            int j = i - 1;
+            while (j >= 0 && f[fg_idx[cand[j]]] < vi) { cand[j + 1] = cand[j]; --j; }
+            cand[j + 1] = ci;
+        }
+        // ensure_spacing: drop points closer than 2 (Chebyshev) to an already kept, brighter one
+        int kept[64], nk = 0;
+        for (int i = 0; i < nc; ++i) {
+            const int y = fg_idx[cand[i]] / W, x = fg_idx[cand[i]] - y * W;
+            bool ok = true;
+            for (int k = 0; k < nk && ok; ++k) {
+                const int yk = fg_idx[kept[k]] / W, xk = fg_idx[kept[k]] - yk * W;
+                if (max(abs(yk - y), abs(xk - x)) < 2) ok = false;
+            }
+            if (ok) kept[nk++] = cand[i];
+        }
+        for (int k = 0; k < nk; ++k) {
+            if (np_out >= D_MAXPEAKS) { flag |= 8; break; }
+            out[2 * np_out] = fg_idx[kept[k]] / W;
+            out[2 * np_out + 1] = fg_idx[kept[k]] % W;
+            ++np_out;
+        }
+    }
+    npeaks[b] = np_out;
+    flags[b] = flag;
+}
+
+}  // namespace
+
+extern "C" int sted_nanodomain_candidates(const float* sted_dev, int B, int H, int W, const double weights[3], int64_t k0,
+                                          double gamma, double* scratch_dev, int32_t* peaks_dev, int32_t* npeaks_dev,
+                                          int32_t* flags_dev, void* stream) {
+    if (!sted_dev || !weights || !scratch_dev || !peaks_dev || !npeaks_dev || !flags_dev)
+        return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B, H, W must be positive");
+    if ((long long)H * W > 100ll * D_MAXFG) return fail(STED_EUNSUPPORTED, "image larger than %d pixels", 100 * D_MAXFG);
+    int rc = check_device();
+    if (rc) return rc;
+    const size_t n = (size_t)B * H * W;
+    nanodomain_kernel<<<B, D_THREADS, 0, (cudaStream_t)stream>>>(sted_dev, H, W, weights[0], weights[1], weights[2], k0, gamma,
+                                                                 scratch_dev, scratch_dev + n, peaks_dev, npeaks_dev, flags_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}

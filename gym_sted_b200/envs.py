@@ -216,11 +216,9 @@ class VectorContextualMOSTED:
         bleached = bm.datamaps_roi().clone()
         fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
         res = rewards.resolution(sted)
-        sted_np = sted.cpu().numpy()
         mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)      # (B,3)
         if self.compute_f1:
-            f1 = np.array([rewards.nanodomain_f1(np.rint(sted_np[b]).astype(np.int64), self.synapses[b].nanodomains_coords)
-                           for b in range(self.B)])
+            f1 = rewards.nanodomain_f1_batch(sted, [s.nanodomains_coords for s in self.synapses])
         else:
             f1 = np.zeros(self.B)
         reward = f1 * self.scale_nanodomain_reward

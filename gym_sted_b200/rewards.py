@@ -173,6 +173,48 @@ def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, 
 # ------------------------------------------------------------------------------------------------
 # a9: nanodomain detection + F1 (host side in this round)
 # ------------------------------------------------------------------------------------------------
+def _gauss_taps(sigma=0.5, truncate=4.0):
+    """scipy.ndimage._filters._gaussian_kernel1d (order 0): the three distinct taps of the 5-tap kernel."""
+    radius = int(truncate * sigma + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    phi = phi / phi.sum()
+    return phi[radius], phi[radius + 1], phi[radius + 2]
+
+
+def _quantile_index(n, q=0.99):
+    """numpy.quantile's 'linear' virtual index (_compute_virtual_index with alpha = beta = 1) -> (k0, gamma)."""
+    vi = np.float64(n) * np.float64(q) + (np.float64(1) + np.float64(q) * (np.float64(1) - np.float64(1) - np.float64(1))) - np.float64(1)
+    prev = np.floor(vi)
+    return int(prev), float(vi - prev)
+
+
+def nanodomain_candidates(sted: torch.Tensor):
+    """(B,H,W) photon counts on the GPU -> list of (n_i, 2) int arrays: peak_local_max candidates per image
+    (gaussian -> q99 mask -> remove_small_objects -> label -> per-label maxima), computed by one CUDA kernel."""
+    lib = _lib.load()
+    B, H, W = sted.shape
+    dev = sted.device
+    sted = sted.contiguous().to(torch.float32)
+    scratch = torch.empty((2, B, H, W), dtype=torch.float64, device=dev)
+    peaks = torch.empty((B, 256, 2), dtype=torch.int32, device=dev)
+    npk = torch.empty((B,), dtype=torch.int32, device=dev)
+    flags = torch.empty((B,), dtype=torch.int32, device=dev)
+    import ctypes
+    w = (ctypes.c_double * 3)(*_gauss_taps())
+    k0, gamma = _quantile_index(H * W)
+    _lib.check(lib.sted_nanodomain_candidates(sted.data_ptr(), B, H, W, w, k0, gamma, scratch.data_ptr(), peaks.data_ptr(),
+                                              npk.data_ptr(), flags.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    peaks, npk, flags = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy()
+    out = []
+    for b in range(B):
+        if flags[b]:        # capacity exceeded or a flat component (skimage's isolated-pixel rule): host path for this image
+            out.append(_candidate_peaks_host(np.rint(sted[b].cpu().numpy()).astype(np.int64)))
+        else:
+            out.append(peaks[b, :npk[b]].astype(np.int64))
+    return out
+
+
 def _ensure_spacing(coords, spacing):
     keep = []
     for i, c in enumerate(coords):
@@ -181,14 +223,11 @@ def _ensure_spacing(coords, spacing):
     return coords[keep]
 
 
-def detect_nanodomains(sted: np.ndarray, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
-    """``NumberNanodomains`` detector: gaussian(0.5) -> q99 mask -> drop objects < 4 px (8-conn.) -> label ->
-    per-label local maxima (5x5, Chebyshev spacing 2) -> 7x7 Gaussian-fit validation (40 nm <= FWHM <= 200 nm)."""
+def _candidate_peaks_host(sted: np.ndarray, threshold=2) -> np.ndarray:
+    """Host twin of ``nanodomain_kernel`` (used for flagged images and by the single-image API)."""
     import scipy.ndimage as ndi
-    import scipy.optimize
 
-    sted = np.asarray(sted)
-    filtered = ndi.gaussian_filter(sted.astype(np.float64), 0.5, mode="nearest", truncate=4.0)
+    filtered = ndi.gaussian_filter(2.0 * np.asarray(sted, dtype=np.float64) + 1.0, 0.5, mode="nearest", truncate=4.0)
     mask = filtered > np.quantile(filtered, 0.99)
     eight = np.ones((3, 3), dtype=bool)
     lab, n = ndi.label(mask, structure=eight)
@@ -217,8 +256,15 @@ def detect_nanodomains(sted: np.ndarray, pixelsize=PIXELSIZE, threshold=2) -> np
         cc = cc[np.argsort(-obj[tuple(cc.T)], kind="stable")]
         cc = _ensure_spacing(cc, threshold)
         peaks.append(cc + np.array([s.start for s in roi]))
-    guess = np.vstack(peaks) if peaks else np.zeros((0, 2), dtype=np.int64)
-    padded = np.pad(sted, 3, constant_values=0)
+    return np.vstack(peaks) if peaks else np.zeros((0, 2), dtype=np.int64)
+
+
+def validate_positions(guess, sted: np.ndarray, pixelsize=PIXELSIZE):
+    """``rewards/utils.validate_positions``: 7x7 Levenberg-Marquardt Gaussian fit per candidate (MINPACK through
+    ``scipy.optimize.leastsq``, as in the reference); keeps 40 nm <= FWHM <= 200 nm in both directions."""
+    import scipy.optimize
+
+    padded = np.pad(np.asarray(sted), 3, constant_values=0)
     X, Y = np.indices((7, 7)) - 3.0
     valid = []
     for row, col in guess:
@@ -233,6 +279,20 @@ def detect_nanodomains(sted: np.ndarray, pixelsize=PIXELSIZE, threshold=2) -> np
         if not (fx > 200e-9 or fx < 40e-9 or fy > 200e-9 or fy < 40e-9):
             valid.append((row, col))
     return np.asarray(valid, dtype=np.int64).reshape(-1, 2)
+
+
+def detect_nanodomains(sted: np.ndarray, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
+    """Single image, host side (``NumberNanodomains`` detector end to end)."""
+    sted = np.asarray(sted)
+    return validate_positions(_candidate_peaks_host(sted, threshold), sted, pixelsize)
+
+
+def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
+    """F1 of B images: candidates on the GPU, Gaussian-fit validation and Hungarian matching on the host."""
+    cands = nanodomain_candidates(sted)
+    imgs = np.rint(sted.cpu().numpy()).astype(np.int64)
+    return np.array([f1_from_counts(*match_counts(truths[b], validate_positions(cands[b], imgs[b], pixelsize), threshold))
+                     for b in range(len(cands))])
 
 
 def match_counts(truth, guess, threshold=2):

@@ -185,6 +185,20 @@ int sted_foreground_objectives(const float* conf1_dev, const float* sted_dev, co
                                double* objs_dev, int32_t* flags_dev, int32_t* hist_scratch_dev,
                                void* stream);
 
+/* Nanodomain candidates of B STED images: the integer part of NumberNanodomains.evaluate
+ * (gym_sted/rewards/objectives.py:416-422): gaussian(sigma 0.5) -> > quantile 0.99 -> remove_small_objects(4,
+ * 8-connected) -> label -> peak_local_max(min_distance 2, per label, no border exclusion).
+ *   sted_dev    : float32 [B][H][W] photon counts
+ *   weights     : host, the 3 distinct taps {w0, w1, w2} of scipy's 5-tap Gaussian kernel for sigma 0.5
+ *   k0, gamma   : numpy.quantile's lower order-statistic index and interpolation weight for q = 0.99, N = H*W
+ *   scratch_dev : float64 [2][B][H][W]
+ *   peaks_dev   : int32 [B][256][2] (row, col) in skimage's order; npeaks_dev: int32 [B]
+ *   flags_dev   : int32 [B] bit 0/1/3: capacity exceeded, bit 2: a flat component needs skimage's
+ *                 isolated-pixel rule (handled by the caller) */
+int sted_nanodomain_candidates(const float* sted_dev, int B, int H, int W, const double weights[3],
+                               int64_t k0, double gamma, double* scratch_dev, int32_t* peaks_dev,
+                               int32_t* npeaks_dev, int32_t* flags_dev, void* stream);
+
 /* Debug: per-phase cycle sums of the scan kernel (non-zero only in SWEEP_PROBE=2 builds). */
 int sted_debug_phase_cycles(unsigned long long out_host[8], int reset);
 

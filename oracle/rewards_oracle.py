@@ -262,9 +262,12 @@ def validate_positions(guess, signal, pixelsize, half=3):
     return np.asarray(valid)
 
 
-def detect_nanodomains(sted, pixelsize=20e-9, threshold=2):
+def candidate_peaks(sted, threshold=2):
+    """Everything of the detector before the Gaussian-fit validation (integer outputs).  skimage.filters.gaussian
+    converts the int64 image with img_as_float first: x -> ((x + 0.5) * 2) / (imax - imin) = (2x + 1) * 2**-64; the
+    power of two commutes with rounding, so 2x + 1 is filtered here."""
     sted = np.asarray(sted)
-    filtered = ndi.gaussian_filter(sted.astype(np.float64), 0.5, mode="nearest", truncate=4.0)
+    filtered = ndi.gaussian_filter(2.0 * sted.astype(np.float64) + 1.0, 0.5, mode="nearest", truncate=4.0)
     mask = filtered > np.quantile(filtered, 0.99)
     lab, n = ndi.label(mask, structure=_EIGHT)
     if n:
@@ -273,8 +276,11 @@ def detect_nanodomains(sted, pixelsize=20e-9, threshold=2):
         small[0] = False
         mask = mask & ~small[lab]
     labels, _ = ndi.label(mask, structure=_EIGHT)
-    guess = peak_local_max(filtered, labels, min_distance=threshold)
-    return validate_positions(guess, sted, pixelsize)
+    return peak_local_max(filtered, labels, min_distance=threshold)
+
+
+def detect_nanodomains(sted, pixelsize=20e-9, threshold=2):
+    return validate_positions(candidate_peaks(sted, threshold), np.asarray(sted), pixelsize)
 
 
 def match_counts(truth, guess, threshold=2):

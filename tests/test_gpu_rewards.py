@@ -155,3 +155,43 @@ def test_preference_count_rate_env():
     art = rewards.PreferenceArticulator()
     np.testing.assert_allclose(reward[ok], art.articulate(info["mo_objs"][ok])[0].ravel(), rtol=1e-6)
     assert not done.any() and vec.max_episode_steps == 30
+
+
+def test_nanodomain_candidates_bit_exact():
+    """Integer detection outputs (peak coordinates, in skimage's order) against the oracle on recorded STED images,
+    simulated acquisitions of several sizes and synthetic spot images."""
+    _gpu()
+    demo = helpers.load_demonstrations()
+    images = [demo["sted_image"].astype(np.int64)]
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[:64, :64]
+    spots = []
+    for _ in range(12):
+        img = rng.poisson(0.3, (64, 64)).astype(np.int64)
+        for (y, x) in rng.integers(5, 59, (7, 2)):
+            img += rng.poisson(rng.uniform(30, 150) * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * rng.uniform(1.0, 2.5) ** 2)))
+        spots.append(img)
+    images.append(np.stack(spots))
+    images.append(np.zeros((2, 64, 64), dtype=np.int64))                          # empty image: no candidates
+    from gym_sted_b200.batch import BatchedMicroscope
+    from gym_sted_b200 import synapse
+    m = helpers.product_microscope(noise=True, background=defaults.DETECTOR["background"])
+    for size, B in ((96, 4), (256, 3)):
+        maps, _ = synapse.generate_batch(B, size, size, seed=size)
+        bm = BatchedMicroscope(m, B, size, size, seed=1)
+        bm.set_datamaps(torch.from_numpy(maps))
+        sted, _ = bm.get_signal_and_bleach(15e-6, 8e-6, 0.12, bleach=True)
+        images.append(np.rint(sted.cpu().numpy()).astype(np.int64))
+    total = 0
+    for stack in images:
+        got = rewards.nanodomain_candidates(torch.from_numpy(stack).float().cuda())
+        for b in range(len(stack)):
+            ref = ro.candidate_peaks(stack[b])
+            assert np.array_equal(got[b], ref.reshape(-1, 2)), (stack.shape, b, got[b], ref)
+            total += len(ref)
+    assert total > 100
+    # end to end: batched F1 equals the oracle's per-image F1
+    truth = [rng.integers(5, 59, (6, 2)) for _ in range(len(spots))]
+    f1 = rewards.nanodomain_f1_batch(torch.from_numpy(np.stack(spots)).float().cuda(), truth)
+    ref = np.array([ro.nanodomain_f1(spots[i], truth[i]) for i in range(len(spots))])
+    assert np.array_equal(f1, ref)
