@@ -153,6 +153,20 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read + dram__bytes_write per launch (bytes) from the committed `ncu --set full` summary of the
+    default workload (profiles/r01_ncu_summary.json); None when absent."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+    except OSError:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(r["dram__bytes_read.sum"]) * scale.get(r["dram__bytes_read.sum.unit"], 1.0)
+            + float(r["dram__bytes_write.sum"]) * scale.get(r["dram__bytes_write.sum.unit"], 1.0)
+            for r in table if kernel_substr in r["kernel"]]
+    return float(np.mean(vals)) if vals else None
+
+
 def workload_config(args, envs_per_gpu, world):
     return {"workload": f"ContextualMOSTED-easy-hslb-v0 acquisition schedule (conf, STED+bleach, conf, conf-on-new-map), "
                         f"{envs_per_gpu} envs/GPU, {args.size}x{args.size} px, K=59, stochastic bleaching + Poisson detection",
@@ -332,7 +346,8 @@ def run_ours(args, rank, local_rank, world):
         except OSError:
             pass
         roofline = {"bound": "fp32", "kernel": "gather_kernel<59>", "achieved": achieved, "peak": pk.value,
-                    "unit": "TFLOP/s", "frac": achieved / pk.value if pk.value else None, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / pk.value if pk.value else None,
+                    "traffic": ncu_traffic("gather_kernel") if (H, B) == (256, 256) else None,
                     "peak_source": "FP32 FFMA micro-benchmark run in this process (sted_fma_peak); "
                                    "MEASURED_PEAKS.json has no FP32 entry",
                     "algorithmic_flops_per_launch": fl_launch, "launch_ms": gather_ms,
