@@ -163,16 +163,22 @@ class VectorContextualMOSTED:
         self.conf = (defaults.PDT, defaults.P_EX, 0.0)            # generate_params(): pdt, p_ex, p_sted
         self.current_step = 0
         self.synapses = None
+        self.frames = None
+        self.torch_gen = None
         self.state = None
         self.episode_memory = {"actions": [], "mo_objs": [], "reward": []}
 
     # ------------------------------------------------------------------ helpers
     def _new_datamaps(self):
         """``_update_datamap`` (mosted_env.py:168-187): new synapse, new datamap, confocal image of it."""
-        self.synapses = [synapse.generate(self.H, self.W, seed=int(self.np_rng.integers(0, 2 ** 63 - 1)))
-                         for _ in range(self.B)]
-        frames = np.stack([s.frame for s in self.synapses])
-        self.bm.set_datamaps(torch.from_numpy(frames), max_molecules=int(frames.sum()))
+        if self.torch_gen is None:
+            self.torch_gen = torch.Generator(device=self.device)
+            self.torch_gen.manual_seed(int(self.np_rng.integers(0, 2 ** 62)))
+        frames, coords = synapse.generate_batch_torch(self.B, self.H, self.W, self.device, self.torch_gen)
+        self.synapses = [synapse.Synapse(None, c) for c in coords]
+        self.frames = frames                                   # molecule maps of the current synapses (device, int32)
+        cells = -(-self.H // synapse.CELL) * -(-self.W // synapse.CELL)
+        self.bm.set_datamaps(frames, max_molecules=self.B * cells * (5 * synapse.CELL ** 2 + 15 * 175))
         state, _ = self.bm.get_signal_and_bleach(*self.conf, bleach=False)
         return state
 
@@ -190,6 +196,7 @@ class VectorContextualMOSTED:
     def reset(self, seed=None, options=None):
         if seed is not None:
             self.np_rng = np.random.default_rng(seed)
+            self.torch_gen = None
         fluos = [base.Fluorescence(**self.bleach_sampler.sample(self.microscope)) for _ in range(self.B)] \
             if self.bleach_sampler.mode != "constant" else None
         if fluos is None:

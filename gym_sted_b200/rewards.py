@@ -54,6 +54,7 @@ def foreground_objectives(conf1: torch.Tensor, sted: torch.Tensor, conf2: torch.
 # a8: resolution
 # ------------------------------------------------------------------------------------------------
 def _decorr_peak(d: np.ndarray, tol: float):
+    """Reference's ``decorr_peak`` (objectives.py:217-227) for one curve."""
     idx = int(np.argmax(d))
     A = d[idx]
     while len(d) > 1:
@@ -63,6 +64,30 @@ def _decorr_peak(d: np.ndarray, tol: float):
         idx = int(np.argmax(d))
         A = d[idx]
     return idx, A
+
+
+def _decorr_peak_batch(d: np.ndarray, tol: float):
+    """``decorr_peak`` for a (B, n) stack of curves at once: the loop shortens the curve from the right until
+    the leading maximum stands ``tol`` above the minimum to its right (or sits at index 0); evaluate that
+    condition for every length L and take the largest L that satisfies it."""
+    B, n = d.shape
+    pos = np.arange(n)
+    prefix_max = np.maximum.accumulate(d, axis=1)
+    prev_max = np.concatenate([np.full((B, 1), -np.inf), prefix_max[:, :-1]], axis=1)
+    new_max = d > prev_max                                           # first occurrence of each running maximum
+    idx_L = np.maximum.accumulate(np.where(new_max, pos[None, :], 0), axis=1)      # argmax(d[:L]) at column L-1
+    A_L = np.take_along_axis(d, idx_L, axis=1)
+    # min(d[idx_L:L]): running minimum restarted at every new leading maximum
+    m_L = np.empty_like(d)
+    run = d[:, 0].copy()
+    for j in range(n):
+        run = np.where(new_max[:, j], d[:, j], np.minimum(run, d[:, j]))
+        m_L[:, j] = run
+    ok = ((A_L - m_L) >= tol) | (idx_L == 0)
+    ok[:, 0] = True                                                  # a single point always ends the loop
+    L = n - 1 - np.argmax(ok[:, ::-1], axis=1)                       # last column (largest length) where ok
+    idx = idx_L[np.arange(B), L]
+    return idx, d[np.arange(B), idx]
 
 
 class _Decorrelator:
@@ -130,9 +155,8 @@ def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, 
     r = np.linspace(0, 1, Nr)
     b_shared = bounds_for(np.broadcast_to(r, (B, Nr)))
     d0 = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_shared).cpu().numpy()
-    first = [_decorr_peak(d0[b], tol) for b in range(B)]
-    r0 = np.array([r[i] for i, _ in first])
-    A0 = np.array([a for _, a in first])
+    i0, A0 = _decorr_peak_batch(d0, tol)
+    r0 = r[i0]
     with np.errstate(divide="ignore"):
         g_max = 2 / r0
     g_max[np.isinf(g_max)] = max(geo.Hc, geo.Wc) / 2
@@ -142,12 +166,12 @@ def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, 
     rs = [r0]
     for j in range(Ng + 1):
         d = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_shared, torch.from_numpy(sigmas[:, j]).to(dev)).cpu().numpy()
-        pk = [_decorr_peak(d[b], tol) for b in range(B)]
-        rs.append(np.array([r[i] for i, _ in pk]))
-        As.append(np.array([a for _, a in pk]))
+        ik, Ak = _decorr_peak_batch(d, tol)
+        rs.append(r[ik])
+        As.append(Ak)
     rs_a = np.stack(rs, axis=1)            # (B, Ng+2)
     As_a = np.stack(As, axis=1)
-    kmax = np.array([int(np.where(row == row.max())[0][-1]) for row in rs_a])
+    kmax = rs_a.shape[1] - 1 - np.argmax((rs_a == rs_a.max(axis=1, keepdims=True))[:, ::-1], axis=1)
     ind1 = np.where(kmax == 0, 0, np.where(kmax >= Ng, kmax - 2, kmax - 1))
     peak_r = rs_a[np.arange(B), kmax]
     r_fine = np.linspace(peak_r - (r[1] - r[0]), np.minimum(peak_r + 0.4, r[-1]), Nr, axis=1)
@@ -157,9 +181,9 @@ def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, 
     As_l = [As_a[:, :-1]]
     for j in range(Ng):
         d = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_fine, torch.from_numpy(sig_fine[:, j]).to(dev)).cpu().numpy()
-        pk = [_decorr_peak(d[b], tol) for b in range(B)]
-        rs_l.append(np.array([r_fine[b, i] for b, (i, _) in enumerate(pk)])[:, None])
-        As_l.append(np.array([a for _, a in pk])[:, None])
+        ik, Ak = _decorr_peak_batch(d, tol)
+        rs_l.append(r_fine[np.arange(B), ik][:, None])
+        As_l.append(Ak[:, None])
     rs_l.append(r0[:, None])
     As_l.append(A0[:, None])
     rs_f = np.concatenate(rs_l, axis=1)

@@ -122,9 +122,10 @@ def test_vector_env_routine_and_per_env_fluorophores():
     (img, v), _ = vec.reset(seed=1)
     assert img.shape == (6, 64, 64, 3) and v.shape == (6, 60)
     acts = np.tile(np.array([[0.15, 10e-6, 30e-6]], dtype=np.float32), (6, 1))
+    before = vec.frames.clone()
     (img, v), reward, done, trunc, info = vec.step(acts)
     assert reward.shape == (6,) and done.shape == (6,) and info["mo_objs"].shape == (6, 3)
-    assert float(info["bleached"].sum()) < sum(s.frame.sum() for s in vec.synapses) * 2       # molecules were lost
+    assert float(info["bleached"].sum()) < float(before.sum())                               # molecules were lost
     hard = envs.make_vec("ContextualMOSTED-hard-v0", 4, compute_f1=False, seed=3)
     (img, v), _ = hard.reset(seed=3)
     (img, v), reward, done, trunc, info = hard.step(acts[:4])
