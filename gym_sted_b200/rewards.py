@@ -283,26 +283,67 @@ def _candidate_peaks_host(sted: np.ndarray, threshold=2) -> np.ndarray:
     return np.vstack(peaks) if peaks else np.zeros((0, 2), dtype=np.int64)
 
 
-def validate_positions(guess, sted: np.ndarray, pixelsize=PIXELSIZE):
-    """``rewards/utils.validate_positions``: 7x7 Levenberg-Marquardt Gaussian fit per candidate (MINPACK through
-    ``scipy.optimize.leastsq``, as in the reference); keeps 40 nm <= FWHM <= 200 nm in both directions."""
+def _fit_windows(windows: np.ndarray, pixelsize: float) -> np.ndarray:
+    """``rewards/utils.fitgaussian`` + the FWHM test of ``validate_positions`` for a stack of 7x7 windows:
+    Levenberg-Marquardt through MINPACK (``scipy.optimize.leastsq``, ftol 1e-3) exactly as in the reference."""
     import scipy.optimize
 
-    padded = np.pad(np.asarray(sted), 3, constant_values=0)
     X, Y = np.indices((7, 7)) - 3.0
-    valid = []
-    for row, col in guess:
-        data = padded[row:row + 7, col:col + 7]
-
+    ok = np.zeros(len(windows), dtype=bool)
+    for i, data in enumerate(windows):
         def err(p):
             wx, wy = float(p[3]) + 1e-3, float(p[4]) + 1e-3
             return np.ravel(p[0] * np.exp(-(((p[1] - X) ** 2.0 / (2 * wx ** 2.0)) + ((p[2] - Y) ** 2.0 / (2 * wy ** 2.0)))) - data)
 
         p, _ = scipy.optimize.leastsq(err, [data.max(), 0, 0, 1, 1], ftol=1e-3)
         fx, fy = 2.355 * p[3] * pixelsize, 2.355 * p[4] * pixelsize
-        if not (fx > 200e-9 or fx < 40e-9 or fy > 200e-9 or fy < 40e-9):
-            valid.append((row, col))
-    return np.asarray(valid, dtype=np.int64).reshape(-1, 2)
+        ok[i] = not (fx > 200e-9 or fx < 40e-9 or fy > 200e-9 or fy < 40e-9)
+    return ok
+
+
+def _windows(guess, sted: np.ndarray) -> np.ndarray:
+    padded = np.pad(np.asarray(sted), 3, constant_values=0)
+    return np.stack([padded[r:r + 7, c:c + 7] for r, c in guess]) if len(guess) else np.zeros((0, 7, 7), dtype=padded.dtype)
+
+
+def validate_positions(guess, sted: np.ndarray, pixelsize=PIXELSIZE):
+    """``rewards/utils.validate_positions``: keeps the candidates whose fitted Gaussian has 40 nm <= FWHM <= 200 nm
+    in both directions."""
+    guess = np.asarray(guess, dtype=np.int64).reshape(-1, 2)
+    return guess[_fit_windows(_windows(guess, sted), pixelsize)]
+
+
+_POOL = None
+
+
+def _pool(workers):
+    """Optional worker processes for the per-candidate MINPACK fits (``STED_B200_FIT_WORKERS=n``).  Forked like
+    torch's DataLoader workers: they only run numpy/scipy and never touch CUDA."""
+    global _POOL
+    if _POOL is None:
+        import atexit
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        _POOL = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("fork"))
+        atexit.register(_POOL.shutdown, wait=False, cancel_futures=True)
+    return _POOL
+
+
+def validate_positions_batch(guesses, images, pixelsize=PIXELSIZE):
+    """``validate_positions`` for many images at once (serial by default; see ``_pool``)."""
+    wins = [_windows(g, im) for g, im in zip(guesses, images)]
+    workers = int(os.environ.get("STED_B200_FIT_WORKERS", "0"))
+    if workers <= 1 or sum(len(w) for w in wins) < 8 * workers:
+        oks = [_fit_windows(w, pixelsize) for w in wins]
+    else:
+        flat = np.concatenate(wins)
+        parts = np.array_split(flat, min(len(flat), 2 * workers))
+        ok = np.concatenate(list(_pool(workers).map(_fit_windows, parts, [pixelsize] * len(parts))))
+        oks, at = [], 0
+        for w in wins:
+            oks.append(ok[at:at + len(w)])
+            at += len(w)
+    return [np.asarray(g, dtype=np.int64).reshape(-1, 2)[o] for g, o in zip(guesses, oks)]
 
 
 def detect_nanodomains(sted: np.ndarray, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
@@ -315,8 +356,8 @@ def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, thresho
     """F1 of B images: candidates on the GPU, Gaussian-fit validation and Hungarian matching on the host."""
     cands = nanodomain_candidates(sted)
     imgs = np.rint(sted.cpu().numpy()).astype(np.int64)
-    return np.array([f1_from_counts(*match_counts(truths[b], validate_positions(cands[b], imgs[b], pixelsize), threshold))
-                     for b in range(len(cands))])
+    valid = validate_positions_batch(cands, imgs, pixelsize)
+    return np.array([f1_from_counts(*match_counts(truths[b], valid[b], threshold)) for b in range(len(cands))])
 
 
 def match_counts(truth, guess, threshold=2):
