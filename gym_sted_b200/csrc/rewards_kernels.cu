@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
+#include "lm_minpack.cuh"
 
 namespace {
 
@@ -459,6 +460,80 @@ extern "C" int sted_nanodomain_candidates(const float* sted_dev, int B, int H, i
     const size_t n = (size_t)B * H * W;
     nanodomain_kernel<<<B, D_THREADS, 0, (cudaStream_t)stream>>>(sted_dev, H, W, weights[0], weights[1], weights[2], k0, gamma,
                                                                  scratch_dev, scratch_dev + n, peaks_dev, npeaks_dev, flags_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+// =============================================================================================================
+// Gaussian-fit validation of the candidates (gym_sted/rewards/utils.py:6-49): for every candidate a 7x7 window of
+// the (zero-padded) STED image is fitted with amplitude*exp(-((cx-x)^2/(2 wx^2) + (cy-y)^2/(2 wy^2))) by
+// Levenberg-Marquardt, and the candidate is kept when 40 nm <= 2.355*w*pixelsize <= 200 nm for both widths.
+// The reference calls scipy.optimize.leastsq(errorfunction, [data.max(), 0, 0, 1, 1], ftol=1e-3), i.e. MINPACK's
+// LMDIF with xtol = 1.49012e-8, gtol = 0, maxfev = 200*(n+1), epsfcn = eps, factor = 100, mode 1.  lm_minpack.cuh
+// restates LMDIF / FDJAC2 / QRFAC / LMPAR / QRSOLV / ENORM (Moré, Garbow, Hillstrom, MINPACK-1) for
+// m = 49 residuals and n = 5 parameters, one fit per thread, in float64.  The residuals go through exp(), whose
+// last bit differs between libm/numpy and CUDA, so fitted parameters agree to ~1e-9 rather than bitwise; the
+// keep/reject decisions are identical except for widths that sit within that distance of a limit.
+// =============================================================================================================
+namespace {
+
+using namespace lm;
+
+__global__ void __launch_bounds__(64) gaussfit_kernel(const float* __restrict__ sted, int H, int W, const int* __restrict__ peaks,
+                                                    const int* __restrict__ npeaks, int maxp, double pixelsize,
+                                                    unsigned char* __restrict__ valid, double* __restrict__ params) {
+    const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npeaks[b] || k >= maxp) return;
+    const int row = peaks[((size_t)b * maxp + k) * 2], col = peaks[((size_t)b * maxp + k) * 2 + 1];
+    const float* img = sted + (size_t)b * H * W;
+    double data[LM_M], dmax = -1.0e300;
+    for (int i = 0; i < LM_M; ++i) {
+        const int y = row + i / 7 - 3, x = col + i % 7 - 3;
+        data[i] = (y >= 0 && y < H && x >= 0 && x < W) ? rint((double)img[y * W + x]) : 0.0;     // numpy.pad(..., constant_values=0)
+        dmax = fmax(dmax, data[i]);
+    }
+    double p[LM_N] = {dmax, 0.0, 0.0, 1.0, 1.0};
+    lm_fit(GaussResiduals{data}, p, 1e-3, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0);
+    const double fx = 2.355 * p[3] * pixelsize, fy = 2.355 * p[4] * pixelsize;
+    valid[(size_t)b * maxp + k] = !(fx > 200e-9 || fx < 40e-9 || fy > 200e-9 || fy < 40e-9);
+    if (params) for (int j = 0; j < LM_N; ++j) params[((size_t)b * maxp + k) * LM_N + j] = p[j];
+}
+
+// Test hook: run the solver on n windows with caller-supplied starts; model 0 = the Gaussian, 1 = the rational test model.
+__global__ void lmfit_test_kernel(const double* __restrict__ data, int n, int model, double ftol, double* __restrict__ params,
+                                  int* __restrict__ info) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double d[LM_M], p[LM_N];
+    for (int i = 0; i < LM_M; ++i) d[i] = data[(size_t)k * LM_M + i];
+    for (int j = 0; j < LM_N; ++j) p[j] = params[(size_t)k * LM_N + j];
+    const int rc = model == 0 ? lm_fit(GaussResiduals{d}, p, ftol, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0)
+                              : lm_fit(RationalResiduals{d}, p, ftol, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0);
+    for (int j = 0; j < LM_N; ++j) params[(size_t)k * LM_N + j] = p[j];
+    info[k] = rc;
+}
+
+}  // namespace
+
+extern "C" int sted_lmfit_test(const double* data_dev, int n, int model, double ftol, double* params_dev, int32_t* info_dev,
+                               void* stream) {
+    if (!data_dev || !params_dev || !info_dev || n <= 0 || (model != 0 && model != 1)) return fail(STED_EINVAL, "bad lmfit arguments");
+    int rc = check_device();
+    if (rc) return rc;
+    lmfit_test_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(data_dev, n, model, ftol, params_dev, info_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+extern "C" int sted_gaussfit_validate(const float* sted_dev, int B, int H, int W, const int32_t* peaks_dev, const int32_t* npeaks_dev,
+                                      int max_peaks, double pixelsize, uint8_t* valid_dev, double* params_dev, void* stream) {
+    if (!sted_dev || !peaks_dev || !npeaks_dev || !valid_dev) return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0 || max_peaks <= 0) return fail(STED_EINVAL, "B, H, W, max_peaks must be positive");
+    int rc = check_device();
+    if (rc) return rc;
+    dim3 grid((max_peaks + 63) / 64, B);
+    gaussfit_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(sted_dev, H, W, peaks_dev, npeaks_dev, max_peaks, pixelsize, valid_dev,
+                                                          params_dev);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }

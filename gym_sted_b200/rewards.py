@@ -213,9 +213,8 @@ def _quantile_index(n, q=0.99):
     return int(prev), float(vi - prev)
 
 
-def nanodomain_candidates(sted: torch.Tensor):
-    """(B,H,W) photon counts on the GPU -> list of (n_i, 2) int arrays: peak_local_max candidates per image
-    (gaussian -> q99 mask -> remove_small_objects -> label -> per-label maxima), computed by one CUDA kernel."""
+def _candidates_device(sted: torch.Tensor):
+    """Launch ``nanodomain_kernel``; returns the device tensors (sted_f32, peaks (B,256,2), npeaks (B,), flags (B,))."""
     lib = _lib.load()
     B, H, W = sted.shape
     dev = sted.device
@@ -229,13 +228,50 @@ def nanodomain_candidates(sted: torch.Tensor):
     k0, gamma = _quantile_index(H * W)
     _lib.check(lib.sted_nanodomain_candidates(sted.data_ptr(), B, H, W, w, k0, gamma, scratch.data_ptr(), peaks.data_ptr(),
                                               npk.data_ptr(), flags.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return sted, peaks, npk, flags
+
+
+def nanodomain_candidates(sted: torch.Tensor):
+    """(B,H,W) photon counts on the GPU -> list of (n_i, 2) int arrays: peak_local_max candidates per image
+    (gaussian -> q99 mask -> remove_small_objects -> label -> per-label maxima), computed by one CUDA kernel."""
+    sted, peaks, npk, flags = _candidates_device(sted)
     peaks, npk, flags = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy()
     out = []
-    for b in range(B):
+    for b in range(sted.shape[0]):
         if flags[b]:        # capacity exceeded or a flat component (skimage's isolated-pixel rule): host path for this image
             out.append(_candidate_peaks_host(np.rint(sted[b].cpu().numpy()).astype(np.int64)))
         else:
             out.append(peaks[b, :npk[b]].astype(np.int64))
+    return out
+
+
+def gaussfit_validate(sted: torch.Tensor, peaks: torch.Tensor, npeaks: torch.Tensor, pixelsize=PIXELSIZE, want_params=False):
+    """Levenberg-Marquardt validation of device-resident candidates (``sted_gaussfit_validate``): returns the
+    uint8 (B, max_peaks) validity tensor (and the fitted parameters when asked)."""
+    lib = _lib.load()
+    B, H, W = sted.shape
+    sted = sted.contiguous().to(torch.float32)
+    maxp = peaks.shape[1]
+    valid = torch.zeros((B, maxp), dtype=torch.uint8, device=sted.device)
+    params = torch.zeros((B, maxp, 5), dtype=torch.float64, device=sted.device) if want_params else None
+    _lib.check(lib.sted_gaussfit_validate(sted.data_ptr(), B, H, W, peaks.data_ptr(), npeaks.data_ptr(), maxp, float(pixelsize),
+                                          valid.data_ptr(), params.data_ptr() if want_params else None,
+                                          torch.cuda.current_stream(sted.device).cuda_stream))
+    return (valid, params) if want_params else valid
+
+
+def detect_nanodomains_batch(sted: torch.Tensor, pixelsize=PIXELSIZE):
+    """``NumberNanodomains`` detector for B device images: candidates and Gaussian-fit validation on the GPU, one
+    device->host read of the surviving coordinates.  Flagged images (capacity / flat component) take the host path."""
+    sted, peaks, npk, flags = _candidates_device(sted)
+    valid = gaussfit_validate(sted, peaks, npk, pixelsize)
+    peaks, npk, flags, valid = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy(), valid.cpu().numpy().astype(bool)
+    out = []
+    for b in range(sted.shape[0]):
+        if flags[b]:
+            out.append(detect_nanodomains(np.rint(sted[b].cpu().numpy()).astype(np.int64), pixelsize))
+        else:
+            out.append(peaks[b, :npk[b]][valid[b, :npk[b]]].astype(np.int64))
     return out
 
 
@@ -352,12 +388,16 @@ def detect_nanodomains(sted: np.ndarray, pixelsize=PIXELSIZE, threshold=2) -> np
     return validate_positions(_candidate_peaks_host(sted, threshold), sted, pixelsize)
 
 
-def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
-    """F1 of B images: candidates on the GPU, Gaussian-fit validation and Hungarian matching on the host."""
-    cands = nanodomain_candidates(sted)
-    imgs = np.rint(sted.cpu().numpy()).astype(np.int64)
-    valid = validate_positions_batch(cands, imgs, pixelsize)
-    return np.array([f1_from_counts(*match_counts(truths[b], valid[b], threshold)) for b in range(len(cands))])
+def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, host_fit=False) -> np.ndarray:
+    """F1 of B images: candidates and Gaussian-fit validation on the GPU, Hungarian matching on the host.
+    ``host_fit=True`` validates with scipy's MINPACK instead (the reference's own solver; slower)."""
+    if host_fit:
+        cands = nanodomain_candidates(sted)
+        imgs = np.rint(sted.cpu().numpy()).astype(np.int64)
+        valid = validate_positions_batch(cands, imgs, pixelsize)
+    else:
+        valid = detect_nanodomains_batch(sted, pixelsize)
+    return np.array([f1_from_counts(*match_counts(truths[b], valid[b], threshold)) for b in range(len(valid))])
 
 
 def match_counts(truth, guess, threshold=2):

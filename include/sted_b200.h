@@ -199,6 +199,22 @@ int sted_nanodomain_candidates(const float* sted_dev, int B, int H, int W, const
                                int64_t k0, double gamma, double* scratch_dev, int32_t* peaks_dev,
                                int32_t* npeaks_dev, int32_t* flags_dev, void* stream);
 
+/* Gaussian-fit validation of nanodomain candidates (gym_sted/rewards/utils.py:6-49, called from
+ * gym_sted/rewards/objectives.py:424): one Levenberg-Marquardt fit (MINPACK LMDIF restated, float64) of a 7x7
+ * zero-padded window per candidate; valid = both FWHMs 2.355*w*pixelsize inside [40 nm, 200 nm].
+ *   peaks_dev/npeaks_dev : as written by sted_nanodomain_candidates, max_peaks rows per image
+ *   valid_dev  : uint8 [B][max_peaks]
+ *   params_dev : optional float64 [B][max_peaks][5] fitted (amplitude, cx, cy, wx, wy), may be NULL */
+int sted_gaussfit_validate(const float* sted_dev, int B, int H, int W, const int32_t* peaks_dev,
+                           const int32_t* npeaks_dev, int max_peaks, double pixelsize, uint8_t* valid_dev,
+                           double* params_dev, void* stream);
+
+/* Test hook for the Levenberg-Marquardt solver: n windows of 49 float64 values, params_dev float64 [n][5] holds the
+ * starting points on entry and the solutions on return, info_dev int32 [n] MINPACK's info code.
+ * model 0: the Gaussian of sted_gaussfit_validate; model 1: a rational peak (no transcendental, bit-reproducible). */
+int sted_lmfit_test(const double* data_dev, int n, int model, double ftol, double* params_dev, int32_t* info_dev,
+                    void* stream);
+
 /* Debug: per-phase cycle sums of the scan kernel (non-zero only in SWEEP_PROBE=2 builds). */
 int sted_debug_phase_cycles(unsigned long long out_host[8], int reset);
 

@@ -1,9 +1,12 @@
 """GPU parity of the reward side (Otsu foregrounds, Bleach, SNR, Resolution) and env API conformance."""
+import os
+
 import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from gym_sted_b200 import defaults, envs, rewards  # noqa: E402
 from oracle import rewards_oracle as ro  # noqa: E402
 from tests import helpers  # noqa: E402
@@ -196,3 +199,85 @@ def test_nanodomain_candidates_bit_exact():
     f1 = rewards.nanodomain_f1_batch(torch.from_numpy(np.stack(spots)).float().cuda(), truth)
     ref = np.array([ro.nanodomain_f1(spots[i], truth[i]) for i in range(len(spots))])
     assert np.array_equal(f1, ref)
+
+
+def test_gaussfit_validation_matches_minpack():
+    """The device Levenberg-Marquardt fit against scipy.optimize.leastsq (the reference's solver, through the
+    oracle) on every candidate of many images: same keep/reject decision.  The fitted parameters differ only through
+    the last bit of exp() (tests/test_lm_minpack.py pins the solver itself bit for bit), which the forward-difference
+    Jacobian and the loose ftol = 1e-3 amplify to ~1e-6 typically, more on ill-conditioned windows."""
+    _gpu()
+    import scipy.optimize
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[:64, :64]
+    imgs = []
+    for i in range(256):
+        img = rng.poisson(rng.uniform(0.1, 1.0), (64, 64)).astype(np.int64)
+        for (y, x) in rng.integers(0, 64, (rng.integers(3, 12), 2)):       # includes spots cut by the border (zero padding)
+            s = rng.uniform(0.6, 4.5, 2)
+            img += rng.poisson(rng.uniform(10, 200) * np.exp(-((yy - y) ** 2 / (2 * s[0] ** 2) + (xx - x) ** 2 / (2 * s[1] ** 2))))
+        imgs.append(img)
+    stack = np.stack(imgs)
+    dev = torch.from_numpy(stack).float().cuda()
+    sted, peaks, npk, flags = rewards._candidates_device(dev)
+    valid, params = rewards.gaussfit_validate(sted, peaks, npk, want_params=True)
+    peaks, npk, flags, valid, params = (t.cpu().numpy() for t in (peaks, npk, flags, valid, params))
+    X, Y = np.indices((7, 7)) - 3.0
+    nfit = nagree = 0
+    diffs = []
+    for b in range(len(stack)):
+        if flags[b]:
+            continue
+        padded = np.pad(stack[b], 3, mode="constant")
+        for k in range(npk[b]):
+            r, c = peaks[b, k]
+            data = padded[r:r + 7, c:c + 7].astype(np.float64)
+
+            def err(p):
+                wx, wy = float(p[3]) + 1e-3, float(p[4]) + 1e-3
+                return np.ravel(p[0] * np.exp(-1 * ((p[1] - X) ** 2.0 / (2 * wx ** 2.0) + (p[2] - Y) ** 2.0 / (2 * wy ** 2.0))) - data)
+
+            p, _ = scipy.optimize.leastsq(err, [data.max(), 0, 0, 1, 1], ftol=1e-3)
+            fw = 2.355 * p[3:5] * defaults.PIXELSIZE
+            ok = not np.any((fw > 200e-9) | (fw < 40e-9))
+            nfit += 1
+            margin = np.min(np.abs(np.concatenate([fw - 200e-9, fw - 40e-9]))) / 40e-9
+            if bool(valid[b, k]) == ok:
+                nagree += 1
+            else:
+                assert margin < 1e-6, (b, k, p, params[b, k])            # only a width sitting on a limit may flip
+            diffs.append(np.max(np.abs(params[b, k] - p) / (np.abs(p) + 1e-3)))
+    assert nfit > 500 and nagree == nfit, (nfit, nagree)
+    diffs = np.array(diffs)
+    print(f'{nfit} fits; parameter difference quantiles 50/90/99/100 %: {np.quantile(diffs, [0.5, 0.9, 0.99, 1.0])}; >1e-6: {np.sum(diffs > 1e-6)}')
+    assert np.median(diffs) < 1e-5 and np.mean(diffs > 1e-3) < 0.03, np.quantile(diffs, [0.5, 0.9, 0.99, 1.0])
+    # the batched detector equals the oracle's detector (candidates + scipy fit) image by image
+    got = rewards.detect_nanodomains_batch(dev)
+    for b in range(0, len(stack), 7):
+        assert np.array_equal(got[b], ro.detect_nanodomains(stack[b]).reshape(-1, 2)), b
+
+
+def test_lm_solver_device_equals_host_build():
+    """The solver on the GPU against the g++ build of the same header (itself bit-exact against scipy's MINPACK in
+    tests/test_lm_minpack.py): identical bits on the transcendental-free model, solution and info code."""
+    _gpu()
+    import ctypes
+    import subprocess
+    import tempfile
+    from gym_sted_b200 import _lib
+    from tests import test_lm_minpack as tl
+    out = os.path.join(tempfile.mkdtemp(), "liblm.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, os.path.join(ROOT, "tests", "lm_harness.cpp")])
+    host = ctypes.CDLL(out)
+    host.lm_harness_fit.restype = ctypes.c_int
+    host.lm_harness_fit.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+    ws = tl.windows(500, 3)
+    data = torch.from_numpy(np.stack([w.ravel() for w in ws])).cuda()
+    for ftol in (1e-3, 1e-10):
+        params = torch.from_numpy(np.stack([[w.max(), 0, 0, 1, 1.0] for w in ws])).cuda()
+        info = torch.zeros(len(ws), dtype=torch.int32, device="cuda")
+        _lib.check(_lib.load().sted_lmfit_test(data.data_ptr(), len(ws), 1, ftol, params.data_ptr(), info.data_ptr(), None))
+        params, info = params.cpu().numpy(), info.cpu().numpy()
+        for i, w in enumerate(ws):
+            x, rc = tl.fit_harness(host, w, 1, ftol)
+            assert rc == info[i] and np.array_equal(x, params[i]), (i, x, params[i])
