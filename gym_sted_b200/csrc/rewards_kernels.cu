@@ -465,6 +465,177 @@ extern "C" int sted_nanodomain_candidates(const float* sted_dev, int B, int H, i
 }
 
 // =============================================================================================================
+// Resolution objective: image-decorrelation analysis (gym_sted/rewards/objectives.py:146-335, Descloux et al. 2019).
+// The host prepares the apodised, Fourier-transformed image (cuFFT through torch) with its pixels sorted by radius;
+// this kernel runs all 22 decorrelation passes and the three dependent peak searches of one image in one CTA:
+//   pass 0        : d(r_i) on r = linspace(0, 1, 50)                              -> r0, A0
+//   passes 1..11  : high-pass sigma_0 = Hc/4, sigma_1..10 = exp(linspace(log g_max, log 0.15, 10))
+//   passes 12..21 : refined radii around the best peak and 10 refined sigmas
+//   resolution    = 2 / max(r_k with A_k >= 0.05) * pixelsize / 1 nm, capped.
+// d(r) = sum_{R<r} Re(Ik' conj(Ikn)) / sqrt(sum_{R<r} |Ikn|^2 * sum |Ik'|^2), Ik' = Ik (1 - exp(-2 sigma^2 R^2)),
+// then floor(1000 d)/1000.  Pixels are radius-sorted, so every ring [r_{i-1}, r_i) is a contiguous range: one warp
+// per ring, lanes striding the range, fixed-order shuffles (deterministic), float64 throughout.
+// =============================================================================================================
+namespace {
+
+constexpr int DC_NR = 50, DC_NG = 10, DC_THREADS = 512;
+
+struct DecorrShared {
+    int bounds[DC_NR];
+    double ring_num[DC_NR + 1], ring_abs[DC_NR + 1], ring_pow[DC_NR + 1];
+    double d[DC_NR], r[DC_NR], r_fine[DC_NR], sigmas[DC_NG + 1], sig_fine[DC_NG], rs[2 * DC_NG + 3], As[2 * DC_NG + 3];
+    int idx;
+    double A;
+};
+
+__device__ void dc_linspace(double a, double b, int n, double* out) {            // numpy.linspace(a, b, n)
+    const double step = (b - a) / (double)(n - 1);
+    for (int i = 0; i < n; ++i) out[i] = (double)i * step + a;
+    out[n - 1] = b;
+}
+
+// objectives.py:217-227: shorten the curve from the right until its maximum stands tol above the minimum to its right
+__device__ void dc_peak(const double* d, int n, double tol, int* idx_out, double* A_out) {
+    auto argmax = [&](int len) { int k = 0; for (int i = 1; i < len; ++i) if (d[i] > d[k]) k = i; return k; };
+    int len = n, idx = argmax(len);
+    double A = d[idx];
+    while (len > 1) {
+        double mn = d[idx];
+        for (int i = idx + 1; i < len; ++i) mn = fmin(mn, d[i]);
+        if ((A - mn) >= tol || idx == 0) break;
+        --len;
+        idx = argmax(len);
+        A = d[idx];
+    }
+    *idx_out = idx;
+    *A_out = A;
+}
+
+__device__ void dc_bounds(DecorrShared& sh, const double* __restrict__ R, int N, const double* radii) {
+    if (threadIdx.x < DC_NR) {                 // numpy.searchsorted(R_sorted, r, 'left') = number of pixels with R < r
+        const double r = radii[threadIdx.x];
+        int lo = 0, hi = N;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (R[mid] < r) lo = mid + 1; else hi = mid; }
+        sh.bounds[threadIdx.x] = lo;
+    }
+    __syncthreads();
+}
+
+__device__ void dc_pass(DecorrShared& sh, const double2* __restrict__ Ik, const double2* __restrict__ Ikn,
+                        const double* __restrict__ R2, int n_inside, bool filtered, double sigma, double tol) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double c = -2.0 * (sigma * sigma);
+    for (int ring = warp; ring <= DC_NR; ring += DC_THREADS / 32) {
+        const int lo = ring == 0 ? 0 : min(sh.bounds[ring - 1], n_inside);
+        const int hi = ring < DC_NR ? min(sh.bounds[ring], n_inside) : n_inside;
+        double sn = 0.0, sa = 0.0, sp = 0.0;
+        for (int p = lo + lane; p < hi; p += 32) {
+            double2 a = Ik[p];
+            const double2 b = Ikn[p];
+            if (filtered) { const double f = 1.0 - exp(c * R2[p]); a.x *= f; a.y *= f; }
+            sn += a.x * b.x + a.y * b.y;
+            sp += a.x * a.x + a.y * a.y;
+            sa += b.x * b.x + b.y * b.y;
+        }
+        for (int o = 16; o; o >>= 1) {
+            sn += __shfl_xor_sync(0xffffffffu, sn, o);
+            sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        }
+        if (lane == 0) { sh.ring_num[ring] = sn; sh.ring_pow[ring] = sp; sh.ring_abs[ring] = sa; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double denom2 = 0.0;
+        for (int i = 0; i <= DC_NR; ++i) denom2 += sh.ring_pow[i];
+        double cn = 0.0, ca = 0.0;
+        for (int i = 0; i < DC_NR; ++i) {
+            cn += sh.ring_num[i];
+            ca += sh.ring_abs[i];
+            double v = cn / sqrt(ca * denom2);
+            v = floor(1000.0 * v) / 1000.0;
+            sh.d[i] = isnan(v) ? 0.0 : v;
+        }
+        dc_peak(sh.d, DC_NR, tol, &sh.idx, &sh.A);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(DC_THREADS) decorr_kernel(const double2* __restrict__ Ik_all, const double2* __restrict__ Ikn_all,
+                                                            const double* __restrict__ R, const double* __restrict__ R2, int N,
+                                                            int n_inside, const double* __restrict__ r_coarse, double sigma0,
+                                                            double gmax_flat, double pixelsize, double res_cap, double tol,
+                                                            double* __restrict__ res_out) {
+    __shared__ DecorrShared sh;
+    const double2* Ik = Ik_all + (size_t)blockIdx.x * N;
+    const double2* Ikn = Ikn_all + (size_t)blockIdx.x * N;
+    if (threadIdx.x < DC_NR) sh.r[threadIdx.x] = r_coarse[threadIdx.x];
+    __syncthreads();
+    dc_bounds(sh, R, N, sh.r);
+    dc_pass(sh, Ik, Ikn, R2, n_inside, false, 0.0, tol);
+    if (threadIdx.x == 0) {
+        const double r0 = sh.r[sh.idx];
+        sh.rs[0] = r0;
+        sh.As[0] = sh.A;
+        double g_max = 2.0 / r0;
+        if (isinf(g_max)) g_max = gmax_flat;
+        sh.sigmas[0] = sigma0;
+        dc_linspace(log(g_max), log(0.15), DC_NG, sh.sigmas + 1);
+        for (int j = 1; j <= DC_NG; ++j) sh.sigmas[j] = exp(sh.sigmas[j]);
+    }
+    __syncthreads();
+    for (int j = 0; j <= DC_NG; ++j) {
+        dc_pass(sh, Ik, Ikn, R2, n_inside, sh.sigmas[j] != 0.0, sh.sigmas[j], tol);
+        if (threadIdx.x == 0) { sh.rs[1 + j] = sh.r[sh.idx]; sh.As[1 + j] = sh.A; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int n = DC_NG + 2;
+        double mx = sh.rs[0];
+        for (int i = 1; i < n; ++i) mx = fmax(mx, sh.rs[i]);
+        int k = 0;
+        for (int i = 0; i < n; ++i) if (sh.rs[i] == mx) k = i;                     // last index of the maximum
+        const int ind1 = k == 0 ? 0 : (k >= DC_NG ? k - 2 : k - 1);
+        dc_linspace(sh.rs[k] - (sh.r[1] - sh.r[0]), fmin(sh.rs[k] + 0.4, sh.r[DC_NR - 1]), DC_NR, sh.r_fine);
+        dc_linspace(log(sh.sigmas[ind1]), log(sh.sigmas[ind1 + 1]), DC_NG, sh.sig_fine);
+        for (int j = 0; j < DC_NG; ++j) sh.sig_fine[j] = exp(sh.sig_fine[j]);
+    }
+    __syncthreads();
+    dc_bounds(sh, R, N, sh.r_fine);
+    for (int j = 0; j < DC_NG; ++j) {
+        dc_pass(sh, Ik, Ikn, R2, n_inside, sh.sig_fine[j] != 0.0, sh.sig_fine[j], tol);
+        // the last coarse entry (index DC_NG+1) is dropped by the reference before the refined ones are appended
+        if (threadIdx.x == 0) { sh.rs[DC_NG + 1 + j] = sh.r_fine[sh.idx]; sh.As[DC_NG + 1 + j] = sh.A; }
+    }
+    if (threadIdx.x == 0) {
+        const int n = 2 * DC_NG + 2;
+        sh.rs[n - 1] = sh.rs[0];
+        sh.As[n - 1] = sh.As[0];
+        double mx = -1.0e300;
+        for (int i = 0; i < n; ++i) mx = fmax(mx, sh.As[i] < 0.05 ? 0.0 : sh.rs[i]);
+        const double res = 2.0 / mx * pixelsize / 1e-9;
+        res_out[blockIdx.x] = res > res_cap ? res_cap : res;
+    }
+}
+
+}  // namespace
+
+extern "C" int sted_decorrelation_resolution(const void* ik_dev, const void* ikn_dev, int B, int N, int n_inside,
+                                             const double* radius_dev, const double* radius2_dev, const double* r_coarse_dev,
+                                             double sigma0, double gmax_flat, double pixelsize, double res_cap, double tol,
+                                             double* res_dev, void* stream) {
+    if (!ik_dev || !ikn_dev || !radius_dev || !radius2_dev || !r_coarse_dev || !res_dev) return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || N <= 0 || n_inside < 0 || n_inside > N) return fail(STED_EINVAL, "bad decorrelation sizes");
+    int rc = check_device();
+    if (rc) return rc;
+    decorr_kernel<<<B, DC_THREADS, 0, (cudaStream_t)stream>>>((const double2*)ik_dev, (const double2*)ikn_dev, radius_dev, radius2_dev,
+                                                             N, n_inside, r_coarse_dev, sigma0, gmax_flat, pixelsize, res_cap, tol,
+                                                             res_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+// =============================================================================================================
 // Gaussian-fit validation of the candidates (gym_sted/rewards/utils.py:6-49): for every candidate a 7x7 window of
 // the (zero-padded) STED image is fitted with amplitude*exp(-((cx-x)^2/(2 wx^2) + (cy-y)^2/(2 wy^2))) by
 // Levenberg-Marquardt, and the candidate is kept when 40 nm <= 2.355*w*pixelsize <= 200 nm for both widths.

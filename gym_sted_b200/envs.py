@@ -158,6 +158,8 @@ class VectorContextualMOSTED:
             self.bleach_sampler = BleachSampler(**bleach_sampling)
         else:
             self.bleach_sampler = BleachSampler(mode=bleach_sampling)
+        if seed is not None:
+            self.bleach_sampler.rng.seed(int(self.np_rng.integers(0, 2 ** 31 - 1)))
         self.bm = BatchedMicroscope(self.microscope, self.B, self.H, self.W, defaults.PIXELSIZE, device=self.device,
                                     env_base=self.env_base, seed=int(self.np_rng.integers(0, 2 ** 31 - 1)))
         self.conf = (defaults.PDT, defaults.P_EX, 0.0)            # generate_params(): pdt, p_ex, p_sted
@@ -196,6 +198,7 @@ class VectorContextualMOSTED:
     def reset(self, seed=None, options=None):
         if seed is not None:
             self.np_rng = np.random.default_rng(seed)
+            self.bleach_sampler.rng.seed(int(self.np_rng.integers(0, 2 ** 31 - 1)))
             self.torch_gen = None
         fluos = [base.Fluorescence(**self.bleach_sampler.sample(self.microscope)) for _ in range(self.B)] \
             if self.bleach_sampler.mode != "constant" else None
@@ -362,6 +365,7 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
     def reset(self, seed=None, options=None):
         if seed is not None:
             self.np_rng = np.random.default_rng(seed)
+            self.bleach_sampler.rng.seed(int(self.np_rng.integers(0, 2 ** 31 - 1)))
             self.datamap_generator.rng = np.random.default_rng(seed + 1)
         self.groups = [self.datamap_generator.sample_group() for _ in range(self.B)]
         self.conf_p_ex = None

@@ -53,43 +53,6 @@ def foreground_objectives(conf1: torch.Tensor, sted: torch.Tensor, conf2: torch.
 # ------------------------------------------------------------------------------------------------
 # a8: resolution
 # ------------------------------------------------------------------------------------------------
-def _decorr_peak(d: np.ndarray, tol: float):
-    """Reference's ``decorr_peak`` (objectives.py:217-227) for one curve."""
-    idx = int(np.argmax(d))
-    A = d[idx]
-    while len(d) > 1:
-        if (A - np.min(d[idx:])) >= tol or idx == 0:
-            break
-        d = d[:-1]
-        idx = int(np.argmax(d))
-        A = d[idx]
-    return idx, A
-
-
-def _decorr_peak_batch(d: np.ndarray, tol: float):
-    """``decorr_peak`` for a (B, n) stack of curves at once: the loop shortens the curve from the right until
-    the leading maximum stands ``tol`` above the minimum to its right (or sits at index 0); evaluate that
-    condition for every length L and take the largest L that satisfies it."""
-    B, n = d.shape
-    pos = np.arange(n)
-    prefix_max = np.maximum.accumulate(d, axis=1)
-    prev_max = np.concatenate([np.full((B, 1), -np.inf), prefix_max[:, :-1]], axis=1)
-    new_max = d > prev_max                                           # first occurrence of each running maximum
-    idx_L = np.maximum.accumulate(np.where(new_max, pos[None, :], 0), axis=1)      # argmax(d[:L]) at column L-1
-    A_L = np.take_along_axis(d, idx_L, axis=1)
-    # min(d[idx_L:L]): running minimum restarted at every new leading maximum
-    m_L = np.empty_like(d)
-    run = d[:, 0].copy()
-    for j in range(n):
-        run = np.where(new_max[:, j], d[:, j], np.minimum(run, d[:, j]))
-        m_L[:, j] = run
-    ok = ((A_L - m_L) >= tol) | (idx_L == 0)
-    ok[:, 0] = True                                                  # a single point always ends the loop
-    L = n - 1 - np.argmax(ok[:, ::-1], axis=1)                       # last column (largest length) where ok
-    idx = idx_L[np.arange(B), L]
-    return idx, d[np.arange(B), idx]
-
-
 class _Decorrelator:
     """Geometry shared by every image of one shape: apodisation window, radius map, radius-sorted order."""
 
@@ -105,30 +68,25 @@ class _Decorrelator:
         self.R_sorted_np = R[order]
         self.order = torch.from_numpy(order).to(device)
         self.R_sorted = torch.from_numpy(self.R_sorted_np).to(device)
+        self.R2_sorted = self.R_sorted ** 2
         self.inside = self.R_sorted < 1
+        self.n_inside = int(np.sum(self.R_sorted_np < 1))
+        self._r = {}
 
-
-def _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, bounds, sigmas=None):
-    """Ik, Ikn_conj: (B,N) complex in radius-sorted order; cum_abs2: (B,N+1) prefix sums of |Ikn|^2;
-    bounds: (B,Nr) int64 = number of pixels with R < r_i; sigmas: (B,) or None.  Returns d (B,Nr) float64."""
-    if sigmas is not None:
-        Ik = Ik * (1 - torch.exp(-2 * sigmas[:, None] ** 2 * R2[None, :]))
-    num = torch.real(Ik * Ikn_conj)
-    cum = torch.zeros((Ik.shape[0], Ik.shape[1] + 1), dtype=torch.float64, device=Ik.device)
-    torch.cumsum(num, dim=1, out=cum[:, 1:])
-    nom = torch.gather(cum, 1, bounds)
-    denom1 = torch.gather(cum_abs2, 1, bounds)
-    denom2 = torch.sum(Ik.real ** 2 + Ik.imag ** 2, dim=1, keepdim=True)
-    d = nom / torch.sqrt(denom1 * denom2)
-    d = torch.floor(1000 * d) / 1000
-    return torch.nan_to_num(d, nan=0.0, posinf=float("inf"), neginf=float("-inf"))
+    def r_coarse(self, Nr):
+        if Nr not in self._r:
+            self._r[Nr] = torch.from_numpy(np.linspace(0, 1, Nr)).to(self.R_sorted.device)
+        return self._r[Nr]
 
 
 _DECORR_CACHE: dict = {}
 
 
 def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, Ng=10, tol=0.0005) -> np.ndarray:
-    """(B,H,W) photon counts on the GPU -> (B,) float64 numpy array of resolutions in nm (capped)."""
+    """(B,H,W) photon counts on the GPU -> (B,) float64 numpy array of resolutions in nm (capped).
+    Apodisation, FFT (cuFFT) and the radius sort run through torch; the 22 decorrelation passes and their peak
+    searches are one launch of ``decorr_kernel`` (one CTA per image)."""
+    assert Nr == 50 and Ng == 10, "decorr_kernel is compiled for the reference's Nr = 50, Ng = 10"
     B, H, W = sted.shape
     dev = sted.device
     key = (H, W, str(dev))
@@ -144,54 +102,13 @@ def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, 
     mag = torch.abs(Ik)
     Ikn = torch.where(mag > 0, Ik / mag, torch.zeros_like(Ik))
     Ikn = torch.where(torch.isfinite(Ikn.real) & torch.isfinite(Ikn.imag), Ikn, torch.zeros_like(Ikn))
-    Ikn_conj = torch.conj(Ikn)
-    cum_abs2 = torch.zeros((B, Ik.shape[1] + 1), dtype=torch.float64, device=dev)
-    torch.cumsum(Ikn.real ** 2 + Ikn.imag ** 2, dim=1, out=cum_abs2[:, 1:])
-    R2 = geo.R_sorted ** 2
-
-    def bounds_for(radii_np):          # (B,Nr) radii -> number of pixels with R < r
-        return torch.from_numpy(np.searchsorted(geo.R_sorted_np, radii_np, side="left")).to(dev)
-
-    r = np.linspace(0, 1, Nr)
-    b_shared = bounds_for(np.broadcast_to(r, (B, Nr)))
-    d0 = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_shared).cpu().numpy()
-    i0, A0 = _decorr_peak_batch(d0, tol)
-    r0 = r[i0]
-    with np.errstate(divide="ignore"):
-        g_max = 2 / r0
-    g_max[np.isinf(g_max)] = max(geo.Hc, geo.Wc) / 2
-    sigmas = np.concatenate([np.full((B, 1), geo.Hc / 4),
-                             np.exp(np.linspace(np.log(g_max), np.log(0.15), Ng, axis=1))], axis=1)      # (B, Ng+1)
-    As = [A0]
-    rs = [r0]
-    for j in range(Ng + 1):
-        d = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_shared, torch.from_numpy(sigmas[:, j]).to(dev)).cpu().numpy()
-        ik, Ak = _decorr_peak_batch(d, tol)
-        rs.append(r[ik])
-        As.append(Ak)
-    rs_a = np.stack(rs, axis=1)            # (B, Ng+2)
-    As_a = np.stack(As, axis=1)
-    kmax = rs_a.shape[1] - 1 - np.argmax((rs_a == rs_a.max(axis=1, keepdims=True))[:, ::-1], axis=1)
-    ind1 = np.where(kmax == 0, 0, np.where(kmax >= Ng, kmax - 2, kmax - 1))
-    peak_r = rs_a[np.arange(B), kmax]
-    r_fine = np.linspace(peak_r - (r[1] - r[0]), np.minimum(peak_r + 0.4, r[-1]), Nr, axis=1)
-    sig_fine = np.exp(np.linspace(np.log(sigmas[np.arange(B), ind1]), np.log(sigmas[np.arange(B), ind1 + 1]), Ng, axis=1))
-    b_fine = bounds_for(r_fine)
-    rs_l = [rs_a[:, :-1]]
-    As_l = [As_a[:, :-1]]
-    for j in range(Ng):
-        d = _decorr_batch(Ik, Ikn_conj, cum_abs2, R2, b_fine, torch.from_numpy(sig_fine[:, j]).to(dev)).cpu().numpy()
-        ik, Ak = _decorr_peak_batch(d, tol)
-        rs_l.append(r_fine[np.arange(B), ik][:, None])
-        As_l.append(Ak[:, None])
-    rs_l.append(r0[:, None])
-    As_l.append(A0[:, None])
-    rs_f = np.concatenate(rs_l, axis=1)
-    As_f = np.concatenate(As_l, axis=1)
-    rs_f[As_f < 0.05] = 0
-    with np.errstate(divide="ignore"):
-        res = 2 / rs_f.max(axis=1) * pixelsize / 1e-9
-    return np.minimum(res, res_cap)
+    res = torch.empty((B,), dtype=torch.float64, device=dev)
+    Ik, Ikn = Ik.contiguous(), Ikn.contiguous()
+    _lib.check(_lib.load().sted_decorrelation_resolution(
+        Ik.data_ptr(), Ikn.data_ptr(), B, Ik.shape[1], geo.n_inside, geo.R_sorted.data_ptr(), geo.R2_sorted.data_ptr(),
+        geo.r_coarse(Nr).data_ptr(), geo.Hc / 4, max(geo.Hc, geo.Wc) / 2, float(pixelsize), float(res_cap), float(tol),
+        res.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return res.cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------------

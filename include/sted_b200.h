@@ -199,6 +199,19 @@ int sted_nanodomain_candidates(const float* sted_dev, int B, int H, int W, const
                                int64_t k0, double gamma, double* scratch_dev, int32_t* peaks_dev,
                                int32_t* npeaks_dev, int32_t* flags_dev, void* stream);
 
+/* Resolution objective by image decorrelation (gym_sted/rewards/objectives.py:146-335, 378-385): all 22 decorrelation
+ * passes and peak searches of B images, one CTA per image.
+ *   ik_dev, ikn_dev : complex128 [B][N] centred Fourier transform of the apodised image and its phase-only version,
+ *                     pixels sorted by normalised radius (stable), zero where R >= 1
+ *   radius_dev, radius2_dev : float64 [N] the sorted radii and their squares; n_inside = number of radii < 1
+ *   r_coarse_dev    : float64 [50] = numpy.linspace(0, 1, 50)
+ *   sigma0 = Hc/4, gmax_flat = max(Hc, Wc)/2 (the reference's substitutes when the first peak sits at r = 0)
+ *   res_dev         : float64 [B] resolution in nm, capped at res_cap */
+int sted_decorrelation_resolution(const void* ik_dev, const void* ikn_dev, int B, int N, int n_inside,
+                                  const double* radius_dev, const double* radius2_dev, const double* r_coarse_dev,
+                                  double sigma0, double gmax_flat, double pixelsize, double res_cap, double tol,
+                                  double* res_dev, void* stream);
+
 /* Gaussian-fit validation of nanodomain candidates (gym_sted/rewards/utils.py:6-49, called from
  * gym_sted/rewards/objectives.py:424): one Levenberg-Marquardt fit (MINPACK LMDIF restated, float64) of a 7x7
  * zero-padded window per candidate; valid = both FWHMs 2.355*w*pixelsize inside [40 nm, 200 nm].

