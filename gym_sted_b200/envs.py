@@ -233,7 +233,7 @@ class VectorContextualMOSTED:
             f1 = np.zeros(self.B)
         reward = f1 * self.scale_nanodomain_reward
 
-        done = self.current_step >= self.max_episode_steps - 1
+        done = np.full(self.B, self.current_step >= self.max_episode_steps - 1) | self._exhausted()
         self.current_step += 1
         self.episode_memory["mo_objs"].append(mo_objs)
         self.episode_memory["actions"].append(action)
@@ -252,13 +252,34 @@ class VectorContextualMOSTED:
         obs = np.concatenate(obs, axis=1)
         obs = np.pad(obs, ((0, 0), (0, self.observation_space[1].shape[0] - obs.shape[1])))
 
-        state = self._new_datamaps()
+        state = self._next_state()
         self.state = torch.stack((state, conf1, sted), dim=-1)
         img = self._u16(self.state).cpu().numpy().astype(np.uint16)
-        return (img, obs.astype(np.float32)), reward, np.full(self.B, done), np.zeros(self.B, dtype=bool), info
+        return (img, obs.astype(np.float32)), reward, done, np.zeros(self.B, dtype=bool), info
+
+    def _next_state(self):
+        """Contextual bandit: every step ends on a fresh synapse (contextual_sted_env.py:90)."""
+        return self._new_datamaps()
+
+    def _exhausted(self):
+        return np.zeros(self.B, dtype=bool)
 
     def close(self):
         return None
+
+
+class VectorSequenceMOSTED(VectorContextualMOSTED):
+    """B ``SequenceSTEDMultiObjectivesEnv`` environments (``gym_sted/envs/sequence_sted_env.py:19-140``): the same
+    structure is imaged again at every step, so the datamap carries its photobleaching through the episode
+    (the boundary's in-place update, ``:84-90``), and an environment is done early once its datamap is empty
+    (``:109``)."""
+
+    def _next_state(self):
+        state, _ = self.bm.get_signal_and_bleach(*self.conf, bleach=False)
+        return state
+
+    def _exhausted(self):
+        return (self.bm.datamaps_roi().amax(dim=(1, 2)) == 0).cpu().numpy()
 
 
 class ContextualSTEDMultiObjectivesEnv:
@@ -267,10 +288,12 @@ class ContextualSTEDMultiObjectivesEnv:
     metadata = {"render.modes": ["human"]}
     obj_names = OBJ_NAMES
 
+    vector_cls = VectorContextualMOSTED
+
     def __init__(self, bleach_sampling="constant", actions=("p_sted",), max_episode_steps=10, scale_nanodomain_reward=1.0,
                  normalize_observations=True, **kwargs):
-        self.vec = VectorContextualMOSTED(1, bleach_sampling, actions, max_episode_steps, scale_nanodomain_reward,
-                                          normalize_observations, **kwargs)
+        self.vec = self.vector_cls(1, bleach_sampling, actions, max_episode_steps, scale_nanodomain_reward,
+                                   normalize_observations, **kwargs)
         self.action_space, self.observation_space = self.vec.action_space, self.vec.observation_space
         self.actions = self.vec.actions
         self.spec = SimpleNamespace(id=None, max_episode_steps=max_episode_steps)
@@ -291,6 +314,12 @@ class ContextualSTEDMultiObjectivesEnv:
 
     def close(self):
         return None
+
+
+class SequenceSTEDMultiObjectivesEnv(ContextualSTEDMultiObjectivesEnv):
+    """Single-environment view of ``VectorSequenceMOSTED``."""
+
+    vector_cls = VectorSequenceMOSTED
 
 
 class SyntheticDatamapGenerator:
@@ -423,7 +452,7 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         count_rate = sted.amax(dim=(1, 2)).cpu().numpy() / pdt
         reward = np.where(count_rate > self.max_count_rate, self.negative_reward, reward)
 
-        done = self.current_step >= self.max_episode_steps - 1
+        done = np.full(self.B, self.current_step >= self.max_episode_steps - 1) | self._exhausted()
         self.current_step += 1
         self.episode_memory["mo_objs"].append(mo_objs)
         self.episode_memory["actions"].append(action)
@@ -452,6 +481,13 @@ REGISTRY = {
         scale_nanodomain_reward=1.0)),
     "ContextualMOSTED-hard-v0": dict(max_episode_steps=10, kwargs=dict(
         actions=["p_sted", "p_ex", "pdt"], bleach_sampling="uniform", scale_nanodomain_reward=1.0)),
+    # gym_sted/__init__.py:822-909
+    **{f"SequenceMOSTED-{name}-v0": dict(max_episode_steps=10, cls="sequence", kwargs=dict(
+        actions=["p_sted", "p_ex", "pdt"], bleach_sampling=sampling, scale_nanodomain_reward=1.0))
+       for name, sampling in (("easy", "constant"), ("mid", "choice"), ("hard", "uniform"),
+                              *((f"easy-{short}", {"mode": "constant", "routine": routine}) for short, routine in (
+                                  ("hslb", "high-signal_low-bleach"), ("hshb", "high-signal_high-bleach"),
+                                  ("lslb", "low-signal_low-bleach"), ("lshb", "low-signal_high-bleach"))))},
     # gym_sted/__init__.py:522-531
     "PreferenceCountRateMOSTED-hard-v0": dict(max_episode_steps=30, cls="preference", kwargs=dict(
         actions=["p_sted", "p_ex", "pdt"], bleach_sampling="uniform", max_episode_steps=30)),
@@ -466,7 +502,8 @@ def make(env_id: str, **overrides):
     entry = REGISTRY[key]
     if entry.get("cls") == "preference":
         raise NotImplementedError("PreferenceCountRateMOSTED is provided as a vector env: use make_vec(id, num_envs)")
-    env = ContextualSTEDMultiObjectivesEnv(max_episode_steps=entry["max_episode_steps"], **{**entry["kwargs"], **overrides})
+    cls = SequenceSTEDMultiObjectivesEnv if entry.get("cls") == "sequence" else ContextualSTEDMultiObjectivesEnv
+    env = cls(max_episode_steps=entry["max_episode_steps"], **{**entry["kwargs"], **overrides})
     env.spec = SimpleNamespace(id=key, max_episode_steps=entry["max_episode_steps"])
     return env
 
@@ -475,5 +512,5 @@ def make_vec(env_id: str, num_envs: int, **overrides):
     key = env_id.split(":")[-1]
     entry = REGISTRY[key]
     kwargs = {"max_episode_steps": entry["max_episode_steps"], **entry["kwargs"], **overrides}
-    cls = VectorPreferenceCountRateMOSTED if entry.get("cls") == "preference" else VectorContextualMOSTED
+    cls = {"preference": VectorPreferenceCountRateMOSTED, "sequence": VectorSequenceMOSTED}.get(entry.get("cls"), VectorContextualMOSTED)
     return cls(num_envs, **kwargs)

@@ -308,3 +308,41 @@ def test_resolution_matches_oracle_on_other_sizes():
     ref = np.array([ro.resolution(i) for i in imgs])
     np.testing.assert_allclose(got, ref, rtol=1e-12)
     assert got[0] < got[1] < got[2] <= 300
+
+
+def test_sequence_env_carries_bleaching_and_terminates_on_empty_datamap():
+    """SequenceMOSTED (sequence_sted_env.py:53-140): one structure per episode, the datamap keeps its photobleaching
+    from step to step, the next observation is a confocal of the bleached structure, done when it is empty."""
+    _gpu()
+    assert {"SequenceMOSTED-easy-v0", "SequenceMOSTED-easy-hshb-v0", "SequenceMOSTED-mid-v0", "SequenceMOSTED-hard-v0"} <= set(envs.REGISTRY)
+    vec = envs.make_vec("SequenceMOSTED-easy-hslb-v0", 6, seed=3)
+    (img0, v0), _ = vec.reset(seed=3)
+    coords0 = [c.copy() for c in (s.nanodomains_coords for s in vec.synapses)]
+    total = [float(vec.bm.datamaps_roi().sum())]
+    acts = np.tile(np.array([[0.15, 10e-6, 20e-6]], dtype=np.float32), (6, 1))         # STED power that bleaches visibly
+    acts[5] = [0.0, 1e-6, 1e-6]                                                        # nearly harmless confocal
+    for t in range(4):
+        before = vec.bm.datamaps_roi().clone()
+        (img, v), reward, done, trunc, info = vec.step(acts)
+        after = vec.bm.datamaps_roi()
+        assert torch.equal(info["bleached"], after) and bool((after <= before).all())    # same maps, only ever bleached
+        total.append(float(after.sum()))
+        for c, s in zip(coords0, vec.synapses):
+            assert np.array_equal(c, s.nanodomains_coords)                             # same structure all episode
+        assert not done.any()
+    assert total[4] < total[3] < total[2] < total[1] < total[0] and total[4] < 0.85 * total[0], total
+    # channel 0 of the next observation is a confocal of the *bleached* structure: dimmer than the first one
+    assert img[:5, ..., 0].astype(np.int64).sum() < 0.9 * img0[:5, ..., 0].astype(np.int64).sum()
+    assert abs(int(img[5, ..., 0].astype(np.int64).sum()) - int(img0[5, ..., 0].astype(np.int64).sum())) < 0.2 * img0[5, ..., 0].sum()
+    # an empty datamap ends the episode of that environment only
+    roi = vec.bm.datamaps_roi().clone()
+    roi[2] = 0
+    vec.bm.set_datamaps(roi)
+    _, _, done, _, _ = vec.step(acts)
+    assert done.tolist() == [False, False, True, False, False, False]
+    # single-environment view
+    env = envs.make("SequenceMOSTED-easy-v0")
+    (img, v), _ = env.reset(seed=1)
+    for t in range(10):
+        (img, v), r, d, tr, info = env.step(np.array([0.1, 10e-6, 20e-6], dtype=np.float32))
+        assert d == (t == 9) and tr is False and info["bleached"].shape == (64, 64)
