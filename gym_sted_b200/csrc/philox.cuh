@@ -78,6 +78,14 @@ struct PhiloxStream {
         buf.w = first;
         have = 1;
     }
+    // same with two given words (one Philox block shared by two pixels)
+    STED_HD void init_with_two(uint32_t first, uint32_t second, uint64_t seed, uint32_t offset, uint32_t env,
+                               uint32_t site, uint32_t purpose, uint32_t row) {
+        init(seed, offset, env, site, purpose, row);
+        buf.z = first;
+        buf.w = second;
+        have = 2;
+    }
     STED_HD uint32_t next() {
         if (have == 0) {
             buf = philox4x32_10(ctr, k0, k1);
@@ -155,8 +163,8 @@ __device__ __forceinline__ float poisson_sample(float lam, PhiloxStream& rng) {
         float pmf = __expf(-lam);
         int k = 0;
         while (k < 200) {
-            pmf *= lam / (float)(k + 1);
             ++k;
+            pmf *= __fdividef(lam, (float)k);
             tail -= pmf;
             if (w >= tail) break;
         }
@@ -191,6 +199,35 @@ __device__ __forceinline__ float poisson_sample(float lam, PhiloxStream& rng) {
         if (lhs <= rhs) return kf;
     }
     return floorf(lam + 0.5f);
+}
+
+// First, branch-light stage of poisson_sample for the detector kernel: resolves the common exits with the two given
+// words (inversion: K <= 2; PTRS: the squeeze acceptance of the first proposal).  Returns false when the pixel needs
+// the full sampler; poisson_sample started from the same two words retraces these steps and continues, so a caller
+// may defer such pixels and run them together (same result as calling poisson_sample directly).
+__device__ __forceinline__ bool poisson_fast(float lam, uint32_t w0, uint32_t w1, float* out) {
+    if (!(lam > 0.0f)) { *out = 0.0f; return true; }
+    const float u0 = ((float)w0 + 0.5f) * 2.3283064365386963e-10f;
+    if (lam < 12.0f) {
+        float tail = -expm1f(-lam);
+        if (u0 >= tail) { *out = 0.0f; return true; }
+        float pmf = __expf(-lam) * lam;
+        tail -= pmf;
+        if (u0 >= tail) { *out = 1.0f; return true; }
+        pmf *= lam * 0.5f;
+        tail -= pmf;
+        if (u0 >= tail) { *out = 2.0f; return true; }
+        return false;
+    }
+    const float slam = sqrtf(lam);
+    const float b = 0.931f + 2.53f * slam;
+    const float a = -0.059f + 0.02483f * b;
+    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+    const float U = u0 - 0.5f;
+    const float V = ((float)w1 + 0.5f) * 2.3283064365386963e-10f;
+    const float us = 0.5f - fabsf(U);
+    *out = floorf((2.0f * a / us + b) * U + lam + 0.43f);
+    return us >= 0.07f && V <= vr;
 }
 
 #endif  // __CUDACC__

@@ -9,6 +9,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -118,11 +119,11 @@ struct AcqParams {
 // Detector.get_signal: photons = floor(I/e_photon); mean = photons*pcef*pdef*pdt + bg*pdt; Poisson when noisy.
 // `first` is this pixel's first random word (one Philox block serves four neighbouring pixels).
 __device__ __forceinline__ float detect(const AcqParams& P, float I, float gain, float bg_mean,
-                                        uint32_t env, uint32_t site, uint32_t first) {
+                                        uint32_t env, uint32_t site, uint32_t first, uint32_t second) {
     const float mean = floorf(I * P.inv_e_photon) * gain + bg_mean;
     if (P.flags & STED_SAMPLE_PHOTONS) {
         PhiloxStream rng;
-        rng.init_with_first(first, P.seed, P.offset, env, site, STED_RNG_PHOTON2, 0);
+        rng.init_with_two(first, second, P.seed, P.offset, env, site, STED_RNG_PHOTON2, 0);
         return poisson_sample(mean, rng);
     }
     return mean;
@@ -273,36 +274,81 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
 // Detector.get_signal for every pixel of the batch, in place on `signal` (power -> photon counts).
 // A separate, light kernel: the Poisson sampler is latency bound and runs at full occupancy here
 // instead of at the 12 warps/SM of the gather kernel.
-__global__ void __launch_bounds__(256) detect_kernel(const AcqParams P) {
+constexpr int DET_THREADS = 256, DET_QCAP = 1024;     // ring capacity >= (DET_THREADS - 1) + 2 * DET_THREADS
+
+__global__ void __launch_bounds__(DET_THREADS) detect_kernel(const AcqParams P) {
+    // thread = two neighbouring pixels sharing one Philox block (two words each).  Stage 1 computes the Poisson mean
+    // and resolves the common sampler exits in straight-line code (poisson_fast).  Every other pixel is queued in a
+    // shared-memory ring by sampler class - inversion (mean < 12) or PTRS - and the rings are drained 256 entries at
+    // a time by whole warps, so the lanes of a warp run the same slow branch instead of the union of both at 3-9
+    // active lanes.
+    __shared__ uint32_t q_pix[2][DET_QCAP], q_w0[2][DET_QCAP], q_w1[2][DET_QCAP];
+    __shared__ unsigned q_head[2], q_tail[2];
     const size_t hw = (size_t)P.H * P.W;
-    const size_t groups_per_env = (hw + 3) / 4, n_groups = groups_per_env * P.B;
-    const bool vec = (hw & 3) == 0;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(g / groups_per_env);
-        const uint32_t grp = (uint32_t)(g - (size_t)b * groups_per_env);
-        const uint32_t env = P.env_base + (uint32_t)b;
-        const float dwell = (float)P.pdt[b];
-        const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
-        Philox4 r4 = {0u, 0u, 0u, 0u};
-        if (P.flags & STED_SAMPLE_PHOTONS) {
-            Philox4 c;
-            c.x = grp; c.y = env; c.z = STED_RNG_PHOTON << 28; c.w = P.offset;
-            r4 = philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+    const size_t groups_per_env = (hw + 1) / 2, n_groups = groups_per_env * P.B;
+    const bool sample = (P.flags & STED_SAMPLE_PHOTONS) != 0;
+    if (threadIdx.x < 2) { q_head[threadIdx.x] = 0; q_tail[threadIdx.x] = 0; }
+    __syncthreads();
+    auto drain = [&](bool all) {            // all threads; whole batches of DET_THREADS entries unless `all`
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+            const unsigned head = q_head[q], pending = q_tail[q] - head;
+            const unsigned n = all ? pending : pending / DET_THREADS * DET_THREADS;
+#pragma unroll 1
+            for (unsigned i = threadIdx.x; i < n; i += DET_THREADS) {
+                const unsigned slot = (head + i) % DET_QCAP;
+                const uint32_t pix = q_pix[q][slot];              // pixel index within this launch (< 2^31)
+                const int b = (int)(pix / hw);
+                const uint32_t site = (uint32_t)(pix - (size_t)b * hw);
+                const float dwell = (float)P.pdt[b];
+                float* px = P.signal + pix;
+                *px = detect(P, *px, P.det_eff * dwell, P.background * dwell, P.env_base + (uint32_t)b, site, q_w0[q][slot],
+                             q_w1[q][slot]);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) q_head[q] = head + n;
         }
-        float* px = P.signal + (size_t)b * hw + 4 * (size_t)grp;
-        const uint32_t site = 4u * grp;
-        if (vec) {
-            float4 v = *reinterpret_cast<float4*>(px);
-            v.x = detect(P, v.x, gain, bg_mean, env, site, r4.x);
-            v.y = detect(P, v.y, gain, bg_mean, env, site + 1, r4.y);
-            v.z = detect(P, v.z, gain, bg_mean, env, site + 2, r4.z);
-            v.w = detect(P, v.w, gain, bg_mean, env, site + 3, r4.w);
-            *reinterpret_cast<float4*>(px) = v;
-        } else {
-            const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
-            for (int j = 0; j < 4 && site + j < hw; ++j) px[j] = detect(P, px[j], gain, bg_mean, env, site + j, w4[j]);
+        __syncthreads();
+    };
+    for (size_t base = (size_t)blockIdx.x * DET_THREADS; base < n_groups; base += (size_t)gridDim.x * DET_THREADS) {
+        const size_t g = base + threadIdx.x;
+        bool full = false;                  // this thread's push completed a batch of DET_THREADS pending entries
+        if (g < n_groups) {
+            const int b = (int)(g / groups_per_env);
+            const uint32_t grp = (uint32_t)(g - (size_t)b * groups_per_env);
+            const uint32_t env = P.env_base + (uint32_t)b;
+            const float dwell = (float)P.pdt[b];
+            const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
+            const uint32_t site = 2u * grp;
+            const size_t pix = (size_t)b * hw + site;
+            float* px = P.signal + pix;
+            const bool two = site + 1 < hw;
+            const float i0 = px[0], i1 = two ? px[1] : 0.0f;
+            const float m0 = floorf(i0 * P.inv_e_photon) * gain + bg_mean;
+            const float m1 = floorf(i1 * P.inv_e_photon) * gain + bg_mean;
+            if (sample) {
+                Philox4 c;
+                c.x = grp; c.y = env; c.z = STED_RNG_PHOTON << 28; c.w = P.offset;
+                const Philox4 r4 = philox4x32_10(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+                auto stage1 = [&](float mean, uint32_t w0, uint32_t w1, uint32_t at_pix, float* dst) {
+                    float k;
+                    if (poisson_fast(mean, w0, w1, &k)) { *dst = k; return; }
+                    const int q = mean < 12.0f ? 0 : 1;
+                    const unsigned at = atomicAdd(&q_tail[q], 1u);
+                    const unsigned slot = at % DET_QCAP;
+                    q_pix[q][slot] = at_pix; q_w0[q][slot] = w0; q_w1[q][slot] = w1;   // the intensity stays in *dst for the drain
+                    full |= at + 1u - q_head[q] >= (unsigned)DET_THREADS;
+                };
+                stage1(m0, r4.x, r4.y, (uint32_t)pix, px);
+                if (two) stage1(m1, r4.z, r4.w, (uint32_t)pix + 1u, px + 1);
+            } else {
+                px[0] = m0;
+                if (two) px[1] = m1;
+            }
         }
+        if (__syncthreads_or(full)) drain(false);     // uniform decision; all pushes are visible after the barrier
     }
+    drain(true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -916,11 +962,20 @@ int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cu
 }
 
 int launch_detect(const AcqParams& P, cudaStream_t st) {
-    const size_t npx = (((size_t)P.H * P.W + 3) / 4) * P.B;      // one thread per group of four pixels
-    const size_t want = (npx + 255) / 256;
-    const unsigned blocks = (unsigned)(want < 148u * 32u ? want : 148u * 32u);
-    detect_kernel<<<blocks, 256, 0, st>>>(P);
-    CUDA_TRY(cudaGetLastError());
+    const size_t hw = (size_t)P.H * P.W;
+    const int per_launch = (int)std::max<size_t>(1, std::min<size_t>((size_t)P.B, 0x7fffffffull / hw));   // 32-bit pixel indices
+    for (int b0 = 0; b0 < P.B; b0 += per_launch) {
+        AcqParams Q = P;
+        Q.B = std::min(per_launch, P.B - b0);
+        Q.signal = P.signal + (size_t)b0 * hw;
+        Q.pdt = P.pdt + b0;
+        Q.env_base = P.env_base + (uint32_t)b0;
+        const size_t npx = ((hw + 1) / 2) * Q.B;                 // one thread per pair of pixels
+        const size_t want = (npx + DET_THREADS - 1) / DET_THREADS;
+        const unsigned blocks = (unsigned)(want < 148u * 32u ? want : 148u * 32u);
+        detect_kernel<<<blocks, DET_THREADS, 0, st>>>(Q);
+        CUDA_TRY(cudaGetLastError());
+    }
     return STED_OK;
 }
 
