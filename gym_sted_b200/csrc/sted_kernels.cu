@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -925,7 +926,10 @@ int launch_sweep_t(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
 
 template <bool STOCH>
 int launch_sweep_m(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
-    const bool wide = P.W > 64;
+#ifndef SWEEP_WIDE_MIN
+#define SWEEP_WIDE_MIN 64      // widest image still scanned in 64-column strips
+#endif
+    const bool wide = P.W > SWEEP_WIDE_MIN;
     if (P.K == 59) return wide ? launch_sweep_t<59, 16, STOCH>(P, ws, st) : launch_sweep_t<59, 8, STOCH>(P, ws, st);
     return wide ? launch_sweep_t<0, 16, STOCH>(P, ws, st) : launch_sweep_t<0, 8, STOCH>(P, ws, st);
 }
@@ -1118,7 +1122,7 @@ namespace {
 
 // Streams / events of the host-buffer entry point: upload, compute and download of different chunks overlap.
 struct HostPipe {
-    static constexpr int MAXC = 8;
+    static constexpr int MAXC = 16;
     cudaStream_t s_in = nullptr, s_out = nullptr, s_comp[MAXC];   // one compute stream per chunk: their kernels co-run
     cudaEvent_t e_in[MAXC], e_comp[MAXC];
     int* h_drop = nullptr;               // pinned: dropped-event counter of each chunk
@@ -1161,7 +1165,11 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
     const bool bleach = (flags & STED_BLEACH) != 0;
     const bool stoch = bleach && (flags & STED_SAMPLE_BLEACH);
     // chunks: upload of chunk i+1, compute of chunk i and download of chunk i-1 run concurrently
-    const int nch = B >= 32 ? 4 : (B >= 8 ? 2 : 1);
+    int nch = B >= 128 ? 8 : (B >= 32 ? 4 : (B >= 8 ? 2 : 1));      // measured on B200, 256 envs x 256^2: 2 -> 3.9, 4 -> 3.4, 8..16 -> 3.2 ms/call
+    if (const char* e = getenv("STED_B200_HOST_CHUNKS")) {        // tuning knob: 1..16 chunks
+        const int v = atoi(e);
+        if (v >= 1 && v <= HostPipe::MAXC && v <= B) nch = v;
+    }
     const int cb = (B + nch - 1) / nch;
     // scratch of the stochastic scan: starts at 4 deaths per pixel and grows when a scan reports dropped events
     static unsigned long long s_max_events = 0;
