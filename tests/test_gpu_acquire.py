@@ -391,3 +391,39 @@ def test_full_size_properties(micro):
     tot_exp, tot_st = float(d_exp.sum()), float(d_st.sum())
     assert abs(tot_exp - tot_st) < 6 * np.sqrt(float(a.sum()))
     assert abs(float(i_st.sum()) / float(i_exp.sum()) - 1) < 0.01
+
+
+@pytest.mark.parametrize("B", [5, 40, 131])
+def test_host_api_equals_device_api_for_every_chunking(B):
+    """``sted_acquire_host`` cuts the batch in 1/2/4/8 chunks on separate streams; with the same seed, offset and
+    env_base it must return exactly what the device-resident call returns (Philox is keyed by the global environment
+    id, the scan workspace is per chunk): photons, intensity and bleached maps, stochastic mode included."""
+    _require_gpu()
+    import ctypes
+    from gym_sted_b200.base import fluo_struct
+    H, W = 48, 80
+    m = helpers.product_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
+                                   background=defaults.DETECTOR["background"])
+    rng = np.random.default_rng(B)
+    maps = np.stack([helpers.synthetic_datamap(rng, H, W) for _ in range(B)]).astype(np.float32)
+    pdt, p_ex, p_sted = rng.uniform(5e-6, 40e-6, B), rng.uniform(2e-6, 15e-6, B), rng.uniform(0.02, 0.25, B)
+    lib = _lib.load()
+    cache = m._packed_cache(PX)
+    K = cache.shape[-1]
+    fl = (_lib.StedFluoParams * B)(*[fluo_struct(m.fluo, m.excitation, m.sted)] * B)
+    det = m.detector.params()
+    vp = ctypes.c_void_p
+    flags = _lib.STED_BLEACH | _lib.STED_SAMPLE_BLEACH | _lib.STED_SAMPLE_PHOTONS
+    h_map = maps.copy()
+    h_int, h_sig = np.empty_like(maps), np.empty_like(maps)
+    _lib.check(lib.sted_acquire_host(h_map.ctypes.data_as(vp), cache.ctypes.data_as(vp), ctypes.cast(fl, vp),
+                                     p_ex.ctypes.data_as(vp), p_sted.ctypes.data_as(vp), pdt.ctypes.data_as(vp), B, H, W, K,
+                                     flags, ctypes.byref(det), 77, 5, 1000, h_int.ctypes.data_as(vp), h_sig.ctypes.data_as(vp)))
+    bm = batched(m, B, H, W, pixelsize=PX, env_base=1000, seed=77)
+    bm.set_datamaps(torch.from_numpy(maps))
+    bm.offset = 4                                        # the call increments it to 5
+    sig, inten = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True, want_intensity=True)
+    assert np.array_equal(h_sig, sig.cpu().numpy())
+    assert np.array_equal(h_int, inten.cpu().numpy())
+    assert np.array_equal(h_map, bm.datamaps_roi().cpu().numpy())
+    assert h_map.sum() < maps.sum() and h_sig.max() > 5
