@@ -411,10 +411,23 @@ __global__ void __launch_bounds__(D_THREADS) nanodomain_kernel(const float* __re
             if (is_max) { ++npk; if (v > vmin) { if (nc < 64) cand[nc++] = i; else flag |= 2; } }
         }
         if (npk == size && size > 1) {
-            // "trivial image": every pixel of the component is a maximum (all values equal).  skimage then keeps
-            // only isolated pixels (mask xor its binary opening); flagged, handled on the host.
-            flag |= 4;
-            continue;
+            // "trivial image": every pixel of the component is a maximum (all values equal).  skimage then keeps only
+            // the pixels the binary opening (3x3 cross, zero border) removes: mask xor opening(mask).
+            nc = 0;
+            auto member = [&](int y, int x) {
+                if (y < 0 || x < 0 || y >= H || x >= W) return false;
+                const int j = find(y * W + x);
+                return j >= 0 && lab[j] == c;
+            };
+            auto eroded = [&](int y, int x) {
+                return member(y, x) && member(y - 1, x) && member(y + 1, x) && member(y, x - 1) && member(y, x + 1);
+            };
+            for (int i = c; i < n; ++i) {
+                if (lab[i] != c) continue;
+                const int y = fg_idx[i] / W, x = fg_idx[i] - y * W;
+                const bool opened = eroded(y, x) || eroded(y - 1, x) || eroded(y + 1, x) || eroded(y, x - 1) || eroded(y, x + 1);
+                if (!opened && f[fg_idx[i]] > vmin) { if (nc < 64) cand[nc++] = i; else flag |= 2; }
+            }
         }
         // sort by value, descending, stable in raster order (insertion sort on a handful of entries)
         for (int i = 1; i < nc; ++i) {

@@ -148,18 +148,20 @@ def _candidates_device(sted: torch.Tensor):
     return sted, peaks, npk, flags
 
 
+def _check_capacity(flags: np.ndarray):
+    if flags.any():
+        b = int(np.flatnonzero(flags)[0])
+        raise _lib.StedError(f"nanodomain_kernel capacity exceeded for image {b} (flags={int(flags[b])}: bit0 >4096 mask pixels, "
+                             f"bit1 >64 maxima in one component, bit3 >256 peaks)")
+
+
 def nanodomain_candidates(sted: torch.Tensor):
     """(B,H,W) photon counts on the GPU -> list of (n_i, 2) int arrays: peak_local_max candidates per image
     (gaussian -> q99 mask -> remove_small_objects -> label -> per-label maxima), computed by one CUDA kernel."""
     sted, peaks, npk, flags = _candidates_device(sted)
     peaks, npk, flags = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy()
-    out = []
-    for b in range(sted.shape[0]):
-        if flags[b]:        # capacity exceeded or a flat component (skimage's isolated-pixel rule): host path for this image
-            out.append(_candidate_peaks_host(np.rint(sted[b].cpu().numpy()).astype(np.int64)))
-        else:
-            out.append(peaks[b, :npk[b]].astype(np.int64))
-    return out
+    _check_capacity(flags)
+    return [peaks[b, :npk[b]].astype(np.int64) for b in range(sted.shape[0])]
 
 
 def gaussfit_validate(sted: torch.Tensor, peaks: torch.Tensor, npeaks: torch.Tensor, pixelsize=PIXELSIZE, want_params=False):
@@ -179,141 +181,24 @@ def gaussfit_validate(sted: torch.Tensor, peaks: torch.Tensor, npeaks: torch.Ten
 
 def detect_nanodomains_batch(sted: torch.Tensor, pixelsize=PIXELSIZE):
     """``NumberNanodomains`` detector for B device images: candidates and Gaussian-fit validation on the GPU, one
-    device->host read of the surviving coordinates.  Flagged images (capacity / flat component) take the host path."""
+    device->host read of the surviving coordinates."""
     sted, peaks, npk, flags = _candidates_device(sted)
     valid = gaussfit_validate(sted, peaks, npk, pixelsize)
     peaks, npk, flags, valid = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy(), valid.cpu().numpy().astype(bool)
-    out = []
-    for b in range(sted.shape[0]):
-        if flags[b]:
-            out.append(detect_nanodomains(np.rint(sted[b].cpu().numpy()).astype(np.int64), pixelsize))
-        else:
-            out.append(peaks[b, :npk[b]][valid[b, :npk[b]]].astype(np.int64))
-    return out
+    _check_capacity(flags)
+    return [peaks[b, :npk[b]][valid[b, :npk[b]]].astype(np.int64) for b in range(sted.shape[0])]
 
 
-def _ensure_spacing(coords, spacing):
-    keep = []
-    for i, c in enumerate(coords):
-        if all(np.max(np.abs(c - coords[k])) >= spacing for k in keep):
-            keep.append(i)
-    return coords[keep]
+def detect_nanodomains(sted, pixelsize=PIXELSIZE) -> np.ndarray:
+    """Single image (array or tensor) through the same device path."""
+    t = torch.as_tensor(np.asarray(sted, dtype=np.float32) if not torch.is_tensor(sted) else sted)
+    return detect_nanodomains_batch(t.to("cuda", torch.float32)[None], pixelsize)[0]
 
 
-def _candidate_peaks_host(sted: np.ndarray, threshold=2) -> np.ndarray:
-    """Host twin of ``nanodomain_kernel`` (used for flagged images and by the single-image API)."""
-    import scipy.ndimage as ndi
-
-    filtered = ndi.gaussian_filter(2.0 * np.asarray(sted, dtype=np.float64) + 1.0, 0.5, mode="nearest", truncate=4.0)
-    mask = filtered > np.quantile(filtered, 0.99)
-    eight = np.ones((3, 3), dtype=bool)
-    lab, n = ndi.label(mask, structure=eight)
-    if n:
-        sizes = np.bincount(lab.ravel())
-        small = sizes < 4
-        small[0] = False
-        mask &= ~small[lab]
-    labels, _ = ndi.label(mask, structure=eight)
-    lowest = filtered.min()
-    peaks = []
-    for li, roi in enumerate(ndi.find_objects(labels)):
-        if roi is None:
-            continue
-        inside = labels[roi] == li + 1
-        obj = np.where(inside, filtered[roi], np.finfo(np.float64).min)
-        if obj.size == 1:
-            pm = obj > lowest
-        else:
-            pm = obj == ndi.maximum_filter(obj, size=2 * threshold + 1, mode="nearest")
-            if np.all(pm[inside]):
-                pm[:] = False
-                pm[np.logical_xor(inside, ndi.binary_opening(inside))] = True
-            pm &= obj > lowest
-        cc = np.transpose(np.nonzero(pm))
-        cc = cc[np.argsort(-obj[tuple(cc.T)], kind="stable")]
-        cc = _ensure_spacing(cc, threshold)
-        peaks.append(cc + np.array([s.start for s in roi]))
-    return np.vstack(peaks) if peaks else np.zeros((0, 2), dtype=np.int64)
-
-
-def _fit_windows(windows: np.ndarray, pixelsize: float) -> np.ndarray:
-    """``rewards/utils.fitgaussian`` + the FWHM test of ``validate_positions`` for a stack of 7x7 windows:
-    Levenberg-Marquardt through MINPACK (``scipy.optimize.leastsq``, ftol 1e-3) exactly as in the reference."""
-    import scipy.optimize
-
-    X, Y = np.indices((7, 7)) - 3.0
-    ok = np.zeros(len(windows), dtype=bool)
-    for i, data in enumerate(windows):
-        def err(p):
-            wx, wy = float(p[3]) + 1e-3, float(p[4]) + 1e-3
-            return np.ravel(p[0] * np.exp(-(((p[1] - X) ** 2.0 / (2 * wx ** 2.0)) + ((p[2] - Y) ** 2.0 / (2 * wy ** 2.0)))) - data)
-
-        p, _ = scipy.optimize.leastsq(err, [data.max(), 0, 0, 1, 1], ftol=1e-3)
-        fx, fy = 2.355 * p[3] * pixelsize, 2.355 * p[4] * pixelsize
-        ok[i] = not (fx > 200e-9 or fx < 40e-9 or fy > 200e-9 or fy < 40e-9)
-    return ok
-
-
-def _windows(guess, sted: np.ndarray) -> np.ndarray:
-    padded = np.pad(np.asarray(sted), 3, constant_values=0)
-    return np.stack([padded[r:r + 7, c:c + 7] for r, c in guess]) if len(guess) else np.zeros((0, 7, 7), dtype=padded.dtype)
-
-
-def validate_positions(guess, sted: np.ndarray, pixelsize=PIXELSIZE):
-    """``rewards/utils.validate_positions``: keeps the candidates whose fitted Gaussian has 40 nm <= FWHM <= 200 nm
-    in both directions."""
-    guess = np.asarray(guess, dtype=np.int64).reshape(-1, 2)
-    return guess[_fit_windows(_windows(guess, sted), pixelsize)]
-
-
-_POOL = None
-
-
-def _pool(workers):
-    """Optional worker processes for the per-candidate MINPACK fits (``STED_B200_FIT_WORKERS=n``).  Forked like
-    torch's DataLoader workers: they only run numpy/scipy and never touch CUDA."""
-    global _POOL
-    if _POOL is None:
-        import atexit
-        import multiprocessing as mp
-        from concurrent.futures import ProcessPoolExecutor
-        _POOL = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("fork"))
-        atexit.register(_POOL.shutdown, wait=False, cancel_futures=True)
-    return _POOL
-
-
-def validate_positions_batch(guesses, images, pixelsize=PIXELSIZE):
-    """``validate_positions`` for many images at once (serial by default; see ``_pool``)."""
-    wins = [_windows(g, im) for g, im in zip(guesses, images)]
-    workers = int(os.environ.get("STED_B200_FIT_WORKERS", "0"))
-    if workers <= 1 or sum(len(w) for w in wins) < 8 * workers:
-        oks = [_fit_windows(w, pixelsize) for w in wins]
-    else:
-        flat = np.concatenate(wins)
-        parts = np.array_split(flat, min(len(flat), 2 * workers))
-        ok = np.concatenate(list(_pool(workers).map(_fit_windows, parts, [pixelsize] * len(parts))))
-        oks, at = [], 0
-        for w in wins:
-            oks.append(ok[at:at + len(w)])
-            at += len(w)
-    return [np.asarray(g, dtype=np.int64).reshape(-1, 2)[o] for g, o in zip(guesses, oks)]
-
-
-def detect_nanodomains(sted: np.ndarray, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
-    """Single image, host side (``NumberNanodomains`` detector end to end)."""
-    sted = np.asarray(sted)
-    return validate_positions(_candidate_peaks_host(sted, threshold), sted, pixelsize)
-
-
-def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, host_fit=False) -> np.ndarray:
-    """F1 of B images: candidates and Gaussian-fit validation on the GPU, Hungarian matching on the host.
-    ``host_fit=True`` validates with scipy's MINPACK instead (the reference's own solver; slower)."""
-    if host_fit:
-        cands = nanodomain_candidates(sted)
-        imgs = np.rint(sted.cpu().numpy()).astype(np.int64)
-        valid = validate_positions_batch(cands, imgs, pixelsize)
-    else:
-        valid = detect_nanodomains_batch(sted, pixelsize)
+def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
+    """F1 of B images: candidates and Gaussian-fit validation on the GPU, Hungarian matching of the few surviving
+    coordinates on the host."""
+    valid = detect_nanodomains_batch(sted, pixelsize)
     return np.array([f1_from_counts(*match_counts(truths[b], valid[b], threshold)) for b in range(len(valid))])
 
 
@@ -340,8 +225,8 @@ def f1_from_counts(tp, fp, fn):
     return 2 * prec * rec / (prec + rec + 1e-6)
 
 
-def nanodomain_f1(sted: np.ndarray, truth_coords, pixelsize=PIXELSIZE, threshold=2):
-    return f1_from_counts(*match_counts(truth_coords, detect_nanodomains(sted, pixelsize, threshold), threshold))
+def nanodomain_f1(sted, truth_coords, pixelsize=PIXELSIZE, threshold=2):
+    return f1_from_counts(*match_counts(truth_coords, detect_nanodomains(sted, pixelsize), threshold))
 
 
 # ------------------------------------------------------------------------------------------------

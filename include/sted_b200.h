@@ -193,8 +193,9 @@ int sted_foreground_objectives(const float* conf1_dev, const float* sted_dev, co
  *   k0, gamma   : numpy.quantile's lower order-statistic index and interpolation weight for q = 0.99, N = H*W
  *   scratch_dev : float64 [2][B][H][W]
  *   peaks_dev   : int32 [B][256][2] (row, col) in skimage's order; npeaks_dev: int32 [B]
- *   flags_dev   : int32 [B] bit 0/1/3: capacity exceeded, bit 2: a flat component needs skimage's
- *                 isolated-pixel rule (handled by the caller) */
+ *   flags_dev   : int32 [B] non-zero = a capacity of the kernel was exceeded (bit 0: more than 4096 mask pixels,
+ *                 bit 1: more than 64 maxima in one component, bit 3: more than 256 peaks); the output is then
+ *                 incomplete and the caller must treat it as an error */
 int sted_nanodomain_candidates(const float* sted_dev, int B, int H, int W, const double weights[3],
                                int64_t k0, double gamma, double* scratch_dev, int32_t* peaks_dev,
                                int32_t* npeaks_dev, int32_t* flags_dev, void* stream);

@@ -346,3 +346,48 @@ def test_sequence_env_carries_bleaching_and_terminates_on_empty_datamap():
     for t in range(10):
         (img, v), r, d, tr, info = env.step(np.array([0.1, 10e-6, 20e-6], dtype=np.float32))
         assert d == (t == 9) and tr is False and info["bleached"].shape == (64, 64)
+
+
+def test_detection_and_f1_match_oracle():
+    _gpu()
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[:64, :64]
+    for trial in range(4):
+        img = rng.poisson(0.3, (64, 64)).astype(np.int64)
+        truth = rng.integers(6, 58, (6, 2))
+        for (y, x) in truth:
+            img += rng.poisson(90 * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * 1.8 ** 2)))
+        a = rewards.detect_nanodomains(img)
+        b = ro.detect_nanodomains(img)
+        assert np.array_equal(a, b)
+        assert rewards.match_counts(truth, a) == ro.match_counts(truth, b)
+        assert rewards.nanodomain_f1(img, truth) == ro.nanodomain_f1(img, truth)
+
+
+def test_flat_components_follow_skimage_isolated_pixel_rule():
+    """Constant plateaus make whole components 'all maxima'; skimage then keeps only the pixels a binary opening
+    removes (mask xor opening).  Saturated blocks, bars and crosses, against the oracle (host restatement of skimage)."""
+    _gpu()
+    imgs = []
+    base_img = np.zeros((64, 64), dtype=np.int64)
+    a = base_img.copy(); a[10:16, 10:17] = 1000; a[40:42, 20:40] = 1000            # block + 2-pixel-thick bar
+    b = base_img.copy(); b[30, 10:30] = 500; b[20:41, 20] = 500                    # thin cross
+    c = base_img.copy(); c[5:9, 5:9] = 70; c[50:54, 50:60] = 70; c[20:24, 30:33] = 70
+    d = np.full((64, 64), 7, dtype=np.int64)                                       # constant image: no candidates
+    imgs = [a, b, c, d]
+    got = rewards.nanodomain_candidates(torch.from_numpy(np.stack(imgs)).float().cuda())
+    n = 0
+    for g, img in zip(got, imgs):
+        ref = ro.candidate_peaks(img).reshape(-1, 2)
+        assert np.array_equal(g, ref), (g, ref)
+        n += len(ref)
+    assert n > 0
+
+
+def test_detection_capacity_overflow_is_an_error_not_a_fallback():
+    _gpu()
+    from gym_sted_b200 import _lib
+    rng = np.random.default_rng(0)
+    big = rng.poisson(5.0, (1, 700, 700)).astype(np.float32)        # 1 % of 490 000 pixels > 4096 mask pixels
+    with pytest.raises(_lib.StedError):
+        rewards.nanodomain_candidates(torch.from_numpy(big).cuda())

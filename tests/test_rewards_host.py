@@ -8,21 +8,6 @@ from oracle import rewards_oracle as ro
 from tests import helpers
 
 
-def test_detection_and_f1_match_oracle():
-    rng = np.random.default_rng(1)
-    yy, xx = np.mgrid[:64, :64]
-    for trial in range(4):
-        img = rng.poisson(0.3, (64, 64)).astype(np.int64)
-        truth = rng.integers(6, 58, (6, 2))
-        for (y, x) in truth:
-            img += rng.poisson(90 * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * 1.8 ** 2)))
-        a = rewards.detect_nanodomains(img)
-        b = ro.detect_nanodomains(img)
-        assert np.array_equal(a, b)
-        assert rewards.match_counts(truth, a) == ro.match_counts(truth, b)
-        assert rewards.nanodomain_f1(img, truth) == ro.nanodomain_f1(img, truth)
-
-
 def test_prefnet_known_answer():
     """SURVEY App. B probe: model 2021-07-12 scores mo_objs = [80, 0.2, 0.9] at 0.9572."""
     art = rewards.PreferenceArticulator()
@@ -34,7 +19,9 @@ def test_prefnet_known_answer():
 def test_registry_and_spaces_without_gpu():
     from gym_sted_b200 import envs
     assert set(envs.REGISTRY) == {"ContextualMOSTED-easy-v0", "ContextualMOSTED-easy-hslb-v0", "ContextualMOSTED-hard-v0",
-                                  "PreferenceCountRateMOSTED-hard-v0"}
+                                  "PreferenceCountRateMOSTED-hard-v0", "SequenceMOSTED-easy-v0", "SequenceMOSTED-mid-v0",
+                                  "SequenceMOSTED-hard-v0", "SequenceMOSTED-easy-hslb-v0", "SequenceMOSTED-easy-hshb-v0",
+                                  "SequenceMOSTED-easy-lslb-v0", "SequenceMOSTED-easy-lshb-v0"}
     for key, entry in envs.REGISTRY.items():
         assert entry["max_episode_steps"] == (30 if key.startswith("Preference") else 10)
         assert entry["kwargs"]["actions"] == ["p_sted", "p_ex", "pdt"]
