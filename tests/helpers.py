@@ -5,7 +5,6 @@ import os
 import numpy as np
 
 from gym_sted_b200 import base, defaults
-from oracle import pysted_oracle as po
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PX = defaults.PIXELSIZE
@@ -23,11 +22,13 @@ def oracle_psf_cache():
     if os.path.exists(path):
         z = np.load(path)
         return z["i_ex"], z["i_sted"], z["psf_det"]
+    from oracle import pysted_oracle as po        # lazy: bench.py's GPU arm imports this module for its builders only
     m = po.default_microscope(defaults.FLUO, _det(), defaults.LASER_EX, defaults.LASER_STED, defaults.OBJECTIVE)
     return m.cache(PX)
 
 
 def oracle_microscope(fluo=None, noise=False, background=0.0):
+    from oracle import pysted_oracle as po
     m = po.default_microscope(fluo or defaults.FLUO, _det(noise, background), defaults.LASER_EX, defaults.LASER_STED,
                               defaults.OBJECTIVE)
     m._cache[int(round(PX * 1e9))] = oracle_psf_cache()
