@@ -367,6 +367,56 @@ class SyntheticDatamapGenerator:
             img = np.flip(img, axis=1)
         return np.ascontiguousarray(img)
 
+    def batch(self, groups, device) -> torch.Tensor:
+        """One structure map per entry of ``groups`` as a (B,H,W) float32 device tensor: the same procedural model as
+        ``__call__`` with the random parameters drawn on the host (a few numbers per map) and the images rendered on
+        the GPU."""
+        H, W = self.shape
+        B = len(groups)
+        rng = self.rng
+        fil = np.array([g in ("actin", "tubulin", "lifeact") for g in groups])
+        width = np.array([{"actin": 1.2, "tubulin": 1.0, "lifeact": 1.6}.get(g, 1.0) for g in groups])
+        NF, NC = 7, 24
+        n_obj = np.where(fil, rng.integers(3, 8, B), rng.integers(8, 25, B))
+        th = rng.uniform(0, np.pi, (B, NF))
+        off = rng.uniform(0.1, 0.9, (B, NF)) * (H * np.abs(np.sin(th)) + W * np.abs(np.cos(th)))
+        cy, cx = rng.uniform(4, H - 4, (B, NC)), rng.uniform(4, W - 4, (B, NC))
+        sig = rng.uniform(1.0, 2.5, (B, NC))
+        scale = rng.normal(self.molecules, self.molecules_scale * self.molecules, B)
+        bad = (scale < 1) | (scale > self.molecules)
+        while bad.any():
+            scale[bad] = rng.normal(self.molecules, self.molecules_scale * self.molecules, int(bad.sum()))
+            bad = (scale < 1) | (scale > self.molecules)
+        rot = np.where(rng.random(B) < 0.5, rng.integers(1, 4, B), 0)
+        flip0, flip1 = rng.random(B) < 0.5, rng.random(B) < 0.5
+
+        def dev(a, dtype=torch.float32):
+            return torch.as_tensor(np.asarray(a), device=device).to(dtype)
+
+        yy = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
+        xx = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
+        img = torch.zeros((B, H, W), device=device)
+        n_t, fil_t, width_t = dev(n_obj)[:, None, None], dev(fil, torch.bool)[:, None, None], dev(width)[:, None, None]
+        th_t, off_t, cy_t, cx_t, sig_t = dev(th), dev(off), dev(cy), dev(cx), dev(sig)
+        for j in range(NC):
+            blob = torch.exp(-0.5 * ((yy - cy_t[:, j, None, None]) ** 2 + (xx - cx_t[:, j, None, None]) ** 2)
+                             / sig_t[:, j, None, None] ** 2)
+            if j < NF:
+                c, sn = torch.cos(th_t[:, j, None, None]), torch.sin(th_t[:, j, None, None])
+                d = torch.abs(xx * c + yy * sn - off_t[:, j, None, None] + 3 * torch.sin(0.08 * (yy * c - xx * sn)))
+                blob = torch.where(fil_t, torch.exp(-0.5 * (d / width_t) ** 2), blob)
+            img = torch.where(j < n_t, torch.maximum(img, blob), img)
+        img = torch.where(img < 0.5, torch.zeros_like(img), img)
+        img = torch.floor(img * dev(np.floor(scale))[:, None, None])
+        if H == W:
+            rot_t = dev(rot, torch.int64)[:, None, None]
+            turned = [torch.rot90(img, k, dims=(1, 2)) for k in (1, 2, 3)]
+            for k in (1, 2, 3):
+                img = torch.where(rot_t == k, turned[k - 1], img)
+        img = torch.where(dev(flip0, torch.bool)[:, None, None], torch.flip(img, dims=(1,)), img)
+        img = torch.where(dev(flip1, torch.bool)[:, None, None], torch.flip(img, dims=(2,)), img)
+        return img.contiguous()
+
 
 FACTORS = {"synthetic": 1.0, "clusters": 2.25, "camkii": 2.25, "psd95": 2.25, "PSD95-Bassoon": 2.25, "actin": 3.0,
            "tubulin": 3.75, "lifeact": 3.75}          # gym_sted/utils.py:447-456
@@ -418,8 +468,8 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
 
     def _new_datamaps(self):
         """``_update_datamap`` (preference_sted_env.py:173-203) with the per-env count-rate loop."""
-        frames = np.stack([self.datamap_generator(g) for g in self.groups])
-        self.bm.set_datamaps(torch.from_numpy(frames), max_molecules=int(frames.sum()))
+        frames = self.datamap_generator.batch(self.groups, self.device)
+        self.bm.set_datamaps(frames, max_molecules=self.B * self.H * self.W * self.datamap_generator.molecules)
         pdt = defaults.PDT
         if self.conf_p_ex is None:
             p_ex = np.full(self.B, defaults.P_EX)

@@ -56,3 +56,20 @@ def test_synthetic_synapse_generator():
     big, coords = synapse.generate_batch(2, 256, 256, seed=1)
     assert big.shape == (2, 256, 256) and 0.05 < (big > 0).mean() < 0.3
     assert np.array_equal(synapse.generate_batch(2, 256, 256, seed=1)[0], big)
+
+
+def test_batched_structure_maps_follow_the_single_map_model():
+    """``SyntheticDatamapGenerator.batch`` (device rendering; here on the CPU device) draws from the same procedural
+    model as ``__call__``: integer molecule counts in [0, 40], empty below the 0.5 structure threshold, filament
+    groups cover more pixels than cluster groups."""
+    from gym_sted_b200 import envs
+    gen = envs.SyntheticDatamapGenerator((96, 96), seed=4)
+    groups = [gen.GROUPS[i % 6] for i in range(48)]
+    maps = gen.batch(groups, "cpu").numpy()
+    assert maps.shape == (48, 96, 96) and np.array_equal(maps, np.floor(maps)) and maps.min() == 0 and 20 <= maps.max() <= 40
+    single = np.stack([gen(g) for g in groups])
+    for kind in (("actin", "tubulin", "lifeact"), ("psd95", "camkii", "PSD95-Bassoon")):
+        sel = np.array([g in kind for g in groups])
+        cover_b, cover_s = (maps[sel] > 0).mean(), (single[sel] > 0).mean()
+        assert 0.5 < cover_b / cover_s < 2.0, (kind, cover_b, cover_s)
+        assert abs(maps[sel][maps[sel] > 0].mean() - single[sel][single[sel] > 0].mean()) < 3
