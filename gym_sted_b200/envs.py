@@ -224,11 +224,12 @@ class VectorContextualMOSTED:
         sted, _ = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True)
         conf2, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)
         bleached = bm.datamaps_roi().clone()
+        pending = rewards.detect_nanodomains_launch(sted) if self.compute_f1 else None     # side stream: overlaps the rest
         fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
         res = rewards.resolution(sted)
         mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)      # (B,3)
         if self.compute_f1:
-            f1 = rewards.nanodomain_f1_batch(sted, [s.nanodomains_coords for s in self.synapses])
+            f1 = rewards.nanodomain_f1_batch(sted, [s.nanodomains_coords for s in self.synapses], handle=pending)
         else:
             f1 = np.zeros(self.B)
         reward = f1 * self.scale_nanodomain_reward

@@ -179,14 +179,36 @@ def gaussfit_validate(sted: torch.Tensor, peaks: torch.Tensor, npeaks: torch.Ten
     return (valid, params) if want_params else valid
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def detect_nanodomains_launch(sted: torch.Tensor, pixelsize=PIXELSIZE):
+    """Enqueue candidates + Gaussian-fit validation of B device images on a side stream and return a handle for
+    ``detect_nanodomains_collect``; the fits (few warps, long latency) then overlap whatever the caller runs next."""
+    dev = sted.device
+    side = _SIDE_STREAMS.setdefault(str(dev), torch.cuda.Stream(dev))
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        sted32, peaks, npk, flags = _candidates_device(sted)
+        valid = gaussfit_validate(sted32, peaks, npk, pixelsize)
+        done = torch.cuda.Event()
+        done.record(side)
+    return sted, sted32, peaks, npk, flags, valid, done
+
+
+def detect_nanodomains_collect(handle):
+    """Device->host read of the surviving coordinates of a ``detect_nanodomains_launch`` handle."""
+    _, sted32, peaks, npk, flags, valid, done = handle
+    done.synchronize()
+    peaks, npk, flags, valid = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy(), valid.cpu().numpy().astype(bool)
+    _check_capacity(flags)
+    return [peaks[b, :npk[b]][valid[b, :npk[b]]].astype(np.int64) for b in range(sted32.shape[0])]
+
+
 def detect_nanodomains_batch(sted: torch.Tensor, pixelsize=PIXELSIZE):
     """``NumberNanodomains`` detector for B device images: candidates and Gaussian-fit validation on the GPU, one
     device->host read of the surviving coordinates."""
-    sted, peaks, npk, flags = _candidates_device(sted)
-    valid = gaussfit_validate(sted, peaks, npk, pixelsize)
-    peaks, npk, flags, valid = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy(), valid.cpu().numpy().astype(bool)
-    _check_capacity(flags)
-    return [peaks[b, :npk[b]][valid[b, :npk[b]]].astype(np.int64) for b in range(sted.shape[0])]
+    return detect_nanodomains_collect(detect_nanodomains_launch(sted, pixelsize))
 
 
 def detect_nanodomains(sted, pixelsize=PIXELSIZE) -> np.ndarray:
@@ -195,10 +217,10 @@ def detect_nanodomains(sted, pixelsize=PIXELSIZE) -> np.ndarray:
     return detect_nanodomains_batch(t.to("cuda", torch.float32)[None], pixelsize)[0]
 
 
-def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2) -> np.ndarray:
-    """F1 of B images: candidates and Gaussian-fit validation on the GPU, Hungarian matching of the few surviving
-    coordinates on the host."""
-    valid = detect_nanodomains_batch(sted, pixelsize)
+def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, handle=None) -> np.ndarray:
+    """F1 of B images: candidates and Gaussian-fit validation on the GPU (already enqueued when ``handle`` is given),
+    Hungarian matching of the few surviving coordinates on the host."""
+    valid = detect_nanodomains_collect(handle if handle is not None else detect_nanodomains_launch(sted, pixelsize))
     return np.array([f1_from_counts(*match_counts(truths[b], valid[b], threshold)) for b in range(len(valid))])
 
 
