@@ -51,6 +51,18 @@ class ClockSampler:
         self.gpu, self.proc, self.lines = gpu_index, None, []
 
     def start(self):
+        # NVML in-process (5 ms period) when nvidia_ml_py is importable, else the nvidia-smi loop of the profiling recipe
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu))
+            self.samples, self.stop_flag = [], threading.Event()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "25"],
@@ -60,11 +72,34 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _stop_nvml(self):
+        nv, _ = self.nvml
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(n for n, b in bits.items() if any(s[2] & b for s in self.samples))
+        sm = [s[0] for s in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(s[1] for s in self.samples)) if sm else None,
+                "samples": len(sm), "reasons": reasons, "source": "nvml"}
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            return self._stop_nvml()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
