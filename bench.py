@@ -230,6 +230,9 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    # several ranks streaming host buffers: keep each rank (and the pinned memory it allocates) on its GPU's NUMA node
+    from gym_sted_b200 import dist as sted_dist
+    numa_bound = sted_dist.bind_to_gpu_numa(local_rank) if world > 1 else False
     H = W = args.size
     B = args.envs
     env_base = rank * B
@@ -431,7 +434,7 @@ def run_ours(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, B, world), "env_steps_per_s": value / ACQ_PER_STEP,
             "e2e": {"value": e2e_value, "unit": "acquisitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "sted_acquire_host (C ABI, pinned host buffers)"},
+                    "steps": e2e_steps, "api": "sted_acquire_host (C ABI, pinned host buffers)", "numa_bound": numa_bound},
             "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "roofline_scan": roofline_scan,
             "cpu_baseline": cpu,
         }

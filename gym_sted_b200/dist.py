@@ -19,6 +19,26 @@ def shard_range(n_envs: int, rank: int, world: int):
     return lo, min(lo + per, n_envs)
 
 
+def bind_to_gpu_numa(gpu_index: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to GPU ``gpu_index`` (its NUMA node), so pinned host
+    buffers allocated afterwards and the H2D/D2H copies of the host-buffer API stay on the socket the GPU hangs off.
+    Matters when 8 ranks stream host buffers at once; returns False (and changes nothing) when NVML is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def init_from_env(backend=None, device=None):
     """``torchrun`` rendezvous (RANK / WORLD_SIZE / MASTER_* from the environment)."""
     if not dist.is_initialized():
