@@ -2,8 +2,8 @@
 //
 // Path rebuilt here: pysted.base.Microscope.get_effective / fluo.get_k_bleach
 // (a2, a3) -> make_effective_kernel; Microscope.get_signal_and_bleach (a5) ->
-// gather_kernel (bleach=False) and sweep_kernel (bleach=True); Detector.get_signal is fused into
-// both epilogues.  Reference call sites: gym_sted/envs/mosted_env.py:184,222,227,232 and
+// gather_kernel (bleach=False) and presample_kernel + bucket_scan_kernel + sweep_kernel (bleach=True);
+// Detector.get_signal -> detect_kernel.  Reference call sites: gym_sted/envs/mosted_env.py:184,222,227,232 and
 // gym_sted/utils.py:616-631,646-657.  See DESIGN.md for the derivations.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build).
@@ -30,7 +30,7 @@ constexpr double kPlanck = 6.62607015e-34;
 constexpr double kLight = 299792458.0;
 
 // ------------------------------------------------------------------------------------------
-// K1: effective PSF + bleaching tables, one CTA per environment, one thread per tap row.
+// K1: effective PSF + bleaching tables, one CTA per environment: taps in parallel, suffix sums by one thread per tap row.
 // All physics in float64; tables are rounded to float32 once.
 //   E[u][v]  = sigma_abs*I_ex*qy * eta(I_sted) * psf_det            (Microscope.get_effective)
 //   k_b[u][v]= sigma_abs*phi_ex * tau_sted * (k0*I + k1*I^b),  I = instantaneous STED W/m^2
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     };
     int yy = 0;
     for (; yy < G_RT - 1 && yy < K; ++yy) band_row(yy, true);       // ramp-up
-    for (; yy < K; ++yy) band_row(yy, false);                       // steady: all 8 rows active
+    for (; yy < K; ++yy) band_row(yy, false);                       // steady: all G_RT output rows active
     for (; yy < G_RT + K - 1; ++yy) band_row(yy, true);             // ramp-down
 
     // ---- epilogue: stage the tile in shared memory (the datamap tile is dead), then run the detector
