@@ -425,9 +425,12 @@ def run_ours(args, rank, local_rank, world):
             cores = os.cpu_count() or 1
             n_envs = args.cpu_envs or max(cores, 8)
             tcpu, a = cpu_env_steps(n_envs, H, W, cores)
+            t1, a1 = cpu_env_steps(1, H, W, 1)                       # the same loop on one core
             cpu = {"value": a / tcpu, "unit": "acquisitions/s", "cores": cores, "kind": "port",
+                   "single_core_value": a1 / t1,
                    "sample": f"{n_envs} envs x 4 acquisitions of the same workload ({H}x{W}, K=59) on {cores} host "
-                             f"threads, {tcpu:.1f} s; C restatement of pySTED's dwell loop (oracle/raster_oracle.c), not pySTED"}
+                             f"threads, {tcpu:.1f} s (+ 1 env on 1 thread, {t1:.1f} s); C restatement of pySTED's dwell "
+                             f"loop (oracle/raster_oracle.c), not pySTED"}
         line = {
             "metric": "STED acquisitions/sec", "value": value, "unit": "acquisitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
