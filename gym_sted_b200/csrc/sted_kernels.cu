@@ -148,11 +148,18 @@ __device__ __forceinline__ float detect(const AcqParams& P, float I, float gain,
 #endif
 constexpr int G_TH = G_TILE_H, G_TW = 64, G_RT = G_ROWS_PER_THREAD, G_THREADS = (G_TILE_H / G_ROWS_PER_THREAD) * 16,
               kGatherUnroll = G_UNROLL;
-constexpr int G_MINB = G_TILE_H == 64 ? 3 : 2;
+constexpr int G_MINB = 2;       // tile (60.5 KB) + row-interleaved PSF (28.8 KB) per CTA
 
 #ifndef GATHER_TMA
 #define GATHER_TMA 1   // 0: stage the tile with coalesced float4 loads instead of TMA (A/B timing only)
 #endif
+
+// packed FP32 pairs for FFMA2 (fma.rn.f32x2, sm_100): lo = first element.  A pair built from one scalar becomes the
+// instruction's scalar-broadcast operand (R.F32), so pack2(w, w) costs nothing.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -173,33 +180,30 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     const int rows = G_TH + K - 1;
     extern __shared__ __align__(128) float smem[];
     float* sD = smem;
-    float* sE = smem + rows * PITCH;
+    // PSF rows interleaved in pairs for FFMA2: sE2[u][v] = (E[u][v], E[u-1][v]) for u = 0..K, E[-1] = E[K] = 0
+    float2* sE2 = reinterpret_cast<float2*>(smem + rows * PITCH);
     __shared__ __align__(8) unsigned long long mbar;
 
     const int b = blockIdx.z;
     const int tr0 = blockIdx.y * G_TH, tc0 = blockIdx.x * G_TW;
     const int tid = threadIdx.x;
+    const float* gE = P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP;
 
 #if GATHER_TMA
-    // ---- stage tile + PSF with TMA: one 3-D tensor box (zero filled outside the padded map) and one bulk copy,
-    // both completing on the same mbarrier
+    // ---- stage the tile with TMA: one 3-D tensor box (zero filled outside the padded map) completing on an mbarrier
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t bytes_d = (uint32_t)(rows * PITCH * sizeof(float)), bytes_e = (uint32_t)(K * KP * sizeof(float));
-        const float* gE = P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(bytes_d + bytes_e) : "memory");
+        const uint32_t bytes_d = (uint32_t)(rows * PITCH * sizeof(float));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(bytes_d) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                      :: "r"(smem_u32(sD)), "l"(&tmap), "r"(tc0), "r"(tr0), "r"(b), "r"(smem_u32(&mbar)) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"(smem_u32(sE)), "l"(gE), "r"(bytes_e), "r"(smem_u32(&mbar)) : "memory");
     }
-    mbar_wait(smem_u32(&mbar), 0);
 #else
-    // ---- stage tile + PSF (float4, zero fill outside the padded map)
+    // ---- stage the tile (float4, zero fill outside the padded map)
     {
         const float* src = P.din + (size_t)b * P.Hp * P.Wpitch;
         const int q = PITCH / 4;
@@ -210,17 +214,31 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
             if (y < P.Hp && x < P.Wpitch) val = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * P.Wpitch + x));
             *reinterpret_cast<float4*>(sD + ry * PITCH + cx) = val;
         }
-        const float4* e4 = reinterpret_cast<const float4*>(P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP);
-        for (int i = tid; i < K * KP / 4; i += G_THREADS) reinterpret_cast<float4*>(sE)[i] = __ldg(e4 + i);
+    }
+#endif
+    // the PSF (14 KB, L2 resident) goes through registers into the interleaved layout while the tile is in flight
+    for (int i = tid; i < (K + 1) * KP; i += G_THREADS) {
+        const int u = i / KP, v = i - u * KP;
+        sE2[i] = make_float2(u < K ? __ldg(gE + u * KP + v) : 0.f, u > 0 ? __ldg(gE + (u - 1) * KP + v) : 0.f);
     }
     __syncthreads();
+#if GATHER_TMA
+    mbar_wait(smem_u32(&mbar), 0);
 #endif
 
     const int lane16 = tid & 15, rg = tid >> 4;
     const int r0 = rg * G_RT, c0 = lane16 * 4;
-    float acc[G_RT][4];
+    // Accumulators are packed pairs of two output ROWS (2p, 2p+1) of one column, and the inner loop issues FFMA2
+    // (fma.rn.f32x2): the FP32 pipe delivers the same flops as with scalar FFMA but one instruction covers two, which
+    // takes the kernel from issue bound (85 % of the issue slots for 77 % of the FMA pipe) to FMA-pipe bound.  Both
+    // rows read the same datamap value (the instruction's scalar-broadcast operand) against the PSF taps of rows u and
+    // u-1 (one 64-bit shared-memory word of the interleaved table).  Each half performs exactly the fused
+    // multiply-adds of the scalar form, in the same order: results are bit-identical to it.
+    static_assert(G_RT % 2 == 0, "row pairs");
+    constexpr int NP = G_RT / 2;
+    u64 acc[NP][4];
 #pragma unroll
-    for (int i = 0; i < G_RT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    for (int p = 0; p < NP; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0ull; }
 
     const int nchunk = KP / 4;
     auto band_row = [&](const int yy, const bool check) {
@@ -229,27 +247,30 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
 #pragma unroll kGatherUnroll
         for (int vc = 0; vc < nchunk; ++vc) {
             const float4 wb = *reinterpret_cast<const float4*>(drow + 4 * (vc + 1));
+            const u64 w0 = pack2(wa.x, wa.x), w1 = pack2(wa.y, wa.y), w2 = pack2(wa.z, wa.z), w3 = pack2(wa.w, wa.w),
+                      w4 = pack2(wb.x, wb.x), w5 = pack2(wb.y, wb.y), w6 = pack2(wb.z, wb.z);
 #pragma unroll
-            for (int i = 0; i < G_RT; ++i) {
-                const int u = yy - i;
-                if (!check || (u >= 0 && u < K)) {
-                    const float4 e = *reinterpret_cast<const float4*>(sE + u * KP + 4 * vc);
-                    acc[i][0] = fmaf(e.x, wa.x, acc[i][0]); acc[i][0] = fmaf(e.y, wa.y, acc[i][0]);
-                    acc[i][0] = fmaf(e.z, wa.z, acc[i][0]); acc[i][0] = fmaf(e.w, wa.w, acc[i][0]);
-                    acc[i][1] = fmaf(e.x, wa.y, acc[i][1]); acc[i][1] = fmaf(e.y, wa.z, acc[i][1]);
-                    acc[i][1] = fmaf(e.z, wa.w, acc[i][1]); acc[i][1] = fmaf(e.w, wb.x, acc[i][1]);
-                    acc[i][2] = fmaf(e.x, wa.z, acc[i][2]); acc[i][2] = fmaf(e.y, wa.w, acc[i][2]);
-                    acc[i][2] = fmaf(e.z, wb.x, acc[i][2]); acc[i][2] = fmaf(e.w, wb.y, acc[i][2]);
-                    acc[i][3] = fmaf(e.x, wa.w, acc[i][3]); acc[i][3] = fmaf(e.y, wb.x, acc[i][3]);
-                    acc[i][3] = fmaf(e.z, wb.y, acc[i][3]); acc[i][3] = fmaf(e.w, wb.z, acc[i][3]);
+            for (int p = 0; p < NP; ++p) {
+                const int u = yy - 2 * p;                   // tap row of output row 2p; row 2p+1 uses u-1
+                if (!check || (u >= 0 && u <= K)) {
+                    const ulonglong2* e2 = reinterpret_cast<const ulonglong2*>(sE2 + u * KP + 4 * vc);
+                    const ulonglong2 ea = e2[0], eb = e2[1];              // taps v, v+1 | v+2, v+3
+                    acc[p][0] = fma2(ea.x, w0, acc[p][0]); acc[p][0] = fma2(ea.y, w1, acc[p][0]);
+                    acc[p][0] = fma2(eb.x, w2, acc[p][0]); acc[p][0] = fma2(eb.y, w3, acc[p][0]);
+                    acc[p][1] = fma2(ea.x, w1, acc[p][1]); acc[p][1] = fma2(ea.y, w2, acc[p][1]);
+                    acc[p][1] = fma2(eb.x, w3, acc[p][1]); acc[p][1] = fma2(eb.y, w4, acc[p][1]);
+                    acc[p][2] = fma2(ea.x, w2, acc[p][2]); acc[p][2] = fma2(ea.y, w3, acc[p][2]);
+                    acc[p][2] = fma2(eb.x, w4, acc[p][2]); acc[p][2] = fma2(eb.y, w5, acc[p][2]);
+                    acc[p][3] = fma2(ea.x, w3, acc[p][3]); acc[p][3] = fma2(ea.y, w4, acc[p][3]);
+                    acc[p][3] = fma2(eb.x, w5, acc[p][3]); acc[p][3] = fma2(eb.y, w6, acc[p][3]);
                 }
             }
             wa = wb;
         }
     };
     int yy = 0;
-    for (; yy < G_RT - 1 && yy < K; ++yy) band_row(yy, true);       // ramp-up
-    for (; yy < K; ++yy) band_row(yy, false);                       // steady: all G_RT output rows active
+    for (; yy < 2 * (NP - 1) && yy <= K; ++yy) band_row(yy, true);  // ramp-up
+    for (; yy <= K; ++yy) band_row(yy, false);                      // steady: every row pair has a tap row
     for (; yy < G_RT + K - 1; ++yy) band_row(yy, true);             // ramp-down
 
     // ---- epilogue: stage the tile in shared memory (the datamap tile is dead), then run the detector
@@ -258,8 +279,12 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     __syncthreads();
     float* sOut = sD;
 #pragma unroll
-    for (int i = 0; i < G_RT; ++i)
-        *reinterpret_cast<float4*>(sOut + (r0 + i) * G_TW + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    for (int p = 0; p < NP; ++p) {
+        float4 lo, hi;
+        unpack2(acc[p][0], lo.x, hi.x); unpack2(acc[p][1], lo.y, hi.y); unpack2(acc[p][2], lo.z, hi.z); unpack2(acc[p][3], lo.w, hi.w);
+        *reinterpret_cast<float4*>(sOut + (r0 + 2 * p) * G_TW + c0) = lo;
+        *reinterpret_cast<float4*>(sOut + (r0 + 2 * p + 1) * G_TW + c0) = hi;
+    }
     __syncthreads();
     // detected power goes to `signal`; detect_kernel turns it into photon counts in place
     for (int idx = tid; idx < G_TH * G_TW; idx += G_THREADS) {
@@ -893,7 +918,7 @@ int make_tile_map(const AcqParams& P, CUtensorMap* map) {
 }
 
 int launch_gather(const AcqParams& P, cudaStream_t st) {
-    const size_t smem = ((size_t)(G_TH + P.K - 1) * (G_TW + P.KP) + (size_t)P.K * P.KP) * sizeof(float);
+    const size_t smem = ((size_t)(G_TH + P.K - 1) * (G_TW + P.KP) + 2 * (size_t)(P.K + 1) * P.KP) * sizeof(float);
     dim3 grid((P.W + G_TW - 1) / G_TW, (P.H + G_TH - 1) / G_TH, P.B);
     CUtensorMap map;
     int rc;
