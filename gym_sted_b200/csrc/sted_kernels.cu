@@ -79,6 +79,14 @@ __global__ void __launch_bounds__(256) make_effective_kernel(const double* __res
         sA[t] = kb * dwell;
     }
     __syncthreads();
+    // row-interleaved copy of E for the FFMA2 gather: E2[u][v] = (E[u][v], E[u-1][v]), u = 0..K, zero outside
+    {
+        float2* tE2 = reinterpret_cast<float2*>(tables + ((size_t)b * STED_TABLES + STED_TAB_E2) * K * KP);
+        for (int i = threadIdx.x; i < (K + 1) * KP; i += blockDim.x) {
+            const int uu = i / KP, v = i - uu * KP;
+            tE2[i] = make_float2((uu < K && v < K) ? (float)sE[uu * K + v] : 0.f, (uu > 0 && v < K) ? (float)sE[(uu - 1) * K + v] : 0.f);
+        }
+    }
     const int u = threadIdx.x;
     if (u >= K) return;
     float* tE = tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP + (size_t)u * KP;
@@ -154,6 +162,8 @@ constexpr int G_MINB = 2;       // tile (60.5 KB) + row-interleaved PSF (28.8 KB
 #define GATHER_TMA 1   // 0: stage the tile with coalesced float4 loads instead of TMA (A/B timing only)
 #endif
 
+__device__ unsigned long long g_phase_cycles[8];   // timing experiments only (SWEEP_PROBE==2 / GATHER_PROBE builds)
+
 // packed FP32 pairs for FFMA2 (fma.rn.f32x2, sm_100): lo = first element.  A pair built from one scalar becomes the
 // instruction's scalar-broadcast operand (R.F32), so pack2(w, w) costs nothing.
 typedef unsigned long long u64;
@@ -184,26 +194,33 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     float2* sE2 = reinterpret_cast<float2*>(smem + rows * PITCH);
     __shared__ __align__(8) unsigned long long mbar;
 
+#ifdef GATHER_PROBE
+    const long long t_start = clock64();
+#endif
     const int b = blockIdx.z;
     const int tr0 = blockIdx.y * G_TH, tc0 = blockIdx.x * G_TW;
     const int tid = threadIdx.x;
-    const float* gE = P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP;
+    const float* gE2 = P.tables + ((size_t)b * STED_TABLES + STED_TAB_E2) * K * KP;      // written by make_effective_kernel
 
 #if GATHER_TMA
-    // ---- stage the tile with TMA: one 3-D tensor box (zero filled outside the padded map) completing on an mbarrier
+    // ---- stage tile + PSF with TMA: one 3-D tensor box (zero filled outside the padded map) and one bulk copy,
+    // both completing on the same mbarrier
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t bytes_d = (uint32_t)(rows * PITCH * sizeof(float));
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(bytes_d) : "memory");
+        const uint32_t bytes_d = (uint32_t)(rows * PITCH * sizeof(float)), bytes_e = (uint32_t)((K + 1) * KP * sizeof(float2));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(&mbar)), "r"(bytes_d + bytes_e) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                      :: "r"(smem_u32(sD)), "l"(&tmap), "r"(tc0), "r"(tr0), "r"(b), "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(sE2)), "l"(gE2), "r"(bytes_e), "r"(smem_u32(&mbar)) : "memory");
     }
+    mbar_wait(smem_u32(&mbar), 0);
 #else
-    // ---- stage the tile (float4, zero fill outside the padded map)
+    // ---- stage tile + PSF (float4, zero fill outside the padded map)
     {
         const float* src = P.din + (size_t)b * P.Hp * P.Wpitch;
         const int q = PITCH / 4;
@@ -214,18 +231,15 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
             if (y < P.Hp && x < P.Wpitch) val = __ldg(reinterpret_cast<const float4*>(src + (size_t)y * P.Wpitch + x));
             *reinterpret_cast<float4*>(sD + ry * PITCH + cx) = val;
         }
-    }
-#endif
-    // the PSF (14 KB, L2 resident) goes through registers into the interleaved layout while the tile is in flight
-    for (int i = tid; i < (K + 1) * KP; i += G_THREADS) {
-        const int u = i / KP, v = i - u * KP;
-        sE2[i] = make_float2(u < K ? __ldg(gE + u * KP + v) : 0.f, u > 0 ? __ldg(gE + (u - 1) * KP + v) : 0.f);
+        const float4* e4 = reinterpret_cast<const float4*>(gE2);
+        for (int i = tid; i < (K + 1) * KP / 2; i += G_THREADS) reinterpret_cast<float4*>(sE2)[i] = __ldg(e4 + i);
     }
     __syncthreads();
-#if GATHER_TMA
-    mbar_wait(smem_u32(&mbar), 0);
 #endif
 
+#ifdef GATHER_PROBE
+    const long long t_ready = clock64();
+#endif
     const int lane16 = tid & 15, rg = tid >> 4;
     const int r0 = rg * G_RT, c0 = lane16 * 4;
     // Accumulators are packed pairs of two output ROWS (2p, 2p+1) of one column, and the inner loop issues FFMA2
@@ -273,6 +287,9 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     for (; yy <= K; ++yy) band_row(yy, false);                      // steady: every row pair has a tap row
     for (; yy < G_RT + K - 1; ++yy) band_row(yy, true);             // ramp-down
 
+#ifdef GATHER_PROBE
+    const long long t_main = clock64();
+#endif
     // ---- epilogue: stage the tile in shared memory (the datamap tile is dead), then run the detector
     // in a compact, non-unrolled loop with coalesced stores.  (Unrolling the Poisson sampler over the
     // 32 register accumulators made the kernel instruction-fetch bound: ncu stall_no_instruction.)
@@ -295,6 +312,15 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
         if (P.intensity) P.intensity[o] = I;
         P.signal[o] = I;
     }
+#ifdef GATHER_PROBE
+    if (tid == 0) {
+        const long long t_end = clock64();
+        atomicAdd(&g_phase_cycles[0], (unsigned long long)(t_ready - t_start));
+        atomicAdd(&g_phase_cycles[1], (unsigned long long)(t_main - t_ready));
+        atomicAdd(&g_phase_cycles[2], (unsigned long long)(t_end - t_main));
+        atomicAdd(&g_phase_cycles[3], 1ull);
+    }
+#endif
 }
 
 // Detector.get_signal for every pixel of the batch, in place on `signal` (power -> photon counts).
@@ -404,7 +430,6 @@ constexpr int S_THREADS = 256;
 #ifndef SWEEP_PROBE
 #define SWEEP_PROBE 0   // 2: per-phase cycle counters (timing experiments only)
 #endif
-__device__ unsigned long long g_phase_cycles[8];   // SWEEP_PROBE==2: per-phase cycle sums of sweep_kernel
 
 __host__ __device__ inline int sweep_pitch(int TC, int KP) {
     int p = TC + KP;

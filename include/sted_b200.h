@@ -92,7 +92,9 @@ typedef struct StedDetectorParams {
 #define STED_TAB_ET  1   /* E[u][v]*exp(-sum_{v'>v} A[u][v']): in-row expected-survival weights */
 #define STED_TAB_CH  2   /* suffix hazard CH[u][v] = sum_{v'>=v} A[u][v'], A = k_bleach*pdt    */
 #define STED_TAB_RS  3   /* exp(-CH[u][v]): survival of a whole in-row pass starting at tap v     */
-#define STED_TABLES  4
+#define STED_TAB_E2  4   /* slots 4..7: float32 [K+1][KP][2] = (E[u][v], E[u-1][v]), zero outside: the packed operand
+                          * of the gather kernel's FFMA2 (two output rows per instruction)                      */
+#define STED_TABLES  8
 
 const char* sted_version(void);
 const char* sted_last_error(void);

@@ -64,3 +64,23 @@ def load_demonstrations():
     out["fg_c"] = np.unpackbits(out["fg_c"], axis=-1).astype(bool)
     out["fg_s"] = np.unpackbits(out["fg_s"], axis=-1).astype(bool)
     return out
+
+
+def empty_tables(B, K):
+    """Zeroed (B, STED_TABLES, K, KP) float32 table block as sted_acquire expects it (include/sted_b200.h)."""
+    from gym_sted_b200 import _lib
+    return np.zeros((B, _lib.STED_TABLES, K, _lib.kpitch(K)), dtype=np.float32)
+
+
+def fill_e2(tab):
+    """Derive the row-interleaved copy E2[u][v] = (E[u][v], E[u-1][v]) (slots STED_TAB_E2..) from slot STED_TAB_E,
+    as sted_make_effective does."""
+    from gym_sted_b200 import _lib
+    B, _, K, KP = tab.shape
+    for b in range(B):
+        pad = np.zeros((K + 2, KP), dtype=np.float32)
+        pad[1:K + 1] = tab[b, _lib.STED_TAB_E]
+        e2 = np.stack([pad[1:], pad[:-1]], axis=-1)                    # (K+1, KP, 2)
+        flat = tab[b, _lib.STED_TAB_E2:].reshape(-1)
+        flat[:e2.size] = e2.reshape(-1)
+    return tab

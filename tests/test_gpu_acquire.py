@@ -62,7 +62,7 @@ def test_make_effective_tables_match_oracle(micro, omicro):
     kb = bm.make_effective(p_ex, p_sted, pdt, want_kbleach=True).cpu().numpy()
     tab = bm.tables.cpu().numpy()
     K = bm.K
-    assert tab.shape == (B, 4, K, 60) and np.all(tab[:, :3, :, K:] == 0)
+    assert tab.shape == (B, _lib.STED_TABLES, K, 60) and np.all(tab[:, :3, :, K:] == 0)
     for b, (dt, pe, ps) in enumerate(ACTIONS):
         E = omicro.get_effective(PX, pe, ps)
         kref = omicro.get_k_bleach_map(PX, pe, ps, dt)
@@ -72,6 +72,11 @@ def test_make_effective_tables_match_oracle(micro, omicro):
         np.testing.assert_allclose(tab[b, _lib.STED_TAB_ET, :, :K], ET, rtol=3e-7)
         np.testing.assert_allclose(tab[b, _lib.STED_TAB_CH, :, :K], CH[:, :K], rtol=3e-7)
         np.testing.assert_allclose(tab[b, _lib.STED_TAB_RS, :, :K], np.exp(-CH[:, :K]), rtol=3e-7)
+        # row-interleaved copy for the FFMA2 gather: E2[u][v] = (E[u][v], E[u-1][v]), u = 0..K, zero outside
+        e2 = tab[b, _lib.STED_TAB_E2:].reshape(-1)[:(K + 1) * 60 * 2].reshape(K + 1, 60, 2)
+        e_pad = np.zeros((K + 2, 60), dtype=np.float32)
+        e_pad[1:K + 1] = tab[b, _lib.STED_TAB_E]
+        assert np.array_equal(e2[..., 0], e_pad[1:]) and np.array_equal(e2[..., 1], e_pad[:-1])
 
 
 def test_get_effective_facade(micro, omicro):
@@ -117,8 +122,9 @@ def test_gather_generic_psf_size(micro):
         E = rng.random((B, K, K))
         D = np.zeros((B, Hp, Wpitch), dtype=np.float32)
         D[:, :, :Wp] = rng.integers(0, 50, (B, Hp, Wp))
-        tab = np.zeros((B, 4, K, KP), dtype=np.float32)
+        tab = helpers.empty_tables(B, K)
         tab[:, 0, :, :K] = E
+        helpers.fill_e2(tab)
         d_D, d_tab = torch.from_numpy(D).cuda(), torch.from_numpy(tab).cuda()
         d_pdt = torch.full((B,), 1e-5, dtype=torch.float64, device="cuda")
         d_int = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
@@ -174,13 +180,14 @@ def test_sweep_generic_psf_edge_shapes(micro):
         p = K // 2
         D = np.zeros((B, Hp, Wpitch), dtype=np.float32)
         D[:, p:p + H, p:p + W] = rng.integers(0, 9, (B, H, W)) * (rng.random((B, H, W)) < 0.6)
-        tab = np.zeros((B, 4, K, KP), dtype=np.float32)
+        tab = helpers.empty_tables(B, K)
         tab[:, 3] = 1.0
         Es, As = rng.random((B, K, K)), rng.random((B, K, K)) * 0.3
         for b in range(B):
             ET, CH = rm.tables(Es[b], As[b])
             tab[b, 0, :, :K], tab[b, 1, :, :K] = Es[b], ET
             tab[b, 2, :, :K], tab[b, 3, :, :K] = CH[:, :K], np.exp(-CH[:, :K])
+        helpers.fill_e2(tab)
         d_D, d_tab = torch.from_numpy(D).cuda(), torch.from_numpy(tab).cuda()
         d_out = torch.full_like(d_D, -1.0)
         d_pdt = torch.full((B,), 1e-5, dtype=torch.float64, device="cuda")
