@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("STED_B200_LIB", os.path.join(_HERE, "libsted_b200.so"))
 
-STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH, STED_NO_DETECT = 1, 2, 4, 8
+STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH, STED_NO_DETECT, STED_HOST_U16 = 1, 2, 4, 8, 16
 STED_TAB_E, STED_TAB_ET, STED_TAB_CH, STED_TAB_RS, STED_TAB_E2, STED_TABLES = 0, 1, 2, 3, 4, 8
 STED_MAX_K = 63
 

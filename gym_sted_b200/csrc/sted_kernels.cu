@@ -1036,8 +1036,8 @@ int launch_detect(const AcqParams& P, cudaStream_t st) {
 // growable device workspace for the *_host entry points
 struct Workspace {
     std::mutex mu;
-    void* dev[9] = {nullptr};
-    size_t cap[9] = {0};
+    void* dev[10] = {nullptr};
+    size_t cap[10] = {0};
     int ensure(int slot, size_t bytes) {
         if (cap[slot] >= bytes) return STED_OK;
         if (dev[slot]) cudaFree(dev[slot]);
@@ -1049,7 +1049,14 @@ struct Workspace {
 };
 Workspace g_ws;
 
-__global__ void pad_kernel(const float* __restrict__ roi, float* __restrict__ padded, int B, int H, int W, int p,
+__device__ __forceinline__ float host_to_count(float v) { return v; }
+__device__ __forceinline__ float host_to_count(uint16_t v) { return (float)v; }
+__device__ __forceinline__ void count_to_host(float v, float* o) { *o = v; }
+__device__ __forceinline__ void count_to_host(float v, uint16_t* o) { *o = (uint16_t)fminf(fmaxf(rintf(v), 0.f), 65535.f); }   // saturating
+
+// host-format ROI (float32 or uint16 counts) -> zero-framed float32 map, and back
+template <class T>
+__global__ void pad_kernel(const T* __restrict__ roi, float* __restrict__ padded, int B, int H, int W, int p,
                            int Hp, int Wpitch) {
     const size_t n = (size_t)B * Hp * Wpitch;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -1057,19 +1064,26 @@ __global__ void pad_kernel(const float* __restrict__ roi, float* __restrict__ pa
         const int y = (int)((i / Wpitch) % Hp);
         const int b = (int)(i / ((size_t)Wpitch * Hp));
         const int r = y - p, c = x - p;
-        padded[i] = (r >= 0 && r < H && c >= 0 && c < W) ? roi[((size_t)b * H + r) * W + c] : 0.f;
+        padded[i] = (r >= 0 && r < H && c >= 0 && c < W) ? host_to_count(roi[((size_t)b * H + r) * W + c]) : 0.f;
     }
 }
 
-__global__ void unpad_kernel(const float* __restrict__ padded, float* __restrict__ roi, int B, int H, int W, int p,
+template <class T>
+__global__ void unpad_kernel(const float* __restrict__ padded, T* __restrict__ roi, int B, int H, int W, int p,
                              int Hp, int Wpitch) {
     const size_t n = (size_t)B * H * W;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % W);
         const int r = (int)((i / W) % H);
         const int b = (int)(i / ((size_t)W * H));
-        roi[i] = padded[((size_t)b * Hp + r + p) * Wpitch + c + p];
+        count_to_host(padded[((size_t)b * Hp + r + p) * Wpitch + c + p], roi + i);
     }
+}
+
+// photon counts float32 -> uint16 (saturating) for the STED_HOST_U16 transport
+__global__ void counts_to_u16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        count_to_host(in[i], out + i);
 }
 
 }  // namespace
@@ -1195,10 +1209,10 @@ HostPipe g_pipe;
 
 }  // namespace
 
-extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host, const StedFluoParams* fluo_host,
+extern "C" int sted_acquire_host(void* dmap_host, const double* psf_cache_host, const StedFluoParams* fluo_host,
                                  const double* p_ex_host, const double* p_sted_host, const double* pdt_host, int B, int H,
                                  int W, int K, uint32_t flags, const StedDetectorParams* det, uint64_t seed, uint64_t offset,
-                                 int64_t env_base, float* intensity_host, float* signal_host) {
+                                 int64_t env_base, float* intensity_host, void* signal_host) {
     if (!dmap_host || !psf_cache_host || !fluo_host || !p_ex_host || !p_sted_host || !pdt_host || !signal_host || !det)
         return fail(STED_EINVAL, "null pointer argument");
     if (B <= 0 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B, H, W must be positive");
@@ -1211,9 +1225,15 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
     const int KP = STED_KPITCH(K), Hp = H + K - 1, Wp = W + K - 1, Wpitch = (Wp + 3) & ~3, p = K / 2;
     const size_t px_roi = (size_t)H * W, px_pad = (size_t)Hp * Wpitch;
     const size_t n_roi = (size_t)B * px_roi, n_pad = (size_t)B * px_pad;
-    enum { ROI, PADA, PADB, TAB, CACHE, FLUO, SCAL, OUT, WS };
+    enum { ROI, PADA, PADB, TAB, CACHE, FLUO, SCAL, OUT, WS, SIG16 };
     const bool bleach = (flags & STED_BLEACH) != 0;
     const bool stoch = bleach && (flags & STED_SAMPLE_BLEACH);
+    // STED_HOST_U16: maps and photon counts cross the bus as uint16 (half the bytes); counts must stay integers
+    const bool u16 = (flags & STED_HOST_U16) != 0;
+    if (u16 && ((bleach && !stoch) || !(flags & STED_SAMPLE_PHOTONS)))
+        return fail(STED_EINVAL, "STED_HOST_U16 needs integer outputs: STED_SAMPLE_PHOTONS, and STED_SAMPLE_BLEACH when bleaching");
+    const size_t esz = u16 ? sizeof(uint16_t) : sizeof(float);
+    flags &= ~STED_HOST_U16;
     // chunks: upload of chunk i+1, compute of chunk i and download of chunk i-1 run concurrently
     int nch = B >= 128 ? 8 : (B >= 32 ? 4 : (B >= 8 ? 2 : 1));      // measured on B200, 256 envs x 256^2: 2 -> 3.9, 4 -> 3.4, 8..16 -> 3.2 ms/call
     if (const char* e = getenv("STED_B200_HOST_CHUNKS")) {        // tuning knob: 1..16 chunks
@@ -1228,8 +1248,12 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
         (rc = g_ws.ensure(PADB, bleach ? n_pad * 4 : 16)) ||
         (rc = g_ws.ensure(TAB, (size_t)B * STED_TABLES * K * KP * 4)) || (rc = g_ws.ensure(CACHE, 3ull * K * K * 8)) ||
         (rc = g_ws.ensure(FLUO, (size_t)B * sizeof(StedFluoParams))) || (rc = g_ws.ensure(SCAL, 3ull * B * 8)) ||
-        (rc = g_ws.ensure(OUT, 2 * n_roi * 4)))
+        (rc = g_ws.ensure(OUT, 2 * n_roi * 4)) || (rc = g_ws.ensure(SIG16, u16 ? n_roi * 2 : 16)))
         return rc;
+    uint16_t* d_sig16 = (uint16_t*)g_ws.dev[SIG16];
+    char* h_map = (char*)dmap_host;
+    char* h_sig = (char*)signal_host;
+    char* d_roi_b = (char*)g_ws.dev[ROI];
     float* d_roi = (float*)g_ws.dev[ROI];
     float* d_a = (float*)g_ws.dev[PADA];
     float* d_b = (float*)g_ws.dev[PADB];
@@ -1261,10 +1285,11 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
             cudaStream_t s_comp = g_pipe.s_comp[c];
             char* ws_c = stoch ? (char*)g_ws.dev[WS] + (size_t)c * ws_bytes : nullptr;
             if (!uploaded) {
-                CUDA_TRY(cudaMemcpyAsync(d_roi + o_roi, dmap_host + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyHostToDevice, s_in));
+                CUDA_TRY(cudaMemcpyAsync(d_roi_b + o_roi * esz, h_map + o_roi * esz, (size_t)nb * px_roi * esz, cudaMemcpyHostToDevice, s_in));
                 CUDA_TRY(cudaEventRecord(g_pipe.e_in[c], s_in));
                 CUDA_TRY(cudaStreamWaitEvent(s_comp, g_pipe.e_in[c], 0));
-                pad_kernel<<<296, 256, 0, s_comp>>>(d_roi + o_roi, d_a + o_pad, nb, H, W, p, Hp, Wpitch);
+                if (u16) pad_kernel<<<296, 256, 0, s_comp>>>((const uint16_t*)d_roi_b + o_roi, d_a + o_pad, nb, H, W, p, Hp, Wpitch);
+                else pad_kernel<<<296, 256, 0, s_comp>>>(d_roi + o_roi, d_a + o_pad, nb, H, W, p, Hp, Wpitch);
                 CUDA_TRY(cudaGetLastError());
                 if ((rc = sted_make_effective(d_cache, d_fluo + b0, d_scal + b0, d_scal + B + b0, d_scal + 2 * B + b0, nb, K,
                                               d_tab + (size_t)b0 * STED_TABLES * K * KP, nullptr, s_comp)))
@@ -1278,15 +1303,21 @@ extern "C" int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
             g_pipe.h_drop[c] = 0;
             if (stoch) CUDA_TRY(cudaMemcpyAsync(&g_pipe.h_drop[c], ws_c, sizeof(int), cudaMemcpyDeviceToHost, s_comp));
             if (bleach) {
-                unpad_kernel<<<296, 256, 0, s_comp>>>(d_b + o_pad, d_roi + o_roi, nb, H, W, p, Hp, Wpitch);
+                if (u16) unpad_kernel<<<296, 256, 0, s_comp>>>(d_b + o_pad, (uint16_t*)d_roi_b + o_roi, nb, H, W, p, Hp, Wpitch);
+                else unpad_kernel<<<296, 256, 0, s_comp>>>(d_b + o_pad, d_roi + o_roi, nb, H, W, p, Hp, Wpitch);
+                CUDA_TRY(cudaGetLastError());
+            }
+            if (u16) {
+                counts_to_u16_kernel<<<296, 256, 0, s_comp>>>(d_sig + o_roi, d_sig16 + o_roi, (size_t)nb * px_roi);
                 CUDA_TRY(cudaGetLastError());
             }
             CUDA_TRY(cudaEventRecord(g_pipe.e_comp[c], s_comp));
             CUDA_TRY(cudaStreamWaitEvent(s_out, g_pipe.e_comp[c], 0));
-            if (bleach) CUDA_TRY(cudaMemcpyAsync(dmap_host + o_roi, d_roi + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
+            if (bleach) CUDA_TRY(cudaMemcpyAsync(h_map + o_roi * esz, d_roi_b + o_roi * esz, (size_t)nb * px_roi * esz, cudaMemcpyDeviceToHost, s_out));
             if (intensity_host)
                 CUDA_TRY(cudaMemcpyAsync(intensity_host + o_roi, d_int + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
-            CUDA_TRY(cudaMemcpyAsync(signal_host + o_roi, d_sig + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
+            if (u16) CUDA_TRY(cudaMemcpyAsync(h_sig + o_roi * 2, d_sig16 + o_roi, (size_t)nb * px_roi * 2, cudaMemcpyDeviceToHost, s_out));
+            else CUDA_TRY(cudaMemcpyAsync(h_sig + o_roi * 4, d_sig + o_roi, (size_t)nb * px_roi * 4, cudaMemcpyDeviceToHost, s_out));
         }
         for (int c = 0; c < nch; ++c) CUDA_TRY(cudaStreamSynchronize(g_pipe.s_comp[c]));
         CUDA_TRY(cudaStreamSynchronize(s_out));

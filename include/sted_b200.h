@@ -53,6 +53,9 @@ extern "C" {
 #define STED_BLEACH         1u  /* apply in-scan photobleaching (pySTED bleach=True)          */
 #define STED_SAMPLE_PHOTONS 2u  /* detector noise: Poisson photon counts (Detector.noise)     */
 #define STED_SAMPLE_BLEACH  4u  /* binomial molecule thinning; otherwise expected counts      */
+#define STED_HOST_U16      16u  /* sted_acquire_host only: dmap_host and signal_host are uint16 counts (half the bus
+                                 * traffic; saturating at 65535).  Needs integer outputs: STED_SAMPLE_PHOTONS, and
+                                 * STED_SAMPLE_BLEACH when STED_BLEACH is set.                                     */
 #define STED_NO_DETECT      8u  /* sted_acquire leaves the detected power (W) in signal_dev; the
                                    detector is applied later by sted_detect                   */
 
@@ -150,18 +153,18 @@ int sted_detect(float* signal_dev, const double* pdt_dev, int B, int H, int W, u
                 int64_t env_base, void* stream);
 
 /* Same, from HOST buffers: pads, uploads, runs sted_make_effective + sted_acquire, downloads.
- *   dmap_host     : float32 [B][H][W] molecule maps of the region of interest (un-padded);
- *                   overwritten with the bleached maps when STED_BLEACH is set
+ *   dmap_host     : float32 (uint16 with STED_HOST_U16) [B][H][W] molecule maps of the region of interest
+ *                   (un-padded); overwritten with the bleached maps when STED_BLEACH is set
  *   psf_cache_host: float64 [3][K][K]
  *   fluo_host     : StedFluoParams [B];  p_ex/p_sted/pdt_host : float64 [B]
- *   intensity_host, signal_host : float32 [B][H][W] (intensity_host may be NULL)
+ *   intensity_host : float32 [B][H][W], may be NULL;  signal_host : float32 (uint16 with STED_HOST_U16) [B][H][W]
  */
-int sted_acquire_host(float* dmap_host, const double* psf_cache_host,
+int sted_acquire_host(void* dmap_host, const double* psf_cache_host,
                       const StedFluoParams* fluo_host, const double* p_ex_host,
                       const double* p_sted_host, const double* pdt_host,
                       int B, int H, int W, int K, uint32_t flags,
                       const StedDetectorParams* det, uint64_t seed, uint64_t offset,
-                      int64_t env_base, float* intensity_host, float* signal_host);
+                      int64_t env_base, float* intensity_host, void* signal_host);
 
 /* Samplers exposed for the statistical tests (same device functions the kernels use).
  *   out_dev[i] ~ Poisson(lambda_dev[i]) / Binomial(n_dev[i], q_dev[i]); counter = i. */

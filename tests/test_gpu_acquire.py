@@ -434,3 +434,15 @@ def test_host_api_equals_device_api_for_every_chunking(B):
     assert np.array_equal(h_int, inten.cpu().numpy())
     assert np.array_equal(h_map, bm.datamaps_roi().cpu().numpy())
     assert h_map.sum() < maps.sum() and h_sig.max() > 5
+    # uint16 transport (STED_HOST_U16): same counts, half the bytes over the bus
+    m16, s16 = maps.astype(np.uint16), np.empty(maps.shape, dtype=np.uint16)
+    _lib.check(lib.sted_acquire_host(m16.ctypes.data_as(vp), cache.ctypes.data_as(vp), ctypes.cast(fl, vp),
+                                     p_ex.ctypes.data_as(vp), p_sted.ctypes.data_as(vp), pdt.ctypes.data_as(vp), B, H, W, K,
+                                     flags | _lib.STED_HOST_U16, ctypes.byref(det), 77, 5, 1000, None, s16.ctypes.data_as(vp)))
+    assert np.array_equal(m16, h_map.astype(np.uint16)) and np.array_equal(s16, h_sig.astype(np.uint16))
+    # fractional outputs cannot travel as uint16
+    rc = lib.sted_acquire_host(m16.ctypes.data_as(vp), cache.ctypes.data_as(vp), ctypes.cast(fl, vp), p_ex.ctypes.data_as(vp),
+                               p_sted.ctypes.data_as(vp), pdt.ctypes.data_as(vp), B, H, W, K,
+                               _lib.STED_BLEACH | _lib.STED_SAMPLE_PHOTONS | _lib.STED_HOST_U16, ctypes.byref(det), 77, 5, 1000,
+                               None, s16.ctypes.data_as(vp))
+    assert rc == -1 and b"STED_HOST_U16" in lib.sted_last_error()            # STED_EINVAL
