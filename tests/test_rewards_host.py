@@ -73,3 +73,20 @@ def test_batched_structure_maps_follow_the_single_map_model():
         cover_b, cover_s = (maps[sel] > 0).mean(), (single[sel] > 0).mean()
         assert 0.5 < cover_b / cover_s < 2.0, (kind, cover_b, cover_s)
         assert abs(maps[sel][maps[sel] > 0].mean() - single[sel][single[sel] > 0].mean()) < 3
+
+
+def test_batched_matching_equals_hungarian():
+    """``match_counts_batch`` (vectorised; Hungarian only for contested pairs) against ``match_counts`` per image,
+    including empty sets, duplicates and contested detections."""
+    rng = np.random.default_rng(7)
+    truths, guesses = [], []
+    for i in range(200):
+        t = rng.integers(5, 59, (rng.integers(0, 15), 2))
+        g = [t[:len(t) // 2] + rng.integers(-1, 2, (len(t) // 2, 2)), rng.integers(5, 59, (rng.integers(0, 4), 2))]
+        if i % 3 == 0 and len(t) >= 2:
+            g.append(t[:2] + 1)                                  # two detections competing for the same truths
+        truths.append(t)
+        guesses.append(np.vstack(g) if i % 7 else np.zeros((0, 2), dtype=np.int64))
+    ref = np.array([rewards.match_counts(t, g) for t, g in zip(truths, guesses)])
+    assert np.array_equal(rewards.match_counts_batch(truths, guesses), ref)
+    assert rewards.match_counts_batch([], []).shape == (0, 3)
