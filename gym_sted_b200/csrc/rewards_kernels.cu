@@ -663,10 +663,35 @@ namespace {
 
 using namespace lm;
 
-__global__ void __launch_bounds__(64) gaussfit_kernel(const float* __restrict__ sted, int H, int W, const int* __restrict__ peaks,
-                                                    const int* __restrict__ npeaks, int maxp, double pixelsize,
-                                                    unsigned char* __restrict__ valid, double* __restrict__ params) {
-    const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+// The Gaussian residuals of one fit evaluated by a whole warp: lane l computes residuals l and l+32 (the 49 exp()
+// calls are ~90 % of a fit's instructions), then every lane receives all 49 values by shuffle.  All lanes of the warp
+// run the solver redundantly on bitwise identical state, so control flow never diverges and the result equals the
+// one-thread fit (GaussResiduals) bit for bit.
+struct WarpGaussResiduals {
+    const double* data;       // this lane's copy of the 49 window values
+    __device__ void operator()(const double* p, double* f) const {
+        const int lane = threadIdx.x & 31;
+        const double wx = p[3] + 1e-3, wy = p[4] + 1e-3;
+        const double dx2 = 2.0 * (wx * wx), dy2 = 2.0 * (wy * wy);
+        auto one = [&](int i) {
+            const double X = (double)(i / 7) - 3.0, Y = (double)(i % 7) - 3.0;
+            const double a = (p[1] - X) * (p[1] - X) / dx2, b = (p[2] - Y) * (p[2] - Y) / dy2;
+            return p[0] * exp(-1.0 * (a + b)) - data[i];
+        };
+        const double r0 = one(lane), r1 = lane + 32 < LM_M ? one(lane + 32) : 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __shfl_sync(0xffffffffu, r0, i);
+#pragma unroll
+        for (int i = 32; i < LM_M; ++i) f[i] = __shfl_sync(0xffffffffu, r1, i - 32);
+    }
+};
+
+constexpr int GF_THREADS = 128;      // 4 fits per CTA, one warp each
+
+__global__ void __launch_bounds__(GF_THREADS) gaussfit_kernel(const float* __restrict__ sted, int H, int W, const int* __restrict__ peaks,
+                                                            const int* __restrict__ npeaks, int maxp, double pixelsize,
+                                                            unsigned char* __restrict__ valid, double* __restrict__ params) {
+    const int b = blockIdx.y, k = blockIdx.x * (GF_THREADS / 32) + (threadIdx.x >> 5);      // warp-uniform
     if (k >= npeaks[b] || k >= maxp) return;
     const int row = peaks[((size_t)b * maxp + k) * 2], col = peaks[((size_t)b * maxp + k) * 2 + 1];
     const float* img = sted + (size_t)b * H * W;
@@ -677,7 +702,8 @@ __global__ void __launch_bounds__(64) gaussfit_kernel(const float* __restrict__ 
         dmax = fmax(dmax, data[i]);
     }
     double p[LM_N] = {dmax, 0.0, 0.0, 1.0, 1.0};
-    lm_fit(GaussResiduals{data}, p, 1e-3, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0);
+    lm_fit(WarpGaussResiduals{data}, p, 1e-3, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0);
+    if ((threadIdx.x & 31) != 0) return;
     const double fx = 2.355 * p[3] * pixelsize, fy = 2.355 * p[4] * pixelsize;
     valid[(size_t)b * maxp + k] = !(fx > 200e-9 || fx < 40e-9 || fy > 200e-9 || fy < 40e-9);
     if (params) for (int j = 0; j < LM_N; ++j) params[((size_t)b * maxp + k) * LM_N + j] = p[j];
@@ -715,8 +741,8 @@ extern "C" int sted_gaussfit_validate(const float* sted_dev, int B, int H, int W
     if (B <= 0 || H <= 0 || W <= 0 || max_peaks <= 0) return fail(STED_EINVAL, "B, H, W, max_peaks must be positive");
     int rc = check_device();
     if (rc) return rc;
-    dim3 grid((max_peaks + 63) / 64, B);
-    gaussfit_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(sted_dev, H, W, peaks_dev, npeaks_dev, max_peaks, pixelsize, valid_dev,
+    dim3 grid((max_peaks + GF_THREADS / 32 - 1) / (GF_THREADS / 32), B);
+    gaussfit_kernel<<<grid, GF_THREADS, 0, (cudaStream_t)stream>>>(sted_dev, H, W, peaks_dev, npeaks_dev, max_peaks, pixelsize, valid_dev,
                                                           params_dev);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;

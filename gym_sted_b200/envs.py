@@ -228,20 +228,12 @@ class VectorContextualMOSTED:
         fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
         res = rewards.resolution(sted)
         mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)      # (B,3)
-        if self.compute_f1:
-            f1 = rewards.nanodomain_f1_batch(sted, [s.nanodomains_coords for s in self.synapses], handle=pending)
-        else:
-            f1 = np.zeros(self.B)
-        reward = f1 * self.scale_nanodomain_reward
+        coords = [s.nanodomains_coords for s in self.synapses]
 
         done = np.full(self.B, self.current_step >= self.max_episode_steps - 1) | self._exhausted()
         self.current_step += 1
         self.episode_memory["mo_objs"].append(mo_objs)
         self.episode_memory["actions"].append(action)
-        self.episode_memory["reward"].append(reward)
-        info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,
-                "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "f1-score": f1,
-                "nanodomains-coords": [s.nanodomains_coords for s in self.synapses]}
 
         obs = []
         for a, mo in zip(self.episode_memory["actions"], self.episode_memory["mo_objs"]):
@@ -256,6 +248,13 @@ class VectorContextualMOSTED:
         state = self._next_state()
         self.state = torch.stack((state, conf1, sted), dim=-1)
         img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+
+        # the Gaussian fits have been running under everything above; read them last
+        f1 = rewards.nanodomain_f1_batch(sted, coords, handle=pending) if self.compute_f1 else np.zeros(self.B)
+        reward = f1 * self.scale_nanodomain_reward
+        self.episode_memory["reward"].append(reward)
+        info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,
+                "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "f1-score": f1, "nanodomains-coords": coords}
         return (img, obs.astype(np.float32)), reward, done, np.zeros(self.B, dtype=bool), info
 
     def _next_state(self):

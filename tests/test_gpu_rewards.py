@@ -391,3 +391,38 @@ def test_detection_capacity_overflow_is_an_error_not_a_fallback():
     big = rng.poisson(5.0, (1, 700, 700)).astype(np.float32)        # 1 % of 490 000 pixels > 4096 mask pixels
     with pytest.raises(_lib.StedError):
         rewards.nanodomain_candidates(torch.from_numpy(big).cuda())
+
+
+def test_warp_parallel_fit_equals_single_thread_fit():
+    """``gaussfit_kernel`` runs one fit per warp (residuals spread over the lanes, solver state replicated); it must
+    return exactly what the one-thread solver (``sted_lmfit_test``, model 0) returns for the same windows."""
+    _gpu()
+    from gym_sted_b200 import _lib
+    rng = np.random.default_rng(21)
+    yy, xx = np.mgrid[:64, :64]
+    imgs = []
+    for _ in range(48):
+        img = rng.poisson(0.4, (64, 64)).astype(np.int64)
+        for (y, x) in rng.integers(0, 64, (8, 2)):
+            s = rng.uniform(0.7, 4.0, 2)
+            img += rng.poisson(rng.uniform(15, 180) * np.exp(-((yy - y) ** 2 / (2 * s[0] ** 2) + (xx - x) ** 2 / (2 * s[1] ** 2))))
+        imgs.append(img)
+    stack = np.stack(imgs)
+    sted, peaks, npk, flags = rewards._candidates_device(torch.from_numpy(stack).float().cuda())
+    valid, params = rewards.gaussfit_validate(sted, peaks, npk, want_params=True)
+    peaks_h, npk_h, params_h = peaks.cpu().numpy(), npk.cpu().numpy(), params.cpu().numpy()
+    wins, starts, where = [], [], []
+    for b in range(len(stack)):
+        padded = np.pad(stack[b], 3, mode="constant").astype(np.float64)
+        for k in range(npk_h[b]):
+            r, c = peaks_h[b, k]
+            w = padded[r:r + 7, c:c + 7]
+            wins.append(w.ravel()); starts.append([w.max(), 0, 0, 1, 1.0]); where.append((b, k))
+    assert len(wins) > 100
+    d = torch.from_numpy(np.stack(wins)).cuda()
+    x = torch.from_numpy(np.array(starts)).cuda()
+    info = torch.zeros(len(wins), dtype=torch.int32, device="cuda")
+    _lib.check(_lib.load().sted_lmfit_test(d.data_ptr(), len(wins), 0, 1e-3, x.data_ptr(), info.data_ptr(), None))
+    x = x.cpu().numpy()
+    for i, (b, k) in enumerate(where):
+        assert np.array_equal(x[i], params_h[b, k]), (b, k, x[i], params_h[b, k])
