@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
 // instead of at the 12 warps/SM of the gather kernel.
 constexpr int DET_THREADS = 256, DET_QCAP = 1024;     // ring capacity >= (DET_THREADS - 1) + 2 * DET_THREADS
 
-__global__ void __launch_bounds__(DET_THREADS) detect_kernel(const AcqParams P) {
+__global__ void __launch_bounds__(DET_THREADS, 5) detect_kernel(const AcqParams P) {
     // thread = two neighbouring pixels sharing one Philox block (two words each).  Stage 1 computes the Poisson mean
     // and resolves the common sampler exits in straight-line code (poisson_fast).  Every other pixel is queued in a
     // shared-memory ring by sampler class - inversion (mean < 12) or PTRS - and the rings are drained 256 entries at
@@ -481,7 +481,7 @@ struct BleachWs {
 constexpr int PS_THREADS = 256, PS_CHUNK = 4096, PS_ITEMS = 2048, PS_PER = PS_CHUNK / PS_THREADS;
 
 template <bool FILL>
-__global__ void __launch_bounds__(PS_THREADS) presample_kernel(const AcqParams P, const BleachWs ws) {
+__global__ void __launch_bounds__(PS_THREADS, 4) presample_kernel(const AcqParams P, const BleachWs ws) {
     const int K = P.K, KP = P.KP, H = P.H, W = P.W, Wp = P.Wp;
     extern __shared__ __align__(128) float smem[];
     float* sCH = smem;                                   // [K][KP]
