@@ -323,6 +323,8 @@ def run_ours(args, rank, local_rank, world):
     while sampler.proc is not None and not sampler.lines and time.perf_counter() - t_wait < 3.0:
         time.sleep(0.02)                     # nvidia-smi needs a moment before its first sample
     sampler.lines.clear()                    # keep only samples taken from here on (the timed region)
+    if sampler.nvml is not None:
+        sampler.samples.clear()
     launches[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
