@@ -178,6 +178,7 @@ class VectorContextualMOSTED:
             self.torch_gen.manual_seed(int(self.np_rng.integers(0, 2 ** 62)))
         frames, coords = synapse.generate_batch_torch(self.B, self.H, self.W, self.device, self.torch_gen)
         self.synapses = [synapse.Synapse(None, c) for c in coords]
+        self._truths = rewards.pad_coords(coords)           # padded once per structure for the batched F1 matching
         self.frames = frames                                   # molecule maps of the current synapses (device, int32)
         cells = -(-self.H // synapse.CELL) * -(-self.W // synapse.CELL)
         self.bm.set_datamaps(frames, max_molecules=self.B * cells * (5 * synapse.CELL ** 2 + 15 * 175))
@@ -228,7 +229,7 @@ class VectorContextualMOSTED:
         fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
         res = rewards.resolution(sted)
         mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)      # (B,3)
-        coords = [s.nanodomains_coords for s in self.synapses]
+        coords, truths = [s.nanodomains_coords for s in self.synapses], self._truths
 
         done = np.full(self.B, self.current_step >= self.max_episode_steps - 1) | self._exhausted()
         self.current_step += 1
@@ -250,7 +251,7 @@ class VectorContextualMOSTED:
         img = self._u16(self.state).cpu().numpy().astype(np.uint16)
 
         # the Gaussian fits have been running under everything above; read them last
-        f1 = rewards.nanodomain_f1_batch(sted, coords, handle=pending) if self.compute_f1 else np.zeros(self.B)
+        f1 = rewards.nanodomain_f1_batch(sted, truths, handle=pending) if self.compute_f1 else np.zeros(self.B)
         reward = f1 * self.scale_nanodomain_reward
         self.episode_memory["reward"].append(reward)
         info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,

@@ -217,40 +217,57 @@ def detect_nanodomains(sted, pixelsize=PIXELSIZE) -> np.ndarray:
     return detect_nanodomains_batch(t.to("cuda", torch.float32)[None], pixelsize)[0]
 
 
-def match_counts_batch(truths, guesses, threshold=2):
-    """``match_counts`` for many images: (B,3) int array of (TP, FP, FN).  Pairs closer than ``threshold`` form a
-    bipartite graph and TP is its maximum matching (that is what the Hungarian solution on the masked costs counts);
-    when no detection and no truth has more than one partner the matching is the edge set itself, so only images with
-    a contested pair go through the Hungarian solver."""
-    B = len(truths)
-    nt = np.array([len(t) for t in truths])
-    ng = np.array([len(g) for g in guesses])
-    out = np.zeros((B, 3), dtype=np.int64)
-    if B == 0:
-        return out
-    T = np.full((B, max(int(nt.max()), 1), 2), 1e9)
-    G = np.full((B, max(int(ng.max()), 1), 2), -1e9)
-    for b in range(B):
-        if nt[b]:
-            T[b, :nt[b]] = np.asarray(truths[b], dtype=np.float64).reshape(-1, 2)
-        if ng[b]:
-            G[b, :ng[b]] = np.asarray(guesses[b], dtype=np.float64).reshape(-1, 2)
+def pad_coords(coords, fill=1e9):
+    """List of (n_i, 2) coordinate arrays -> ((B, max n, 2) float64 padded with ``fill``, (B,) counts)."""
+    n = np.array([len(c) for c in coords], dtype=np.int64)
+    out = np.full((len(coords), max(int(n.max()) if len(n) else 0, 1), 2), fill, dtype=np.float64)
+    for b, c in enumerate(coords):
+        if n[b]:
+            out[b, :n[b]] = np.asarray(c, dtype=np.float64).reshape(-1, 2)
+    return out, n
+
+
+def _match_padded(T, nt, G, keep, threshold=2):
+    """(B,3) int array of (TP, FP, FN) from padded truths ``T`` (rows >= nt are far away) and candidate detections ``G``
+    with their ``keep`` mask.  Pairs closer than ``threshold`` form a bipartite graph and TP is its maximum matching
+    (that is what the Hungarian solution on the masked costs counts); when no detection and no truth has more than one
+    partner the matching is the edge set itself, so only images with a contested pair go through the Hungarian solver."""
+    ng = keep.sum(axis=1)
     d = T[:, :, None, :] - G[:, None, :, :]
-    close = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) < threshold          # padding is never close
+    close = (np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) < threshold) & keep[:, None, :]
+    close &= (np.arange(T.shape[1])[None, :] < nt[:, None])[:, :, None]
     simple = (close.sum(axis=1).max(axis=1) <= 1) & (close.sum(axis=2).max(axis=1) <= 1)
     tp = close.sum(axis=(1, 2))
     for b in np.flatnonzero(~simple):
-        tp[b] = match_counts(truths[b], guesses[b], threshold)[0]
-    out[:, 0], out[:, 1], out[:, 2] = tp, ng - tp, nt - tp
-    return out
+        tp[b] = match_counts(T[b, :nt[b]], G[b][keep[b]], threshold)[0]
+    return np.stack([tp, ng - tp, nt - tp], axis=1).astype(np.int64)
+
+
+def match_counts_batch(truths, guesses, threshold=2):
+    """``match_counts`` for many images (lists of coordinate arrays): (B,3) int array of (TP, FP, FN)."""
+    if len(truths) == 0:
+        return np.zeros((0, 3), dtype=np.int64)
+    T, nt = pad_coords(truths)
+    G, ng = pad_coords(guesses, fill=-1e9)
+    return _match_padded(T, nt, G, np.arange(G.shape[1])[None, :] < ng[:, None], threshold)
 
 
 def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, handle=None) -> np.ndarray:
     """F1 of B images: candidates and Gaussian-fit validation on the GPU (already enqueued when ``handle`` is given),
-    matching of the few surviving coordinates on the host."""
-    valid = detect_nanodomains_collect(handle if handle is not None else detect_nanodomains_launch(sted, pixelsize))
-    counts = match_counts_batch(truths, valid, threshold)
-    return np.array([f1_from_counts(*c) for c in counts.tolist()])
+    matching of the few surviving coordinates on the host.  ``truths``: list of (n_i, 2) arrays, or the
+    ``pad_coords`` tuple of such a list (saves re-padding when the same structures are scored repeatedly)."""
+    _, sted32, peaks, npk, flags, valid, done = handle if handle is not None else detect_nanodomains_launch(sted, pixelsize)
+    done.synchronize()
+    peaks, npk, flags, valid = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy(), valid.cpu().numpy()
+    _check_capacity(flags)
+    pm = max(int(npk.max()), 1)
+    keep = (np.arange(pm)[None, :] < npk[:, None]) & (valid[:, :pm] != 0)
+    T, nt = truths if isinstance(truths, tuple) else pad_coords(truths)
+    counts = _match_padded(T, nt, peaks[:, :pm].astype(np.float64), keep, threshold)
+    tp, fp, fn = counts[:, 0].astype(np.float64), counts[:, 1].astype(np.float64), counts[:, 2].astype(np.float64)
+    prec = tp / (tp + fp + 1e-6)
+    rec = tp / (tp + fn + 1e-6)
+    return 2 * prec * rec / (prec + rec + 1e-6)
 
 
 def match_counts(truth, guess, threshold=2):
