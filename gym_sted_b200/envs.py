@@ -193,7 +193,7 @@ class VectorContextualMOSTED:
     @staticmethod
     def _u16(x: torch.Tensor) -> torch.Tensor:
         # numpy's int64 -> uint16 cast wraps modulo 2^16 (contextual_sted_env.py:93)
-        return (x.to(torch.int64) & 0xFFFF).to(torch.int32)
+        return (x.to(torch.int64) & 0xFFFF).to(torch.uint16)
 
     # ------------------------------------------------------------------ gym API
     def reset(self, seed=None, options=None):
@@ -212,7 +212,7 @@ class VectorContextualMOSTED:
         state = self._new_datamaps()
         zeros = torch.zeros_like(state)
         self.state = torch.stack((state, zeros, zeros), dim=-1)
-        img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+        img = self._u16(self.state).cpu().numpy()
         vec = np.zeros((self.B, self.observation_space[1].shape[0]), dtype=np.float32)
         return (img, vec), {}
 
@@ -248,7 +248,7 @@ class VectorContextualMOSTED:
 
         state = self._next_state()
         self.state = torch.stack((state, conf1, sted), dim=-1)
-        img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+        img = self._u16(self.state).cpu().numpy()
 
         # the Gaussian fits have been running under everything above; read them last
         f1 = rewards.nanodomain_f1_batch(sted, truths, handle=pending) if self.compute_f1 else np.zeros(self.B)
@@ -464,7 +464,7 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         state = self._new_datamaps()
         zeros = torch.zeros_like(state)
         self.state = torch.stack((state, zeros, zeros), dim=-1)
-        img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+        img = self._u16(self.state).cpu().numpy()
         return (img, np.zeros((self.B, self.observation_space[1].shape[0]), dtype=np.float32)), {}
 
     def _new_datamaps(self):
@@ -519,7 +519,7 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         obs = np.pad(obs, ((0, 0), (0, self.observation_space[1].shape[0] - obs.shape[1])))
         state = self._new_datamaps()
         self.state = torch.stack((state, conf1, sted), dim=-1)
-        img = self._u16(self.state).cpu().numpy().astype(np.uint16)
+        img = self._u16(self.state).cpu().numpy()
         return (img, obs.astype(np.float32)), reward, np.full(self.B, done), np.zeros(self.B, dtype=bool), info
 
 
