@@ -52,3 +52,15 @@ def test_reward_gather_world_size_2(n_envs):
     for rank, full, full_obs in got:
         np.testing.assert_array_equal(full, expect)
         np.testing.assert_array_equal(full_obs[:, 1], np.arange(n_envs, dtype=np.float32))
+
+
+def test_numa_binding_is_a_safe_noop_without_nvml_devices():
+    """``bind_to_gpu_numa`` never raises: it returns False (affinity untouched) when NVML or the GPU is absent."""
+    import os
+    from gym_sted_b200 import dist as sd
+    before = os.sched_getaffinity(0)
+    ok = sd.bind_to_gpu_numa(0)
+    assert isinstance(ok, bool)
+    if not ok:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
