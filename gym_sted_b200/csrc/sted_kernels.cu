@@ -895,6 +895,7 @@ int make_params(AcqParams& P, const float* din, float* dout, const float* tables
     if (K < 1 || (K & 1) == 0) return fail(STED_EINVAL, "K must be odd (got %d)", K);
     if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
     if (H > 65535) return fail(STED_EUNSUPPORTED, "H=%d exceeds 65535 scan rows", H);
+    if (B > 65535) return fail(STED_EUNSUPPORTED, "B=%d exceeds 65535 environments per launch (grid limit): split the batch", B);
     if (W + K - 1 > 4095) return fail(STED_EUNSUPPORTED, "W=%d exceeds the 4095-column limit of the event encoding", W);
     if ((flags & STED_BLEACH) && (!dout || dout == din))
         return fail(STED_EINVAL, "bleaching needs dmap_out_dev distinct from dmap_in_dev");
