@@ -218,6 +218,7 @@ def workload_config(args, envs_per_gpu, world):
             "envs_per_gpu": envs_per_gpu, "global_envs": envs_per_gpu * world, "image": [args.size, args.size],
             "psf": [K, K], "fluorophore": "high-signal_low-bleach", "actions": "uniform in action box",
             "l2": l2_note(envs_per_gpu, args.size),
+            "schedule": "sequential" if args.sequential else "next structure's confocal on a low-priority stream under the scan",
             "parallelism": f"env-parallel x{world}, no data-path collective"}
 
 
@@ -249,6 +250,12 @@ def run_ours(args, rank, local_rank, world):
     micro = helpers.product_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
                                        background=defaults.DETECTOR["background"])
     bm = BatchedMicroscope(micro, B, H, W, device=dev, env_base=env_base, seed=1234)
+    # the next structure's confocal image does not depend on the current structure's acquisitions: it is acquired on
+    # a low-priority stream with its own device buffers and fills the idle slots of the main stream's kernels (the
+    # scan's second wave above all); --sequential issues the four acquisitions one after the other instead
+    bm_next = None if args.sequential else BatchedMicroscope(micro, B, H, W, device=dev, env_base=env_base, seed=1234 ^ 0x5EED)
+    main_stream = torch.cuda.Stream(dev, priority=-1)
+    side_stream = torch.cuda.Stream(dev, priority=0)
 
     # synthetic inputs: two pools of B maps (current / fresh), resident in HBM and in pinned host memory
     n_unique = min(B, 32)
@@ -271,6 +278,7 @@ def run_ours(args, rank, local_rank, world):
     kern_ev = []
 
     def step(i, timed):
+        """The four acquisitions of one ContextualMOSTED env-step for the whole batch (mosted_env.py:184,222-234)."""
         a = actions_dev[i]
         bm.set_datamaps(pool_dev[0], max_molecules=pool_tot[0])
         ev = None
@@ -278,10 +286,19 @@ def run_ours(args, rank, local_rank, world):
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         bm.make_effective(conf[1], conf[2], conf[0])
         _gather_only(bm, conf[0], sig[0], ev)
+        cur = torch.cuda.current_stream(dev)
+        if bm_next is not None:
+            side_stream.wait_stream(cur)                 # after the bracketed gather: its timing stays undisturbed
+            with torch.cuda.stream(side_stream):
+                bm_next.set_datamaps(pool_dev[1], max_molecules=pool_tot[1])
+                bm_next.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
         _scan_only(bm, a, sig[1], timed)
         bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[2])
-        bm.set_datamaps(pool_dev[1], max_molecules=pool_tot[1])
-        bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
+        if bm_next is not None:
+            cur.wait_stream(side_stream)
+        else:
+            bm.set_datamaps(pool_dev[1], max_molecules=pool_tot[1])
+            bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
         launches[0] += 15     # 3 x (make_effective, gather, detect) + (make_effective, presample x2, bucket scan, sweep, detect)
 
     scan_ev = []
@@ -326,6 +343,8 @@ def run_ours(args, rank, local_rank, world):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    torch.cuda.synchronize(dev)
+    torch.cuda.set_stream(main_stream)       # everything below is issued on the high-priority stream
     for i in range(args.warmup):
         step(i, False)
     sync_all()
@@ -433,7 +452,8 @@ def run_ours(args, rank, local_rank, world):
                          "achieved": fl_scan / (scan_ms * 1e-3) * 1e-12, "peak": pk.value, "unit": "TFLOP/s",
                          "frac": fl_scan / (scan_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
                          "algorithmic_flops_per_launch": fl_scan, "launch_ms": scan_ms,
-                         "note": "3N algorithmic flops (SURVEY 8d); the kernels execute 2N"}
+                         "note": "3N algorithmic flops (SURVEY 8d); the kernels execute 2N" + ("" if args.sequential else
+                                 "; timed with the next structure's low-priority gather co-running (run --sequential for the scan alone)")}
         cpu = None
         if not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -470,6 +490,8 @@ def main():
     ap.add_argument("--size", type=int, default=256, help="image side in pixels")
     ap.add_argument("--cpu-envs", type=int, default=None, help="env-steps in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sequential", action="store_true",
+                    help="issue the four acquisitions of a step one after the other (no overlap of the next structure's confocal)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

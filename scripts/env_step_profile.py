@@ -23,7 +23,8 @@ wrap(rewards, "gaussfit_validate")
 wrap(rewards, "match_counts")
 wrap(rewards, "detect_nanodomains_batch")
 B = 256
-vec = envs.make_vec("ContextualMOSTED-easy-hslb-v0", B, compute_f1=True, seed=0)
+SIZE = int(os.environ.get("PROBE_HW", 64))
+vec = envs.make_vec("ContextualMOSTED-easy-hslb-v0", B, compute_f1=True, seed=0, image_size=SIZE)
 vec.reset(seed=0)
 rng = np.random.default_rng(0)
 acts = rng.uniform(vec.action_space.low, vec.action_space.high, (B, 3)).astype(np.float32)
