@@ -371,6 +371,15 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop()
     gather_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
     scan_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev]))
+    # the scan on its own (nothing co-running): three extra scans after the timed region
+    scan_alone_ms = scan_ms
+    if bm_next is not None:
+        n_before = len(scan_ev)
+        for i in range(3):
+            bm.set_datamaps(pool_dev[0], max_molecules=pool_tot[0])
+            _scan_only(bm, actions_dev[args.warmup + i % max(args.steps, 1)], sig[1], True)
+            torch.cuda.synchronize(dev)
+        scan_alone_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev[n_before:]]))
 
     # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region
     import ctypes
@@ -452,6 +461,8 @@ def run_ours(args, rank, local_rank, world):
                          "achieved": fl_scan / (scan_ms * 1e-3) * 1e-12, "peak": pk.value, "unit": "TFLOP/s",
                          "frac": fl_scan / (scan_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
                          "algorithmic_flops_per_launch": fl_scan, "launch_ms": scan_ms,
+                         "alone": {"launch_ms": scan_alone_ms, "frac": fl_scan / (scan_alone_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
+                                   "note": "same scan with nothing co-running, 3 launches after the timed region"},
                          "note": "3N algorithmic flops (SURVEY 8d); the kernels execute 2N" + ("" if args.sequential else
                                  "; timed with the next structure's low-priority gather co-running (run --sequential for the scan alone)")}
         cpu = None
