@@ -1048,7 +1048,9 @@ struct Workspace {
         return STED_OK;
     }
 };
-Workspace g_ws;
+// one workspace and one stream set per host thread: concurrent sted_acquire_host calls from different threads do not
+// serialise on each other (each thread pays for its own device scratch)
+thread_local Workspace g_ws;
 
 __device__ __forceinline__ float host_to_count(float v) { return v; }
 __device__ __forceinline__ float host_to_count(uint16_t v) { return (float)v; }
@@ -1192,12 +1194,15 @@ struct HostPipe {
     cudaEvent_t e_in[MAXC], e_comp[MAXC];
     int* h_drop = nullptr;               // pinned: dropped-event counter of each chunk
     bool ready = false;
-    int init() {
+    int init(bool low_priority) {
         if (ready) return STED_OK;
-        CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        int lo = 0, hi = 0;                  // numerically lower = higher priority
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const int prio = low_priority ? lo : hi;
+        CUDA_TRY(cudaStreamCreateWithPriority(&s_in, cudaStreamNonBlocking, prio));
+        CUDA_TRY(cudaStreamCreateWithPriority(&s_out, cudaStreamNonBlocking, prio));
         for (int i = 0; i < MAXC; ++i) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&s_comp[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithPriority(&s_comp[i], cudaStreamNonBlocking, prio));
             CUDA_TRY(cudaEventCreateWithFlags(&e_in[i], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&e_comp[i], cudaEventDisableTiming));
         }
@@ -1206,9 +1211,16 @@ struct HostPipe {
         return STED_OK;
     }
 };
-HostPipe g_pipe;
+thread_local HostPipe g_pipe;
+thread_local bool g_host_low_priority = false;
 
 }  // namespace
+
+extern "C" int sted_host_thread_priority(int low) {
+    if (g_pipe.ready) return fail(STED_EINVAL, "sted_host_thread_priority must be called before this thread's first sted_acquire_host");
+    g_host_low_priority = low != 0;
+    return STED_OK;
+}
 
 extern "C" int sted_acquire_host(void* dmap_host, const double* psf_cache_host, const StedFluoParams* fluo_host,
                                  const double* p_ex_host, const double* p_sted_host, const double* pdt_host, int B, int H,
@@ -1221,8 +1233,7 @@ extern "C" int sted_acquire_host(void* dmap_host, const double* psf_cache_host, 
     if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
     int rc = check_device();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lock(g_ws.mu);
-    if ((rc = g_pipe.init())) return rc;
+    if ((rc = g_pipe.init(g_host_low_priority))) return rc;
     const int KP = STED_KPITCH(K), Hp = H + K - 1, Wp = W + K - 1, Wpitch = (Wp + 3) & ~3, p = K / 2;
     const size_t px_roi = (size_t)H * W, px_pad = (size_t)Hp * Wpitch;
     const size_t n_roi = (size_t)B * px_roi, n_pad = (size_t)B * px_pad;
@@ -1243,7 +1254,7 @@ extern "C" int sted_acquire_host(void* dmap_host, const double* psf_cache_host, 
     }
     const int cb = (B + nch - 1) / nch;
     // scratch of the stochastic scan: starts at 4 deaths per pixel and grows when a scan reports dropped events
-    static unsigned long long s_max_events = 0;
+    static thread_local unsigned long long s_max_events = 0;
     if (stoch && s_max_events < 4ull * cb * px_roi) s_max_events = 4ull * cb * px_roi;
     if ((rc = g_ws.ensure(ROI, n_roi * 4)) || (rc = g_ws.ensure(PADA, n_pad * 4)) ||
         (rc = g_ws.ensure(PADB, bleach ? n_pad * 4 : 16)) ||

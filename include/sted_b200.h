@@ -159,6 +159,12 @@ int sted_detect(float* signal_dev, const double* pdt_dev, int B, int H, int W, u
  *   fluo_host     : StedFluoParams [B];  p_ex/p_sted/pdt_host : float64 [B]
  *   intensity_host : float32 [B][H][W], may be NULL;  signal_host : float32 (uint16 with STED_HOST_U16) [B][H][W]
  */
+/* sted_acquire_host keeps its device scratch and its streams per calling host thread, so calls from different threads
+ * run concurrently.  A thread that carries work nobody waits for yet (e.g. the confocal image of the next structure)
+ * can ask for low-priority streams before its first call: the GPU then runs it in the idle slots of the other
+ * threads' kernels. */
+int sted_host_thread_priority(int low);
+
 int sted_acquire_host(void* dmap_host, const double* psf_cache_host,
                       const StedFluoParams* fluo_host, const double* p_ex_host,
                       const double* p_sted_host, const double* pdt_host,

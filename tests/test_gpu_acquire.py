@@ -446,3 +446,59 @@ def test_host_api_equals_device_api_for_every_chunking(B):
                                _lib.STED_BLEACH | _lib.STED_SAMPLE_PHOTONS | _lib.STED_HOST_U16, ctypes.byref(det), 77, 5, 1000,
                                None, s16.ctypes.data_as(vp))
     assert rc == -1 and b"STED_HOST_U16" in lib.sted_last_error()            # STED_EINVAL
+
+
+def test_host_api_calls_from_two_threads_run_concurrently_and_agree():
+    """``sted_acquire_host`` keeps its scratch and streams per host thread: two threads (one on low-priority streams)
+    calling it at the same time get exactly the results of the same calls made one after the other."""
+    _require_gpu()
+    import ctypes
+    import threading
+    from gym_sted_b200.base import fluo_struct
+    B, H, W = 48, 64, 64
+    m = helpers.product_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
+                                   background=defaults.DETECTOR["background"])
+    rng = np.random.default_rng(5)
+    maps = [np.stack([helpers.synthetic_datamap(rng, H, W) for _ in range(B)]).astype(np.float32) for _ in range(2)]
+    lib = _lib.load()
+    cache = m._packed_cache(PX)
+    K = cache.shape[-1]
+    fl = (_lib.StedFluoParams * B)(*[fluo_struct(m.fluo, m.excitation, m.sted)] * B)
+    det = m.detector.params()
+    vp = ctypes.c_void_p
+    pdt, p_ex, p_sted = np.full(B, 20e-6), np.full(B, 8e-6), np.full(B, 0.12)
+    flags = _lib.STED_BLEACH | _lib.STED_SAMPLE_BLEACH | _lib.STED_SAMPLE_PHOTONS
+
+    def call(h_map, h_sig, off):
+        _lib.check(lib.sted_acquire_host(h_map.ctypes.data_as(vp), cache.ctypes.data_as(vp), ctypes.cast(fl, vp),
+                                         p_ex.ctypes.data_as(vp), p_sted.ctypes.data_as(vp), pdt.ctypes.data_as(vp), B, H, W, K,
+                                         flags, ctypes.byref(det), 7, off, 0, None, h_sig.ctypes.data_as(vp)))
+
+    ref = []
+    for k in range(2):
+        hm, hs = maps[k].copy(), np.empty_like(maps[k])
+        for rep in range(3):
+            call(hm, hs, 10 * k + rep)
+        ref.append((hm, hs))
+    got = [None, None]
+    errors = []
+
+    def worker(k):
+        try:
+            if k == 1:
+                _lib.check(lib.sted_host_thread_priority(1))
+            hm, hs = maps[k].copy(), np.empty_like(maps[k])
+            for rep in range(3):
+                call(hm, hs, 10 * k + rep)
+            got[k] = (hm, hs)
+        except Exception as exc:                     # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(2):
+        assert np.array_equal(got[k][0], ref[k][0]) and np.array_equal(got[k][1], ref[k][1])
