@@ -520,7 +520,7 @@ def run_ours(args, rank, local_rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, B, world), "env_steps_per_s": value / ACQ_PER_STEP,
             "e2e": {"value": e2e_value, "unit": "acquisitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "sted_acquire_host (C ABI, pinned host buffers, uint16 counts: STED_HOST_U16)", "numa_bound": numa_bound},
+                    "steps": e2e_steps, "api": "sted_acquire_host (C ABI, pinned host buffers, uint16 counts: STED_HOST_U16)" + ("" if args.sequential else "; the next structure's call comes from a second host thread on low-priority streams"), "numa_bound": numa_bound},
             "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "roofline_scan": roofline_scan,
             "cpu_baseline": cpu,
         }
