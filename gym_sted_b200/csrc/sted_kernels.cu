@@ -1036,9 +1036,11 @@ int launch_detect(const AcqParams& P, cudaStream_t st) {
 
 // growable device workspace for the *_host entry points
 struct Workspace {
-    std::mutex mu;
     void* dev[10] = {nullptr};
     size_t cap[10] = {0};
+    ~Workspace() {                           // thread exit: give the scratch back (errors at process teardown are moot)
+        for (void* p : dev) if (p) cudaFree(p);
+    }
     int ensure(int slot, size_t bytes) {
         if (cap[slot] >= bytes) return STED_OK;
         if (dev[slot]) cudaFree(dev[slot]);
@@ -1194,6 +1196,12 @@ struct HostPipe {
     cudaEvent_t e_in[MAXC], e_comp[MAXC];
     int* h_drop = nullptr;               // pinned: dropped-event counter of each chunk
     bool ready = false;
+    ~HostPipe() {
+        if (!ready) return;
+        cudaStreamDestroy(s_in); cudaStreamDestroy(s_out);
+        for (int i = 0; i < MAXC; ++i) { cudaStreamDestroy(s_comp[i]); cudaEventDestroy(e_in[i]); cudaEventDestroy(e_comp[i]); }
+        cudaFreeHost(h_drop);
+    }
     int init(bool low_priority) {
         if (ready) return STED_OK;
         int lo = 0, hi = 0;                  // numerically lower = higher priority
