@@ -107,8 +107,22 @@ class Fluorescence:
         return self.sigma_ste[int(round(lambda_ * 1e9))]
 
     def get_photons(self, intensity, lambda_=None):
+        """Photon flux of an intensity (W/m^2) -> photons/(m^2 s), floor division like pySTED
+        (called at ``gym_sted/utils.py:624-625,653``)."""
         lambda_ = self.lambda_ if lambda_ is None else lambda_
         return np.asarray(intensity, dtype=np.float64) // (physics.H_PLANCK * physics.C_LIGHT / lambda_)
+
+    def get_k_bleach(self, lambda_ex, lambda_sted, phi_ex, phi_sted, tau_sted, tau_rep, dwelltime):
+        """Bleaching-rate map (1/s) from photon-flux maps: the 7-argument accessor the reference calls at
+        ``gym_sted/utils.py:627-630`` (``phi_sted`` is the TIME-AVERAGED STED flux, ``phi*tau_sted/tau_rep``).
+        Host float64 twin of the formula ``make_effective_kernel`` evaluates per environment on the device
+        (``csrc/sted_kernels.cu``); the scan itself never calls this."""
+        if self.triplet_dynamics_frac:
+            raise NotImplementedError("triplet_dynamics_frac != 0 is outside the modelled path")
+        e_sted = physics.H_PLANCK * physics.C_LIGHT / lambda_sted
+        i_inst = np.asarray(phi_sted, dtype=np.float64) * e_sted * tau_rep / tau_sted
+        k_ex = self.get_sigma_abs(lambda_ex) * np.asarray(phi_ex, dtype=np.float64)
+        return k_ex * tau_sted * (self.k0 * i_inst + self.k1 * i_inst ** self.b)
 
 
 def fluo_struct(fluo: Fluorescence, excitation: GaussianBeam, sted: DonutBeam) -> _lib.StedFluoParams:
@@ -211,21 +225,42 @@ class Microscope:
     def get_signal_and_bleach(self, datamap, pixelsize, pdt, p_ex, p_sted, indices=None, acquired_intensity=None,
                               pixel_list=None, bleach=True, update=True, seed=None, filter_bypass=False,
                               bleach_func=None, sample_func=None, steps=None, sample_bleach=True):
+        """One raster-scan acquisition of ``datamap`` (``gym_sted/envs/mosted_env.py:184,222,227,232``).
+
+        ``pdt`` and ``p_ex`` may be scalars or (H, W) arrays (one value per dwell, as the timed environments pass:
+        ``gym_sted/envs/timed_sted_env.py:141-148``); ``p_sted`` must be a scalar (the depletion efficiency is not
+        separable in it).  The whole padded map takes part — molecules a caller placed in the K//2 frame are imaged
+        and bleached like pySTED does — and with ``bleach`` and ``update`` the datamap is mutated in place."""
+        import torch  # device memory only
+
         if datamap.roi is None:
             raise ValueError("Datamap ROI is not set; call datamap.set_roi(i_ex, 'max') first")
-        if np.ndim(pdt) or np.ndim(p_ex) or np.ndim(p_sted):
-            raise NotImplementedError("array-valued pdt/p_ex/p_sted (timed envs) are outside the rebuilt path")
+        if np.ndim(p_sted):
+            if np.ptp(p_sted) != 0:
+                raise NotImplementedError("array-valued p_sted is outside the rebuilt path (per-dwell effective PSFs)")
+            p_sted = float(np.ravel(p_sted)[0])
         if pixel_list is not None or bleach_func is not None or sample_func is not None:
             raise NotImplementedError("custom pixel lists / bleach functions are outside the rebuilt path")
         lib = _lib.load()
+        if _lib.device_count() == 0:
+            raise _lib.StedError(-2, "no CUDA device: gym_sted_b200 has no CPU fallback")
         cache = self._packed_cache(pixelsize)
         K = cache.shape[-1]
         rs, cs = datamap.roi
         H, W = rs.stop - rs.start, cs.stop - cs.start
-        whole = datamap.whole_datamap
-        if whole.shape != (H + K - 1, W + K - 1):
+        whole = np.asarray(datamap.whole_datamap)
+        Hp, Wp = H + K - 1, W + K - 1
+        if whole.shape != (Hp, Wp):
             raise ValueError(f"datamap shape {whole.shape} does not match ROI {H}x{W} padded for K={K}")
-        roi = np.ascontiguousarray(whole[rs, cs], dtype=np.float32).reshape(1, H, W).copy()
+        per_dwell = bool(np.ndim(pdt) or np.ndim(p_ex))
+        if per_dwell:
+            pdt_map = np.ascontiguousarray(np.broadcast_to(np.asarray(pdt, dtype=np.float64), (H, W)))
+            pex_map = np.ascontiguousarray(np.broadcast_to(np.asarray(p_ex, dtype=np.float64), (H, W)))
+            pdt_ref, pex_ref = float(pdt_map.max()), float(pex_map.max())
+            if not (pdt_ref > 0 and pex_ref >= 0):
+                raise ValueError("per-dwell pdt must be positive somewhere")
+        else:
+            pdt_ref, pex_ref = float(pdt), float(p_ex)
         flags = 0
         if bleach:
             flags |= _lib.STED_BLEACH
@@ -236,25 +271,49 @@ class Microscope:
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 31 - 1))
         self._acq_counter += 1
+        dev = torch.device("cuda")
+        st = torch.cuda.current_stream(dev).cuda_stream
+        Wpitch = (Wp + 3) & ~3
+        d_in = torch.zeros((1, Hp, Wpitch), dtype=torch.float32, device=dev)
+        d_in[0, :, :Wp] = torch.from_numpy(np.ascontiguousarray(whole, dtype=np.float32)).to(dev)
+        d_out = torch.zeros_like(d_in) if bleach else None
         fl = fluo_struct(self.fluo, self.excitation, self.sted)
         det = self.detector.params()
-        scal = np.array([p_ex, p_sted, pdt], dtype=np.float64)
-        intensity = np.empty((1, H, W), dtype=np.float32)
-        signal = np.empty((1, H, W), dtype=np.float32)
-        vp = ctypes.c_void_p
-        _lib.check(lib.sted_acquire_host(
-            roi.ctypes.data_as(vp), cache.ctypes.data_as(vp), ctypes.cast(ctypes.byref(fl), vp),
-            scal[0:1].ctypes.data_as(vp), scal[1:2].ctypes.data_as(vp), scal[2:3].ctypes.data_as(vp),
-            1, H, W, K, flags, ctypes.byref(det), int(seed), self._acq_counter, 0,
-            intensity.ctypes.data_as(vp), signal.ctypes.data_as(vp)))
+        d_cache = torch.from_numpy(cache).to(dev)
+        d_fluo = torch.frombuffer(bytearray(bytes(fl)), dtype=torch.uint8).to(dev)
+        scal = torch.tensor([[pex_ref], [p_sted], [pdt_ref]], dtype=torch.float64, device=dev)
+        tables = torch.empty((1, _lib.STED_TABLES, K, _lib.kpitch(K)), dtype=torch.float32, device=dev)
+        _lib.check(lib.sted_make_effective(d_cache.data_ptr(), d_fluo.data_ptr(), scal[0].data_ptr(), scal[1].data_ptr(),
+                                           scal[2].data_ptr(), 1, K, tables.data_ptr(), None, st))
+        intensity = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        signal = torch.empty_like(intensity)
+        ws, ws_bytes = None, 0
+        if bleach and sample_bleach:
+            ws_bytes = int(lib.sted_bleach_workspace_bytes(1, H, int(max(whole.sum(), 0)) + 16))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        if per_dwell:
+            # weights relative to the reference values the tables were built with
+            d_wdt = torch.from_numpy(pdt_map / pdt_ref).to(dev, torch.float32).reshape(1, H, W).contiguous()
+            d_wex = torch.from_numpy(pex_map / pex_ref if pex_ref > 0 else pex_map).to(dev, torch.float32).reshape(1, H, W).contiguous()
+            _lib.check(lib.sted_acquire_dwellmaps(
+                d_in.data_ptr(), d_out.data_ptr() if bleach else None, tables.data_ptr(), scal[2].data_ptr(),
+                d_wdt.data_ptr(), d_wex.data_ptr(), 1, H, W, K, flags, ctypes.byref(det), float(self.fluo.lambda_),
+                int(seed), self._acq_counter, 0, intensity.data_ptr(), signal.data_ptr(),
+                ws.data_ptr() if ws is not None else None, ws_bytes, st))
+        else:
+            _lib.check(lib.sted_acquire(
+                d_in.data_ptr(), d_out.data_ptr() if bleach else None, tables.data_ptr(), scal[2].data_ptr(), 1, H, W, K,
+                flags, ctypes.byref(det), float(self.fluo.lambda_), int(seed), self._acq_counter, 0,
+                intensity.data_ptr(), signal.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes, st))
         if bleach:
-            out = np.zeros(whole.shape, dtype=np.int64 if sample_bleach else np.float64)
-            out[rs, cs] = np.rint(roi[0]) if sample_bleach else roi[0]
+            out = d_out[0, :, :Wp].cpu().numpy()
+            out = np.rint(out).astype(np.int64) if sample_bleach else out.astype(np.float64)
         else:
             out = whole.copy()
         bleached = {"base": out}
         if bleach and update:
             datamap.whole_datamap = out
             datamap.sub_datamaps_dict = {"base": out}
-        photons = np.rint(signal[0]).astype(np.int64) if self.detector.noise else signal[0].astype(np.float64)
-        return photons, bleached, intensity[0].astype(np.float64)
+        sig = signal[0].cpu().numpy()
+        photons = np.rint(sig).astype(np.int64) if self.detector.noise else sig.astype(np.float64)
+        return photons, bleached, intensity[0].cpu().numpy().astype(np.float64)

@@ -135,7 +135,14 @@ class VectorContextualMOSTED:
 
     def __init__(self, num_envs=1, bleach_sampling="constant", actions=("p_sted", "p_ex", "pdt"), max_episode_steps=10,
                  scale_nanodomain_reward=1.0, normalize_observations=True, image_size=64, device="cuda", seed=None,
-                 env_base=0, compute_f1=True):
+                 env_base=0, compute_f1=True, on_invalid="mask"):
+        """``on_invalid``: what a ``None`` objective (negative SNR, ``objectives.py:95-96``) does.  The reference's
+        ``Normalizer`` raises ``TypeError`` on it; "raise" keeps that (the single-environment views use it), "mask"
+        (default for batches) carries NaN in that environment's objective / observation entries and lists the
+        environment in ``info["invalid"]`` instead of aborting the other B-1 environments mid-step."""
+        if on_invalid not in ("mask", "raise"):
+            raise ValueError("on_invalid must be 'mask' or 'raise'")
+        self.on_invalid = on_invalid
         self.B, self.H, self.W = int(num_envs), int(image_size), int(image_size)
         self.actions = list(actions)
         self.max_episode_steps = int(max_episode_steps)
@@ -177,7 +184,7 @@ class VectorContextualMOSTED:
             self.torch_gen = torch.Generator(device=self.device)
             self.torch_gen.manual_seed(int(self.np_rng.integers(0, 2 ** 62)))
         frames, coords = synapse.generate_batch_torch(self.B, self.H, self.W, self.device, self.torch_gen)
-        self.synapses = [synapse.Synapse(None, c) for c in coords]
+        self.synapses = [synapse.Synapse(frame=np.zeros((0, 0)), coords=c) for c in coords]
         self._truths = rewards.pad_coords(coords)           # padded once per structure for the batched F1 matching
         self.frames = frames                                   # molecule maps of the current synapses (device, int32)
         cells = -(-self.H // synapse.CELL) * -(-self.W // synapse.CELL)
@@ -236,11 +243,12 @@ class VectorContextualMOSTED:
         self.episode_memory["mo_objs"].append(mo_objs)
         self.episode_memory["actions"].append(action)
 
+        invalid = np.isnan(mo_objs).any(axis=1)
+        if invalid.any() and self.on_invalid == "raise" and self.normalize_observations:
+            # the reference's Normalizer raises TypeError on a None objective (SURVEY App. C "edge cases")
+            raise TypeError("unsupported operand type(s) for -: 'NoneType' and 'int' (SNR objective is None)")
         obs = []
         for a, mo in zip(self.episode_memory["actions"], self.episode_memory["mo_objs"]):
-            if np.isnan(mo).any() and self.normalize_observations:
-                # the reference's Normalizer raises TypeError on a None objective (SURVEY App. C "edge cases")
-                raise TypeError("unsupported operand type(s) for -: 'NoneType' and 'int' (SNR objective is None)")
             obs.append(self.action_normalizer(a) if self.normalize_observations else a)
             obs.append(self.obj_normalizer(mo) if self.normalize_observations else mo)
         obs = np.concatenate(obs, axis=1)
@@ -255,7 +263,8 @@ class VectorContextualMOSTED:
         reward = f1 * self.scale_nanodomain_reward
         self.episode_memory["reward"].append(reward)
         info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,
-                "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "f1-score": f1, "nanodomains-coords": coords}
+                "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "f1-score": f1, "nanodomains-coords": coords,
+                "invalid": invalid}
         return (img, obs.astype(np.float32)), reward, done, np.zeros(self.B, dtype=bool), info
 
     def _next_state(self):
@@ -293,8 +302,10 @@ class ContextualSTEDMultiObjectivesEnv:
 
     def __init__(self, bleach_sampling="constant", actions=("p_sted",), max_episode_steps=10, scale_nanodomain_reward=1.0,
                  normalize_observations=True, **kwargs):
-        self.vec = self.vector_cls(1, bleach_sampling, actions, max_episode_steps, scale_nanodomain_reward,
-                                   normalize_observations, **kwargs)
+        kwargs.setdefault("on_invalid", "raise")             # one environment: fail like the reference does
+        self.vec = self.vector_cls(1, bleach_sampling=bleach_sampling, actions=actions, max_episode_steps=max_episode_steps,
+                                   scale_nanodomain_reward=scale_nanodomain_reward,
+                                   normalize_observations=normalize_observations, **kwargs)
         self.action_space, self.observation_space = self.vec.action_space, self.vec.observation_space
         self.actions = self.vec.actions
         self.spec = SimpleNamespace(id=None, max_episode_steps=max_episode_steps)
@@ -432,6 +443,7 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
 
     def __init__(self, num_envs=1, bleach_sampling="constant", actions=("p_sted", "p_ex", "pdt"), max_episode_steps=30,
                  max_count_rate=20e6, negative_reward=-10.0, image_size=96, **kw):
+        kw.pop("scale_nanodomain_reward", None)
         super().__init__(num_envs, bleach_sampling, actions, max_episode_steps, image_size=image_size, compute_f1=False, **kw)
         vec = 1 + (len(OBJ_NAMES) + len(self.actions)) * self.max_episode_steps
         self.observation_space = Tuple((Box(0, 2 ** 16, shape=(self.H, self.W, 3), dtype=np.uint16),
@@ -496,10 +508,11 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
         res = rewards.resolution(sted)
         mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)
-        if np.isnan(mo_objs).any():
+        invalid = np.isnan(mo_objs).any(axis=1)
+        if invalid.any() and self.on_invalid == "raise":
             raise TypeError("SNR objective is None (negative signal ratio): the reference fails here as well")
-        scores, _, _ = self.articulator.articulate(mo_objs, use_sigmoid=False)
-        reward = scores.ravel().astype(np.float64)
+        scores, _, _ = self.articulator.articulate(np.nan_to_num(mo_objs), use_sigmoid=False)
+        reward = np.where(invalid, np.nan, scores.ravel().astype(np.float64))
         count_rate = sted.amax(dim=(1, 2)).cpu().numpy() / pdt
         reward = np.where(count_rate > self.max_count_rate, self.negative_reward, reward)
 
@@ -510,7 +523,8 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         self.episode_memory["reward"].append(reward)
         info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,
                 "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "sample": list(self.groups),
-                "conf_params": [{"pdt": defaults.PDT, "p_ex": float(p), "p_sted": 0.0} for p in self.conf_p_ex]}
+                "conf_params": [{"pdt": defaults.PDT, "p_ex": float(p), "p_sted": 0.0} for p in self.conf_p_ex],
+                "invalid": invalid}
         obs = [(self.conf_p_ex / defaults.P_EX)[:, None]]
         for a, mo in zip(self.episode_memory["actions"], self.episode_memory["mo_objs"]):
             obs.append(self.action_normalizer(a) if self.normalize_observations else a)
@@ -545,16 +559,28 @@ REGISTRY = {
 }
 
 
+class PreferenceCountRateScaleSTEDMultiObjectivesEnv(ContextualSTEDMultiObjectivesEnv):
+    """Single-environment view of ``VectorPreferenceCountRateMOSTED``
+    (``gym_sted/envs/preference_sted_env.py:205-323``; id ``PreferenceCountRateMOSTED-hard-v0``)."""
+
+    vector_cls = VectorPreferenceCountRateMOSTED
+
+    def __init__(self, bleach_sampling="constant", actions=("p_sted", "p_ex", "pdt"), max_episode_steps=30, **kwargs):
+        super().__init__(bleach_sampling=bleach_sampling, actions=actions, max_episode_steps=max_episode_steps, **kwargs)
+
+
+_SINGLE = {"preference": PreferenceCountRateScaleSTEDMultiObjectivesEnv, "sequence": SequenceSTEDMultiObjectivesEnv}
+_VECTOR = {"preference": VectorPreferenceCountRateMOSTED, "sequence": VectorSequenceMOSTED}
+
+
 def make(env_id: str, **overrides):
     """``gym.make`` for the registered ids (accepts the ``gym_sted:`` prefix)."""
     key = env_id.split(":")[-1]
     if key not in REGISTRY:
         raise KeyError(f"unknown environment id {env_id!r}; known: {sorted(REGISTRY)}")
     entry = REGISTRY[key]
-    if entry.get("cls") == "preference":
-        raise NotImplementedError("PreferenceCountRateMOSTED is provided as a vector env: use make_vec(id, num_envs)")
-    cls = SequenceSTEDMultiObjectivesEnv if entry.get("cls") == "sequence" else ContextualSTEDMultiObjectivesEnv
-    env = cls(max_episode_steps=entry["max_episode_steps"], **{**entry["kwargs"], **overrides})
+    cls = _SINGLE.get(entry.get("cls"), ContextualSTEDMultiObjectivesEnv)
+    env = cls(**{"max_episode_steps": entry["max_episode_steps"], **entry["kwargs"], **overrides})
     env.spec = SimpleNamespace(id=key, max_episode_steps=entry["max_episode_steps"])
     return env
 
@@ -563,5 +589,39 @@ def make_vec(env_id: str, num_envs: int, **overrides):
     key = env_id.split(":")[-1]
     entry = REGISTRY[key]
     kwargs = {"max_episode_steps": entry["max_episode_steps"], **entry["kwargs"], **overrides}
-    cls = {"preference": VectorPreferenceCountRateMOSTED, "sequence": VectorSequenceMOSTED}.get(entry.get("cls"), VectorContextualMOSTED)
-    return cls(num_envs, **kwargs)
+    return _VECTOR.get(entry.get("cls"), VectorContextualMOSTED)(num_envs, **kwargs)
+
+
+def register_with_gym(namespace=None):
+    """``register()`` every id of ``REGISTRY`` with ``gymnasium`` or ``gym``, whichever imports
+    (``gym_sted/__init__.py:522-531,587-674,822-909``), onto the single-environment classes of this module.
+    Returns the list of registered ids (empty when neither package is installed).  Ids are registered as
+    ``<id>`` under the entry point ``gym_sted_b200.envs:<Class>`` so ``gym.make("ContextualMOSTED-easy-v0")`` or
+    ``gym.make("gym_sted_b200.envs:ContextualMOSTED-easy-v0")`` resolves to the CUDA path."""
+    import importlib
+    registration = None
+    for name in ("gymnasium", "gym"):
+        try:
+            registration = importlib.import_module(name + ".envs.registration")
+            break
+        except ImportError:
+            continue
+    if registration is None:
+        return []
+    register, registry = registration.register, registration.registry
+    done = []
+    for key, entry in REGISTRY.items():
+        cls = _SINGLE.get(entry.get("cls"), ContextualSTEDMultiObjectivesEnv)
+        full = f"{namespace}/{key}" if namespace else key
+        if full in registry:
+            continue
+        register(id=full, entry_point=f"{__name__}:{cls.__name__}", max_episode_steps=entry["max_episode_steps"],
+                 kwargs=dict(entry["kwargs"]))
+        done.append(full)
+    return done
+
+
+try:                                        # same side effect as ``import gym_sted``: the ids exist after the import
+    register_with_gym()
+except Exception:                           # an incompatible gym must not break the package
+    pass

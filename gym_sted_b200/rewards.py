@@ -5,9 +5,10 @@
 * ``resolution``             image-decorrelation resolution (``objectives.py:121-291``): apodisation,
   FFT, high-pass sweeps and ring sums run batched on the GPU in float64 (torch tensors; the ring sums are
   prefix sums in radius-sorted pixel order); only the 50-point peak searches run on the host.
-* ``nanodomain_f1``          detection + F1 (``objectives.py:404-430``, ``rewards/utils.py:6-49``):
-  **host side in this round** (scipy.ndimage + MINPACK ``leastsq`` + Hungarian matching, per
-  environment) — the device version is the next item of this row.
+* ``nanodomain_f1``          detection + F1 (``objectives.py:404-430``, ``rewards/utils.py:6-49``): candidates
+  (``nanodomain_kernel``), Gaussian-fit validation (``gaussfit_kernel``, MINPACK restated) and the matching +
+  F1 (``f1_match_kernel``: maximum matching of the pairs closer than the threshold, which is what the
+  reference's Hungarian solution counts) all run on the device; one packed device->host read per step.
 * ``PrefNet`` / ``PreferenceArticulator``  the 3-10-10-1 ReLU MLP of ``gym_sted/prefnet`` on the device.
 """
 from __future__ import annotations
@@ -112,7 +113,7 @@ def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, 
 
 
 # ------------------------------------------------------------------------------------------------
-# a9: nanodomain detection + F1 (host side in this round)
+# a9: nanodomain detection + F1
 # ------------------------------------------------------------------------------------------------
 def _gauss_taps(sigma=0.5, truncate=4.0):
     """scipy.ndimage._filters._gaussian_kernel1d (order 0): the three distinct taps of the 5-tap kernel."""
@@ -151,8 +152,8 @@ def _candidates_device(sted: torch.Tensor):
 def _check_capacity(flags: np.ndarray):
     if flags.any():
         b = int(np.flatnonzero(flags)[0])
-        raise _lib.StedError(f"nanodomain_kernel capacity exceeded for image {b} (flags={int(flags[b])}: bit0 >4096 mask pixels, "
-                             f"bit1 >64 maxima in one component, bit3 >256 peaks)")
+        raise _lib.StedError(-4, f"nanodomain_kernel capacity exceeded for image {b} (flags={int(flags[b])}: bit0 >4096 mask "
+                                 f"pixels, bit1 >64 maxima in one component, bit3 >256 peaks)")
 
 
 def nanodomain_candidates(sted: torch.Tensor):
