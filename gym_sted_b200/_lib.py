@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("STED_B200_LIB", os.path.join(_HERE, "libsted_b200.so"))
 
-STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH, STED_NO_DETECT, STED_HOST_U16 = 1, 2, 4, 8, 16
+STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH, STED_NO_DETECT, STED_HOST_U16, STED_FRAME_MOLECULES = 1, 2, 4, 8, 16, 32
 STED_TAB_E, STED_TAB_ET, STED_TAB_CH, STED_TAB_RS, STED_TAB_E2, STED_TABLES = 0, 1, 2, 3, 4, 8
 STED_MAX_K = 63
 
@@ -54,6 +54,15 @@ SIGNATURES = {
     "sted_detect": (_i, [_vp, _vp, _i, _i, _i, _u32, ctypes.POINTER(StedDetectorParams), _d, _u64, _u64, _i64, _vp]),
     "sted_acquire_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _u32,
                                ctypes.POINTER(StedDetectorParams), _u64, _u64, _i64, _vp, _vp]),
+    "sted_session_create": (_i, [_i, _i, _i, _i, _vp, _i, ctypes.POINTER(_vp)]),
+    "sted_session_destroy": (_i, [_vp]),
+    "sted_session_set_fluorophores": (_i, [_vp, _vp]),
+    "sted_session_upload": (_i, [_vp, _vp, _u32, _u64]),
+    "sted_session_acquire": (_i, [_vp, _vp, _vp, _vp, _u32, ctypes.POINTER(StedDetectorParams), _d, _u64, _u64, _i64, _vp,
+                                  _vp]),
+    "sted_session_download": (_i, [_vp, _vp, _u32]),
+    "sted_session_sync": (_i, [_vp, ctypes.POINTER(_i64)]),
+    "sted_session_device_map": (_i, [_vp, ctypes.POINTER(_vp)]),
     "sted_sample_poisson": (_i, [_vp, _i64, _u64, _u64, _vp, _vp]),
     "sted_sample_binomial": (_i, [_vp, _vp, _i64, _u64, _u64, _vp, _vp]),
     "sted_philox4x32_10": (None, [ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),
@@ -61,6 +70,9 @@ SIGNATURES = {
     "sted_nanodomain_candidates": (_i, [_vp, _i, _i, _i, ctypes.POINTER(_d), _i64, _d, _vp, _vp, _vp, _vp, _vp]),
     "sted_decorrelation_resolution": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _d, _d, _d, _d, _vp, _vp]),
     "sted_gaussfit_validate": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _d, _vp, _vp, _vp]),
+    "sted_f1_match": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),
+    "sted_apodize_for_fft": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sted_spectrum_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sted_lmfit_test": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp]),
     "sted_debug_phase_cycles": (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     "sted_fma_peak": (_i, [ctypes.POINTER(_d), _vp]),

@@ -268,6 +268,8 @@ class Microscope:
                 flags |= _lib.STED_SAMPLE_BLEACH
         if self.detector.noise:
             flags |= _lib.STED_SAMPLE_PHOTONS
+        if float(np.sum(whole)) != float(np.sum(whole[rs, cs])):
+            flags |= _lib.STED_FRAME_MOLECULES          # the caller placed molecules in the K//2 frame
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 31 - 1))
         self._acq_counter += 1

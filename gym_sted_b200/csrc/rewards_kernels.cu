@@ -747,3 +747,197 @@ extern "C" int sted_gaussfit_validate(const float* sted_dev, int B, int H, int W
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }
+
+// =============================================================================================================
+// F1 of the nanodomain detections (gym_sted/rewards/objectives.py:425-430): metrics.CentroidDetectionError(truth,
+// guess, threshold, algorithm="hungarian").f1_score.  The Hungarian solution on the cost matrix with the pairs at
+// distance >= threshold priced out assigns as many allowed pairs as possible (one forbidden pair costs more than all
+// allowed ones together), so TP is the size of a MAXIMUM MATCHING of the bipartite graph "truth i - guess j closer than
+// the threshold"; FP and FN are what is left on either side.  Coordinates are integer pixels, so the distance test is
+// exact in integers (threshold^2 as a double compared with an integer sum of squares).  One thread per image runs
+// Kuhn's augmenting-path algorithm with an explicit stack (graphs are tiny and very sparse: <= 9 integer points lie
+// within 2 px of a truth); F1 = 2PR/(P+R+1e-6), P = TP/(TP+FP+1e-6), R = TP/(TP+FN+1e-6) in float64, numpy's order.
+// =============================================================================================================
+namespace {
+
+constexpr int F1_MAXN = 512;         // truths and kept guesses per image
+
+__global__ void __launch_bounds__(32) f1_match_kernel(const int* __restrict__ peaks, const int* __restrict__ npeaks,
+                                                       const unsigned char* __restrict__ valid, int maxp,
+                                                       const int* __restrict__ truth, const int* __restrict__ ntruth, int maxt,
+                                                       double thr2, int* __restrict__ counts, double* __restrict__ f1,
+                                                       int* __restrict__ flags) {
+    __shared__ short gy[F1_MAXN], gx[F1_MAXN], ty[F1_MAXN], tx[F1_MAXN];
+    __shared__ short match_g[F1_MAXN];               // truth matched to guess g, -1 if free
+    __shared__ short stack_t[F1_MAXN], stack_j[F1_MAXN], stack_g[F1_MAXN];
+    __shared__ unsigned visited[F1_MAXN / 32];
+    __shared__ int s_ng;
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int np_ = min(npeaks[b], maxp), nt = min(ntruth[b], maxt);
+    // compact the kept guesses (order preserved: warp-wide ballots)
+    if (lane == 0) s_ng = 0;
+    __syncwarp();
+    bool overflow = nt > F1_MAXN;
+    for (int base = 0; base < np_; base += 32) {
+        const int k = base + lane;
+        const bool keep = k < np_ && (!valid || valid[(size_t)b * maxp + k]);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int at = s_ng + __popc(m & ((1u << lane) - 1));
+        if (keep && at < F1_MAXN) {
+            gy[at] = (short)peaks[((size_t)b * maxp + k) * 2];
+            gx[at] = (short)peaks[((size_t)b * maxp + k) * 2 + 1];
+        }
+        __syncwarp();
+        if (lane == 0) s_ng += __popc(m);
+        __syncwarp();
+    }
+    const int ng_all = s_ng;
+    overflow |= ng_all > F1_MAXN;
+    const int ng = min(ng_all, F1_MAXN), ntc = min(nt, F1_MAXN);
+    for (int i = lane; i < ntc; i += 32) {
+        ty[i] = (short)truth[((size_t)b * maxt + i) * 2];
+        tx[i] = (short)truth[((size_t)b * maxt + i) * 2 + 1];
+    }
+    for (int i = lane; i < ng; i += 32) match_g[i] = -1;
+    __syncwarp();
+    if (lane != 0) return;
+    auto close_pair = [&](int t, int g) {
+        const int dy = (int)ty[t] - (int)gy[g], dx = (int)tx[t] - (int)gx[g];
+        return (double)(dy * dy + dx * dx) < thr2;
+    };
+    int tp = 0;
+    for (int t0 = 0; t0 < ntc; ++t0) {
+        for (int i = 0; i < (ng + 31) / 32; ++i) visited[i] = 0u;
+        // iterative DFS: frame d tries guesses stack_j[d].. for truth stack_t[d]; stack_g[d] = guess taken to descend
+        int d = 0;
+        stack_t[0] = (short)t0; stack_j[0] = 0;
+        bool found = false;
+        while (d >= 0) {
+            const int t = stack_t[d];
+            int j = stack_j[d];
+            bool descended = false;
+            for (; j < ng; ++j) {
+                if ((visited[j >> 5] >> (j & 31)) & 1u) continue;
+                if (!close_pair(t, j)) continue;
+                visited[j >> 5] |= 1u << (j & 31);
+                stack_g[d] = (short)j;
+                if (match_g[j] < 0) { found = true; break; }
+                stack_j[d] = (short)(j + 1);
+                ++d;
+                stack_t[d] = match_g[j]; stack_j[d] = 0;
+                descended = true;
+                break;
+            }
+            if (found) break;
+            if (!descended) --d;                       // dead end: back to the caller, which continues after its guess
+        }
+        if (found) {
+            for (int k = d; k >= 0; --k) match_g[stack_g[k]] = stack_t[k];   // flip the augmenting path
+            ++tp;
+        }
+    }
+    const int fp = ng - tp, fn = ntc - tp;
+    counts[b * 3] = tp; counts[b * 3 + 1] = fp; counts[b * 3 + 2] = fn;
+    const double dtp = (double)tp, dfp = (double)fp, dfn = (double)fn;
+    const double prec = dtp / (dtp + dfp + 1e-6), rec = dtp / (dtp + dfn + 1e-6);
+    f1[b] = 2.0 * prec * rec / (prec + rec + 1e-6);
+    if (flags) flags[b] = overflow ? 1 : 0;
+}
+
+// ---- apodisation + centring in front of the FFT (objectives.py:150-160): window * (image - mean) + mean rounded to
+// float32 like the reference's astype(float32), cropped to odd sides, ifftshift-ed so that a plain forward FFT
+// followed by the gather below equals fftshift(fftn(fftshift(image))).  The mean of an integer image is exact (integer
+// sum / N), whatever the summation order.
+constexpr int AP_THREADS = 256;
+
+__global__ void __launch_bounds__(AP_THREADS) apodize_kernel(const float* __restrict__ img, const double* __restrict__ window,
+                                                            int H, int W, int Hc, int Wc, double2* __restrict__ out) {
+    __shared__ long long s_part[AP_THREADS / 32];
+    __shared__ double s_mean;
+    const int b = blockIdx.x;
+    const float* im = img + (size_t)b * H * W;
+    long long acc = 0;
+    for (int i = threadIdx.x; i < H * W; i += AP_THREADS) acc += (long long)rintf(im[i]);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < AP_THREADS / 32; ++i) t += s_part[i];
+        s_mean = (double)t / (double)(H * W);
+    }
+    __syncthreads();
+    const double mean = s_mean;
+    double2* o = out + (size_t)b * Hc * Wc;
+    const int sy = Hc / 2, sx = Wc / 2;                  // fftshift of an odd length n moves index i to (i + n/2) % n
+    for (int i = threadIdx.x; i < Hc * Wc; i += AP_THREADS) {
+        const int y = i / Wc, x = i - y * Wc;
+        const double v = (double)(float)(window[y * W + x] * ((double)im[y * W + x] - mean) + mean);
+        const int yd = (y + sy) % Hc, xd = (x + sx) % Wc;
+        o[yd * Wc + xd] = make_double2(v, 0.0);
+    }
+}
+
+// ---- after the FFT: centre the spectrum, take the pixels in radius order, zero those at R >= 1, and form the
+// phase-only copy Ik/|Ik| (0 where |Ik| = 0 or not finite) — the two inputs of decorr_kernel.
+__global__ void __launch_bounds__(256) spectrum_gather_kernel(const double2* __restrict__ spec, const long long* __restrict__ order,
+                                                             int N, int n_inside, int Hc, int Wc, double2* __restrict__ ik,
+                                                             double2* __restrict__ ikn) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double2 v = make_double2(0.0, 0.0), n = make_double2(0.0, 0.0);
+    if (i < n_inside) {
+        const int src = (int)order[i];                   // index in the centred (fftshift-ed) spectrum
+        const int y = src / Wc, x = src - y * Wc;
+        const int ys = (y + Hc - Hc / 2) % Hc, xs = (x + Wc - Wc / 2) % Wc;      // where the plain FFT holds it
+        v = spec[(size_t)b * N + (size_t)ys * Wc + xs];
+        const double mag = hypot(v.x, v.y);              // numpy.abs of a complex number
+        if (mag > 0.0) {
+            n = make_double2(v.x / mag, v.y / mag);
+            if (!(isfinite(n.x) && isfinite(n.y))) n = make_double2(0.0, 0.0);
+        }
+    }
+    ik[(size_t)b * N + i] = v;
+    ikn[(size_t)b * N + i] = n;
+}
+
+}  // namespace
+
+extern "C" int sted_f1_match(const int32_t* peaks_dev, const int32_t* npeaks_dev, const uint8_t* valid_dev, int max_peaks,
+                             const int32_t* truth_dev, const int32_t* ntruth_dev, int max_truth, int B, double threshold,
+                             int32_t* counts_dev, double* f1_dev, int32_t* flags_dev, void* stream) {
+    if (!peaks_dev || !npeaks_dev || !truth_dev || !ntruth_dev || !counts_dev || !f1_dev) return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || max_peaks <= 0 || max_truth <= 0) return fail(STED_EINVAL, "B, max_peaks, max_truth must be positive");
+    int rc = check_device();
+    if (rc) return rc;
+    f1_match_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(peaks_dev, npeaks_dev, valid_dev, max_peaks, truth_dev, ntruth_dev, max_truth,
+                                                       threshold * threshold, counts_dev, f1_dev, flags_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+extern "C" int sted_apodize_for_fft(const float* image_dev, const double* window_dev, int B, int H, int W, int Hc, int Wc,
+                                    void* out_dev, void* stream) {
+    if (!image_dev || !window_dev || !out_dev) return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0 || Hc <= 0 || Wc <= 0 || Hc > H || Wc > W) return fail(STED_EINVAL, "bad shape");
+    int rc = check_device();
+    if (rc) return rc;
+    apodize_kernel<<<B, AP_THREADS, 0, (cudaStream_t)stream>>>(image_dev, window_dev, H, W, Hc, Wc, (double2*)out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+extern "C" int sted_spectrum_gather(const void* spectrum_dev, const int64_t* order_dev, int B, int Hc, int Wc, int n_inside,
+                                    void* ik_dev, void* ikn_dev, void* stream) {
+    if (!spectrum_dev || !order_dev || !ik_dev || !ikn_dev) return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || Hc <= 0 || Wc <= 0 || n_inside < 0 || n_inside > Hc * Wc) return fail(STED_EINVAL, "bad shape");
+    int rc = check_device();
+    if (rc) return rc;
+    const int N = Hc * Wc;
+    dim3 grid((N + 255) / 256, B);
+    spectrum_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const double2*)spectrum_dev, (const long long*)order_dev, N, n_inside,
+                                                                  Hc, Wc, (double2*)ik_dev, (double2*)ikn_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}

@@ -461,12 +461,14 @@ __device__ __forceinline__ float reduce_scatter(float (&a)[CT], int lane) {
     return a[0];
 }
 
-// workspace of the stochastic scan: [4 ints status][B*H ints cursor][B*H+1 ints offsets][cap events]
+// workspace of the stochastic scan:
+//   [4 ints status][B*H ints cursor][B*H+1 (+3 pad) ints offsets][cap events][cap staged (key, event) pairs]
 struct BleachWs {
-    int* status;         // [0] = events dropped because the workspace was too small
+    int* status;         // [0] = events dropped because the workspace was too small, [1] = staging cursor
     int* cnt;            // [B*H] events per (env, scan row); reused as fill cursor
     int* off;            // [B*H + 1] exclusive prefix sums
-    uint32_t* ev;        // [cap] events  x | u<<12 | a<<18
+    uint32_t* ev;        // [cap] events  x | u<<12 | a<<18 | (scan row & 255)<<24, bucketed by (env, scan row)
+    uint2* stage;        // [cap] (env*H + scan row, event) in generation order (fused presample)
     unsigned long long cap;
 };
 
@@ -479,8 +481,11 @@ struct BleachWs {
 // Cumulative pass hazards come from QQ[v][u] = sum_{u'>=u} CH[u'][v]: for a pixel whose taps are clipped to
 // [lo,hi] the hazard of the passes u..u_hi is G(u) - G(u_hi+1) with G(u) = QQ[lo][u] - QQ[hi+1][u].
 constexpr int PS_THREADS = 256, PS_CHUNK = 4096, PS_ITEMS = 2048, PS_PER = PS_CHUNK / PS_THREADS;
-
-template <bool FILL>
+// MODE 0: count the events of each (env, scan row).  MODE 1: regenerate them and store them in their row bucket.
+// MODE 2 (the default path): ONE pass — every death is drawn once, written with its bucket key to a staging area
+// (the chunk reserves room for all its molecules with one atomic) and counted; scatter_events_kernel then moves the
+// staged events into their buckets.  No second Philox pass.
+template <int MODE>
 __global__ void __launch_bounds__(PS_THREADS, 4) presample_kernel(const AcqParams P, const BleachWs ws) {
     const int K = P.K, KP = P.KP, H = P.H, W = P.W, Wp = P.Wp;
     extern __shared__ __align__(128) float smem[];
@@ -489,6 +494,8 @@ __global__ void __launch_bounds__(PS_THREADS, 4) presample_kernel(const AcqParam
     uint32_t* items = reinterpret_cast<uint32_t*>(sQQ + (K + 1) * KP);      // [PS_ITEMS] pixel | sub<<12 | m<<24
     __shared__ int s_warp[PS_THREADS / 32];
     __shared__ int s_total;
+    __shared__ unsigned long long s_stage_base;
+    __shared__ unsigned s_stage_n, s_stage_cap;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const float4* c4 = reinterpret_cast<const float4*>(P.tables + ((size_t)b * STED_TABLES + STED_TAB_CH) * K * KP);
@@ -507,15 +514,35 @@ __global__ void __launch_bounds__(PS_THREADS, 4) presample_kernel(const AcqParam
     const uint32_t env = P.env_base + (uint32_t)b;
     const int base = blockIdx.x * PS_CHUNK;
 
+    // region holding molecules: the H x W region of interest, or the whole padded map with STED_FRAME_MOLECULES
+    const bool whole = (P.flags & STED_FRAME_MOLECULES) != 0;
+    const int RW = whole ? Wp : W, RH = whole ? P.Hp : H, ro = whole ? 0 : p;
     int cnt[PS_PER];
-    int mine = 0;
+    int mine = 0, molecules = 0;
 #pragma unroll
     for (int j = 0; j < PS_PER; ++j) {
         const int idx = base + j * PS_THREADS + tid;
         int n = 0;
-        if (idx < H * W) n = (int)__ldg(din + (size_t)(p + idx / W) * P.Wpitch + p + idx % W);
+        if (idx < RH * RW) n = (int)__ldg(din + (size_t)(ro + idx / RW) * P.Wpitch + ro + idx % RW);
+        if (n > 32767) { n = 32767; atomicAdd(&ws.status[0], 1); }   // 12-bit sub-stream index x 8 molecules: reported as dropped
         cnt[j] = n > 0 ? n : 0;
         mine += (cnt[j] + 7) >> 3;
+        molecules += cnt[j];
+    }
+    if (MODE == 2) {                                     // room for every molecule of this chunk, one atomic
+        for (int o = 16; o; o >>= 1) molecules += __shfl_xor_sync(0xffffffffu, molecules, o);
+        if (tid == 0) s_stage_n = 0;
+        __syncthreads();
+        if (lane == 0 && molecules) atomicAdd(&s_stage_n, (unsigned)molecules);
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned want = s_stage_n;
+            const unsigned long long at = want ? atomicAdd(reinterpret_cast<unsigned long long*>(ws.status + 2), (unsigned long long)want) : 0ull;
+            s_stage_base = at;
+            s_stage_cap = at >= ws.cap ? 0u : (unsigned)min((unsigned long long)want, ws.cap - at);
+            s_stage_n = 0;
+        }
+        __syncthreads();
     }
     // exclusive scan of the per-thread item counts over the CTA
     int incl = mine;
@@ -549,7 +576,7 @@ __global__ void __launch_bounds__(PS_THREADS, 4) presample_kernel(const AcqParam
         for (int q = tid; q < n_items; q += PS_THREADS) {
             const uint32_t it = items[q];
             const int idx = base + (int)(it & 0xFFFu), sub = (it >> 12) & 0xFFF, m = it >> 24;
-            const int y = p + idx / W, x = p + idx % W;
+            const int y = ro + idx / RW, x = ro + idx % RW;
             const int lo = max(0, x - W + 1), hi = min(K - 1, x);        // taps that ever visit this column
             const int u_hi = min(K - 1, y), u_lo = max(0, y - (H - 1));   // passes, visited from u_hi down to u_lo
             const float* qa = sQQ + lo * KP;
@@ -570,7 +597,7 @@ __global__ void __launch_bounds__(PS_THREADS, 4) presample_kernel(const AcqParam
                     if (qa[mid] - qb[mid] >= thr) a = mid; else z = mid - 1;
                 }
                 const int u = a, r = y - u;
-                if (!FILL) {
+                if (MODE == 0) {
                     atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
                 } else {
                     // tap: largest v in [lo,hi] whose suffix hazard still covers the in-pass position
@@ -582,14 +609,42 @@ __global__ void __launch_bounds__(PS_THREADS, 4) presample_kernel(const AcqParam
                         const int mid = (a2 + z2 + 1) >> 1;
                         if (ch[mid] >= thr2) a2 = mid; else z2 = mid - 1;
                     }
-                    const unsigned long long slot = (unsigned long long)ws.off[(size_t)b * H + r] +
-                                                    (unsigned long long)atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
-                    if (slot < ws.cap) ws.ev[slot] = (uint32_t)x | ((uint32_t)u << 12) | ((uint32_t)a2 << 18);
-                    else atomicAdd(&ws.status[0], 1);
+                    const uint32_t ev = (uint32_t)x | ((uint32_t)u << 12) | ((uint32_t)a2 << 18) | ((uint32_t)(r & 255) << 24);
+                    if (MODE == 1) {
+                        const unsigned long long slot = (unsigned long long)ws.off[(size_t)b * H + r] +
+                                                        (unsigned long long)atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
+                        if (slot < ws.cap) ws.ev[slot] = ev;
+                        else atomicAdd(&ws.status[0], 1);
+                    } else {
+                        const unsigned at = atomicAdd(&s_stage_n, 1u);
+                        if (at < s_stage_cap) {
+                            ws.stage[s_stage_base + at] = make_uint2((uint32_t)(b * H + r), ev);
+                            atomicAdd(&ws.cnt[(size_t)b * H + r], 1);
+                        } else {
+                            atomicAdd(&ws.status[0], 1);
+                        }
+                    }
                 }
             }
         }
         __syncthreads();
+    }
+    if (MODE == 2) {                                     // unused tail of this chunk's reservation: mark it empty
+        const unsigned used = min(s_stage_n, s_stage_cap);
+        for (unsigned i = used + tid; i < s_stage_cap; i += PS_THREADS) ws.stage[s_stage_base + i] = make_uint2(0xFFFFFFFFu, 0u);
+    }
+}
+
+// staged (key, event) pairs -> row buckets (counting sort, third step; off[] holds the bucket starts, cnt[] the cursors)
+__global__ void __launch_bounds__(256) scatter_events_kernel(const BleachWs ws) {
+    unsigned long long n = *reinterpret_cast<const unsigned long long*>(ws.status + 2);
+    if (n > ws.cap) n = ws.cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint2 e = ws.stage[i];
+        if (e.x == 0xFFFFFFFFu) continue;
+        const unsigned long long slot = (unsigned long long)ws.off[e.x] + (unsigned long long)atomicAdd(&ws.cnt[e.x], 1);
+        ws.ev[slot] = e.y;
     }
 }
 
@@ -850,6 +905,203 @@ __global__ void __launch_bounds__(S_THREADS, STOCH ? 3 : 2) sweep_kernel(const A
 }
 
 // ------------------------------------------------------------------------------------------
+// K3b: the stochastic scan, second generation (sweep2_kernel).
+//
+// Same arithmetic as sweep_kernel<.., true> — dense gather of every scan row against the row-start counts, replay of
+// that row's pre-drawn deaths — reorganised around three measurements of round 1 (profiles/r01_summary.md):
+//  * the grid was 512 CTAs on 444 slots (the second wave 15 % full): work items are now (environment, column strip,
+//    RANGE OF SCAN ROWS).  A range can start anywhere because the state of the map at scan row r0 is known in advance:
+//    the initial counts minus the deaths of the K-1 scan rows before r0 that hit band rows >= r0 (events carry the low
+//    byte of their scan row for this).  Four times as many, four times shorter CTAs leave a tail of a few percent;
+//  * replaying a row cost as much as half of its gather, on the critical path, in CAS-free but latency-bound atomics:
+//    only the ring decrements (one atomic per death) stay between two gathers; the intensity corrections — which touch
+//    nothing the next gather reads — are done by two extra warps WHILE the eight gather warps work on the next row;
+//  * three CTA-wide barriers per row: the ring has K+1 slots, so the row entering the band is installed in the slot
+//    of the row retired one iteration earlier and the retire/install step shares a phase with the decrements: two
+//    barriers per row.
+// ------------------------------------------------------------------------------------------
+constexpr int S2_GATHER = 256, S2_AUX = 64, S2_THREADS = S2_GATHER + S2_AUX;
+
+template <int KT, int CT>
+__global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P, const BleachWs ws, const int RR) {
+    constexpr int TC = 8 * CT;
+    const int K = KT ? KT : P.K;
+    const int KP = KT ? STED_KPITCH(KT) : P.KP;
+    const int NS = K + 1;                     // ring slots
+    const int PR = sweep_pitch(TC, KP);
+    const int span = TC + K - 1;
+
+    extern __shared__ __align__(128) float smem[];
+    float* ring = smem;                       // [K+1][PR] band of the molecule map (integer counts)
+    float* sWt = ring + NS * PR;              // [K][KP]   effective PSF E
+    float* sI = sWt + K * KP;                 // [2][TC]   dense row intensities (even / odd scan rows)
+    float* sScale = sI + 2 * TC;              // [2][TC]   2^30 / sI  (fixed-point scale of the corrections)
+    int* sCorr = reinterpret_cast<int*>(sScale + 2 * TC);    // [2][TC] sum of removed taps, fixed point
+
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.x * TC;
+    const int r0 = blockIdx.y * RR;
+    const int r1 = min(P.H, r0 + RR);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool aux = tid >= S2_GATHER;
+    const int at = tid - S2_GATHER;           // index among the auxiliary threads
+    const int W = P.W, H = P.H;
+    const float* din = P.din + (size_t)b * P.Hp * P.Wpitch;
+    float* dout = P.dout + (size_t)b * P.Hp * P.Wpitch;
+    const int* row_off = ws.off + (size_t)b * H;
+
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP);
+        for (int i = tid; i < K * KP / 4; i += S2_THREADS) reinterpret_cast<float4*>(sWt)[i] = __ldg(w4 + i);
+    }
+    if (tid < 2 * TC) sCorr[tid] = 0;
+
+    // columns of the molecule map this strip writes back (each column has exactly one owner)
+    const int p = K / 2;
+    const int xs = (c0 == 0) ? 0 : c0 + p;
+    const int xe = (c0 + TC >= W) ? P.Wpitch : c0 + TC + p;
+    const int q4 = PR / 4;                    // float4 groups of a ring row
+
+    auto slot_of = [&](const int y) { return (KT ? y % (KT + 1) : y % NS) * PR; };
+    auto fetch_row = [&](const int y, const int g) -> float4 {
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int x = c0 + 4 * g;
+        if (y >= 0 && y < P.Hp && x < P.Wpitch) val = __ldg(reinterpret_cast<const float4*>(din + (size_t)y * P.Wpitch + x));
+        return val;
+    };
+    auto retire_row = [&](const int y, const int g) {
+        const float4 old = *reinterpret_cast<const float4*>(ring + slot_of(y) + 4 * g);
+        const float* po_ = reinterpret_cast<const float*>(&old);
+        const int x = c0 + 4 * g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x + j >= xs && x + j < xe) dout[(size_t)y * P.Wpitch + x + j] = po_[j];
+    };
+    auto clamp_hi = [&](const int v) { return (unsigned long long)v > ws.cap ? (int)ws.cap : v; };
+
+    // band rows r0 .. r0+K-1 as they were BEFORE the scan ...
+    for (int i = tid; i < K * q4; i += S2_THREADS) {
+        const int yy = i / q4, g = i - yy * q4;
+        *reinterpret_cast<float4*>(ring + slot_of(r0 + yy) + 4 * g) = fetch_row(r0 + yy, g);
+    }
+    __syncthreads();
+    // ... minus the deaths of the scan rows before r0 that hit them (scan row r' reaches band rows r' .. r'+K-1)
+    if (r0 > 0) {
+        const int rp = max(0, r0 - (K - 1));
+        const int lo = __ldg(row_off + rp), hi = clamp_hi(__ldg(row_off + r0));
+        for (int q = lo + tid; q < hi; q += S2_THREADS) {
+            const uint32_t ev = __ldg(ws.ev + q);
+            const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F;
+            const int rr = r0 - 1 - (int)(((uint32_t)(r0 - 1) - (ev >> 24)) & 255u);     // scan row of the event
+            const int y = rr + u;
+            if (y >= r0 && xl >= 0 && xl < span) atomicAdd(&ring[slot_of(y) + xl], -1.0f);
+        }
+        __syncthreads();
+    }
+
+    // intensity of scan row r: dense gather minus the taps removed by the deaths of that row (auxiliary warps)
+    auto corrections_and_write = [&](const int r) {
+        const int par = r & 1;
+        const float* sc = sScale + par * TC;
+        int* corr = sCorr + par * TC;
+        const int ev_lo = __ldg(row_off + r), ev_hi = clamp_hi(__ldg(row_off + r + 1));
+        constexpr int EV_LANES = 4, EV_SLOTS = S2_AUX / EV_LANES;
+        const int sub = at % EV_LANES;
+        for (int q = ev_lo + at / EV_LANES; q < ev_hi; q += EV_SLOTS) {
+            const uint32_t ev = __ldg(ws.ev + q);
+            const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F, a = (ev >> 18) & 0x3F;
+            if (xl < 0 || xl >= span) continue;                       // another strip's pixel
+            const float* e = sWt + u * KP;
+            const int v0 = max(max(0, c0 + xl - W + 1), xl - (TC - 1)), v1 = min(a, xl + 1);   // 0 <= xl - v < TC
+#pragma unroll 4
+            for (int v = v0 + sub; v < v1; v += EV_LANES) atomicAdd(&corr[xl - v], __float2int_rn(e[v] * sc[xl - v]));
+        }
+        asm volatile("bar.sync 1, %0;" :: "n"(S2_AUX) : "memory");
+        for (int t = at; t < TC; t += S2_AUX) {
+            if (c0 + t < W) {
+                const float I = fmaxf(sI[par * TC + t] * (1.0f - (float)corr[t] * 9.313225746154785e-10f), 0.f);
+                const size_t o = ((size_t)b * H + r) * W + c0 + t;
+                if (P.intensity) P.intensity[o] = I;
+                P.signal[o] = I;                          // detect_kernel converts to photon counts
+            }
+            corr[t] = 0;
+        }
+        asm volatile("bar.sync 1, %0;" :: "n"(S2_AUX) : "memory");
+    };
+
+    for (int r = r0; r < r1; ++r) {
+        const int par = r & 1;
+        float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (aux) {
+            // ---- auxiliary warps: prefetch the row entering the band, finish the previous row's intensities
+            if (at < q4) pre = fetch_row(r + K < P.Hp ? r + K : -1, at);
+            if (r > r0) corrections_and_write(r - 1);
+        } else {
+            // ---- gather warps: dense gather of scan row r against the row-start counts
+            float acc[CT];
+#pragma unroll
+            for (int j = 0; j < CT; ++j) acc[j] = 0.f;
+            for (int uu = lane; uu < K; uu += 32) {
+                const float* drow = ring + slot_of(r + uu) + CT * warp;
+                const float* erow = sWt + uu * KP;
+                float win[CT + 4];
+#pragma unroll
+                for (int j = 0; j < CT; j += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(drow + j);
+                    win[j] = t.x; win[j + 1] = t.y; win[j + 2] = t.z; win[j + 3] = t.w;
+                }
+                const int nchunk = KP / 4;
+#pragma unroll 5
+                for (int vc = 0; vc < nchunk; ++vc) {
+                    const float4 nw = *reinterpret_cast<const float4*>(drow + CT + 4 * vc);
+                    const float4 e = *reinterpret_cast<const float4*>(erow + 4 * vc);
+                    win[CT] = nw.x; win[CT + 1] = nw.y; win[CT + 2] = nw.z; win[CT + 3] = nw.w;
+#pragma unroll
+                    for (int j = 0; j < CT; ++j) {
+                        acc[j] = fmaf(e.x, win[j], acc[j]);
+                        acc[j] = fmaf(e.y, win[j + 1], acc[j]);
+                        acc[j] = fmaf(e.z, win[j + 2], acc[j]);
+                        acc[j] = fmaf(e.w, win[j + 3], acc[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < CT; ++j) win[j] = win[j + 4];
+                }
+            }
+            const float tot = reduce_scatter<CT>(acc, lane);
+            constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
+            if ((lane & ((1 << SH) - 1)) == 0) {
+                sI[par * TC + CT * warp + (lane >> SH)] = tot;
+                sScale[par * TC + CT * warp + (lane >> SH)] = 1073741824.0f / fmaxf(tot, 1e-30f);
+            }
+        }
+        __syncthreads();
+        // ---- between two gathers: the pixels of this row's deaths lose their molecule; band row r-1 (final since the
+        // previous iteration) leaves for global memory and row r+K takes its ring slot
+        {
+            const int ev_lo = __ldg(row_off + r), ev_hi = clamp_hi(__ldg(row_off + r + 1));
+            for (int q = ev_lo + tid; q < ev_hi; q += S2_THREADS) {
+                const uint32_t ev = __ldg(ws.ev + q);
+                const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F;
+                if (xl >= 0 && xl < span) atomicAdd(&ring[slot_of(r + u) + xl], -1.0f);
+            }
+            if (aux && at < q4) {
+                if (r > r0) retire_row(r - 1, at);
+                *reinterpret_cast<float4*>(ring + slot_of(r + K) + 4 * at) = pre;      // zeros below the map
+            }
+        }
+        __syncthreads();
+    }
+    // ---- epilogue: last row's intensities, the band rows this range owns
+    if (aux) corrections_and_write(r1 - 1);
+    for (int i = tid; i < q4; i += S2_THREADS) retire_row(r1 - 1, i);
+    if (r1 == H)
+        for (int i = tid; i < (K - 1) * q4; i += S2_THREADS) {
+            const int yy = i / q4;
+            retire_row(H + yy, i - yy * q4);
+        }
+}
+
+// ------------------------------------------------------------------------------------------
 // sampler test kernels, FMA peak
 // ------------------------------------------------------------------------------------------
 __global__ void poisson_test_kernel(const float* lam, int64_t n, uint64_t seed, uint32_t offset, float* out) {
@@ -985,35 +1237,99 @@ int launch_sweep_m(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     return wide ? launch_sweep_t<0, 16, STOCH>(P, ws, st) : launch_sweep_t<0, 8, STOCH>(P, ws, st);
 }
 
-// bytes of workspace the stochastic scan needs for B environments of H rows and at most max_events deaths
+// bytes of workspace the stochastic scan needs for B environments of H rows and at most max_events deaths:
+// status + per-row counters and offsets + per event 8 bytes of staging and 4 bytes in its row bucket
 size_t bleach_ws_bytes(int B, int H, unsigned long long max_events) {
-    return 16 + ((size_t)B * H * 2 + 4) * sizeof(int) + (size_t)max_events * sizeof(uint32_t);
+    return 16 + ((size_t)B * H * 2 + 4) * sizeof(int) + (size_t)max_events * (sizeof(uint2) + sizeof(uint32_t));
+}
+
+// rows per work item of sweep2_kernel: few enough waves of `slots` concurrent CTAs, long enough ranges that the
+// K-row preload of a range stays small next to its gathers (cost model in units of one gathered row)
+int pick_row_range(int B, int strips, int H, int slots) {
+    int best_rr = H;
+    double best = 1e300;
+    for (int parts = 1; parts <= 16 && (H + parts - 1) / parts >= 16; ++parts) {
+        const int rr = (H + parts - 1) / parts;
+        const long long items = (long long)B * strips * ((H + rr - 1) / rr);
+        const double waves = (double)((items + slots - 1) / slots);
+        const double cost = waves * (rr + 8.0);
+        if (cost < best - 1e-9) { best = cost; best_rr = rr; }
+    }
+    if (const char* e = getenv("STED_B200_ROW_RANGE")) {           // tuning knob
+        const int v = atoi(e);
+        if (v >= 1) best_rr = v < H ? v : H;
+    }
+    return best_rr;
+}
+
+template <int KT, int CT>
+int launch_sweep2_t(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
+    constexpr int TC = 8 * CT;
+    const int PR = sweep_pitch(TC, P.KP);
+    const size_t smem = ((size_t)(P.K + 1) * PR + (size_t)P.K * P.KP + 6 * TC) * sizeof(float);
+    int rc;
+    if ((rc = set_smem(sweep2_kernel<KT, CT>, smem))) return rc;
+    static thread_local int slots_cache[2] = {0, 0};               // concurrent CTAs on this device (per CT)
+    int& slots = slots_cache[CT == 16];
+    if (!slots) {
+        int dev = 0, sms = 0, per_sm = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep2_kernel<KT, CT>, S2_THREADS, smem));
+        slots = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int strips = (P.W + TC - 1) / TC;
+    const int RR = pick_row_range(P.B, strips, P.H, slots);
+    dim3 grid(strips, (P.H + RR - 1) / RR, P.B);
+    sweep2_kernel<KT, CT><<<grid, S2_THREADS, smem, st>>>(P, ws, RR);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+int launch_sweep2(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
+    const bool wide = P.W > SWEEP_WIDE_MIN;
+    if (P.K == 59) return wide ? launch_sweep2_t<59, 16>(P, ws, st) : launch_sweep2_t<59, 8>(P, ws, st);
+    return wide ? launch_sweep2_t<0, 16>(P, ws, st) : launch_sweep2_t<0, 8>(P, ws, st);
 }
 
 int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     BleachWs ws{};
     if (!(P.flags & STED_SAMPLE_BLEACH)) return launch_sweep_m<false>(P, ws, st);
     const size_t fixed = bleach_ws_bytes(P.B, P.H, 0);
-    if (!workspace || workspace_bytes < fixed + 4)
+    if (!workspace || workspace_bytes < fixed + 12)
         return fail(STED_EINVAL, "stochastic bleaching needs a workspace of at least %zu bytes (see sted_bleach_workspace_bytes)",
-                    fixed + 4);
+                    fixed + 12);
+    if (((uintptr_t)workspace & 7u) != 0) return fail(STED_EINVAL, "workspace_dev must be 8-byte aligned");
     const int n = P.B * P.H;
     ws.status = reinterpret_cast<int*>(workspace);
     ws.cnt = ws.status + 4;
     ws.off = ws.cnt + n;
-    ws.ev = reinterpret_cast<uint32_t*>(ws.off + n + 4);
-    ws.cap = (workspace_bytes - fixed) / sizeof(uint32_t);
+    ws.cap = (workspace_bytes - fixed) / (sizeof(uint2) + sizeof(uint32_t));
     if (ws.cap > 0x7FFFFFFFull) ws.cap = 0x7FFFFFFFull;
+    ws.stage = reinterpret_cast<uint2*>(ws.off + n + 4);           // 16 + (2n + 4) * 4 bytes in: 8-byte aligned
+    ws.ev = reinterpret_cast<uint32_t*>(ws.stage + ws.cap);
     CUDA_TRY(cudaMemsetAsync(workspace, 0, 16 + (size_t)n * sizeof(int), st));
     const size_t psmem = ((size_t)(2 * P.K + 1) * P.KP + PS_ITEMS) * sizeof(float);
-    dim3 pgrid((unsigned)((P.H * P.W + PS_CHUNK - 1) / PS_CHUNK), P.B);
-    presample_kernel<false><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
+    const bool whole = (P.flags & STED_FRAME_MOLECULES) != 0;
+    const size_t region = whole ? (size_t)P.Hp * P.Wp : (size_t)P.H * P.W;
+    dim3 pgrid((unsigned)((region + PS_CHUNK - 1) / PS_CHUNK), P.B);
+    const bool v1 = getenv("STED_B200_SCAN_V1") != nullptr;         // round-1 schedule, kept for A/B timing and tests
+    if (v1) {
+        presample_kernel<0><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
+        CUDA_TRY(cudaGetLastError());
+        bucket_scan_kernel<<<1, 1024, 0, st>>>(ws, n);
+        CUDA_TRY(cudaGetLastError());
+        presample_kernel<1><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
+        CUDA_TRY(cudaGetLastError());
+        return launch_sweep_m<true>(P, ws, st);
+    }
+    presample_kernel<2><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
     CUDA_TRY(cudaGetLastError());
     bucket_scan_kernel<<<1, 1024, 0, st>>>(ws, n);
     CUDA_TRY(cudaGetLastError());
-    presample_kernel<true><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
+    scatter_events_kernel<<<148 * 8, 256, 0, st>>>(ws);
     CUDA_TRY(cudaGetLastError());
-    return launch_sweep_m<true>(P, ws, st);
+    return launch_sweep2(P, ws, st);
 }
 
 int launch_detect(const AcqParams& P, cudaStream_t st) {
@@ -1038,8 +1354,18 @@ int launch_detect(const AcqParams& P, cudaStream_t st) {
 struct Workspace {
     void* dev[10] = {nullptr};
     size_t cap[10] = {0};
+    int device = -1;                         // the scratch lives on the device that was current at the first call
     ~Workspace() {                           // thread exit: give the scratch back (errors at process teardown are moot)
         for (void* p : dev) if (p) cudaFree(p);
+    }
+    int bind() {                             // one device per host thread: a later cudaSetDevice(other) is refused, not mis-launched
+        int cur = 0;
+        CUDA_TRY(cudaGetDevice(&cur));
+        if (device < 0) device = cur;
+        if (device != cur)
+            return fail(STED_EINVAL, "this host thread first called the host API on device %d and now runs on device %d: "
+                                     "use one host thread per device", device, cur);
+        return STED_OK;
     }
     int ensure(int slot, size_t bytes) {
         if (cap[slot] >= bytes) return STED_OK;
@@ -1134,24 +1460,10 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
                          offset, env_base, intensity_dev, signal_dev);
     if (rc) return rc;
     if ((rc = check_device())) return rc;
-    // grid.y/z limits: split very large batches
-    const int maxB = 65535;
-    for (int b0 = 0; b0 < B; b0 += maxB) {
-        AcqParams Q = P;
-        Q.B = (B - b0 < maxB) ? B - b0 : maxB;
-        const size_t dm = (size_t)b0 * P.Hp * P.Wpitch, im = (size_t)b0 * H * W;
-        Q.din = P.din + dm;
-        Q.dout = P.dout ? P.dout + dm : nullptr;
-        Q.tables = P.tables + (size_t)b0 * STED_TABLES * K * P.KP;
-        Q.pdt = P.pdt + b0;
-        Q.intensity = P.intensity ? P.intensity + im : nullptr;
-        Q.signal = P.signal + im;
-        Q.env_base = P.env_base + (uint32_t)b0;
-        rc = (flags & STED_BLEACH) ? launch_sweep(Q, workspace_dev, (size_t)workspace_bytes, (cudaStream_t)stream)
-                                   : launch_gather(Q, (cudaStream_t)stream);
-        if (rc) return rc;
-        if (!(flags & STED_NO_DETECT) && (rc = launch_detect(Q, (cudaStream_t)stream))) return rc;
-    }
+    rc = (flags & STED_BLEACH) ? launch_sweep(P, workspace_dev, (size_t)workspace_bytes, (cudaStream_t)stream)
+                               : launch_gather(P, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (!(flags & STED_NO_DETECT) && (rc = launch_detect(P, (cudaStream_t)stream))) return rc;
     return STED_OK;
 }
 
@@ -1215,6 +1527,7 @@ struct HostPipe {
             CUDA_TRY(cudaEventCreateWithFlags(&e_comp[i], cudaEventDisableTiming));
         }
         CUDA_TRY(cudaMallocHost(&h_drop, MAXC * sizeof(int)));
+        for (int i = 0; i < MAXC; ++i) h_drop[i] = 0;
         ready = true;
         return STED_OK;
     }
@@ -1241,6 +1554,7 @@ extern "C" int sted_acquire_host(void* dmap_host, const double* psf_cache_host, 
     if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
     int rc = check_device();
     if (rc) return rc;
+    if ((rc = g_ws.bind())) return rc;
     if ((rc = g_pipe.init(g_host_low_priority))) return rc;
     const int KP = STED_KPITCH(K), Hp = H + K - 1, Wp = W + K - 1, Wpitch = (Wp + 3) & ~3, p = K / 2;
     const size_t px_roi = (size_t)H * W, px_pad = (size_t)Hp * Wpitch;
@@ -1261,6 +1575,7 @@ extern "C" int sted_acquire_host(void* dmap_host, const double* psf_cache_host, 
         if (v >= 1 && v <= HostPipe::MAXC && v <= B) nch = v;
     }
     const int cb = (B + nch - 1) / nch;
+    nch = (B + cb - 1) / cb;                                      // chunks actually issued (e.g. B = 17, 16 asked: 9 chunks of 2)
     // scratch of the stochastic scan: starts at 4 deaths per pixel and grows when a scan reports dropped events
     static thread_local unsigned long long s_max_events = 0;
     if (stoch && s_max_events < 4ull * cb * px_roi) s_max_events = 4ull * cb * px_roi;
@@ -1393,9 +1708,10 @@ int sted_fma_peak(double* tflops, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     float* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, 4));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, 0));
-    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, iters = 1 << 15;
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
@@ -1413,6 +1729,263 @@ int sted_fma_peak(double* tflops, void* stream) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops = best;
+    return STED_OK;
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// Sessions: a structure stays on the device across the acquisitions made of it
+// ==========================================================================================
+// gym-sted images every structure three or four times (confocal, STED + bleaching, confocal; mosted_env.py:222-234)
+// and pySTED keeps the datamap object alive in between.  sted_acquire_host re-uploads the map on every call; a session
+// uploads it once, keeps the padded map (and its bleached successor) resident, and queues uploads, acquisitions and
+// downloads asynchronously on its own streams: host code only waits in sted_session_sync.
+struct StedSession {
+    static constexpr int NSIG = 4;           // result buffers in flight
+    int device = -1, B = 0, H = 0, W = 0, K = 0, KP = 0, Hp = 0, Wp = 0, Wpitch = 0;
+    size_t n_roi = 0, n_pad = 0;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t e_up = nullptr, e_pad = nullptr, e_comp = nullptr, e_unpad = nullptr, e_out[NSIG] = {nullptr}, e_mapout = nullptr;
+    char* d_stage = nullptr;                 // un-padded upload / download staging [B][H][W] (4 bytes per pixel)
+    float* d_map[2] = {nullptr, nullptr};    // padded maps, ping-pong
+    float* d_tab = nullptr;
+    double* d_cache = nullptr;
+    StedFluoParams* d_fluo = nullptr;
+    double* d_scal[NSIG] = {nullptr};        // p_ex | p_sted | pdt of each queued acquisition
+    double* h_scal[NSIG] = {nullptr};        // pinned copies (the caller's arrays may die after the call returns)
+    float* d_sig[NSIG] = {nullptr};
+    uint16_t* d_sig16[NSIG] = {nullptr};
+    float* d_int[NSIG] = {nullptr};
+    void* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    unsigned long long max_events = 0;
+    int* h_drop = nullptr;                   // pinned [NSIG]
+    int cur = 0, next_sig = 0;
+    bool fluo_set = false, map_set = false, stage_busy = false;
+};
+
+namespace {
+
+int session_bind(StedSession* s) {
+    if (!s) return fail(STED_EINVAL, "null session");
+    int cur = 0;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != s->device)
+        return fail(STED_EINVAL, "session was created on device %d but the calling thread runs on device %d", s->device, cur);
+    return STED_OK;
+}
+
+void session_free(StedSession* s) {
+    if (!s) return;
+    if (s->s_in) { cudaStreamSynchronize(s->s_in); cudaStreamSynchronize(s->s_comp); cudaStreamSynchronize(s->s_out); }
+    cudaFree(s->d_stage); cudaFree(s->d_map[0]); cudaFree(s->d_map[1]); cudaFree(s->d_tab); cudaFree(s->d_cache);
+    cudaFree(s->d_fluo); cudaFree(s->d_ws);
+    for (int i = 0; i < StedSession::NSIG; ++i) {
+        cudaFree(s->d_scal[i]); cudaFree(s->d_sig[i]); cudaFree(s->d_sig16[i]); cudaFree(s->d_int[i]);
+        if (s->h_scal[i]) cudaFreeHost(s->h_scal[i]);
+        if (s->e_out[i]) cudaEventDestroy(s->e_out[i]);
+    }
+    if (s->h_drop) cudaFreeHost(s->h_drop);
+    for (cudaEvent_t e : {s->e_up, s->e_pad, s->e_comp, s->e_unpad, s->e_mapout}) if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {s->s_in, s->s_comp, s->s_out}) if (st) cudaStreamDestroy(st);
+    delete s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sted_session_create(int B, int H, int W, int K, const double* psf_cache_host, int low_priority, StedSession** out) {
+    if (!out || !psf_cache_host) return fail(STED_EINVAL, "null pointer argument");
+    *out = nullptr;
+    if (B <= 0 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B, H, W must be positive");
+    if (K < 1 || (K & 1) == 0) return fail(STED_EINVAL, "K must be odd (got %d)", K);
+    if (K > STED_MAX_K) return fail(STED_EUNSUPPORTED, "K=%d exceeds STED_MAX_K=%d", K, STED_MAX_K);
+    if (B > 65535) return fail(STED_EUNSUPPORTED, "B=%d exceeds 65535 environments per session", B);
+    int rc = check_device();
+    if (rc) return rc;
+    StedSession* s = new StedSession();
+    auto bail = [&](int code) { session_free(s); return code; };
+#define S_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return bail(fail(STED_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e))); } while (0)
+    S_TRY(cudaGetDevice(&s->device));
+    s->B = B; s->H = H; s->W = W; s->K = K; s->KP = STED_KPITCH(K);
+    s->Hp = H + K - 1; s->Wp = W + K - 1; s->Wpitch = (s->Wp + 3) & ~3;
+    s->n_roi = (size_t)B * H * W; s->n_pad = (size_t)B * s->Hp * s->Wpitch;
+    int lo = 0, hi = 0;
+    S_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const int prio = low_priority ? lo : hi;
+    S_TRY(cudaStreamCreateWithPriority(&s->s_in, cudaStreamNonBlocking, prio));
+    S_TRY(cudaStreamCreateWithPriority(&s->s_comp, cudaStreamNonBlocking, prio));
+    S_TRY(cudaStreamCreateWithPriority(&s->s_out, cudaStreamNonBlocking, prio));
+    for (cudaEvent_t* e : {&s->e_up, &s->e_pad, &s->e_comp, &s->e_unpad, &s->e_mapout}) S_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    S_TRY(cudaMalloc(&s->d_stage, s->n_roi * 4));
+    S_TRY(cudaMalloc(&s->d_map[0], s->n_pad * 4));
+    S_TRY(cudaMalloc(&s->d_map[1], s->n_pad * 4));
+    S_TRY(cudaMemsetAsync(s->d_map[0], 0, s->n_pad * 4, s->s_comp));
+    S_TRY(cudaMemsetAsync(s->d_map[1], 0, s->n_pad * 4, s->s_comp));
+    S_TRY(cudaMalloc(&s->d_tab, (size_t)B * STED_TABLES * K * s->KP * 4));
+    S_TRY(cudaMalloc(&s->d_cache, 3ull * K * K * 8));
+    S_TRY(cudaMalloc(&s->d_fluo, (size_t)B * sizeof(StedFluoParams)));
+    S_TRY(cudaMallocHost(&s->h_drop, StedSession::NSIG * sizeof(int)));
+    for (int i = 0; i < StedSession::NSIG; ++i) {
+        s->h_drop[i] = 0;
+        S_TRY(cudaEventCreateWithFlags(&s->e_out[i], cudaEventDisableTiming));
+        S_TRY(cudaMalloc(&s->d_scal[i], 3ull * B * 8));
+        S_TRY(cudaMallocHost(&s->h_scal[i], 3ull * B * 8));
+        S_TRY(cudaMalloc(&s->d_sig[i], s->n_roi * 4));
+        S_TRY(cudaMalloc(&s->d_sig16[i], s->n_roi * 2));
+        S_TRY(cudaMalloc(&s->d_int[i], s->n_roi * 4));
+    }
+    S_TRY(cudaMemcpyAsync(s->d_cache, psf_cache_host, 3ull * K * K * 8, cudaMemcpyHostToDevice, s->s_comp));
+    S_TRY(cudaStreamSynchronize(s->s_comp));
+#undef S_TRY
+    *out = s;
+    return STED_OK;
+}
+
+int sted_session_destroy(StedSession* s) {
+    session_free(s);
+    return STED_OK;
+}
+
+int sted_session_set_fluorophores(StedSession* s, const StedFluoParams* fluo_host) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if (!fluo_host) return fail(STED_EINVAL, "null pointer argument");
+    // synchronous: called once per episode, and the caller's array need not outlive the call
+    CUDA_TRY(cudaStreamSynchronize(s->s_comp));
+    CUDA_TRY(cudaMemcpy(s->d_fluo, fluo_host, (size_t)s->B * sizeof(StedFluoParams), cudaMemcpyHostToDevice));
+    s->fluo_set = true;
+    return STED_OK;
+}
+
+int sted_session_upload(StedSession* s, const void* dmap_host, uint32_t flags, uint64_t max_molecules) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if (!dmap_host) return fail(STED_EINVAL, "null pointer argument");
+    const bool u16 = (flags & STED_HOST_U16) != 0;
+    const size_t esz = u16 ? 2 : 4;
+    // the staging buffer is free once the previous pad / unpad + copy that used it has run
+    CUDA_TRY(cudaStreamWaitEvent(s->s_in, s->e_pad, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s->s_in, s->e_mapout, 0));
+    CUDA_TRY(cudaMemcpyAsync(s->d_stage, dmap_host, s->n_roi * esz, cudaMemcpyHostToDevice, s->s_in));
+    CUDA_TRY(cudaEventRecord(s->e_up, s->s_in));
+    CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_up, 0));
+    const int p = s->K / 2;
+    if (u16) pad_kernel<<<296, 256, 0, s->s_comp>>>((const uint16_t*)s->d_stage, s->d_map[s->cur], s->B, s->H, s->W, p, s->Hp, s->Wpitch);
+    else pad_kernel<<<296, 256, 0, s->s_comp>>>((const float*)s->d_stage, s->d_map[s->cur], s->B, s->H, s->W, p, s->Hp, s->Wpitch);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->e_pad, s->s_comp));
+    s->map_set = true;
+    if (max_molecules == 0) max_molecules = 4ull * s->n_roi;           // grown by sted_session_sync when a scan overflows
+    if (max_molecules + 16 > s->max_events) {
+        s->max_events = max_molecules + 16;
+        const size_t need = (bleach_ws_bytes(s->B, s->H, s->max_events) + 255) & ~(size_t)255;
+        if (need > s->ws_bytes) {
+            CUDA_TRY(cudaStreamSynchronize(s->s_comp));
+            if (s->d_ws) cudaFree(s->d_ws);
+            s->d_ws = nullptr; s->ws_bytes = 0;
+            CUDA_TRY(cudaMalloc(&s->d_ws, need));
+            s->ws_bytes = need;
+        }
+    }
+    return STED_OK;
+}
+
+int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* p_sted_host, const double* pdt_host,
+                         uint32_t flags, const StedDetectorParams* det, double lambda_fluo, uint64_t seed, uint64_t offset,
+                         int64_t env_base, void* signal_host, float* intensity_host) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if (!p_ex_host || !p_sted_host || !pdt_host || !det) return fail(STED_EINVAL, "null pointer argument");
+    if (!s->fluo_set || !s->map_set) return fail(STED_EINVAL, "session needs sted_session_set_fluorophores and sted_session_upload first");
+    const bool bleach = (flags & STED_BLEACH) != 0;
+    const bool stoch = bleach && (flags & STED_SAMPLE_BLEACH);
+    const bool u16 = (flags & STED_HOST_U16) != 0;
+    if (u16 && ((bleach && !stoch) || !(flags & STED_SAMPLE_PHOTONS)))
+        return fail(STED_EINVAL, "STED_HOST_U16 needs integer outputs: STED_SAMPLE_PHOTONS, and STED_SAMPLE_BLEACH when bleaching");
+    flags &= ~STED_HOST_U16;
+    const int i = s->next_sig;
+    s->next_sig = (i + 1) % StedSession::NSIG;
+    const int B = s->B;
+    // result slot i is reusable once its previous download has finished (also covers h_scal[i] / d_scal[i])
+    CUDA_TRY(cudaEventSynchronize(s->e_out[i]));
+    memcpy(s->h_scal[i], p_ex_host, (size_t)B * 8);
+    memcpy(s->h_scal[i] + B, p_sted_host, (size_t)B * 8);
+    memcpy(s->h_scal[i] + 2 * B, pdt_host, (size_t)B * 8);
+    CUDA_TRY(cudaMemcpyAsync(s->d_scal[i], s->h_scal[i], 3ull * B * 8, cudaMemcpyHostToDevice, s->s_comp));
+    if ((rc = sted_make_effective(s->d_cache, s->d_fluo, s->d_scal[i], s->d_scal[i] + B, s->d_scal[i] + 2 * B, B, s->K, s->d_tab,
+                                  nullptr, s->s_comp)))
+        return rc;
+    float* d_in = s->d_map[s->cur];
+    float* d_out = s->d_map[s->cur ^ 1];
+    if ((rc = sted_acquire(d_in, bleach ? d_out : nullptr, s->d_tab, s->d_scal[i] + 2 * B, B, s->H, s->W, s->K, flags, det,
+                           lambda_fluo, seed, offset, env_base, intensity_host ? s->d_int[i] : nullptr, s->d_sig[i],
+                           stoch ? s->d_ws : nullptr, stoch ? s->ws_bytes : 0, s->s_comp)))
+        return rc;
+    s->h_drop[i] = 0;
+    if (stoch) CUDA_TRY(cudaMemcpyAsync(&s->h_drop[i], s->d_ws, sizeof(int), cudaMemcpyDeviceToHost, s->s_comp));
+    if (bleach) s->cur ^= 1;
+    if (signal_host || intensity_host) {
+        if (u16 && signal_host) {
+            counts_to_u16_kernel<<<296, 256, 0, s->s_comp>>>(s->d_sig[i], s->d_sig16[i], s->n_roi);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(s->e_comp, s->s_comp));
+        CUDA_TRY(cudaStreamWaitEvent(s->s_out, s->e_comp, 0));
+        if (signal_host) {
+            if (u16) CUDA_TRY(cudaMemcpyAsync(signal_host, s->d_sig16[i], s->n_roi * 2, cudaMemcpyDeviceToHost, s->s_out));
+            else CUDA_TRY(cudaMemcpyAsync(signal_host, s->d_sig[i], s->n_roi * 4, cudaMemcpyDeviceToHost, s->s_out));
+        }
+        if (intensity_host) CUDA_TRY(cudaMemcpyAsync(intensity_host, s->d_int[i], s->n_roi * 4, cudaMemcpyDeviceToHost, s->s_out));
+    }
+    CUDA_TRY(cudaEventRecord(s->e_out[i], s->s_out));
+    // the next kernels on s_comp must not overwrite slot i ... they use slot i+1; slot i is guarded by e_out[i] above
+    return STED_OK;
+}
+
+int sted_session_download(StedSession* s, void* dmap_host, uint32_t flags) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if (!dmap_host) return fail(STED_EINVAL, "null pointer argument");
+    if (!s->map_set) return fail(STED_EINVAL, "no map uploaded");
+    const bool u16 = (flags & STED_HOST_U16) != 0;
+    const int p = s->K / 2;
+    // the staging buffer may still feed a pad kernel or an earlier download
+    CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_mapout, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_up, 0));
+    if (u16) unpad_kernel<<<296, 256, 0, s->s_comp>>>(s->d_map[s->cur], (uint16_t*)s->d_stage, s->B, s->H, s->W, p, s->Hp, s->Wpitch);
+    else unpad_kernel<<<296, 256, 0, s->s_comp>>>(s->d_map[s->cur], (float*)s->d_stage, s->B, s->H, s->W, p, s->Hp, s->Wpitch);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->e_unpad, s->s_comp));
+    CUDA_TRY(cudaEventRecord(s->e_pad, s->s_comp));                     // later uploads wait for the unpad as well
+    CUDA_TRY(cudaStreamWaitEvent(s->s_out, s->e_unpad, 0));
+    CUDA_TRY(cudaMemcpyAsync(dmap_host, s->d_stage, s->n_roi * (u16 ? 2 : 4), cudaMemcpyDeviceToHost, s->s_out));
+    CUDA_TRY(cudaEventRecord(s->e_mapout, s->s_out));
+    return STED_OK;
+}
+
+int sted_session_sync(StedSession* s, int64_t* dropped_events) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->s_in));
+    CUDA_TRY(cudaStreamSynchronize(s->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(s->s_out));
+    long long dropped = 0;
+    for (int i = 0; i < StedSession::NSIG; ++i) { dropped += s->h_drop[i]; s->h_drop[i] = 0; }
+    if (dropped_events) *dropped_events = dropped;
+    if (dropped > 0)
+        return fail(STED_EOVERFLOW, "%lld bleaching events did not fit the session's event scratch: the results since the last "
+                                    "sync are invalid; upload again with a larger max_molecules", dropped);
+    return STED_OK;
+}
+
+int sted_session_device_map(StedSession* s, float** map_dev) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if (!map_dev) return fail(STED_EINVAL, "null pointer argument");
+    *map_dev = s->d_map[s->cur];
     return STED_OK;
 }
 

@@ -83,10 +83,11 @@ class _Decorrelator:
 _DECORR_CACHE: dict = {}
 
 
-def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, Ng=10, tol=0.0005) -> np.ndarray:
-    """(B,H,W) photon counts on the GPU -> (B,) float64 numpy array of resolutions in nm (capped).
-    Apodisation, FFT (cuFFT) and the radius sort run through torch; the 22 decorrelation passes and their peak
-    searches are one launch of ``decorr_kernel`` (one CTA per image)."""
+def resolution_device(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, Ng=10, tol=0.0005) -> torch.Tensor:
+    """(B,H,W) photon counts on the GPU -> (B,) float64 DEVICE tensor of resolutions in nm (capped); nothing is read
+    back.  ``apodize_kernel`` (mean, window, float32 rounding, crop, ifftshift) -> cuFFT (through torch, complex128)
+    -> ``spectrum_gather_kernel`` (centring, radius order, R < 1 mask, phase-only copy) -> ``decorr_kernel`` (the 22
+    decorrelation passes and their peak searches, one CTA per image)."""
     assert Nr == 50 and Ng == 10, "decorr_kernel is compiled for the reference's Nr = 50, Ng = 10"
     B, H, W = sted.shape
     dev = sted.device
@@ -94,22 +95,28 @@ def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, 
     if key not in _DECORR_CACHE:
         _DECORR_CACHE[key] = _Decorrelator(H, W, dev)
     geo = _DECORR_CACHE[key]
-    img = sted.to(torch.float64)
-    mean = img.mean(dim=(1, 2), keepdim=True)
-    img = (geo.window * (img - mean) + mean).to(torch.float32).to(torch.float64)[:, :geo.Hc, :geo.Wc]
-    Ik = torch.fft.fftshift(torch.fft.fftn(torch.fft.fftshift(img, dim=(1, 2)), dim=(1, 2)), dim=(1, 2))
-    Ik = Ik.reshape(B, -1)[:, geo.order]
-    Ik = Ik * geo.inside
-    mag = torch.abs(Ik)
-    Ikn = torch.where(mag > 0, Ik / mag, torch.zeros_like(Ik))
-    Ikn = torch.where(torch.isfinite(Ikn.real) & torch.isfinite(Ikn.imag), Ikn, torch.zeros_like(Ikn))
+    lib = _lib.load()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    img = sted.contiguous().to(torch.float32)
+    N = geo.Hc * geo.Wc
+    pre = torch.empty((B, geo.Hc, geo.Wc), dtype=torch.complex128, device=dev)
+    _lib.check(lib.sted_apodize_for_fft(img.data_ptr(), geo.window.data_ptr(), B, H, W, geo.Hc, geo.Wc, pre.data_ptr(), st))
+    spec = torch.fft.fftn(pre, dim=(1, 2))
+    Ik = torch.empty((B, N), dtype=torch.complex128, device=dev)
+    Ikn = torch.empty_like(Ik)
+    _lib.check(lib.sted_spectrum_gather(spec.data_ptr(), geo.order.data_ptr(), B, geo.Hc, geo.Wc, geo.n_inside,
+                                        Ik.data_ptr(), Ikn.data_ptr(), st))
     res = torch.empty((B,), dtype=torch.float64, device=dev)
-    Ik, Ikn = Ik.contiguous(), Ikn.contiguous()
-    _lib.check(_lib.load().sted_decorrelation_resolution(
-        Ik.data_ptr(), Ikn.data_ptr(), B, Ik.shape[1], geo.n_inside, geo.R_sorted.data_ptr(), geo.R2_sorted.data_ptr(),
+    _lib.check(lib.sted_decorrelation_resolution(
+        Ik.data_ptr(), Ikn.data_ptr(), B, N, geo.n_inside, geo.R_sorted.data_ptr(), geo.R2_sorted.data_ptr(),
         geo.r_coarse(Nr).data_ptr(), geo.Hc / 4, max(geo.Hc, geo.Wc) / 2, float(pixelsize), float(res_cap), float(tol),
-        res.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
-    return res.cpu().numpy()
+        res.data_ptr(), st))
+    return res
+
+
+def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, Ng=10, tol=0.0005) -> np.ndarray:
+    """``resolution_device`` read back as a (B,) float64 numpy array."""
+    return resolution_device(sted, pixelsize, res_cap, Nr, Ng, tol).cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------------

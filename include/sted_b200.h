@@ -45,6 +45,7 @@ extern "C" {
 #define STED_ENODEVICE    -2   /* no usable CUDA device / driver                            */
 #define STED_ECUDA        -3   /* a CUDA runtime call or kernel launch failed                */
 #define STED_EUNSUPPORTED -4   /* shape outside the compiled limits (K > STED_MAX_K, ...)    */
+#define STED_EOVERFLOW    -5   /* a device-side capacity was exceeded; the outputs are invalid */
 
 #define STED_MAX_K        63   /* largest PSF side (odd)                                     */
 #define STED_KPITCH(K)    ((((K) + 1) + 3) & ~3)   /* row pitch of the per-env K x K tables  */
@@ -58,6 +59,9 @@ extern "C" {
                                  * STED_SAMPLE_BLEACH when STED_BLEACH is set.                                     */
 #define STED_NO_DETECT      8u  /* sted_acquire leaves the detected power (W) in signal_dev; the
                                    detector is applied later by sted_detect                   */
+#define STED_FRAME_MOLECULES 32u /* the K/2 frame of dmap_in_dev may hold molecules (a caller assigned the whole padded
+                                  * map, gym_sted/envs/sted_env.py:170): the stochastic scan then draws deaths for the
+                                  * whole padded map instead of the H x W region of interest only                   */
 
 /* Fluorophore + STED-pulse parameters of one environment.
  * Mirrors pysted.base.Fluorescence(**defaults.FLUO) (gym_sted/defaults.py:25-42) and the
@@ -136,9 +140,12 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
                  float* intensity_dev, float* signal_dev,
                  void* workspace_dev, uint64_t workspace_bytes, void* stream);
 
-/* Scratch for STED_BLEACH|STED_SAMPLE_BLEACH: the deaths of the whole scan are drawn before it and
- * bucketed by scan row.  max_events bounds the number of molecules that can bleach (the total
- * molecule count of the B maps is always enough).  Other modes accept workspace_dev = NULL. */
+/* Scratch for STED_BLEACH|STED_SAMPLE_BLEACH: the deaths of the whole scan are drawn before it, staged and
+ * bucketed by scan row (12 bytes per event).  max_events must cover the total molecule count of the B maps
+ * (every 4096-pixel chunk reserves staging room for all of its molecules).  workspace_dev must be 8-byte
+ * aligned.  Other modes accept workspace_dev = NULL.
+ * Limits of sted_acquire: B <= 65535 environments per call, H <= 65535, W + K - 1 <= 4095, fewer than 32768
+ * molecules per pixel. */
 uint64_t sted_bleach_workspace_bytes(int B, int H, uint64_t max_events);
 /* Number of deaths the last stochastic scan could not store (0 unless max_events was too small;
  * a non-zero value means that scan's outputs are invalid).  Synchronises `stream`. */
@@ -171,6 +178,36 @@ int sted_acquire_host(void* dmap_host, const double* psf_cache_host,
                       int B, int H, int W, int K, uint32_t flags,
                       const StedDetectorParams* det, uint64_t seed, uint64_t offset,
                       int64_t env_base, float* intensity_host, void* signal_host);
+
+/* ---- Sessions: a structure stays resident across the acquisitions made of it ------------------------------------
+ * gym-sted images every structure several times (confocal, STED + bleaching, confocal: gym_sted/envs/mosted_env.py:
+ * 222-234) on ONE pysted Datamap object that carries the bleaching (sequence_sted_env.py:86-92).  A session is that
+ * object for B environments: the map is uploaded once, acquisitions advance it on the device, and every call only
+ * QUEUES work (own streams; uploads, kernels and downloads of successive calls overlap).  Host buffers handed to
+ * sted_session_acquire / _download must stay valid, and are only defined, after the next sted_session_sync.
+ * One session belongs to one device (the one current at creation) and must be driven by one host thread at a time.
+ *   psf_cache_host : float64 [3][K][K] (copied at creation);  low_priority != 0: streams of the lowest priority, for
+ *                    work nobody waits for yet (e.g. the first confocal image of the NEXT structure)
+ *   dmap_host      : [B][H][W] un-padded molecule maps, float32, or uint16 with STED_HOST_U16
+ *   max_molecules  : upper bound of the total molecule count of the B maps (sizes the event scratch of the stochastic
+ *                    scan: 12 bytes each); 0 = 4 per pixel, and sted_session_sync reports STED_EOVERFLOW if a scan
+ *                    needed more
+ *   flags          : as sted_acquire, plus STED_HOST_U16 for uint16 signal_host
+ *   signal_host / intensity_host : [B][H][W] or NULL (result stays on the device / is not wanted)                */
+typedef struct StedSession StedSession;
+int sted_session_create(int B, int H, int W, int K, const double* psf_cache_host, int low_priority, StedSession** out);
+int sted_session_destroy(StedSession* s);
+int sted_session_set_fluorophores(StedSession* s, const StedFluoParams* fluo_host /* [B] */);
+int sted_session_upload(StedSession* s, const void* dmap_host, uint32_t flags, uint64_t max_molecules);
+int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* p_sted_host, const double* pdt_host,
+                         uint32_t flags, const StedDetectorParams* det, double lambda_fluo, uint64_t seed, uint64_t offset,
+                         int64_t env_base, void* signal_host, float* intensity_host);
+/* Current (bleached) maps -> host, same format rules as sted_session_upload. */
+int sted_session_download(StedSession* s, void* dmap_host, uint32_t flags);
+/* Waits for everything queued on the session; *dropped_events (may be NULL) = deaths that did not fit the scratch. */
+int sted_session_sync(StedSession* s, int64_t* dropped_events);
+/* Device pointer of the current padded maps [B][Hp][Wpitch] (valid until the next bleaching acquisition / upload). */
+int sted_session_device_map(StedSession* s, float** map_dev);
 
 /* Samplers exposed for the statistical tests (same device functions the kernels use).
  *   out_dev[i] ~ Poisson(lambda_dev[i]) / Binomial(n_dev[i], q_dev[i]); counter = i. */
@@ -233,6 +270,31 @@ int sted_decorrelation_resolution(const void* ik_dev, const void* ikn_dev, int B
 int sted_gaussfit_validate(const float* sted_dev, int B, int H, int W, const int32_t* peaks_dev,
                            const int32_t* npeaks_dev, int max_peaks, double pixelsize, uint8_t* valid_dev,
                            double* params_dev, void* stream);
+
+/* F1 score of the validated detections against the ground-truth nanodomains (gym_sted/rewards/objectives.py:425-430:
+ * metrics.CentroidDetectionError(truth, guess, threshold, "hungarian").f1_score).  TP = size of a maximum matching of
+ * the pairs closer than `threshold` (what the Hungarian solution on the priced-out cost matrix counts), FP / FN the
+ * unmatched guesses / truths; F1 = 2PR/(P+R+1e-6) with P = TP/(TP+FP+1e-6), R = TP/(TP+FN+1e-6), float64.
+ *   peaks_dev/npeaks_dev/valid_dev : as written by sted_nanodomain_candidates / sted_gaussfit_validate (valid_dev NULL =
+ *                                    keep every candidate), max_peaks rows per image
+ *   truth_dev  : int32 [B][max_truth][2] (row, col);  ntruth_dev : int32 [B]
+ *   counts_dev : int32 [B][3] = TP, FP, FN;  f1_dev : float64 [B];  flags_dev : int32 [B] (NULL allowed), 1 = more than
+ *                512 truths or kept guesses in the image (outputs then cover the first 512 only: treat as an error) */
+int sted_f1_match(const int32_t* peaks_dev, const int32_t* npeaks_dev, const uint8_t* valid_dev, int max_peaks,
+                  const int32_t* truth_dev, const int32_t* ntruth_dev, int max_truth, int B, double threshold,
+                  int32_t* counts_dev, double* f1_dev, int32_t* flags_dev, void* stream);
+
+/* The two element-wise ends of the Resolution objective's Fourier transform (gym_sted/rewards/objectives.py:150-175).
+ * sted_apodize_for_fft: out = ifftshift(crop(float32(window * (image - mean) + mean))) as complex128 [B][Hc][Wc]
+ *   (image_dev float32 [B][H][W] photon counts, window_dev float64 [H][W] the cosine edge window), ready for a plain
+ *   forward FFT.  sted_spectrum_gather: from that FFT (complex128 [B][Hc][Wc]) the centred spectrum in radius order
+ *   (order_dev int64 [Hc*Wc]: stable argsort of the normalised radii of the CENTRED spectrum), zero at R >= 1 (the
+ *   first n_inside entries are inside), plus its phase-only copy Ik/|Ik| — the inputs of
+ *   sted_decorrelation_resolution. */
+int sted_apodize_for_fft(const float* image_dev, const double* window_dev, int B, int H, int W, int Hc, int Wc,
+                         void* out_dev, void* stream);
+int sted_spectrum_gather(const void* spectrum_dev, const int64_t* order_dev, int B, int Hc, int Wc, int n_inside,
+                         void* ik_dev, void* ikn_dev, void* stream);
 
 /* Test hook for the Levenberg-Marquardt solver: n windows of 49 float64 values, params_dev float64 [n][5] holds the
  * starting points on entry and the solutions on return, info_dev int32 [n] MINPACK's info code.

@@ -111,6 +111,18 @@ def _stochastic_replicas(micro, roi, R, act, seed):
     return inten.cpu().numpy().astype(np.float64), bm.datamaps_roi().cpu().numpy().astype(np.float64)
 
 
+def discrete_ks_pvalue(sample, dist, n):
+    """Kolmogorov-Smirnov against a DISCRETE law on {0..n}: D = max_k |F_R(k) - F(k)| evaluated at the integers
+    (both functions right-continuous), p-value from the continuous-case distribution of D, which is conservative
+    for discrete laws.  (scipy.stats.kstest assumes a continuous cdf: its D- term compares F(k) with the empirical
+    cdf just BELOW k and is inflated by the probability mass at k.)"""
+    from scipy import stats
+    ks = np.arange(n + 1)
+    ecdf = np.searchsorted(np.sort(sample), ks, side="right") / len(sample)
+    d = np.abs(ecdf - dist.cdf(ks)).max()
+    return float(stats.kstwo.sf(d, len(sample)))
+
+
 def _check_counts_against_exact_law(gd, roi, exp_d, R):
     """Final counts are Binomial(n, s) with s = exp_d / n exactly (survival factors commute)."""
     assert np.all(gd == np.rint(gd)) and np.all(gd >= 0) and np.all(gd <= roi)
@@ -125,6 +137,13 @@ def _check_counts_against_exact_law(gd, roi, exp_d, R):
     # sample variance against the exact one, pooled
     ratio = gd.var(0, ddof=1)[occ][ok] / var[ok]
     assert abs(ratio.mean() - 1) < 0.05, f"variance ratio {ratio.mean():.3f}"
+    # the same for the nanodomain pixels alone (their deaths are drawn as several sub-binomials)
+    big = (n > 50)[ok]
+    if big.sum() >= 8:
+        rb = ratio[big].mean()
+        tol = 4.5 * np.sqrt(2.0 / (R - 1) / big.sum()) + 0.01
+        assert abs(rb - 1) < tol, f"nanodomain variance ratio {rb:.3f} (tolerance {tol:.3f}, {big.sum()} pixels)"
+        assert np.abs(z[big]).max() < 4.5
     return z
 
 
@@ -164,8 +183,8 @@ def test_stochastic_scan_two_strips_moments_seam_and_ks(micro, omicro, H, W, R):
     ys, xs = np.nonzero(roi > 50)
     for (yy, xx) in zip(ys, xs):
         n, s = int(roi[yy, xx]), exp_d[yy, xx] / roi[yy, xx]
-        # KS against the exact binomial law (discrete: the statistic is conservative) and against the oracle's draws
-        assert stats.kstest(gd[:, yy, xx], stats.binom(n, s).cdf).pvalue > 1e-4, (yy, xx)
+        # KS against the exact binomial law and against the oracle's draws
+        assert discrete_ks_pvalue(gd[:, yy, xx], stats.binom(n, s), n) > 1e-3, (yy, xx)
         assert stats.ks_2samp(gd[:, yy, xx], od[:, yy, xx]).pvalue > 1e-4, (yy, xx)
     y, x = np.unravel_index(exp_i.argmax(), exp_i.shape)
     assert stats.ks_2samp(gi[:, y, x], oi[:, y, x]).pvalue > 1e-4
@@ -228,5 +247,5 @@ def test_per_env_fluorophores_match_oracle(micro):
         ref_i, ref_d = oracle_acquire(om, rois[b], pdt[b], p_ex[b], p_sted[b], 1)
         np.testing.assert_allclose(inten[b], ref_i, rtol=RTOL, atol=1e-7 * ref_i.max())
         np.testing.assert_allclose(bleached[b], ref_d, rtol=RTOL, atol=1e-6)
-        distinct.add(round(float(E.max() / (p_ex[b] * 1e20)), 9))
+        distinct.add(float(np.float32(E.max() / p_ex[b])))
     assert len(distinct) == B                        # the environments really ran different fluorophores

@@ -1,0 +1,140 @@
+"""The second-generation stochastic scan (fused presample + scatter + ``sweep2_kernel``: row-range work items,
+correction warps, K+1-slot ring) against the round-1 schedule it replaces and against the session API.
+
+Both schedules draw the same deaths (same Philox keys) and apply them with order-independent integer arithmetic, so
+their outputs must be IDENTICAL bit for bit — for every split of the scan into row ranges."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from gym_sted_b200 import defaults, session as sess, synapse  # noqa: E402
+from tests import helpers  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(m, maps, act, seed, env=None):
+    from gym_sted_b200.batch import BatchedMicroscope
+    saved = {k: os.environ.get(k) for k in ("STED_B200_SCAN_V1", "STED_B200_ROW_RANGE")}
+    try:
+        for k, v in (env or {}).items():
+            os.environ[k] = v
+        B, H, W = maps.shape
+        bm = BatchedMicroscope(m, B, H, W, device="cuda:0", seed=seed, env_base=100)
+        bm.set_datamaps(torch.from_numpy(maps))
+        sig, inten = bm.get_signal_and_bleach(*act, bleach=True, want_intensity=True)
+        assert bm.dropped_events() == 0
+        return sig.cpu().numpy(), inten.cpu().numpy(), bm.datamaps_roi().cpu().numpy()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("H,W,B", [(64, 64, 7), (96, 96, 5), (100, 200, 3), (256, 256, 3), (40, 300, 2), (17, 23, 4)])
+def test_scan_v2_equals_v1_for_every_row_range(H, W, B):
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device")
+    m = helpers.product_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
+                                   background=defaults.DETECTOR["background"])
+    maps, _ = synapse.generate_batch(B, max(H, 64), max(W, 64), seed=H + W)
+    maps = np.ascontiguousarray(maps[:, -H:, -W:]).astype(np.float32)
+    rng = np.random.default_rng(H)
+    if maps.sum() < 50 * B:                          # a crop that missed the structure: add a dense patch
+        maps[:, H // 4:H // 2 + 2, W // 4:W // 2 + 2] = rng.integers(1, 30, (B, H // 2 + 2 - H // 4, W // 2 + 2 - W // 4))
+    act = (rng.uniform(10e-6, 50e-6, B), rng.uniform(3e-6, 15e-6, B), rng.uniform(0.05, 0.3, B))
+    ref = _run(m, maps, act, 5, {"STED_B200_SCAN_V1": "1"})
+    assert ref[2].sum() < maps.sum()
+    for rr in (None, "16", "1", "37", str(H)):
+        got = _run(m, maps, act, 5, {} if rr is None else {"STED_B200_ROW_RANGE": rr})
+        for a, b, name in zip(got, ref, ("photons", "intensity", "bleached map")):
+            assert np.array_equal(a, b), f"{name} differs from the round-1 schedule (row range {rr})"
+
+
+def test_frame_molecules_take_part_in_the_scan():
+    """STED_FRAME_MOLECULES: molecules in the K//2 frame are imaged and bleached (expectation and stochastic modes
+    agree on the totals); without the flag the stochastic scan leaves the frame alone."""
+    from gym_sted_b200 import base
+    m = helpers.product_microscope()
+    rng = np.random.default_rng(0)
+    H = W = 40
+    dm = base.Datamap(helpers.synthetic_datamap(rng, H, W), helpers.PX)
+    dm.set_roi(m.cache(helpers.PX)[0], "max")
+    whole = dm.whole_datamap.copy()
+    whole[24:29, 29:60] = 50                      # inside the frame (rows < 29), next to the first scan rows
+    dm.whole_datamap = whole
+    act = dict(pdt=40e-6, p_ex=10e-6, p_sted=0.2)
+    _, bl_e, _ = m.get_signal_and_bleach(dm, helpers.PX, **act, bleach=True, update=False, sample_bleach=False)
+    _, bl_s, _ = m.get_signal_and_bleach(dm, helpers.PX, **act, bleach=True, update=False, seed=1)
+    fe, fs = bl_e["base"][24:29, 29:60].sum(), bl_s["base"][24:29, 29:60].sum()
+    assert fe < 0.98 * whole[24:29, 29:60].sum()
+    assert abs(fs - fe) < 6 * np.sqrt(whole[24:29, 29:60].sum())
+    assert np.all(bl_s["base"] <= whole)
+
+
+def test_session_equals_device_api():
+    """upload once -> confocal, STED + bleaching, confocal, download: identical to the device-resident calls."""
+    from gym_sted_b200.batch import BatchedMicroscope
+    m = helpers.product_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
+                                   background=defaults.DETECTOR["background"])
+    B, H, W = 12, 48, 80
+    maps, _ = synapse.generate_batch(B, 64, 128, seed=2)
+    maps = np.ascontiguousarray(maps[:, :H, :W])
+    rng = np.random.default_rng(1)
+    pdt, p_ex, p_sted = rng.uniform(10e-6, 40e-6, B), rng.uniform(3e-6, 15e-6, B), rng.uniform(0.05, 0.25, B)
+    bm = BatchedMicroscope(m, B, H, W, device="cuda:0", seed=9, env_base=40)
+    bm.set_datamaps(torch.from_numpy(maps))
+    ref = []
+    ref.append(bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)[0].cpu().numpy())
+    s, i = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True, want_intensity=True)
+    ref.append(s.cpu().numpy())
+    ref_int = i.cpu().numpy()
+    ref.append(bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)[0].cpu().numpy())
+    ref_map = bm.datamaps_roi().cpu().numpy()
+
+    for u16 in (True, False):
+        dt = np.uint16 if u16 else np.float32
+        s = sess.StedSession(m, B, H, W, env_base=40, seed=9)
+        s.upload(maps.astype(dt), max_molecules=int(maps.sum()))
+        outs = [sess.pinned_empty((B, H, W), dt) for _ in range(3)]
+        inten = np.empty((B, H, W), dtype=np.float32)
+        s.acquire(10e-6, 10e-6, 0.0, bleach=False, out=outs[0])
+        s.acquire(pdt, p_ex, p_sted, bleach=True, out=outs[1], intensity_out=inten)
+        s.acquire(10e-6, 10e-6, 0.0, bleach=False, out=outs[2])
+        got_map = s.download(np.empty((B, H, W), dtype=dt))
+        assert s.sync() == 0
+        for a, b in zip(outs, ref):
+            assert np.array_equal(np.asarray(a).astype(np.float32), b)
+        assert np.array_equal(inten, ref_int)
+        assert np.array_equal(got_map.astype(np.float32), ref_map)
+        # a second structure through the same session; results independent of what ran before
+        s.upload(maps[::-1].copy().astype(dt), max_molecules=int(maps.sum()))
+        out2 = s.acquire(10e-6, 10e-6, 0.0, bleach=False, noise=False, out=np.empty((B, H, W), dtype=np.float32))
+        s.sync()
+        bm2 = BatchedMicroscope(m, B, H, W, device="cuda:0")
+        bm2.set_datamaps(torch.from_numpy(maps[::-1].copy()))
+        exp2 = bm2.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False, noise=False)[0].cpu().numpy()
+        assert np.array_equal(out2, exp2)
+        s.close()
+
+
+def test_session_reports_event_overflow():
+    m = helpers.product_microscope()
+    B, H, W = 2, 32, 32
+    maps = np.full((B, H, W), 40, dtype=np.uint16)
+    s = sess.StedSession(m, B, H, W)
+    s.upload(maps, max_molecules=100)                 # far too small for 2 x 1024 x 40 molecules
+    s.acquire(50e-6, 10e-6, 0.3, bleach=True, noise=False)
+    from gym_sted_b200 import _lib
+    with pytest.raises(_lib.StedError) as err:
+        s.sync()
+    assert err.value.code == -5
+    s.upload(maps, max_molecules=int(maps.sum()))
+    s.acquire(50e-6, 10e-6, 0.3, bleach=True, noise=False)
+    assert s.sync() == 0
+    s.close()
