@@ -7,7 +7,11 @@ the batch (gym_sted/envs/mosted_env.py:222-234 + :184): confocal, STED with in-s
 Workload at N=1: BASELINE.json configs[1], ContextualMOSTED-easy-hslb-v0, 256 envs, 256x256 px,
 K=59 PSF, actions uniform in the action box.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload acquisitions|config5|env_step]
+
+``--workload config5``: BASELINE.json configs[4], 512x512 px, 2048 environments in total, split over the N GPUs
+(strong scaling: 2048 / N environments per GPU).  ``--workload env_step``: whole ``VectorContextualMOSTED.step`` calls
+(4 acquisitions + foreground / objectives / nanodomain F1 + observation packing, results as numpy arrays on the host).
 
 Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU restatement of pySTED's loop
 (oracle/raster_oracle.c, kind "port": pySTED itself is not installable here) on the host cores.
@@ -133,27 +137,32 @@ def cpu_env_steps(n_envs, H, W, threads, seed=1234):
     from concurrent.futures import ThreadPoolExecutor
     from gym_sted_b200 import defaults, synapse
     from oracle import pysted_oracle as po
-    from tests import helpers
 
-    om = helpers.oracle_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
-                                   background=defaults.DETECTOR["background"])
+    PX = defaults.PIXELSIZE
+    om = po.default_microscope(defaults.load_routine("high-signal_low-bleach"),
+                               {"noise": True, "background": defaults.DETECTOR["background"]},
+                               defaults.LASER_EX, defaults.LASER_STED, defaults.OBJECTIVE)
+    cache_file = os.path.join(ROOT, "tests", "golden", "oracle_psf_cache.npz")     # the oracle's quad beams, memoised
+    if os.path.exists(cache_file):
+        z = np.load(cache_file)
+        om._cache[int(round(PX * 1e9))] = (z["i_ex"], z["i_sted"], z["psf_det"])
     po.raster_lib()
     rng = np.random.default_rng(seed)
     lo = np.array([defaults.action_spaces[k]["low"] for k in ("p_sted", "p_ex", "pdt")])
     hi = np.array([defaults.action_spaces[k]["high"] for k in ("p_sted", "p_ex", "pdt")])
     actions = rng.uniform(lo, hi, (n_envs, 3))
     maps, _ = synapse.generate_batch(2 * n_envs, H, W, seed=seed)
-    i_ex = om.cache(helpers.PX)[0]
+    i_ex = om.cache(PX)[0]
 
     def one(i):
-        dm = po.Datamap(maps[i], helpers.PX); dm.set_roi(i_ex, "max")
+        dm = po.Datamap(maps[i], PX); dm.set_roi(i_ex, "max")
         conf = dict(pdt=defaults.PDT, p_ex=defaults.P_EX, p_sted=0.0)
-        om.get_signal_and_bleach(dm, helpers.PX, **conf, bleach=False)
-        om.get_signal_and_bleach(dm, helpers.PX, pdt=actions[i, 2], p_ex=actions[i, 1], p_sted=actions[i, 0],
+        om.get_signal_and_bleach(dm, PX, **conf, bleach=False)
+        om.get_signal_and_bleach(dm, PX, pdt=actions[i, 2], p_ex=actions[i, 1], p_sted=actions[i, 0],
                                  bleach=True, seed=i + 1)
-        om.get_signal_and_bleach(dm, helpers.PX, **conf, bleach=False)
-        dm2 = po.Datamap(maps[n_envs + i], helpers.PX); dm2.set_roi(i_ex, "max")
-        om.get_signal_and_bleach(dm2, helpers.PX, **conf, bleach=False)
+        om.get_signal_and_bleach(dm, PX, **conf, bleach=False)
+        dm2 = po.Datamap(maps[n_envs + i], PX); dm2.set_roi(i_ex, "max")
+        om.get_signal_and_bleach(dm2, PX, **conf, bleach=False)
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads) as ex:
@@ -180,7 +189,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "STED acquisitions/sec", "value": value, "unit": "acquisitions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n_envs, 1),
+        "config": workload_config(args, n_envs, 1, schedule=f"one environment per host thread ({cores} threads), the four "
+                                  f"acquisitions of an env-step one after the other; {n_envs} environments per step — the per-"
+                                  f"environment work is the GPU arm's, the batch is bounded so that a step takes seconds"),
         "cpu_baseline": {"value": value, "unit": "acquisitions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "acquisitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -212,13 +223,17 @@ def l2_note(envs, size):
     return f"inputs smaller than L2 ({mb:.0f} MB per step, not flushed): not a valid timing configuration, parity/contract runs only"
 
 
-def workload_config(args, envs_per_gpu, world):
-    return {"workload": f"ContextualMOSTED-easy-hslb-v0 acquisition schedule (conf, STED+bleach, conf, conf-on-new-map), "
+def workload_config(args, envs_per_gpu, world, schedule=None):
+    name = {"acquisitions": "ContextualMOSTED-easy-hslb-v0 acquisition schedule",
+            "config5": "BASELINE config 5 (512x512 synthetic spine datamaps, 2048 envs env-parallel), ContextualMOSTED acquisition schedule",
+            "env_step": "ContextualMOSTED-easy-hslb-v0 whole env.step (acquisitions + objectives + F1 + observation)"}[args.workload]
+    if schedule is None:
+        schedule = "sequential" if args.sequential else "next structure's confocal on a low-priority stream under the scan"
+    return {"workload": f"{name} (conf, STED+bleach, conf, conf-on-new-map), "
                         f"{envs_per_gpu} envs/GPU, {args.size}x{args.size} px, K=59, stochastic bleaching + Poisson detection",
             "envs_per_gpu": envs_per_gpu, "global_envs": envs_per_gpu * world, "image": [args.size, args.size],
             "psf": [K, K], "fluorophore": "high-signal_low-bleach", "actions": "uniform in action box",
-            "l2": l2_note(envs_per_gpu, args.size),
-            "schedule": "sequential" if args.sequential else "next structure's confocal on a low-priority stream under the scan",
+            "l2": l2_note(envs_per_gpu, args.size), "schedule": schedule,
             "parallelism": f"env-parallel x{world}, no data-path collective"}
 
 
@@ -235,9 +250,9 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
         dist.barrier()
-    from gym_sted_b200 import _lib, defaults, synapse
+    from gym_sted_b200 import _lib, defaults, envs, synapse
     from gym_sted_b200.batch import BatchedMicroscope
-    from tests import helpers  # builders only (no oracle use on this path except cpu_baseline below)
+    from gym_sted_b200.session import StedSession, pinned_empty
 
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
@@ -247,8 +262,7 @@ def run_ours(args, rank, local_rank, world):
     H = W = args.size
     B = args.envs
     env_base = rank * B
-    micro = helpers.product_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
-                                       background=defaults.DETECTOR["background"])
+    micro = envs.make_microscope(defaults.load_routine("high-signal_low-bleach"))     # detector: defaults.DETECTOR (noise + background)
     bm = BatchedMicroscope(micro, B, H, W, device=dev, env_base=env_base, seed=1234)
     # the next structure's confocal image does not depend on the current structure's acquisitions: it is acquired on
     # a low-priority stream with its own device buffers and fills the idle slots of the main stream's kernels (the
@@ -299,7 +313,7 @@ def run_ours(args, rank, local_rank, world):
         else:
             bm.set_datamaps(pool_dev[1], max_molecules=pool_tot[1])
             bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
-        launches[0] += 15     # 3 x (make_effective, gather, detect) + (make_effective, presample x2, bucket scan, sweep, detect)
+        launches[0] += 15     # 3 x (make_effective, gather, detect) + (make_effective, presample, bucket scan, scatter, sweep2, detect)
 
     scan_ev = []
 
@@ -373,82 +387,46 @@ def run_ours(args, rank, local_rank, world):
     scan_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev]))
     # the scan on its own (nothing co-running): three extra scans after the timed region
     scan_alone_ms = scan_ms
-    if bm_next is not None:
-        n_before = len(scan_ev)
-        for i in range(3):
-            bm.set_datamaps(pool_dev[0], max_molecules=pool_tot[0])
-            _scan_only(bm, actions_dev[args.warmup + i % max(args.steps, 1)], sig[1], True)
-            torch.cuda.synchronize(dev)
-        scan_alone_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev[n_before:]]))
+    n_before = len(scan_ev)
+    for i in range(5):
+        bm.set_datamaps(pool_dev[0], max_molecules=pool_tot[0])
+        torch.cuda.synchronize(dev)
+        _scan_only(bm, actions_dev[args.warmup + i % max(args.steps, 1)], sig[1], True)
+        torch.cuda.synchronize(dev)
+    scan_alone_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev[n_before:]]))
 
-    # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region
+    # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region.
+    # Sessions (sted_session_*): a structure is uploaded ONCE, as the next structure of the step before (its first confocal
+    # image is that step's observation, mosted_env.py:174-186), then the main session adopts it on the device and images
+    # it three times (conf, STED + bleaching, conf) and returns the bleached map.  Per step: 1 map up, 4 images + 1 map
+    # down, all uint16 (the env's observation dtype), host synchronisation at the end of every step.
     import ctypes
     lib = bm.lib
-    cache = micro._packed_cache(helpers.PX)
-    from gym_sted_b200.base import fluo_struct
-    fl = (_lib.StedFluoParams * B)(*[fluo_struct(micro.fluo, micro.excitation, micro.sted)] * B)
-    det = micro.detector.params()
-    # host buffers of the e2e leg: uint16 molecule maps / photon counts (STED_HOST_U16; the env's observation is uint16
-    # too, contextual_sted_env.py:93), pinned
-    h_sig = torch.empty((B, H, W), dtype=torch.uint16).pin_memory()
-    conf_np = [np.full(B, v) for v in (defaults.P_EX, 0.0, defaults.PDT)]
-    vp = ctypes.c_void_p
     e2e_steps = max(1, min(args.steps, 5))
-    # the STED call overwrites its host map with the bleached one, so every e2e step gets its own pinned copy of the
-    # current maps (prepared before the timed region); the fresh maps are only read
-    h_cur = [pool[0].to(torch.uint16).pin_memory() for _ in range(e2e_steps + 1)]
-    h_new = pool_pin[1].to(torch.uint16).pin_memory()
-
-    def host_acquire(h_map, p_ex, p_sted, pdt, flags, off, out=None):
-        _lib.check(lib.sted_acquire_host(h_map.data_ptr(), cache.ctypes.data_as(vp), ctypes.cast(fl, vp),
-                                         p_ex.ctypes.data_as(vp), p_sted.ctypes.data_as(vp), pdt.ctypes.data_as(vp),
-                                         B, H, W, K, flags | _lib.STED_HOST_U16, ctypes.byref(det), 1234, off, env_base, None,
-                                         (h_sig if out is None else out).data_ptr()))
-
-    # The next structure's confocal does not depend on the other three calls of the step: a second host thread issues it
-    # on low-priority streams (sted_acquire_host keeps its scratch and streams per thread; ctypes drops the GIL).
-    import queue
-    import threading
-    jobs, finished, failure = queue.Queue(), queue.Queue(), []
-    h_sig_next = torch.empty((B, H, W), dtype=torch.uint16).pin_memory()
-
-    def side_worker():
-        torch.cuda.set_device(dev)
-        try:
-            _lib.check(lib.sted_host_thread_priority(1))
-        except Exception as exc:                       # pragma: no cover - reported through the queue
-            failure.append(exc)
-        while True:
-            off = jobs.get()
-            if off is None:
-                return
-            try:
-                host_acquire(h_new, *conf_np, _lib.STED_SAMPLE_PHOTONS, off, out=h_sig_next)
-            except Exception as exc:                   # pragma: no cover
-                failure.append(exc)
-            finished.put(off)
-
-    worker = None
-    if not args.sequential:
-        worker = threading.Thread(target=side_worker, daemon=True)
-        worker.start()
+    main_sess = StedSession(micro, B, H, W, env_base=env_base, seed=1234)
+    next_sess = StedSession(micro, B, H, W, env_base=env_base, seed=1234 ^ 0x5EED, low_priority=not args.sequential)
+    h_maps = [pinned_empty((B, H, W), np.uint16) for _ in range(2)]
+    for i in range(2):
+        h_maps[i][...] = pool[i].numpy().astype(np.uint16)
+    h_out = [pinned_empty((B, H, W), np.uint16) for _ in range(4)]
+    h_bleached = pinned_empty((B, H, W), np.uint16)
+    conf_np = (defaults.PDT, defaults.P_EX, 0.0)
+    mol = max(pool_tot)
 
     def e2e_step(i):
         a = actions[i].numpy()
-        h_map = h_cur[i]
-        if worker is not None:
-            jobs.put(4 * i + 4)
-        host_acquire(h_map, *conf_np, _lib.STED_SAMPLE_PHOTONS, 4 * i + 1)
-        host_acquire(h_map, np.ascontiguousarray(a[:, 1]), np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 2]),
-                     _lib.STED_BLEACH | _lib.STED_SAMPLE_BLEACH | _lib.STED_SAMPLE_PHOTONS, 4 * i + 2)
-        host_acquire(h_map, *conf_np, _lib.STED_SAMPLE_PHOTONS, 4 * i + 3)
-        if worker is not None:
-            finished.get()
-            if failure:
-                raise failure[0]
-        else:
-            host_acquire(h_new, *conf_np, _lib.STED_SAMPLE_PHOTONS, 4 * i + 4)
+        next_sess.upload(h_maps[(i + 1) % 2], max_molecules=mol)
+        next_sess.acquire(*conf_np, bleach=False, out=h_out[3])
+        main_sess.acquire(*conf_np, bleach=False, out=h_out[0])
+        main_sess.acquire(np.ascontiguousarray(a[:, 2]), np.ascontiguousarray(a[:, 1]), np.ascontiguousarray(a[:, 0]),
+                          bleach=True, out=h_out[1])
+        main_sess.download(h_bleached)
+        main_sess.acquire(*conf_np, bleach=False, out=h_out[2])
+        main_sess.adopt(next_sess)                     # the next step images the structure uploaded in this one
+        dropped = main_sess.sync() + next_sess.sync()
+        assert dropped == 0
 
+    main_sess.upload(h_maps[0], max_molecules=mol)
     e2e_step(0)
     sync_all()
     t0 = time.perf_counter()
@@ -456,18 +434,25 @@ def run_ours(args, rank, local_rank, world):
         e2e_step(i + 1)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    if worker is not None:
-        jobs.put(None)
-        worker.join(timeout=10)
+    e2e_check = int(h_out[1].astype(np.int64).sum())          # the step's result was read on the host
+    main_sess.close(); next_sess.close()
     img_bytes = B * H * W * 2          # uint16 transport
-    h2d = 4 * img_bytes + 4 * (3 * K * K * 8 + B * (136 + 24))
+    h2d = img_bytes + 4 * (3 * B * 8)
     d2h = 4 * img_bytes + img_bytes
 
+    # ---- the one collective of the design: per-step rewards gathered on rank 0 over NCCL (outside the timed region)
+    gathered = None
+    if world > 1:
+        r_local = torch.full((B,), float(rank), dtype=torch.float32, device=dev)
+        allr = sted_dist.gather_rewards(r_local, world * B)
+        assert allr.shape == (world * B,) and all(float(allr[k * B]) == k for k in range(world)), "NCCL reward gather"
+        gathered = int(allr.numel())
+
     # ---- max over ranks
-    t = torch.tensor([ms, e2e_s, gather_ms, scan_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s, gather_ms, scan_ms, scan_alone_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_s, gather_ms, scan_ms = [float(x) for x in t.tolist()]
+    ms, e2e_s, gather_ms, scan_ms, scan_alone_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
         acq = ACQ_PER_STEP * B * world * args.steps
@@ -494,15 +479,17 @@ def run_ours(args, rank, local_rank, world):
                     "hbm": {"achieved": by_launch / (gather_ms * 1e-3) * 1e-9, "peak": peaks.get("hbm_gbs", 6650.0),
                             "unit": "GB/s", "peak_source": "measured" if peaks else "fallback"}}
         fl_scan = algorithmic_flops(H, W, True) * B
-        roofline_scan = {"bound": "fp32", "kernel": "presample_kernel x2 + bucket_scan_kernel + sweep_kernel<59,16,stoch> "
-                                                    "(one STED acquisition with in-scan bleaching)",
-                         "achieved": fl_scan / (scan_ms * 1e-3) * 1e-12, "peak": pk.value, "unit": "TFLOP/s",
-                         "frac": fl_scan / (scan_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
-                         "algorithmic_flops_per_launch": fl_scan, "launch_ms": scan_ms,
-                         "alone": {"launch_ms": scan_alone_ms, "frac": fl_scan / (scan_alone_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
-                                   "note": "same scan with nothing co-running, 3 launches after the timed region"},
-                         "note": "3N algorithmic flops (SURVEY 8d); the kernels execute 2N" + ("" if args.sequential else
-                                 "; timed with the next structure's low-priority gather co-running (run --sequential for the scan alone)")}
+        roofline_scan = {"bound": "fp32", "kernel": "presample_kernel<2> + bucket_scan_kernel + scatter_events_kernel + "
+                                                    "sweep2_kernel<59,16,1> (one STED acquisition with in-scan bleaching)",
+                         "achieved": fl_scan / (scan_alone_ms * 1e-3) * 1e-12, "peak": pk.value, "unit": "TFLOP/s",
+                         "frac": fl_scan / (scan_alone_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
+                         "algorithmic_flops_per_launch": fl_scan, "launch_ms": scan_alone_ms,
+                         "in_step": {"launch_ms": scan_ms, "frac": fl_scan / (scan_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
+                                     "note": "the same bracket inside the timed steps" + ("" if args.sequential else
+                                             ", where the next structure's low-priority gather shares the SMs with the scan")},
+                         "note": "3N algorithmic flops (SURVEY 8d); the kernels execute 2N.  Like the gather bracket, launch_ms is "
+                                 "taken with nothing else on the GPU (CUDA events on the launching stream, 5 scans after the timed "
+                                 "region, each on freshly loaded maps)"}
         cpu = None
         if not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -517,13 +504,95 @@ def run_ours(args, rank, local_rank, world):
         line = {
             "metric": "STED acquisitions/sec", "value": value, "unit": "acquisitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if args.workload == "config5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, B, world), "env_steps_per_s": value / ACQ_PER_STEP,
             "e2e": {"value": e2e_value, "unit": "acquisitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "sted_acquire_host (C ABI, pinned host buffers, uint16 counts: STED_HOST_U16)" + ("" if args.sequential else "; the next structure's call comes from a second host thread on low-priority streams"), "numa_bound": numa_bound},
+                    "steps": e2e_steps, "frac_of_device_resident": e2e_value / value,
+                    "api": "sted_session_* (C ABI, pinned host buffers, uint16 maps and counts): per step the next structure is "
+                           "uploaded once and imaged by a " + ("second" if args.sequential else "low-priority") + " session, the main "
+                           "session adopts it on the device, images it 3x and returns the bleached map; host sync every step",
+                    "numa_bound": numa_bound, "rewards_gathered_over_nccl": gathered},
             "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "roofline_scan": roofline_scan,
             "cpu_baseline": cpu,
         }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# whole env.step (acquisitions + rewards + observation), through the vector environment's public API
+# ------------------------------------------------------------------------------------------------
+def run_env_step(args, rank, local_rank, world):
+    """``VectorContextualMOSTED.step`` for B environments per GPU: every step returns its observation, rewards and
+    objectives as numpy arrays on the host, so the device-resident and the end-to-end number are the same number."""
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist.barrier()
+    from gym_sted_b200 import envs
+    from gym_sted_b200 import dist as sted_dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    B = args.envs
+    env = envs.make_vec("ContextualMOSTED-easy-hslb-v0", B, image_size=args.size, device=dev, seed=1234 + rank,
+                        env_base=rank * B, max_episode_steps=args.steps + args.warmup + 2)
+    rng = np.random.default_rng(rank)
+    env.reset(seed=1234 + rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    acts = rng.uniform(env.action_space.low, env.action_space.high, (args.steps + args.warmup, B, len(env.actions)))
+    for i in range(args.warmup):
+        env.step(acts[i])
+    sync_all()
+    if sampler.nvml is not None:
+        sampler.samples.clear()
+    sampler.lines.clear()
+    d2h = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        (img, vec), reward, done, _, info = env.step(acts[args.warmup + i])
+        d2h = img.nbytes + reward.nbytes + info["mo_objs"].nbytes
+    e1.record()
+    sync_all()
+    wall = time.perf_counter() - t0
+    ms = max(e0.elapsed_time(e1), wall * 1e3)            # the host work of a step is part of the step
+    clocks = sampler.stop()
+    rewards_all = sted_dist.gather_rewards(torch.as_tensor(reward, dtype=torch.float32, device=dev), world * B) if world > 1 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        steps_s = B * world * args.steps / (ms * 1e-3)
+        value = ACQ_PER_STEP * steps_s
+        line = {"metric": "STED acquisitions/sec", "value": value, "unit": "acquisitions/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, B, world, schedule="VectorContextualMOSTED.step: conf, STED+bleach, conf, objectives + "
+                                          "Otsu + decorrelation + nanodomain F1, new synapses generated on the device, confocal "
+                                          "of the new structure, uint16 observation to the host"),
+                "env_steps_per_s": steps_s,
+                "e2e": {"value": value, "unit": "acquisitions/s", "h2d_bytes_per_step": int(acts[0].nbytes), "d2h_bytes_per_step": int(d2h),
+                        "api": "gym_sted_b200.envs.make_vec(...).step(actions) -> numpy observation / reward / info",
+                        "note": "value IS the end-to-end number for this workload: every step ends on the host",
+                        "rewards_gathered_over_nccl": None if rewards_all is None else int(rewards_all.numel())},
+                "gpu_launches": None, "clocks": clocks, "roofline": None, "cpu_baseline": None,
+                "mean_reward": float(np.mean(reward))}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -535,8 +604,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=256, help="environments per GPU")
-    ap.add_argument("--size", type=int, default=256, help="image side in pixels")
+    ap.add_argument("--workload", default="acquisitions", choices=["acquisitions", "config5", "env_step"])
+    ap.add_argument("--envs", type=int, default=None, help="environments per GPU (default 256; config5: 2048 / N)")
+    ap.add_argument("--size", type=int, default=None, help="image side in pixels (default 256; config5: 512; env_step: 64)")
     ap.add_argument("--cpu-envs", type=int, default=None, help="env-steps in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sequential", action="store_true",
@@ -545,8 +615,14 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.size is None:
+        args.size = {"acquisitions": 256, "config5": 512, "env_step": 64}[args.workload]
+    if args.envs is None:
+        args.envs = 2048 // world if args.workload == "config5" else 256
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "env_step":
+        run_env_step(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -60,6 +60,7 @@ SIGNATURES = {
     "sted_session_upload": (_i, [_vp, _vp, _u32, _u64]),
     "sted_session_acquire": (_i, [_vp, _vp, _vp, _vp, _u32, ctypes.POINTER(StedDetectorParams), _d, _u64, _u64, _i64, _vp,
                                   _vp]),
+    "sted_session_adopt": (_i, [_vp, _vp]),
     "sted_session_download": (_i, [_vp, _vp, _u32]),
     "sted_session_sync": (_i, [_vp, ctypes.POINTER(_i64)]),
     "sted_session_device_map": (_i, [_vp, ctypes.POINTER(_vp)]),

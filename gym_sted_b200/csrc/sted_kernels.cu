@@ -907,36 +907,44 @@ __global__ void __launch_bounds__(S_THREADS, STOCH ? 3 : 2) sweep_kernel(const A
 // ------------------------------------------------------------------------------------------
 // K3b: the stochastic scan, second generation (sweep2_kernel).
 //
-// Same arithmetic as sweep_kernel<.., true> — dense gather of every scan row against the row-start counts, replay of
-// that row's pre-drawn deaths — reorganised around three measurements of round 1 (profiles/r01_summary.md):
+// Same arithmetic as sweep_kernel<.., true> — dense gather of scan rows against known counts, replay of the pre-drawn
+// deaths — reorganised around the measurements of round 1 (profiles/r01_summary.md) and of round 2
+// (profiles/r02_summary.md):
 //  * the grid was 512 CTAs on 444 slots (the second wave 15 % full): work items are now (environment, column strip,
 //    RANGE OF SCAN ROWS).  A range can start anywhere because the state of the map at scan row r0 is known in advance:
 //    the initial counts minus the deaths of the K-1 scan rows before r0 that hit band rows >= r0 (events carry the low
-//    byte of their scan row for this).  Four times as many, four times shorter CTAs leave a tail of a few percent;
-//  * replaying a row cost as much as half of its gather, on the critical path, in CAS-free but latency-bound atomics:
-//    only the ring decrements (one atomic per death) stay between two gathers; the intensity corrections — which touch
-//    nothing the next gather reads — are done by two extra warps WHILE the eight gather warps work on the next row;
-//  * three CTA-wide barriers per row: the ring has K+1 slots, so the row entering the band is installed in the slot
-//    of the row retired one iteration earlier and the retire/install step shares a phase with the decrements: two
-//    barriers per row.
+//    byte of their scan row for this).  Several times as many, shorter CTAs leave a tail of a few percent;
+//  * the row loop was latency bound (three CTA-wide barriers and a replay phase per scan row; barrier stalls lead the
+//    ncu stall list): scan rows are processed in GROUPS of T.  The T gathers of a group run back to back, without a
+//    barrier, against the counts at the START of the group; the deaths of the group then leave the ring in one phase
+//    (two barriers per group, not per row).  What a later row of the group saw too much — the molecules that died in
+//    the earlier rows of the group — is removed with the intensity corrections, which already existed for the taps a
+//    death removes from its own row: a death costs (T-1)/2 * K more fixed-point atomics on average;
+//  * those corrections touch nothing a gather reads, so two auxiliary warps apply them WHILE the eight gather warps
+//    work on the next group; the auxiliary warps also move the ring: the rows retired by the previous group leave for
+//    global memory and the rows the next group needs take their slots (ring of K + 2T - 1 rows).
 // ------------------------------------------------------------------------------------------
 constexpr int S2_GATHER = 256, S2_AUX = 64, S2_THREADS = S2_GATHER + S2_AUX;
+__host__ __device__ constexpr int s2_evcap(int T) { return T <= 2 ? 1024 : T == 3 ? 512 : 256; }
 
-template <int KT, int CT>
+template <int KT, int CT, int T>
 __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P, const BleachWs ws, const int RR) {
     constexpr int TC = 8 * CT;
     const int K = KT ? KT : P.K;
     const int KP = KT ? STED_KPITCH(KT) : P.KP;
-    const int NS = K + 1;                     // ring slots
+    const int NS = K + 2 * T - 1;             // ring slots
     const int PR = sweep_pitch(TC, KP);
     const int span = TC + K - 1;
 
     extern __shared__ __align__(128) float smem[];
-    float* ring = smem;                       // [K+1][PR] band of the molecule map (integer counts)
-    float* sWt = ring + NS * PR;              // [K][KP]   effective PSF E
-    float* sI = sWt + K * KP;                 // [2][TC]   dense row intensities (even / odd scan rows)
-    float* sScale = sI + 2 * TC;              // [2][TC]   2^30 / sI  (fixed-point scale of the corrections)
-    int* sCorr = reinterpret_cast<int*>(sScale + 2 * TC);    // [2][TC] sum of removed taps, fixed point
+    float* ring = smem;                       // [K+2T-1][PR] band of the molecule map (integer counts)
+    float* sWt = ring + NS * PR;              // [K][KP]    effective PSF E
+    float* sI = sWt + K * KP;                 // [2][T][TC] dense row intensities (even / odd groups)
+    float* sScale = sI + 2 * T * TC;          // [T][TC]    2^30 / sI  (fixed-point scale of the corrections)
+    int* sCorr = reinterpret_cast<int*>(sScale + T * TC);    // [T][TC] sum of removed taps, fixed point
+    constexpr int EVCAP = s2_evcap(T);        // staged events per group (the rest is read from global memory)
+    uint32_t* sEv = reinterpret_cast<uint32_t*>(sCorr + T * TC);            // [2][EVCAP] this / the previous group's events
+    int* sMeta = reinterpret_cast<int*>(sEv + 2 * EVCAP);                   // [2][2] their range in ws.ev
 
     const int b = blockIdx.z;
     const int c0 = blockIdx.x * TC;
@@ -954,7 +962,9 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
         const float4* w4 = reinterpret_cast<const float4*>(P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP);
         for (int i = tid; i < K * KP / 4; i += S2_THREADS) reinterpret_cast<float4*>(sWt)[i] = __ldg(w4 + i);
     }
-    if (tid < 2 * TC) sCorr[tid] = 0;
+    if (tid < T * TC) sCorr[tid] = 0;
+    if (T * TC > S2_THREADS)
+        for (int i = tid + S2_THREADS; i < T * TC; i += S2_THREADS) sCorr[i] = 0;
 
     // columns of the molecule map this strip writes back (each column has exactly one owner)
     const int p = K / 2;
@@ -962,7 +972,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
     const int xe = (c0 + TC >= W) ? P.Wpitch : c0 + TC + p;
     const int q4 = PR / 4;                    // float4 groups of a ring row
 
-    auto slot_of = [&](const int y) { return (KT ? y % (KT + 1) : y % NS) * PR; };
+    auto slot_of = [&](const int y) { return (KT ? y % (KT + 2 * T - 1) : y % NS) * PR; };
     auto fetch_row = [&](const int y, const int g) -> float4 {
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
         const int x = c0 + 4 * g;
@@ -979,8 +989,8 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
     };
     auto clamp_hi = [&](const int v) { return (unsigned long long)v > ws.cap ? (int)ws.cap : v; };
 
-    // band rows r0 .. r0+K-1 as they were BEFORE the scan ...
-    for (int i = tid; i < K * q4; i += S2_THREADS) {
+    // band rows r0 .. r0+K+T-2 (what the first group reads) as they were BEFORE the scan ...
+    for (int i = tid; i < (K + T - 1) * q4; i += S2_THREADS) {
         const int yy = i / q4, g = i - yy * q4;
         *reinterpret_cast<float4*>(ring + slot_of(r0 + yy) + 4 * g) = fetch_row(r0 + yy, g);
     }
@@ -999,106 +1009,167 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
         __syncthreads();
     }
 
-    // intensity of scan row r: dense gather minus the taps removed by the deaths of that row (auxiliary warps)
-    auto corrections_and_write = [&](const int r) {
-        const int par = r & 1;
-        const float* sc = sScale + par * TC;
-        int* corr = sCorr + par * TC;
-        const int ev_lo = __ldg(row_off + r), ev_hi = clamp_hi(__ldg(row_off + r + 1));
-        constexpr int EV_LANES = 4, EV_SLOTS = S2_AUX / EV_LANES;
-        const int sub = at % EV_LANES;
-        for (int q = ev_lo + at / EV_LANES; q < ev_hi; q += EV_SLOTS) {
-            const uint32_t ev = __ldg(ws.ev + q);
-            const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F, a = (ev >> 18) & 0x3F;
-            if (xl < 0 || xl >= span) continue;                       // another strip's pixel
-            const float* e = sWt + u * KP;
-            const int v0 = max(max(0, c0 + xl - W + 1), xl - (TC - 1)), v1 = min(a, xl + 1);   // 0 <= xl - v < TC
-#pragma unroll 4
-            for (int v = v0 + sub; v < v1; v += EV_LANES) atomicAdd(&corr[xl - v], __float2int_rn(e[v] * sc[xl - v]));
-        }
-        asm volatile("bar.sync 1, %0;" :: "n"(S2_AUX) : "memory");
-        for (int t = at; t < TC; t += S2_AUX) {
-            if (c0 + t < W) {
-                const float I = fmaxf(sI[par * TC + t] * (1.0f - (float)corr[t] * 9.313225746154785e-10f), 0.f);
-                const size_t o = ((size_t)b * H + r) * W + c0 + t;
+    // intensities of the group of scan rows R0 .. R0+Tg-1: dense gathers against the counts at the start of the group,
+    // minus (a) the taps a death removes from the rest of its own row and (b) everything the molecules that died in
+    // an earlier row of the group would have contributed to the later rows of the group: fixed-point sums in sCorr
+    // (filled between the two barriers of the group), applied here when the auxiliary warps write the rows out
+    auto write_rows = [&](const int R0, const int Tg, const int par) {
+        const float* dense = sI + par * T * TC;
+        for (int t = at; t < Tg * TC; t += S2_AUX) {
+            const int j = t / TC, c = t - j * TC;
+            if (c0 + c < W) {
+                const float I = fmaxf(dense[t] * (1.0f - (float)sCorr[t] * 9.313225746154785e-10f), 0.f);
+                const size_t o = ((size_t)b * H + R0 + j) * W + c0 + c;
                 if (P.intensity) P.intensity[o] = I;
                 P.signal[o] = I;                          // detect_kernel converts to photon counts
             }
-            corr[t] = 0;
+            sCorr[t] = 0;
         }
-        asm volatile("bar.sync 1, %0;" :: "n"(S2_AUX) : "memory");
     };
 
-    for (int r = r0; r < r1; ++r) {
-        const int par = r & 1;
-        float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+#if SWEEP_PROBE == 3
+    long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_a = clock64(), t_b;
+    const long long t_begin = t_a;
+#define S2_TICK(i) do { t_b = clock64(); t_ph[i] += t_b - t_a; t_a = t_b; } while (0)
+#else
+#define S2_TICK(i) do { } while (0)
+#endif
+    int grp = 0;
+    for (int R0 = r0; R0 < r1; R0 += T, ++grp) {
+        const int Tg = min(T, r1 - R0);
+        const int par = grp & 1;
+        S2_TICK(7);
         if (aux) {
-            // ---- auxiliary warps: prefetch the row entering the band, finish the previous row's intensities
-            if (at < q4) pre = fetch_row(r + K < P.Hp ? r + K : -1, at);
-            if (r > r0) corrections_and_write(r - 1);
-        } else {
-            // ---- gather warps: dense gather of scan row r against the row-start counts
-            float acc[CT];
+            // ---- auxiliary warps: the rows the previous group finished leave the ring, the rows the NEXT group needs
+            // take their slots (nothing of this group touches them); then the previous group's intensities
+            const int ev_lo = __ldg(row_off + R0), ev_hi = clamp_hi(__ldg(row_off + R0 + Tg));
+            {   // this group's events -> shared memory (read by every thread between the two barriers and by these warps
+                // during the next group): loads first, stores after, so that their latencies overlap
+                uint32_t* sev = sEv + par * EVCAP;
+                const int ns = min(ev_hi - ev_lo, EVCAP);
+                for (int i0 = 0; i0 < ns; i0 += 4 * S2_AUX) {
+                    uint32_t t4[4];
 #pragma unroll
-            for (int j = 0; j < CT; ++j) acc[j] = 0.f;
-            for (int uu = lane; uu < K; uu += 32) {
-                const float* drow = ring + slot_of(r + uu) + CT * warp;
-                const float* erow = sWt + uu * KP;
-                float win[CT + 4];
+                    for (int k = 0; k < 4; ++k) t4[k] = (i0 + k * S2_AUX + at < ns) ? __ldg(ws.ev + ev_lo + i0 + k * S2_AUX + at) : 0u;
 #pragma unroll
-                for (int j = 0; j < CT; j += 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(drow + j);
-                    win[j] = t.x; win[j + 1] = t.y; win[j + 2] = t.z; win[j + 3] = t.w;
+                    for (int k = 0; k < 4; ++k) if (i0 + k * S2_AUX + at < ns) sev[i0 + k * S2_AUX + at] = t4[k];
                 }
-                const int nchunk = KP / 4;
-#pragma unroll 5
-                for (int vc = 0; vc < nchunk; ++vc) {
-                    const float4 nw = *reinterpret_cast<const float4*>(drow + CT + 4 * vc);
-                    const float4 e = *reinterpret_cast<const float4*>(erow + 4 * vc);
-                    win[CT] = nw.x; win[CT + 1] = nw.y; win[CT + 2] = nw.z; win[CT + 3] = nw.w;
+                if (at == 0) { sMeta[2 * par] = ev_lo; sMeta[2 * par + 1] = ev_hi; }
+            }
+            for (int i = at; i < T * q4; i += S2_AUX) {
+                const int j = i / q4, g = i - j * q4;
+                const int y_old = R0 - T + j, y_new = y_old + NS;
+                if (grp > 0) retire_row(y_old, g);
+                *reinterpret_cast<float4*>(ring + slot_of(y_new) + 4 * g) = fetch_row(y_new, g);     // zeros below the map
+            }
+            S2_TICK(3);
+            if (grp > 0) write_rows(R0 - T, T, par ^ 1);
+            S2_TICK(4);
+        } else {
+            // ---- gather warps: dense gathers of scan rows R0 .. R0+Tg-1 against the counts at the start of the group
+            for (int j = 0; j < Tg; ++j) {
+                float acc[CT];
 #pragma unroll
-                    for (int j = 0; j < CT; ++j) {
-                        acc[j] = fmaf(e.x, win[j], acc[j]);
-                        acc[j] = fmaf(e.y, win[j + 1], acc[j]);
-                        acc[j] = fmaf(e.z, win[j + 2], acc[j]);
-                        acc[j] = fmaf(e.w, win[j + 3], acc[j]);
+                for (int jj = 0; jj < CT; ++jj) acc[jj] = 0.f;
+                for (int uu = lane; uu < K; uu += 32) {
+                    const float* drow = ring + slot_of(R0 + j + uu) + CT * warp;
+                    const float* erow = sWt + uu * KP;
+                    float win[CT + 4];
+#pragma unroll
+                    for (int jj = 0; jj < CT; jj += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(drow + jj);
+                        win[jj] = t.x; win[jj + 1] = t.y; win[jj + 2] = t.z; win[jj + 3] = t.w;
+                    }
+                    const int nchunk = KP / 4;
+#pragma unroll 5
+                    for (int vc = 0; vc < nchunk; ++vc) {
+                        const float4 nw = *reinterpret_cast<const float4*>(drow + CT + 4 * vc);
+                        const float4 e = *reinterpret_cast<const float4*>(erow + 4 * vc);
+                        win[CT] = nw.x; win[CT + 1] = nw.y; win[CT + 2] = nw.z; win[CT + 3] = nw.w;
+#pragma unroll
+                        for (int jj = 0; jj < CT; ++jj) {
+                            acc[jj] = fmaf(e.x, win[jj], acc[jj]);
+                            acc[jj] = fmaf(e.y, win[jj + 1], acc[jj]);
+                            acc[jj] = fmaf(e.z, win[jj + 2], acc[jj]);
+                            acc[jj] = fmaf(e.w, win[jj + 3], acc[jj]);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < CT; ++jj) win[jj] = win[jj + 4];
+                    }
+                }
+                const float tot = reduce_scatter<CT>(acc, lane);
+                constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
+                if ((lane & ((1 << SH) - 1)) == 0) {
+                    sI[(par * T + j) * TC + CT * warp + (lane >> SH)] = tot;
+                    sScale[j * TC + CT * warp + (lane >> SH)] = 1073741824.0f / fmaxf(tot, 1e-30f);
+                }
+            }
+            S2_TICK(0);
+        }
+        __syncthreads();
+        S2_TICK(aux ? 5 : 1);
+        // ---- between two groups, every thread: the pixels of this group's deaths lose their molecules, and the dwells
+        // that saw those molecules although they were gone lose the corresponding taps (eight lanes per death, all
+        // loads first so that every thread keeps eight independent chains in flight)
+        {
+            const uint32_t* sev = sEv + par * EVCAP;
+            const int ev_lo = sMeta[2 * par], n_ev = sMeta[2 * par + 1] - ev_lo;
+            for (int q = tid; q < n_ev; q += S2_THREADS) {
+                const uint32_t ev = q < EVCAP ? sev[q] : __ldg(ws.ev + ev_lo + q);
+                const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F;
+                const int rd = R0 + (int)(((ev >> 24) - (uint32_t)R0) & 255u);
+                if (xl >= 0 && xl < span) atomicAdd(&ring[slot_of(rd + u) + xl], -1.0f);
+            }
+            constexpr int EV_LANES = 8, EV_SLOTS = S2_THREADS / EV_LANES;
+            const int sub = tid % EV_LANES;
+            for (int q = tid / EV_LANES; q < n_ev; q += EV_SLOTS) {
+                const uint32_t ev = q < EVCAP ? sev[q] : __ldg(ws.ev + ev_lo + q);
+                const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F, a = (ev >> 18) & 0x3F;
+                if (xl < 0 || xl >= span) continue;                       // another strip's pixel
+                const int jd = (int)(((ev >> 24) - (uint32_t)R0) & 255u);       // row of the death inside the group
+                const int v0 = max(max(0, c0 + xl - W + 1), xl - (TC - 1));     // dwell column t = xl - v, 0 <= t < TC
+                const int vall = min(K, xl + 1);
+                const int jend = min(Tg, jd + u + 1);                           // tap row u - (j - jd) >= 0
+                for (int j = jd; j < jend; ++j) {
+                    const float* e = sWt + (u - (j - jd)) * KP;
+                    const float* sc = sScale + j * TC + xl;
+                    int* corr = sCorr + j * TC + xl;
+                    const int v1 = (j == jd) ? min(a, vall) : vall;
+                    float te[8], ts[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int v = v0 + sub + EV_LANES * k;
+                        const bool ok = v < v1;
+                        te[k] = ok ? e[v] : 0.f;
+                        ts[k] = ok ? sc[-v] : 0.f;
                     }
 #pragma unroll
-                    for (int j = 0; j < CT; ++j) win[j] = win[j + 4];
+                    for (int k = 0; k < 8; ++k) {
+                        const int v = v0 + sub + EV_LANES * k;
+                        if (v < v1) atomicAdd(corr - v, __float2int_rn(te[k] * ts[k]));
+                    }
                 }
             }
-            const float tot = reduce_scatter<CT>(acc, lane);
-            constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
-            if ((lane & ((1 << SH) - 1)) == 0) {
-                sI[par * TC + CT * warp + (lane >> SH)] = tot;
-                sScale[par * TC + CT * warp + (lane >> SH)] = 1073741824.0f / fmaxf(tot, 1e-30f);
-            }
         }
         __syncthreads();
-        // ---- between two gathers: the pixels of this row's deaths lose their molecule; band row r-1 (final since the
-        // previous iteration) leaves for global memory and row r+K takes its ring slot
-        {
-            const int ev_lo = __ldg(row_off + r), ev_hi = clamp_hi(__ldg(row_off + r + 1));
-            for (int q = ev_lo + tid; q < ev_hi; q += S2_THREADS) {
-                const uint32_t ev = __ldg(ws.ev + q);
-                const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F;
-                if (xl >= 0 && xl < span) atomicAdd(&ring[slot_of(r + u) + xl], -1.0f);
-            }
-            if (aux && at < q4) {
-                if (r > r0) retire_row(r - 1, at);
-                *reinterpret_cast<float4*>(ring + slot_of(r + K) + 4 * at) = pre;      // zeros below the map
-            }
-        }
-        __syncthreads();
+        S2_TICK(2);
     }
-    // ---- epilogue: last row's intensities, the band rows this range owns
-    if (aux) corrections_and_write(r1 - 1);
-    for (int i = tid; i < q4; i += S2_THREADS) retire_row(r1 - 1, i);
-    if (r1 == H)
-        for (int i = tid; i < (K - 1) * q4; i += S2_THREADS) {
-            const int yy = i / q4;
-            retire_row(H + yy, i - yy * q4);
-        }
+#if SWEEP_PROBE == 3
+    if (tid == 0 || tid == S2_GATHER) {
+        t_ph[6] = (tid == 0) ? grp : 0;
+        t_ph[7] = (tid == 0) ? (t_a - t_begin) : 0;     // whole loop, gather thread
+        if (tid == 0) { t_ph[3] = t_ph[4] = t_ph[5] = 0; } else { t_ph[0] = t_ph[1] = t_ph[2] = 0; }
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)t_ph[i]);
+    }
+#endif
+    // ---- epilogue: the last group's intensities, the band rows this range owns and has not written yet
+    const int Rl = r0 + (grp - 1) * T;        // first row of the last group
+    if (aux) write_rows(Rl, r1 - Rl, (grp - 1) & 1);
+    const int yend = (r1 == H) ? P.Hp : r1;
+    for (int i = tid; i < (yend - Rl) * q4; i += S2_THREADS) {
+        const int yy = i / q4;
+        retire_row(Rl + yy, i - yy * q4);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1262,34 +1333,49 @@ int pick_row_range(int B, int strips, int H, int slots) {
     return best_rr;
 }
 
-template <int KT, int CT>
+template <int KT, int CT, int T>
 int launch_sweep2_t(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     constexpr int TC = 8 * CT;
     const int PR = sweep_pitch(TC, P.KP);
-    const size_t smem = ((size_t)(P.K + 1) * PR + (size_t)P.K * P.KP + 6 * TC) * sizeof(float);
+    const size_t smem = ((size_t)(P.K + 2 * T - 1) * PR + (size_t)P.K * P.KP + 4 * T * TC + 2 * s2_evcap(T) + 4) * sizeof(float);
     int rc;
-    if ((rc = set_smem(sweep2_kernel<KT, CT>, smem))) return rc;
-    static thread_local int slots_cache[2] = {0, 0};               // concurrent CTAs on this device (per CT)
-    int& slots = slots_cache[CT == 16];
+    if ((rc = set_smem(sweep2_kernel<KT, CT, T>, smem))) return rc;
+    static thread_local int slots = 0;                             // concurrent CTAs on this device
     if (!slots) {
         int dev = 0, sms = 0, per_sm = 0;
         CUDA_TRY(cudaGetDevice(&dev));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep2_kernel<KT, CT>, S2_THREADS, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep2_kernel<KT, CT, T>, S2_THREADS, smem));
         slots = sms * (per_sm > 0 ? per_sm : 1);
     }
     const int strips = (P.W + TC - 1) / TC;
-    const int RR = pick_row_range(P.B, strips, P.H, slots);
+    int RR = pick_row_range(P.B, strips, P.H, slots);
+    RR = (RR + T - 1) / T * T;                                     // whole groups, except at the end of a range
     dim3 grid(strips, (P.H + RR - 1) / RR, P.B);
-    sweep2_kernel<KT, CT><<<grid, S2_THREADS, smem, st>>>(P, ws, RR);
+    sweep2_kernel<KT, CT, T><<<grid, S2_THREADS, smem, st>>>(P, ws, RR);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }
 
-int launch_sweep2(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
+template <int T>
+int launch_sweep2_g(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     const bool wide = P.W > SWEEP_WIDE_MIN;
-    if (P.K == 59) return wide ? launch_sweep2_t<59, 16>(P, ws, st) : launch_sweep2_t<59, 8>(P, ws, st);
-    return wide ? launch_sweep2_t<0, 16>(P, ws, st) : launch_sweep2_t<0, 8>(P, ws, st);
+    if (P.K == 59) return wide ? launch_sweep2_t<59, 16, T>(P, ws, st) : launch_sweep2_t<59, 8, T>(P, ws, st);
+    return wide ? launch_sweep2_t<0, 16, T>(P, ws, st) : launch_sweep2_t<0, 8, T>(P, ws, st);
+}
+
+#ifndef SWEEP_GROUP
+#define SWEEP_GROUP 1          // scan rows gathered between two barriers (measured: 1 -> 3.89 ms, 2 -> 4.16 ms, 4 -> 4.58 ms)
+#endif
+int launch_sweep2(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
+    int T = SWEEP_GROUP;
+    if (const char* e = getenv("STED_B200_ROW_GROUP")) T = atoi(e);            // tuning knob
+    switch (T) {
+        case 2: return launch_sweep2_g<2>(P, ws, st);
+        case 3: return launch_sweep2_g<3>(P, ws, st);
+        case 4: return launch_sweep2_g<4>(P, ws, st);
+        default: return launch_sweep2_g<1>(P, ws, st);
+    }
 }
 
 int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -1746,7 +1832,8 @@ struct StedSession {
     int device = -1, B = 0, H = 0, W = 0, K = 0, KP = 0, Hp = 0, Wp = 0, Wpitch = 0;
     size_t n_roi = 0, n_pad = 0;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    cudaEvent_t e_up = nullptr, e_pad = nullptr, e_comp = nullptr, e_unpad = nullptr, e_out[NSIG] = {nullptr}, e_mapout = nullptr;
+    cudaEvent_t e_up = nullptr, e_pad = nullptr, e_comp = nullptr, e_unpad = nullptr, e_out[NSIG] = {nullptr}, e_mapout = nullptr,
+                e_lent = nullptr;            // another session has finished copying this session's map (sted_session_adopt)
     char* d_stage = nullptr;                 // un-padded upload / download staging [B][H][W] (4 bytes per pixel)
     float* d_map[2] = {nullptr, nullptr};    // padded maps, ping-pong
     float* d_tab = nullptr;
@@ -1776,6 +1863,20 @@ int session_bind(StedSession* s) {
     return STED_OK;
 }
 
+int session_reserve(StedSession* s, unsigned long long max_events) {
+    if (max_events <= s->max_events) return STED_OK;
+    s->max_events = max_events;
+    const size_t need = (bleach_ws_bytes(s->B, s->H, s->max_events) + 255) & ~(size_t)255;
+    if (need > s->ws_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(s->s_comp));
+        if (s->d_ws) cudaFree(s->d_ws);
+        s->d_ws = nullptr; s->ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&s->d_ws, need));
+        s->ws_bytes = need;
+    }
+    return STED_OK;
+}
+
 void session_free(StedSession* s) {
     if (!s) return;
     if (s->s_in) { cudaStreamSynchronize(s->s_in); cudaStreamSynchronize(s->s_comp); cudaStreamSynchronize(s->s_out); }
@@ -1787,7 +1888,7 @@ void session_free(StedSession* s) {
         if (s->e_out[i]) cudaEventDestroy(s->e_out[i]);
     }
     if (s->h_drop) cudaFreeHost(s->h_drop);
-    for (cudaEvent_t e : {s->e_up, s->e_pad, s->e_comp, s->e_unpad, s->e_mapout}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s->e_up, s->e_pad, s->e_comp, s->e_unpad, s->e_mapout, s->e_lent}) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {s->s_in, s->s_comp, s->s_out}) if (st) cudaStreamDestroy(st);
     delete s;
 }
@@ -1818,7 +1919,7 @@ int sted_session_create(int B, int H, int W, int K, const double* psf_cache_host
     S_TRY(cudaStreamCreateWithPriority(&s->s_in, cudaStreamNonBlocking, prio));
     S_TRY(cudaStreamCreateWithPriority(&s->s_comp, cudaStreamNonBlocking, prio));
     S_TRY(cudaStreamCreateWithPriority(&s->s_out, cudaStreamNonBlocking, prio));
-    for (cudaEvent_t* e : {&s->e_up, &s->e_pad, &s->e_comp, &s->e_unpad, &s->e_mapout}) S_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&s->e_up, &s->e_pad, &s->e_comp, &s->e_unpad, &s->e_mapout, &s->e_lent}) S_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     S_TRY(cudaMalloc(&s->d_stage, s->n_roi * 4));
     S_TRY(cudaMalloc(&s->d_map[0], s->n_pad * 4));
     S_TRY(cudaMalloc(&s->d_map[1], s->n_pad * 4));
@@ -1872,24 +1973,32 @@ int sted_session_upload(StedSession* s, const void* dmap_host, uint32_t flags, u
     CUDA_TRY(cudaMemcpyAsync(s->d_stage, dmap_host, s->n_roi * esz, cudaMemcpyHostToDevice, s->s_in));
     CUDA_TRY(cudaEventRecord(s->e_up, s->s_in));
     CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_up, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_lent, 0));           // a session that adopted the previous map has copied it
     const int p = s->K / 2;
     if (u16) pad_kernel<<<296, 256, 0, s->s_comp>>>((const uint16_t*)s->d_stage, s->d_map[s->cur], s->B, s->H, s->W, p, s->Hp, s->Wpitch);
     else pad_kernel<<<296, 256, 0, s->s_comp>>>((const float*)s->d_stage, s->d_map[s->cur], s->B, s->H, s->W, p, s->Hp, s->Wpitch);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->e_pad, s->s_comp));
     s->map_set = true;
-    if (max_molecules == 0) max_molecules = 4ull * s->n_roi;           // grown by sted_session_sync when a scan overflows
-    if (max_molecules + 16 > s->max_events) {
-        s->max_events = max_molecules + 16;
-        const size_t need = (bleach_ws_bytes(s->B, s->H, s->max_events) + 255) & ~(size_t)255;
-        if (need > s->ws_bytes) {
-            CUDA_TRY(cudaStreamSynchronize(s->s_comp));
-            if (s->d_ws) cudaFree(s->d_ws);
-            s->d_ws = nullptr; s->ws_bytes = 0;
-            CUDA_TRY(cudaMalloc(&s->d_ws, need));
-            s->ws_bytes = need;
-        }
-    }
+    if (max_molecules == 0) max_molecules = 4ull * s->n_roi;           // too small: sted_session_sync reports STED_EOVERFLOW
+    return session_reserve(s, max_molecules + 16);
+}
+
+int sted_session_adopt(StedSession* dst, StedSession* src) {
+    int rc = session_bind(dst);
+    if (rc) return rc;
+    if ((rc = session_bind(src))) return rc;
+    if (dst == src) return fail(STED_EINVAL, "a session cannot adopt its own map");
+    if (dst->B != src->B || dst->H != src->H || dst->W != src->W || dst->K != src->K)
+        return fail(STED_EINVAL, "sessions of different shapes");
+    if (!src->map_set) return fail(STED_EINVAL, "the source session has no map");
+    if ((rc = session_reserve(dst, src->max_events))) return rc;
+    // after everything queued on both sessions' compute streams; the source's next upload waits for the copy
+    CUDA_TRY(cudaEventRecord(src->e_comp, src->s_comp));
+    CUDA_TRY(cudaStreamWaitEvent(dst->s_comp, src->e_comp, 0));
+    CUDA_TRY(cudaMemcpyAsync(dst->d_map[dst->cur], src->d_map[src->cur], dst->n_pad * 4, cudaMemcpyDeviceToDevice, dst->s_comp));
+    CUDA_TRY(cudaEventRecord(src->e_lent, dst->s_comp));
+    dst->map_set = true;
     return STED_OK;
 }
 

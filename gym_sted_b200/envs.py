@@ -321,7 +321,8 @@ class ContextualSTEDMultiObjectivesEnv:
     def step(self, action):
         self.vec.max_episode_steps = self.spec.max_episode_steps
         (img, vec), reward, done, trunc, info = self.vec.step(np.asarray(action)[None])
-        one = {k: (v[0] if isinstance(v, (np.ndarray, list)) else v[0].cpu().numpy()) for k, v in info.items()}
+        one = {k: (v[0] if isinstance(v, (np.ndarray, list)) else v[0].cpu().numpy()) for k, v in info.items()
+               if k != "invalid"}                            # the reference's info keys only (contextual_sted_env.py:69-81)
         return (img[0], vec[0]), float(reward[0]), bool(done[0]), False, one
 
     def close(self):

@@ -106,6 +106,11 @@ class StedSession:
             intensity_out.ctypes.data_as(_VP) if intensity_out is not None else None))
         return out
 
+    def adopt(self, other: "StedSession"):
+        """Take over ``other``'s current maps (queued device-to-device copy): the structure ``other`` uploaded and imaged
+        as the NEXT structure becomes this session's current one."""
+        _lib.check(self.lib.sted_session_adopt(self._h, other._h))
+
     def download(self, out: np.ndarray):
         """Queue the download of the current (bleached) maps into ``out`` ((B,H,W) uint16 or float32)."""
         assert out.shape == (self.B, self.H, self.W) and out.flags.c_contiguous

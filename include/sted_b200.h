@@ -202,6 +202,11 @@ int sted_session_upload(StedSession* s, const void* dmap_host, uint32_t flags, u
 int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* p_sted_host, const double* pdt_host,
                          uint32_t flags, const StedDetectorParams* det, double lambda_fluo, uint64_t seed, uint64_t offset,
                          int64_t env_base, void* signal_host, float* intensity_host);
+/* dst takes over src's current maps (device-to-device, queued after everything already queued on both sessions).
+ * gym-sted's step ends with the first confocal image of the NEXT structure (mosted_env.py:174-186), which is the
+ * structure the next step images three times: a low-priority session uploads and images it while the main session
+ * works, then the main session adopts it — one upload per structure.  Same B, H, W, K required. */
+int sted_session_adopt(StedSession* dst, StedSession* src);
 /* Current (bleached) maps -> host, same format rules as sted_session_upload. */
 int sted_session_download(StedSession* s, void* dmap_host, uint32_t flags);
 /* Waits for everything queued on the session; *dropped_events (may be NULL) = deaths that did not fit the scratch. */

@@ -40,6 +40,13 @@ def scan(n, label):
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
     t = float(np.median(times[1:])) if n > 1 else times[0]
+    import ctypes
+    ph = (ctypes.c_uint64 * 8)()
+    bm.lib.sted_debug_phase_cycles(ph, 1)
+    if sum(ph):                                          # SWEEP_PROBE == 3 build: cycles per group of rows and CTA
+        g = max(1, ph[6])
+        names = ("gather", "g.wait1", "g.phaseB", "aux.stage+ring", "aux.corr", "aux.wait1")
+        print("    per group: " + "  ".join(f"{nm} {ph[i] / g:.0f}" for i, nm in enumerate(names)) + f"  loop {ph[7] / g:.0f}", flush=True)
     print(f"{label:40s} {t:7.3f} ms   {flops / t / 1e9:6.1f} TFLOP/s (3N)   deaths/env {int(maps.sum() - bm.datamaps_roi().sum().item()) // B}", flush=True)
     return t
 
