@@ -33,6 +33,11 @@ class StedFluoParams(ctypes.Structure):
         ("anti_stoke", ctypes.c_int32), ("_pad", ctypes.c_int32)]
 
 
+class StedFluoCriteria(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in ("sig_p_ex", "sig_p_sted", "sig_pdt", "sig_target", "bl_p_ex", "bl_p_sted",
+                                               "bl_pdt", "bl_target")]
+
+
 class StedDetectorParams(ctypes.Structure):
     _fields_ = [("pcef", ctypes.c_double), ("pdef", ctypes.c_double), ("background", ctypes.c_double)]
 
@@ -64,6 +69,7 @@ SIGNATURES = {
     "sted_session_download": (_i, [_vp, _vp, _u32]),
     "sted_session_sync": (_i, [_vp, ctypes.POINTER(_i64)]),
     "sted_session_device_map": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "sted_fluo_optimize": (_i, [_vp, _vp, _i, _i, _vp, ctypes.POINTER(StedDetectorParams), _vp, _i, _i, _vp, _vp]),
     "sted_sample_poisson": (_i, [_vp, _i64, _u64, _u64, _vp, _vp]),
     "sted_sample_binomial": (_i, [_vp, _vp, _i64, _u64, _u64, _vp, _vp]),
     "sted_philox4x32_10": (None, [ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),

@@ -129,10 +129,11 @@ def fluo_struct(fluo: Fluorescence, excitation: GaussianBeam, sted: DonutBeam) -
     if fluo.triplet_dynamics_frac:
         raise NotImplementedError("triplet_dynamics_frac != 0 is outside the modelled path "
                                   "(every gym-sted parameter set uses 0: defaults.py:41, routines.json)")
+    num = lambda v: float(np.asarray(v, dtype=np.float64).reshape(-1)[0])     # optimisers hand in 1-element arrays
     return _lib.StedFluoParams(
-        excitation.lambda_, sted.lambda_, fluo.lambda_, fluo.get_sigma_abs(excitation.lambda_),
-        fluo.sigma_abs.get(int(round(sted.lambda_ * 1e9)), 0.0), fluo.get_sigma_ste(sted.lambda_), fluo.qy, fluo.tau,
-        fluo.tau_vib, fluo.tau_tri, fluo.k0, fluo.k1, fluo.b, fluo.triplet_dynamics_frac, sted.tau, sted.rate,
+        excitation.lambda_, sted.lambda_, fluo.lambda_, num(fluo.get_sigma_abs(excitation.lambda_)),
+        num(fluo.sigma_abs.get(int(round(sted.lambda_ * 1e9)), 0.0)), num(fluo.get_sigma_ste(sted.lambda_)), fluo.qy, fluo.tau,
+        fluo.tau_vib, fluo.tau_tri, num(fluo.k0), num(fluo.k1), num(fluo.b), fluo.triplet_dynamics_frac, sted.tau, sted.rate,
         int(bool(sted.anti_stoke)), 0)
 
 

@@ -79,7 +79,7 @@ class BleachSampler:
         self.criterions = criterions or defaults.fluorescence_criterions
         if mode not in ("constant", "uniform", "choice"):
             raise ValueError(f"unknown bleach sampling mode {mode!r}")
-        self._anchor = None
+        self._optimizer, self.criteria = None, None
 
     def _draw(self, v):
         if isinstance(v, (list, tuple)):
@@ -88,44 +88,38 @@ class BleachSampler:
             return self.rng.uniform(*v)
         return v
 
-    def sample(self, microscope=None):
+    def draw_criteria(self):
+        """One ``UniformCriterion`` / ``ChoiceCriterion`` (``utils.py:718-769``): dict order, one draw per range."""
+        return {k: {kk: self._draw(vv) for kk, vv in v.items()} for k, v in self.criterions.items()}
+
+    def sample_batch(self, n, microscope=None, samples=None):
+        """``n`` fluorophore parameter dicts.  ``uniform`` / ``choice``: ``n`` criteria are drawn and fitted together by
+        the device-side ``FluorescenceOptimizer`` (``optimizer.py``), which follows the reference's optimisation path.
+        ``samples``: per environment the sample type whose correction factor sizes the test structure
+        (``optimizer.set_correction_factor(self.group)``, ``preference_sted_env.py:154``); one launch per distinct factor."""
         if self.mode == "constant":
-            return self.value or defaults.FLUO
-        crit = {k: {kk: self._draw(vv) for kk, vv in v.items()} for k, v in self.criterions.items()}
-        fluo = {k: (dict(v) if isinstance(v, dict) else v) for k, v in defaults.FLUO.items()}
-        if self._anchor is None:
-            self._anchor = _ClosedForms(microscope or make_microscope())
-        s, bl = crit["signal"], crit["bleach"]
-        fluo["sigma_abs"][635] = self._anchor.sigma_abs_for(s["p_ex"], s["pdt"], s["target"])
-        fluo["k1"] = self._anchor.k1_for(fluo["sigma_abs"][635], bl["p_ex"], bl["p_sted"], bl["pdt"], bl["target"])
-        return fluo
+            return [self.value or defaults.FLUO] * n
+        from .optimizer import FluorescenceOptimizer
+        if self._optimizer is None:
+            self._optimizer = FluorescenceOptimizer(microscope or make_microscope())
+        opt = self._optimizer
+        self.criteria = [self.draw_criteria() for _ in range(n)]
+        fits = np.empty((n, 5))
+        names = ["clusters"] * n if samples is None else list(samples)
+        for name in sorted(set(names)):
+            idx = [i for i, s_ in enumerate(names) if s_ == name]
+            opt.set_correction_factor(name)
+            fits[idx] = opt.optimize_batch([self.criteria[i] for i in idx])
+        lam_ex = int(round(self._optimizer.microscope.excitation.lambda_ * 1e9))
+        out = []
+        for sigma, k1, b, _, _ in fits:
+            fluo = {k: (dict(v) if isinstance(v, dict) else v) for k, v in defaults.FLUO.items()}
+            fluo["sigma_abs"][lam_ex], fluo["k1"], fluo["b"] = float(sigma), float(k1), float(b)
+            out.append(fluo)
+        return out
 
-
-class _ClosedForms:
-    """The reference's own closed forms (``gym_sted/utils.py:599-661``) are linear in ``sigma_abs`` (signal)
-    and in ``k1`` (bleach hazard) once ``b`` is fixed, so both are solved directly from one evaluation."""
-
-    def __init__(self, microscope, factor=2.25, scale=40.0):
-        import scipy.ndimage as ndi
-        self.m = microscope
-        K = microscope.cache(defaults.PIXELSIZE)[0].shape[0]
-        blob = np.zeros((K, K))
-        blob[K // 2, K // 2] = 1
-        blob = ndi.gaussian_filter(blob, factor, mode="nearest", truncate=4.0)
-        self.blob = blob / blob.max() * scale
-
-    def sigma_abs_for(self, p_ex, pdt, target):
-        m = self.m
-        E = m.get_effective(defaults.PIXELSIZE, p_ex, 0.0)
-        photons = float((E * self.blob).sum()) / (6.62607015e-34 * 299792458.0 / m.fluo.lambda_)
-        signal = photons * m.detector.pcef * m.detector.pdef * pdt
-        return m.fluo.get_sigma_abs(m.excitation.lambda_) * target / signal
-
-    def k1_for(self, sigma_abs, p_ex, p_sted, pdt, target):
-        m = self.m
-        kb = m.get_k_bleach(defaults.PIXELSIZE, p_ex, p_sted, pdt)
-        hazard = float(kb.sum()) * pdt * sigma_abs / m.fluo.get_sigma_abs(m.excitation.lambda_)
-        return m.fluo.k1 * (-np.log(1.0 - target)) / hazard
+    def sample(self, microscope=None):
+        return self.sample_batch(1, microscope)[0]
 
 
 class VectorContextualMOSTED:
@@ -208,7 +202,7 @@ class VectorContextualMOSTED:
             self.np_rng = np.random.default_rng(seed)
             self.bleach_sampler.rng.seed(int(self.np_rng.integers(0, 2 ** 31 - 1)))
             self.torch_gen = None
-        fluos = [base.Fluorescence(**self.bleach_sampler.sample(self.microscope)) for _ in range(self.B)] \
+        fluos = [base.Fluorescence(**f) for f in self.bleach_sampler.sample_batch(self.B, self.microscope)] \
             if self.bleach_sampler.mode != "constant" else None
         if fluos is None:
             self.microscope = make_microscope(self.bleach_sampler.sample())
@@ -463,10 +457,7 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         self.groups = [self.datamap_generator.sample_group() for _ in range(self.B)]
         self.conf_p_ex = None
         if self.bleach_sampler.mode != "constant":
-            fluos = []
-            for g in self.groups:
-                self.bleach_sampler._anchor = _ClosedForms(self.microscope, factor=FACTORS[g])
-                fluos.append(base.Fluorescence(**self.bleach_sampler.sample(self.microscope)))
+            fluos = [base.Fluorescence(**f) for f in self.bleach_sampler.sample_batch(self.B, self.microscope, samples=self.groups)]
             self.bm.set_fluorophores(fluos)
         else:
             self.microscope = make_microscope(self.bleach_sampler.sample())

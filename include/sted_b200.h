@@ -214,6 +214,24 @@ int sted_session_sync(StedSession* s, int64_t* dropped_events);
 /* Device pointer of the current padded maps [B][Hp][Wpitch] (valid until the next bleaching acquisition / upload). */
 int sted_session_device_map(StedSession* s, float** map_dev);
 
+/* ---- Fluorophore fitting (gym_sted/utils.py:442-686, FluorescenceOptimizer.optimize; BleachSampler "uniform"/"choice",
+ * utils.py:339-376): for each environment the (sigma_abs, k1, b) that give a confocal signal of sig_target photons and a
+ * bleached fraction of bl_target under the stated imaging parameters, found along the path of the reference's optimiser
+ * (25 rounds of two L-BFGS-B fits, forward differences of 0.01 in the scaled variables, targets blended in).  A target
+ * <= 0 skips that criterion.  Detector noise is replaced by its expectation.
+ *   psf_cache_dev : float64 [3][K][K] (Microscope.cache);  blob_dev: float64 [K][K], the test structure of
+ *                   expected_confocal_signal (a Gaussian-filtered unit pixel scaled to a peak of 40 molecules), zero
+ *                   outside the centred square of half-side blob_radius
+ *   fluo_host     : start values (sigma_abs_ex, k1, b = defaults.FLUO) and the fixed parameters;  det_host: detector
+ *   out_dev       : float64 [B][5] = sigma_abs (m2), k1, b, signal reached (photons), bleach reached            */
+typedef struct StedFluoCriteria {
+    double sig_p_ex, sig_p_sted, sig_pdt, sig_target;
+    double bl_p_ex, bl_p_sted, bl_pdt, bl_target;
+} StedFluoCriteria;
+int sted_fluo_optimize(const double* psf_cache_dev, const double* blob_dev, int K, int blob_radius, const StedFluoParams* fluo_host,
+                       const StedDetectorParams* det_host, const StedFluoCriteria* criteria_dev, int B, int iterations,
+                       double* out_dev, void* stream);
+
 /* Samplers exposed for the statistical tests (same device functions the kernels use).
  *   out_dev[i] ~ Poisson(lambda_dev[i]) / Binomial(n_dev[i], q_dev[i]); counter = i. */
 int sted_sample_poisson(const float* lambda_dev, int64_t n, uint64_t seed, uint64_t offset,

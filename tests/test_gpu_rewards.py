@@ -152,8 +152,9 @@ def test_preference_count_rate_env():
     acts = np.tile(np.array([[0.08, 5e-6, 15e-6]], dtype=np.float32), (4, 1))
     acts[3] = [0.0, 20e-6, 100e-6]                                                # confocal at full power, long dwell
     (img, v), reward, done, trunc, info = vec.step(acts)
+    # the reference's keys (preference_sted_env.py:299-311) + the vector environments' per-env validity mask
     assert set(info) == {"action", "bleached", "sted_image", "conf1", "conf2", "fg_c", "fg_s", "mo_objs", "reward", "sample",
-                         "conf_params"}
+                         "conf_params", "invalid"}
     np.testing.assert_allclose(v[:, 0], vec.conf_p_ex / defaults.P_EX, rtol=1e-6)
     rate = info["sted_image"].amax(dim=(1, 2)).cpu().numpy() / acts[:, 2]
     assert np.array_equal(reward == -10.0, rate > 20e6)
