@@ -53,6 +53,8 @@ SIGNATURES = {
     "sted_make_effective": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sted_acquire": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _u32, ctypes.POINTER(StedDetectorParams), _d, _u64,
                           _u64, _i64, _vp, _vp, _vp, _u64, _vp]),
+    "sted_acquire_dwellmaps": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32,
+                                    ctypes.POINTER(StedDetectorParams), _d, _u64, _u64, _i64, _vp, _vp, _vp]),
     "sted_bleach_workspace_bytes": (_u64, [_i, _i, _u64]),
     "sted_bleach_dropped_events": (_i, [_vp, ctypes.POINTER(ctypes.c_int), _vp]),
     "sted_host_thread_priority": (_i, [_i]),

@@ -228,18 +228,16 @@ class Microscope:
                               bleach_func=None, sample_func=None, steps=None, sample_bleach=True):
         """One raster-scan acquisition of ``datamap`` (``gym_sted/envs/mosted_env.py:184,222,227,232``).
 
-        ``pdt`` and ``p_ex`` may be scalars or (H, W) arrays (one value per dwell, as the timed environments pass:
-        ``gym_sted/envs/timed_sted_env.py:141-148``); ``p_sted`` must be a scalar (the depletion efficiency is not
-        separable in it).  The whole padded map takes part — molecules a caller placed in the K//2 frame are imaged
-        and bleached like pySTED does — and with ``bleach`` and ``update`` the datamap is mutated in place."""
+        ``pdt``, ``p_ex`` and ``p_sted`` may be scalars or (H, W) arrays with one value per dwell, as the timed
+        environments pass them (``gym_sted/envs/timed_sted_env.py:141-148``).  Constant arrays take the scalar path;
+        anything else runs the general dwell-by-dwell scan (``sted_acquire_dwellmaps``), which allows up to 256
+        distinct ``p_sted`` values per image.  The whole padded map takes part — molecules a caller placed in the
+        K//2 frame are imaged and bleached like pySTED does — and with ``bleach`` and ``update`` the datamap is
+        mutated in place."""
         import torch  # device memory only
 
         if datamap.roi is None:
             raise ValueError("Datamap ROI is not set; call datamap.set_roi(i_ex, 'max') first")
-        if np.ndim(p_sted):
-            if np.ptp(p_sted) != 0:
-                raise NotImplementedError("array-valued p_sted is outside the rebuilt path (per-dwell effective PSFs)")
-            p_sted = float(np.ravel(p_sted)[0])
         if pixel_list is not None or bleach_func is not None or sample_func is not None:
             raise NotImplementedError("custom pixel lists / bleach functions are outside the rebuilt path")
         lib = _lib.load()
@@ -253,15 +251,30 @@ class Microscope:
         Hp, Wp = H + K - 1, W + K - 1
         if whole.shape != (Hp, Wp):
             raise ValueError(f"datamap shape {whole.shape} does not match ROI {H}x{W} padded for K={K}")
-        per_dwell = bool(np.ndim(pdt) or np.ndim(p_ex))
+        maps = [np.asarray(x, dtype=np.float64) for x in (pdt, p_ex, p_sted)]
+        per_dwell = any(m.ndim and np.ptp(m) != 0 for m in maps)
+        n_tables = 1
         if per_dwell:
-            pdt_map = np.ascontiguousarray(np.broadcast_to(np.asarray(pdt, dtype=np.float64), (H, W)))
-            pex_map = np.ascontiguousarray(np.broadcast_to(np.asarray(p_ex, dtype=np.float64), (H, W)))
-            pdt_ref, pex_ref = float(pdt_map.max()), float(pex_map.max())
-            if not (pdt_ref > 0 and pex_ref >= 0):
-                raise ValueError("per-dwell pdt must be positive somewhere")
+            pdt_map, pex_map, psted_map = (np.ascontiguousarray(np.broadcast_to(m, (H, W))) for m in maps)
+            if pdt_map.min() < 0 or pex_map.min() < 0 or psted_map.min() < 0:
+                raise ValueError("pdt, p_ex and p_sted must be non-negative")
+            pdt_ref = float(pdt_map.max()) or 1e-6
+            # E and k_b are linear in p_ex unless the depletion beam also excites (anti_stoke): one table per distinct
+            # p_sted, or per distinct (p_ex, p_sted) pair in that case
+            if self.sted.anti_stoke and np.ptp(pex_map) != 0:
+                keys, table_id = np.unique(np.stack([pex_map.ravel(), psted_map.ravel()], 1), axis=0, return_inverse=True)
+                tab_pex, tab_psted, wex_map = keys[:, 0].copy(), keys[:, 1].copy(), np.ones((H, W))
+            else:
+                tab_psted, table_id = np.unique(psted_map.ravel(), return_inverse=True)
+                pex_ref = float(pex_map.max()) or 1e-6
+                tab_pex, wex_map = np.full(tab_psted.shape, pex_ref), pex_map / pex_ref
+            n_tables = int(tab_psted.size)
+            if n_tables > 256:
+                raise NotImplementedError(f"{n_tables} distinct depletion settings in one image; the general scan "
+                                          "holds at most 256")
         else:
-            pdt_ref, pex_ref = float(pdt), float(p_ex)
+            pdt_ref, pex_ref, p_sted = (float(m.reshape(-1)[0]) for m in maps)
+            tab_pex, tab_psted = np.array([pex_ref]), np.array([p_sted])
         flags = 0
         if bleach:
             flags |= _lib.STED_BLEACH
@@ -284,26 +297,28 @@ class Microscope:
         det = self.detector.params()
         d_cache = torch.from_numpy(cache).to(dev)
         d_fluo = torch.frombuffer(bytearray(bytes(fl)), dtype=torch.uint8).to(dev)
-        scal = torch.tensor([[pex_ref], [p_sted], [pdt_ref]], dtype=torch.float64, device=dev)
-        tables = torch.empty((1, _lib.STED_TABLES, K, _lib.kpitch(K)), dtype=torch.float32, device=dev)
+        d_fluo = d_fluo.repeat(n_tables)
+        scal = torch.from_numpy(np.stack([tab_pex, tab_psted, np.full(n_tables, pdt_ref)])).to(dev)
+        tables = torch.empty((n_tables, _lib.STED_TABLES, K, _lib.kpitch(K)), dtype=torch.float32, device=dev)
+        kb = torch.empty((n_tables, K, K), dtype=torch.float64, device=dev) if per_dwell else None
         _lib.check(lib.sted_make_effective(d_cache.data_ptr(), d_fluo.data_ptr(), scal[0].data_ptr(), scal[1].data_ptr(),
-                                           scal[2].data_ptr(), 1, K, tables.data_ptr(), None, st))
+                                           scal[2].data_ptr(), n_tables, K, tables.data_ptr(),
+                                           kb.data_ptr() if per_dwell else None, st))
         intensity = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         signal = torch.empty_like(intensity)
-        ws, ws_bytes = None, 0
-        if bleach and sample_bleach:
-            ws_bytes = int(lib.sted_bleach_workspace_bytes(1, H, int(max(whole.sum(), 0)) + 16))
-            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         if per_dwell:
-            # weights relative to the reference values the tables were built with
             d_wdt = torch.from_numpy(pdt_map / pdt_ref).to(dev, torch.float32).reshape(1, H, W).contiguous()
-            d_wex = torch.from_numpy(pex_map / pex_ref if pex_ref > 0 else pex_map).to(dev, torch.float32).reshape(1, H, W).contiguous()
+            d_wex = torch.from_numpy(wex_map).to(dev, torch.float32).reshape(1, H, W).contiguous()
+            d_tid = torch.from_numpy(table_id.astype(np.uint8)).to(dev).reshape(1, H, W).contiguous()
             _lib.check(lib.sted_acquire_dwellmaps(
-                d_in.data_ptr(), d_out.data_ptr() if bleach else None, tables.data_ptr(), scal[2].data_ptr(),
-                d_wdt.data_ptr(), d_wex.data_ptr(), 1, H, W, K, flags, ctypes.byref(det), float(self.fluo.lambda_),
-                int(seed), self._acq_counter, 0, intensity.data_ptr(), signal.data_ptr(),
-                ws.data_ptr() if ws is not None else None, ws_bytes, st))
+                d_in.data_ptr(), d_out.data_ptr() if bleach else None, tables.data_ptr(), kb.data_ptr(), scal[2].data_ptr(),
+                d_wdt.data_ptr(), d_wex.data_ptr(), d_tid.data_ptr(), n_tables, 1, H, W, K, flags, ctypes.byref(det),
+                float(self.fluo.lambda_), int(seed), self._acq_counter, 0, intensity.data_ptr(), signal.data_ptr(), st))
         else:
+            ws, ws_bytes = None, 0
+            if bleach and sample_bleach:
+                ws_bytes = int(lib.sted_bleach_workspace_bytes(1, H, int(max(whole.sum(), 0)) + 16))
+                ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
             _lib.check(lib.sted_acquire(
                 d_in.data_ptr(), d_out.data_ptr() if bleach else None, tables.data_ptr(), scal[2].data_ptr(), 1, H, W, K,
                 flags, ctypes.byref(det), float(self.fluo.lambda_), int(seed), self._acq_counter, 0,

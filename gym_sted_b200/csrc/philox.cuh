@@ -54,6 +54,7 @@ STED_HD Philox4 philox4x32_10(Philox4 c, uint32_t k0, uint32_t k1) {
 #define STED_RNG_TEST   3u
 #define STED_RNG_BLEACH2 4u
 #define STED_RNG_PHOTON2 5u
+#define STED_RNG_BLEACH3 6u   /* per-dwell binomials of the general scan: site = pixel, row field = tap index */
 
 // Stream of 32-bit words for one (pixel, env, purpose, row) site; refills by bumping a sub-counter.
 struct PhiloxStream {

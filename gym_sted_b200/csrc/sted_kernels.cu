@@ -123,6 +123,7 @@ struct AcqParams {
     float inv_e_photon;   // lambda_fluo/(h c)
     float det_eff;        // pcef*pdef
     float background;     // counts per second
+    const float* wdt;     // [B][H][W] dwell time of every pixel relative to pdt[b], or nullptr (general scan only)
 };
 
 // Detector.get_signal: photons = floor(I/e_photon); mean = photons*pcef*pdef*pdt + bg*pdt; Poisson when noisy.
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(DET_THREADS, 5) detect_kernel(const AcqParams 
                 const uint32_t pix = q_pix[q][slot];              // pixel index within this launch (< 2^31)
                 const int b = (int)(pix / hw);
                 const uint32_t site = (uint32_t)(pix - (size_t)b * hw);
-                const float dwell = (float)P.pdt[b];
+                const float dwell = (float)P.pdt[b] * (P.wdt ? P.wdt[pix] : 1.0f);
                 float* px = P.signal + pix;
                 *px = detect(P, *px, P.det_eff * dwell, P.background * dwell, P.env_base + (uint32_t)b, site, q_w0[q][slot],
                              q_w1[q][slot]);
@@ -370,14 +371,14 @@ __global__ void __launch_bounds__(DET_THREADS, 5) detect_kernel(const AcqParams 
             const uint32_t grp = (uint32_t)(g - (size_t)b * groups_per_env);
             const uint32_t env = P.env_base + (uint32_t)b;
             const float dwell = (float)P.pdt[b];
-            const float gain = P.det_eff * dwell, bg_mean = P.background * dwell;
             const uint32_t site = 2u * grp;
             const size_t pix = (size_t)b * hw + site;
             float* px = P.signal + pix;
             const bool two = site + 1 < hw;
+            const float d0 = dwell * (P.wdt ? P.wdt[pix] : 1.0f), d1 = dwell * ((P.wdt && two) ? P.wdt[pix + 1] : 1.0f);
             const float i0 = px[0], i1 = two ? px[1] : 0.0f;
-            const float m0 = floorf(i0 * P.inv_e_photon) * gain + bg_mean;
-            const float m1 = floorf(i1 * P.inv_e_photon) * gain + bg_mean;
+            const float m0 = floorf(i0 * P.inv_e_photon) * (P.det_eff * d0) + P.background * d0;
+            const float m1 = floorf(i1 * P.inv_e_photon) * (P.det_eff * d1) + P.background * d1;
             if (sample) {
                 Philox4 c;
                 c.x = grp; c.y = env; c.z = STED_RNG_PHOTON << 28; c.w = P.offset;
@@ -1173,6 +1174,144 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
 }
 
 // ------------------------------------------------------------------------------------------
+// K4: the general scan — per-dwell imaging parameters.
+//
+// The timed environments hand get_signal_and_bleach one dwell time PER PIXEL (gym_sted/envs/timed_sted_env.py:141-148:
+// `pdt * numpy.ones(dmap_shape)`, zeros where the experiment's clock runs out), and pySTED accepts the same for p_ex
+// and p_sted.  With per-dwell hazards the suffix-sum tables of the row sweep no longer describe a scan row, so this
+// path keeps the reference's order instead: dwells are visited one after the other, the K x K window of every dwell is
+// gathered and thinned cooperatively by the whole CTA (512 threads, band of K map rows in shared memory, float64 when
+// it fits), and the parallelism comes from the window and from the batch — one CTA per environment, which is what the
+// north star's "wavefront" amounts to once the footprints of consecutive dwells overlap (K = 59 against 64-pixel
+// rows: the dwells of a row never have disjoint footprints).
+//   I[r][c]      = w_ex[r][c] * sum E_j[u][v] * D[r+u][c+v]                      j = table_id[r][c]
+//   D[r+u][c+v] <- Binomial(D, exp(-A_j[u][v] * w_dt[r][c] * w_ex[r][c]))   or  D * exp(...) in expectation mode
+// with E_j, A_j = k_b * pdt_ref the tables of the j-th distinct (p_sted) value at the reference p_ex and pdt (E and
+// k_b are linear in p_ex; the photon-flux floor of get_photons moves k_b by < 1e-20 relative).  The per-dwell
+// binomials are the reference's own chain (sample_molecules), drawn with Philox keyed by (pixel, tap).
+// ------------------------------------------------------------------------------------------
+constexpr int GS_THREADS = 512;
+
+template <typename BandT>
+__global__ void __launch_bounds__(GS_THREADS) general_scan_kernel(const AcqParams P, const double* __restrict__ kbleach,
+                                                                  const float* __restrict__ w_dt, const float* __restrict__ w_ex,
+                                                                  const unsigned char* __restrict__ table_id, const int n_tables) {
+    const int K = P.K, KP = P.KP, KK = K * K, H = P.H, W = P.W, Wp = P.Wp, Hp = P.Hp;
+    extern __shared__ __align__(16) unsigned char gs_smem[];
+    double* sS = reinterpret_cast<double*>(gs_smem);                 // [KK] survival of the current dwell
+    BandT* band = reinterpret_cast<BandT*>(sS + KK);                 // [K][Wp] ring of map rows, slot = row % K
+    float* sE = reinterpret_cast<float*>(band + (size_t)K * Wp);     // [KK] effective PSF of the current table
+    float* sA = sE + KK;                                             // [KK] hazard k_b * pdt_ref of the current table
+    __shared__ double s_red[2][GS_THREADS / 32];     // double-buffered by dwell parity: one barrier per dwell
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const bool bleach = (P.flags & STED_BLEACH) != 0, stoch = bleach && (P.flags & STED_SAMPLE_BLEACH);
+    const float* din = P.din + (size_t)b * Hp * P.Wpitch;
+    float* dout = bleach ? P.dout + (size_t)b * Hp * P.Wpitch : nullptr;
+    const uint32_t env = P.env_base + (uint32_t)b;
+    const double pdt_ref = P.pdt[b];
+
+    auto load_table = [&](const int j) {
+        const float* tE = P.tables + ((size_t)(b * n_tables + j) * STED_TABLES + STED_TAB_E) * K * KP;
+        const double* kb = kbleach + (size_t)(b * n_tables + j) * KK;
+        for (int t = tid; t < KK; t += GS_THREADS) {
+            sE[t] = tE[(t / K) * KP + (t % K)];
+            sA[t] = (float)(kb[t] * pdt_ref);
+        }
+    };
+    for (int i = tid; i < K * Wp; i += GS_THREADS) {
+        const int y = i / Wp, x = i - y * Wp;
+        band[(size_t)(y % K) * Wp + x] = (y < Hp) ? (BandT)din[(size_t)y * P.Wpitch + x] : (BandT)0;
+    }
+    int cur_table = 0;
+    float cur_w = -1.0f;
+    load_table(0);
+    __syncthreads();
+
+    // taps of this thread: t = tid + i * GS_THREADS, fixed for the whole scan
+    constexpr int GS_TAPS = (STED_MAX_K * STED_MAX_K + GS_THREADS - 1) / GS_THREADS;
+    int tap_u[GS_TAPS], tap_v[GS_TAPS];
+#pragma unroll
+    for (int i = 0; i < GS_TAPS; ++i) {
+        const int t = tid + i * GS_THREADS;
+        tap_u[i] = t < KK ? t / K : -1;
+        tap_v[i] = t < KK ? t % K : 0;
+    }
+    int parity = 0, r0 = 0;                                            // r0 = r % K
+    for (int r = 0; r < H; ++r, r0 = (r0 + 1 == K ? 0 : r0 + 1)) {
+        for (int c = 0; c < W; ++c) {
+            const size_t o = ((size_t)b * H + r) * W + c;
+            const float wx = w_ex ? w_ex[o] : 1.0f;
+            const float w = (w_dt ? w_dt[o] : 1.0f) * wx;              // hazard scale of this dwell
+            const int j = table_id ? (int)table_id[o] : 0;
+            if (j != cur_table) {                                      // uniform: every thread reads the same dwell record
+                __syncthreads();
+                load_table(j);
+                cur_table = j;
+                cur_w = -1.0f;
+                __syncthreads();
+            }
+            if (bleach && !stoch && w != cur_w) {
+                for (int t = tid; t < KK; t += GS_THREADS) sS[t] = exp(-(double)sA[t] * (double)w);
+                cur_w = w;
+                __syncthreads();
+            }
+            double acc = 0.0;
+            if (wx != 0.0f || (bleach && w != 0.0f)) {
+#pragma unroll
+                for (int i = 0; i < GS_TAPS; ++i) {
+                    const int u = tap_u[i], v = tap_v[i];
+                    if (u < 0) continue;
+                    const int t = tid + i * GS_THREADS;
+                    int slot = r0 + u;
+                    slot -= slot >= K ? K : 0;
+                    BandT* cell = band + (size_t)slot * Wp + c + v;
+                    const BandT d = *cell;
+                    if (d != (BandT)0) {
+                        acc += (double)sE[t] * (double)d;
+                        if (stoch) {
+                            PhiloxStream rng;
+                            rng.init(P.seed, P.offset, env, (uint32_t)((r + u) * Wp + c + v), STED_RNG_BLEACH3, (uint32_t)t);
+                            *cell = d - (BandT)binomial_deaths((int)d, sA[t] * w, rng);
+                        } else if (bleach) {
+                            *cell = (BandT)((double)d * sS[t]);
+                        }
+                    }
+                }
+            }
+            for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if ((tid & 31) == 0) s_red[parity][tid >> 5] = acc;
+            __syncthreads();                                           // the only barrier of a dwell: orders the band
+            if (tid < 32) {                                            // updates and publishes the partial sums
+                double tot = tid < GS_THREADS / 32 ? s_red[parity][tid] : 0.0;
+                for (int off = 16; off; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+                if (tid == 0) {
+                    const float I = (float)(tot * (double)wx);
+                    if (P.intensity) P.intensity[o] = I;
+                    P.signal[o] = I;
+                }
+            }
+            parity ^= 1;
+        }
+        __syncthreads();
+        // map row r is final: it leaves the band and row r + K takes its slot
+        BandT* slot = band + (size_t)(r % K) * Wp;
+        for (int x = tid; x < Wp; x += GS_THREADS) {
+            if (bleach) dout[(size_t)r * P.Wpitch + x] = (float)slot[x];
+            slot[x] = (r + K < Hp) ? (BandT)din[(size_t)(r + K) * P.Wpitch + x] : (BandT)0;
+        }
+        __syncthreads();
+    }
+    if (bleach) {
+        for (int i = tid; i < (K - 1) * Wp; i += GS_THREADS) {
+            const int y = H + i / Wp, x = i % Wp;
+            dout[(size_t)y * P.Wpitch + x] = (float)band[(size_t)(y % K) * Wp + x];
+        }
+        for (int i = tid; i < Hp * (P.Wpitch - Wp); i += GS_THREADS)           // pitch padding stays zero
+            dout[(size_t)(i / (P.Wpitch - Wp)) * P.Wpitch + Wp + i % (P.Wpitch - Wp)] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // sampler test kernels, FMA peak
 // ------------------------------------------------------------------------------------------
 __global__ void poisson_test_kernel(const float* lam, int64_t n, uint64_t seed, uint32_t offset, float* out) {
@@ -1230,6 +1369,7 @@ int make_params(AcqParams& P, const float* din, float* dout, const float* tables
     P.inv_e_photon = (float)(lambda_fluo / (kPlanck * kLight));
     P.det_eff = (float)(det->pcef * det->pdef);
     P.background = (float)det->background;
+    P.wdt = nullptr;
     return STED_OK;
 }
 
@@ -1550,6 +1690,41 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
                                : launch_gather(P, (cudaStream_t)stream);
     if (rc) return rc;
     if (!(flags & STED_NO_DETECT) && (rc = launch_detect(P, (cudaStream_t)stream))) return rc;
+    return STED_OK;
+}
+
+int sted_acquire_dwellmaps(const float* dmap_in_dev, float* dmap_out_dev, const float* tables_dev, const double* kbleach_dev,
+                           const double* pdt_dev, const float* w_dwell_dev, const float* w_ex_dev, const uint8_t* table_id_dev,
+                           int n_tables, int B, int H, int W, int K, uint32_t flags, const StedDetectorParams* det, double lambda_fluo,
+                           uint64_t seed, uint64_t offset, int64_t env_base, float* intensity_dev, float* signal_dev, void* stream) {
+    AcqParams P;
+    int rc = make_params(P, dmap_in_dev, dmap_out_dev, tables_dev, pdt_dev, B, H, W, K, flags, det, lambda_fluo, seed, offset,
+                         env_base, intensity_dev, signal_dev);
+    if (rc) return rc;
+    if (n_tables < 1 || n_tables > 256) return fail(STED_EINVAL, "n_tables must lie in [1, 256]");
+    if (n_tables > 1 && !table_id_dev) return fail(STED_EINVAL, "several tables need table_id_dev");
+    if ((flags & STED_BLEACH) && !kbleach_dev) return fail(STED_EINVAL, "bleaching needs kbleach_dev (sted_make_effective's second output)");
+    if ((rc = check_device())) return rc;
+    P.wdt = w_dwell_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t fixed = (size_t)K * K * (sizeof(double) + 2 * sizeof(float));
+    const size_t band64 = (size_t)K * P.Wp * sizeof(double), band32 = (size_t)K * P.Wp * sizeof(float);
+    const size_t limit = 200 * 1024;
+    const double* kb = kbleach_dev;
+    if (!kb) {                               // no bleaching: the hazard table is never used, any valid pointer will do
+        kb = reinterpret_cast<const double*>(tables_dev);
+    }
+    if (fixed + band64 <= limit) {
+        if ((rc = set_smem(general_scan_kernel<double>, fixed + band64))) return rc;
+        general_scan_kernel<double><<<B, GS_THREADS, fixed + band64, st>>>(P, kb, w_dwell_dev, w_ex_dev, table_id_dev, n_tables);
+    } else if (fixed + band32 <= limit) {
+        if ((rc = set_smem(general_scan_kernel<float>, fixed + band32))) return rc;
+        general_scan_kernel<float><<<B, GS_THREADS, fixed + band32, st>>>(P, kb, w_dwell_dev, w_ex_dev, table_id_dev, n_tables);
+    } else {
+        return fail(STED_EUNSUPPORTED, "image too wide for the general scan (W + K - 1 = %d columns)", P.Wp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (!(flags & STED_NO_DETECT) && (rc = launch_detect(P, st))) return rc;
     return STED_OK;
 }
 

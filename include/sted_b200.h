@@ -140,6 +140,31 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
                  float* intensity_dev, float* signal_dev,
                  void* workspace_dev, uint64_t workspace_bytes, void* stream);
 
+/* The general scan: imaging parameters that change from dwell to dwell (pySTED accepts (H, W) arrays for pdt, p_ex and
+ * p_sted; the timed environments pass `pdt * numpy.ones(shape)` with zeros where the experiment's clock runs out,
+ * gym_sted/envs/timed_sted_env.py:141-148,199).  Dwells are visited in the reference's row-major order, each one
+ * gathering and bleaching its K x K window before the next starts; one CTA per environment works on a K-row band of
+ * the map held in shared memory.  Scalar parameters belong to sted_acquire, which is an order of magnitude faster.
+ *   tables_dev   : float32 [B][n_tables][STED_TABLES][K][KP] and
+ *   kbleach_dev  : float64 [B][n_tables][K][K]: sted_make_effective's outputs for B * n_tables parameter sets, built at
+ *                  the REFERENCE excitation power and dwell time of each environment (only STED_TAB_E is read);
+ *                  kbleach_dev may be NULL without STED_BLEACH
+ *   pdt_dev      : float64 [B] reference dwell time
+ *   w_dwell_dev  : float32 [B][H][W] dwell time of every pixel / reference dwell time, or NULL (= 1)
+ *   w_ex_dev     : float32 [B][H][W] excitation power of every pixel / reference power, or NULL (= 1): E and k_b are
+ *                  linear in p_ex (without DonutBeam.anti_stoke)
+ *   table_id_dev : uint8 [B][H][W] which of the n_tables (<= 256) parameter sets — distinct p_sted values — a dwell
+ *                  uses, or NULL (= 0)
+ *   others as sted_acquire; the detector uses each pixel's own dwell time.  Stochastic bleaching draws one binomial per
+ *   (dwell, window pixel) — pySTED's own chain — keyed by (seed, offset, env, pixel, tap); no workspace is needed.
+ * Limit: (W + K - 1) * K map values must fit in shared memory (W + K - 1 <= 600 at K = 59). */
+int sted_acquire_dwellmaps(const float* dmap_in_dev, float* dmap_out_dev, const float* tables_dev,
+                           const double* kbleach_dev, const double* pdt_dev, const float* w_dwell_dev,
+                           const float* w_ex_dev, const uint8_t* table_id_dev, int n_tables,
+                           int B, int H, int W, int K, uint32_t flags, const StedDetectorParams* det,
+                           double lambda_fluo, uint64_t seed, uint64_t offset, int64_t env_base,
+                           float* intensity_dev, float* signal_dev, void* stream);
+
 /* Scratch for STED_BLEACH|STED_SAMPLE_BLEACH: the deaths of the whole scan are drawn before it, staged and
  * bucketed by scan row (12 bytes per event).  max_events must cover the total molecule count of the B maps
  * (every 4096-pixel chunk reserves staging room for all of its molecules).  workspace_dev must be 8-byte

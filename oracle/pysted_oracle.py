@@ -274,6 +274,9 @@ def raster_lib():
         _lib.oracle_raster_batch.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp,
                                              ctypes.c_int, ctypes.c_uint64, dp]
         _lib.oracle_raster_batch.restype = None
+        _lib.oracle_raster_tables.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp,
+                                              ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_uint64, dp]
+        _lib.oracle_raster_tables.restype = None
     return _lib
 
 
@@ -288,6 +291,22 @@ def raster(padded, H, W, E, S, mode, seed=0):
     dp = ctypes.POINTER(ctypes.c_double)
     raster_lib().oracle_raster(padded.ctypes.data_as(dp), H, W, K, E.ctypes.data_as(dp), S.ctypes.data_as(dp),
                                int(mode), int(seed), out.ctypes.data_as(dp))
+    return out
+
+
+def raster_tables(padded, H, W, E, S, idx, mode, seed=0):
+    """Dwell loop with one (E, S) table per dwell: ``E``, ``S`` (n,K,K), ``idx`` (H,W) table index of every dwell."""
+    K = E.shape[-1]
+    assert padded.dtype == np.float64 and padded.flags.c_contiguous and padded.shape == (H + K - 1, W + K - 1)
+    E = np.ascontiguousarray(E, dtype=np.float64)
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    assert idx.shape == (H, W) and idx.min() >= 0 and idx.max() < E.shape[0] == S.shape[0]
+    out = np.empty((H, W), dtype=np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    raster_lib().oracle_raster_tables(padded.ctypes.data_as(dp), H, W, K, E.ctypes.data_as(dp), S.ctypes.data_as(dp),
+                                      idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(mode), int(seed),
+                                      out.ctypes.data_as(dp))
     return out
 
 
@@ -352,15 +371,25 @@ class Microscope:
                               sample_bleach=True):
         if datamap.roi is None:
             raise ValueError("datamap ROI is not set")
-        E = self.get_effective(pixelsize, p_ex, p_sted)
-        K = E.shape[0]
+        K = self.cache(pixelsize)[0].shape[0]
         rs, cs = datamap.roi
         H, W = rs.stop - rs.start, cs.stop - cs.start
         work = np.ascontiguousarray(datamap.whole_datamap, dtype=np.float64).copy()
         assert work.shape == (H + K - 1, W + K - 1)
-        S = np.exp(-self.get_k_bleach_map(pixelsize, p_ex, p_sted, pdt) * pdt)
         mode = 0 if not bleach else (2 if sample_bleach else 1)
-        intensity = raster(work, H, W, E, S, mode, 0 if seed is None else seed)
+        if np.ndim(pdt) or np.ndim(p_ex) or np.ndim(p_sted):
+            # per-dwell parameters (timed_sted_env.py:141-148): one table per distinct (pdt, p_ex, p_sted) triple,
+            # each from the physics above
+            trip = np.stack([np.broadcast_to(np.asarray(x, dtype=np.float64), (H, W)).ravel() for x in (pdt, p_ex, p_sted)], 1)
+            keys, idx = np.unique(trip, axis=0, return_inverse=True)
+            E = np.stack([self.get_effective(pixelsize, k[1], k[2]) for k in keys])
+            S = np.stack([np.exp(-self.get_k_bleach_map(pixelsize, k[1], k[2], k[0]) * k[0]) for k in keys])
+            intensity = raster_tables(work, H, W, E, S, idx.reshape(H, W), mode, 0 if seed is None else seed)
+            pdt = np.broadcast_to(np.asarray(pdt, dtype=np.float64), (H, W))
+        else:
+            E = self.get_effective(pixelsize, p_ex, p_sted)
+            S = np.exp(-self.get_k_bleach_map(pixelsize, p_ex, p_sted, pdt) * pdt)
+            intensity = raster(work, H, W, E, S, mode, 0 if seed is None else seed)
         photons = self.fluo.get_photons(intensity)
         rng = np.random.default_rng(seed)
         signal = self.detector.get_signal(photons, pdt, self.sted.rate, rng=rng)

@@ -90,6 +90,45 @@ void oracle_raster(double* D, int H, int W, int K, const double* E, const double
     }
 }
 
+/*
+ * Per-dwell imaging parameters (pySTED accepts (H, W) arrays for pdt, p_ex and p_sted; the timed environments use it,
+ * gym_sted/envs/timed_sted_env.py:141-148): dwell (r, c) uses the idx[r][c]-th effective PSF / survival table, i.e.
+ * the same loop as oracle_raster with E and S looked up per dwell.  The caller builds one table per distinct
+ * (pdt, p_ex, p_sted) triple directly from the physics — no linearity assumption is made here.
+ */
+void oracle_raster_tables(double* D, int H, int W, int K, const double* E, const double* S, const int32_t* idx,
+                          int mode, uint64_t seed, double* out) {
+    const int Wp = W + K - 1;
+    const size_t t = (size_t)K * K;
+    rng_t g;
+    rng_seed(&g, seed);
+    for (int r = 0; r < H; ++r) {
+        for (int c = 0; c < W; ++c) {
+            const double* Ej = E + t * (size_t)idx[(size_t)r * W + c];
+            const double* Sj = S + t * (size_t)idx[(size_t)r * W + c];
+            double acc = 0.0;
+            for (int u = 0; u < K; ++u) {
+                const double* d = D + (size_t)(r + u) * Wp + c;
+                for (int v = 0; v < K; ++v) acc += Ej[u * K + v] * d[v];
+            }
+            out[(size_t)r * W + c] = acc;
+            if (mode == 0) continue;
+            for (int u = 0; u < K; ++u) {
+                double* d = D + (size_t)(r + u) * Wp + c;
+                for (int v = 0; v < K; ++v) {
+                    const double s = Sj[u * K + v];
+                    if (mode == 1) { d[v] *= s; continue; }
+                    const long n = (long)d[v];
+                    if (n <= 0) continue;
+                    long kept = 0;
+                    for (long m = 0; m < n; ++m) kept += (rng_uniform(&g) <= s);
+                    d[v] = (double)kept;
+                }
+            }
+        }
+    }
+}
+
 /* Batched driver used by the CPU baseline: B independent maps, one after the other on this thread. */
 void oracle_raster_batch(double* D, int B, int H, int W, int K, const double* E, const double* S, int mode,
                          uint64_t seed, double* out) {

@@ -164,3 +164,33 @@ def test_oracle_microscope_mutates_datamap_like_pysted():
     assert bl["base"] is dm.whole_datamap and bl["base"].dtype == np.int64
     with pytest.raises(ValueError):
         m.get_signal_and_bleach(po.Datamap(np.ones((4, 4)), PX), PX, pdt=1e-5, p_ex=1e-5, p_sted=0)
+
+
+def test_raster_tables_reduces_to_raster_and_follows_the_dwell_order():
+    """oracle_raster_tables: with one table it IS oracle_raster; with per-dwell tables it equals a plain numpy
+    restatement of the dwell loop (look the table up, gather, thin the window, move on)."""
+    from oracle import pysted_oracle as po
+    rng = np.random.default_rng(0)
+    H, W, K, n = 9, 11, 5, 4
+    E = rng.uniform(0, 1, (n, K, K))
+    S = rng.uniform(0.5, 1, (n, K, K))
+    D0 = rng.integers(0, 20, (H + K - 1, W + K - 1)).astype(np.float64)
+    a, b = D0.copy(), D0.copy()
+    ia = po.raster(a, H, W, E[2], S[2], 1)
+    ib = po.raster_tables(b, H, W, E, S, np.full((H, W), 2), 1)
+    np.testing.assert_array_equal(ia, ib)
+    np.testing.assert_array_equal(a, b)
+    idx = rng.integers(0, n, (H, W))
+    c, d = D0.copy(), D0.copy()
+    ic = po.raster_tables(c, H, W, E, S, idx, 1)
+    idd = np.empty((H, W))
+    for r in range(H):
+        for q in range(W):
+            win = d[r:r + K, q:q + K]
+            idd[r, q] = (E[idx[r, q]] * win).sum()
+            win *= S[idx[r, q]]
+    np.testing.assert_allclose(ic, idd, rtol=1e-13)
+    np.testing.assert_allclose(c, d, rtol=1e-13)
+    e = D0.copy()
+    po.raster_tables(e, H, W, E, S, idx, 2, seed=3)
+    assert (e <= D0).all() and (e == np.floor(e)).all() and e.sum() < D0.sum()
