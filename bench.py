@@ -201,9 +201,9 @@ def run_reference(args, rank, world):
 
 def ncu_traffic(kernel_substr):
     """dram__bytes_read + dram__bytes_write per launch (bytes) from the committed `ncu --set full` summary of the
-    default workload (profiles/r01_ncu_summary.json); None when absent."""
+    default workload (profiles/r02_ncu_gather.json); None when absent."""
     try:
-        table = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+        table = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_gather.json")))
     except OSError:
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -228,7 +228,9 @@ def workload_config(args, envs_per_gpu, world, schedule=None):
             "config5": "BASELINE config 5 (512x512 synthetic spine datamaps, 2048 envs env-parallel), ContextualMOSTED acquisition schedule",
             "env_step": "ContextualMOSTED-easy-hslb-v0 whole env.step (acquisitions + objectives + F1 + observation)"}[args.workload]
     if schedule is None:
-        schedule = "sequential" if args.sequential else "next structure's confocal on a low-priority stream under the scan"
+        schedule = ("sequential: one session, every kernel on one stream" if args.sequential else
+                    "sessions: tables + death schedule of an acquisition under the one before it, detector under the one after "
+                    "it; next structure's confocal on a low-priority session")
     return {"workload": f"{name} (conf, STED+bleach, conf, conf-on-new-map), "
                         f"{envs_per_gpu} envs/GPU, {args.size}x{args.size} px, K=59, stochastic bleaching + Poisson detection",
             "envs_per_gpu": envs_per_gpu, "global_envs": envs_per_gpu * world, "image": [args.size, args.size],
@@ -263,13 +265,16 @@ def run_ours(args, rank, local_rank, world):
     B = args.envs
     env_base = rank * B
     micro = envs.make_microscope(defaults.load_routine("high-signal_low-bleach"))     # detector: defaults.DETECTOR (noise + background)
-    bm = BatchedMicroscope(micro, B, H, W, device=dev, env_base=env_base, seed=1234)
-    # the next structure's confocal image does not depend on the current structure's acquisitions: it is acquired on
-    # a low-priority stream with its own device buffers and fills the idle slots of the main stream's kernels (the
-    # scan's second wave above all); --sequential issues the four acquisitions one after the other instead
-    bm_next = None if args.sequential else BatchedMicroscope(micro, B, H, W, device=dev, env_base=env_base, seed=1234 ^ 0x5EED)
-    main_stream = torch.cuda.Stream(dev, priority=-1)
-    side_stream = torch.cuda.Stream(dev, priority=0)
+    if args.sequential:
+        os.environ["STED_B200_SESSION_SERIAL"] = "1"        # sessions queue every kernel on one stream (A/B of the schedule)
+    # The timed path drives resident SESSIONS (sted_session_*, include/sted_b200.h) with device-resident structures: a
+    # session runs the tables and the death schedule of an acquisition under the gather / scan queued before it and
+    # the detector under the one queued after it (own streams).  The next structure's confocal image does not depend on
+    # the current structure's acquisitions: a second, low-priority session uploads and images it and the main session
+    # then adopts the map, as gym-sted's step does (mosted_env.py:174-186).  --sequential: ONE session, one stream.
+    main_sess = StedSession(micro, B, H, W, env_base=env_base, seed=1234)
+    next_sess = None if args.sequential else StedSession(micro, B, H, W, env_base=env_base, seed=1234 ^ 0x5EED, low_priority=True)
+    bm = BatchedMicroscope(micro, B, H, W, device=dev, env_base=env_base, seed=1234)     # single-stream brackets ("alone")
 
     # synthetic inputs: two pools of B maps (current / fresh), resident in HBM and in pinned host memory
     n_unique = min(B, 32)
@@ -277,75 +282,75 @@ def run_ours(args, rank, local_rank, world):
     reps = (B + n_unique - 1) // n_unique
     pool = [torch.from_numpy(np.tile(maps_np[i * n_unique:(i + 1) * n_unique], (reps, 1, 1))[:B]).to(torch.float32)
             for i in range(2)]
-    pool_dev = [p.to(dev) for p in pool]
+    pool_dev = [p.to(dev).contiguous() for p in pool]
     pool_tot = [int(p.sum().item()) for p in pool]
-    pool_pin = [p.pin_memory() for p in pool]
+    mol = max(pool_tot)
     g = torch.Generator().manual_seed(1234 + rank)
     lo = torch.tensor([defaults.action_spaces[k]["low"] for k in ("p_sted", "p_ex", "pdt")], dtype=torch.float64)
     hi = torch.tensor([defaults.action_spaces[k]["high"] for k in ("p_sted", "p_ex", "pdt")], dtype=torch.float64)
     n_act = args.steps + args.warmup + 2
     actions = (lo + (hi - lo) * torch.rand((n_act, B, 3), generator=g, dtype=torch.float64))
     actions_dev = actions.to(dev)
+    actions_np = actions.numpy()
+    conf_np = (defaults.PDT, defaults.P_EX, 0.0)
     conf = [torch.full((B,), v, dtype=torch.float64, device=dev) for v in (defaults.PDT, defaults.P_EX, 0.0)]
-    sig = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(4)]
+    sig = [torch.empty((B, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
     launches = [0]
-    kern_ev = []
 
-    def step(i, timed):
-        """The four acquisitions of one ContextualMOSTED env-step for the whole batch (mosted_env.py:184,222-234)."""
-        a = actions_dev[i]
-        bm.set_datamaps(pool_dev[0], max_molecules=pool_tot[0])
-        ev = None
-        if timed:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        bm.make_effective(conf[1], conf[2], conf[0])
-        _gather_only(bm, conf[0], sig[0], ev)
-        cur = torch.cuda.current_stream(dev)
-        if bm_next is not None:
-            side_stream.wait_stream(cur)                 # after the bracketed gather: its timing stays undisturbed
-            with torch.cuda.stream(side_stream):
-                bm_next.set_datamaps(pool_dev[1], max_molecules=pool_tot[1])
-                bm_next.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
-        _scan_only(bm, a, sig[1], timed)
-        bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[2])
-        if bm_next is not None:
-            cur.wait_stream(side_stream)
+    def step(i):
+        """The four acquisitions of one ContextualMOSTED env-step for the whole batch (mosted_env.py:184,222-234); the
+        structures and the images stay on the device."""
+        a = actions_np[i]
+        if next_sess is not None:
+            next_sess.upload_device(pool_dev[(i + 1) % 2], max_molecules=mol)
+            next_sess.acquire(*conf_np, bleach=False)
+        main_sess.acquire(*conf_np, bleach=False)
+        main_sess.acquire(np.ascontiguousarray(a[:, 2]), np.ascontiguousarray(a[:, 1]), np.ascontiguousarray(a[:, 0]), bleach=True)
+        main_sess.acquire(*conf_np, bleach=False)
+        if next_sess is not None:
+            main_sess.adopt(next_sess)
         else:
-            bm.set_datamaps(pool_dev[1], max_molecules=pool_tot[1])
-            bm.get_signal_and_bleach(conf[0], conf[1], conf[2], bleach=False, out_signal=sig[3])
-        launches[0] += 15     # 3 x (make_effective, gather, detect) + (make_effective, presample, bucket scan, scatter, sweep2, detect)
+            main_sess.upload_device(pool_dev[(i + 1) % 2], max_molecules=mol)
+            main_sess.acquire(*conf_np, bleach=False)
+        # 3 x (make_effective, gather, detect) + (make_effective, presample, bucket scan, scatter, sweep2, detect) + pad
+        launches[0] += 16
 
-    scan_ev = []
+    def join_all():
+        main_sess.join()
+        if next_sess is not None:
+            next_sess.join()
 
-    def _scan_only(bm, a, out, timed):
-        """STED acquisition with stochastic bleaching; the scan (presample + bucket scan + sweep) is bracketed."""
+    def _scan_only(bm, a, out, evs):
+        """STED acquisition with stochastic bleaching on ONE stream; the scan (presample + bucket scan + scatter + sweep)
+        is bracketed."""
         import ctypes
         pdt, p_ex, p_sted = a[:, 2].contiguous(), a[:, 1].contiguous(), a[:, 0].contiguous()
         bm.make_effective(p_ex, p_sted, pdt)
         bm.offset += 1
         st = torch.cuda.current_stream(dev).cuda_stream
         flags = _lib.STED_BLEACH | _lib.STED_SAMPLE_BLEACH | _lib.STED_SAMPLE_PHOTONS
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if timed else None
-        if ev: ev[0].record()
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         _lib.check(bm.lib.sted_acquire(bm.dmap.data_ptr(), bm.dmap_alt.data_ptr(), bm.tables.data_ptr(), pdt.data_ptr(), bm.B,
                                        bm.H, bm.W, bm.K, flags | _lib.STED_NO_DETECT, ctypes.byref(bm.det), bm.lambda_fluo,
                                        bm.seed, bm.offset, bm.env_base, None, out.data_ptr(), bm.workspace.data_ptr(),
                                        bm.workspace_bytes, st))
-        if ev: ev[1].record(); scan_ev.append(ev)
+        ev[1].record(); evs.append(ev)
         _lib.check(bm.lib.sted_detect(out.data_ptr(), pdt.data_ptr(), bm.B, bm.H, bm.W, flags, ctypes.byref(bm.det),
                                       bm.lambda_fluo, bm.seed, bm.offset, bm.env_base, st))
         bm.dmap, bm.dmap_alt = bm.dmap_alt, bm.dmap
 
-    def _gather_only(bm, pdt, out, ev):
+    def _gather_only(bm, pdt, out, evs):
         import ctypes
         bm.offset += 1
         st = torch.cuda.current_stream(dev).cuda_stream
         flags = _lib.STED_SAMPLE_PHOTONS
-        if ev: ev[0].record()
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         _lib.check(bm.lib.sted_acquire(bm.dmap.data_ptr(), None, bm.tables.data_ptr(), pdt.data_ptr(), bm.B, bm.H,
                                        bm.W, bm.K, flags | _lib.STED_NO_DETECT, ctypes.byref(bm.det), bm.lambda_fluo,
                                        bm.seed, bm.offset, bm.env_base, None, out.data_ptr(), None, 0, st))
-        if ev: ev[1].record(); kern_ev.append(ev)
+        ev[1].record(); evs.append(ev)
         _lib.check(bm.lib.sted_detect(out.data_ptr(), pdt.data_ptr(), bm.B, bm.H, bm.W, flags, ctypes.byref(bm.det),
                                       bm.lambda_fluo, bm.seed, bm.offset, bm.env_base, st))
 
@@ -358,9 +363,12 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize(dev)
-    torch.cuda.set_stream(main_stream)       # everything below is issued on the high-priority stream
+    main_stream = torch.cuda.Stream(dev, priority=-1)
+    torch.cuda.set_stream(main_stream)       # the stream the timing events live on; it joins the sessions' streams
+    main_sess.upload_device(pool_dev[0], max_molecules=mol)
     for i in range(args.warmup):
-        step(i, False)
+        step(i)
+    join_all()
     sync_all()
     t_wait = time.perf_counter()
     while sampler.proc is not None and not sampler.lines and time.perf_counter() - t_wait < 3.0:
@@ -370,30 +378,46 @@ def run_ours(args, rank, local_rank, world):
         sampler.samples.clear()
     launches[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record()                              # the GPU is idle: this is the start of the region on the device
     for i in range(args.steps):
-        step(args.warmup + i, True)
-    e1.record()
+        step(args.warmup + i)
+    join_all()                               # main_stream waits for every stream of both sessions ...
+    e1.record()                              # ... so this fires when the last kernel of the region has finished
     sync_all()
     ms = e0.elapsed_time(e1)
+    assert main_sess.sync() == 0 and (next_sess is None or next_sess.sync() == 0), "bleaching events were dropped"
     n_launch = launches[0]                   # kernels launched inside the timed region
+    # device time of the gather / scan kernels inside the timed region (CUDA events on the session's compute stream)
+    per_step = 3 if next_sess is not None else 4
+    n_back = min(per_step * args.steps, 64)
+    k_ms = [main_sess.kernel_ms(k) for k in range(n_back)][::-1]          # oldest first
+    first = (per_step * args.steps - n_back) % per_step
+    gather_in = [t for k, t in enumerate(k_ms) if (k + first) % per_step != 1]
+    sweep_in = [t for k, t in enumerate(k_ms) if (k + first) % per_step == 1]
     if len(sampler.samples if sampler.nvml is not None else sampler.lines) < 3:      # very short timed region: keep the GPU under the same load a little longer
         t_more = time.perf_counter()
         while len(sampler.samples if sampler.nvml is not None else sampler.lines) < 3 and time.perf_counter() - t_more < 1.0:
-            step(args.warmup, False)
+            step(args.warmup)
+            join_all()
             torch.cuda.synchronize(dev)
     clocks = sampler.stop()
-    gather_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
-    scan_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev]))
-    # the scan on its own (nothing co-running): three extra scans after the timed region
-    scan_alone_ms = scan_ms
-    n_before = len(scan_ev)
+    gather_ms = float(np.mean(gather_in))
+    sweep_ms = float(np.mean(sweep_in))
+    # the same kernels with nothing co-running: single-stream device API, five repetitions after the timed region
+    kern_ev, scan_ev = [], []
     for i in range(5):
         bm.set_datamaps(pool_dev[0], max_molecules=pool_tot[0])
+        bm.make_effective(conf[1], conf[2], conf[0])
         torch.cuda.synchronize(dev)
-        _scan_only(bm, actions_dev[args.warmup + i % max(args.steps, 1)], sig[1], True)
+        _gather_only(bm, conf[0], sig[0], kern_ev)
         torch.cuda.synchronize(dev)
-    scan_alone_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev[n_before:]]))
+        _scan_only(bm, actions_dev[args.warmup + i % max(args.steps, 1)], sig[1], scan_ev)
+        torch.cuda.synchronize(dev)
+    gather_alone_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
+    scan_alone_ms = float(np.mean([a.elapsed_time(b) for a, b in scan_ev]))
+    main_sess.close()
+    if next_sess is not None:
+        next_sess.close()
 
     # ---- e2e: the reference-facing call with HOST buffers (pinned), copies inside the timed region.
     # Sessions (sted_session_*): a structure is uploaded ONCE, as the next structure of the step before (its first confocal
@@ -410,8 +434,6 @@ def run_ours(args, rank, local_rank, world):
         h_maps[i][...] = pool[i].numpy().astype(np.uint16)
     h_out = [pinned_empty((B, H, W), np.uint16) for _ in range(4)]
     h_bleached = pinned_empty((B, H, W), np.uint16)
-    conf_np = (defaults.PDT, defaults.P_EX, 0.0)
-    mol = max(pool_tot)
 
     def e2e_step(i):
         a = actions[i].numpy()
@@ -449,10 +471,10 @@ def run_ours(args, rank, local_rank, world):
         gathered = int(allr.numel())
 
     # ---- max over ranks
-    t = torch.tensor([ms, e2e_s, gather_ms, scan_ms, scan_alone_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s, gather_ms, sweep_ms, scan_alone_ms, gather_alone_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_s, gather_ms, scan_ms, scan_alone_ms = [float(x) for x in t.tolist()]
+    ms, e2e_s, gather_ms, sweep_ms, scan_alone_ms, gather_alone_ms = [float(x) for x in t.tolist()]
 
     if rank == 0:
         acq = ACQ_PER_STEP * B * world * args.steps
@@ -476,6 +498,13 @@ def run_ours(args, rank, local_rank, world):
                     "peak_source": "FP32 FFMA micro-benchmark run in this process (sted_fma_peak); "
                                    "MEASURED_PEAKS.json has no FP32 entry",
                     "algorithmic_flops_per_launch": fl_launch, "launch_ms": gather_ms,
+                    "launch_ms_note": "average over the gather kernels inside the timed region (CUDA events on the session's "
+                                      "compute stream, sted_session_kernel_ms)" + ("" if args.sequential else
+                                      "; the detector of the previous acquisition, the tables / death schedule of the next one "
+                                      "and the low-priority session's kernels share the SMs with it"),
+                    "alone": {"launch_ms": gather_alone_ms, "frac": fl_launch / (gather_alone_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
+                              "note": "the same kernel with nothing else on the GPU (single-stream device API, 5 launches after the "
+                                      "timed region)"},
                     "hbm": {"achieved": by_launch / (gather_ms * 1e-3) * 1e-9, "peak": peaks.get("hbm_gbs", 6650.0),
                             "unit": "GB/s", "peak_source": "measured" if peaks else "fallback"}}
         fl_scan = algorithmic_flops(H, W, True) * B
@@ -484,11 +513,13 @@ def run_ours(args, rank, local_rank, world):
                          "achieved": fl_scan / (scan_alone_ms * 1e-3) * 1e-12, "peak": pk.value, "unit": "TFLOP/s",
                          "frac": fl_scan / (scan_alone_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
                          "algorithmic_flops_per_launch": fl_scan, "launch_ms": scan_alone_ms,
-                         "in_step": {"launch_ms": scan_ms, "frac": fl_scan / (scan_ms * 1e-3) * 1e-12 / pk.value if pk.value else None,
-                                     "note": "the same bracket inside the timed steps" + ("" if args.sequential else
-                                             ", where the next structure's low-priority gather shares the SMs with the scan")},
-                         "note": "3N algorithmic flops (SURVEY 8d); the kernels execute 2N.  Like the gather bracket, launch_ms is "
-                                 "taken with nothing else on the GPU (CUDA events on the launching stream, 5 scans after the timed "
+                         "in_step": {"sweep2_ms": sweep_ms,
+                                     "note": "sweep2_kernel alone inside the timed steps (session compute stream)" + (
+                                             "" if args.sequential else "; its death schedule (presample + bucket scan + scatter) "
+                                             "was drawn on the session's second stream under the confocal gather before it, and the "
+                                             "low-priority session's gather shares the SMs with it")},
+                         "note": "3N algorithmic flops (SURVEY 8d); the kernels execute 2N.  launch_ms is the whole chain on one "
+                                 "stream with nothing else on the GPU (CUDA events on the launching stream, 5 scans after the timed "
                                  "region, each on freshly loaded maps)"}
         cpu = None
         if not args.no_cpu:

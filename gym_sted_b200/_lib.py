@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("STED_B200_LIB", os.path.join(_HERE, "libsted_b200.so"))
 
 STED_BLEACH, STED_SAMPLE_PHOTONS, STED_SAMPLE_BLEACH, STED_NO_DETECT, STED_HOST_U16, STED_FRAME_MOLECULES = 1, 2, 4, 8, 16, 32
+STED_PRESAMPLED = 64
 STED_TAB_E, STED_TAB_ET, STED_TAB_CH, STED_TAB_RS, STED_TAB_E2, STED_TABLES = 0, 1, 2, 3, 4, 8
 STED_MAX_K = 63
 
@@ -55,6 +56,7 @@ SIGNATURES = {
                           _u64, _i64, _vp, _vp, _vp, _u64, _vp]),
     "sted_acquire_dwellmaps": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32,
                                     ctypes.POINTER(StedDetectorParams), _d, _u64, _u64, _i64, _vp, _vp, _vp]),
+    "sted_bleach_presample": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _u32, _u64, _u64, _i64, _vp, _u64, _vp]),
     "sted_bleach_workspace_bytes": (_u64, [_i, _i, _u64]),
     "sted_bleach_dropped_events": (_i, [_vp, ctypes.POINTER(ctypes.c_int), _vp]),
     "sted_host_thread_priority": (_i, [_i]),
@@ -67,6 +69,10 @@ SIGNATURES = {
     "sted_session_upload": (_i, [_vp, _vp, _u32, _u64]),
     "sted_session_acquire": (_i, [_vp, _vp, _vp, _vp, _u32, ctypes.POINTER(StedDetectorParams), _d, _u64, _u64, _i64, _vp,
                                   _vp]),
+    "sted_session_upload_device": (_i, [_vp, _vp, _u32, _u64, _vp]),
+    "sted_session_result": (_i, [_vp, _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _i]),
+    "sted_session_kernel_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float)]),
+    "sted_session_join": (_i, [_vp, _vp]),
     "sted_session_adopt": (_i, [_vp, _vp]),
     "sted_session_download": (_i, [_vp, _vp, _u32]),
     "sted_session_sync": (_i, [_vp, ctypes.POINTER(_i64)]),

@@ -172,6 +172,7 @@ __device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -925,7 +926,13 @@ __global__ void __launch_bounds__(S_THREADS, STOCH ? 3 : 2) sweep_kernel(const A
 //    work on the next group; the auxiliary warps also move the ring: the rows retired by the previous group leave for
 //    global memory and the rows the next group needs take their slots (ring of K + 2T - 1 rows).
 // ------------------------------------------------------------------------------------------
-constexpr int S2_GATHER = 256, S2_AUX = 64, S2_THREADS = S2_GATHER + S2_AUX;
+#ifndef S2_FFMA2
+#define S2_FFMA2 0   // 1: packed FFMA2 gather loop (measured equal at best while the row loop is latency bound, see profiles/r02_summary.md)
+#endif
+#ifndef S2_AUX_THREADS
+#define S2_AUX_THREADS 64
+#endif
+constexpr int S2_GATHER = 256, S2_AUX = S2_AUX_THREADS, S2_THREADS = S2_GATHER + S2_AUX;
 __host__ __device__ constexpr int s2_evcap(int T) { return T <= 2 ? 1024 : T == 3 ? 512 : 256; }
 
 template <int KT, int CT, int T>
@@ -1028,7 +1035,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
         }
     };
 
-#if SWEEP_PROBE == 3
+#if SWEEP_PROBE >= 3
     long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_a = clock64(), t_b;
     const long long t_begin = t_a;
 #define S2_TICK(i) do { t_b = clock64(); t_ph[i] += t_b - t_a; t_a = t_b; } while (0)
@@ -1057,6 +1064,9 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
                 }
                 if (at == 0) { sMeta[2 * par] = ev_lo; sMeta[2 * par + 1] = ev_hi; }
             }
+#ifdef S2_ABLATE_RING                        // timing ablation only: the ring never moves
+            if (false)
+#endif
             for (int i = at; i < T * q4; i += S2_AUX) {
                 const int j = i / q4, g = i - j * q4;
                 const int y_old = R0 - T + j, y_new = y_old + NS;
@@ -1070,6 +1080,58 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
             // ---- gather warps: dense gathers of scan rows R0 .. R0+Tg-1 against the counts at the start of the group
             for (int j = 0; j < Tg; ++j) {
                 float acc[CT];
+#if S2_FFMA2
+                // FFMA2 (fma.rn.f32x2), one issue slot per two FMAs: the ncu profile of the scalar loop was issue bound
+                // (83 % of the issue slots for 65 % of the FMA pipe).  A tap E[u][v] — the instruction's scalar-broadcast
+                // operand — meets the datamap values of two neighbouring columns, which must be an even-aligned register
+                // pair of the sliding window: true for the column pairs (2p, 2p+1) when v is even and for the pairs
+                // (2q-1, 2q) when v is odd.  Hence two sets of packed accumulators, one per tap parity (the outer halves
+                // of the odd set, columns -1 and CT, are discarded: 1/16 more FMA work); a column's sum is even + odd.
+                u64 accA[CT / 2], accB[CT / 2 + 1];
+#pragma unroll
+                for (int pp = 0; pp < CT / 2; ++pp) accA[pp] = 0ull;
+#pragma unroll
+                for (int pp = 0; pp <= CT / 2; ++pp) accB[pp] = 0ull;
+                for (int uu = lane; uu < K; uu += 32) {
+                    const float* drow = ring + slot_of(R0 + j + uu) + CT * warp;
+                    const float* erow = sWt + uu * KP;
+                    u64 wp[CT / 2 + 2];                               // window pairs (w[2k], w[2k+1])
+#pragma unroll
+                    for (int jj = 0; jj < CT / 4; ++jj) {
+                        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(drow + 4 * jj);
+                        wp[2 * jj] = t.x; wp[2 * jj + 1] = t.y;
+                    }
+                    const int nchunk = KP / 4;
+#pragma unroll 5
+                    for (int vc = 0; vc < nchunk; ++vc) {
+                        const ulonglong2 nw = *reinterpret_cast<const ulonglong2*>(drow + CT + 4 * vc);
+                        const float4 e = *reinterpret_cast<const float4*>(erow + 4 * vc);
+                        wp[CT / 2] = nw.x; wp[CT / 2 + 1] = nw.y;
+                        const u64 e0 = pack2(e.x, e.x), e1 = pack2(e.y, e.y), e2 = pack2(e.z, e.z), e3 = pack2(e.w, e.w);
+#pragma unroll
+                        for (int pp = 0; pp < CT / 2; ++pp) {
+                            accA[pp] = fma2(e0, wp[pp], accA[pp]);
+                            accA[pp] = fma2(e2, wp[pp + 1], accA[pp]);
+                        }
+#pragma unroll
+                        for (int pp = 0; pp <= CT / 2; ++pp) {
+                            accB[pp] = fma2(e1, wp[pp], accB[pp]);
+                            accB[pp] = fma2(e3, wp[pp + 1], accB[pp]);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < CT / 2; ++jj) wp[jj] = wp[jj + 2];
+                    }
+                }
+#pragma unroll
+                for (int pp = 0; pp < CT / 2; ++pp) {
+                    float a0, a1, b0, b1, c0_, c1;
+                    unpack2(accA[pp], a0, a1);
+                    unpack2(accB[pp], b0, b1);            // (column 2pp-1, column 2pp)
+                    unpack2(accB[pp + 1], c0_, c1);        // (column 2pp+1, column 2pp+2)
+                    acc[2 * pp] = a0 + b1;
+                    acc[2 * pp + 1] = a1 + c0_;
+                }
+#else
 #pragma unroll
                 for (int jj = 0; jj < CT; ++jj) acc[jj] = 0.f;
                 for (int uu = lane; uu < K; uu += 32) {
@@ -1098,6 +1160,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
                         for (int jj = 0; jj < CT; ++jj) win[jj] = win[jj + 4];
                     }
                 }
+#endif
                 const float tot = reduce_scatter<CT>(acc, lane);
                 constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
                 if ((lane & ((1 << SH) - 1)) == 0) {
@@ -1115,14 +1178,23 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
         {
             const uint32_t* sev = sEv + par * EVCAP;
             const int ev_lo = sMeta[2 * par], n_ev = sMeta[2 * par + 1] - ev_lo;
+#ifdef S2_ABLATE_DEC                         // timing ablation only: nothing bleaches
+            if (false)
+#endif
             for (int q = tid; q < n_ev; q += S2_THREADS) {
                 const uint32_t ev = q < EVCAP ? sev[q] : __ldg(ws.ev + ev_lo + q);
                 const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F;
                 const int rd = R0 + (int)(((ev >> 24) - (uint32_t)R0) & 255u);
                 if (xl >= 0 && xl < span) atomicAdd(&ring[slot_of(rd + u) + xl], -1.0f);
             }
+#if SWEEP_PROBE == 4
+            if (!aux) S2_TICK(3);            // ring decrements of this thread done
+#endif
             constexpr int EV_LANES = 8, EV_SLOTS = S2_THREADS / EV_LANES;
             const int sub = tid % EV_LANES;
+#ifdef S2_ABLATE_CORR                        // timing ablation only: wrong intensities
+            if (false)
+#endif
             for (int q = tid / EV_LANES; q < n_ev; q += EV_SLOTS) {
                 const uint32_t ev = q < EVCAP ? sev[q] : __ldg(ws.ev + ev_lo + q);
                 const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F, a = (ev >> 18) & 0x3F;
@@ -1152,9 +1224,18 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
                 }
             }
         }
+#if SWEEP_PROBE == 4
+        if (!aux) S2_TICK(4);                // corrections of this thread done
+#endif
         __syncthreads();
         S2_TICK(2);
     }
+#if SWEEP_PROBE == 4
+    if (tid == 0) {
+        t_ph[6] = grp; t_ph[7] = t_a - t_begin; t_ph[5] = 0;
+        for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)t_ph[i]);
+    }
+#endif
 #if SWEEP_PROBE == 3
     if (tid == 0 || tid == S2_GATHER) {
         t_ph[6] = (tid == 0) ? grp : 0;
@@ -1477,7 +1558,8 @@ template <int KT, int CT, int T>
 int launch_sweep2_t(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     constexpr int TC = 8 * CT;
     const int PR = sweep_pitch(TC, P.KP);
-    const size_t smem = ((size_t)(P.K + 2 * T - 1) * PR + (size_t)P.K * P.KP + 4 * T * TC + 2 * s2_evcap(T) + 4) * sizeof(float);
+    size_t smem = ((size_t)(P.K + 2 * T - 1) * PR + (size_t)P.K * P.KP + 4 * T * TC + 2 * s2_evcap(T) + 4) * sizeof(float);
+    if (const char* e = getenv("STED_B200_S2_PAD_SMEM")) smem += (size_t)atoi(e);     // occupancy experiments only
     int rc;
     if ((rc = set_smem(sweep2_kernel<KT, CT, T>, smem))) return rc;
     static thread_local int slots = 0;                             // concurrent CTAs on this device
@@ -1518,9 +1600,8 @@ int launch_sweep2(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     }
 }
 
-int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-    BleachWs ws{};
-    if (!(P.flags & STED_SAMPLE_BLEACH)) return launch_sweep_m<false>(P, ws, st);
+// workspace pointers of the stochastic scan; fails when the buffer cannot even hold the fixed part
+int bind_workspace(const AcqParams& P, void* workspace, size_t workspace_bytes, BleachWs& ws) {
     const size_t fixed = bleach_ws_bytes(P.B, P.H, 0);
     if (!workspace || workspace_bytes < fixed + 12)
         return fail(STED_EINVAL, "stochastic bleaching needs a workspace of at least %zu bytes (see sted_bleach_workspace_bytes)",
@@ -1534,13 +1615,41 @@ int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cu
     if (ws.cap > 0x7FFFFFFFull) ws.cap = 0x7FFFFFFFull;
     ws.stage = reinterpret_cast<uint2*>(ws.off + n + 4);           // 16 + (2n + 4) * 4 bytes in: 8-byte aligned
     ws.ev = reinterpret_cast<uint32_t*>(ws.stage + ws.cap);
+    return STED_OK;
+}
+
+// the death schedule of a stochastic scan: drawn, counted per (environment, scan row) and bucketed (second-generation
+// schedule; the round-1 schedule draws twice and is only reachable through launch_sweep)
+int launch_presample(const AcqParams& P, const BleachWs& ws, void* workspace, cudaStream_t st) {
+    const int n = P.B * P.H;
     CUDA_TRY(cudaMemsetAsync(workspace, 0, 16 + (size_t)n * sizeof(int), st));
     const size_t psmem = ((size_t)(2 * P.K + 1) * P.KP + PS_ITEMS) * sizeof(float);
     const bool whole = (P.flags & STED_FRAME_MOLECULES) != 0;
     const size_t region = whole ? (size_t)P.Hp * P.Wp : (size_t)P.H * P.W;
     dim3 pgrid((unsigned)((region + PS_CHUNK - 1) / PS_CHUNK), P.B);
+    presample_kernel<2><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
+    CUDA_TRY(cudaGetLastError());
+    bucket_scan_kernel<<<1, 1024, 0, st>>>(ws, n);
+    CUDA_TRY(cudaGetLastError());
+    scatter_events_kernel<<<148 * 8, 256, 0, st>>>(ws);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    BleachWs ws{};
+    if (!(P.flags & STED_SAMPLE_BLEACH)) return launch_sweep_m<false>(P, ws, st);
+    int rc = bind_workspace(P, workspace, workspace_bytes, ws);
+    if (rc) return rc;
+    if (P.flags & STED_PRESAMPLED) return launch_sweep2(P, ws, st);   // sted_bleach_presample filled the workspace
+    const int n = P.B * P.H;
     const bool v1 = getenv("STED_B200_SCAN_V1") != nullptr;         // round-1 schedule, kept for A/B timing and tests
     if (v1) {
+        CUDA_TRY(cudaMemsetAsync(workspace, 0, 16 + (size_t)n * sizeof(int), st));
+        const size_t psmem = ((size_t)(2 * P.K + 1) * P.KP + PS_ITEMS) * sizeof(float);
+        const bool whole = (P.flags & STED_FRAME_MOLECULES) != 0;
+        const size_t region = whole ? (size_t)P.Hp * P.Wp : (size_t)P.H * P.W;
+        dim3 pgrid((unsigned)((region + PS_CHUNK - 1) / PS_CHUNK), P.B);
         presample_kernel<0><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
         CUDA_TRY(cudaGetLastError());
         bucket_scan_kernel<<<1, 1024, 0, st>>>(ws, n);
@@ -1549,12 +1658,7 @@ int launch_sweep(const AcqParams& P, void* workspace, size_t workspace_bytes, cu
         CUDA_TRY(cudaGetLastError());
         return launch_sweep_m<true>(P, ws, st);
     }
-    presample_kernel<2><<<pgrid, PS_THREADS, psmem, st>>>(P, ws);
-    CUDA_TRY(cudaGetLastError());
-    bucket_scan_kernel<<<1, 1024, 0, st>>>(ws, n);
-    CUDA_TRY(cudaGetLastError());
-    scatter_events_kernel<<<148 * 8, 256, 0, st>>>(ws);
-    CUDA_TRY(cudaGetLastError());
+    if ((rc = launch_presample(P, ws, workspace, st))) return rc;
     return launch_sweep2(P, ws, st);
 }
 
@@ -1691,6 +1795,23 @@ int sted_acquire(const float* dmap_in_dev, float* dmap_out_dev, const float* tab
     if (rc) return rc;
     if (!(flags & STED_NO_DETECT) && (rc = launch_detect(P, (cudaStream_t)stream))) return rc;
     return STED_OK;
+}
+
+int sted_bleach_presample(const float* dmap_in_dev, const float* tables_dev, const double* pdt_dev, int B, int H, int W, int K,
+                          uint32_t flags, uint64_t seed, uint64_t offset, int64_t env_base, void* workspace_dev,
+                          uint64_t workspace_bytes, void* stream) {
+    if ((flags & (STED_BLEACH | STED_SAMPLE_BLEACH)) != (STED_BLEACH | STED_SAMPLE_BLEACH))
+        return fail(STED_EINVAL, "sted_bleach_presample is the first half of a STED_BLEACH | STED_SAMPLE_BLEACH acquisition");
+    AcqParams P;
+    const StedDetectorParams det{1.0, 1.0, 0.0};                    // the detector plays no part here
+    float dummy = 0.f;
+    int rc = make_params(P, dmap_in_dev, &dummy, tables_dev, pdt_dev, B, H, W, K, flags, &det, 1.0, seed, offset, env_base,
+                         nullptr, &dummy);
+    if (rc) return rc;
+    if ((rc = check_device())) return rc;
+    BleachWs ws{};
+    if ((rc = bind_workspace(P, workspace_dev, (size_t)workspace_bytes, ws))) return rc;
+    return launch_presample(P, ws, workspace_dev, (cudaStream_t)stream);
 }
 
 int sted_acquire_dwellmaps(const float* dmap_in_dev, float* dmap_out_dev, const float* tables_dev, const double* kbleach_dev,
@@ -2006,12 +2127,23 @@ struct StedSession {
     static constexpr int NSIG = 4;           // result buffers in flight
     int device = -1, B = 0, H = 0, W = 0, K = 0, KP = 0, Hp = 0, Wp = 0, Wpitch = 0;
     size_t n_roi = 0, n_pad = 0;
-    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    // s_comp carries the gathers and scans (and everything that changes the maps); the work around them runs beside them:
+    // s_prep the tables and the death schedule of an acquisition (under the acquisition queued before it), s_post the
+    // detector and the uint16 conversion (under the acquisition queued after it)
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr, s_prep = nullptr, s_post = nullptr;
     cudaEvent_t e_up = nullptr, e_pad = nullptr, e_comp = nullptr, e_unpad = nullptr, e_out[NSIG] = {nullptr}, e_mapout = nullptr,
                 e_lent = nullptr;            // another session has finished copying this session's map (sted_session_adopt)
+    cudaEvent_t e_prep[NSIG] = {nullptr}, e_main[NSIG] = {nullptr}, e_det[NSIG] = {nullptr};
+    static constexpr int NT = 64;            // timing brackets kept (ring)
+    cudaEvent_t e_t0[NT] = {nullptr}, e_t1[NT] = {nullptr};        // around the gather / scan kernel of an acquisition, on s_comp
+    cudaEvent_t e_join[5] = {nullptr};
+    long long n_acq = 0;
+    bool serial = false;                     // STED_B200_SESSION_SERIAL: everything on s_comp (A/B timing)
+    cudaEvent_t e_map = nullptr;             // the current map is final (upload / adopt / bleaching acquisition, on s_comp)
+    cudaEvent_t e_wsfree = nullptr;          // the last scan has consumed the event scratch
     char* d_stage = nullptr;                 // un-padded upload / download staging [B][H][W] (4 bytes per pixel)
     float* d_map[2] = {nullptr, nullptr};    // padded maps, ping-pong
-    float* d_tab = nullptr;
+    float* d_tab[NSIG] = {nullptr};          // tables of each queued acquisition
     double* d_cache = nullptr;
     StedFluoParams* d_fluo = nullptr;
     double* d_scal[NSIG] = {nullptr};        // p_ex | p_sted | pdt of each queued acquisition
@@ -2043,6 +2175,7 @@ int session_reserve(StedSession* s, unsigned long long max_events) {
     s->max_events = max_events;
     const size_t need = (bleach_ws_bytes(s->B, s->H, s->max_events) + 255) & ~(size_t)255;
     if (need > s->ws_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(s->s_prep));
         CUDA_TRY(cudaStreamSynchronize(s->s_comp));
         if (s->d_ws) cudaFree(s->d_ws);
         s->d_ws = nullptr; s->ws_bytes = 0;
@@ -2054,17 +2187,20 @@ int session_reserve(StedSession* s, unsigned long long max_events) {
 
 void session_free(StedSession* s) {
     if (!s) return;
-    if (s->s_in) { cudaStreamSynchronize(s->s_in); cudaStreamSynchronize(s->s_comp); cudaStreamSynchronize(s->s_out); }
-    cudaFree(s->d_stage); cudaFree(s->d_map[0]); cudaFree(s->d_map[1]); cudaFree(s->d_tab); cudaFree(s->d_cache);
+    for (cudaStream_t st : {s->s_in, s->s_prep, s->s_comp, s->s_post, s->s_out}) if (st) cudaStreamSynchronize(st);
+    cudaFree(s->d_stage); cudaFree(s->d_map[0]); cudaFree(s->d_map[1]); cudaFree(s->d_cache);
     cudaFree(s->d_fluo); cudaFree(s->d_ws);
     for (int i = 0; i < StedSession::NSIG; ++i) {
-        cudaFree(s->d_scal[i]); cudaFree(s->d_sig[i]); cudaFree(s->d_sig16[i]); cudaFree(s->d_int[i]);
+        cudaFree(s->d_scal[i]); cudaFree(s->d_sig[i]); cudaFree(s->d_sig16[i]); cudaFree(s->d_int[i]); cudaFree(s->d_tab[i]);
         if (s->h_scal[i]) cudaFreeHost(s->h_scal[i]);
-        if (s->e_out[i]) cudaEventDestroy(s->e_out[i]);
+        for (cudaEvent_t e : {s->e_out[i], s->e_prep[i], s->e_main[i], s->e_det[i]}) if (e) cudaEventDestroy(e);
     }
     if (s->h_drop) cudaFreeHost(s->h_drop);
-    for (cudaEvent_t e : {s->e_up, s->e_pad, s->e_comp, s->e_unpad, s->e_mapout, s->e_lent}) if (e) cudaEventDestroy(e);
-    for (cudaStream_t st : {s->s_in, s->s_comp, s->s_out}) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t e : {s->e_up, s->e_pad, s->e_comp, s->e_unpad, s->e_mapout, s->e_lent, s->e_map, s->e_wsfree}) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < StedSession::NT; ++i) { if (s->e_t0[i]) cudaEventDestroy(s->e_t0[i]); if (s->e_t1[i]) cudaEventDestroy(s->e_t1[i]); }
+    for (cudaEvent_t e : s->e_join) if (e) cudaEventDestroy(e);
+    if (s->serial) s->s_prep = s->s_post = nullptr;           // aliases of s_comp
+    for (cudaStream_t st : {s->s_in, s->s_prep, s->s_comp, s->s_post, s->s_out}) if (st) cudaStreamDestroy(st);
     delete s;
 }
 
@@ -2094,19 +2230,29 @@ int sted_session_create(int B, int H, int W, int K, const double* psf_cache_host
     S_TRY(cudaStreamCreateWithPriority(&s->s_in, cudaStreamNonBlocking, prio));
     S_TRY(cudaStreamCreateWithPriority(&s->s_comp, cudaStreamNonBlocking, prio));
     S_TRY(cudaStreamCreateWithPriority(&s->s_out, cudaStreamNonBlocking, prio));
-    for (cudaEvent_t* e : {&s->e_up, &s->e_pad, &s->e_comp, &s->e_unpad, &s->e_mapout, &s->e_lent}) S_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    s->serial = getenv("STED_B200_SESSION_SERIAL") != nullptr;
+    if (s->serial) {
+        s->s_prep = s->s_post = s->s_comp;
+    } else {
+        S_TRY(cudaStreamCreateWithPriority(&s->s_prep, cudaStreamNonBlocking, prio));
+        S_TRY(cudaStreamCreateWithPriority(&s->s_post, cudaStreamNonBlocking, prio));
+    }
+    for (int i = 0; i < StedSession::NT; ++i) { S_TRY(cudaEventCreate(&s->e_t0[i])); S_TRY(cudaEventCreate(&s->e_t1[i])); }
+    for (cudaEvent_t& e : s->e_join) S_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&s->e_up, &s->e_pad, &s->e_comp, &s->e_unpad, &s->e_mapout, &s->e_lent, &s->e_map, &s->e_wsfree})
+        S_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     S_TRY(cudaMalloc(&s->d_stage, s->n_roi * 4));
     S_TRY(cudaMalloc(&s->d_map[0], s->n_pad * 4));
     S_TRY(cudaMalloc(&s->d_map[1], s->n_pad * 4));
     S_TRY(cudaMemsetAsync(s->d_map[0], 0, s->n_pad * 4, s->s_comp));
     S_TRY(cudaMemsetAsync(s->d_map[1], 0, s->n_pad * 4, s->s_comp));
-    S_TRY(cudaMalloc(&s->d_tab, (size_t)B * STED_TABLES * K * s->KP * 4));
     S_TRY(cudaMalloc(&s->d_cache, 3ull * K * K * 8));
     S_TRY(cudaMalloc(&s->d_fluo, (size_t)B * sizeof(StedFluoParams)));
     S_TRY(cudaMallocHost(&s->h_drop, StedSession::NSIG * sizeof(int)));
     for (int i = 0; i < StedSession::NSIG; ++i) {
         s->h_drop[i] = 0;
-        S_TRY(cudaEventCreateWithFlags(&s->e_out[i], cudaEventDisableTiming));
+        for (cudaEvent_t* e : {&s->e_out[i], &s->e_prep[i], &s->e_main[i], &s->e_det[i]}) S_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        S_TRY(cudaMalloc(&s->d_tab[i], (size_t)B * STED_TABLES * K * s->KP * 4));
         S_TRY(cudaMalloc(&s->d_scal[i], 3ull * B * 8));
         S_TRY(cudaMallocHost(&s->h_scal[i], 3ull * B * 8));
         S_TRY(cudaMalloc(&s->d_sig[i], s->n_roi * 4));
@@ -2130,6 +2276,7 @@ int sted_session_set_fluorophores(StedSession* s, const StedFluoParams* fluo_hos
     if (rc) return rc;
     if (!fluo_host) return fail(STED_EINVAL, "null pointer argument");
     // synchronous: called once per episode, and the caller's array need not outlive the call
+    CUDA_TRY(cudaStreamSynchronize(s->s_prep));
     CUDA_TRY(cudaStreamSynchronize(s->s_comp));
     CUDA_TRY(cudaMemcpy(s->d_fluo, fluo_host, (size_t)s->B * sizeof(StedFluoParams), cudaMemcpyHostToDevice));
     s->fluo_set = true;
@@ -2154,9 +2301,63 @@ int sted_session_upload(StedSession* s, const void* dmap_host, uint32_t flags, u
     else pad_kernel<<<296, 256, 0, s->s_comp>>>((const float*)s->d_stage, s->d_map[s->cur], s->B, s->H, s->W, p, s->Hp, s->Wpitch);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->e_pad, s->s_comp));
+    CUDA_TRY(cudaEventRecord(s->e_map, s->s_comp));
     s->map_set = true;
     if (max_molecules == 0) max_molecules = 4ull * s->n_roi;           // too small: sted_session_sync reports STED_EOVERFLOW
     return session_reserve(s, max_molecules + 16);
+}
+
+int sted_session_upload_device(StedSession* s, const void* roi_dev, uint32_t flags, uint64_t max_molecules, void* stream) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if (!roi_dev) return fail(STED_EINVAL, "null pointer argument");
+    const bool u16 = (flags & STED_HOST_U16) != 0;
+    // roi_dev is ready once what `stream` holds now has run
+    CUDA_TRY(cudaEventRecord(s->e_up, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_up, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_lent, 0));
+    const int p = s->K / 2;
+    if (u16) pad_kernel<<<296, 256, 0, s->s_comp>>>((const uint16_t*)roi_dev, s->d_map[s->cur], s->B, s->H, s->W, p, s->Hp, s->Wpitch);
+    else pad_kernel<<<296, 256, 0, s->s_comp>>>((const float*)roi_dev, s->d_map[s->cur], s->B, s->H, s->W, p, s->Hp, s->Wpitch);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->e_map, s->s_comp));
+    s->map_set = true;
+    if (max_molecules == 0) max_molecules = 4ull * s->n_roi;
+    return session_reserve(s, max_molecules + 16);
+}
+
+int sted_session_result(StedSession* s, int back, float** signal_dev, float** intensity_dev, void* stream, int wait) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if (back < 0 || back >= StedSession::NSIG) return fail(STED_EINVAL, "back must lie in [0, %d)", StedSession::NSIG);
+    const int i = (s->next_sig + 2 * StedSession::NSIG - 1 - back) % StedSession::NSIG;
+    if (signal_dev) *signal_dev = s->d_sig[i];
+    if (intensity_dev) *intensity_dev = s->d_int[i];
+    if (wait) CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->e_det[i], 0));
+    return STED_OK;
+}
+
+int sted_session_kernel_ms(StedSession* s, int back, float* ms) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if (!ms) return fail(STED_EINVAL, "null pointer argument");
+    if (back < 0 || back >= StedSession::NT || back >= s->n_acq)
+        return fail(STED_EINVAL, "back must lie in [0, min(%d, acquisitions queued so far))", StedSession::NT);
+    const int it = (int)((s->n_acq - 1 - back) % StedSession::NT);
+    CUDA_TRY(cudaEventSynchronize(s->e_t1[it]));
+    CUDA_TRY(cudaEventElapsedTime(ms, s->e_t0[it], s->e_t1[it]));
+    return STED_OK;
+}
+
+int sted_session_join(StedSession* s, void* stream) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    const cudaStream_t all[5] = {s->s_in, s->s_prep, s->s_comp, s->s_post, s->s_out};
+    for (int k = 0; k < 5; ++k) {
+        CUDA_TRY(cudaEventRecord(s->e_join[k], all[k]));
+        CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->e_join[k], 0));
+    }
+    return STED_OK;
 }
 
 int sted_session_adopt(StedSession* dst, StedSession* src) {
@@ -2173,6 +2374,7 @@ int sted_session_adopt(StedSession* dst, StedSession* src) {
     CUDA_TRY(cudaStreamWaitEvent(dst->s_comp, src->e_comp, 0));
     CUDA_TRY(cudaMemcpyAsync(dst->d_map[dst->cur], src->d_map[src->cur], dst->n_pad * 4, cudaMemcpyDeviceToDevice, dst->s_comp));
     CUDA_TRY(cudaEventRecord(src->e_lent, dst->s_comp));
+    CUDA_TRY(cudaEventRecord(dst->e_map, dst->s_comp));
     dst->map_set = true;
     return STED_OK;
 }
@@ -2198,31 +2400,61 @@ int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* 
     memcpy(s->h_scal[i], p_ex_host, (size_t)B * 8);
     memcpy(s->h_scal[i] + B, p_sted_host, (size_t)B * 8);
     memcpy(s->h_scal[i] + 2 * B, pdt_host, (size_t)B * 8);
-    CUDA_TRY(cudaMemcpyAsync(s->d_scal[i], s->h_scal[i], 3ull * B * 8, cudaMemcpyHostToDevice, s->s_comp));
-    if ((rc = sted_make_effective(s->d_cache, s->d_fluo, s->d_scal[i], s->d_scal[i] + B, s->d_scal[i] + 2 * B, B, s->K, s->d_tab,
-                                  nullptr, s->s_comp)))
+    // ---- s_prep: parameters, tables and (stochastic scan) the death schedule.  Neither depends on the acquisition queued
+    // before this one, so they run under it; the schedule needs the final map and a free event scratch.
+    const double* d_pdt = s->d_scal[i] + 2 * B;
+    CUDA_TRY(cudaMemcpyAsync(s->d_scal[i], s->h_scal[i], 3ull * B * 8, cudaMemcpyHostToDevice, s->s_prep));
+    if ((rc = sted_make_effective(s->d_cache, s->d_fluo, s->d_scal[i], s->d_scal[i] + B, d_pdt, B, s->K, s->d_tab[i], nullptr,
+                                  s->s_prep)))
         return rc;
     float* d_in = s->d_map[s->cur];
     float* d_out = s->d_map[s->cur ^ 1];
-    if ((rc = sted_acquire(d_in, bleach ? d_out : nullptr, s->d_tab, s->d_scal[i] + 2 * B, B, s->H, s->W, s->K, flags, det,
-                           lambda_fluo, seed, offset, env_base, intensity_host ? s->d_int[i] : nullptr, s->d_sig[i],
-                           stoch ? s->d_ws : nullptr, stoch ? s->ws_bytes : 0, s->s_comp)))
+    if (stoch) {
+        CUDA_TRY(cudaStreamWaitEvent(s->s_prep, s->e_map, 0));
+        CUDA_TRY(cudaStreamWaitEvent(s->s_prep, s->e_wsfree, 0));
+        if ((rc = sted_bleach_presample(d_in, s->d_tab[i], d_pdt, B, s->H, s->W, s->K, flags, seed, offset, env_base, s->d_ws,
+                                        s->ws_bytes, s->s_prep)))
+            return rc;
+    }
+    CUDA_TRY(cudaEventRecord(s->e_prep[i], s->s_prep));
+    // ---- s_comp: the gather or the scan
+    CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_prep[i], 0));
+    const int it = (int)(s->n_acq++ % StedSession::NT);
+    CUDA_TRY(cudaEventRecord(s->e_t0[it], s->s_comp));
+    if ((rc = sted_acquire(d_in, bleach ? d_out : nullptr, s->d_tab[i], d_pdt, B, s->H, s->W, s->K,
+                           flags | STED_NO_DETECT | (stoch ? STED_PRESAMPLED : 0u), det, lambda_fluo, seed, offset, env_base,
+                           intensity_host ? s->d_int[i] : nullptr, s->d_sig[i], stoch ? s->d_ws : nullptr,
+                           stoch ? s->ws_bytes : 0, s->s_comp)))
         return rc;
+    CUDA_TRY(cudaEventRecord(s->e_t1[it], s->s_comp));
     s->h_drop[i] = 0;
-    if (stoch) CUDA_TRY(cudaMemcpyAsync(&s->h_drop[i], s->d_ws, sizeof(int), cudaMemcpyDeviceToHost, s->s_comp));
-    if (bleach) s->cur ^= 1;
+    if (stoch) {
+        CUDA_TRY(cudaMemcpyAsync(&s->h_drop[i], s->d_ws, sizeof(int), cudaMemcpyDeviceToHost, s->s_comp));
+        CUDA_TRY(cudaEventRecord(s->e_wsfree, s->s_comp));
+    }
+    if (bleach) {
+        s->cur ^= 1;
+        CUDA_TRY(cudaEventRecord(s->e_map, s->s_comp));
+    }
+    CUDA_TRY(cudaEventRecord(s->e_main[i], s->s_comp));
+    // ---- s_post: detector (+ uint16 conversion), under whatever s_comp runs next
+    CUDA_TRY(cudaStreamWaitEvent(s->s_post, s->e_main[i], 0));
+    if ((rc = sted_detect(s->d_sig[i], d_pdt, B, s->H, s->W, flags, det, lambda_fluo, seed, offset, env_base, s->s_post))) return rc;
     if (signal_host || intensity_host) {
         if (u16 && signal_host) {
-            counts_to_u16_kernel<<<296, 256, 0, s->s_comp>>>(s->d_sig[i], s->d_sig16[i], s->n_roi);
+            counts_to_u16_kernel<<<296, 256, 0, s->s_post>>>(s->d_sig[i], s->d_sig16[i], s->n_roi);
             CUDA_TRY(cudaGetLastError());
         }
-        CUDA_TRY(cudaEventRecord(s->e_comp, s->s_comp));
-        CUDA_TRY(cudaStreamWaitEvent(s->s_out, s->e_comp, 0));
+        CUDA_TRY(cudaEventRecord(s->e_det[i], s->s_post));
+        CUDA_TRY(cudaStreamWaitEvent(s->s_out, s->e_det[i], 0));
         if (signal_host) {
             if (u16) CUDA_TRY(cudaMemcpyAsync(signal_host, s->d_sig16[i], s->n_roi * 2, cudaMemcpyDeviceToHost, s->s_out));
             else CUDA_TRY(cudaMemcpyAsync(signal_host, s->d_sig[i], s->n_roi * 4, cudaMemcpyDeviceToHost, s->s_out));
         }
         if (intensity_host) CUDA_TRY(cudaMemcpyAsync(intensity_host, s->d_int[i], s->n_roi * 4, cudaMemcpyDeviceToHost, s->s_out));
+    } else {
+        CUDA_TRY(cudaEventRecord(s->e_det[i], s->s_post));
+        CUDA_TRY(cudaStreamWaitEvent(s->s_out, s->e_det[i], 0));      // e_out[i] below then covers the slot's kernels too
     }
     CUDA_TRY(cudaEventRecord(s->e_out[i], s->s_out));
     // the next kernels on s_comp must not overwrite slot i ... they use slot i+1; slot i is guarded by e_out[i] above
@@ -2253,9 +2485,7 @@ int sted_session_download(StedSession* s, void* dmap_host, uint32_t flags) {
 int sted_session_sync(StedSession* s, int64_t* dropped_events) {
     int rc = session_bind(s);
     if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(s->s_in));
-    CUDA_TRY(cudaStreamSynchronize(s->s_comp));
-    CUDA_TRY(cudaStreamSynchronize(s->s_out));
+    for (cudaStream_t st : {s->s_in, s->s_prep, s->s_comp, s->s_post, s->s_out}) CUDA_TRY(cudaStreamSynchronize(st));
     long long dropped = 0;
     for (int i = 0; i < StedSession::NSIG; ++i) { dropped += s->h_drop[i]; s->h_drop[i] = 0; }
     if (dropped_events) *dropped_events = dropped;

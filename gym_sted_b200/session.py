@@ -82,6 +82,39 @@ class StedSession:
         self._keep = maps
         _lib.check(self.lib.sted_session_upload(self._h, maps.ctypes.data_as(_VP), self._map_flags(maps), int(max_molecules)))
 
+    def upload_device(self, maps, max_molecules: int = 0):
+        """Same from a (B,H,W) float32 / uint16 torch tensor on the session's device, ready on torch's current stream."""
+        import torch
+        assert tuple(maps.shape) == (self.B, self.H, self.W) and maps.is_contiguous() and maps.is_cuda
+        flags = {torch.float32: 0, torch.uint16: _lib.STED_HOST_U16}[maps.dtype]
+        self._keep = maps
+        _lib.check(self.lib.sted_session_upload_device(self._h, maps.data_ptr(), flags, int(max_molecules),
+                                                       torch.cuda.current_stream(maps.device).cuda_stream))
+
+    def result(self, back: int = 0, intensity: bool = False, wait: bool = True):
+        """Device view (torch, float32 (B,H,W), no copy) of the photon counts of the acquisition queued ``back`` calls
+        ago; torch's current stream is made to wait for it.  Overwritten by the fourth acquisition after its own."""
+        import torch
+        sig, inten = _VP(), _VP()
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.lib.sted_session_result(self._h, int(back), ctypes.byref(sig), ctypes.byref(inten), st, int(wait)))
+
+        def view(ptr):
+            arr = {"data": (ptr.value, False), "shape": (self.B, self.H, self.W), "typestr": "<f4", "version": 3}
+            return torch.as_tensor(type("_Dev", (), {"__cuda_array_interface__": arr})(), device="cuda")
+        return (view(sig), view(inten)) if intensity else view(sig)
+
+    def kernel_ms(self, back: int = 0) -> float:
+        """Device time of the gather / scan kernel of the acquisition queued ``back`` calls ago (waits for it)."""
+        ms = ctypes.c_float(0)
+        _lib.check(self.lib.sted_session_kernel_ms(self._h, int(back), ctypes.byref(ms)))
+        return float(ms.value)
+
+    def join(self):
+        """torch's current stream waits for everything queued on the session so far."""
+        import torch
+        _lib.check(self.lib.sted_session_join(self._h, torch.cuda.current_stream().cuda_stream))
+
     def _vec(self, x):
         return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (self.B,)))
 

@@ -63,6 +63,10 @@ extern "C" {
                                   * map, gym_sted/envs/sted_env.py:170): the stochastic scan then draws deaths for the
                                   * whole padded map instead of the H x W region of interest only                   */
 
+#define STED_PRESAMPLED     64u  /* sted_acquire: the workspace already holds this scan's death schedule, written by
+                                  * sted_bleach_presample with the same maps, tables, dwell times, flags, seed, offset and
+                                  * env_base                                                                          */
+
 /* Fluorophore + STED-pulse parameters of one environment.
  * Mirrors pysted.base.Fluorescence(**defaults.FLUO) (gym_sted/defaults.py:25-42) and the
  * lambda_/tau/rate attributes gym-sted reads from microscope.excitation / microscope.sted
@@ -172,6 +176,14 @@ int sted_acquire_dwellmaps(const float* dmap_in_dev, float* dmap_out_dev, const 
  * Limits of sted_acquire: B <= 65535 environments per call, H <= 65535, W + K - 1 <= 4095, fewer than 32768
  * molecules per pixel. */
 uint64_t sted_bleach_workspace_bytes(int B, int H, uint64_t max_events);
+/* First half of a stochastic scan on its own: draws every death of the scan (Philox, keyed as in sted_acquire) and
+ * buckets the events by scan row in workspace_dev.  It depends on the maps and on the STED acquisition's tables only,
+ * not on the images acquired in between, so a caller can queue it on a second stream — e.g. under the confocal
+ * acquisition that precedes the STED one (gym_sted/envs/mosted_env.py:222-227) — and then call sted_acquire with
+ * STED_PRESAMPLED on the same arguments.  Arguments as sted_acquire. */
+int sted_bleach_presample(const float* dmap_in_dev, const float* tables_dev, const double* pdt_dev,
+                          int B, int H, int W, int K, uint32_t flags, uint64_t seed, uint64_t offset,
+                          int64_t env_base, void* workspace_dev, uint64_t workspace_bytes, void* stream);
 /* Number of deaths the last stochastic scan could not store (0 unless max_events was too small;
  * a non-zero value means that scan's outputs are invalid).  Synchronises `stream`. */
 int sted_bleach_dropped_events(const void* workspace_dev, int* dropped_host, void* stream);
@@ -208,7 +220,9 @@ int sted_acquire_host(void* dmap_host, const double* psf_cache_host,
  * gym-sted images every structure several times (confocal, STED + bleaching, confocal: gym_sted/envs/mosted_env.py:
  * 222-234) on ONE pysted Datamap object that carries the bleaching (sequence_sted_env.py:86-92).  A session is that
  * object for B environments: the map is uploaded once, acquisitions advance it on the device, and every call only
- * QUEUES work (own streams; uploads, kernels and downloads of successive calls overlap).  Host buffers handed to
+ * QUEUES work (own streams; uploads, kernels and downloads of successive calls overlap, and so do the parts of
+ * successive acquisitions that do not depend on each other: the tables and the death schedule of an acquisition are
+ * prepared under the gather or scan of the one before it, its detector runs under the one after it).  Host buffers handed to
  * sted_session_acquire / _download must stay valid, and are only defined, after the next sted_session_sync.
  * One session belongs to one device (the one current at creation) and must be driven by one host thread at a time.
  *   psf_cache_host : float64 [3][K][K] (copied at creation);  low_priority != 0: streams of the lowest priority, for
@@ -227,6 +241,21 @@ int sted_session_upload(StedSession* s, const void* dmap_host, uint32_t flags, u
 int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* p_sted_host, const double* pdt_host,
                          uint32_t flags, const StedDetectorParams* det, double lambda_fluo, uint64_t seed, uint64_t offset,
                          int64_t env_base, void* signal_host, float* intensity_host);
+/* Device-resident callers (the vectorised environments keep their structures and images on the GPU):
+ * sted_session_upload_device pads [B][H][W] maps that already live in device memory (float32, or uint16 with
+ * STED_HOST_U16), ready once the work `stream` holds at the time of the call has run; roi_dev must stay unchanged until
+ * the session has been synchronised or a stream has waited (sted_session_result) on an acquisition queued after it.
+ * sted_session_result hands out the device buffers of the acquisition queued `back` calls ago (0 = the last one,
+ * back < 4): float32 [B][H][W] photon counts and detected power (the latter only when that call asked for the
+ * intensity); with wait != 0 `stream` is made to wait for that acquisition's detector.  A buffer is overwritten by the
+ * fourth acquisition queued after its own.
+ * sted_session_kernel_ms: device time (CUDA events on the session's compute stream) of the gather or scan kernel of
+ * the acquisition queued `back` calls ago (back < 64); waits for it.
+ * sted_session_join: `stream` waits for everything queued on the session so far (all of its streams). */
+int sted_session_upload_device(StedSession* s, const void* roi_dev, uint32_t flags, uint64_t max_molecules, void* stream);
+int sted_session_result(StedSession* s, int back, float** signal_dev, float** intensity_dev, void* stream, int wait);
+int sted_session_kernel_ms(StedSession* s, int back, float* ms);
+int sted_session_join(StedSession* s, void* stream);
 /* dst takes over src's current maps (device-to-device, queued after everything already queued on both sessions).
  * gym-sted's step ends with the first confocal image of the NEXT structure (mosted_env.py:174-186), which is the
  * structure the next step images three times: a low-priority session uploads and images it while the main session

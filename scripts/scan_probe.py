@@ -46,6 +46,8 @@ def scan(n, label):
     if sum(ph):                                          # SWEEP_PROBE == 3 build: cycles per group of rows and CTA
         g = max(1, ph[6])
         names = ("gather", "g.wait1", "g.phaseB", "aux.stage+ring", "aux.corr", "aux.wait1")
+        if os.environ.get("PROBE_SPLIT_B"):              # SWEEP_PROBE == 4 build: thread 0's view of the phase between the barriers
+            names = ("gather", "wait1", "B.wait2", "B.ring", "B.corr", "-")
         print("    per group: " + "  ".join(f"{nm} {ph[i] / g:.0f}" for i, nm in enumerate(names)) + f"  loop {ph[7] / g:.0f}", flush=True)
     print(f"{label:40s} {t:7.3f} ms   {flops / t / 1e9:6.1f} TFLOP/s (3N)   deaths/env {int(maps.sum() - bm.datamaps_roi().sum().item()) // B}", flush=True)
     return t
