@@ -1255,6 +1255,311 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
 }
 
 // ------------------------------------------------------------------------------------------
+// K3c: the stochastic scan, third generation (sweep3_kernel).
+//
+// Same work items and the same arithmetic as sweep2_kernel with one scan row per group, reorganised around the round-2
+// measurements (profiles/r02_summary.md): per scan row a sweep2 CTA spent as long between its two CTA-wide barriers
+// (ring decrements + intensity corrections, every warp) and in the auxiliary warps' ring traffic as in the gather, and
+// three CTAs per SM could not hide that.  Here
+//  * the eight GATHER warps do nothing but gather: after the dense gather of scan row r they apply the row's deaths to
+//    the ring (one compare-and-swap per death — the only thing the next row's gather depends on), meet at a barrier of
+//    their own, and start on row r + 1;
+//  * four CORRECTION warps take the intensity corrections of row r and its write-out WHILE row r + 1 is gathered
+//    (named barriers hand the row over and back; dense intensities, scales and corrections are double buffered);
+//  * the ring moves by TMA: the finished band row leaves with cp.async.bulk (shared -> global) and the row the gather
+//    needs two scan rows later arrives with cp.async.bulk (global -> shared) on an mbarrier, issued by one gather
+//    thread in a handful of instructions; the per-row event lists arrive the same way, three rows ahead.
+// MEASURED (B200, 256 envs x 256 x 256, profiles/r02_summary.md): identical results, but 4.21 ms against sweep2's 3.87 ms
+// for the whole scan.  Per scan row the correction warps need 15 k cycles for ~1.5 k instructions each: next to six
+// always-ready FFMA warps per scheduler a latency-bound helper warp gets an issue slot every ~7 cycles, so the gather
+// warps end up waiting for it (4.8 k cycles per row).  An owner-computes variant without atomics was no faster (17 k).
+// sweep2's shape — every warp does the side work between two barriers — wastes fewer issue slots, so it stays the
+// default; this kernel runs with STED_B200_SCAN_V3=1 and is covered by the same equality tests.
+// ------------------------------------------------------------------------------------------
+constexpr int S3_GATHER = 256, S3_CORR = 128, S3_THREADS = S3_GATHER + S3_CORR, S3_EVCAP = 512;
+constexpr int S3_BAR_GATHER = 1, S3_BAR_READY = 2 /* +parity */, S3_BAR_FREE = 4 /* +parity */, S3_BAR_CORR = 6;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// named barriers with immediate ids (a register id makes ptxas reserve all sixteen)
+template <int ID, int N> __device__ __forceinline__ void named_sync() { asm volatile("bar.sync %0, %1;" :: "n"(ID), "n"(N) : "memory"); }
+template <int ID, int N> __device__ __forceinline__ void named_arrive() { asm volatile("bar.arrive %0, %1;" :: "n"(ID), "n"(N) : "memory"); }
+template <int ID, int N> __device__ __forceinline__ void named_sync2(int par) { if (par) named_sync<ID + 1, N>(); else named_sync<ID, N>(); }
+template <int ID, int N> __device__ __forceinline__ void named_arrive2(int par) { if (par) named_arrive<ID + 1, N>(); else named_arrive<ID, N>(); }
+
+__host__ __device__ inline size_t sweep3_smem_floats(int K, int KP, int TC) {
+    return (size_t)(K + 2) * sweep_pitch(TC, KP) + (size_t)K * KP + 6 * TC + 3 * S3_EVCAP + 12;
+}
+
+template <int KT, int CT>
+__global__ void __launch_bounds__(S3_THREADS, 3) sweep3_kernel(const AcqParams P, const BleachWs ws, const int RR) {
+    constexpr int TC = 8 * CT;
+    const int K = KT ? KT : P.K;
+    const int KP = KT ? STED_KPITCH(KT) : P.KP;
+    const int NS = K + 2;                     // ring slots: the K rows of a gather, the next one, and one in flight
+    const int PR = sweep_pitch(TC, KP);
+    const int span = TC + K - 1;
+
+    extern __shared__ __align__(128) float smem[];
+    float* ring = smem;                       // [K+2][PR] band of the molecule map (integer counts)
+    float* sWt = ring + NS * PR;              // [K][KP]   effective PSF E
+    float* sI = sWt + K * KP;                 // [2][TC]   dense row intensities (even / odd scan rows)
+    float* sScale = sI + 2 * TC;              // [2][TC]   2^30 / sI  (fixed-point scale of the corrections)
+    int* sCorr = reinterpret_cast<int*>(sScale + 2 * TC);               // [2][TC] sum of removed taps, fixed point
+    uint32_t* sEv = reinterpret_cast<uint32_t*>(sCorr + 2 * TC);        // [3][S3_EVCAP] events of three scan rows
+    int* sMeta = reinterpret_cast<int*>(sEv + 3 * S3_EVCAP);            // [3][4] lo, hi in ws.ev; offset and count staged
+    __shared__ __align__(8) unsigned long long mbar[5];                 // [0..1] ring rows in flight, [2..4] event lists
+
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.x * TC;
+    const int r0 = blockIdx.y * RR;
+    const int r1 = min(P.H, r0 + RR);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool corr = tid >= S3_GATHER;
+    const int ct = tid - S3_GATHER;           // index among the correction threads
+    const int W = P.W, H = P.H;
+    const float* din = P.din + (size_t)b * P.Hp * P.Wpitch;
+    float* dout = P.dout + (size_t)b * P.Hp * P.Wpitch;
+    const int* row_off = ws.off + (size_t)b * H;
+    const uint32_t bar_full = smem_u32(&mbar[0]), bar_ev = smem_u32(&mbar[2]);
+
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(P.tables + ((size_t)b * STED_TABLES + STED_TAB_E) * K * KP);
+        for (int i = tid; i < K * KP / 4; i += S3_THREADS) reinterpret_cast<float4*>(sWt)[i] = __ldg(w4 + i);
+    }
+    for (int i = tid; i < 2 * TC; i += S3_THREADS) sCorr[i] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&mbar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // columns of the molecule map this strip writes back (each column has exactly one owner; the border lies in the
+    // overlap of two strips, where both hold the same counts, on a 16-byte boundary for the bulk copies)
+    const int xs = (c0 == 0) ? 0 : c0 + 32;
+    const int xe = (c0 + TC >= W) ? P.Wpitch : c0 + TC + 32;
+    const int q4 = PR / 4;                    // float4 groups of a ring row
+    const uint32_t row_bytes = (uint32_t)(min(PR, P.Wpitch - c0) * 4);   // what a bulk load brings (the rest of the slot stays zero)
+
+    auto slot_of = [&](const int y) { return (KT ? y % (KT + 2) : y % NS) * PR; };
+    auto clamp_hi = [&](const int v) { return (unsigned long long)v > ws.cap ? (int)ws.cap : v; };
+
+    // band rows r0 .. r0+K+1 as they were BEFORE the scan ...
+    for (int i = tid; i < NS * q4; i += S3_THREADS) {
+        const int yy = i / q4, g = i - yy * q4;
+        const int y = r0 + yy, x = c0 + 4 * g;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y < P.Hp && x < P.Wpitch) val = __ldg(reinterpret_cast<const float4*>(din + (size_t)y * P.Wpitch + x));
+        *reinterpret_cast<float4*>(ring + slot_of(y) + 4 * g) = val;
+    }
+    __syncthreads();
+    // ... minus the deaths of the scan rows before r0 that hit them (scan row r' reaches band rows r' .. r'+K-1)
+    if (r0 > 0) {
+        const int rp = max(0, r0 - (K - 1));
+        const int lo = __ldg(row_off + rp), hi = clamp_hi(__ldg(row_off + r0));
+        for (int q = lo + tid; q < hi; q += S3_THREADS) {
+            const uint32_t ev = __ldg(ws.ev + q);
+            const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F;
+            const int rr = r0 - 1 - (int)(((uint32_t)(r0 - 1) - (ev >> 24)) & 255u);     // scan row of the event
+            const int y = rr + u;
+            if (y >= r0 && xl >= 0 && xl < span) atomicAdd(&ring[slot_of(y) + xl], -1.0f);
+        }
+    }
+
+    // event list of scan row r -> shared memory (bulk copy of the 16-byte blocks that hold it, at most S3_EVCAP words;
+    // longer rows read their tail from global memory)
+    auto issue_events = [&](const int r) {
+        const int k = (r - r0) % 3;
+        const int lo = __ldg(row_off + r), hi = clamp_hi(__ldg(row_off + r + 1));
+        const int n = max(hi - lo, 0);
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(ws.ev + lo);
+        const uintptr_t base = a0 & ~(uintptr_t)15;
+        const int off = (int)((a0 - base) >> 2);
+        const int cnt = n ? min((off + n + 3) & ~3, S3_EVCAP) : 0;
+        sMeta[4 * k] = lo; sMeta[4 * k + 1] = lo + n; sMeta[4 * k + 2] = off; sMeta[4 * k + 3] = max(cnt - off, 0);
+        mbar_expect_tx(bar_ev + 8 * k, (uint32_t)cnt * 4u);
+        if (cnt) bulk_g2s(smem_u32(sEv + k * S3_EVCAP), reinterpret_cast<const void*>(base), (uint32_t)cnt * 4u, bar_ev + 8 * k);
+    };
+    __syncthreads();                          // ring, tables and mbarriers are ready
+    if (tid == S3_GATHER)
+        for (int r = r0; r < min(r1, r0 + 3); ++r) issue_events(r);
+
+#if SWEEP_PROBE == 5
+    long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_a = clock64(), t_b;
+#define S3_TICK(i) do { t_b = clock64(); t_ph[i] += t_b - t_a; t_a = t_b; } while (0)
+#else
+#define S3_TICK(i) do { } while (0)
+#endif
+    if (!corr) {
+        // =================================== gather warps ===================================
+        for (int r = r0; r < r1; ++r) {
+            const int it = r - r0, par = it & 1;
+            if (it >= 3) mbar_wait(bar_full + 8 * ((it - 2) & 1), (uint32_t)(((it - 3) >> 1) & 1));   // band row r+K-1 has landed
+            if (it >= 2) named_sync2<S3_BAR_FREE, S3_THREADS>(par);       // row r-2 has been written out: sI / sScale[par] are free
+            S3_TICK(0);                                                   // waits: ring row + free buffers
+            {
+                float acc[CT];
+#pragma unroll
+                for (int jj = 0; jj < CT; ++jj) acc[jj] = 0.f;
+                for (int uu = lane; uu < K; uu += 32) {
+                    const float* drow = ring + slot_of(r + uu) + CT * warp;
+                    const float* erow = sWt + uu * KP;
+                    float win[CT + 4];
+#pragma unroll
+                    for (int jj = 0; jj < CT; jj += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(drow + jj);
+                        win[jj] = t.x; win[jj + 1] = t.y; win[jj + 2] = t.z; win[jj + 3] = t.w;
+                    }
+                    const int nchunk = KP / 4;
+#pragma unroll 5
+                    for (int vc = 0; vc < nchunk; ++vc) {
+                        const float4 nw = *reinterpret_cast<const float4*>(drow + CT + 4 * vc);
+                        const float4 e = *reinterpret_cast<const float4*>(erow + 4 * vc);
+                        win[CT] = nw.x; win[CT + 1] = nw.y; win[CT + 2] = nw.z; win[CT + 3] = nw.w;
+#pragma unroll
+                        for (int jj = 0; jj < CT; ++jj) {
+                            acc[jj] = fmaf(e.x, win[jj], acc[jj]);
+                            acc[jj] = fmaf(e.y, win[jj + 1], acc[jj]);
+                            acc[jj] = fmaf(e.z, win[jj + 2], acc[jj]);
+                            acc[jj] = fmaf(e.w, win[jj + 3], acc[jj]);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < CT; ++jj) win[jj] = win[jj + 4];
+                    }
+                }
+                const float tot = reduce_scatter<CT>(acc, lane);
+                constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
+                if ((lane & ((1 << SH) - 1)) == 0) {
+                    sI[par * TC + CT * warp + (lane >> SH)] = tot;
+                    sScale[par * TC + CT * warp + (lane >> SH)] = 1073741824.0f / fmaxf(tot, 1e-30f);
+                }
+            }
+            S3_TICK(1);                                                   // gather
+            __syncwarp();
+            named_sync<S3_BAR_GATHER, S3_GATHER>();                         // every gather of row r is done: the ring may change
+            S3_TICK(2);
+            {   // the pixels of this row's deaths lose their molecules
+                const int k = it % 3;
+                mbar_wait(bar_ev + 8 * k, (uint32_t)((it / 3) & 1));
+                const uint32_t* sev = sEv + k * S3_EVCAP + sMeta[4 * k + 2];
+                const int ev_lo = sMeta[4 * k], n_ev = sMeta[4 * k + 1] - ev_lo, staged = sMeta[4 * k + 3];
+                for (int q = tid; q < n_ev; q += S3_GATHER) {
+                    const uint32_t ev = q < staged ? sev[q] : __ldg(ws.ev + ev_lo + q);
+                    const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F;
+                    if (xl >= 0 && xl < span) atomicAdd(&ring[slot_of(r + u) + xl], -1.0f);
+                }
+            }
+            fence_async_smem();                                           // the bulk store below reads what was just written
+            S3_TICK(3);                                                   // decrements
+            __syncwarp();
+            named_sync<S3_BAR_GATHER, S3_GATHER>();
+            if (tid == 0) {
+                if (it >= 1) {
+                    bulk_wait_read0();                                    // row r-1 has left its slot (stored one scan row ago)
+                    if (r + 2 < r1) {                                     // band row r+K+1, first needed by the gather of row r+2
+                        const int y = r - 1 + NS;
+                        mbar_expect_tx(bar_full + 8 * (it & 1), row_bytes);
+                        bulk_g2s(smem_u32(ring + slot_of(y)), din + (size_t)y * P.Wpitch + c0, row_bytes, bar_full + 8 * (it & 1));
+                    }
+                }
+                // band row r is final: the columns this strip owns go back to global memory
+                bulk_s2g(dout + (size_t)r * P.Wpitch + xs, smem_u32(ring + slot_of(r) + (xs - c0)), (uint32_t)(xe - xs) * 4u);
+                bulk_commit();
+            }
+            __syncwarp();
+            named_arrive2<S3_BAR_READY, S3_THREADS>(par);                 // row r: dense intensities, scales and ring are settled
+            S3_TICK(4);                                                   // second barrier + bulk copies
+        }
+#if SWEEP_PROBE == 5
+        if (tid == 0) { t_ph[7] = r1 - r0; for (int i = 0; i < 8; ++i) if (i != 5 && i != 6) atomicAdd(&g_phase_cycles[i], (unsigned long long)t_ph[i]); }
+#endif
+    } else {
+        // ================================= correction warps =================================
+        constexpr int EV_LANES = 8, EV_SLOTS = S3_CORR / EV_LANES;
+        const int sub = ct % EV_LANES;
+        for (int r = r0; r < r1; ++r) {
+            const int it = r - r0, par = it & 1, k = it % 3;
+            named_sync2<S3_BAR_READY, S3_THREADS>(par);
+            mbar_wait(bar_ev + 8 * k, (uint32_t)((it / 3) & 1));
+            S3_TICK(5);                                                   // correction warps: waiting for a row
+            const uint32_t* sev = sEv + k * S3_EVCAP + sMeta[4 * k + 2];
+            const int ev_lo = sMeta[4 * k], n_ev = sMeta[4 * k + 1] - ev_lo, staged = sMeta[4 * k + 3];
+            // a death removes the taps its molecule no longer contributes to from the rest of its own scan row
+            // (eight lanes per death, all loads first so that every thread keeps eight independent chains in flight)
+            for (int q = ct / EV_LANES; q < n_ev; q += EV_SLOTS) {
+                const uint32_t ev = q < staged ? sev[q] : __ldg(ws.ev + ev_lo + q);
+                const int xl = (int)(ev & 0xFFFu) - c0, u = (ev >> 12) & 0x3F, a = (ev >> 18) & 0x3F;
+                if (xl < 0 || xl >= span) continue;                       // another strip's pixel
+                const int v0 = max(max(0, c0 + xl - W + 1), xl - (TC - 1));     // dwell column t = xl - v, 0 <= t < TC
+                const int v1 = min(a, min(K, xl + 1));
+                const float* e = sWt + u * KP;
+                const float* sc = sScale + par * TC + xl;
+                int* cr = sCorr + par * TC + xl;
+                float te[8], ts[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int v = v0 + sub + EV_LANES * kk;
+                    const bool ok = v < v1;
+                    te[kk] = ok ? e[v] : 0.f;
+                    ts[kk] = ok ? sc[-v] : 0.f;
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const int v = v0 + sub + EV_LANES * kk;
+                    if (v < v1) atomicAdd(cr - v, __float2int_rn(te[kk] * ts[kk]));
+                }
+            }
+            __syncwarp();
+            named_sync<S3_BAR_CORR, S3_CORR>();
+            for (int t = ct; t < TC; t += S3_CORR) {
+                if (c0 + t < W) {
+                    const float I = fmaxf(sI[par * TC + t] * (1.0f - (float)sCorr[par * TC + t] * 9.313225746154785e-10f), 0.f);
+                    const size_t o = ((size_t)b * H + r) * W + c0 + t;
+                    if (P.intensity) P.intensity[o] = I;
+                    P.signal[o] = I;                          // detect_kernel converts to photon counts
+                }
+                sCorr[par * TC + t] = 0;
+            }
+            if (ct == 0 && r + 3 < r1) issue_events(r + 3);   // this row's list has been read by everybody: its buffer is free
+            __syncwarp();
+            if (r + 2 < r1) named_arrive2<S3_BAR_FREE, S3_THREADS>(par);
+            S3_TICK(6);                                                   // corrections + write-out
+        }
+#if SWEEP_PROBE == 5
+        if (tid == S3_GATHER) { atomicAdd(&g_phase_cycles[5], (unsigned long long)t_ph[5]); atomicAdd(&g_phase_cycles[6], (unsigned long long)t_ph[6]); }
+#endif
+    }
+    __syncthreads();
+    if (tid == 0) bulk_wait0();               // the bulk stores have left shared memory and reached global memory
+    // the band rows below the image belong to the last range of the strip
+    if (r1 == H) {
+        for (int i = tid; i < (P.Hp - H) * q4; i += S3_THREADS) {
+            const int yy = i / q4, g = i - yy * q4;
+            const int y = H + yy, x = c0 + 4 * g;
+            const float4 old = *reinterpret_cast<const float4*>(ring + slot_of(y) + 4 * g);
+            const float* po_ = reinterpret_cast<const float*>(&old);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j >= xs && x + j < xe) dout[(size_t)y * P.Wpitch + x + j] = po_[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4: the general scan — per-dwell imaging parameters.
 //
 // The timed environments hand get_signal_and_bleach one dwell time PER PIXEL (gym_sted/envs/timed_sted_env.py:141-148:
@@ -1532,7 +1837,8 @@ int launch_sweep_m(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
 // bytes of workspace the stochastic scan needs for B environments of H rows and at most max_events deaths:
 // status + per-row counters and offsets + per event 8 bytes of staging and 4 bytes in its row bucket
 size_t bleach_ws_bytes(int B, int H, unsigned long long max_events) {
-    return 16 + ((size_t)B * H * 2 + 4) * sizeof(int) + (size_t)max_events * (sizeof(uint2) + sizeof(uint32_t));
+    // (+ 16 bytes: the bulk copies of the event lists move whole 16-byte blocks)
+    return 16 + ((size_t)B * H * 2 + 4) * sizeof(int) + (size_t)max_events * (sizeof(uint2) + sizeof(uint32_t)) + 16;
 }
 
 // rows per work item of sweep2_kernel: few enough waves of `slots` concurrent CTAs, long enough ranges that the
@@ -1586,12 +1892,43 @@ int launch_sweep2_g(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     return wide ? launch_sweep2_t<0, 16, T>(P, ws, st) : launch_sweep2_t<0, 8, T>(P, ws, st);
 }
 
+template <int KT, int CT>
+int launch_sweep3_t(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
+    constexpr int TC = 8 * CT;
+    size_t smem = sweep3_smem_floats(P.K, P.KP, TC) * sizeof(float);
+    if (const char* e = getenv("STED_B200_S2_PAD_SMEM")) smem += (size_t)atoi(e);     // occupancy experiments only
+    int rc;
+    if ((rc = set_smem(sweep3_kernel<KT, CT>, smem))) return rc;
+    static thread_local int slots = 0;                             // concurrent CTAs on this device
+    if (!slots) {
+        int dev = 0, sms = 0, per_sm = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep3_kernel<KT, CT>, S3_THREADS, smem));
+        slots = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int strips = (P.W + TC - 1) / TC;
+    const int RR = pick_row_range(P.B, strips, P.H, slots);
+    dim3 grid(strips, (P.H + RR - 1) / RR, P.B);
+    sweep3_kernel<KT, CT><<<grid, S3_THREADS, smem, st>>>(P, ws, RR);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+int launch_sweep3(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
+    const bool wide = P.W > SWEEP_WIDE_MIN;
+    if (P.K == 59) return wide ? launch_sweep3_t<59, 16>(P, ws, st) : launch_sweep3_t<59, 8>(P, ws, st);
+    return wide ? launch_sweep3_t<0, 16>(P, ws, st) : launch_sweep3_t<0, 8>(P, ws, st);
+}
+
 #ifndef SWEEP_GROUP
 #define SWEEP_GROUP 1          // scan rows gathered between two barriers (measured: 1 -> 3.89 ms, 2 -> 4.16 ms, 4 -> 4.58 ms)
 #endif
 int launch_sweep2(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     int T = SWEEP_GROUP;
-    if (const char* e = getenv("STED_B200_ROW_GROUP")) T = atoi(e);            // tuning knob
+    const char* grp = getenv("STED_B200_ROW_GROUP");
+    if (!grp && getenv("STED_B200_SCAN_V3")) return launch_sweep3(P, ws, st);    // third generation: opt-in (8 % slower, see K3c)
+    if (const char* e = grp) T = atoi(e);                                      // tuning knob
     switch (T) {
         case 2: return launch_sweep2_g<2>(P, ws, st);
         case 3: return launch_sweep2_g<3>(P, ws, st);
@@ -1611,7 +1948,7 @@ int bind_workspace(const AcqParams& P, void* workspace, size_t workspace_bytes, 
     ws.status = reinterpret_cast<int*>(workspace);
     ws.cnt = ws.status + 4;
     ws.off = ws.cnt + n;
-    ws.cap = (workspace_bytes - fixed) / (sizeof(uint2) + sizeof(uint32_t));
+    ws.cap = (workspace_bytes - fixed) / (sizeof(uint2) + sizeof(uint32_t));       // `fixed` includes the 16 bytes of slack
     if (ws.cap > 0x7FFFFFFFull) ws.cap = 0x7FFFFFFFull;
     ws.stage = reinterpret_cast<uint2*>(ws.off + n + 4);           // 16 + (2n + 4) * 4 bytes in: 8-byte aligned
     ws.ev = reinterpret_cast<uint32_t*>(ws.stage + ws.cap);
@@ -2137,6 +2474,14 @@ struct StedSession {
     static constexpr int NT = 64;            // timing brackets kept (ring)
     cudaEvent_t e_t0[NT] = {nullptr}, e_t1[NT] = {nullptr};        // around the gather / scan kernel of an acquisition, on s_comp
     cudaEvent_t e_join[5] = {nullptr};
+    // tables of the most recent non-bleaching parameter set: gym-sted's confocal acquisitions always use the same
+    // imaging parameters (generate_params() defaults, mosted_env.py:219), so three of the four acquisitions of a step
+    // find their tables here instead of rebuilding them
+    float* d_tab_keep = nullptr;
+    double* d_scal_keep = nullptr;
+    double* h_scal_keep = nullptr;           // host copy the next call's parameters are compared with
+    cudaEvent_t e_keep = nullptr, e_keep_used = nullptr;
+    bool keep_valid = false;
     long long n_acq = 0;
     bool serial = false;                     // STED_B200_SESSION_SERIAL: everything on s_comp (A/B timing)
     cudaEvent_t e_map = nullptr;             // the current map is final (upload / adopt / bleaching acquisition, on s_comp)
@@ -2189,6 +2534,9 @@ void session_free(StedSession* s) {
     if (!s) return;
     for (cudaStream_t st : {s->s_in, s->s_prep, s->s_comp, s->s_post, s->s_out}) if (st) cudaStreamSynchronize(st);
     cudaFree(s->d_stage); cudaFree(s->d_map[0]); cudaFree(s->d_map[1]); cudaFree(s->d_cache);
+    cudaFree(s->d_tab_keep); cudaFree(s->d_scal_keep);
+    if (s->h_scal_keep) free(s->h_scal_keep);
+    for (cudaEvent_t e : {s->e_keep, s->e_keep_used}) if (e) cudaEventDestroy(e);
     cudaFree(s->d_fluo); cudaFree(s->d_ws);
     for (int i = 0; i < StedSession::NSIG; ++i) {
         cudaFree(s->d_scal[i]); cudaFree(s->d_sig[i]); cudaFree(s->d_sig16[i]); cudaFree(s->d_int[i]); cudaFree(s->d_tab[i]);
@@ -2239,6 +2587,11 @@ int sted_session_create(int B, int H, int W, int K, const double* psf_cache_host
     }
     for (int i = 0; i < StedSession::NT; ++i) { S_TRY(cudaEventCreate(&s->e_t0[i])); S_TRY(cudaEventCreate(&s->e_t1[i])); }
     for (cudaEvent_t& e : s->e_join) S_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&s->e_keep, &s->e_keep_used}) S_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    S_TRY(cudaMalloc(&s->d_tab_keep, (size_t)B * STED_TABLES * K * s->KP * 4));
+    S_TRY(cudaMalloc(&s->d_scal_keep, 3ull * B * 8));
+    s->h_scal_keep = (double*)malloc(3ull * B * 8);
+    if (!s->h_scal_keep) return bail(fail(STED_ECUDA, "out of host memory"));
     for (cudaEvent_t* e : {&s->e_up, &s->e_pad, &s->e_comp, &s->e_unpad, &s->e_mapout, &s->e_lent, &s->e_map, &s->e_wsfree})
         S_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     S_TRY(cudaMalloc(&s->d_stage, s->n_roi * 4));
@@ -2280,6 +2633,7 @@ int sted_session_set_fluorophores(StedSession* s, const StedFluoParams* fluo_hos
     CUDA_TRY(cudaStreamSynchronize(s->s_comp));
     CUDA_TRY(cudaMemcpy(s->d_fluo, fluo_host, (size_t)s->B * sizeof(StedFluoParams), cudaMemcpyHostToDevice));
     s->fluo_set = true;
+    s->keep_valid = false;                   // tables depend on the fluorophores
     return STED_OK;
 }
 
@@ -2403,16 +2757,34 @@ int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* 
     // ---- s_prep: parameters, tables and (stochastic scan) the death schedule.  Neither depends on the acquisition queued
     // before this one, so they run under it; the schedule needs the final map and a free event scratch.
     const double* d_pdt = s->d_scal[i] + 2 * B;
-    CUDA_TRY(cudaMemcpyAsync(s->d_scal[i], s->h_scal[i], 3ull * B * 8, cudaMemcpyHostToDevice, s->s_prep));
-    if ((rc = sted_make_effective(s->d_cache, s->d_fluo, s->d_scal[i], s->d_scal[i] + B, d_pdt, B, s->K, s->d_tab[i], nullptr,
-                                  s->s_prep)))
-        return rc;
+    const float* d_tab = s->d_tab[i];
+    if (!bleach) {
+        // confocal-type acquisition: the kept tables, rebuilt only when the parameters differ from the kept ones
+        if (!s->keep_valid || memcmp(s->h_scal_keep, s->h_scal[i], 3ull * B * 8) != 0) {
+            memcpy(s->h_scal_keep, s->h_scal[i], 3ull * B * 8);
+            CUDA_TRY(cudaStreamWaitEvent(s->s_prep, s->e_keep_used, 0));      // acquisitions still reading the old ones
+            CUDA_TRY(cudaMemcpyAsync(s->d_scal_keep, s->h_scal[i], 3ull * B * 8, cudaMemcpyHostToDevice, s->s_prep));
+            if ((rc = sted_make_effective(s->d_cache, s->d_fluo, s->d_scal_keep, s->d_scal_keep + B, s->d_scal_keep + 2 * B, B, s->K,
+                                          s->d_tab_keep, nullptr, s->s_prep)))
+                return rc;
+            CUDA_TRY(cudaEventRecord(s->e_keep, s->s_prep));
+            s->keep_valid = true;
+        }
+        CUDA_TRY(cudaStreamWaitEvent(s->s_prep, s->e_keep, 0));
+        d_pdt = s->d_scal_keep + 2 * B;
+        d_tab = s->d_tab_keep;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(s->d_scal[i], s->h_scal[i], 3ull * B * 8, cudaMemcpyHostToDevice, s->s_prep));
+        if ((rc = sted_make_effective(s->d_cache, s->d_fluo, s->d_scal[i], s->d_scal[i] + B, d_pdt, B, s->K, s->d_tab[i], nullptr,
+                                      s->s_prep)))
+            return rc;
+    }
     float* d_in = s->d_map[s->cur];
     float* d_out = s->d_map[s->cur ^ 1];
     if (stoch) {
         CUDA_TRY(cudaStreamWaitEvent(s->s_prep, s->e_map, 0));
         CUDA_TRY(cudaStreamWaitEvent(s->s_prep, s->e_wsfree, 0));
-        if ((rc = sted_bleach_presample(d_in, s->d_tab[i], d_pdt, B, s->H, s->W, s->K, flags, seed, offset, env_base, s->d_ws,
+        if ((rc = sted_bleach_presample(d_in, d_tab, d_pdt, B, s->H, s->W, s->K, flags, seed, offset, env_base, s->d_ws,
                                         s->ws_bytes, s->s_prep)))
             return rc;
     }
@@ -2421,7 +2793,7 @@ int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* 
     CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_prep[i], 0));
     const int it = (int)(s->n_acq++ % StedSession::NT);
     CUDA_TRY(cudaEventRecord(s->e_t0[it], s->s_comp));
-    if ((rc = sted_acquire(d_in, bleach ? d_out : nullptr, s->d_tab[i], d_pdt, B, s->H, s->W, s->K,
+    if ((rc = sted_acquire(d_in, bleach ? d_out : nullptr, d_tab, d_pdt, B, s->H, s->W, s->K,
                            flags | STED_NO_DETECT | (stoch ? STED_PRESAMPLED : 0u), det, lambda_fluo, seed, offset, env_base,
                            intensity_host ? s->d_int[i] : nullptr, s->d_sig[i], stoch ? s->d_ws : nullptr,
                            stoch ? s->ws_bytes : 0, s->s_comp)))
@@ -2440,6 +2812,7 @@ int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* 
     // ---- s_post: detector (+ uint16 conversion), under whatever s_comp runs next
     CUDA_TRY(cudaStreamWaitEvent(s->s_post, s->e_main[i], 0));
     if ((rc = sted_detect(s->d_sig[i], d_pdt, B, s->H, s->W, flags, det, lambda_fluo, seed, offset, env_base, s->s_post))) return rc;
+    if (!bleach) CUDA_TRY(cudaEventRecord(s->e_keep_used, s->s_post));
     if (signal_host || intensity_host) {
         if (u16 && signal_host) {
             counts_to_u16_kernel<<<296, 256, 0, s->s_post>>>(s->d_sig[i], s->d_sig16[i], s->n_roi);

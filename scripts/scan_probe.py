@@ -43,7 +43,11 @@ def scan(n, label):
     import ctypes
     ph = (ctypes.c_uint64 * 8)()
     bm.lib.sted_debug_phase_cycles(ph, 1)
-    if sum(ph):                                          # SWEEP_PROBE == 3 build: cycles per group of rows and CTA
+    if sum(ph) and os.environ.get("PROBE_S3"):           # SWEEP_PROBE == 5 build: sweep3_kernel, cycles per scan row and CTA
+        g = max(1, ph[7])
+        names = ("g.wait", "gather", "g.bar1", "g.decrement", "g.bar2+tma", "c.wait", "c.corr+write")
+        print("    per row: " + "  ".join(f"{nm} {ph[i] / g:.0f}" for i, nm in enumerate(names)), flush=True)
+    elif sum(ph):                                        # SWEEP_PROBE == 3 build: cycles per group of rows and CTA
         g = max(1, ph[6])
         names = ("gather", "g.wait1", "g.phaseB", "aux.stage+ring", "aux.corr", "aux.wait1")
         if os.environ.get("PROBE_SPLIT_B"):              # SWEEP_PROBE == 4 build: thread 0's view of the phase between the barriers

@@ -39,7 +39,7 @@ def test_gpu_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["metric"] == "STED acquisitions/sec" and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["dtype"] == "f32" and d["scaling"] == "weak" and d["vs_baseline"] is None
-    assert d["gpu_launches"] == 15 * 3
+    assert d["gpu_launches"] == 13 * 3
     e = d["e2e"]
     assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     r = d["roofline"]

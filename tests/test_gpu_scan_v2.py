@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 def _run(m, maps, act, seed, env=None):
     from gym_sted_b200.batch import BatchedMicroscope
-    saved = {k: os.environ.get(k) for k in ("STED_B200_SCAN_V1", "STED_B200_ROW_RANGE", "STED_B200_ROW_GROUP")}
+    saved = {k: os.environ.get(k) for k in ("STED_B200_SCAN_V1", "STED_B200_ROW_RANGE", "STED_B200_ROW_GROUP", "STED_B200_SCAN_V3")}
     try:
         for k, v in (env or {}).items():
             os.environ[k] = v
@@ -54,9 +54,11 @@ def test_scan_v2_equals_v1_for_every_row_range(H, W, B):
     ref = _run(m, maps, act, 5, {"STED_B200_SCAN_V1": "1"})
     assert ref[2].sum() < maps.sum()
     for rr in (None, "16", "1", "37", str(H)):
-        for grp in (None, "1", "2", "3", "4"):
+        for grp in (None, "1", "2", "3", "4", "v3"):     # "v3": the third-generation kernel (TMA ring, specialised warps)
             env = {} if rr is None else {"STED_B200_ROW_RANGE": rr}
-            if grp is not None:
+            if grp == "v3":
+                env["STED_B200_SCAN_V3"] = "1"
+            elif grp is not None:
                 env["STED_B200_ROW_GROUP"] = grp
             got = _run(m, maps, act, 5, env)
             what = f"(row range {rr}, row group {grp})"
