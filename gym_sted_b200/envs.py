@@ -179,7 +179,7 @@ class VectorContextualMOSTED:
             self.torch_gen.manual_seed(int(self.np_rng.integers(0, 2 ** 62)))
         frames, coords = synapse.generate_batch_torch(self.B, self.H, self.W, self.device, self.torch_gen)
         self.synapses = [synapse.Synapse(frame=np.zeros((0, 0)), coords=c) for c in coords]
-        self._truths = rewards.pad_coords(coords)           # padded once per structure for the batched F1 matching
+        self._truths = rewards.DeviceTruths(coords, self.device)   # uploaded once per structure for the device F1 matching
         self.frames = frames                                   # molecule maps of the current synapses (device, int32)
         cells = -(-self.H // synapse.CELL) * -(-self.W // synapse.CELL)
         self.bm.set_datamaps(frames, max_molecules=self.B * cells * (5 * synapse.CELL ** 2 + 15 * 175))

@@ -260,22 +260,59 @@ def match_counts_batch(truths, guesses, threshold=2):
     return _match_padded(T, nt, G, np.arange(G.shape[1])[None, :] < ng[:, None], threshold)
 
 
-def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, handle=None) -> np.ndarray:
-    """F1 of B images: candidates and Gaussian-fit validation on the GPU (already enqueued when ``handle`` is given),
-    matching of the few surviving coordinates on the host.  ``truths``: list of (n_i, 2) arrays, or the
-    ``pad_coords`` tuple of such a list (saves re-padding when the same structures are scored repeatedly)."""
+class DeviceTruths:
+    """Ground-truth nanodomain coordinates of B structures on the device: int32 (B, max_truth, 2) + int32 (B,) counts
+    (built once per structure; ``sted_f1_match`` reads them at every step)."""
+
+    def __init__(self, coords, device="cuda"):
+        n = np.array([len(c) for c in coords], dtype=np.int32)
+        T = np.zeros((len(coords), max(int(n.max()) if len(n) else 0, 1), 2), dtype=np.int32)
+        for b, c in enumerate(coords):
+            if n[b]:
+                T[b, :n[b]] = np.asarray(c, dtype=np.int64).reshape(-1, 2)
+        self.coords, self.counts = torch.from_numpy(T).to(device), torch.from_numpy(n).to(device)
+
+
+def nanodomain_f1_counts(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, handle=None):
+    """F1 of B images entirely on the device (north_star: "nanocluster detection plus the F1 reward run on the device"):
+    candidates, Gaussian-fit validation (already enqueued when ``handle`` is given), then ``f1_match_kernel`` — TP = size
+    of a maximum matching of the (truth, detection) pairs closer than ``threshold``, which is what the reference's
+    Hungarian solution on the priced-out cost matrix counts (``objectives.py:425-430``).  One packed device->host read.
+    ``truths``: ``DeviceTruths``, a list of (n_i, 2) arrays, or the ``pad_coords`` tuple of such a list.
+    Returns (f1 (B,) float64, counts (B, 3) int64 = TP, FP, FN)."""
+    lib = _lib.load()
     _, sted32, peaks, npk, flags, valid, done = handle if handle is not None else detect_nanodomains_launch(sted, pixelsize)
-    done.synchronize()
-    peaks, npk, flags, valid = peaks.cpu().numpy(), npk.cpu().numpy(), flags.cpu().numpy(), valid.cpu().numpy()
-    _check_capacity(flags)
-    pm = max(int(npk.max()), 1)
-    keep = (np.arange(pm)[None, :] < npk[:, None]) & (valid[:, :pm] != 0)
-    T, nt = truths if isinstance(truths, tuple) else pad_coords(truths)
-    counts = _match_padded(T, nt, peaks[:, :pm].astype(np.float64), keep, threshold)
-    tp, fp, fn = counts[:, 0].astype(np.float64), counts[:, 1].astype(np.float64), counts[:, 2].astype(np.float64)
-    prec = tp / (tp + fp + 1e-6)
-    rec = tp / (tp + fn + 1e-6)
-    return 2 * prec * rec / (prec + rec + 1e-6)
+    dev = sted32.device
+    if isinstance(truths, tuple):                                     # pad_coords output
+        T, nt = truths
+        truths = [T[b, :nt[b]] for b in range(len(nt))]
+    if not isinstance(truths, DeviceTruths):
+        truths = DeviceTruths(truths, dev)
+    B = sted32.shape[0]
+    cur = torch.cuda.current_stream(dev)
+    cur.wait_event(done)                                              # the detection ran on the side stream
+    out = torch.empty((B, 6), dtype=torch.float64, device=dev)        # f1 | TP FP FN | detector flags | matcher flags
+    counts = torch.empty((B, 3), dtype=torch.int32, device=dev)
+    mflags = torch.empty((B,), dtype=torch.int32, device=dev)
+    f1 = torch.empty((B,), dtype=torch.float64, device=dev)
+    _lib.check(lib.sted_f1_match(peaks.data_ptr(), npk.data_ptr(), valid.data_ptr(), peaks.shape[1], truths.coords.data_ptr(),
+                                 truths.counts.data_ptr(), truths.coords.shape[1], B, float(threshold), counts.data_ptr(),
+                                 f1.data_ptr(), mflags.data_ptr(), cur.cuda_stream))
+    out[:, 0] = f1
+    out[:, 1:4] = counts
+    out[:, 4] = flags
+    out[:, 5] = mflags
+    host = out.cpu().numpy()
+    _check_capacity(host[:, 4].astype(np.int64))
+    if host[:, 5].any():
+        raise _lib.StedError(-4, f"f1_match_kernel capacity exceeded (more than 512 truths or detections) for image "
+                                 f"{int(np.flatnonzero(host[:, 5])[0])}")
+    return host[:, 0].copy(), host[:, 1:4].astype(np.int64)
+
+
+def nanodomain_f1_batch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, handle=None) -> np.ndarray:
+    """(B,) F1 scores; see ``nanodomain_f1_counts``."""
+    return nanodomain_f1_counts(sted, truths, pixelsize, threshold, handle)[0]
 
 
 def match_counts(truth, guess, threshold=2):

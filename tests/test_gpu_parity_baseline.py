@@ -249,3 +249,39 @@ def test_per_env_fluorophores_match_oracle(micro):
         np.testing.assert_allclose(bleached[b], ref_d, rtol=RTOL, atol=1e-6)
         distinct.add(float(np.float32(E.max() / p_ex[b])))
     assert len(distinct) == B                        # the environments really ran different fluorophores
+
+
+# ------------------------------------------------------------------ f2: a structure imaged again and again
+def test_sequence_trajectory_matches_oracle(micro, omicro):
+    """SequenceMOSTED (gym_sted/envs/sequence_sted_env.py:84-109): the same datamap object is imaged step after step and
+    carries its photobleaching.  Four steps of (confocal, STED + bleaching, confocal) with different actions per step and
+    environment, resident maps on the GPU against the oracle's datamap object mutated in place: every image and the map
+    after every step within the noise-free tolerance (float32 rounding accumulates over the steps: 3e-5 at the end)."""
+    rng = np.random.default_rng(21)
+    B, H, W, steps = 3, 64, 64, 4
+    rois = spine_maps(B, H, W, seed=77)
+    bm = batched(micro, B, H, W)
+    bm.set_datamaps(torch.from_numpy(rois))
+    dms = []
+    for b in range(B):
+        dm = po.Datamap(rois[b], PX)
+        dm.set_roi(omicro.cache(PX)[0], "max")
+        dms.append(dm)
+    conf = (defaults.PDT, defaults.P_EX, 0.0)
+    t = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))
+    for s in range(steps):
+        pdt, p_ex, p_sted = rng.uniform(10e-6, 60e-6, B), rng.uniform(2e-6, 18e-6, B), rng.uniform(0.02, 0.3, B)
+        _, c1 = bm.get_signal_and_bleach(*conf, bleach=False, want_intensity=True, noise=False)
+        _, st = bm.get_signal_and_bleach(t(pdt), t(p_ex), t(p_sted), bleach=True, sample_bleach=False, want_intensity=True,
+                                         noise=False)
+        _, c2 = bm.get_signal_and_bleach(*conf, bleach=False, want_intensity=True, noise=False)
+        maps = bm.datamaps_roi().cpu().numpy()
+        tol = RTOL * (1 + s)
+        for b in range(B):
+            _, _, o1 = omicro.get_signal_and_bleach(dms[b], PX, *conf, bleach=False)
+            _, _, os_ = omicro.get_signal_and_bleach(dms[b], PX, pdt[b], p_ex[b], p_sted[b], bleach=True, sample_bleach=False)
+            _, _, o2 = omicro.get_signal_and_bleach(dms[b], PX, *conf, bleach=False)
+            for got, ref in ((c1, o1), (st, os_), (c2, o2)):
+                np.testing.assert_allclose(got[b].cpu().numpy(), ref, rtol=tol, atol=1e-7 * ref.max(), err_msg=f"step {s} env {b}")
+            np.testing.assert_allclose(maps[b], dms[b]["base"][dms[b].roi], rtol=tol, atol=1e-6, err_msg=f"map, step {s} env {b}")
+    assert maps.sum() < 0.9 * rois.sum()                 # the trajectory does bleach

@@ -427,3 +427,87 @@ def test_warp_parallel_fit_equals_single_thread_fit():
     x = x.cpu().numpy()
     for i, (b, k) in enumerate(where):
         assert np.array_equal(x[i], params_h[b, k]), (b, k, x[i], params_h[b, k])
+
+
+def test_device_f1_matching_equals_hungarian():
+    """``sted_f1_match`` (maximum matching under the distance threshold, on the device) against the Hungarian matching
+    on the priced-out cost matrix (``metrics.CentroidDetectionError(..., "hungarian")`` as restated by
+    ``rewards.match_counts``): TP / FP / FN identical, F1 identical in float64 — with contested pairs (several detections
+    within reach of one truth and vice versa, chains that need an augmenting path), invalid candidates, empty lists."""
+    from gym_sted_b200 import _lib
+    _gpu()
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    B, maxp = 64, 256
+    peaks = np.zeros((B, maxp, 2), dtype=np.int32)
+    npk = np.zeros(B, dtype=np.int32)
+    valid = np.zeros((B, maxp), dtype=np.uint8)
+    truths = []
+    for b in range(B):
+        nt = int(rng.integers(0, 16)) if b else 0
+        t = rng.integers(4, 60, (nt, 2))
+        if b % 3 == 1 and nt:                                        # dense clusters: many pairs closer than 2 px
+            t = (t[0] + rng.integers(-2, 3, (nt, 2))).clip(0, 63)
+        truths.append(t)
+        ng = int(rng.integers(0, 40)) if b != 1 else 0
+        g = rng.integers(0, 64, (ng, 2))
+        k = min(nt, ng)
+        if k:
+            g[:k] = t[:k] + rng.integers(-1, 2, (k, 2))              # near misses of the truths
+        if b % 5 == 2 and nt >= 2 and ng >= 2:                       # a chain: g0 reaches t0 and t1, g1 only t0
+            t[0], t[1] = (20, 20), (20, 22)
+            g[0], g[1] = (20, 21), (19, 20)
+        peaks[b, :ng] = g
+        npk[b] = ng
+        valid[b, :ng] = rng.random(ng) < 0.8
+    dt = rewards.DeviceTruths(truths, "cuda")
+    d = lambda a: torch.from_numpy(a).cuda()
+    dp, dn, dv = d(peaks), d(npk), d(valid)
+    counts = torch.empty((B, 3), dtype=torch.int32, device="cuda")
+    f1 = torch.empty((B,), dtype=torch.float64, device="cuda")
+    flags = torch.empty((B,), dtype=torch.int32, device="cuda")
+    _lib.check(lib.sted_f1_match(dp.data_ptr(), dn.data_ptr(), dv.data_ptr(), maxp, dt.coords.data_ptr(), dt.counts.data_ptr(),
+                                 dt.coords.shape[1], B, 2.0, counts.data_ptr(), f1.data_ptr(), flags.data_ptr(), None))
+    torch.cuda.synchronize()
+    counts, f1 = counts.cpu().numpy(), f1.cpu().numpy()
+    assert not flags.cpu().numpy().any()
+    contested = 0
+    for b in range(B):
+        g = peaks[b, :npk[b]][valid[b, :npk[b]].astype(bool)]
+        ref = rewards.match_counts(truths[b], g)
+        assert tuple(counts[b]) == ref, (b, counts[b], ref)
+        assert f1[b] == rewards.f1_from_counts(*ref)
+        dist = np.sqrt(((np.asarray(truths[b])[:, None, :] - g[None, :, :]) ** 2).sum(-1)) if len(truths[b]) and len(g) else np.zeros((0, 0))
+        contested += int(((dist < 2).sum(0) > 1).any() or ((dist < 2).sum(1) > 1).any()) if dist.size else 0
+    assert contested >= 10                                           # the augmenting-path code was exercised
+    # valid_dev = NULL keeps every candidate
+    c2 = torch.empty((B, 3), dtype=torch.int32, device="cuda")
+    f2 = torch.empty((B,), dtype=torch.float64, device="cuda")
+    _lib.check(lib.sted_f1_match(dp.data_ptr(), dn.data_ptr(), None, maxp, dt.coords.data_ptr(), dt.counts.data_ptr(),
+                                 dt.coords.shape[1], B, 2.0, c2.data_ptr(), f2.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    for b in (2, 7, 30):
+        assert tuple(c2[b].cpu().numpy()) == rewards.match_counts(truths[b], peaks[b, :npk[b]])
+
+
+def test_f1_batch_runs_on_the_device_and_matches_the_host_path():
+    _gpu()
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[:64, :64]
+    B = 5
+    imgs, truths = [], []
+    for b in range(B):
+        img = rng.poisson(0.3, (64, 64)).astype(np.float32)
+        t = rng.integers(6, 58, (5, 2))
+        for (y, x) in t:
+            img += rng.poisson(90 * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * 1.8 ** 2)))
+        imgs.append(img)
+        truths.append(t)
+    sted = torch.from_numpy(np.stack(imgs)).cuda()
+    f1, counts = rewards.nanodomain_f1_counts(sted, truths)
+    for b in range(B):
+        ref = rewards.match_counts(truths[b], rewards.detect_nanodomains(imgs[b]))
+        assert tuple(counts[b]) == ref
+        assert f1[b] == rewards.f1_from_counts(*ref)
+    assert np.array_equal(rewards.nanodomain_f1_batch(sted, rewards.pad_coords(truths)), f1)
+    assert np.array_equal(rewards.nanodomain_f1_batch(sted, rewards.DeviceTruths(truths)), f1)
