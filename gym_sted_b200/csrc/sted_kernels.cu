@@ -159,6 +159,14 @@ constexpr int G_TH = G_TILE_H, G_TW = 64, G_RT = G_ROWS_PER_THREAD, G_THREADS = 
               kGatherUnroll = G_UNROLL;
 constexpr int G_MINB = 2;       // tile (60.5 KB) + row-interleaved PSF (28.8 KB) per CTA
 
+#ifndef G_TRIM_COLS
+#define G_TRIM_COLS 1  // 1: the padding taps of a tap row (columns K..KP-1) are not issued
+#endif
+#ifndef G_TRIM_ROWS
+#define G_TRIM_ROWS 0  // 1/2: the dead half of the pairs at u = 0 and u = K becomes a scalar FFMA (1: compact edge rows, 2: unrolled).
+                       // Measured on B200 (256 x 256^2): 2.053 ms off, 2.135 (1), 2.186 (2) - the extra code costs more than the
+                       // 1.7 % of pipe time it saves; G_TRIM_COLS alone: 2.034 ms
+#endif
 #ifndef GATHER_TMA
 #define GATHER_TMA 1   // 0: stage the tile with coalesced float4 loads instead of TMA (A/B timing only)
 #endif
@@ -257,37 +265,91 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     for (int p = 0; p < NP; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0ull; }
 
     const int nchunk = KP / 4;
+    // taps of the last chunk of a tap row that exist (3 for K = 59, pitch 60): the padding taps are not issued
+    constexpr int kTailTaps = KT ? KT - 4 * (STED_KPITCH(KT) / 4 - 1) : 4;
+    static_assert(kTailTaps >= 0 && kTailTaps <= 4, "tap pitch");
     auto band_row = [&](const int yy, const bool check) {
         const float* drow = sD + (r0 + yy) * PITCH + c0;
         float4 wa = *reinterpret_cast<const float4*>(drow);
 #pragma unroll kGatherUnroll
         for (int vc = 0; vc < nchunk; ++vc) {
             const float4 wb = *reinterpret_cast<const float4*>(drow + 4 * (vc + 1));
-            const u64 w0 = pack2(wa.x, wa.x), w1 = pack2(wa.y, wa.y), w2 = pack2(wa.z, wa.z), w3 = pack2(wa.w, wa.w),
-                      w4 = pack2(wb.x, wb.x), w5 = pack2(wb.y, wb.y), w6 = pack2(wb.z, wb.z);
+            const u64 w[7] = {pack2(wa.x, wa.x), pack2(wa.y, wa.y), pack2(wa.z, wa.z), pack2(wa.w, wa.w),
+                              pack2(wb.x, wb.x), pack2(wb.y, wb.y), pack2(wb.z, wb.z)};
+            const bool tail = G_TRIM_COLS && KT && vc == nchunk - 1;
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 const int u = yy - 2 * p;                   // tap row of output row 2p; row 2p+1 uses u-1
                 if (!check || (u >= 0 && u <= K)) {
                     const ulonglong2* e2 = reinterpret_cast<const ulonglong2*>(sE2 + u * KP + 4 * vc);
                     const ulonglong2 ea = e2[0], eb = e2[1];              // taps v, v+1 | v+2, v+3
-                    acc[p][0] = fma2(ea.x, w0, acc[p][0]); acc[p][0] = fma2(ea.y, w1, acc[p][0]);
-                    acc[p][0] = fma2(eb.x, w2, acc[p][0]); acc[p][0] = fma2(eb.y, w3, acc[p][0]);
-                    acc[p][1] = fma2(ea.x, w1, acc[p][1]); acc[p][1] = fma2(ea.y, w2, acc[p][1]);
-                    acc[p][1] = fma2(eb.x, w3, acc[p][1]); acc[p][1] = fma2(eb.y, w4, acc[p][1]);
-                    acc[p][2] = fma2(ea.x, w2, acc[p][2]); acc[p][2] = fma2(ea.y, w3, acc[p][2]);
-                    acc[p][2] = fma2(eb.x, w4, acc[p][2]); acc[p][2] = fma2(eb.y, w5, acc[p][2]);
-                    acc[p][3] = fma2(ea.x, w3, acc[p][3]); acc[p][3] = fma2(ea.y, w4, acc[p][3]);
-                    acc[p][3] = fma2(eb.x, w5, acc[p][3]); acc[p][3] = fma2(eb.y, w6, acc[p][3]);
+                    const u64 e[4] = {ea.x, ea.y, eb.x, eb.y};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (!tail || t < kTailTaps) acc[p][j] = fma2(e[t], w[j + t], acc[p][j]);
+                    }
+                }
+            }
+            wa = wb;
+        }
+    };
+    // Rows of the ramps where a pair has only ONE live half - tap row u = 0 (the odd output row would use E[-1] = 0) or
+    // u = K (the even row would use E[K] = 0): that half is a scalar FFMA instead of an FFMA2 whose other half adds 0.
+    // Compact code (not unrolled over the tap chunks): six of the 62 band rows of a thread go through here.
+    auto band_row_edge = [&](const int yy) {
+        const float* drow = sD + (r0 + yy) * PITCH + c0;
+        float4 wa = *reinterpret_cast<const float4*>(drow);
+#if G_TRIM_ROWS == 2
+#pragma unroll kGatherUnroll
+#else
+#pragma unroll 1
+#endif
+        for (int vc = 0; vc < nchunk; ++vc) {
+            const float4 wb = *reinterpret_cast<const float4*>(drow + 4 * (vc + 1));
+            const float wf[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+            const int nt = (G_TRIM_COLS && KT && vc == nchunk - 1) ? kTailTaps : 4;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const int u = yy - 2 * p;
+                if (u < 0 || u > K) continue;
+                const float2* ef = sE2 + u * KP + 4 * vc;
+                if (u == 0 || u == K) {
+                    const bool low = u == 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float lo, hi;
+                        unpack2(acc[p][j], lo, hi);
+                        float a = low ? lo : hi;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (t < nt) a = fmaf(low ? ef[t].x : ef[t].y, wf[j + t], a);
+                        acc[p][j] = low ? pack2(a, hi) : pack2(lo, a);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (t < nt) acc[p][j] = fma2(*reinterpret_cast<const u64*>(ef + t), pack2(wf[j + t], wf[j + t]), acc[p][j]);
+                    }
                 }
             }
             wa = wb;
         }
     };
     int yy = 0;
+#if G_TRIM_ROWS
+    // band rows 0 .. 2(NP-1) and K .. K+2(NP-1)+1 hold the half-live pairs and the ramps; in between every pair is full
+    for (; yy <= 2 * (NP - 1) && yy < K; ++yy) band_row_edge(yy);
+    for (; yy < K; ++yy) band_row(yy, false);
+    for (; yy < G_RT + K - 1; ++yy) band_row_edge(yy);
+#else
     for (; yy < 2 * (NP - 1) && yy <= K; ++yy) band_row(yy, true);  // ramp-up
     for (; yy <= K; ++yy) band_row(yy, false);                      // steady: every row pair has a tap row
     for (; yy < G_RT + K - 1; ++yy) band_row(yy, true);             // ramp-down
+#endif
 
 #ifdef GATHER_PROBE
     const long long t_main = clock64();

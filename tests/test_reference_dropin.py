@@ -135,7 +135,9 @@ def test_reference_bleach_sampler_uniform_runs(ref_on_product):
     sampler = gu.BleachSampler("uniform")
     fluo = sampler.sample()
     crit = sampler.criterion.criterions
-    assert 1e-22 < fluo["sigma_abs"][635] < 2e-20 and 0 < fluo["k1"] < 1e-14 and 0 < fluo["b"] <= 5
+    # criteria are uniform in gym_sted/defaults.py:149-162: up to 400 photons at as little as 1 uW of excitation needs
+    # sigma_abs up to ~8e-20 m^2 (3.2e-21 gives ~163 photons at 10 uW); the fit is run on a Poisson-noisy objective
+    assert 1e-22 < fluo["sigma_abs"][635] < 1.2e-19 and 0 < fluo["k1"] < 1e-14 and 0 < fluo["b"] <= 5
     opt = sampler.optimizer
     opt.microscope.fluo.sigma_abs, opt.microscope.fluo.k1, opt.microscope.fluo.b = fluo["sigma_abs"], fluo["k1"], fluo["b"]
     reached = opt.expected_bleach(crit["bleach"]["p_ex"], crit["bleach"]["p_sted"], crit["bleach"]["pdt"])
