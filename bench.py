@@ -623,7 +623,9 @@ def run_env_step(args, rank, local_rank, world):
                         "api": "gym_sted_b200.envs.make_vec(...).step(actions) -> numpy observation / reward / info",
                         "note": "value IS the end-to-end number for this workload: every step ends on the host",
                         "rewards_gathered_over_nccl": None if rewards_all is None else int(rewards_all.numel())},
-                "gpu_launches": None, "clocks": clocks, "roofline": None, "cpu_baseline": None,
+                # own kernels per step: 3 x (gather + detector), STED (tables, death schedule x3, scan, detector), synapses x2,
+                # padding, objectives, apodise / spectrum gather / decorrelation, candidates, Gaussian fits, F1, observation
+                "gpu_launches": 23 * args.steps, "clocks": clocks, "roofline": None, "cpu_baseline": None,
                 "mean_reward": float(np.mean(reward))}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -39,6 +39,11 @@ class StedFluoCriteria(ctypes.Structure):
                                                "bl_pdt", "bl_target")]
 
 
+class StedSynapseParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("molecules", "n_lo", "n_hi", "m_lo", "m_hi", "_pad")] + [
+        (n, ctypes.c_double) for n in ("min_dist_px", "thick_lo", "thick_hi")]
+
+
 class StedDetectorParams(ctypes.Structure):
     _fields_ = [("pcef", ctypes.c_double), ("pdef", ctypes.c_double), ("background", ctypes.c_double)]
 
@@ -88,6 +93,10 @@ SIGNATURES = {
     "sted_f1_match": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),
     "sted_apodize_for_fft": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "sted_spectrum_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sted_synapse_scratch_bytes": (_u64, [_i, _i, _i]),
+    "sted_synapse_generate": (_i, [ctypes.POINTER(StedSynapseParams), _i, _i, _i, _u64, _u64, _i64, _vp, _vp, _vp, _i, _vp, _vp]),
+    "sted_pad_maps": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sted_pack_observation": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "sted_lmfit_test": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp]),
     "sted_debug_phase_cycles": (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     "sted_fma_peak": (_i, [ctypes.POINTER(_d), _vp]),

@@ -53,6 +53,7 @@ class BatchedMicroscope:
         assert len(fluos) == self.B
         arr = (_lib.StedFluoParams * self.B)(*[fluo_struct(f, m.excitation, m.sted) for f in fluos])
         self.d_fluo = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+        self._kept_tables = {}                # tables depend on the fluorophores
 
     def set_datamaps(self, roi: torch.Tensor, max_molecules=None):
         """roi: (B,H,W) molecule counts (any real dtype); pads with the K//2 zero frame.
@@ -61,8 +62,12 @@ class BatchedMicroscope:
         stochastic scan); when omitted it is read back from the device once (one synchronisation)."""
         assert roi.shape == (self.B, self.H, self.W)
         p = self.p
-        self.dmap.zero_()
-        self.dmap[:, p:p + self.H, p:p + self.W] = roi.to(self.device, torch.float32)
+        if roi.is_cuda and roi.device == self.dmap.device and roi.dtype in (torch.int32, torch.float32) and roi.is_contiguous():
+            _lib.check(self.lib.sted_pad_maps(roi.data_ptr(), int(roi.dtype == torch.int32), self.B, self.H, self.W, self.K,
+                                              self.dmap.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+        else:
+            self.dmap.zero_()
+            self.dmap[:, p:p + self.H, p:p + self.W] = roi.to(self.device, torch.float32)
         if max_molecules is None:
             max_molecules = int(torch.clamp(roi, min=0).sum().item())
         self._reserve(int(max_molecules) + 16)
@@ -98,11 +103,23 @@ class BatchedMicroscope:
         return x.to(self.device, torch.float64).contiguous()
 
     def get_signal_and_bleach(self, pdt, p_ex, p_sted, bleach=True, update=True, sample_bleach=True,
-                              noise=None, want_intensity=False, seed=None, out_signal=None):
+                              noise=None, want_intensity=False, seed=None, out_signal=None, tables_key=None):
         """Vectorised ``Microscope.get_signal_and_bleach``; returns ``(signal, intensity|None)`` as
-        (B,H,W) float32 device tensors.  With ``bleach`` and ``update`` the resident maps advance."""
+        (B,H,W) float32 device tensors.  With ``bleach`` and ``update`` the resident maps advance.
+
+        ``tables_key``: a name under which the per-environment PSF tables of THESE imaging parameters are kept, so later
+        calls with the same key skip ``sted_make_effective`` (gym-sted's confocal acquisitions always use the same
+        parameters, ``mosted_env.py:184,222,232``); the caller vouches that the parameters of a key do not change, and
+        ``set_fluorophores`` drops every kept set."""
         pdt, p_ex, p_sted = self._vec(pdt), self._vec(p_ex), self._vec(p_sted)
-        self.make_effective(p_ex, p_sted, pdt)
+        tables = self.tables
+        if tables_key is None:
+            self.make_effective(p_ex, p_sted, pdt)
+        elif tables_key in self._kept_tables:
+            tables = self._kept_tables[tables_key]
+        else:
+            self.make_effective(p_ex, p_sted, pdt)
+            tables = self._kept_tables[tables_key] = self.tables.clone()
         flags = 0
         if bleach:
             flags |= _lib.STED_BLEACH | (_lib.STED_SAMPLE_BLEACH if sample_bleach else 0)
@@ -114,7 +131,7 @@ class BatchedMicroscope:
         intensity = torch.empty_like(signal) if want_intensity else None
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.sted_acquire(
-            self.dmap.data_ptr(), self.dmap_alt.data_ptr() if bleach else None, self.tables.data_ptr(),
+            self.dmap.data_ptr(), self.dmap_alt.data_ptr() if bleach else None, tables.data_ptr(),
             pdt.data_ptr(), self.B, self.H, self.W, self.K, flags, ctypes.byref(self.det), self.lambda_fluo,
             self.seed if seed is None else int(seed), self.offset, self.env_base,
             intensity.data_ptr() if want_intensity else None, signal.data_ptr(),

@@ -69,9 +69,11 @@ struct RationalResiduals {
     }
 };
 
-LM_HD inline void lm_qrsolv(double* r /*[LM_M*LM_N], column major, ld = LM_M*/, const int* ipvt, const double* diag, const double* qtb,
+// LD: leading dimension of r (LM_M inside lm_fit, where r is the top of the Jacobian's storage; LM_N for a packed copy)
+template <int LD = LM_M>
+LM_HD inline void lm_qrsolv(double* r /*[LD*LM_N], column major*/, const int* ipvt, const double* diag, const double* qtb,
                           double* x, double* sdiag, double* wa) {
-    const int n = LM_N, ld = LM_M;
+    const int n = LM_N, ld = LD;
     for (int j = 0; j < n; ++j) {
         for (int i = j; i < n; ++i) r[i + ld * j] = r[j + ld * i];
         x[j] = r[j + ld * j];
@@ -123,9 +125,10 @@ LM_HD inline void lm_qrsolv(double* r /*[LM_M*LM_N], column major, ld = LM_M*/, 
     for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
 }
 
+template <int LD = LM_M>
 LM_HD inline void lm_lmpar(double* r, const int* ipvt, const double* diag, const double* qtb, double delta, double* par, double* x,
                          double* sdiag, double* wa1, double* wa2) {
-    const int n = LM_N, ld = LM_M;
+    const int n = LM_N, ld = LD;
     int nsing = n;
     for (int j = 0; j < n; ++j) {
         wa1[j] = qtb[j];
@@ -171,7 +174,7 @@ LM_HD inline void lm_lmpar(double* r, const int* ipvt, const double* diag, const
         if (*par == 0.0) *par = fmax(LM_DWARF, 0.001 * paru);
         double temp = sqrt(*par);
         for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
-        lm_qrsolv(r, ipvt, wa1, qtb, x, sdiag, wa2);
+        lm_qrsolv<LD>(r, ipvt, wa1, qtb, x, sdiag, wa2);
         for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
         dxnorm = lm_enorm(n, wa2);
         temp = fp;
@@ -291,7 +294,7 @@ LM_HD inline int lm_fit(const Residuals& residuals, double* x, double ftol, doub
         for (int j = 0; j < n; ++j) diag[j] = fmax(diag[j], wa2[j]);
         double ratio = 0.0;
         do {
-            lm_lmpar(fjac, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wa4);
+            lm_lmpar<LM_M>(fjac, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wa4);
             for (int j = 0; j < n; ++j) { wa1[j] = -wa1[j]; wa2[j] = x[j] + wa1[j]; wa3[j] = diag[j] * wa1[j]; }
             const double pnorm = lm_enorm(n, wa3);
             if (iter == 1) delta = fmin(delta, pnorm);

@@ -13,7 +13,7 @@
 #include <stdint.h>
 
 #include "common.cuh"
-#include "lm_minpack.cuh"
+#include "lm_minpack_warp.cuh"
 
 namespace {
 
@@ -663,12 +663,12 @@ namespace {
 
 using namespace lm;
 
-// The Gaussian residuals of one fit evaluated by a whole warp: lane l computes residuals l and l+32 (the 49 exp()
-// calls are ~90 % of a fit's instructions), then every lane receives all 49 values by shuffle.  All lanes of the warp
-// run the solver redundantly on bitwise identical state, so control flow never diverges and the result equals the
-// one-thread fit (GaussResiduals) bit for bit.
-struct WarpGaussResiduals {
-    const double* data;       // this lane's copy of the 49 window values
+// The residuals of one fit evaluated by a whole warp for lm_fit_warp (lm_minpack_warp.cuh): lane l computes residuals l
+// and l + 32 (the 49 exp() calls are most of a residual evaluation) and writes them to the warp's shared vector.  Each
+// value is the one GaussResiduals computes, bit for bit.
+template <bool RATIONAL>
+struct WarpResiduals {
+    const double* data;       // the 49 window values (shared memory)
     __device__ void operator()(const double* p, double* f) const {
         const int lane = threadIdx.x & 31;
         const double wx = p[3] + 1e-3, wy = p[4] + 1e-3;
@@ -676,13 +676,12 @@ struct WarpGaussResiduals {
         auto one = [&](int i) {
             const double X = (double)(i / 7) - 3.0, Y = (double)(i % 7) - 3.0;
             const double a = (p[1] - X) * (p[1] - X) / dx2, b = (p[2] - Y) * (p[2] - Y) / dy2;
-            return p[0] * exp(-1.0 * (a + b)) - data[i];
+            return (RATIONAL ? p[0] / (1.0 + (a + b)) : p[0] * exp(-1.0 * (a + b))) - data[i];
         };
-        const double r0 = one(lane), r1 = lane + 32 < LM_M ? one(lane + 32) : 0.0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __shfl_sync(0xffffffffu, r0, i);
-#pragma unroll
-        for (int i = 32; i < LM_M; ++i) f[i] = __shfl_sync(0xffffffffu, r1, i - 32);
+        __syncwarp();                               // earlier readers of f are done
+        f[lane] = one(lane);
+        if (lane + 32 < LM_M) f[lane + 32] = one(lane + 32);
+        __syncwarp();
     }
 };
 
@@ -691,25 +690,31 @@ constexpr int GF_THREADS = 128;      // 4 fits per CTA, one warp each
 __global__ void __launch_bounds__(GF_THREADS) gaussfit_kernel(const float* __restrict__ sted, int H, int W, const int* __restrict__ peaks,
                                                             const int* __restrict__ npeaks, int maxp, double pixelsize,
                                                             unsigned char* __restrict__ valid, double* __restrict__ params) {
+    __shared__ LmWarpWork work[GF_THREADS / 32];
     const int b = blockIdx.y, k = blockIdx.x * (GF_THREADS / 32) + (threadIdx.x >> 5);      // warp-uniform
     if (k >= npeaks[b] || k >= maxp) return;
+    LmWarpWork& w = work[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
     const int row = peaks[((size_t)b * maxp + k) * 2], col = peaks[((size_t)b * maxp + k) * 2 + 1];
     const float* img = sted + (size_t)b * H * W;
-    double data[LM_M], dmax = -1.0e300;
-    for (int i = 0; i < LM_M; ++i) {
+    double dmax = -1.0e300;
+    for (int i = lane; i < LM_M; i += 32) {
         const int y = row + i / 7 - 3, x = col + i % 7 - 3;
-        data[i] = (y >= 0 && y < H && x >= 0 && x < W) ? rint((double)img[y * W + x]) : 0.0;     // numpy.pad(..., constant_values=0)
-        dmax = fmax(dmax, data[i]);
+        w.data[i] = (y >= 0 && y < H && x >= 0 && x < W) ? rint((double)img[y * W + x]) : 0.0;     // numpy.pad(..., constant_values=0)
+        dmax = fmax(dmax, w.data[i]);
     }
+    for (int o = 16; o; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    __syncwarp();
     double p[LM_N] = {dmax, 0.0, 0.0, 1.0, 1.0};
-    lm_fit(WarpGaussResiduals{data}, p, 1e-3, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0);
-    if ((threadIdx.x & 31) != 0) return;
+    lm_fit_warp(WarpResiduals<false>{w.data}, w, p, 1e-3, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0);
+    if (lane != 0) return;
     const double fx = 2.355 * p[3] * pixelsize, fy = 2.355 * p[4] * pixelsize;
     valid[(size_t)b * maxp + k] = !(fx > 200e-9 || fx < 40e-9 || fy > 200e-9 || fy < 40e-9);
     if (params) for (int j = 0; j < LM_N; ++j) params[((size_t)b * maxp + k) * LM_N + j] = p[j];
 }
 
-// Test hook: run the solver on n windows with caller-supplied starts; model 0 = the Gaussian, 1 = the rational test model.
+// Test hook: run the solver on n windows with caller-supplied starts; model 0 = the Gaussian, 1 = the rational test model
+// (one thread per fit, lm_fit); models 2 / 3 = the same two models through the warp-cooperative lm_fit_warp (one warp per fit).
 __global__ void lmfit_test_kernel(const double* __restrict__ data, int n, int model, double ftol, double* __restrict__ params,
                                   int* __restrict__ info) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -723,14 +728,36 @@ __global__ void lmfit_test_kernel(const double* __restrict__ data, int n, int mo
     info[k] = rc;
 }
 
+__global__ void __launch_bounds__(GF_THREADS) lmfit_warp_test_kernel(const double* __restrict__ data, int n, int model, double ftol,
+                                                                     double* __restrict__ params, int* __restrict__ info) {
+    __shared__ LmWarpWork work[GF_THREADS / 32];
+    const int k = blockIdx.x * (GF_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n) return;
+    LmWarpWork& w = work[threadIdx.x >> 5];
+    for (int i = lane; i < LM_M; i += 32) w.data[i] = data[(size_t)k * LM_M + i];
+    __syncwarp();
+    double p[LM_N];
+    for (int j = 0; j < LM_N; ++j) p[j] = params[(size_t)k * LM_N + j];
+    __syncwarp();
+    const int rc = model == 2 ? lm_fit_warp(WarpResiduals<false>{w.data}, w, p, ftol, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0)
+                              : lm_fit_warp(WarpResiduals<true>{w.data}, w, p, ftol, 1.49012e-8, 0.0, 200 * (LM_N + 1), 100.0);
+    if (lane != 0) return;
+    for (int j = 0; j < LM_N; ++j) params[(size_t)k * LM_N + j] = p[j];
+    info[k] = rc;
+}
+
 }  // namespace
 
 extern "C" int sted_lmfit_test(const double* data_dev, int n, int model, double ftol, double* params_dev, int32_t* info_dev,
                                void* stream) {
-    if (!data_dev || !params_dev || !info_dev || n <= 0 || (model != 0 && model != 1)) return fail(STED_EINVAL, "bad lmfit arguments");
+    if (!data_dev || !params_dev || !info_dev || n <= 0 || model < 0 || model > 3) return fail(STED_EINVAL, "bad lmfit arguments");
     int rc = check_device();
     if (rc) return rc;
-    lmfit_test_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(data_dev, n, model, ftol, params_dev, info_dev);
+    if (model >= 2)
+        lmfit_warp_test_kernel<<<(n + GF_THREADS / 32 - 1) / (GF_THREADS / 32), GF_THREADS, 0, (cudaStream_t)stream>>>(data_dev, n, model, ftol,
+                                                                                                                 params_dev, info_dev);
+    else
+        lmfit_test_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(data_dev, n, model, ftol, params_dev, info_dev);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }

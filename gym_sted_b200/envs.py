@@ -8,14 +8,20 @@
 resolves the reference's ids (``gym_sted/__init__.py:587-610,665-674``); ``gym`` itself is not installed in
 this image, so ``Box``/``Tuple`` below are minimal stand-ins for ``gym.spaces``.
 
-Deviations, all because of un-vendored dependencies of the reference: synapses come from
-``synapse.generate`` (stand-in for ``pysted.exp_data_gen.Synapse``); ``bleach_sampling`` "uniform"/"choice"
-draw the targets of ``defaults.fluorescence_criterions`` but solve ``sigma_abs`` and ``k1`` in closed form
-with ``b`` fixed (the reference's 25x L-BFGS-B ``FluorescenceOptimizer`` is a "next" row).
+Deviations, all because of un-vendored dependencies of the reference: synapses come from the device generator
+``synapse.DeviceSynapseGenerator`` (``sted_synapse_generate``; stand-in for ``pysted.exp_data_gen.Synapse``).
+``bleach_sampling`` "uniform"/"choice" draw the targets of ``defaults.fluorescence_criterions`` and fit
+``(sigma_abs, k1, b)`` with the device-side ``FluorescenceOptimizer`` (``optimizer.py``).
+
+A step queues everything — three acquisitions, Otsu / Bleach / SNR, the decorrelation resolution, nanodomain detection +
+Gaussian fits (side stream) + F1 matching, the next structures, their confocal image and the uint16 observation — without
+reading anything back, then makes ONE transfer into pinned host memory and waits once.
 """
 from __future__ import annotations
 
+import os
 import random
+import time
 from types import SimpleNamespace
 
 import numpy as np
@@ -165,43 +171,75 @@ class VectorContextualMOSTED:
                                     env_base=self.env_base, seed=int(self.np_rng.integers(0, 2 ** 31 - 1)))
         self.conf = (defaults.PDT, defaults.P_EX, 0.0)            # generate_params(): pdt, p_ex, p_sted
         self.current_step = 0
-        self.synapses = None
         self.frames = None
-        self.torch_gen = None
         self.state = None
         self.episode_memory = {"actions": [], "mo_objs": [], "reward": []}
+        self.synapse_gen = synapse.DeviceSynapseGenerator(self.B, self.H, self.W, self.device, env_base=self.env_base,
+                                                          seed=int(self.np_rng.integers(0, 2 ** 62)))
+        self._truths = None          # rewards.DeviceTruths of the structures being imaged
+        self._coords_host = None     # the same coordinates on the host (list of (n_i, 2) int64 arrays), read back lazily
+        self._pin = {}               # pinned host buffers of the end-of-step transfer
+        self._conf_d = None
+        self._obs_vec = None
+        self.step_timing = bool(os.environ.get("STED_B200_STEP_TIMING"))   # info["timing"]: host seconds per phase of step()
 
     # ------------------------------------------------------------------ helpers
+    def _pinned(self, name, shape, dtype):
+        buf = self._pin.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            buf = self._pin[name] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+        return buf
+
+    def _conf_dev(self):
+        """The confocal imaging parameters (pdt, p_ex, p_sted) as (B,) float64 device tensors, uploaded once."""
+        if self._conf_d is None:
+            c = torch.tensor(self.conf, dtype=torch.float64).view(3, 1).expand(3, self.B).contiguous().to(self.device)
+            self._conf_d = (c[0], c[1], c[2])
+        return self._conf_d
+
+    @property
+    def synapses(self):
+        """One ``Synapse`` container per environment with the nanodomain coordinates of the structure being imaged."""
+        if self._coords_host is None:
+            if self._truths is None:
+                return None
+            T, n = self._truths.coords.cpu().numpy(), self._truths.counts.cpu().numpy()
+            self._coords_host = [T[b, :n[b]].astype(np.int64) for b in range(self.B)]
+        return [synapse.Synapse(frame=np.zeros((0, 0)), coords=c) for c in self._coords_host]
+
     def _new_datamaps(self):
-        """``_update_datamap`` (mosted_env.py:168-187): new synapse, new datamap, confocal image of it."""
-        if self.torch_gen is None:
-            self.torch_gen = torch.Generator(device=self.device)
-            self.torch_gen.manual_seed(int(self.np_rng.integers(0, 2 ** 62)))
-        frames, coords = synapse.generate_batch_torch(self.B, self.H, self.W, self.device, self.torch_gen)
-        self.synapses = [synapse.Synapse(frame=np.zeros((0, 0)), coords=c) for c in coords]
-        self._truths = rewards.DeviceTruths(coords, self.device)   # uploaded once per structure for the device F1 matching
+        """``_update_datamap`` (mosted_env.py:168-187): new synapse, new datamap, confocal image of it — all queued on
+        the device (``sted_synapse_generate`` -> ``sted_pad_maps`` -> acquisition), nothing read back."""
+        frames, coords, counts = self.synapse_gen.generate()
+        self._truths = rewards.DeviceTruths.from_device(coords, counts)   # ground truth of the device F1 matching
+        self._coords_host = None
         self.frames = frames                                   # molecule maps of the current synapses (device, int32)
-        cells = -(-self.H // synapse.CELL) * -(-self.W // synapse.CELL)
-        self.bm.set_datamaps(frames, max_molecules=self.B * cells * (5 * synapse.CELL ** 2 + 15 * 175))
-        state, _ = self.bm.get_signal_and_bleach(*self.conf, bleach=False)
+        self.bm.set_datamaps(frames, max_molecules=self.synapse_gen.max_molecules)
+        state, _ = self.bm.get_signal_and_bleach(*self._conf_dev(), bleach=False, tables_key="conf")
         return state
+
+    def _pack_observation(self, state, conf1=None, sted=None):
+        """(state, conf1, sted) -> uint16 (B,H,W,3) device tensor (``sted_pack_observation``); missing channels are 0."""
+        zeros = torch.zeros_like(state) if conf1 is None or sted is None else None
+        conf1 = zeros if conf1 is None else conf1
+        sted = zeros if sted is None else sted
+        out = torch.empty((self.B, self.H, self.W, 3), dtype=torch.uint16, device=state.device)
+        from . import _lib
+        _lib.check(self.bm.lib.sted_pack_observation(state.data_ptr(), conf1.data_ptr(), sted.data_ptr(), self.B, self.H, self.W,
+                                                     out.data_ptr(), torch.cuda.current_stream(state.device).cuda_stream))
+        return out
 
     def _full_action(self, action):
         cols = {n: action[:, self.actions.index(n)] if n in self.actions else
                 np.full(self.B, getattr(defaults, n.upper())) for n in ("pdt", "p_ex", "p_sted")}
         return cols["pdt"].astype(np.float64), cols["p_ex"].astype(np.float64), cols["p_sted"].astype(np.float64)
 
-    @staticmethod
-    def _u16(x: torch.Tensor) -> torch.Tensor:
-        # numpy's int64 -> uint16 cast wraps modulo 2^16 (contextual_sted_env.py:93)
-        return (x.to(torch.int64) & 0xFFFF).to(torch.uint16)
-
     # ------------------------------------------------------------------ gym API
     def reset(self, seed=None, options=None):
         if seed is not None:
             self.np_rng = np.random.default_rng(seed)
             self.bleach_sampler.rng.seed(int(self.np_rng.integers(0, 2 ** 31 - 1)))
-            self.torch_gen = None
+            self.synapse_gen.seed, self.synapse_gen.offset = int(self.np_rng.integers(0, 2 ** 62)), 0
         fluos = [base.Fluorescence(**f) for f in self.bleach_sampler.sample_batch(self.B, self.microscope)] \
             if self.bleach_sampler.mode != "constant" else None
         if fluos is None:
@@ -210,30 +248,74 @@ class VectorContextualMOSTED:
         self.bm.set_fluorophores(fluos)
         self.current_step = 0
         self.episode_memory = {"actions": [], "mo_objs": [], "reward": []}
+        self._obs_vec = np.zeros((self.B, self.observation_space[1].shape[0]), dtype=np.float32)
         state = self._new_datamaps()
         zeros = torch.zeros_like(state)
-        self.state = torch.stack((state, zeros, zeros), dim=-1)
-        img = self._u16(self.state).cpu().numpy()
-        vec = np.zeros((self.B, self.observation_space[1].shape[0]), dtype=np.float32)
-        return (img, vec), {}
+        self.state = (state, zeros, zeros)
+        img = self._pack_observation(state).cpu().numpy()
+        return (img, self._obs_vec.copy()), {}
 
     def step(self, action):
         action = np.clip(np.asarray(action, dtype=np.float32).reshape(self.B, len(self.actions)),
                          self.action_space.low, self.action_space.high)
+        if self._obs_vec is None:
+            raise RuntimeError("step() called before reset()")
+        per_step = len(self.actions) + len(OBJ_NAMES)
+        if (self.current_step + 1) * per_step > self._obs_vec.shape[1]:
+            raise ValueError("episode longer than max_episode_steps: the observation vector is full (call reset())")
+        marks = [("start", time.perf_counter())] if self.step_timing else None
         pdt, p_ex, p_sted = self._full_action(action)
-        bm = self.bm
-        conf1, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)
-        sted, _ = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True)
-        conf2, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)
+        bm, dev, B = self.bm, self.device, self.B
+        h_act = self._pinned("act", (3, B), torch.float64)
+        h_act.numpy()[:] = (pdt, p_ex, p_sted)
+        d_act = h_act.to(dev, non_blocking=True)
+        conf = self._conf_dev()
+        # ---- everything below only queues work
+        conf1, _ = bm.get_signal_and_bleach(*conf, bleach=False, tables_key="conf")
+        sted, _ = bm.get_signal_and_bleach(d_act[0], d_act[1], d_act[2], bleach=True)
+        conf2, _ = bm.get_signal_and_bleach(*conf, bleach=False, tables_key="conf")
         bleached = bm.datamaps_roi().clone()
         pending = rewards.detect_nanodomains_launch(sted) if self.compute_f1 else None     # side stream: overlaps the rest
-        fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
-        res = rewards.resolution(sted)
-        mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)      # (B,3)
-        coords, truths = [s.nanodomains_coords for s in self.synapses], self._truths
+        fg_s, fg_c, objs_d, oflags_d = rewards.foreground_objectives_device(conf1, sted, conf2)
+        res_d = rewards.resolution_device(sted)
+        truths, coords = self._truths, self._coords_host
+        exhausted = self._exhausted()
+        state = self._next_state()
+        obs_img = self._pack_observation(state, conf1, sted)
+        # ---- one transfer into pinned memory, one wait
+        pulls = [("res", res_d), ("objs", objs_d), ("oflags", oflags_d), ("img", obs_img)]
+        if self.compute_f1:
+            f1_d, cnt_d, dfl_d, mfl_d = rewards.nanodomain_f1_launch(sted, truths, handle=pending)
+            pulls += [("f1", f1_d), ("cnt", cnt_d), ("dfl", dfl_d), ("mfl", mfl_d)]
+        if coords is None:
+            pulls += [("tc", truths.coords), ("tn", truths.counts)]
+        if self._truths is not truths:                       # the next structures' ground truth rides along
+            pulls += [("nc", self._truths.coords), ("nn", self._truths.counts)]
+        host = {}
+        for name, t in pulls:
+            host[name] = self._pinned(name, t.shape, t.dtype)
+            host[name].copy_(t, non_blocking=True)
+        if marks:
+            marks.append(("queued", time.perf_counter()))
+        torch.cuda.current_stream(dev).synchronize()
+        if marks:
+            marks.append(("device_done", time.perf_counter()))
+        host = {k: v.numpy() for k, v in host.items()}
+        if coords is None:
+            coords = [host["tc"][b, :host["tn"][b]].astype(np.int64) for b in range(B)]
+        if self._truths is not truths:
+            self._coords_host = [host["nc"][b, :host["nn"][b]].astype(np.int64) for b in range(B)]
+        else:
+            self._coords_host = coords
+        snr = np.where((host["oflags"] & 1) != 0, np.nan, host["objs"][:, 1])
+        mo_objs = np.stack([host["res"], host["objs"][:, 0], snr], axis=1)      # (B,3)
+        if self.compute_f1:
+            rewards.check_f1_flags(host["dfl"], host["mfl"])
+            f1 = host["f1"].copy()
+        else:
+            f1 = np.zeros(B)
 
-        done = np.full(self.B, self.current_step >= self.max_episode_steps - 1) | self._exhausted()
-        self.current_step += 1
+        done = np.full(B, self.current_step >= self.max_episode_steps - 1) | exhausted
         self.episode_memory["mo_objs"].append(mo_objs)
         self.episode_memory["actions"].append(action)
 
@@ -241,25 +323,23 @@ class VectorContextualMOSTED:
         if invalid.any() and self.on_invalid == "raise" and self.normalize_observations:
             # the reference's Normalizer raises TypeError on a None objective (SURVEY App. C "edge cases")
             raise TypeError("unsupported operand type(s) for -: 'NoneType' and 'int' (SNR objective is None)")
-        obs = []
-        for a, mo in zip(self.episode_memory["actions"], self.episode_memory["mo_objs"]):
-            obs.append(self.action_normalizer(a) if self.normalize_observations else a)
-            obs.append(self.obj_normalizer(mo) if self.normalize_observations else mo)
-        obs = np.concatenate(obs, axis=1)
-        obs = np.pad(obs, ((0, 0), (0, self.observation_space[1].shape[0] - obs.shape[1])))
+        # per past step [action || objectives] (contextual_sted_env.py:84-93): this step's slice of the running vector
+        at = self.current_step * per_step
+        self._obs_vec[:, at:at + len(self.actions)] = self.action_normalizer(action) if self.normalize_observations else action
+        self._obs_vec[:, at + len(self.actions):at + per_step] = self.obj_normalizer(mo_objs) if self.normalize_observations else mo_objs
+        self.current_step += 1
+        self.state = (state, conf1, sted)
+        img = host["img"].copy()
 
-        state = self._next_state()
-        self.state = torch.stack((state, conf1, sted), dim=-1)
-        img = self._u16(self.state).cpu().numpy()
-
-        # the Gaussian fits have been running under everything above; read them last
-        f1 = rewards.nanodomain_f1_batch(sted, truths, handle=pending) if self.compute_f1 else np.zeros(self.B)
         reward = f1 * self.scale_nanodomain_reward
         self.episode_memory["reward"].append(reward)
-        info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,
-                "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "f1-score": f1, "nanodomains-coords": coords,
-                "invalid": invalid}
-        return (img, obs.astype(np.float32)), reward, done, np.zeros(self.B, dtype=bool), info
+        info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2,
+                "fg_c": fg_c.view(torch.bool), "fg_s": fg_s.view(torch.bool), "mo_objs": mo_objs, "reward": reward,
+                "f1-score": f1, "nanodomains-coords": coords, "invalid": invalid}
+        if marks:                                            # host seconds: queueing, waiting for the device, unpacking
+            marks.append(("end", time.perf_counter()))
+            info["timing"] = {b[0]: b[1] - a[1] for a, b in zip(marks, marks[1:])}
+        return (img, self._obs_vec.copy()), reward, done, np.zeros(B, dtype=bool), info
 
     def _next_state(self):
         """Contextual bandit: every step ends on a fresh synapse (contextual_sted_env.py:90)."""
@@ -279,7 +359,7 @@ class VectorSequenceMOSTED(VectorContextualMOSTED):
     (``:109``)."""
 
     def _next_state(self):
-        state, _ = self.bm.get_signal_and_bleach(*self.conf, bleach=False)
+        state, _ = self.bm.get_signal_and_bleach(*self._conf_dev(), bleach=False, tables_key="conf")
         return state
 
     def _exhausted(self):
@@ -467,8 +547,8 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         self.episode_memory = {"actions": [], "mo_objs": [], "reward": []}
         state = self._new_datamaps()
         zeros = torch.zeros_like(state)
-        self.state = torch.stack((state, zeros, zeros), dim=-1)
-        img = self._u16(self.state).cpu().numpy()
+        self.state = (state, zeros, zeros)
+        img = self._pack_observation(state).cpu().numpy()
         return (img, np.zeros((self.B, self.observation_space[1].shape[0]), dtype=np.float32)), {}
 
     def _new_datamaps(self):
@@ -524,8 +604,8 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         obs = np.concatenate(obs, axis=1)
         obs = np.pad(obs, ((0, 0), (0, self.observation_space[1].shape[0] - obs.shape[1])))
         state = self._new_datamaps()
-        self.state = torch.stack((state, conf1, sted), dim=-1)
-        img = self._u16(self.state).cpu().numpy()
+        self.state = (state, conf1, sted)
+        img = self._pack_observation(state, conf1, sted).cpu().numpy()
         return (img, obs.astype(np.float32)), reward, np.full(self.B, done), np.zeros(self.B, dtype=bool), info
 
 

@@ -29,9 +29,13 @@ PIXELSIZE = 20e-9
 # ------------------------------------------------------------------------------------------------
 # a6 + a7
 # ------------------------------------------------------------------------------------------------
-def foreground_objectives(conf1: torch.Tensor, sted: torch.Tensor, conf2: torch.Tensor):
-    """(B,H,W) float32 photon counts -> fg_s, fg_c (bool), bleach, snr (float64, NaN where the reference
-    returns None), flags (int32)."""
+_HIST_SCRATCH: dict = {}
+
+
+def foreground_objectives_device(conf1: torch.Tensor, sted: torch.Tensor, conf2: torch.Tensor):
+    """``objectives_kernel`` with nothing read back: (B,H,W) float32 photon counts -> fg_s, fg_c (uint8 0/1), objs
+    (B,2) float64 = {Bleach, SNR}, flags (B,) int32 (bit 0: SNR < 0, the reference's None), all device tensors.  The
+    64 Ki-bin histogram scratch (only touched by images spanning more than 8192 values) is kept per (B, device)."""
     lib = _lib.load()
     B, H, W = conf1.shape
     dev = conf1.device
@@ -40,15 +44,22 @@ def foreground_objectives(conf1: torch.Tensor, sted: torch.Tensor, conf2: torch.
     fg_s = torch.empty_like(fg_c)
     objs = torch.empty((B, 2), dtype=torch.float64, device=dev)
     flags = torch.empty((B,), dtype=torch.int32, device=dev)
-    scratch = None
-    if float(torch.maximum(conf1.amax(), sted.amax())) >= 8192:
-        scratch = torch.empty((B, 2, 65536), dtype=torch.int32, device=dev)
+    key = (B, str(dev))
+    if key not in _HIST_SCRATCH:
+        _HIST_SCRATCH.clear()                                         # one batch shape at a time: 0.5 MB per environment
+        _HIST_SCRATCH[key] = torch.empty((B, 2, 65536), dtype=torch.int32, device=dev)
     _lib.check(lib.sted_foreground_objectives(conf1.data_ptr(), sted.data_ptr(), conf2.data_ptr(), B, H, W,
                                               fg_c.data_ptr(), fg_s.data_ptr(), objs.data_ptr(), flags.data_ptr(),
-                                              scratch.data_ptr() if scratch is not None else None,
-                                              torch.cuda.current_stream(dev).cuda_stream))
+                                              _HIST_SCRATCH[key].data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return fg_s, fg_c, objs, flags
+
+
+def foreground_objectives(conf1: torch.Tensor, sted: torch.Tensor, conf2: torch.Tensor):
+    """(B,H,W) float32 photon counts -> fg_s, fg_c (bool), bleach, snr (float64, NaN where the reference
+    returns None), flags (int32)."""
+    fg_s, fg_c, objs, flags = foreground_objectives_device(conf1, sted, conf2)
     snr = torch.where((flags & 1) != 0, torch.full_like(objs[:, 1], float("nan")), objs[:, 1])
-    return fg_s.bool(), fg_c.bool(), objs[:, 0], snr, flags
+    return fg_s.view(torch.bool), fg_c.view(torch.bool), objs[:, 0], snr, flags
 
 
 # ------------------------------------------------------------------------------------------------
@@ -272,14 +283,18 @@ class DeviceTruths:
                 T[b, :n[b]] = np.asarray(c, dtype=np.int64).reshape(-1, 2)
         self.coords, self.counts = torch.from_numpy(T).to(device), torch.from_numpy(n).to(device)
 
+    @classmethod
+    def from_device(cls, coords: torch.Tensor, counts: torch.Tensor):
+        """Wrap tensors that already live on the device (``DeviceSynapseGenerator.generate``)."""
+        self = cls.__new__(cls)
+        self.coords, self.counts = coords.contiguous(), counts.contiguous()
+        return self
 
-def nanodomain_f1_counts(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, handle=None):
-    """F1 of B images entirely on the device (north_star: "nanocluster detection plus the F1 reward run on the device"):
-    candidates, Gaussian-fit validation (already enqueued when ``handle`` is given), then ``f1_match_kernel`` — TP = size
-    of a maximum matching of the (truth, detection) pairs closer than ``threshold``, which is what the reference's
-    Hungarian solution on the priced-out cost matrix counts (``objectives.py:425-430``).  One packed device->host read.
-    ``truths``: ``DeviceTruths``, a list of (n_i, 2) arrays, or the ``pad_coords`` tuple of such a list.
-    Returns (f1 (B,) float64, counts (B, 3) int64 = TP, FP, FN)."""
+
+def nanodomain_f1_launch(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, handle=None):
+    """Queue the F1 of B images on the current stream and return DEVICE tensors ``(f1 (B,) float64, counts (B,3) int32 =
+    TP FP FN, detector flags (B,) int32, matcher flags (B,) int32)`` — nothing is read back, so a caller can fold them
+    into its own end-of-step transfer.  ``truths``: ``DeviceTruths`` (or anything ``nanodomain_f1_counts`` accepts)."""
     lib = _lib.load()
     _, sted32, peaks, npk, flags, valid, done = handle if handle is not None else detect_nanodomains_launch(sted, pixelsize)
     dev = sted32.device
@@ -291,22 +306,41 @@ def nanodomain_f1_counts(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, thresh
     B = sted32.shape[0]
     cur = torch.cuda.current_stream(dev)
     cur.wait_event(done)                                              # the detection ran on the side stream
-    out = torch.empty((B, 6), dtype=torch.float64, device=dev)        # f1 | TP FP FN | detector flags | matcher flags
     counts = torch.empty((B, 3), dtype=torch.int32, device=dev)
     mflags = torch.empty((B,), dtype=torch.int32, device=dev)
     f1 = torch.empty((B,), dtype=torch.float64, device=dev)
     _lib.check(lib.sted_f1_match(peaks.data_ptr(), npk.data_ptr(), valid.data_ptr(), peaks.shape[1], truths.coords.data_ptr(),
                                  truths.counts.data_ptr(), truths.coords.shape[1], B, float(threshold), counts.data_ptr(),
                                  f1.data_ptr(), mflags.data_ptr(), cur.cuda_stream))
+    for t in (peaks, npk, valid, truths.coords, truths.counts):       # read on `cur`, allocated on the side stream
+        t.record_stream(cur)
+    return f1, counts, flags, mflags
+
+
+def check_f1_flags(dflags: np.ndarray, mflags: np.ndarray):
+    """Raise for the capacity flags of the detector / matcher (host arrays)."""
+    _check_capacity(np.asarray(dflags).astype(np.int64))
+    if np.asarray(mflags).any():
+        raise _lib.StedError(-4, f"f1_match_kernel capacity exceeded (more than 512 truths or detections) for image "
+                                 f"{int(np.flatnonzero(mflags)[0])}")
+
+
+def nanodomain_f1_counts(sted: torch.Tensor, truths, pixelsize=PIXELSIZE, threshold=2, handle=None):
+    """F1 of B images entirely on the device (north_star: "nanocluster detection plus the F1 reward run on the device"):
+    candidates, Gaussian-fit validation (already enqueued when ``handle`` is given), then ``f1_match_kernel`` — TP = size
+    of a maximum matching of the (truth, detection) pairs closer than ``threshold``, which is what the reference's
+    Hungarian solution on the priced-out cost matrix counts (``objectives.py:425-430``).  One packed device->host read.
+    ``truths``: ``DeviceTruths``, a list of (n_i, 2) arrays, or the ``pad_coords`` tuple of such a list.
+    Returns (f1 (B,) float64, counts (B, 3) int64 = TP, FP, FN)."""
+    f1, counts, flags, mflags = nanodomain_f1_launch(sted, truths, pixelsize, threshold, handle)
+    B = f1.shape[0]
+    out = torch.empty((B, 6), dtype=torch.float64, device=f1.device)  # f1 | TP FP FN | detector flags | matcher flags
     out[:, 0] = f1
     out[:, 1:4] = counts
     out[:, 4] = flags
     out[:, 5] = mflags
     host = out.cpu().numpy()
-    _check_capacity(host[:, 4].astype(np.int64))
-    if host[:, 5].any():
-        raise _lib.StedError(-4, f"f1_match_kernel capacity exceeded (more than 512 truths or detections) for image "
-                                 f"{int(np.flatnonzero(host[:, 5])[0])}")
+    check_f1_flags(host[:, 4], host[:, 5])
     return host[:, 0].copy(), host[:, 1:4].astype(np.int64)
 
 

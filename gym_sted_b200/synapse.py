@@ -188,44 +188,47 @@ def generate_batch(B, H, W, seed=1234, env_base=0, **kw):
     return maps, coords
 
 
-def generate_batch_torch(B, H, W, device="cuda", generator=None, molecules=5, n_nanodomains=(3, 15),
-                         n_molecs_in_domain=(100, 175), min_dist_px=5, valid_thickness=(3, 10)):
-    """Batched generator on the device: same construction as ``generate`` (elliptical outline band per 64x64 cell,
-    single-pixel nanodomains inside the band, at least ``min_dist_px`` apart), vectorised over B x cells.
-    The spacing comes from keeping only local maxima of a random priority map inside a (2*min_dist-1)^2 window.
-    Returns ``(frames int32 (B,H,W) on the device, [coords (n_i,2) int64 numpy arrays])``."""
-    import torch
-    import torch.nn.functional as F
+class DeviceSynapseGenerator:
+    """Structures for B environments generated ON the device (``sted_synapse_generate``, ``csrc/env_kernels.cu``):
+    the same construction as ``generate`` (per 64 x 64 cell one elliptical outline band, single-pixel nanodomains inside
+    the band at least ``min_dist_px`` apart), one CTA per cell, Philox keyed by (seed, env_base + b, cell, structure
+    number) so the maps do not depend on the batch split.  Nothing is read back: frames, ground-truth coordinates and
+    their counts stay on the device for the acquisition and the F1 kernel.  Checked bit for bit against
+    ``oracle/synapse_oracle.py`` (``tests/test_gpu_synapse.py``)."""
 
-    dev = torch.device(device)
-    ny, nx = -(-H // CELL), -(-W // CELL)
-    C = B * ny * nx
-    g = generator
-    u = lambda lo, hi: lo + (hi - lo) * torch.rand((C, 1, 1), device=dev, generator=g)
-    yy = torch.arange(CELL, device=dev, dtype=torch.float32).view(1, CELL, 1)
-    xx = torch.arange(CELL, device=dev, dtype=torch.float32).view(1, 1, CELL)
-    cy, cx, a, b = u(CELL / 2 - 6, CELL / 2 + 6), u(CELL / 2 - 6, CELL / 2 + 6), u(12, 20), u(9, 16)
-    th, thick = u(0, float(np.pi)), u(*valid_thickness)
-    dy, dx = yy - cy, xx - cx
-    rad = torch.hypot((dx * torch.cos(th) + dy * torch.sin(th)) / a, (-dx * torch.sin(th) + dy * torch.cos(th)) / b)
-    band = (rad - 1.0).abs() * (0.5 * (a + b)) <= thick / 2
-    prio = torch.where(band, torch.rand((C, CELL, CELL), device=dev, generator=g) + 1e-6, torch.zeros((), device=dev))
-    win = 2 * int(min_dist_px) - 1
-    local_max = prio == F.max_pool2d(prio[:, None], win, stride=1, padding=win // 2)[:, 0]
-    score = torch.where(band & local_max, prio, torch.zeros((), device=dev)).view(C, -1)
-    kmax = n_nanodomains[1]
-    top, pos = torch.topk(score, kmax, dim=1)
-    n = torch.randint(n_nanodomains[0], n_nanodomains[1] + 1, (C, 1), device=dev, generator=g)
-    valid = (top > 0) & (torch.arange(kmax, device=dev)[None, :] < n)
-    counts = torch.randint(n_molecs_in_domain[0], n_molecs_in_domain[1] + 1, (C, kmax), device=dev, generator=g)
-    cells = (band.to(torch.int32) * molecules).view(C, -1)
-    cells.scatter_(1, pos, torch.where(valid, counts.to(torch.int32), cells.gather(1, pos)))
-    cells = cells.view(B, ny, nx, CELL, CELL).permute(0, 1, 3, 2, 4).reshape(B, ny * CELL, nx * CELL)
-    frames = cells[:, :H, :W].contiguous()
-    # coordinates on the host (ground truth of the F1 reward)
-    cyx = torch.stack((pos // CELL, pos % CELL), dim=-1).view(B, ny, nx, kmax, 2)
-    off = torch.stack(torch.meshgrid(torch.arange(ny, device=dev) * CELL, torch.arange(nx, device=dev) * CELL, indexing="ij"), dim=-1)
-    cyx = (cyx + off[None, :, :, None, :]).reshape(B, -1, 2)
-    ok = valid.view(B, -1) & (cyx[..., 0] < H) & (cyx[..., 1] < W)
-    cyx_h, ok_h = cyx.cpu().numpy().astype(np.int64), ok.cpu().numpy()
-    return frames, [cyx_h[i][ok_h[i]] for i in range(B)]
+    def __init__(self, B, H, W, device="cuda", seed=0, env_base=0, molecules=5, n_nanodomains=(3, 15),
+                 n_molecs_in_domain=(100, 175), min_dist_px=5.0, valid_thickness=(3, 10)):
+        import torch
+        from . import _lib
+        self.lib = _lib.load()
+        if _lib.device_count() == 0:
+            raise _lib.StedError(-2, "no CUDA device: gym_sted_b200 has no CPU fallback")
+        self._check = _lib.check
+        self.B, self.H, self.W = int(B), int(H), int(W)
+        self.device = torch.device(device)
+        self.seed, self.env_base, self.offset = int(seed), int(env_base), 0
+        self.cells = -(-self.H // CELL) * -(-self.W // CELL)
+        self.max_truth = self.cells * int(n_nanodomains[1])
+        self.max_molecules = self.B * self.cells * (int(molecules) * CELL * CELL + int(n_nanodomains[1]) * int(n_molecs_in_domain[1]))
+        self.params = _lib.StedSynapseParams(int(molecules), int(n_nanodomains[0]), int(n_nanodomains[1]),
+                                             int(n_molecs_in_domain[0]), int(n_molecs_in_domain[1]), 0,
+                                             float(min_dist_px), float(valid_thickness[0]), float(valid_thickness[1]))
+        self.scratch = torch.empty((int(self.lib.sted_synapse_scratch_bytes(self.B, self.H, self.W)),), dtype=torch.uint8,
+                                   device=self.device)
+
+    def generate(self, offset=None):
+        """-> (frames int32 (B,H,W), coords int32 (B,max_truth,2), counts int32 (B,)), all on the device; queued on the
+        current stream.  ``offset``: structure number (defaults to a counter that advances with every call)."""
+        import ctypes
+        import torch
+        if offset is None:
+            offset = self.offset
+            self.offset += 1
+        frames = torch.empty((self.B, self.H, self.W), dtype=torch.int32, device=self.device)
+        coords = torch.empty((self.B, self.max_truth, 2), dtype=torch.int32, device=self.device)
+        counts = torch.empty((self.B,), dtype=torch.int32, device=self.device)
+        self._check(self.lib.sted_synapse_generate(
+            ctypes.byref(self.params), self.B, self.H, self.W, self.seed, int(offset), self.env_base, frames.data_ptr(),
+            coords.data_ptr(), counts.data_ptr(), self.max_truth, self.scratch.data_ptr(),
+            torch.cuda.current_stream(self.device).cuda_stream))
+        return frames, coords, counts

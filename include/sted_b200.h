@@ -373,9 +373,36 @@ int sted_apodize_for_fft(const float* image_dev, const double* window_dev, int B
 int sted_spectrum_gather(const void* spectrum_dev, const int64_t* order_dev, int B, int Hc, int Wc, int n_inside,
                          void* ik_dev, void* ikn_dev, void* stream);
 
+/* ---- env.step plumbing between the acquisitions (gym_sted/envs/contextual_sted_env.py:49-93, mosted_env.py:168-187) ----
+ * sted_synapse_generate: the structures a ContextualMOSTED step ends on (`self.synapse_generator(rotate=True)`,
+ * mosted_env.py:80-83,174; gym_sted/utils.py:26-78), for B environments on the device.  pysted.exp_data_gen.Synapse is
+ * not vendored in the reference; the geometry is the synthetic spine datamap of SURVEY.md 8d: per 64 x 64 cell one
+ * elliptical outline band thick_lo..thick_hi px thick holding `molecules` per pixel and n_lo..n_hi single-pixel
+ * nanodomains of m_lo..m_hi molecules inside the band, at least min_dist_px apart (dart throwing in the order of a
+ * random priority).  Every draw is a Philox4x32-10 word keyed by (seed, env_base + b, cell, offset) and the geometry is
+ * float64 +, -, *, /, sqrt only, so oracle/synapse_oracle.py reproduces the outputs bit for bit.
+ *   frames_dev : int32 [B][H][W] molecule maps;  coords_dev : int32 [B][max_truth][2] (row, col) of the nanodomains in
+ *   cell order, zero filled;  counts_dev : int32 [B];  scratch_dev : sted_synapse_scratch_bytes(B, H, W) bytes. */
+typedef struct StedSynapseParams {
+    int32_t molecules, n_lo, n_hi, m_lo, m_hi, _pad;
+    double min_dist_px, thick_lo, thick_hi;
+} StedSynapseParams;
+uint64_t sted_synapse_scratch_bytes(int B, int H, int W);
+int sted_synapse_generate(const StedSynapseParams* prm, int B, int H, int W, uint64_t seed, uint64_t offset, int64_t env_base,
+                          int32_t* frames_dev, int32_t* coords_dev, int32_t* counts_dev, int max_truth, void* scratch_dev,
+                          void* stream);
+/* Datamap.set_roi(i_ex, "max") (gym_sted/utils.py:179-180) for device-resident maps: roi_dev int32 or float32 [B][H][W]
+ * -> padded_dev float32 [B][H+K-1][roundup4(W+K-1)] with the zero frame of K/2 pixels. */
+int sted_pad_maps(const void* roi_dev, int roi_is_int32, int B, int H, int W, int K, float* padded_dev, void* stream);
+/* Image half of the observation (gym_sted/envs/contextual_sted_env.py:84-93): (state, conf1, sted) float32 [B][H][W]
+ * photon counts -> uint16 [B][H][W][3], cast like numpy's int64 -> uint16 (wrap modulo 2^16). */
+int sted_pack_observation(const float* state_dev, const float* conf1_dev, const float* sted_dev, int B, int H, int W,
+                          uint16_t* obs_dev, void* stream);
+
 /* Test hook for the Levenberg-Marquardt solver: n windows of 49 float64 values, params_dev float64 [n][5] holds the
  * starting points on entry and the solutions on return, info_dev int32 [n] MINPACK's info code.
- * model 0: the Gaussian of sted_gaussfit_validate; model 1: a rational peak (no transcendental, bit-reproducible). */
+ * model 0: the Gaussian of sted_gaussfit_validate; model 1: a rational peak (no transcendental, bit-reproducible), both
+ * with the one-thread solver; models 2 / 3: the same two through the warp-cooperative solver sted_gaussfit_validate runs. */
 int sted_lmfit_test(const double* data_dev, int n, int model, double ftol, double* params_dev, int32_t* info_dev,
                     void* stream);
 

@@ -1,0 +1,27 @@
+"""Kernels launched by ONE VectorContextualMOSTED.step (torch.profiler / CUPTI): name, launches, device time."""
+import os
+import sys
+import numpy as np
+import torch
+from torch.profiler import profile, ProfilerActivity
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gym_sted_b200 import envs  # noqa: E402
+
+B = int(os.environ.get("PROBE_B", 256)); SIZE = int(os.environ.get("PROBE_HW", 64))
+vec = envs.make_vec("ContextualMOSTED-easy-hslb-v0", B, compute_f1=True, seed=0, image_size=SIZE)
+vec.reset(seed=0)
+acts = np.random.default_rng(0).uniform(vec.action_space.low, vec.action_space.high, (B, 3)).astype(np.float32)
+for _ in range(3):
+    vec.step(acts)
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    vec.step(acts)
+    torch.cuda.synchronize()
+rows = {}
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        n, t = rows.get(ev.name, (0, 0.0))
+        rows[ev.name] = (n + 1, t + ev.device_time)
+print(f"{'kernel':110s} launches   us")
+for name, (n, t) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+    print(f"{name[:110]:110s} {n:5d} {t:8.1f}")

@@ -15,9 +15,11 @@ def wrap(obj, name, label=None):
 wrap(BatchedMicroscope, "get_signal_and_bleach")
 wrap(BatchedMicroscope, "set_datamaps")
 wrap(rewards, "foreground_objectives")
-wrap(rewards, "resolution")
+wrap(rewards, "resolution_device")
+wrap(rewards, "foreground_objectives_device")
+wrap(rewards, "nanodomain_f1_launch")
 wrap(rewards, "nanodomain_f1_batch")
-wrap(synapse, "generate_batch_torch")
+wrap(synapse.DeviceSynapseGenerator, "generate")
 wrap(rewards, "_candidates_device")
 wrap(rewards, "gaussfit_validate")
 wrap(rewards, "match_counts")

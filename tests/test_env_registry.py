@@ -62,15 +62,15 @@ def test_invalid_objective_masks_one_env_instead_of_aborting_the_batch():
     from gym_sted_b200 import envs, rewards
     env = envs.make_vec("ContextualMOSTED-easy-v0", 4, seed=0, compute_f1=False)
     env.reset(seed=0)
-    real = rewards.foreground_objectives
+    real = rewards.foreground_objectives_device
 
-    def with_a_none(conf1, sted, conf2):
-        fg_s, fg_c, bleach, snr, flags = real(conf1, sted, conf2)
-        snr = snr.clone()
-        snr[2] = float("nan")
-        return fg_s, fg_c, bleach, snr, flags
+    def with_a_none(conf1, sted, conf2):                 # flag bit 0: SNR < 0, the reference's None
+        fg_s, fg_c, objs, flags = real(conf1, sted, conf2)
+        flags = flags.clone()
+        flags[2] |= 1
+        return fg_s, fg_c, objs, flags
 
-    rewards.foreground_objectives = with_a_none
+    rewards.foreground_objectives_device = with_a_none
     try:
         obs, reward, done, trunc, info = env.step(np.tile([0.1, 10e-6, 10e-6], (4, 1)).astype(np.float32))
         assert info["invalid"].tolist() == [False, False, True, False]
@@ -79,11 +79,11 @@ def test_invalid_objective_masks_one_env_instead_of_aborting_the_batch():
         single.reset(seed=0)
 
         def always_none(conf1, sted, conf2):
-            fg_s, fg_c, bleach, snr, flags = real(conf1, sted, conf2)
-            return fg_s, fg_c, bleach, torch.full_like(snr, float("nan")), flags
+            fg_s, fg_c, objs, flags = real(conf1, sted, conf2)
+            return fg_s, fg_c, objs, flags | 1
 
-        rewards.foreground_objectives = always_none
+        rewards.foreground_objectives_device = always_none
         with pytest.raises(TypeError):
             single.step(np.array([0.1, 10e-6, 10e-6], dtype=np.float32))
     finally:
-        rewards.foreground_objectives = real
+        rewards.foreground_objectives_device = real

@@ -429,6 +429,33 @@ def test_warp_parallel_fit_equals_single_thread_fit():
         assert np.array_equal(x[i], params_h[b, k]), (b, k, x[i], params_h[b, k])
 
 
+def test_cooperative_solver_equals_one_thread_solver_bit_for_bit():
+    """``lm_fit_warp`` (lm_minpack_warp.cuh: rows owned by lanes, reductions in MINPACK's order) against ``lm_fit`` on the
+    device: same solutions and info codes, bit for bit, for both models, at the reference's ftol and at a tight one,
+    including the all-zero and the flat window (singular Jacobians, the general ENORM path) and windows with huge and
+    tiny counts."""
+    _gpu()
+    from gym_sted_b200 import _lib
+    from tests import test_lm_minpack as tl
+    ws = tl.windows(400, 5)
+    rng = np.random.default_rng(6)
+    ws += [w * s for w, s in zip(tl.windows(20, 7), rng.choice([1e-25, 1e-12, 1e9, 1e21], 22))]
+    one = np.zeros((7, 7)); one[3, 3] = 50.0
+    ws += [one, np.roll(one, 2, axis=0), rng.poisson(0.3, (7, 7)).astype(np.float64)]
+    data = torch.from_numpy(np.stack([w.ravel() for w in ws])).cuda()
+    for ftol in (1e-3, 1e-10):
+        for serial, coop in ((0, 2), (1, 3)):
+            out = []
+            for model in (serial, coop):
+                params = torch.from_numpy(np.stack([[w.max(), 0, 0, 1, 1.0] for w in ws])).cuda()
+                info = torch.full((len(ws),), -7, dtype=torch.int32, device="cuda")
+                _lib.check(_lib.load().sted_lmfit_test(data.data_ptr(), len(ws), model, ftol, params.data_ptr(), info.data_ptr(), None))
+                out.append((params.cpu().numpy(), info.cpu().numpy()))
+            assert np.array_equal(out[0][1], out[1][1]), np.flatnonzero(out[0][1] != out[1][1])
+            same = (out[0][0] == out[1][0]) | (np.isnan(out[0][0]) & np.isnan(out[1][0]))
+            assert same.all(), np.flatnonzero(~same.all(axis=1))
+
+
 def test_device_f1_matching_equals_hungarian():
     """``sted_f1_match`` (maximum matching under the distance threshold, on the device) against the Hungarian matching
     on the priced-out cost matrix (``metrics.CentroidDetectionError(..., "hungarian")`` as restated by
