@@ -463,6 +463,27 @@ def run_ours(args, rank, local_rank, world):
     h2d = img_bytes + 4 * (3 * B * 8)
     d2h = 4 * img_bytes + img_bytes
 
+    # ---- the host's transfer ceiling with every rank copying at once (no kernels): the step's five device->host buffers,
+    # 4 rounds, then the map upload.  The e2e leg cannot be faster than d2h_bytes_per_step / this rate.
+    d_buf = torch.empty((B, H, W), dtype=torch.uint16, device=dev)
+    t_pins = [h._owner for h in h_out + [h_bleached]]        # the pinned torch tensors behind pinned_empty's arrays
+    cs = torch.cuda.Stream(dev)
+
+    def copy_rate(down):
+        def burst(n):
+            with torch.cuda.stream(cs):
+                for _ in range(n):
+                    for tp in t_pins:
+                        tp.copy_(d_buf, non_blocking=True) if down else d_buf.copy_(tp, non_blocking=True)
+            cs.synchronize()
+        burst(1)
+        sync_all()
+        c0 = time.perf_counter()
+        burst(4)
+        return 4 * len(t_pins) * img_bytes / (time.perf_counter() - c0) * 1e-9
+
+    d2h_gbs, h2d_gbs = copy_rate(True), copy_rate(False)
+
     # ---- the one collective of the design: per-step rewards gathered on rank 0 over NCCL (outside the timed region)
     gathered = None
     if world > 1:
@@ -472,10 +493,12 @@ def run_ours(args, rank, local_rank, world):
         gathered = int(allr.numel())
 
     # ---- max over ranks
-    t = torch.tensor([ms, e2e_s, gather_ms, sweep_ms, scan_alone_ms, gather_alone_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s, gather_ms, sweep_ms, scan_alone_ms, gather_alone_ms, -d2h_gbs, -h2d_gbs], dtype=torch.float64,
+                     device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_s, gather_ms, sweep_ms, scan_alone_ms, gather_alone_ms = [float(x) for x in t.tolist()]
+    ms, e2e_s, gather_ms, sweep_ms, scan_alone_ms, gather_alone_ms, d2h_gbs, h2d_gbs = [float(x) for x in t.tolist()]
+    d2h_gbs, h2d_gbs = -d2h_gbs, -h2d_gbs                   # slowest rank
 
     if rank == 0:
         acq = ACQ_PER_STEP * B * world * args.steps
@@ -543,7 +566,12 @@ def run_ours(args, rank, local_rank, world):
                     "api": "sted_session_* (C ABI, pinned host buffers, uint16 maps and counts): per step the next structure is "
                            "uploaded once and imaged by a " + ("second" if args.sequential else "low-priority") + " session, the main "
                            "session adopts it on the device, images it 3x and returns the bleached map; host sync every step",
-                    "numa_bound": numa_bound, "rewards_gathered_over_nccl": gathered},
+                    "numa_bound": numa_bound, "rewards_gathered_over_nccl": gathered,
+                    "host_ceiling": {"d2h_gbs_per_rank": d2h_gbs, "h2d_gbs_per_rank": h2d_gbs, "ranks_copying": world,
+                                     "d2h_bound_value": ACQ_PER_STEP * B * world / (d2h / (d2h_gbs * 1e9)),
+                                     "note": "pinned-memory copy rate of the slowest rank with all ranks copying at once and no "
+                                             "kernels running (measured right after the e2e leg); d2h_bound_value = acquisitions/s "
+                                             "if a step cost only its device->host bytes at that rate"}},
             "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "roofline_scan": roofline_scan,
             "cpu_baseline": cpu,
         }
