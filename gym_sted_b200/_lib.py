@@ -79,6 +79,7 @@ SIGNATURES = {
     "sted_session_kernel_ms": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float)]),
     "sted_session_join": (_i, [_vp, _vp]),
     "sted_session_adopt": (_i, [_vp, _vp]),
+    "sted_session_after": (_i, [_vp, _vp]),
     "sted_session_download": (_i, [_vp, _vp, _u32]),
     "sted_session_sync": (_i, [_vp, ctypes.POINTER(_i64)]),
     "sted_session_device_map": (_i, [_vp, ctypes.POINTER(_vp)]),

@@ -2673,16 +2673,22 @@ int sted_session_create(int B, int H, int W, int K, const double* psf_cache_host
     s->n_roi = (size_t)B * H * W; s->n_pad = (size_t)B * s->Hp * s->Wpitch;
     int lo = 0, hi = 0;
     S_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    const int prio = low_priority ? lo : hi;
-    S_TRY(cudaStreamCreateWithPriority(&s->s_in, cudaStreamNonBlocking, prio));
+    // Priorities (numerically lower = higher).  The gather / scan stream sits one step BELOW the streams of the light ends
+    // of an acquisition - upload + padding, tables + death schedule, detector, downloads: the block scheduler hands free
+    // slots to the oldest grid of the highest priority, so at equal priority the tables and the death schedule of the next
+    // acquisition only started in the tail wave of the running gather instead of under it.  A low-priority session puts
+    // its gather / scan at the bottom of the range; its light ends stay on top, or its detector would wait for the end of
+    // another session's saturating kernel and its download for the end of the step.
+    const int prio = low_priority ? lo : (hi + 1 <= lo ? hi + 1 : hi);
+    S_TRY(cudaStreamCreateWithPriority(&s->s_in, cudaStreamNonBlocking, hi));
     S_TRY(cudaStreamCreateWithPriority(&s->s_comp, cudaStreamNonBlocking, prio));
-    S_TRY(cudaStreamCreateWithPriority(&s->s_out, cudaStreamNonBlocking, prio));
+    S_TRY(cudaStreamCreateWithPriority(&s->s_out, cudaStreamNonBlocking, hi));
     s->serial = getenv("STED_B200_SESSION_SERIAL") != nullptr;
     if (s->serial) {
         s->s_prep = s->s_post = s->s_comp;
     } else {
-        S_TRY(cudaStreamCreateWithPriority(&s->s_prep, cudaStreamNonBlocking, prio));
-        S_TRY(cudaStreamCreateWithPriority(&s->s_post, cudaStreamNonBlocking, prio));
+        S_TRY(cudaStreamCreateWithPriority(&s->s_prep, cudaStreamNonBlocking, hi));
+        S_TRY(cudaStreamCreateWithPriority(&s->s_post, cudaStreamNonBlocking, hi));
     }
     for (int i = 0; i < StedSession::NT; ++i) { S_TRY(cudaEventCreate(&s->e_t0[i])); S_TRY(cudaEventCreate(&s->e_t1[i])); }
     for (cudaEvent_t& e : s->e_join) S_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2832,6 +2838,16 @@ int sted_session_adopt(StedSession* dst, StedSession* src) {
     return STED_OK;
 }
 
+int sted_session_after(StedSession* s, StedSession* other) {
+    int rc = session_bind(s);
+    if (rc) return rc;
+    if ((rc = session_bind(other))) return rc;
+    if (s == other) return fail(STED_EINVAL, "a session cannot wait for itself");
+    CUDA_TRY(cudaEventRecord(other->e_comp, other->s_comp));
+    CUDA_TRY(cudaStreamWaitEvent(s->s_comp, other->e_comp, 0));
+    return STED_OK;
+}
+
 int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* p_sted_host, const double* pdt_host,
                          uint32_t flags, const StedDetectorParams* det, double lambda_fluo, uint64_t seed, uint64_t offset,
                          int64_t env_base, void* signal_host, float* intensity_host) {
@@ -2892,42 +2908,58 @@ int sted_session_acquire(StedSession* s, const double* p_ex_host, const double* 
     CUDA_TRY(cudaStreamWaitEvent(s->s_comp, s->e_prep[i], 0));
     const int it = (int)(s->n_acq++ % StedSession::NT);
     CUDA_TRY(cudaEventRecord(s->e_t0[it], s->s_comp));
-    if ((rc = sted_acquire(d_in, bleach ? d_out : nullptr, d_tab, d_pdt, B, s->H, s->W, s->K,
-                           flags | STED_NO_DETECT | (stoch ? STED_PRESAMPLED : 0u), det, lambda_fluo, seed, offset, env_base,
-                           intensity_host ? s->d_int[i] : nullptr, s->d_sig[i], stoch ? s->d_ws : nullptr,
-                           stoch ? s->ws_bytes : 0, s->s_comp)))
-        return rc;
-    CUDA_TRY(cudaEventRecord(s->e_t1[it], s->s_comp));
-    s->h_drop[i] = 0;
-    if (stoch) {
-        CUDA_TRY(cudaMemcpyAsync(&s->h_drop[i], s->d_ws, sizeof(int), cudaMemcpyDeviceToHost, s->s_comp));
-        CUDA_TRY(cudaEventRecord(s->e_wsfree, s->s_comp));
-    }
-    if (bleach) {
-        s->cur ^= 1;
-        CUDA_TRY(cudaEventRecord(s->e_map, s->s_comp));
-    }
-    CUDA_TRY(cudaEventRecord(s->e_main[i], s->s_comp));
-    // ---- s_post: detector (+ uint16 conversion), under whatever s_comp runs next
-    CUDA_TRY(cudaStreamWaitEvent(s->s_post, s->e_main[i], 0));
-    if ((rc = sted_detect(s->d_sig[i], d_pdt, B, s->H, s->W, flags, det, lambda_fluo, seed, offset, env_base, s->s_post))) return rc;
-    if (!bleach) CUDA_TRY(cudaEventRecord(s->e_keep_used, s->s_post));
-    if (signal_host || intensity_host) {
-        if (u16 && signal_host) {
-            counts_to_u16_kernel<<<296, 256, 0, s->s_post>>>(s->d_sig[i], s->d_sig16[i], s->n_roi);
-            CUDA_TRY(cudaGetLastError());
+    // A confocal acquisition with a host destination runs as two gathers over halves of the batch: the detector and the
+    // download of the first half then run under the gather of the second, and when the last kernel of a step has
+    // finished only the tail of half an image is left to copy (a caller that synchronises every step waits for exactly
+    // that).  Two launches of >= 2048 CTAs cost about 1 % in partial waves; the scan is not cut (3 CTAs per SM: half a
+    // batch would leave its last wave half empty).  Results do not depend on the cut: Philox counters carry the global
+    // environment id.
+    const size_t hw = (size_t)s->H * s->W;
+    const int nhalf = (!bleach && signal_host && B >= 64) ? 2 : 1;
+    const int nrun = (signal_host && B >= 8) ? 4 / nhalf : 1;         // detector / conversion / copy runs per half
+    for (int h = 0; h < nhalf; ++h) {
+        const int hb0 = (int)((long long)B * h / nhalf), hnb = (int)((long long)B * (h + 1) / nhalf) - hb0;
+        if ((rc = sted_acquire(d_in + (size_t)hb0 * s->Hp * s->Wpitch, bleach ? d_out : nullptr,
+                               d_tab + (size_t)hb0 * STED_TABLES * s->K * s->KP, d_pdt + hb0, hnb, s->H, s->W, s->K,
+                               flags | STED_NO_DETECT | (stoch ? STED_PRESAMPLED : 0u), det, lambda_fluo, seed, offset, env_base + hb0,
+                               intensity_host ? s->d_int[i] + hb0 * hw : nullptr, s->d_sig[i] + hb0 * hw, stoch ? s->d_ws : nullptr,
+                               stoch ? s->ws_bytes : 0, s->s_comp)))
+            return rc;
+        if (h == nhalf - 1) {
+            CUDA_TRY(cudaEventRecord(s->e_t1[it], s->s_comp));
+            s->h_drop[i] = 0;
+            if (stoch) {
+                CUDA_TRY(cudaMemcpyAsync(&s->h_drop[i], s->d_ws, sizeof(int), cudaMemcpyDeviceToHost, s->s_comp));
+                CUDA_TRY(cudaEventRecord(s->e_wsfree, s->s_comp));
+            }
+            if (bleach) {
+                s->cur ^= 1;
+                CUDA_TRY(cudaEventRecord(s->e_map, s->s_comp));
+            }
         }
-        CUDA_TRY(cudaEventRecord(s->e_det[i], s->s_post));
-        CUDA_TRY(cudaStreamWaitEvent(s->s_out, s->e_det[i], 0));
-        if (signal_host) {
-            if (u16) CUDA_TRY(cudaMemcpyAsync(signal_host, s->d_sig16[i], s->n_roi * 2, cudaMemcpyDeviceToHost, s->s_out));
-            else CUDA_TRY(cudaMemcpyAsync(signal_host, s->d_sig[i], s->n_roi * 4, cudaMemcpyDeviceToHost, s->s_out));
+        CUDA_TRY(cudaEventRecord(s->e_main[i], s->s_comp));
+        // ---- s_post: detector (+ uint16 conversion) in runs of environments, under whatever s_comp runs next; the copy of
+        // one run overlaps the detector of the next
+        CUDA_TRY(cudaStreamWaitEvent(s->s_post, s->e_main[i], 0));
+        for (int c = 0; c < nrun; ++c) {
+            const int b0 = hb0 + (int)((long long)hnb * c / nrun), nb = hb0 + (int)((long long)hnb * (c + 1) / nrun) - b0;
+            if ((rc = sted_detect(s->d_sig[i] + b0 * hw, d_pdt + b0, nb, s->H, s->W, flags, det, lambda_fluo, seed, offset, env_base + b0,
+                                  s->s_post)))
+                return rc;
+            if (h == nhalf - 1 && c == nrun - 1 && !bleach) CUDA_TRY(cudaEventRecord(s->e_keep_used, s->s_post));
+            if (u16 && signal_host) {
+                counts_to_u16_kernel<<<296, 256, 0, s->s_post>>>(s->d_sig[i] + b0 * hw, s->d_sig16[i] + b0 * hw, nb * hw);
+                CUDA_TRY(cudaGetLastError());
+            }
+            CUDA_TRY(cudaEventRecord(s->e_det[i], s->s_post));
+            CUDA_TRY(cudaStreamWaitEvent(s->s_out, s->e_det[i], 0));      // e_out[i] below then covers the slot's kernels too
+            if (signal_host) {
+                if (u16) CUDA_TRY(cudaMemcpyAsync((uint16_t*)signal_host + b0 * hw, s->d_sig16[i] + b0 * hw, nb * hw * 2, cudaMemcpyDeviceToHost, s->s_out));
+                else CUDA_TRY(cudaMemcpyAsync((float*)signal_host + b0 * hw, s->d_sig[i] + b0 * hw, nb * hw * 4, cudaMemcpyDeviceToHost, s->s_out));
+            }
         }
-        if (intensity_host) CUDA_TRY(cudaMemcpyAsync(intensity_host, s->d_int[i], s->n_roi * 4, cudaMemcpyDeviceToHost, s->s_out));
-    } else {
-        CUDA_TRY(cudaEventRecord(s->e_det[i], s->s_post));
-        CUDA_TRY(cudaStreamWaitEvent(s->s_out, s->e_det[i], 0));      // e_out[i] below then covers the slot's kernels too
     }
+    if (intensity_host) CUDA_TRY(cudaMemcpyAsync(intensity_host, s->d_int[i], s->n_roi * 4, cudaMemcpyDeviceToHost, s->s_out));
     CUDA_TRY(cudaEventRecord(s->e_out[i], s->s_out));
     // the next kernels on s_comp must not overwrite slot i ... they use slot i+1; slot i is guarded by e_out[i] above
     return STED_OK;

@@ -144,6 +144,10 @@ class StedSession:
         as the NEXT structure becomes this session's current one."""
         _lib.check(self.lib.sted_session_adopt(self._h, other._h))
 
+    def after(self, other: "StedSession"):
+        """The gather / scan kernels queued on this session from now on start after those queued on ``other`` so far."""
+        _lib.check(self.lib.sted_session_after(self._h, other._h))
+
     def download(self, out: np.ndarray):
         """Queue the download of the current (bleached) maps into ``out`` ((B,H,W) uint16 or float32)."""
         assert out.shape == (self.B, self.H, self.W) and out.flags.c_contiguous

@@ -261,6 +261,11 @@ int sted_session_join(StedSession* s, void* stream);
  * structure the next step images three times: a low-priority session uploads and images it while the main session
  * works, then the main session adopts it — one upload per structure.  Same B, H, W, K required. */
 int sted_session_adopt(StedSession* dst, StedSession* src);
+/* Ordering between sessions: the gather / scan kernels queued on s from now on start only after those queued on `other`
+ * so far have finished (other's detector passes and downloads may still be running).  A low-priority session's work is
+ * otherwise free to drift to the very end of a step, where a caller that synchronises every step waits for it with an
+ * idle GPU; ordering the step's last acquisition after it lets its detector and download run under that acquisition. */
+int sted_session_after(StedSession* s, StedSession* other);
 /* Current (bleached) maps -> host, same format rules as sted_session_upload. */
 int sted_session_download(StedSession* s, void* dmap_host, uint32_t flags);
 /* Waits for everything queued on the session; *dropped_events (may be NULL) = deaths that did not fit the scratch. */
