@@ -2,9 +2,9 @@
 
 * ``foreground_objectives``  Otsu foregrounds + Bleach + SNR: one CUDA kernel (``rewards_kernels.cu``),
   bit-identical to ``gym_sted/utils.py:16-24``, ``mosted_env.py:237-244``, ``objectives.py:91-111``.
-* ``resolution``             image-decorrelation resolution (``objectives.py:121-291``): apodisation,
-  FFT, high-pass sweeps and ring sums run batched on the GPU in float64 (torch tensors; the ring sums are
-  prefix sums in radius-sorted pixel order); only the 50-point peak searches run on the host.
+* ``resolution``             image-decorrelation resolution (``objectives.py:121-291``): ``apodize_kernel`` ->
+  cuFFT (complex128) -> ``spectrum_gather_kernel`` -> ``decorr_kernel`` (all 22 decorrelation passes and their peak
+  searches, one CTA per image, float64); nothing runs on the host.
 * ``nanodomain_f1``          detection + F1 (``objectives.py:404-430``, ``rewards/utils.py:6-49``): candidates
   (``nanodomain_kernel``), Gaussian-fit validation (``gaussfit_kernel``, MINPACK restated) and the matching +
   F1 (``f1_match_kernel``: maximum matching of the pairs closer than the threshold, which is what the

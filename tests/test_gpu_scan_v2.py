@@ -205,6 +205,64 @@ def test_session_device_resident_io():
     d.close()
 
 
+def test_session_half_batch_gathers_and_ordering_do_not_change_results():
+    """Batches of >= 64 environments: a confocal acquisition with a host destination runs as two half-batch gathers with
+    the detector / conversion / copy in runs of environments (odd sizes included), a low-priority session is ordered in
+    front with ``after`` and adopted.  Photon counts and maps must equal the single-launch device API bit for bit."""
+    from gym_sted_b200.batch import BatchedMicroscope
+    m = helpers.product_microscope(defaults.load_routine("high-signal_low-bleach"), noise=True,
+                                   background=defaults.DETECTOR["background"])
+    B, H, W = 71, 24, 40
+    maps, _ = synapse.generate_batch(B, 64, 64, seed=9)
+    maps = np.ascontiguousarray(maps[:, 10:10 + H, 8:8 + W]).astype(np.uint16)
+    nxt_maps = np.ascontiguousarray(maps[::-1])
+    rng = np.random.default_rng(5)
+    pdt, p_ex, p_sted = rng.uniform(10e-6, 40e-6, B), rng.uniform(3e-6, 15e-6, B), rng.uniform(0.05, 0.25, B)
+    mol = int(maps.astype(np.int64).sum())
+
+    main = sess.StedSession(m, B, H, W, env_base=3, seed=21)
+    low = sess.StedSession(m, B, H, W, env_base=3, seed=22, low_priority=True)
+    out = [sess.pinned_empty((B, H, W), np.uint16) for _ in range(5)]
+    inten = np.empty((B, H, W), dtype=np.float32)
+    main.upload(maps, max_molecules=mol)
+    low.upload(nxt_maps, max_molecules=mol)
+    low.acquire(10e-6, 10e-6, 0.0, bleach=False, out=out[3])
+    main.acquire(10e-6, 10e-6, 0.0, bleach=False, out=out[0], intensity_out=inten)
+    main.acquire(pdt, p_ex, p_sted, bleach=True, out=out[1])
+    bleached = main.download(sess.pinned_empty((B, H, W), np.uint16))
+    main.after(low)
+    main.acquire(10e-6, 10e-6, 0.0, bleach=False, out=out[2])
+    main.adopt(low)
+    main.acquire(10e-6, 10e-6, 0.0, bleach=False, out=out[4])
+    assert main.sync() == 0 and low.sync() == 0
+    with pytest.raises(_lib_error()):
+        main.after(main)
+    main.close(); low.close()
+
+    bm = BatchedMicroscope(m, B, H, W, device="cuda:0", seed=21, env_base=3)
+    bm.set_datamaps(torch.from_numpy(maps.astype(np.float32)))
+    c1, i1 = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False, want_intensity=True)
+    st, _ = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True)
+    c2, _ = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)
+    assert np.array_equal(out[0], c1.cpu().numpy().astype(np.uint16))
+    assert np.array_equal(inten, i1.cpu().numpy())
+    assert np.array_equal(out[1], st.cpu().numpy().astype(np.uint16))
+    assert np.array_equal(out[2], c2.cpu().numpy().astype(np.uint16))
+    assert np.array_equal(bleached, bm.datamaps_roi().cpu().numpy().astype(np.uint16))
+    bm.set_datamaps(torch.from_numpy(nxt_maps.astype(np.float32)))
+    c4, _ = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)       # 4th acquisition of the main session: offset 4
+    assert np.array_equal(out[4], c4.cpu().numpy().astype(np.uint16))
+    bl = BatchedMicroscope(m, B, H, W, device="cuda:0", seed=22, env_base=3)
+    bl.set_datamaps(torch.from_numpy(nxt_maps.astype(np.float32)))
+    c3, _ = bl.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)
+    assert np.array_equal(out[3], c3.cpu().numpy().astype(np.uint16))
+
+
+def _lib_error():
+    from gym_sted_b200 import _lib
+    return _lib.StedError
+
+
 def test_presample_then_acquire_equals_one_call():
     """sted_bleach_presample + sted_acquire(STED_PRESAMPLED) on two streams == sted_acquire alone."""
     import ctypes
