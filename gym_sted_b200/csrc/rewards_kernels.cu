@@ -507,21 +507,29 @@ __device__ void dc_linspace(double a, double b, int n, double* out) {           
     out[n - 1] = b;
 }
 
-// objectives.py:217-227: shorten the curve from the right until its maximum stands tol above the minimum to its right
-__device__ void dc_peak(const double* d, int n, double tol, int* idx_out, double* A_out) {
-    auto argmax = [&](int len) { int k = 0; for (int i = 1; i < len; ++i) if (d[i] > d[k]) k = i; return k; };
-    int len = n, idx = argmax(len);
-    double A = d[idx];
-    while (len > 1) {
-        double mn = d[idx];
-        for (int i = idx + 1; i < len; ++i) mn = fmin(mn, d[i]);
-        if ((A - mn) >= tol || idx == 0) break;
-        --len;
-        idx = argmax(len);
-        A = d[idx];
-    }
-    *idx_out = idx;
-    *A_out = A;
+// objectives.py:217-227: shorten the curve from the right until its maximum stands tol above the minimum to its right:
+//     len = n; idx = argmax(d[:len]); while len > 1 and not (d[idx] - min(d[idx:len]) >= tol or idx == 0): len -= 1; idx = argmax(d[:len])
+// done by one warp: lane l evaluates the candidate lengths l + 1 and l + 33 on their own (first maximum of the
+// prefix, minimum from there to the end of the prefix, the reference's test); the answer is the longest prefix that
+// passes, which is where the sequential loop stops (length 1 always passes: its maximum is element 0).
+__device__ void dc_peak_warp(const double* d, double tol, int* idx_out, double* A_out) {
+    const int lane = threadIdx.x & 31;
+    auto eval = [&](int len, int* idx_o) {
+        int k = 0;
+        for (int i = 1; i < len; ++i) if (d[i] > d[k]) k = i;
+        double mn = d[k];
+        for (int i = k + 1; i < len; ++i) mn = fmin(mn, d[i]);
+        *idx_o = k;
+        return (d[k] - mn) >= tol || k == 0;
+    };
+    int idx_hi = 0, idx_lo = 0;
+    const bool ok_hi = lane + 33 <= DC_NR && eval(lane + 33, &idx_hi);
+    const bool ok_lo = eval(lane + 1, &idx_lo);
+    const unsigned m_hi = __ballot_sync(0xffffffffu, ok_hi), m_lo = __ballot_sync(0xffffffffu, ok_lo);
+    int idx;
+    if (m_hi) idx = __shfl_sync(0xffffffffu, idx_hi, 31 - __clz(m_hi));
+    else idx = __shfl_sync(0xffffffffu, idx_lo, 31 - __clz(m_lo));
+    if (lane == 0) { *idx_out = idx; *A_out = d[idx]; }
 }
 
 __device__ void dc_bounds(DecorrShared& sh, const double* __restrict__ R, int N, const double* radii) {
@@ -558,6 +566,8 @@ __device__ void dc_pass(DecorrShared& sh, const double2* __restrict__ Ik, const 
         if (lane == 0) { sh.ring_num[ring] = sn; sh.ring_pow[ring] = sp; sh.ring_abs[ring] = sa; }
     }
     __syncthreads();
+    // the curve d(r_i) and its peak: the running sums keep numpy's order (one thread, 150 additions); the divisions, square
+    // roots and the peak search - O(n^2) comparisons in the reference's loop - are spread over the lanes of warp 0
     if (threadIdx.x == 0) {
         double denom2 = 0.0;
         for (int i = 0; i <= DC_NR; ++i) denom2 += sh.ring_pow[i];
@@ -565,12 +575,20 @@ __device__ void dc_pass(DecorrShared& sh, const double2* __restrict__ Ik, const 
         for (int i = 0; i < DC_NR; ++i) {
             cn += sh.ring_num[i];
             ca += sh.ring_abs[i];
-            double v = cn / sqrt(ca * denom2);
+            sh.ring_num[i] = cn;                         // in place: cumulative numerator, cumulative |Ikn|^2 * total power
+            sh.ring_abs[i] = ca * denom2;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        for (int i = threadIdx.x; i < DC_NR; i += 64) {
+            double v = sh.ring_num[i] / sqrt(sh.ring_abs[i]);
             v = floor(1000.0 * v) / 1000.0;
             sh.d[i] = isnan(v) ? 0.0 : v;
         }
-        dc_peak(sh.d, DC_NR, tol, &sh.idx, &sh.A);
     }
+    __syncthreads();
+    if (threadIdx.x < 32) dc_peak_warp(sh.d, tol, &sh.idx, &sh.A);
     __syncthreads();
 }
 
