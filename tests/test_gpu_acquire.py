@@ -502,3 +502,55 @@ def test_host_api_calls_from_two_threads_run_concurrently_and_agree():
     assert not errors, errors
     for k in range(2):
         assert np.array_equal(got[k][0], ref[k][0]) and np.array_equal(got[k][1], ref[k][1])
+
+
+# ------------------------------------------------------------------ other pixel sizes: the PSF side K is not 59
+@pytest.mark.parametrize("px,K", [(30e-9, 39), (25e-9, 47)])
+def test_other_pixel_sizes_take_the_generic_kernels(px, K):
+    """gym-sted images at 20 nm per pixel (K = 59, the compiled-in case); the facade accepts any pixel size, and those
+    run ``gather_kernel<0>`` and the run-time-K scans.  Gather and expectation scan against the sequential oracle at
+    1e-5 (same PSF cache on both sides: ``physics.py`` equals the oracle's quadrature, ``tests/test_oracle.py``), the
+    stochastic scan by its totals."""
+    _require_gpu()
+    m = helpers.product_microscope()
+    cache = m.cache(px)
+    assert cache[0].shape == (K, K)
+    om = helpers.oracle_microscope()
+    om._cache[int(round(px * 1e9))] = tuple(np.asarray(c, dtype=np.float64) for c in cache)
+    rng = np.random.default_rng(int(px * 1e10))
+    B, H, W = 3, 40, 70
+    maps = np.stack([helpers.synthetic_datamap(rng, H, W) for _ in range(B)])
+    bm = batched(m, B, H, W, pixelsize=px, seed=5)
+    assert bm.K == K
+    bm.set_datamaps(torch.from_numpy(maps))
+    _, conf_i = bm.get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False, want_intensity=True, noise=False)
+    _, sted_i = bm.get_signal_and_bleach(30e-6, 10e-6, 0.15, bleach=True, sample_bleach=False, want_intensity=True,
+                                         noise=False, update=False)
+    exp_map = bm.bleached_roi().cpu().numpy()
+    _, stoch_i = bm.get_signal_and_bleach(30e-6, 10e-6, 0.15, bleach=True, want_intensity=True, noise=False)
+    stoch_map = bm.datamaps_roi().cpu().numpy()
+    for b in range(B):
+        dm = po.Datamap(maps[b], px)
+        dm.set_roi(om.cache(px)[0], "max")
+        E0 = om.get_effective(px, 10e-6, 0.0)
+        E1 = om.get_effective(px, 10e-6, 0.15)
+        S1 = np.exp(-om.get_k_bleach_map(px, 10e-6, 0.15, 30e-6) * 30e-6)
+        work = dm.whole_datamap.astype(np.float64).copy()
+        i0 = po.raster(work, H, W, E0, np.ones_like(E0), 0)
+        np.testing.assert_allclose(conf_i[b].cpu().numpy(), i0, rtol=RTOL, atol=1e-7 * i0.max())
+        work = dm.whole_datamap.astype(np.float64).copy()
+        i1 = po.raster(work, H, W, E1, S1, 1)
+        np.testing.assert_allclose(sted_i[b].cpu().numpy(), i1, rtol=RTOL, atol=1e-7 * i1.max())
+        np.testing.assert_allclose(exp_map[b], work[dm.roi], rtol=RTOL, atol=1e-6)
+        # stochastic scan: integer counts that only fall, totals and image within a few sigma of the expectation
+        assert np.all(stoch_map[b] == np.rint(stoch_map[b])) and np.all(stoch_map[b] <= maps[b])
+        lost, lost_exp = maps[b].sum() - stoch_map[b].sum(), maps[b].sum() - work[dm.roi].sum()
+        assert abs(lost - lost_exp) < 6 * np.sqrt(lost_exp + 1)
+        assert abs(stoch_i[b].cpu().numpy().sum() / i1.sum() - 1) < 0.02
+
+
+def test_psf_larger_than_the_compiled_limit_is_refused():
+    _require_gpu()
+    m = helpers.product_microscope()
+    with pytest.raises(_lib.StedError):
+        batched(m, 1, 16, 16, pixelsize=12e-9).get_signal_and_bleach(10e-6, 10e-6, 0.0, bleach=False)
