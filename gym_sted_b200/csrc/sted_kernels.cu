@@ -1031,6 +1031,12 @@ __global__ void __launch_bounds__(S_THREADS, STOCH ? 3 : 2) sweep_kernel(const A
 #ifndef S2_AUX_THREADS
 #define S2_AUX_THREADS 64
 #endif
+#ifndef S2_WRITE_BY_GATHER
+#define S2_WRITE_BY_GATHER 1   // 1: the gather warps write the previous group's intensities out (0: the auxiliary warps)
+#endif
+#ifndef S2_COMPACT
+#define S2_COMPACT 1   // 1: a gather warp only visits the tap rows whose ring row holds a molecule inside its window (see the kernel)
+#endif
 constexpr int S2_GATHER = 256, S2_AUX = S2_AUX_THREADS, S2_THREADS = S2_GATHER + S2_AUX;
 __host__ __device__ constexpr int s2_evcap(int T) { return T <= 2 ? 1024 : T == 3 ? 512 : 256; }
 
@@ -1052,6 +1058,13 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
     constexpr int EVCAP = s2_evcap(T);        // staged events per group (the rest is read from global memory)
     uint32_t* sEv = reinterpret_cast<uint32_t*>(sCorr + T * TC);            // [2][EVCAP] this / the previous group's events
     int* sMeta = reinterpret_cast<int*>(sEv + 2 * EVCAP);                   // [2][2] their range in ws.ev
+    // [NS][2] per ring slot: which 4-column chunks of the row held a molecule BEFORE the scan (bit g = chunk g).  Molecule
+    // maps are sparse; a gather warp (CT columns, K tap rows spread over its lanes) visits only the tap rows whose ring
+    // row has a molecule inside the warp's window: the live rows are dealt to the lanes in order, and when there are at
+    // most 32 of them (47 % of the (warp, scan row) pairs of the bench maps) one pass over the taps replaces two.  The
+    // marks come from the map as it was before this acquisition - never from the counts of the moment - so the rows a warp
+    // visits, and with them the order of its sums, do not depend on how the scan is cut in row ranges.
+    uint32_t* sOcc = reinterpret_cast<uint32_t*>(sMeta + 4);
 
     const int b = blockIdx.z;
     const int c0 = blockIdx.x * TC;
@@ -1080,6 +1093,10 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
     const int q4 = PR / 4;                    // float4 groups of a ring row
 
     auto slot_of = [&](const int y) { return (KT ? y % (KT + 2 * T - 1) : y % NS) * PR; };
+    auto slot_idx = [&](const int y) { return KT ? y % (KT + 2 * T - 1) : y % NS; };
+    auto mark_row = [&](const int y, const int g, const float4 v) {
+        if (S2_COMPACT && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)) atomicOr(&sOcc[2 * slot_idx(y) + (g >> 5)], 1u << (g & 31));
+    };
     auto fetch_row = [&](const int y, const int g) -> float4 {
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
         const int x = c0 + 4 * g;
@@ -1097,9 +1114,15 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
     auto clamp_hi = [&](const int v) { return (unsigned long long)v > ws.cap ? (int)ws.cap : v; };
 
     // band rows r0 .. r0+K+T-2 (what the first group reads) as they were BEFORE the scan ...
+    if (S2_COMPACT) {
+        for (int i = tid; i < 2 * NS; i += S2_THREADS) sOcc[i] = 0u;
+        __syncthreads();
+    }
     for (int i = tid; i < (K + T - 1) * q4; i += S2_THREADS) {
         const int yy = i / q4, g = i - yy * q4;
-        *reinterpret_cast<float4*>(ring + slot_of(r0 + yy) + 4 * g) = fetch_row(r0 + yy, g);
+        const float4 v = fetch_row(r0 + yy, g);
+        *reinterpret_cast<float4*>(ring + slot_of(r0 + yy) + 4 * g) = v;
+        mark_row(r0 + yy, g, v);
     }
     __syncthreads();
     // ... minus the deaths of the scan rows before r0 that hit them (scan row r' reaches band rows r' .. r'+K-1)
@@ -1120,9 +1143,9 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
     // minus (a) the taps a death removes from the rest of its own row and (b) everything the molecules that died in
     // an earlier row of the group would have contributed to the later rows of the group: fixed-point sums in sCorr
     // (filled between the two barriers of the group), applied here when the auxiliary warps write the rows out
-    auto write_rows = [&](const int R0, const int Tg, const int par) {
+    auto write_rows = [&](const int R0, const int Tg, const int par, const int first, const int stride) {
         const float* dense = sI + par * T * TC;
-        for (int t = at; t < Tg * TC; t += S2_AUX) {
+        for (int t = first; t < Tg * TC; t += stride) {
             const int j = t / TC, c = t - j * TC;
             if (c0 + c < W) {
                 const float I = fmaxf(dense[t] * (1.0f - (float)sCorr[t] * 9.313225746154785e-10f), 0.f);
@@ -1166,16 +1189,29 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
 #ifdef S2_ABLATE_RING                        // timing ablation only: the ring never moves
             if (false)
 #endif
+            if (S2_COMPACT) {                    // the marks of the rows that leave (their slots are not read by this group)
+                if (at < T) { const int sl = slot_idx(R0 - T + at + NS); sOcc[2 * sl] = 0u; sOcc[2 * sl + 1] = 0u; }
+                asm volatile("bar.sync 1, %0;" :: "n"(S2_AUX) : "memory");
+            }
             for (int i = at; i < T * q4; i += S2_AUX) {
                 const int j = i / q4, g = i - j * q4;
                 const int y_old = R0 - T + j, y_new = y_old + NS;
                 if (grp > 0) retire_row(y_old, g);
-                *reinterpret_cast<float4*>(ring + slot_of(y_new) + 4 * g) = fetch_row(y_new, g);     // zeros below the map
+                const float4 v = fetch_row(y_new, g);                                                 // zeros below the map
+                *reinterpret_cast<float4*>(ring + slot_of(y_new) + 4 * g) = v;
+                mark_row(y_new, g, v);
             }
             S2_TICK(3);
-            if (grp > 0) write_rows(R0 - T, T, par ^ 1);
+#if !S2_WRITE_BY_GATHER
+            if (grp > 0) write_rows(R0 - T, T, par ^ 1, at, S2_AUX);
+#endif
             S2_TICK(4);
         } else {
+#if S2_WRITE_BY_GATHER
+            // the previous group's intensities leave first (the auxiliary warps' chain of dependent loads - event list, ring
+            // rows - is as long as a gather since the gather skips empty tap rows: the write-out moved over here)
+            if (grp > 0) write_rows(R0 - T, T, par ^ 1, tid, S2_GATHER);
+#endif
             // ---- gather warps: dense gathers of scan rows R0 .. R0+Tg-1 against the counts at the start of the group
             for (int j = 0; j < Tg; ++j) {
                 float acc[CT];
@@ -1233,7 +1269,21 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
 #else
 #pragma unroll
                 for (int jj = 0; jj < CT; ++jj) acc[jj] = 0.f;
+#if S2_COMPACT
+                // the tap rows with a molecule inside this warp's window (CT + KP columns from column CT * warp), dealt to
+                // the lanes in order
+                const unsigned long long wmask = ((1ull << ((CT + KP) >> 2)) - 1ull) << ((CT * warp) >> 2);
+                auto live = [&](const int uu) {
+                    const uint32_t* o = sOcc + 2 * slot_idx(R0 + j + uu);
+                    return uu < K && ((((unsigned long long)o[1] << 32) | o[0]) & wmask) != 0ull;
+                };
+                const unsigned live0 = __ballot_sync(0xffffffffu, live(lane)), live1 = __ballot_sync(0xffffffffu, live(lane + 32));
+                const int n0 = __popc(live0), nlive = n0 + __popc(live1);
+                for (int il = lane; il < nlive; il += 32) {
+                    const int uu = il < n0 ? (int)__fns(live0, 0, il + 1) : 32 + (int)__fns(live1, 0, il - n0 + 1);
+#else
                 for (int uu = lane; uu < K; uu += 32) {
+#endif
                     const float* drow = ring + slot_of(R0 + j + uu) + CT * warp;
                     const float* erow = sWt + uu * KP;
                     float win[CT + 4];
@@ -1345,7 +1395,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
 #endif
     // ---- epilogue: the last group's intensities, the band rows this range owns and has not written yet
     const int Rl = r0 + (grp - 1) * T;        // first row of the last group
-    if (aux) write_rows(Rl, r1 - Rl, (grp - 1) & 1);
+    if (aux) write_rows(Rl, r1 - Rl, (grp - 1) & 1, at, S2_AUX);
     const int yend = (r1 == H) ? P.Hp : r1;
     for (int i = tid; i < (yend - Rl) * q4; i += S2_THREADS) {
         const int yy = i / q4;
@@ -1963,7 +2013,8 @@ template <int KT, int CT, int T>
 int launch_sweep2_t(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     constexpr int TC = 8 * CT;
     const int PR = sweep_pitch(TC, P.KP);
-    size_t smem = ((size_t)(P.K + 2 * T - 1) * PR + (size_t)P.K * P.KP + 4 * T * TC + 2 * s2_evcap(T) + 4) * sizeof(float);
+    size_t smem = ((size_t)(P.K + 2 * T - 1) * PR + (size_t)P.K * P.KP + 4 * T * TC + 2 * s2_evcap(T) + 4 +
+                   2 * (size_t)(P.K + 2 * T - 1)) * sizeof(float);
     if (const char* e = getenv("STED_B200_S2_PAD_SMEM")) smem += (size_t)atoi(e);     // occupancy experiments only
     int rc;
     if ((rc = set_smem(sweep2_kernel<KT, CT, T>, smem))) return rc;
