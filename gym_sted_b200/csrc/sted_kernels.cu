@@ -1065,6 +1065,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
     // marks come from the map as it was before this acquisition - never from the counts of the moment - so the rows a warp
     // visits, and with them the order of its sums, do not depend on how the scan is cut in row ranges.
     uint32_t* sOcc = reinterpret_cast<uint32_t*>(sMeta + 4);
+    unsigned char* sRows = reinterpret_cast<unsigned char*>(sOcc + 2 * NS);      // [8 gather warps][64] live tap rows, in order
 
     const int b = blockIdx.z;
     const int c0 = blockIdx.x * TC;
@@ -1158,6 +1159,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
     };
 
 #if SWEEP_PROBE >= 3
+    long long s2_passes = 0, s2_rows = 0;
     long long t_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_a = clock64(), t_b;
     const long long t_begin = t_a;
 #define S2_TICK(i) do { t_b = clock64(); t_ph[i] += t_b - t_a; t_a = t_b; } while (0)
@@ -1277,10 +1279,20 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
                     const uint32_t* o = sOcc + 2 * slot_idx(R0 + j + uu);
                     return uu < K && ((((unsigned long long)o[1] << 32) | o[0]) & wmask) != 0ull;
                 };
-                const unsigned live0 = __ballot_sync(0xffffffffu, live(lane)), live1 = __ballot_sync(0xffffffffu, live(lane + 32));
+                const bool mine0 = live(lane), mine1 = live(lane + 32);
+                const unsigned live0 = __ballot_sync(0xffffffffu, mine0), live1 = __ballot_sync(0xffffffffu, mine1);
                 const int n0 = __popc(live0), nlive = n0 + __popc(live1);
+                // each live row writes itself to its rank in the warp's list (__fns, the direct "n-th set bit", is a
+                // software loop that cost as much as the skipped rows saved)
+                unsigned char* my_rows = sRows + 64 * warp;
+                if (mine0) my_rows[__popc(live0 & ((1u << lane) - 1u))] = (unsigned char)lane;
+                if (mine1) my_rows[n0 + __popc(live1 & ((1u << lane) - 1u))] = (unsigned char)(lane + 32);
+                __syncwarp();
+#if SWEEP_PROBE == 3 && defined(S2_COUNT_PASSES)
+                if (tid == 0) { s2_passes += (nlive + 31) / 32; s2_rows += 1; }      // warp 0's view
+#endif
                 for (int il = lane; il < nlive; il += 32) {
-                    const int uu = il < n0 ? (int)__fns(live0, 0, il + 1) : 32 + (int)__fns(live1, 0, il - n0 + 1);
+                    const int uu = my_rows[il];
 #else
                 for (int uu = lane; uu < K; uu += 32) {
 #endif
@@ -1390,6 +1402,9 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
         t_ph[6] = (tid == 0) ? grp : 0;
         t_ph[7] = (tid == 0) ? (t_a - t_begin) : 0;     // whole loop, gather thread
         if (tid == 0) { t_ph[3] = t_ph[4] = t_ph[5] = 0; } else { t_ph[0] = t_ph[1] = t_ph[2] = 0; }
+#ifdef S2_COUNT_PASSES
+        if (tid == 0) { t_ph[4] = s2_passes * 1000; t_ph[5] = s2_rows * 1000; }          // read as passes / rows
+#endif
         for (int i = 0; i < 8; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)t_ph[i]);
     }
 #endif
@@ -2014,7 +2029,7 @@ int launch_sweep2_t(const AcqParams& P, const BleachWs& ws, cudaStream_t st) {
     constexpr int TC = 8 * CT;
     const int PR = sweep_pitch(TC, P.KP);
     size_t smem = ((size_t)(P.K + 2 * T - 1) * PR + (size_t)P.K * P.KP + 4 * T * TC + 2 * s2_evcap(T) + 4 +
-                   2 * (size_t)(P.K + 2 * T - 1)) * sizeof(float);
+                   2 * (size_t)(P.K + 2 * T - 1) + 8 * 64 / 4) * sizeof(float);
     if (const char* e = getenv("STED_B200_S2_PAD_SMEM")) smem += (size_t)atoi(e);     // occupancy experiments only
     int rc;
     if ((rc = set_smem(sweep2_kernel<KT, CT, T>, smem))) return rc;
