@@ -1034,6 +1034,9 @@ __global__ void __launch_bounds__(S_THREADS, STOCH ? 3 : 2) sweep_kernel(const A
 #ifndef S2_WRITE_BY_GATHER
 #define S2_WRITE_BY_GATHER 1   // 1: the gather warps write the previous group's intensities out (0: the auxiliary warps)
 #endif
+#ifndef S2_PARTS
+#define S2_PARTS 3     // work units of the compacted gather per live tap row (runs of tap chunks)
+#endif
 #ifndef S2_COMPACT
 #define S2_COMPACT 1   // 1: a gather warp only visits the tap rows whose ring row holds a molecule inside its window (see the kernel)
 #endif
@@ -1291,11 +1294,38 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
 #if SWEEP_PROBE == 3 && defined(S2_COUNT_PASSES)
                 if (tid == 0) { s2_passes += (nlive + 31) / 32; s2_rows += 1; }      // warp 0's view
 #endif
-                for (int il = lane; il < nlive; il += 32) {
-                    const int uu = my_rows[il];
+                // work units = (live tap row, one of S2_PARTS runs of tap chunks): with whole rows as units a warp with 33
+                // live rows paid two full passes; the finer deal wastes at most one part per lane (1.17 passes per scan row
+                // on the bench maps with three parts, 1.53 with one)
+                const int nchunk = KP / 4, per = (nchunk + S2_PARTS - 1) / S2_PARTS;
+                for (int iu = lane; iu < S2_PARTS * nlive; iu += 32) {
+                    const int uu = my_rows[iu / S2_PARTS], vc0 = (iu % S2_PARTS) * per, vc1 = min(nchunk, vc0 + per);
+                    const float* drow = ring + slot_of(R0 + j + uu) + CT * warp + 4 * vc0;
+                    const float* erow = sWt + uu * KP + 4 * vc0;
+                    float win[CT + 4];
+#pragma unroll
+                    for (int jj = 0; jj < CT; jj += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(drow + jj);
+                        win[jj] = t.x; win[jj + 1] = t.y; win[jj + 2] = t.z; win[jj + 3] = t.w;
+                    }
+#pragma unroll 5
+                    for (int vc = 0; vc < vc1 - vc0; ++vc) {
+                        const float4 nw = *reinterpret_cast<const float4*>(drow + CT + 4 * vc);
+                        const float4 e = *reinterpret_cast<const float4*>(erow + 4 * vc);
+                        win[CT] = nw.x; win[CT + 1] = nw.y; win[CT + 2] = nw.z; win[CT + 3] = nw.w;
+#pragma unroll
+                        for (int jj = 0; jj < CT; ++jj) {
+                            acc[jj] = fmaf(e.x, win[jj], acc[jj]);
+                            acc[jj] = fmaf(e.y, win[jj + 1], acc[jj]);
+                            acc[jj] = fmaf(e.z, win[jj + 2], acc[jj]);
+                            acc[jj] = fmaf(e.w, win[jj + 3], acc[jj]);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < CT; ++jj) win[jj] = win[jj + 4];
+                    }
+                }
 #else
                 for (int uu = lane; uu < K; uu += 32) {
-#endif
                     const float* drow = ring + slot_of(R0 + j + uu) + CT * warp;
                     const float* erow = sWt + uu * KP;
                     float win[CT + 4];
@@ -1321,6 +1351,7 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
                         for (int jj = 0; jj < CT; ++jj) win[jj] = win[jj + 4];
                     }
                 }
+#endif
 #endif
                 const float tot = reduce_scatter<CT>(acc, lane);
                 constexpr int SH = (CT == 32) ? 0 : (CT == 16) ? 1 : (CT == 8) ? 2 : (CT == 4) ? 3 : 4;
