@@ -575,7 +575,9 @@ def run_ours(args, rank, local_rank, world):
                                              "" if args.sequential else "; its death schedule (presample + bucket scan + scatter) "
                                              "was drawn on the session's second stream under the confocal gather before it, and the "
                                              "low-priority session's gather shares the SMs with it")},
-                         "note": "3N algorithmic flops (SURVEY 8d); the kernels execute 2N.  launch_ms is the whole chain on one "
+                         "note": "3N algorithmic flops (SURVEY 8d); the kernels execute at most 2N (the survival factors are pre-drawn deaths, and the "
+                                 "gather visits only the tap rows whose datamap row holds a molecule inside the warp's window - on these "
+                                 "maps about 0.6 of them - so the fraction can approach or exceed 1 like the gather's).  launch_ms is the whole chain on one "
                                  "stream with nothing else on the GPU (CUDA events on the launching stream, 5 scans after the timed "
                                  "region, each on freshly loaded maps)"}
         cpu = None
@@ -657,8 +659,11 @@ def run_env_step(args, rank, local_rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
+    step_ms = []
     for i in range(args.steps):
+        ts = time.perf_counter()
         (img, vec), reward, done, _, info = env.step(acts[args.warmup + i])
+        step_ms.append((time.perf_counter() - ts) * 1e3)
         d2h = img.nbytes + reward.nbytes + info["mo_objs"].nbytes
     e1.record()
     sync_all()
@@ -679,7 +684,8 @@ def run_env_step(args, rank, local_rank, world):
                 "config": workload_config(args, B, world, schedule="VectorContextualMOSTED.step: conf, STED+bleach, conf, objectives + "
                                           "Otsu + decorrelation + nanodomain F1, new synapses generated on the device, confocal "
                                           "of the new structure, uint16 observation to the host"),
-                "env_steps_per_s": steps_s,
+                "env_steps_per_s": steps_s, "step_ms_rank0": {"median": float(np.median(step_ms)), "min": float(np.min(step_ms)),
+                                                                "max": float(np.max(step_ms))},
                 "e2e": {"value": value, "unit": "acquisitions/s", "h2d_bytes_per_step": int(acts[0].nbytes), "d2h_bytes_per_step": int(d2h),
                         "api": "gym_sted_b200.envs.make_vec(...).step(actions) -> numpy observation / reward / info",
                         "note": "value IS the end-to-end number for this workload: every step ends on the host",
