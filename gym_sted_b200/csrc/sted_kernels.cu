@@ -1296,7 +1296,9 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
 #endif
                 // work units = (live tap row, one of S2_PARTS runs of tap chunks): with whole rows as units a warp with 33
                 // live rows paid two full passes; the finer deal wastes at most one part per lane (1.17 passes per scan row
-                // on the bench maps with three parts, 1.53 with one)
+                // on the bench maps with three parts, 1.53 with one).  Testing every (row, run) unit against the row's marks
+                // (0.93 pass-equivalents) measured SLOWER, 3.149 vs 3.085 ms for the whole scan: six ballots and rank stores
+                // per scan row instead of two, and warps of one CTA whose unit counts differ more wait longer for each other.
                 const int nchunk = KP / 4, per = (nchunk + S2_PARTS - 1) / S2_PARTS;
                 for (int iu = lane; iu < S2_PARTS * nlive; iu += 32) {
                     const int uu = my_rows[iu / S2_PARTS], vc0 = (iu % S2_PARTS) * per, vc1 = min(nchunk, vc0 + per);
