@@ -1220,6 +1220,33 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
             // ---- gather warps: dense gathers of scan rows R0 .. R0+Tg-1 against the counts at the start of the group
             for (int j = 0; j < Tg; ++j) {
                 float acc[CT];
+#if S2_COMPACT
+                // the tap rows with a molecule inside this warp's window (CT + KP columns from column CT * warp), dealt to
+                // the lanes in order
+                const unsigned long long wmask = ((1ull << ((CT + KP) >> 2)) - 1ull) << ((CT * warp) >> 2);
+                auto live = [&](const int uu) {
+                    const uint32_t* o = sOcc + 2 * slot_idx(R0 + j + uu);
+                    return uu < K && ((((unsigned long long)o[1] << 32) | o[0]) & wmask) != 0ull;
+                };
+                const bool mine0 = live(lane), mine1 = live(lane + 32);
+                const unsigned live0 = __ballot_sync(0xffffffffu, mine0), live1 = __ballot_sync(0xffffffffu, mine1);
+                const int n0 = __popc(live0), nlive = n0 + __popc(live1);
+                // each live row writes itself to its rank in the warp's list (__fns, the direct "n-th set bit", is a
+                // software loop that cost as much as the skipped rows saved)
+                unsigned char* my_rows = sRows + 64 * warp;
+                if (mine0) my_rows[__popc(live0 & ((1u << lane) - 1u))] = (unsigned char)lane;
+                if (mine1) my_rows[n0 + __popc(live1 & ((1u << lane) - 1u))] = (unsigned char)(lane + 32);
+                __syncwarp();
+#if SWEEP_PROBE == 3 && defined(S2_COUNT_PASSES)
+                if (tid == 0) { s2_passes += (nlive + 31) / 32; s2_rows += 1; }      // warp 0's view
+#endif
+                // work units = (live tap row, one of S2_PARTS runs of tap chunks): with whole rows as units a warp with 33
+                // live rows paid two full passes; the finer deal wastes at most one part per lane (1.17 passes per scan row
+                // on the bench maps with three parts, 1.53 with one).  Testing every (row, run) unit against the row's marks
+                // (0.93 pass-equivalents) measured SLOWER, 3.149 vs 3.085 ms for the whole scan: six ballots and rank stores
+                // per scan row instead of two, and warps of one CTA whose unit counts differ more wait longer for each other.
+                const int nchunk = KP / 4, per = (nchunk + S2_PARTS - 1) / S2_PARTS;
+#endif
 #if S2_FFMA2
                 // FFMA2 (fma.rn.f32x2), one issue slot per two FMAs: the ncu profile of the scalar loop was issue bound
                 // (83 % of the issue slots for 65 % of the FMA pipe).  A tap E[u][v] — the instruction's scalar-broadcast
@@ -1232,18 +1259,23 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
                 for (int pp = 0; pp < CT / 2; ++pp) accA[pp] = 0ull;
 #pragma unroll
                 for (int pp = 0; pp <= CT / 2; ++pp) accB[pp] = 0ull;
+#if S2_COMPACT
+                for (int iu = lane; iu < S2_PARTS * nlive; iu += 32) {
+                    const int uu = my_rows[iu / S2_PARTS], vc0 = (iu % S2_PARTS) * per, nvc = min(nchunk, vc0 + per) - vc0;
+#else
                 for (int uu = lane; uu < K; uu += 32) {
-                    const float* drow = ring + slot_of(R0 + j + uu) + CT * warp;
-                    const float* erow = sWt + uu * KP;
+                    const int vc0 = 0, nvc = KP / 4;
+#endif
+                    const float* drow = ring + slot_of(R0 + j + uu) + CT * warp + 4 * vc0;
+                    const float* erow = sWt + uu * KP + 4 * vc0;
                     u64 wp[CT / 2 + 2];                               // window pairs (w[2k], w[2k+1])
 #pragma unroll
                     for (int jj = 0; jj < CT / 4; ++jj) {
                         const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(drow + 4 * jj);
                         wp[2 * jj] = t.x; wp[2 * jj + 1] = t.y;
                     }
-                    const int nchunk = KP / 4;
 #pragma unroll 5
-                    for (int vc = 0; vc < nchunk; ++vc) {
+                    for (int vc = 0; vc < nvc; ++vc) {
                         const ulonglong2 nw = *reinterpret_cast<const ulonglong2*>(drow + CT + 4 * vc);
                         const float4 e = *reinterpret_cast<const float4*>(erow + 4 * vc);
                         wp[CT / 2] = nw.x; wp[CT / 2 + 1] = nw.y;
@@ -1275,31 +1307,6 @@ __global__ void __launch_bounds__(S2_THREADS, 3) sweep2_kernel(const AcqParams P
 #pragma unroll
                 for (int jj = 0; jj < CT; ++jj) acc[jj] = 0.f;
 #if S2_COMPACT
-                // the tap rows with a molecule inside this warp's window (CT + KP columns from column CT * warp), dealt to
-                // the lanes in order
-                const unsigned long long wmask = ((1ull << ((CT + KP) >> 2)) - 1ull) << ((CT * warp) >> 2);
-                auto live = [&](const int uu) {
-                    const uint32_t* o = sOcc + 2 * slot_idx(R0 + j + uu);
-                    return uu < K && ((((unsigned long long)o[1] << 32) | o[0]) & wmask) != 0ull;
-                };
-                const bool mine0 = live(lane), mine1 = live(lane + 32);
-                const unsigned live0 = __ballot_sync(0xffffffffu, mine0), live1 = __ballot_sync(0xffffffffu, mine1);
-                const int n0 = __popc(live0), nlive = n0 + __popc(live1);
-                // each live row writes itself to its rank in the warp's list (__fns, the direct "n-th set bit", is a
-                // software loop that cost as much as the skipped rows saved)
-                unsigned char* my_rows = sRows + 64 * warp;
-                if (mine0) my_rows[__popc(live0 & ((1u << lane) - 1u))] = (unsigned char)lane;
-                if (mine1) my_rows[n0 + __popc(live1 & ((1u << lane) - 1u))] = (unsigned char)(lane + 32);
-                __syncwarp();
-#if SWEEP_PROBE == 3 && defined(S2_COUNT_PASSES)
-                if (tid == 0) { s2_passes += (nlive + 31) / 32; s2_rows += 1; }      // warp 0's view
-#endif
-                // work units = (live tap row, one of S2_PARTS runs of tap chunks): with whole rows as units a warp with 33
-                // live rows paid two full passes; the finer deal wastes at most one part per lane (1.17 passes per scan row
-                // on the bench maps with three parts, 1.53 with one).  Testing every (row, run) unit against the row's marks
-                // (0.93 pass-equivalents) measured SLOWER, 3.149 vs 3.085 ms for the whole scan: six ballots and rank stores
-                // per scan row instead of two, and warps of one CTA whose unit counts differ more wait longer for each other.
-                const int nchunk = KP / 4, per = (nchunk + S2_PARTS - 1) / S2_PARTS;
                 for (int iu = lane; iu < S2_PARTS * nlive; iu += 32) {
                     const int uu = my_rows[iu / S2_PARTS], vc0 = (iu % S2_PARTS) * per, vc1 = min(nchunk, vc0 + per);
                     const float* drow = ring + slot_of(R0 + j + uu) + CT * warp + 4 * vc0;
