@@ -13,6 +13,8 @@ B = int(os.environ.get("PROBE_B", 256)); H = W = int(os.environ.get("PROBE_HW", 
 micro = make_microscope(defaults.load_routine("high-signal_low-bleach"))
 bm = BatchedMicroscope(micro, B, H, W, seed=1)
 maps, _ = synapse.generate_batch(min(B, 32), H, W, seed=1234)
+if os.environ.get("PROBE_DENSE"):          # every pixel occupied: nothing to skip
+    maps = np.maximum(maps, 1)
 bm.set_datamaps(torch.from_numpy(np.tile(maps, ((B + 31) // 32, 1, 1))[:B]).float().cuda())
 kw = dict(pdt=torch.full((B,), 10e-6, dtype=torch.float64).cuda(), p_ex=torch.full((B,), 10e-6, dtype=torch.float64).cuda(),
           p_sted=torch.full((B,), 0.0, dtype=torch.float64).cuda())
