@@ -97,6 +97,7 @@ SIGNATURES = {
     "sted_synapse_scratch_bytes": (_u64, [_i, _i, _i]),
     "sted_synapse_generate": (_i, [ctypes.POINTER(StedSynapseParams), _i, _i, _i, _u64, _u64, _i64, _vp, _vp, _vp, _i, _vp, _vp]),
     "sted_pad_maps": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sted_structure_maps": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "sted_pack_observation": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "sted_lmfit_test": (_i, [_vp, _i, _i, _d, _vp, _vp, _vp]),
     "sted_debug_phase_cycles": (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),

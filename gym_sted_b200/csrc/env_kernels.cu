@@ -169,6 +169,48 @@ __global__ void synapse_compact_kernel(const int B, const int H, const int W, co
     if (lane == 0) counts[b] = min(total, max_truth);
 }
 
+// Procedural structure maps of the preference environments (stand-in for the U-Net datamaps the reference crops and
+// that are not shipped, gym_sted/datamaps/datamap.py:86-152, defaults.py:6-13): per environment up to 24 objects -
+// sinuous filaments exp(-d^2 / 2 w^2) or round clusters exp(-r^2 / 2 s^2) - combined by maximum, cut below 0.5, scaled
+// by the molecule count and floored, then rotated by k * 90 degrees and flipped.  One thread per OUTPUT pixel: it maps its
+// coordinates back through the flips and the rotation and evaluates the analytic image there (float64).
+constexpr int SM_MAXOBJ = 24;
+__global__ void __launch_bounds__(256) structure_maps_kernel(const double* __restrict__ obj, const double* __restrict__ env, int H, int W,
+                                                             float* __restrict__ out) {
+    __shared__ double so[SM_MAXOBJ * 4];
+    __shared__ double se[6];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < SM_MAXOBJ * 4; i += blockDim.x) so[i] = obj[(size_t)b * SM_MAXOBJ * 4 + i];
+    if (threadIdx.x < 6) se[threadIdx.x] = env[(size_t)b * 6 + threadIdx.x];
+    __syncthreads();
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= H * W) return;
+    int i = pix / W, j = pix % W;
+    const int nobj = (int)se[0], rot = (int)se[2];
+    const bool filament = se[5] != 0.0;
+    if (se[4] != 0.0) j = W - 1 - j;                       // undo flip along the columns
+    if (se[3] != 0.0) i = H - 1 - i;                       // undo flip along the rows
+    int y = i, x = j;                                      // undo numpy.rot90(img, rot) (square maps only: rot = 0 otherwise)
+    if (rot == 1) { y = j; x = W - 1 - i; }
+    else if (rot == 2) { y = H - 1 - i; x = W - 1 - j; }
+    else if (rot == 3) { y = H - 1 - j; x = i; }
+    const double yy = (double)y, xx = (double)x;
+    double img = 0.0;
+    for (int k = 0; k < nobj; ++k) {
+        const double a0 = so[4 * k], a1 = so[4 * k + 1], a2 = so[4 * k + 2], a3 = so[4 * k + 3];
+        double v;
+        if (filament) {                                    // a0 = cos, a1 = sin, a2 = offset, a3 = width
+            const double d = fabs(xx * a0 + yy * a1 - a2 + 3.0 * sin(0.08 * (yy * a0 - xx * a1)));
+            v = exp(-0.5 * ((d / a3) * (d / a3)));
+        } else {                                           // a0 = cy, a1 = cx, a2 = sigma
+            v = exp(-0.5 * ((yy - a0) * (yy - a0) + (xx - a1) * (xx - a1)) / (a2 * a2));
+        }
+        img = fmax(img, v);
+    }
+    if (img < 0.5) img = 0.0;
+    out[(size_t)b * H * W + pix] = (float)floor(img * se[1]);
+}
+
 template <class T>
 __global__ void pad_maps_kernel(const T* __restrict__ roi, float* __restrict__ padded, int B, int H, int W, int p, int Hp, int Wpitch) {
     const size_t n = (size_t)B * Hp * Wpitch;
@@ -221,6 +263,16 @@ int sted_synapse_generate(const StedSynapseParams* prm, int B, int H, int W, uin
                                                                  frames_dev, cell_coords, cell_counts);
     CUDA_TRY(cudaGetLastError());
     synapse_compact_kernel<<<B, 32, 0, st>>>(B, H, W, ncells, max_truth, cell_coords, cell_counts, coords_dev, counts_dev);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+int sted_structure_maps(const double* objects_dev, const double* env_dev, int B, int H, int W, float* maps_dev, void* stream) {
+    int rc = check_device();
+    if (rc) return rc;
+    if (!objects_dev || !env_dev || !maps_dev) return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || B > 65535 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B (<= 65535), H, W must be positive");
+    structure_maps_kernel<<<dim3((H * W + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(objects_dev, env_dev, H, W, maps_dev);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }

@@ -454,16 +454,17 @@ class SyntheticDatamapGenerator:
             img = np.flip(img, axis=1)
         return np.ascontiguousarray(img)
 
-    def batch(self, groups, device) -> torch.Tensor:
-        """One structure map per entry of ``groups`` as a (B,H,W) float32 device tensor: the same procedural model as
-        ``__call__`` with the random parameters drawn on the host (a few numbers per map) and the images rendered on
-        the GPU."""
+    NOBJ = 24
+
+    def draw_batch(self, groups):
+        """The random parameters of one structure map per entry of ``groups`` (host RNG, a few numbers per map) in the
+        layout ``sted_structure_maps`` takes: ``objects`` float64 (B, 24, 4), ``env`` float64 (B, 6)."""
         H, W = self.shape
         B = len(groups)
         rng = self.rng
         fil = np.array([g in ("actin", "tubulin", "lifeact") for g in groups])
         width = np.array([{"actin": 1.2, "tubulin": 1.0, "lifeact": 1.6}.get(g, 1.0) for g in groups])
-        NF, NC = 7, 24
+        NF, NC = 7, self.NOBJ
         n_obj = np.where(fil, rng.integers(3, 8, B), rng.integers(8, 25, B))
         th = rng.uniform(0, np.pi, (B, NF))
         off = rng.uniform(0.1, 0.9, (B, NF)) * (H * np.abs(np.sin(th)) + W * np.abs(np.cos(th)))
@@ -474,35 +475,56 @@ class SyntheticDatamapGenerator:
         while bad.any():
             scale[bad] = rng.normal(self.molecules, self.molecules_scale * self.molecules, int(bad.sum()))
             bad = (scale < 1) | (scale > self.molecules)
-        rot = np.where(rng.random(B) < 0.5, rng.integers(1, 4, B), 0)
+        rot = np.where(rng.random(B) < 0.5, rng.integers(1, 4, B), 0) if H == W else np.zeros(B, dtype=np.int64)
         flip0, flip1 = rng.random(B) < 0.5, rng.random(B) < 0.5
+        objects = np.zeros((B, NC, 4))
+        objects[~fil, :, 0], objects[~fil, :, 1], objects[~fil, :, 2] = cy[~fil], cx[~fil], sig[~fil]
+        objects[fil, :NF, 0], objects[fil, :NF, 1], objects[fil, :NF, 2] = np.cos(th[fil]), np.sin(th[fil]), off[fil]
+        objects[fil, :NF, 3] = width[fil, None]
+        env = np.stack([n_obj, np.floor(scale), rot, flip0, flip1, fil], axis=1).astype(np.float64)
+        return objects, env
 
-        def dev(a, dtype=torch.float32):
-            return torch.as_tensor(np.asarray(a), device=device).to(dtype)
+    def render_numpy(self, objects, env):
+        """Float64 numpy rendering of ``draw_batch`` parameters: the model ``sted_structure_maps`` evaluates (checker of
+        the kernel, and the renderer when no GPU is asked for)."""
+        H, W = self.shape
+        yy, xx = np.mgrid[:H, :W].astype(np.float64)
+        out = np.zeros((len(env), H, W), dtype=np.float32)
+        for b, (e, ob) in enumerate(zip(env, objects)):
+            img = np.zeros((H, W))
+            for a0, a1, a2, a3 in ob[:int(e[0])]:
+                if e[5]:
+                    d = np.abs(xx * a0 + yy * a1 - a2 + 3.0 * np.sin(0.08 * (yy * a0 - xx * a1)))
+                    v = np.exp(-0.5 * ((d / a3) * (d / a3)))
+                else:
+                    v = np.exp(-0.5 * ((yy - a0) * (yy - a0) + (xx - a1) * (xx - a1)) / (a2 * a2))
+                img = np.maximum(img, v)
+            img[img < 0.5] = 0.0
+            img = np.floor(img * e[1])
+            img = np.rot90(img, int(e[2]))
+            if e[3]:
+                img = np.flip(img, axis=0)
+            if e[4]:
+                img = np.flip(img, axis=1)
+            out[b] = img
+        return out
 
-        yy = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
-        xx = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
-        img = torch.zeros((B, H, W), device=device)
-        n_t, fil_t, width_t = dev(n_obj)[:, None, None], dev(fil, torch.bool)[:, None, None], dev(width)[:, None, None]
-        th_t, off_t, cy_t, cx_t, sig_t = dev(th), dev(off), dev(cy), dev(cx), dev(sig)
-        for j in range(NC):
-            blob = torch.exp(-0.5 * ((yy - cy_t[:, j, None, None]) ** 2 + (xx - cx_t[:, j, None, None]) ** 2)
-                             / sig_t[:, j, None, None] ** 2)
-            if j < NF:
-                c, sn = torch.cos(th_t[:, j, None, None]), torch.sin(th_t[:, j, None, None])
-                d = torch.abs(xx * c + yy * sn - off_t[:, j, None, None] + 3 * torch.sin(0.08 * (yy * c - xx * sn)))
-                blob = torch.where(fil_t, torch.exp(-0.5 * (d / width_t) ** 2), blob)
-            img = torch.where(j < n_t, torch.maximum(img, blob), img)
-        img = torch.where(img < 0.5, torch.zeros_like(img), img)
-        img = torch.floor(img * dev(np.floor(scale))[:, None, None])
-        if H == W:
-            rot_t = dev(rot, torch.int64)[:, None, None]
-            turned = [torch.rot90(img, k, dims=(1, 2)) for k in (1, 2, 3)]
-            for k in (1, 2, 3):
-                img = torch.where(rot_t == k, turned[k - 1], img)
-        img = torch.where(dev(flip0, torch.bool)[:, None, None], torch.flip(img, dims=(1,)), img)
-        img = torch.where(dev(flip1, torch.bool)[:, None, None], torch.flip(img, dims=(2,)), img)
-        return img.contiguous()
+    def batch(self, groups, device) -> torch.Tensor:
+        """One structure map per entry of ``groups`` as a (B,H,W) float32 tensor on ``device``: the same procedural model
+        as ``__call__`` with the random parameters drawn on the host and the images rendered by ``sted_structure_maps``
+        (one thread per pixel, float64) on a CUDA device, by ``render_numpy`` otherwise."""
+        objects, env = self.draw_batch(groups)
+        device = torch.device(device)
+        if device.type != "cuda":
+            return torch.from_numpy(self.render_numpy(objects, env)).to(device)
+        from . import _lib
+        lib = _lib.load()
+        H, W = self.shape
+        d_obj, d_env = torch.from_numpy(objects).to(device), torch.from_numpy(env).to(device)
+        out = torch.empty((len(groups), H, W), dtype=torch.float32, device=device)
+        _lib.check(lib.sted_structure_maps(d_obj.data_ptr(), d_env.data_ptr(), len(groups), H, W, out.data_ptr(),
+                                           torch.cuda.current_stream(device).cuda_stream))
+        return out
 
 
 FACTORS = {"synthetic": 1.0, "clusters": 2.25, "camkii": 2.25, "psd95": 2.25, "PSD95-Bassoon": 2.25, "actin": 3.0,

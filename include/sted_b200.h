@@ -396,6 +396,15 @@ uint64_t sted_synapse_scratch_bytes(int B, int H, int W);
 int sted_synapse_generate(const StedSynapseParams* prm, int B, int H, int W, uint64_t seed, uint64_t offset, int64_t env_base,
                           int32_t* frames_dev, int32_t* coords_dev, int32_t* counts_dev, int max_truth, void* scratch_dev,
                           void* stream);
+/* Procedural structure maps of the preference environments (PreferenceCountRateMOSTED-*): stand-in for
+ * DatamapGenerator (gym_sted/datamaps/datamap.py:68-152), whose U-Net datamaps are not shipped with the reference
+ * (defaults.py:6-13).  Per environment up to 24 objects combined by maximum, cut below 0.5, times the molecule count,
+ * floored, rotated by rot * 90 degrees (numpy.rot90; square maps) and flipped along rows / columns.
+ *   objects_dev : float64 [B][24][4]  filament: cos, sin, offset, width of exp(-d^2 / 2 width^2) with
+ *                 d = |x cos + y sin - offset + 3 sin(0.08 (y cos - x sin))|;  cluster: cy, cx, sigma, unused
+ *   env_dev     : float64 [B][6] = number of objects, molecule count, rot (0..3), flip rows, flip columns, 1 = filaments
+ *   maps_dev    : float32 [B][H][W] molecule counts (integer valued) */
+int sted_structure_maps(const double* objects_dev, const double* env_dev, int B, int H, int W, float* maps_dev, void* stream);
 /* Datamap.set_roi(i_ex, "max") (gym_sted/utils.py:179-180) for device-resident maps: roi_dev int32 or float32 [B][H][W]
  * -> padded_dev float32 [B][H+K-1][roundup4(W+K-1)] with the zero frame of K/2 pixels. */
 int sted_pad_maps(const void* roi_dev, int roi_is_int32, int B, int H, int W, int K, float* padded_dev, void* stream);

@@ -112,3 +112,26 @@ def test_pack_observation_casts_like_numpy():
     _lib.check(lib.sted_pack_observation(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), B, H, W, out.data_ptr(), None))
     want = np.stack(chans, axis=-1).astype(np.int64).astype(np.uint16)
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(96, 96), (64, 80)])
+def test_structure_maps_kernel_equals_the_numpy_rendering(shape):
+    """``sted_structure_maps`` (one thread per output pixel, rotation / flips undone analytically) against
+    ``SyntheticDatamapGenerator.render_numpy`` on the same drawn parameters.  Both evaluate the model in float64; libm
+    and CUDA ``exp`` / ``sin`` may differ in the last place, which can move ``floor`` by one molecule at a pixel sitting
+    exactly on a step - allowed for at most 1e-4 of the pixels, never by more than one."""
+    import torch
+    from gym_sted_b200 import envs
+    gen = envs.SyntheticDatamapGenerator(shape, seed=11)
+    groups = [gen.GROUPS[i % len(gen.GROUPS)] for i in range(64)]
+    objects, env = gen.draw_batch(groups)
+    want = gen.render_numpy(objects, env)
+    gen2 = envs.SyntheticDatamapGenerator(shape, seed=11)
+    got = gen2.batch(groups, "cuda:0").cpu().numpy()
+    assert got.shape == want.shape and got.dtype == np.float32
+    diff = np.abs(got - want)
+    assert diff.max() <= 1 and (diff > 0).mean() <= 1e-4, (diff.max(), (diff > 0).mean())
+    if shape[0] == shape[1]:
+        assert (env[:, 2] > 0).any() and (env[:, 3] > 0).any() and (env[:, 4] > 0).any()
+    torch.cuda.synchronize()
