@@ -421,6 +421,7 @@ class SyntheticDatamapGenerator:
     def __init__(self, shape=(96, 96), molecules=40, molecules_scale=0.1, seed=None):
         self.shape, self.molecules, self.molecules_scale = shape, molecules, molecules_scale
         self.rng = np.random.default_rng(seed)
+        self._pin = None
 
     def sample_group(self):
         return str(self.rng.choice(self.GROUPS))
@@ -520,8 +521,15 @@ class SyntheticDatamapGenerator:
         from . import _lib
         lib = _lib.load()
         H, W = self.shape
-        d_obj, d_env = torch.from_numpy(objects).to(device), torch.from_numpy(env).to(device)
-        out = torch.empty((len(groups), H, W), dtype=torch.float32, device=device)
+        B = len(groups)
+        no = B * self.NOBJ * 4
+        if self._pin is None or self._pin.numel() != no + B * 6:   # one pinned block: objects, then env
+            self._pin = torch.empty(no + B * 6, dtype=torch.float64, pin_memory=True)
+        self._pin.numpy()[:no] = objects.ravel()
+        self._pin.numpy()[no:] = env.ravel()
+        d_par = self._pin.to(device, non_blocking=True)        # the caller's step waits for its stream before the next draw
+        d_obj, d_env = d_par[:no], d_par[no:]
+        out = torch.empty((B, H, W), dtype=torch.float32, device=device)
         _lib.check(lib.sted_structure_maps(d_obj.data_ptr(), d_env.data_ptr(), len(groups), H, W, out.data_ptr(),
                                            torch.cuda.current_stream(device).cuda_stream))
         return out
@@ -574,7 +582,8 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         return (img, np.zeros((self.B, self.observation_space[1].shape[0]), dtype=np.float32)), {}
 
     def _new_datamaps(self):
-        """``_update_datamap`` (preference_sted_env.py:173-203) with the per-env count-rate loop."""
+        """``_update_datamap`` (preference_sted_env.py:173-203) with the per-env count-rate loop (first structures of an
+        episode only; afterwards the state image is queued with the kept tables of the lowered confocal powers)."""
         frames = self.datamap_generator.batch(self.groups, self.device)
         self.bm.set_datamaps(frames, max_molecules=self.B * self.H * self.W * self.datamap_generator.molecules)
         pdt = defaults.PDT
@@ -587,36 +596,64 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
                     break
                 p_ex = np.where(hot, p_ex * 0.75, p_ex)
             self.conf_p_ex = p_ex
-        state, _ = self.bm.get_signal_and_bleach(pdt, self.conf_p_ex, 0.0, bleach=False)
+            c = torch.tensor(np.stack([np.full(self.B, pdt), p_ex, np.zeros(self.B)]), dtype=torch.float64).to(self.device)
+            self._state_conf_d = (c[0], c[1], c[2])
+        state, _ = self.bm.get_signal_and_bleach(*self._state_conf_d, bleach=False, tables_key="state")
         return state
 
     def step(self, action):
+        """One step of B environments (preference_sted_env.py:262-323).  Like the contextual step it only QUEUES device
+        work - three acquisitions with kept confocal tables, objectives, the decorrelation chain, the peak count of the
+        STED image, the next structure maps and their state image, the uint16 observation - then makes one transfer into
+        pinned memory and waits once; the PrefNet score of the (B, 3) objectives is a 3-10-10-1 MLP on the host."""
         action = np.clip(np.asarray(action, dtype=np.float32).reshape(self.B, len(self.actions)),
                          self.action_space.low, self.action_space.high)
+        marks = [("start", time.perf_counter())] if self.step_timing else None
         pdt, p_ex, p_sted = self._full_action(action)
-        bm = self.bm
-        conf1, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)           # _acquire uses the DEFAULT confocal params
-        sted, _ = bm.get_signal_and_bleach(pdt, p_ex, p_sted, bleach=True)
-        conf2, _ = bm.get_signal_and_bleach(*self.conf, bleach=False)
+        bm, dev, B = self.bm, self.device, self.B
+        h_act = self._pinned("act", (3, B), torch.float64)
+        h_act.numpy()[:] = (pdt, p_ex, p_sted)
+        d_act = h_act.to(dev, non_blocking=True)
+        conf = self._conf_dev()                               # _acquire uses the DEFAULT confocal params
+        conf1, _ = bm.get_signal_and_bleach(*conf, bleach=False, tables_key="conf")
+        sted, _ = bm.get_signal_and_bleach(d_act[0], d_act[1], d_act[2], bleach=True)
+        res_d, res_done = rewards.resolution_launch(sted)     # side stream: beside conf2, objectives, the next structures
+        conf2, _ = bm.get_signal_and_bleach(*conf, bleach=False, tables_key="conf")
         bleached = bm.datamaps_roi().clone()
-        fg_s, fg_c, bleach_obj, snr, _ = rewards.foreground_objectives(conf1, sted, conf2)
-        res = rewards.resolution(sted)
-        mo_objs = np.stack([res, bleach_obj.cpu().numpy(), snr.cpu().numpy()], axis=1)
+        fg_s, fg_c, objs_d, oflags_d = rewards.foreground_objectives_device(conf1, sted, conf2)
+        peak_d = sted.amax(dim=(1, 2))
+        exhausted = self._exhausted()
+        state = self._new_datamaps()
+        obs_img = self._pack_observation(state, conf1, sted)
+        torch.cuda.current_stream(dev).wait_event(res_done)
+        host = {}
+        for name, t in (("res", res_d), ("objs", objs_d), ("oflags", oflags_d), ("peak", peak_d), ("img", obs_img)):
+            host[name] = self._pinned(name, t.shape, t.dtype)
+            host[name].copy_(t, non_blocking=True)
+        if marks:
+            marks.append(("queued", time.perf_counter()))
+        torch.cuda.current_stream(dev).synchronize()
+        if marks:
+            marks.append(("device_done", time.perf_counter()))
+        host = {k: v.numpy() for k, v in host.items()}
+        snr = np.where((host["oflags"] & 1) != 0, np.nan, host["objs"][:, 1])
+        mo_objs = np.stack([host["res"], host["objs"][:, 0], snr], axis=1)
         invalid = np.isnan(mo_objs).any(axis=1)
         if invalid.any() and self.on_invalid == "raise":
             raise TypeError("SNR objective is None (negative signal ratio): the reference fails here as well")
         scores, _, _ = self.articulator.articulate(np.nan_to_num(mo_objs), use_sigmoid=False)
         reward = np.where(invalid, np.nan, scores.ravel().astype(np.float64))
-        count_rate = sted.amax(dim=(1, 2)).cpu().numpy() / pdt
+        count_rate = host["peak"].astype(np.float64) / pdt
         reward = np.where(count_rate > self.max_count_rate, self.negative_reward, reward)
 
-        done = np.full(self.B, self.current_step >= self.max_episode_steps - 1) | self._exhausted()
+        done = np.full(B, self.current_step >= self.max_episode_steps - 1) | exhausted
         self.current_step += 1
         self.episode_memory["mo_objs"].append(mo_objs)
         self.episode_memory["actions"].append(action)
         self.episode_memory["reward"].append(reward)
-        info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2, "fg_c": fg_c,
-                "fg_s": fg_s, "mo_objs": mo_objs, "reward": reward, "sample": list(self.groups),
+        info = {"action": action, "bleached": bleached, "sted_image": sted, "conf1": conf1, "conf2": conf2,
+                "fg_c": fg_c.view(torch.bool), "fg_s": fg_s.view(torch.bool), "mo_objs": mo_objs, "reward": reward,
+                "sample": list(self.groups),
                 "conf_params": [{"pdt": defaults.PDT, "p_ex": float(p), "p_sted": 0.0} for p in self.conf_p_ex],
                 "invalid": invalid}
         obs = [(self.conf_p_ex / defaults.P_EX)[:, None]]
@@ -625,10 +662,12 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
             obs.append(self.obj_normalizer(mo) if self.normalize_observations else mo)
         obs = np.concatenate(obs, axis=1)
         obs = np.pad(obs, ((0, 0), (0, self.observation_space[1].shape[0] - obs.shape[1])))
-        state = self._new_datamaps()
         self.state = (state, conf1, sted)
-        img = self._pack_observation(state, conf1, sted).cpu().numpy()
-        return (img, obs.astype(np.float32)), reward, np.full(self.B, done), np.zeros(self.B, dtype=bool), info
+        img = host["img"].copy()
+        if marks:                                            # host seconds: queueing, waiting for the device, unpacking
+            marks.append(("end", time.perf_counter()))
+            info["timing"] = {b[0]: b[1] - a[1] for a, b in zip(marks, marks[1:])}
+        return (img, obs.astype(np.float32)), reward, done, np.zeros(B, dtype=bool), info
 
 
 # ids and kwargs of gym_sted/__init__.py:587-610,665-674 (Appendix C)

@@ -125,6 +125,20 @@ def resolution_device(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, 
     return res
 
 
+def resolution_launch(sted: torch.Tensor):
+    """``resolution_device`` queued on the side stream (it then runs beside whatever the caller queues next on its own
+    stream, e.g. ``objectives_kernel``); returns ``(res, done)``: wait for the event ``done`` before using ``res`` on
+    another stream, and keep ``sted`` alive until then."""
+    dev = sted.device
+    side = _SIDE_STREAMS.setdefault(str(dev), torch.cuda.Stream(dev))
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        res = resolution_device(sted)
+        done = torch.cuda.Event()
+        done.record(side)
+    return res, done
+
+
 def resolution(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, Nr=50, Ng=10, tol=0.0005) -> np.ndarray:
     """``resolution_device`` read back as a (B,) float64 numpy array."""
     return resolution_device(sted, pixelsize, res_cap, Nr, Ng, tol).cpu().numpy()

@@ -1,4 +1,4 @@
-"""Kernels launched by ONE VectorContextualMOSTED.step (torch.profiler / CUPTI): name, launches, device time."""
+"""Kernels launched by ONE vector env step (PROBE_ENV, default ContextualMOSTED-easy-hslb-v0) (torch.profiler / CUPTI): name, launches, device time."""
 import os
 import sys
 import numpy as np
@@ -9,7 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gym_sted_b200 import envs  # noqa: E402
 
 B = int(os.environ.get("PROBE_B", 256)); SIZE = int(os.environ.get("PROBE_HW", 64))
-vec = envs.make_vec("ContextualMOSTED-easy-hslb-v0", B, compute_f1=True, seed=0, image_size=SIZE)
+ENV = os.environ.get("PROBE_ENV", "ContextualMOSTED-easy-hslb-v0")
+vec = (envs.make_vec(ENV, B, seed=0) if ENV.startswith("Preference")
+       else envs.make_vec(ENV, B, compute_f1=True, seed=0, image_size=SIZE))
 vec.reset(seed=0)
 acts = np.random.default_rng(0).uniform(vec.action_space.low, vec.action_space.high, (B, 3)).astype(np.float32)
 for _ in range(3):

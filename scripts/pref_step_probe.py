@@ -19,3 +19,6 @@ ts = []
 for _ in range(10):
     t0 = time.perf_counter(); out = vec.step(acts); ts.append(time.perf_counter() - t0)
 print(f"step: median {np.median(ts) * 1e3:.2f} ms  min {min(ts) * 1e3:.2f}  mean reward {np.nanmean(out[1]):.3f}")
+vec.step_timing = True
+tt = [vec.step(acts)[4]["timing"] for _ in range(10)]
+print("host ms per phase (median): " + ", ".join(f"{k} {np.median([t[k] for t in tt]) * 1e3:.2f}" for k in tt[0]))
