@@ -670,6 +670,8 @@ def run_env_step(args, rank, local_rank, world):
     wall = time.perf_counter() - t0
     ms = max(e0.elapsed_time(e1), wall * 1e3)            # the host work of a step is part of the step
     clocks = sampler.stop()
+    if rank == 0:
+        print("env_step: host ms of every timed step: " + " ".join(f"{m:.1f}" for m in step_ms), file=sys.stderr)
     rewards_all = sted_dist.gather_rewards(torch.as_tensor(reward, dtype=torch.float32, device=dev), world * B) if world > 1 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

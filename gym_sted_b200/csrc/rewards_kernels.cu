@@ -238,9 +238,10 @@ extern "C" int sted_foreground_objectives(const float* conf1_dev, const float* s
 // =============================================================================================================
 namespace {
 
-constexpr int D_THREADS = 256;
+constexpr int D_THREADS = 512;         // 16 warps: the passes over the image are latency bound
 constexpr int D_MAXFG = 4096;        // foreground pixels per image (1 % of up to 640 x 640)
 constexpr int D_MAXPEAKS = 256;
+constexpr int D_SMEM_BYTES = D_MAXFG * (3 * (int)sizeof(int) + 2 * (int)sizeof(short));   // 64 KB
 
 __device__ __forceinline__ double gauss5(const double w0, const double w1, const double w2, const double xm2, const double xm1,
                                          const double x0, const double xp1, const double xp2) {
@@ -260,9 +261,14 @@ __global__ void __launch_bounds__(D_THREADS) nanodomain_kernel(const float* __re
     __shared__ long long s_rank;
     __shared__ int s_count, s_warp_off[D_THREADS / 32 + 1];
     __shared__ double s_min[D_THREADS / 32];
-    __shared__ int fg_idx[D_MAXFG];           // raster-ordered pixel indices of the mask
-    __shared__ short lab[D_MAXFG];            // component label of each mask pixel
-    __shared__ int s_nfg;
+    // short-list state of the labelling / peak picking (dynamic shared memory, D_SMEM_BYTES)
+    extern __shared__ __align__(16) unsigned char d_smem[];
+    int* fg_idx = reinterpret_cast<int*>(d_smem);                 // [D_MAXFG] raster-ordered pixel indices of the mask
+    int* csize = fg_idx + D_MAXFG;                                // [D_MAXFG] per root: size -> kept peaks -> output offset
+    int* clast = csize + D_MAXFG;                                 // [D_MAXFG] per root: list position of its last pixel
+    short* lab = reinterpret_cast<short*>(clast + D_MAXFG);       // [D_MAXFG] component label (= list position of its first pixel)
+    short* korder = lab + D_MAXFG;                                // [D_MAXFG] rank of a kept peak inside its component, else -1
+    __shared__ int s_nfg, s_flag, s_total;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = H * W;
     const float* img = sted + (size_t)b * N;
@@ -295,13 +301,21 @@ __global__ void __launch_bounds__(D_THREADS) nanodomain_kernel(const float* __re
     // ---- order statistic k0 by MSB-first radix select on the (non-negative) doubles' bit patterns
     if (tid == 0) { s_prefix = 0ull; s_rank = k0; }
     for (int shift = 56; shift >= 0; shift -= 8) {
-        hist[tid] = 0;
+        if (tid < 256) hist[tid] = 0;
         __syncthreads();
         const unsigned long long prefix = s_prefix;
         const unsigned long long himask = (shift == 56) ? 0ull : (~0ull << (shift + 8));
-        for (int i = tid; i < N; i += D_THREADS) {
-            const unsigned long long key = (unsigned long long)__double_as_longlong(f[i]);
-            if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
+        // lanes of a warp that hit the same bin add once (the high bytes of neighbouring pixels are nearly always equal:
+        // 32-way conflicts on one shared-memory word otherwise)
+        for (int base = 0; base < N; base += D_THREADS) {
+            const int i = base + tid;
+            unsigned int bin = 0xFFFFFFFFu;
+            if (i < N) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(f[i]);
+                if ((key & himask) == prefix) bin = (unsigned int)(key >> shift) & 0xFFu;
+            }
+            const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+            if (bin != 0xFFFFFFFFu && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned int)__popc(peers));
         }
         __syncthreads();
         if (tid == 0) {
@@ -356,59 +370,78 @@ __global__ void __launch_bounds__(D_THREADS) nanodomain_kernel(const float* __re
         }
         __syncthreads();
     }
-    if (tid != 0) return;
-
-    // ---- the rest is a short list: one thread
-    int flag = 0;
+    // ---- the rest runs on the short list of mask pixels (at most 1 % of the image), all threads
     int n = s_nfg;
-    if (n > D_MAXFG) { n = D_MAXFG; flag |= 1; }
-    auto find = [&](int pix) {                 // position of pixel in the sorted list, -1 if absent
-        int lo = 0, hi = n - 1;
-        while (lo <= hi) { const int mid = (lo + hi) >> 1; if (fg_idx[mid] == pix) return mid; if (fg_idx[mid] < pix) lo = mid + 1; else hi = mid - 1; }
-        return -1;
+    if (tid == 0) { s_flag = n > D_MAXFG ? 1 : 0; s_total = 0; }
+    n = min(n, D_MAXFG);
+    auto lower = [&](int pix) {                // first list position whose pixel index is >= pix
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (fg_idx[mid] < pix) lo = mid + 1; else hi = mid; }
+        return lo;
     };
-    // 8-connected components: union-find through the backward neighbours (W, NW, N, NE)
-    for (int i = 0; i < n; ++i) lab[i] = (short)i;
-    auto root = [&](int i) { while (lab[i] != i) { lab[i] = lab[lab[i]]; i = lab[i]; } return i; };
-    for (int i = 0; i < n; ++i) {
-        const int y = fg_idx[i] / W, x = fg_idx[i] - y * W;
-        const int nb[4][2] = {{0, -1}, {-1, -1}, {-1, 0}, {-1, 1}};
-        for (int k = 0; k < 4; ++k) {
-            const int yy = y + nb[k][0], xx = x + nb[k][1];
-            if (yy < 0 || xx < 0 || xx >= W) continue;
-            const int j = find(yy * W + xx);
-            if (j < 0) continue;
-            const int ri = root(i), rj = root(j);
-            if (ri != rj) { if (ri < rj) lab[rj] = (short)ri; else lab[ri] = (short)rj; }
-        }
-    }
-    for (int i = 0; i < n; ++i) lab[i] = (short)root(i);        // root = first (raster) pixel of the component
-    // remove_small_objects(min_size=4): mark pixels of small components with -1
-    for (int i = 0; i < n; ++i) {
-        if (lab[i] != i) continue;
-        int size = 0;
-        for (int j = i; j < n; ++j) size += (lab[j] == i);
-        if (size < 4) for (int j = i; j < n; ++j) if (lab[j] == i) lab[j] = -1;
-    }
-    // per component (in order of first pixel = measure.label numbering): local maxima, spacing, output
-    int np_out = 0;
-    int* out = peaks + (size_t)b * D_MAXPEAKS * 2;
-    for (int c = 0; c < n; ++c) {
-        if (lab[c] != c) continue;
-        // candidates: value equals the 5x5 maximum over the component (other pixels are -DBL_MAX) and exceeds the image minimum
-        int cand[64], nc = 0, size = 0, npk = 0;
-        for (int i = c; i < n; ++i) {
-            if (lab[i] != c) continue;
-            ++size;
+    auto find = [&](int pix) {                 // position of pixel in the sorted list, -1 if absent
+        const int k = lower(pix);
+        return (k < n && fg_idx[k] == pix) ? k : -1;
+    };
+    // 8-connected components (measure.label / remove_small_objects, connectivity 2): every pixel pulls the smallest
+    // label of its 3x3 neighbourhood and then jumps to that label's label, until nothing changes.  The fixed point is
+    // the list position of the component's first pixel in raster order - the root the sequential union-find (smaller
+    // root wins) arrives at - whatever the interleaving of the threads: labels only decrease and stay inside the component.
+    for (int i = tid; i < n; i += D_THREADS) { lab[i] = (short)i; csize[i] = 0; clast[i] = 0; korder[i] = -1; }
+    __syncthreads();
+    for (;;) {
+        bool changed = false;
+        for (int i = tid; i < n; i += D_THREADS) {
             const int y = fg_idx[i] / W, x = fg_idx[i] - y * W;
-            const double v = f[fg_idx[i]];
-            bool is_max = true;
-            for (int j = c; j < n && is_max; ++j) {
-                if (lab[j] != c) continue;
-                const int yj = fg_idx[j] / W, xj = fg_idx[j] - yj * W;
-                if (abs(yj - y) <= 2 && abs(xj - x) <= 2 && f[fg_idx[j]] > v) is_max = false;
+            const int xa = max(x - 1, 0), xb = min(x + 1, W - 1);
+            int m = lab[i];
+            for (int yy = max(y - 1, 0); yy <= min(y + 1, H - 1); ++yy) {
+                const int pb = yy * W + xb;
+                for (int k = lower(yy * W + xa); k < n && fg_idx[k] <= pb; ++k) m = min(m, (int)lab[k]);
             }
-            if (is_max) { ++npk; if (v > vmin) { if (nc < 64) cand[nc++] = i; else flag |= 2; } }
+            m = min(m, (int)lab[m]);
+            if (m < lab[i]) { lab[i] = (short)m; changed = true; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    for (int i = tid; i < n; i += D_THREADS) { atomicAdd(&csize[lab[i]], 1); atomicMax(&clast[lab[i]], i); }
+    __syncthreads();
+    // remove_small_objects(min_size=4): pixels of small components get the label -1
+    for (int i = tid; i < n; i += D_THREADS) if ((csize[lab[i]] & 0xFFFF) < 4) korder[i] = -2;
+    __syncthreads();
+    for (int i = tid; i < n; i += D_THREADS) if (korder[i] == -2) { lab[i] = -1; korder[i] = -1; }
+    __syncthreads();
+    // local maxima (peak_local_max inside one label): a pixel is a maximum when no pixel of ITS component within the 5x5
+    // window is brighter.  One thread per mask pixel; the window's rows are short runs of the raster-ordered list.
+    // csize[root]: size in the low 16 bits, number of maxima in the high 16; korder = -3 marks a candidate
+    // (a maximum above the image minimum).
+    for (int i = tid; i < n; i += D_THREADS) {
+        const int c = lab[i];
+        if (c < 0) continue;
+        const int y = fg_idx[i] / W, x = fg_idx[i] - y * W;
+        const int xa = max(x - 2, 0), xb = min(x + 2, W - 1);
+        const double v = f[fg_idx[i]];
+        bool is_max = true;
+        for (int yy = max(y - 2, 0); yy <= min(y + 2, H - 1) && is_max; ++yy) {
+            const int pb = yy * W + xb;
+            for (int k = lower(yy * W + xa); k < n && fg_idx[k] <= pb; ++k)
+                if (lab[k] == c && f[fg_idx[k]] > v) { is_max = false; break; }
+        }
+        if (is_max) { atomicAdd(&csize[c], 1 << 16); if (v > vmin) korder[i] = -3; }
+    }
+    __syncthreads();
+    // per component: candidates in raster order, spacing.  One thread per component; its pixels lie between its first and
+    // its last list position, a short range because the list is in raster order.
+    for (int c = tid; c < n; c += D_THREADS) {
+        if (lab[c] != c) continue;
+        const int last = clast[c];
+        const int size = csize[c] & 0xFFFF, npk = csize[c] >> 16;
+        int flag = 0;
+        int cand[64], nc = 0;
+        for (int i = c; i <= last; ++i) {
+            if (lab[i] != c || korder[i] != -3) continue;
+            korder[i] = -1;
+            if (nc < 64) cand[nc++] = i; else flag |= 2;
         }
         if (npk == size && size > 1) {
             // "trivial image": every pixel of the component is a maximum (all values equal).  skimage then keeps only
@@ -422,7 +455,7 @@ __global__ void __launch_bounds__(D_THREADS) nanodomain_kernel(const float* __re
             auto eroded = [&](int y, int x) {
                 return member(y, x) && member(y - 1, x) && member(y + 1, x) && member(y, x - 1) && member(y, x + 1);
             };
-            for (int i = c; i < n; ++i) {
+            for (int i = c; i <= last; ++i) {
                 if (lab[i] != c) continue;
                 const int y = fg_idx[i] / W, x = fg_idx[i] - y * W;
                 const bool opened = eroded(y, x) || eroded(y - 1, x) || eroded(y + 1, x) || eroded(y, x - 1) || eroded(y, x + 1);
@@ -446,17 +479,37 @@ __global__ void __launch_bounds__(D_THREADS) nanodomain_kernel(const float* __re
                 const int yk = fg_idx[kept[k]] / W, xk = fg_idx[kept[k]] - yk * W;
                 if (max(abs(yk - y), abs(xk - x)) < 2) ok = false;
             }
-            if (ok) kept[nk++] = cand[i];
+            if (ok) { korder[cand[i]] = (short)nk; kept[nk++] = cand[i]; }
         }
-        for (int k = 0; k < nk; ++k) {
-            if (np_out >= D_MAXPEAKS) { flag |= 8; break; }
-            out[2 * np_out] = fg_idx[kept[k]] / W;
-            out[2 * np_out + 1] = fg_idx[kept[k]] % W;
-            ++np_out;
-        }
+        csize[c] = nk;
+        if (flag) atomicOr(&s_flag, flag);
     }
-    npeaks[b] = np_out;
-    flags[b] = flag;
+    __syncthreads();
+    // output offsets: components in order of their first pixel (= measure.label numbering); exclusive scan by warp 0
+    if (warp == 0) {
+        int carry = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool is_root = i < n && lab[i] == i;
+            const int v = is_root ? csize[i] : 0;
+            int incl = v;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (is_root) csize[i] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_total = carry;
+    }
+    __syncthreads();
+    int* out = peaks + (size_t)b * D_MAXPEAKS * 2;
+    for (int i = tid; i < n; i += D_THREADS) {
+        if (korder[i] < 0) continue;
+        const int pos = csize[lab[i]] + korder[i];
+        if (pos < D_MAXPEAKS) { out[2 * pos] = fg_idx[i] / W; out[2 * pos + 1] = fg_idx[i] % W; }
+    }
+    if (tid == 0) {
+        npeaks[b] = min(s_total, D_MAXPEAKS);
+        flags[b] = s_flag | (s_total > D_MAXPEAKS ? 8 : 0);
+    }
 }
 
 }  // namespace
@@ -471,7 +524,8 @@ extern "C" int sted_nanodomain_candidates(const float* sted_dev, int B, int H, i
     int rc = check_device();
     if (rc) return rc;
     const size_t n = (size_t)B * H * W;
-    nanodomain_kernel<<<B, D_THREADS, 0, (cudaStream_t)stream>>>(sted_dev, H, W, weights[0], weights[1], weights[2], k0, gamma,
+    CUDA_TRY(cudaFuncSetAttribute(nanodomain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM_BYTES));
+    nanodomain_kernel<<<B, D_THREADS, D_SMEM_BYTES, (cudaStream_t)stream>>>(sted_dev, H, W, weights[0], weights[1], weights[2], k0, gamma,
                                                                  scratch_dev, scratch_dev + n, peaks_dev, npeaks_dev, flags_dev);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
@@ -493,12 +547,14 @@ namespace {
 
 constexpr int DC_NR = 50, DC_NG = 10, DC_THREADS = 512;
 
+constexpr int DC_NS = DC_NG + 1;          // high-pass sigmas handled by one sweep over the spectrum
+
 struct DecorrShared {
     int bounds[DC_NR];
-    double ring_num[DC_NR + 1], ring_abs[DC_NR + 1], ring_pow[DC_NR + 1];
-    double d[DC_NR], r[DC_NR], r_fine[DC_NR], sigmas[DC_NG + 1], sig_fine[DC_NG], rs[2 * DC_NG + 3], As[2 * DC_NG + 3];
-    int idx;
-    double A;
+    double ring_num[DC_NS][DC_NR + 1], ring_pow[DC_NS][DC_NR + 1], ring_abs[DC_NR + 1];
+    double d[DC_NS][DC_NR], r[DC_NR], r_fine[DC_NR], sigmas[DC_NG + 1], sig_fine[DC_NG], rs[2 * DC_NG + 3], As[2 * DC_NG + 3];
+    int idx[DC_NS];
+    double A[DC_NS];
 };
 
 __device__ void dc_linspace(double a, double b, int n, double* out) {            // numpy.linspace(a, b, n)
@@ -542,53 +598,77 @@ __device__ void dc_bounds(DecorrShared& sh, const double* __restrict__ R, int N,
     __syncthreads();
 }
 
-__device__ void dc_pass(DecorrShared& sh, const double2* __restrict__ Ik, const double2* __restrict__ Ikn,
-                        const double* __restrict__ R2, int n_inside, bool filtered, double sigma, double tol) {
+// One sweep over the radius-sorted spectrum for NS high-pass sigmas at once (sigma == 0: no filter).  The decorrelation
+// curves of the sigmas of one stage do not depend on each other, so the 1 + 11 + 10 passes of the reference become three
+// sweeps: a pixel is loaded once and weighted NS times.  Per sigma the additions are those of a pass of its own, in the
+// same order - lanes striding the ring, the same shuffle tree, the running sums in numpy's order - so the curves are
+// bit-identical to the pass-per-sigma form.
+template <int NS>
+__device__ void dc_sweep(DecorrShared& sh, const double2* __restrict__ Ik, const double2* __restrict__ Ikn,
+                         const double* __restrict__ R2, int n_inside, const double* sig, double tol) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const double c = -2.0 * (sigma * sigma);
+    double c[NS];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) { c[j] = -2.0 * (sig[j] * sig[j]); any |= sig[j] != 0.0; }
     for (int ring = warp; ring <= DC_NR; ring += DC_THREADS / 32) {
         const int lo = ring == 0 ? 0 : min(sh.bounds[ring - 1], n_inside);
         const int hi = ring < DC_NR ? min(sh.bounds[ring], n_inside) : n_inside;
-        double sn = 0.0, sa = 0.0, sp = 0.0;
+        double sn[NS], sp[NS], sa = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) sn[j] = sp[j] = 0.0;
         for (int p = lo + lane; p < hi; p += 32) {
-            double2 a = Ik[p];
+            const double2 a0 = Ik[p];
             const double2 b = Ikn[p];
-            if (filtered) { const double f = 1.0 - exp(c * R2[p]); a.x *= f; a.y *= f; }
-            sn += a.x * b.x + a.y * b.y;
-            sp += a.x * a.x + a.y * a.y;
+            const double r2 = any ? R2[p] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                double2 a = a0;
+                if (sig[j] != 0.0) { const double f = 1.0 - exp(c[j] * r2); a.x *= f; a.y *= f; }
+                sn[j] += a.x * b.x + a.y * b.y;
+                sp[j] += a.x * a.x + a.y * a.y;
+            }
             sa += b.x * b.x + b.y * b.y;
         }
         for (int o = 16; o; o >>= 1) {
-            sn += __shfl_xor_sync(0xffffffffu, sn, o);
-            sp += __shfl_xor_sync(0xffffffffu, sp, o);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                sn[j] += __shfl_xor_sync(0xffffffffu, sn[j], o);
+                sp[j] += __shfl_xor_sync(0xffffffffu, sp[j], o);
+            }
             sa += __shfl_xor_sync(0xffffffffu, sa, o);
         }
-        if (lane == 0) { sh.ring_num[ring] = sn; sh.ring_pow[ring] = sp; sh.ring_abs[ring] = sa; }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) { sh.ring_num[j][ring] = sn[j]; sh.ring_pow[j][ring] = sp[j]; }
+            sh.ring_abs[ring] = sa;
+        }
     }
     __syncthreads();
-    // the curve d(r_i) and its peak: the running sums keep numpy's order (one thread, 150 additions); the divisions, square
-    // roots and the peak search - O(n^2) comparisons in the reference's loop - are spread over the lanes of warp 0
-    if (threadIdx.x == 0) {
+    // the curves d(r_i) and their peaks: the running sums keep numpy's order (one thread per sigma, 150 additions); the
+    // divisions, square roots and the peak searches - O(n^2) comparisons in the reference's loop - are spread over the CTA
+    if (threadIdx.x < NS) {
+        const int j = threadIdx.x;
         double denom2 = 0.0;
-        for (int i = 0; i <= DC_NR; ++i) denom2 += sh.ring_pow[i];
+        for (int i = 0; i <= DC_NR; ++i) denom2 += sh.ring_pow[j][i];
         double cn = 0.0, ca = 0.0;
         for (int i = 0; i < DC_NR; ++i) {
-            cn += sh.ring_num[i];
+            cn += sh.ring_num[j][i];
             ca += sh.ring_abs[i];
-            sh.ring_num[i] = cn;                         // in place: cumulative numerator, cumulative |Ikn|^2 * total power
-            sh.ring_abs[i] = ca * denom2;
+            sh.ring_num[j][i] = cn;                      // in place: cumulative numerator, cumulative |Ikn|^2 * total power
+            sh.ring_pow[j][i] = ca * denom2;
         }
     }
     __syncthreads();
-    if (threadIdx.x < 64) {
-        for (int i = threadIdx.x; i < DC_NR; i += 64) {
-            double v = sh.ring_num[i] / sqrt(sh.ring_abs[i]);
-            v = floor(1000.0 * v) / 1000.0;
-            sh.d[i] = isnan(v) ? 0.0 : v;
-        }
+    for (int t = threadIdx.x; t < NS * DC_NR; t += DC_THREADS) {
+        const int j = t / DC_NR, i = t - j * DC_NR;
+        double v = sh.ring_num[j][i] / sqrt(sh.ring_pow[j][i]);
+        v = floor(1000.0 * v) / 1000.0;
+        sh.d[j][i] = isnan(v) ? 0.0 : v;
     }
     __syncthreads();
-    if (threadIdx.x < 32) dc_peak_warp(sh.d, tol, &sh.idx, &sh.A);
+    static_assert(NS <= DC_THREADS / 32, "one warp per sigma for the peak search");
+    if (warp < NS) dc_peak_warp(sh.d[warp], tol, &sh.idx[warp], &sh.A[warp]);
     __syncthreads();
 }
 
@@ -603,11 +683,13 @@ __global__ void __launch_bounds__(DC_THREADS) decorr_kernel(const double2* __res
     if (threadIdx.x < DC_NR) sh.r[threadIdx.x] = r_coarse[threadIdx.x];
     __syncthreads();
     dc_bounds(sh, R, N, sh.r);
-    dc_pass(sh, Ik, Ikn, R2, n_inside, false, 0.0, tol);
+    if (threadIdx.x == 0) sh.sigmas[0] = 0.0;
+    __syncthreads();
+    dc_sweep<1>(sh, Ik, Ikn, R2, n_inside, sh.sigmas, tol);
     if (threadIdx.x == 0) {
-        const double r0 = sh.r[sh.idx];
+        const double r0 = sh.r[sh.idx[0]];
         sh.rs[0] = r0;
-        sh.As[0] = sh.A;
+        sh.As[0] = sh.A[0];
         double g_max = 2.0 / r0;
         if (isinf(g_max)) g_max = gmax_flat;
         sh.sigmas[0] = sigma0;
@@ -615,12 +697,9 @@ __global__ void __launch_bounds__(DC_THREADS) decorr_kernel(const double2* __res
         for (int j = 1; j <= DC_NG; ++j) sh.sigmas[j] = exp(sh.sigmas[j]);
     }
     __syncthreads();
-    for (int j = 0; j <= DC_NG; ++j) {
-        dc_pass(sh, Ik, Ikn, R2, n_inside, sh.sigmas[j] != 0.0, sh.sigmas[j], tol);
-        if (threadIdx.x == 0) { sh.rs[1 + j] = sh.r[sh.idx]; sh.As[1 + j] = sh.A; }
-    }
-    __syncthreads();
+    dc_sweep<DC_NG + 1>(sh, Ik, Ikn, R2, n_inside, sh.sigmas, tol);
     if (threadIdx.x == 0) {
+        for (int j = 0; j <= DC_NG; ++j) { sh.rs[1 + j] = sh.r[sh.idx[j]]; sh.As[1 + j] = sh.A[j]; }
         const int n = DC_NG + 2;
         double mx = sh.rs[0];
         for (int i = 1; i < n; ++i) mx = fmax(mx, sh.rs[i]);
@@ -633,11 +712,10 @@ __global__ void __launch_bounds__(DC_THREADS) decorr_kernel(const double2* __res
     }
     __syncthreads();
     dc_bounds(sh, R, N, sh.r_fine);
-    for (int j = 0; j < DC_NG; ++j) {
-        dc_pass(sh, Ik, Ikn, R2, n_inside, sh.sig_fine[j] != 0.0, sh.sig_fine[j], tol);
-        // the last coarse entry (index DC_NG+1) is dropped by the reference before the refined ones are appended
-        if (threadIdx.x == 0) { sh.rs[DC_NG + 1 + j] = sh.r_fine[sh.idx]; sh.As[DC_NG + 1 + j] = sh.A; }
-    }
+    dc_sweep<DC_NG>(sh, Ik, Ikn, R2, n_inside, sh.sig_fine, tol);
+    // the last coarse entry (index DC_NG+1) is dropped by the reference before the refined ones are appended
+    if (threadIdx.x == 0)
+        for (int j = 0; j < DC_NG; ++j) { sh.rs[DC_NG + 1 + j] = sh.r_fine[sh.idx[j]]; sh.As[DC_NG + 1 + j] = sh.A[j]; }
     if (threadIdx.x == 0) {
         const int n = 2 * DC_NG + 2;
         sh.rs[n - 1] = sh.rs[0];

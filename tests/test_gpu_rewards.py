@@ -385,6 +385,62 @@ def test_flat_components_follow_skimage_isolated_pixel_rule():
     assert n > 0
 
 
+def test_long_and_interleaved_components_label_like_skimage():
+    """The detector labels the mask by parallel minimum-label propagation: long winding components (many propagation
+    rounds), components whose raster ranges interleave, diagonal-only (8-connected) links and more than 256 threads'
+    worth of mask pixels, non-square images - peak coordinates and their order against the oracle."""
+    _gpu()
+    rng = np.random.default_rng(17)
+    imgs = []
+    H, W = 160, 224
+    snake = rng.poisson(0.2, (H, W)).astype(np.int64)
+    y, x = 10, 5
+    for k in range(330):                                   # a one-pixel-wide staircase / zig-zag across the image
+        snake[y, x] = 200 + (k * 37) % 90
+        if k % 3 == 0:
+            y += 1 if (k // 60) % 2 == 0 else -1
+            y = min(max(y, 2), H - 3)
+        x = min(x + (1 if k % 3 else 0) + (1 if k % 7 == 0 else 0), W - 2) if k % 3 else x
+    imgs.append(snake)
+    combs = rng.poisson(0.2, (H, W)).astype(np.int64)      # two interleaved combs: raster ranges of the components overlap
+    combs[20, 20:200] = 300; combs[60, 20:200] = 280
+    for c in range(24, 200, 8):
+        combs[20:38, c] = 250 + c % 40
+        combs[43:60, c + 4] = 240 + c % 30
+    imgs.append(combs)
+    diag = rng.poisson(0.2, (H, W)).astype(np.int64)       # diagonal chains: connected only through corners
+    for k in range(120):
+        diag[15 + k, 30 + k] = 150 + (k * 13) % 50
+        diag[140 - k, 60 + k] = 170 + (k * 11) % 60
+    imgs.append(diag)
+    got = rewards.nanodomain_candidates(torch.from_numpy(np.stack(imgs)).float().cuda())
+    n = 0
+    for g, img in zip(got, imgs):
+        ref = ro.candidate_peaks(img).reshape(-1, 2)
+        assert np.array_equal(g, ref), (g, ref)
+        n += len(ref)
+    assert n >= 6
+
+
+def test_resolution_at_the_metric_size_matches_oracle():
+    """256 x 256 (BASELINE metric size): the three fused decorrelation sweeps against the oracle's 22 passes."""
+    _gpu()
+    rng = np.random.default_rng(8)
+    yy, xx = np.mgrid[:256, :256]
+    imgs = []
+    for s in (1.2, 2.5, 5.0):
+        img = np.zeros((256, 256))
+        for _ in range(120):
+            y, x = rng.uniform(10, 246, 2)
+            img += 60 * np.exp(-((yy - y) ** 2 + (xx - x) ** 2) / (2 * s ** 2))
+        imgs.append(rng.poisson(img + 0.2))
+    imgs.append(np.zeros((256, 256), dtype=np.int64))              # empty image: capped resolution
+    got = rewards.resolution(torch.from_numpy(np.stack(imgs)).to(torch.float32).cuda())
+    ref = np.array([ro.resolution(i) for i in imgs])
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    assert got[0] < got[1] < got[2] <= 300
+
+
 def test_detection_capacity_overflow_is_an_error_not_a_fallback():
     _gpu()
     from gym_sted_b200 import _lib
