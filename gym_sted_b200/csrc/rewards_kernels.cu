@@ -548,6 +548,7 @@ namespace {
 constexpr int DC_NR = 50, DC_NG = 10, DC_THREADS = 512;
 
 constexpr int DC_NS = DC_NG + 1;          // high-pass sigmas handled by one sweep over the spectrum
+constexpr int DC_MAXU = 152, DC_CUTS = 96, DC_MIN_CHUNK = 1024;   // units <= rings + cuts
 
 struct DecorrShared {
     int bounds[DC_NR];
@@ -555,6 +556,12 @@ struct DecorrShared {
     double d[DC_NS][DC_NR], r[DC_NR], r_fine[DC_NR], sigmas[DC_NG + 1], sig_fine[DC_NG], rs[2 * DC_NG + 3], As[2 * DC_NG + 3];
     int idx[DC_NS];
     double A[DC_NS];
+    // work units of a sweep: (ring, run of at most `chunk` radius-sorted pixels); a ring longer than a chunk is cut so that
+    // the warps finish together (the first and the last ring of the refined radii hold most of the spectrum)
+    int n_units, next_unit;
+    int unit_lo[DC_MAXU], unit_hi[DC_MAXU];
+    short ring_u0[DC_NR + 2];                  // first unit of every ring (ring_u0[ring + 1] = one past its last)
+    double part_num[DC_NS][DC_MAXU], part_pow[DC_NS][DC_MAXU], part_abs[DC_MAXU];
 };
 
 __device__ void dc_linspace(double a, double b, int n, double* out) {            // numpy.linspace(a, b, n)
@@ -588,12 +595,26 @@ __device__ void dc_peak_warp(const double* d, double tol, int* idx_out, double* 
     if (lane == 0) { *idx_out = idx; *A_out = d[idx]; }
 }
 
-__device__ void dc_bounds(DecorrShared& sh, const double* __restrict__ R, int N, const double* radii) {
+__device__ void dc_bounds(DecorrShared& sh, const double* __restrict__ R, int N, int n_inside, const double* radii) {
     if (threadIdx.x < DC_NR) {                 // numpy.searchsorted(R_sorted, r, 'left') = number of pixels with R < r
         const double r = radii[threadIdx.x];
         int lo = 0, hi = N;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (R[mid] < r) lo = mid + 1; else hi = mid; }
         sh.bounds[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int chunk = (n_inside + DC_CUTS - 1) / DC_CUTS;
+        chunk = max(DC_MIN_CHUNK, (chunk + 31) & ~31);
+        int u = 0;
+        for (int ring = 0; ring <= DC_NR; ++ring) {
+            const int lo = ring == 0 ? 0 : min(sh.bounds[ring - 1], n_inside);
+            const int hi = ring < DC_NR ? min(sh.bounds[ring], n_inside) : n_inside;
+            sh.ring_u0[ring] = (short)u;
+            for (int s0 = lo; s0 < hi; s0 += chunk) { sh.unit_lo[u] = s0; sh.unit_hi[u] = min(s0 + chunk, hi); ++u; }
+        }
+        sh.ring_u0[DC_NR + 1] = (short)u;
+        sh.n_units = u;
     }
     __syncthreads();
 }
@@ -602,7 +623,7 @@ __device__ void dc_bounds(DecorrShared& sh, const double* __restrict__ R, int N,
 // curves of the sigmas of one stage do not depend on each other, so the 1 + 11 + 10 passes of the reference become three
 // sweeps: a pixel is loaded once and weighted NS times.  Per sigma the additions are those of a pass of its own, in the
 // same order - lanes striding the ring, the same shuffle tree, the running sums in numpy's order - so the curves are
-// bit-identical to the pass-per-sigma form.
+// bit-identical to the pass-per-sigma form (a ring cut into several units is summed unit by unit, in order).
 template <int NS>
 __device__ void dc_sweep(DecorrShared& sh, const double2* __restrict__ Ik, const double2* __restrict__ Ikn,
                          const double* __restrict__ R2, int n_inside, const double* sig, double tol) {
@@ -611,9 +632,14 @@ __device__ void dc_sweep(DecorrShared& sh, const double2* __restrict__ Ik, const
     bool any = false;
 #pragma unroll
     for (int j = 0; j < NS; ++j) { c[j] = -2.0 * (sig[j] * sig[j]); any |= sig[j] != 0.0; }
-    for (int ring = warp; ring <= DC_NR; ring += DC_THREADS / 32) {
-        const int lo = ring == 0 ? 0 : min(sh.bounds[ring - 1], n_inside);
-        const int hi = ring < DC_NR ? min(sh.bounds[ring], n_inside) : n_inside;
+    if (threadIdx.x == 0) sh.next_unit = 0;
+    __syncthreads();
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(&sh.next_unit, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= sh.n_units) break;
+        const int lo = sh.unit_lo[u], hi = sh.unit_hi[u];
         double sn[NS], sp[NS], sa = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; ++j) sn[j] = sp[j] = 0.0;
@@ -640,9 +666,18 @@ __device__ void dc_sweep(DecorrShared& sh, const double2* __restrict__ Ik, const
         }
         if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < NS; ++j) { sh.ring_num[j][ring] = sn[j]; sh.ring_pow[j][ring] = sp[j]; }
-            sh.ring_abs[ring] = sa;
+            for (int j = 0; j < NS; ++j) { sh.part_num[j][u] = sn[j]; sh.part_pow[j][u] = sp[j]; }
+            sh.part_abs[u] = sa;
         }
+    }
+    __syncthreads();
+    // ring sums: the units of a ring in order (which warp computed a unit does not matter: the sums are deterministic)
+    for (int t = threadIdx.x; t < (2 * NS + 1) * (DC_NR + 1); t += DC_THREADS) {
+        const int q = t / (DC_NR + 1), ring = t - q * (DC_NR + 1);
+        const double* part = q < NS ? sh.part_num[q] : (q < 2 * NS ? sh.part_pow[q - NS] : sh.part_abs);
+        double v = 0.0;
+        for (int u = sh.ring_u0[ring]; u < sh.ring_u0[ring + 1]; ++u) v += part[u];
+        if (q < NS) sh.ring_num[q][ring] = v; else if (q < 2 * NS) sh.ring_pow[q - NS][ring] = v; else sh.ring_abs[ring] = v;
     }
     __syncthreads();
     // the curves d(r_i) and their peaks: the running sums keep numpy's order (one thread per sigma, 150 additions); the
@@ -682,7 +717,7 @@ __global__ void __launch_bounds__(DC_THREADS) decorr_kernel(const double2* __res
     const double2* Ikn = Ikn_all + (size_t)blockIdx.x * N;
     if (threadIdx.x < DC_NR) sh.r[threadIdx.x] = r_coarse[threadIdx.x];
     __syncthreads();
-    dc_bounds(sh, R, N, sh.r);
+    dc_bounds(sh, R, N, n_inside, sh.r);
     if (threadIdx.x == 0) sh.sigmas[0] = 0.0;
     __syncthreads();
     dc_sweep<1>(sh, Ik, Ikn, R2, n_inside, sh.sigmas, tol);
@@ -711,7 +746,7 @@ __global__ void __launch_bounds__(DC_THREADS) decorr_kernel(const double2* __res
         for (int j = 0; j < DC_NG; ++j) sh.sig_fine[j] = exp(sh.sig_fine[j]);
     }
     __syncthreads();
-    dc_bounds(sh, R, N, sh.r_fine);
+    dc_bounds(sh, R, N, n_inside, sh.r_fine);
     dc_sweep<DC_NG>(sh, Ik, Ikn, R2, n_inside, sh.sig_fine, tol);
     // the last coarse entry (index DC_NG+1) is dropped by the reference before the refined ones are appended
     if (threadIdx.x == 0)
