@@ -920,69 +920,89 @@ namespace {
 
 constexpr int F1_MAXN = 512;         // truths and kept guesses per image
 
-__global__ void __launch_bounds__(32) f1_match_kernel(const int* __restrict__ peaks, const int* __restrict__ npeaks,
-                                                       const unsigned char* __restrict__ valid, int maxp,
-                                                       const int* __restrict__ truth, const int* __restrict__ ntruth, int maxt,
-                                                       double thr2, int* __restrict__ counts, double* __restrict__ f1,
-                                                       int* __restrict__ flags) {
+constexpr int F1_THREADS = 128, F1_ADJ = 8;
+
+__global__ void __launch_bounds__(F1_THREADS) f1_match_kernel(const int* __restrict__ peaks, const int* __restrict__ npeaks,
+                                                               const unsigned char* __restrict__ valid, int maxp,
+                                                               const int* __restrict__ truth, const int* __restrict__ ntruth, int maxt,
+                                                               double thr2, int* __restrict__ counts, double* __restrict__ f1,
+                                                               int* __restrict__ flags) {
     __shared__ short gy[F1_MAXN], gx[F1_MAXN], ty[F1_MAXN], tx[F1_MAXN];
     __shared__ short match_g[F1_MAXN];               // truth matched to guess g, -1 if free
     __shared__ short stack_t[F1_MAXN], stack_j[F1_MAXN], stack_g[F1_MAXN];
+    __shared__ short adj[F1_MAXN][F1_ADJ];           // the guesses within the threshold of truth t, ascending
+    __shared__ unsigned char adjn[F1_MAXN];          // how many (255: more than F1_ADJ, scan all guesses instead)
     __shared__ unsigned visited[F1_MAXN / 32];
     __shared__ int s_ng;
-    const int b = blockIdx.x, lane = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int np_ = min(npeaks[b], maxp), nt = min(ntruth[b], maxt);
-    // compact the kept guesses (order preserved: warp-wide ballots)
-    if (lane == 0) s_ng = 0;
-    __syncwarp();
+    // compact the kept guesses (order preserved: warp-wide ballots, warp 0)
+    if (tid == 0) s_ng = 0;
+    __syncthreads();
     bool overflow = nt > F1_MAXN;
-    for (int base = 0; base < np_; base += 32) {
-        const int k = base + lane;
-        const bool keep = k < np_ && (!valid || valid[(size_t)b * maxp + k]);
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        const int at = s_ng + __popc(m & ((1u << lane) - 1));
-        if (keep && at < F1_MAXN) {
-            gy[at] = (short)peaks[((size_t)b * maxp + k) * 2];
-            gx[at] = (short)peaks[((size_t)b * maxp + k) * 2 + 1];
+    if (tid < 32) {
+        for (int base = 0; base < np_; base += 32) {
+            const int k = base + lane;
+            const bool keep = k < np_ && (!valid || valid[(size_t)b * maxp + k]);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            const int at = s_ng + __popc(m & ((1u << lane) - 1));
+            if (keep && at < F1_MAXN) {
+                gy[at] = (short)peaks[((size_t)b * maxp + k) * 2];
+                gx[at] = (short)peaks[((size_t)b * maxp + k) * 2 + 1];
+            }
+            __syncwarp();
+            if (lane == 0) s_ng += __popc(m);
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0) s_ng += __popc(m);
-        __syncwarp();
     }
+    __syncthreads();
     const int ng_all = s_ng;
     overflow |= ng_all > F1_MAXN;
     const int ng = min(ng_all, F1_MAXN), ntc = min(nt, F1_MAXN);
-    for (int i = lane; i < ntc; i += 32) {
+    for (int i = tid; i < ntc; i += F1_THREADS) {
         ty[i] = (short)truth[((size_t)b * maxt + i) * 2];
         tx[i] = (short)truth[((size_t)b * maxt + i) * 2 + 1];
     }
-    for (int i = lane; i < ng; i += 32) match_g[i] = -1;
-    __syncwarp();
-    if (lane != 0) return;
+    for (int i = tid; i < ng; i += F1_THREADS) match_g[i] = -1;
+    __syncthreads();
     auto close_pair = [&](int t, int g) {
         const int dy = (int)ty[t] - (int)gy[g], dx = (int)tx[t] - (int)gx[g];
         return (double)(dy * dy + dx * dx) < thr2;
     };
+    // admissible pairs, one thread per truth: the search below then walks a few entries instead of every guess
+    for (int t = tid; t < ntc; t += F1_THREADS) {
+        int n = 0;
+        for (int g = 0; g < ng; ++g)
+            if (close_pair(t, g)) { if (n < F1_ADJ) adj[t][n] = (short)g; ++n; }
+        adjn[t] = n > F1_ADJ ? 255 : (unsigned char)n;
+    }
+    __syncthreads();
+    if (tid != 0) return;
     int tp = 0;
     for (int t0 = 0; t0 < ntc; ++t0) {
+        if (adjn[t0] == 0) continue;
         for (int i = 0; i < (ng + 31) / 32; ++i) visited[i] = 0u;
-        // iterative DFS: frame d tries guesses stack_j[d].. for truth stack_t[d]; stack_g[d] = guess taken to descend
+        // iterative DFS: frame d tries the admissible guesses of truth stack_t[d] from position stack_j[d] on, in ascending
+        // order; stack_g[d] = guess taken to descend
         int d = 0;
         stack_t[0] = (short)t0; stack_j[0] = 0;
         bool found = false;
         while (d >= 0) {
             const int t = stack_t[d];
+            const int na = adjn[t];
             int j = stack_j[d];
             bool descended = false;
-            for (; j < ng; ++j) {
-                if ((visited[j >> 5] >> (j & 31)) & 1u) continue;
-                if (!close_pair(t, j)) continue;
-                visited[j >> 5] |= 1u << (j & 31);
-                stack_g[d] = (short)j;
-                if (match_g[j] < 0) { found = true; break; }
+            for (;; ++j) {
+                int g;
+                if (na == 255) { if (j >= ng) break; g = j; if (!close_pair(t, g)) continue; }
+                else { if (j >= na) break; g = adj[t][j]; }
+                if ((visited[g >> 5] >> (g & 31)) & 1u) continue;
+                visited[g >> 5] |= 1u << (g & 31);
+                stack_g[d] = (short)g;
+                if (match_g[g] < 0) { found = true; break; }
                 stack_j[d] = (short)(j + 1);
                 ++d;
-                stack_t[d] = match_g[j]; stack_j[d] = 0;
+                stack_t[d] = match_g[g]; stack_j[d] = 0;
                 descended = true;
                 break;
             }
@@ -1069,7 +1089,7 @@ extern "C" int sted_f1_match(const int32_t* peaks_dev, const int32_t* npeaks_dev
     if (B <= 0 || max_peaks <= 0 || max_truth <= 0) return fail(STED_EINVAL, "B, max_peaks, max_truth must be positive");
     int rc = check_device();
     if (rc) return rc;
-    f1_match_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(peaks_dev, npeaks_dev, valid_dev, max_peaks, truth_dev, ntruth_dev, max_truth,
+    f1_match_kernel<<<B, F1_THREADS, 0, (cudaStream_t)stream>>>(peaks_dev, npeaks_dev, valid_dev, max_peaks, truth_dev, ntruth_dev, max_truth,
                                                        threshold * threshold, counts_dev, f1_dev, flags_dev);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;

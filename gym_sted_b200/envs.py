@@ -135,14 +135,19 @@ class VectorContextualMOSTED:
 
     def __init__(self, num_envs=1, bleach_sampling="constant", actions=("p_sted", "p_ex", "pdt"), max_episode_steps=10,
                  scale_nanodomain_reward=1.0, normalize_observations=True, image_size=64, device="cuda", seed=None,
-                 env_base=0, compute_f1=True, on_invalid="mask"):
-        """``on_invalid``: what a ``None`` objective (negative SNR, ``objectives.py:95-96``) does.  The reference's
+                 env_base=0, compute_f1=True, on_invalid="mask", zero_copy_observation=False):
+        """``zero_copy_observation``: ``step`` returns the uint16 image stack as a VIEW of the pinned buffer the device
+        wrote it to (two buffers, alternating: the array stays valid until the step after the next one) instead of a fresh
+        copy - at 256 x 256 px and 256 environments the copy of the 100 MB stack is half of the step.
+
+        ``on_invalid``: what a ``None`` objective (negative SNR, ``objectives.py:95-96``) does.  The reference's
         ``Normalizer`` raises ``TypeError`` on it; "raise" keeps that (the single-environment views use it), "mask"
         (default for batches) carries NaN in that environment's objective / observation entries and lists the
         environment in ``info["invalid"]`` instead of aborting the other B-1 environments mid-step."""
         if on_invalid not in ("mask", "raise"):
             raise ValueError("on_invalid must be 'mask' or 'raise'")
         self.on_invalid = on_invalid
+        self.zero_copy_observation = bool(zero_copy_observation)
         self.B, self.H, self.W = int(num_envs), int(image_size), int(image_size)
         self.actions = list(actions)
         self.max_episode_steps = int(max_episode_steps)
@@ -189,6 +194,10 @@ class VectorContextualMOSTED:
         if buf is None or tuple(buf.shape) != tuple(shape):
             buf = self._pin[name] = torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
         return buf
+
+    def _img_slot(self):
+        """Name of the pinned buffer this step's observation image goes to (alternating when views are handed out)."""
+        return f"img{self.current_step & 1}" if self.zero_copy_observation else "img"
 
     def _conf_dev(self):
         """The confocal imaging parameters (pdt, p_ex, p_sted) as (B,) float64 device tensors, uploaded once."""
@@ -283,7 +292,8 @@ class VectorContextualMOSTED:
         state = self._next_state()
         obs_img = self._pack_observation(state, conf1, sted)
         # ---- one transfer into pinned memory, one wait
-        pulls = [("res", res_d), ("objs", objs_d), ("oflags", oflags_d), ("img", obs_img)]
+        img_slot = self._img_slot()
+        pulls = [("res", res_d), ("objs", objs_d), ("oflags", oflags_d), (img_slot, obs_img)]
         if self.compute_f1:
             f1_d, cnt_d, dfl_d, mfl_d = rewards.nanodomain_f1_launch(sted, truths, handle=pending)
             pulls += [("f1", f1_d), ("cnt", cnt_d), ("dfl", dfl_d), ("mfl", mfl_d)]
@@ -329,7 +339,7 @@ class VectorContextualMOSTED:
         self._obs_vec[:, at + len(self.actions):at + per_step] = self.obj_normalizer(mo_objs) if self.normalize_observations else mo_objs
         self.current_step += 1
         self.state = (state, conf1, sted)
-        img = host["img"].copy()
+        img = host[img_slot] if self.zero_copy_observation else host[img_slot].copy()
 
         reward = f1 * self.scale_nanodomain_reward
         self.episode_memory["reward"].append(reward)
@@ -627,7 +637,8 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         obs_img = self._pack_observation(state, conf1, sted)
         torch.cuda.current_stream(dev).wait_event(res_done)
         host = {}
-        for name, t in (("res", res_d), ("objs", objs_d), ("oflags", oflags_d), ("peak", peak_d), ("img", obs_img)):
+        img_slot = self._img_slot()
+        for name, t in (("res", res_d), ("objs", objs_d), ("oflags", oflags_d), ("peak", peak_d), (img_slot, obs_img)):
             host[name] = self._pinned(name, t.shape, t.dtype)
             host[name].copy_(t, non_blocking=True)
         if marks:
@@ -663,7 +674,7 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         obs = np.concatenate(obs, axis=1)
         obs = np.pad(obs, ((0, 0), (0, self.observation_space[1].shape[0] - obs.shape[1])))
         self.state = (state, conf1, sted)
-        img = host["img"].copy()
+        img = host[img_slot] if self.zero_copy_observation else host[img_slot].copy()
         if marks:                                            # host seconds: queueing, waiting for the device, unpacking
             marks.append(("end", time.perf_counter()))
             info["timing"] = {b[0]: b[1] - a[1] for a, b in zip(marks, marks[1:])}

@@ -118,6 +118,25 @@ def test_env_api_conformance_single():
     np.testing.assert_allclose(info["action"], env.action_space.high)
 
 
+def test_zero_copy_observation_is_the_same_observation():
+    """``zero_copy_observation=True`` hands out views of two alternating pinned buffers: same values as the copying
+    environment, and the array of step t is untouched by step t + 1."""
+    _gpu()
+    a = envs.make_vec("ContextualMOSTED-easy-hslb-v0", 4, seed=3)
+    b = envs.make_vec("ContextualMOSTED-easy-hslb-v0", 4, seed=3, zero_copy_observation=True)
+    a.reset(seed=3); b.reset(seed=3)
+    acts = np.random.default_rng(0).uniform(a.action_space.low, a.action_space.high, (3, 4, 3)).astype(np.float32)
+    kept = []
+    for t in range(3):
+        (img_a, vec_a), r_a, *_ = a.step(acts[t])
+        (img_b, vec_b), r_b, *_ = b.step(acts[t])
+        assert np.array_equal(img_a, img_b) and np.array_equal(vec_a, vec_b) and np.array_equal(r_a, r_b)
+        assert not img_b.flags.owndata
+        kept.append((img_a, img_b))
+        if t:
+            assert np.array_equal(*kept[t - 1])                  # the previous step's view is still intact
+
+
 def test_vector_env_routine_and_per_env_fluorophores():
     _gpu()
     vec = envs.make_vec("ContextualMOSTED-easy-hslb-v0", 6, compute_f1=False)
