@@ -226,10 +226,15 @@ def run_reference(args, rank, world):
 
 def ncu_traffic(kernel_substr):
     """dram__bytes_read + dram__bytes_write per launch (bytes) from the committed `ncu --set full` summary of the
-    default workload (profiles/r02_ncu_gather.json); None when absent."""
-    try:
-        table = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_gather.json")))
-    except OSError:
+    default workload (the newest of profiles/r02*_ncu_gather.json); None when absent."""
+    table = None
+    for tag in ("r02d", "r02b", "r02"):
+        try:
+            table = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_ncu_gather.json")))
+            break
+        except OSError:
+            continue
+    if table is None:
         return None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     vals = [float(r["dram__bytes_read.sum"]) * scale.get(r["dram__bytes_read.sum.unit"], 1.0)

@@ -11,12 +11,24 @@
 #define LM_HD
 #endif
 
+// see lm_minpack_warp.cuh: one copy of the scalar helpers in device code at the higher LMW_COMPACT levels
+#if defined(__CUDA_ARCH__) && defined(LMW_COMPACT) && LMW_COMPACT >= 2
+#define LM_INL2 __noinline__
+#else
+#define LM_INL2 inline
+#endif
+#if defined(__CUDA_ARCH__) && defined(LMW_COMPACT) && LMW_COMPACT >= 3
+#define LM_INL3 __noinline__
+#else
+#define LM_INL3 inline
+#endif
+
 namespace lm {
 
 constexpr int LM_M = 49, LM_N = 5;
 constexpr double LM_EPS = 2.220446049250313e-16, LM_DWARF = 2.2250738585072014e-308;
 
-LM_HD inline double lm_enorm(int n, const double* x) {
+LM_HD LM_INL2 double lm_enorm(int n, const double* x) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
     const double agiant = rgiant / (double)n;
@@ -71,7 +83,7 @@ struct RationalResiduals {
 
 // LD: leading dimension of r (LM_M inside lm_fit, where r is the top of the Jacobian's storage; LM_N for a packed copy)
 template <int LD = LM_M>
-LM_HD inline void lm_qrsolv(double* r /*[LD*LM_N], column major*/, const int* ipvt, const double* diag, const double* qtb,
+LM_HD LM_INL3 void lm_qrsolv(double* r /*[LD*LM_N], column major*/, const int* ipvt, const double* diag, const double* qtb,
                           double* x, double* sdiag, double* wa) {
     const int n = LM_N, ld = LD;
     for (int j = 0; j < n; ++j) {
@@ -126,7 +138,7 @@ LM_HD inline void lm_qrsolv(double* r /*[LD*LM_N], column major*/, const int* ip
 }
 
 template <int LD = LM_M>
-LM_HD inline void lm_lmpar(double* r, const int* ipvt, const double* diag, const double* qtb, double delta, double* par, double* x,
+LM_HD LM_INL3 void lm_lmpar(double* r, const int* ipvt, const double* diag, const double* qtb, double delta, double* par, double* x,
                          double* sdiag, double* wa1, double* wa2) {
     const int n = LM_N, ld = LD;
     int nsing = n;

@@ -16,6 +16,21 @@
 // tests/test_lm_minpack.py checks that solutions and info codes equal the one-thread device fit bit for bit on both
 // models (and through it scipy.optimize.leastsq on the rational model).
 #pragma once
+// Code size.  With everything inlined and unrolled the Gaussian-fit kernel is ~20 000 SASS instructions (320 KB): warps
+// of different fits sit in different parts of it and the kernel stalls on instruction fetch (`no_instruction` is the top
+// stall in profiles/r02d_ncu_env256.csv).  LMW_COMPACT keeps ONE copy of the residual evaluation, of ENORM and of QRFAC
+// (noinline, loops over the 5 parameters not unrolled); level 2 also keeps one copy of the scalar ENORM, level 3 of
+// LMPAR / QRSOLV.  The arithmetic - and so every result - is the same at every level.
+#ifndef LMW_COMPACT
+#define LMW_COMPACT 3
+#endif
+#if LMW_COMPACT >= 1
+#define LMW_NOINLINE __noinline__
+#define LMW_UNROLL1 _Pragma("unroll 1")
+#else
+#define LMW_NOINLINE inline
+#define LMW_UNROLL1
+#endif
 #include "lm_minpack.cuh"
 
 namespace lm {
@@ -32,7 +47,7 @@ __device__ __forceinline__ double lmw_seq_sum(const double* v, int from, int to)
     return s;
 }
 
-__device__ inline double lmw_enorm(LmWarpWork& w, const double* x, int n) {
+__device__ LMW_NOINLINE double lmw_enorm(LmWarpWork& w, const double* x, int n) {
     const int lane = threadIdx.x & 31;
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     const double agiant = rgiant / (double)n;
@@ -49,14 +64,16 @@ __device__ inline double lmw_enorm(LmWarpWork& w, const double* x, int n) {
     return r;
 }
 
-__device__ inline void lmw_qrfac(LmWarpWork& w, int* ipvt, double* rdiag, double* acnorm, double* wa) {
+__device__ LMW_NOINLINE void lmw_qrfac(LmWarpWork& w, int* ipvt, double* rdiag, double* acnorm, double* wa) {
     const int m = LM_M, n = LM_N, lane = threadIdx.x & 31;
+    LMW_UNROLL1
     for (int j = 0; j < n; ++j) {
         acnorm[j] = lmw_enorm(w, w.fjac[j], m);
         rdiag[j] = acnorm[j];
         wa[j] = rdiag[j];
         ipvt[j] = j;
     }
+    LMW_UNROLL1
     for (int j = 0; j < n; ++j) {
         int kmax = j;
         for (int k = j; k < n; ++k) if (rdiag[k] > rdiag[kmax]) kmax = k;
@@ -75,6 +92,7 @@ __device__ inline void lmw_qrfac(LmWarpWork& w, int* ipvt, double* rdiag, double
             __syncwarp();
             if (lane == 0) w.fjac[j][j] += 1.0;
             __syncwarp();
+            LMW_UNROLL1
             for (int k = j + 1; k < n; ++k) {
                 for (int i = lane; i < m; i += 32) if (i >= j) w.tmp[i] = w.fjac[j][i] * w.fjac[k][i];
                 __syncwarp();
@@ -112,6 +130,7 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
     double fnorm = lmw_enorm(w, w.fvec, m), par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
     const double eps = sqrt(LM_EPS);
     while (info == 0) {
+        LMW_UNROLL1
         for (int j = 0; j < n; ++j) {
             const double temp = x[j];
             double h = eps * fabs(temp);
@@ -133,6 +152,7 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
         }
         for (int i = lane; i < m; i += 32) w.wa4[i] = w.fvec[i];
         __syncwarp();
+        LMW_UNROLL1
         for (int j = 0; j < n; ++j) {
             const double ajj = w.fjac[j][j];
             if (ajj != 0.0) {

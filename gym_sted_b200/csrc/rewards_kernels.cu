@@ -800,7 +800,7 @@ using namespace lm;
 template <bool RATIONAL>
 struct WarpResiduals {
     const double* data;       // the 49 window values (shared memory)
-    __device__ void operator()(const double* p, double* f) const {
+    __device__ LMW_NOINLINE void operator()(const double* p, double* f) const {
         const int lane = threadIdx.x & 31;
         const double wx = p[3] + 1e-3, wy = p[4] + 1e-3;
         const double dx2 = 2.0 * (wx * wx), dy2 = 2.0 * (wy * wy);
@@ -817,8 +817,11 @@ struct WarpResiduals {
 };
 
 constexpr int GF_THREADS = 128;      // 4 fits per CTA, one warp each
+#ifndef GF_MINB
+#define GF_MINB 4
+#endif
 
-__global__ void __launch_bounds__(GF_THREADS) gaussfit_kernel(const float* __restrict__ sted, int H, int W, const int* __restrict__ peaks,
+__global__ void __launch_bounds__(GF_THREADS, GF_MINB) gaussfit_kernel(const float* __restrict__ sted, int H, int W, const int* __restrict__ peaks,
                                                             const int* __restrict__ npeaks, int maxp, double pixelsize,
                                                             unsigned char* __restrict__ valid, double* __restrict__ params) {
     __shared__ LmWarpWork work[GF_THREADS / 32];

@@ -132,6 +132,7 @@ class VectorContextualMOSTED:
     """B ContextualMOSTED environments stepped together on one GPU."""
 
     obj_names = OBJ_NAMES
+    prefetch_structures = True       # step() generates the next structures on a side stream while it images the current ones
 
     def __init__(self, num_envs=1, bleach_sampling="constant", actions=("p_sted", "p_ex", "pdt"), max_episode_steps=10,
                  scale_nanodomain_reward=1.0, normalize_observations=True, image_size=64, device="cuda", seed=None,
@@ -182,11 +183,15 @@ class VectorContextualMOSTED:
         self.synapse_gen = synapse.DeviceSynapseGenerator(self.B, self.H, self.W, self.device, env_base=self.env_base,
                                                           seed=int(self.np_rng.integers(0, 2 ** 62)))
         self._truths = None          # rewards.DeviceTruths of the structures being imaged
+        self._prefetched = None      # ((frames, coords, counts), event) of structures generated ahead on a side stream
         self._coords_host = None     # the same coordinates on the host (list of (n_i, 2) int64 arrays), read back lazily
         self._pin = {}               # pinned host buffers of the end-of-step transfer
         self._conf_d = None
         self._obs_vec = None
         self.step_timing = bool(os.environ.get("STED_B200_STEP_TIMING"))   # info["timing"]: host seconds per phase of step()
+        # STED_B200_STEP_PRIORITY=0 keeps the step on the caller's stream (A/B measurements)
+        self._step_stream = (torch.cuda.Stream(self.device, priority=-2)
+                             if os.environ.get("STED_B200_STEP_PRIORITY", "1") != "0" else None)
 
     # ------------------------------------------------------------------ helpers
     def _pinned(self, name, shape, dtype):
@@ -219,13 +224,33 @@ class VectorContextualMOSTED:
     def _new_datamaps(self):
         """``_update_datamap`` (mosted_env.py:168-187): new synapse, new datamap, confocal image of it — all queued on
         the device (``sted_synapse_generate`` -> ``sted_pad_maps`` -> acquisition), nothing read back."""
-        frames, coords, counts = self.synapse_gen.generate()
+        if self._prefetched is not None:                       # generated on a side stream since the start of the step
+            (frames, coords, counts), ready = self._prefetched
+            self._prefetched = None
+            torch.cuda.current_stream(self.device).wait_event(ready)
+        else:
+            frames, coords, counts = self.synapse_gen.generate()
         self._truths = rewards.DeviceTruths.from_device(coords, counts)   # ground truth of the device F1 matching
         self._coords_host = None
         self.frames = frames                                   # molecule maps of the current synapses (device, int32)
         self.bm.set_datamaps(frames, max_molecules=self.synapse_gen.max_molecules)
         state, _ = self.bm.get_signal_and_bleach(*self._conf_dev(), bleach=False, tables_key="conf")
         return state
+
+    def _prefetch_structures(self):
+        """Queue the generation of the NEXT structures (``sted_synapse_generate``: independent of everything the step
+        images) on a side stream, so that it runs under the step's first acquisitions instead of after the last one;
+        ``_new_datamaps`` waits for it."""
+        cur = torch.cuda.current_stream(self.device)
+        side = rewards.side_stream(self.device, 2)
+        side.wait_stream(cur)                                  # the generator's scratch is shared with earlier calls
+        with torch.cuda.stream(side):
+            out = self.synapse_gen.generate()
+            ready = torch.cuda.Event()
+            ready.record(side)
+        for t in out:
+            t.record_stream(cur)                               # consumed by the step's stream after `ready`
+        self._prefetched = (out, ready)
 
     def _pack_observation(self, state, conf1=None, sted=None):
         """(state, conf1, sted) -> uint16 (B,H,W,3) device tensor (``sted_pack_observation``); missing channels are 0."""
@@ -244,6 +269,23 @@ class VectorContextualMOSTED:
         return cols["pdt"].astype(np.float64), cols["p_ex"].astype(np.float64), cols["p_sted"].astype(np.float64)
 
     # ------------------------------------------------------------------ gym API
+    def step(self, action):
+        """``_step_impl`` queued on the environment's own HIGH-priority stream.  The step's acquisitions then win the SMs
+        from what runs beside them on the (default-priority) side streams - Gaussian fits, decorrelation, the next
+        structures: long grids of light CTAs that, at equal priority, are dispatched in launch order and keep a gather
+        launched after them waiting until their last CTA has started (`scripts/env_step_kernels.py`, PROBE_TIMELINE)."""
+        st = self._step_stream
+        if st is None:
+            return self._step_impl(action)
+        cur = torch.cuda.current_stream(self.device)
+        st.wait_stream(cur)                                    # after whatever the caller queued (reset, its own kernels)
+        with torch.cuda.stream(st):
+            out = self._step_impl(action)                      # ends with a synchronize of `st`
+        for v in out[-1].values():
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(cur)                           # allocated on `st`, used by the caller on its stream
+        return out
+
     def reset(self, seed=None, options=None):
         if seed is not None:
             self.np_rng = np.random.default_rng(seed)
@@ -264,7 +306,7 @@ class VectorContextualMOSTED:
         img = self._pack_observation(state).cpu().numpy()
         return (img, self._obs_vec.copy()), {}
 
-    def step(self, action):
+    def _step_impl(self, action):
         action = np.clip(np.asarray(action, dtype=np.float32).reshape(self.B, len(self.actions)),
                          self.action_space.low, self.action_space.high)
         if self._obs_vec is None:
@@ -279,21 +321,28 @@ class VectorContextualMOSTED:
         h_act.numpy()[:] = (pdt, p_ex, p_sted)
         d_act = h_act.to(dev, non_blocking=True)
         conf = self._conf_dev()
-        # ---- everything below only queues work
+        # ---- everything below only queues work.  Three side streams run beside the acquisitions: the next structures
+        # (from the start), and - as soon as the STED image exists - candidates + Gaussian fits and the decorrelation
+        # chain, both of which need nothing but that image and so overlap the second confocal and what follows it.
+        if self.prefetch_structures:
+            self._prefetch_structures()
         conf1, _ = bm.get_signal_and_bleach(*conf, bleach=False, tables_key="conf")
         sted, _ = bm.get_signal_and_bleach(d_act[0], d_act[1], d_act[2], bleach=True)
+        pending = rewards.detect_nanodomains_launch(sted) if self.compute_f1 else None
+        res_d, res_done = rewards.resolution_launch(sted, lane=1)
         conf2, _ = bm.get_signal_and_bleach(*conf, bleach=False, tables_key="conf")
         bleached = bm.datamaps_roi().clone()
-        pending = rewards.detect_nanodomains_launch(sted) if self.compute_f1 else None     # side stream: overlaps the rest
         fg_s, fg_c, objs_d, oflags_d = rewards.foreground_objectives_device(conf1, sted, conf2)
-        res_d = rewards.resolution_device(sted)
         truths, coords = self._truths, self._coords_host
         exhausted = self._exhausted()
         state = self._next_state()
         obs_img = self._pack_observation(state, conf1, sted)
-        # ---- one transfer into pinned memory, one wait
+        # ---- one transfer into pinned memory, one wait (the image first: it does not wait for the side streams)
         img_slot = self._img_slot()
-        pulls = [("res", res_d), ("objs", objs_d), ("oflags", oflags_d), (img_slot, obs_img)]
+        host = {img_slot: self._pinned(img_slot, obs_img.shape, obs_img.dtype)}
+        host[img_slot].copy_(obs_img, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_event(res_done)
+        pulls = [("res", res_d), ("objs", objs_d), ("oflags", oflags_d)]
         if self.compute_f1:
             f1_d, cnt_d, dfl_d, mfl_d = rewards.nanodomain_f1_launch(sted, truths, handle=pending)
             pulls += [("f1", f1_d), ("cnt", cnt_d), ("dfl", dfl_d), ("mfl", mfl_d)]
@@ -301,7 +350,6 @@ class VectorContextualMOSTED:
             pulls += [("tc", truths.coords), ("tn", truths.counts)]
         if self._truths is not truths:                       # the next structures' ground truth rides along
             pulls += [("nc", self._truths.coords), ("nn", self._truths.counts)]
-        host = {}
         for name, t in pulls:
             host[name] = self._pinned(name, t.shape, t.dtype)
             host[name].copy_(t, non_blocking=True)
@@ -367,6 +415,8 @@ class VectorSequenceMOSTED(VectorContextualMOSTED):
     structure is imaged again at every step, so the datamap carries its photobleaching through the episode
     (the boundary's in-place update, ``:84-90``), and an environment is done early once its datamap is empty
     (``:109``)."""
+
+    prefetch_structures = False      # no new structure inside an episode
 
     def _next_state(self):
         state, _ = self.bm.get_signal_and_bleach(*self._conf_dev(), bleach=False, tables_key="conf")
@@ -611,7 +661,7 @@ class VectorPreferenceCountRateMOSTED(VectorContextualMOSTED):
         state, _ = self.bm.get_signal_and_bleach(*self._state_conf_d, bleach=False, tables_key="state")
         return state
 
-    def step(self, action):
+    def _step_impl(self, action):
         """One step of B environments (preference_sted_env.py:262-323).  Like the contextual step it only QUEUES device
         work - three acquisitions with kept confocal tables, objectives, the decorrelation chain, the peak count of the
         STED image, the next structure maps and their state image, the uint16 observation - then makes one transfer into

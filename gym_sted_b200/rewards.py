@@ -125,17 +125,30 @@ def resolution_device(sted: torch.Tensor, pixelsize=PIXELSIZE, res_cap=RES_CAP, 
     return res
 
 
-def resolution_launch(sted: torch.Tensor):
-    """``resolution_device`` queued on the side stream (it then runs beside whatever the caller queues next on its own
+def side_stream(dev, lane=0):
+    """One of the package's side streams of ``dev`` (created on first use).  Lane 0 carries the nanodomain detection,
+    lane 1 the decorrelation chain of a step that also detects nanodomains, lane 2 the next structures."""
+    key = (str(dev), int(lane))
+    if key not in _SIDE_STREAMS:
+        # the short decorrelation chain goes ahead of the long grids of the fits and of the structure generator when
+        # they compete for the SMs a step's acquisitions (one more priority step up, envs.py) leave free
+        _SIDE_STREAMS[key] = torch.cuda.Stream(dev, priority=-1 if lane == 1 else 0)
+    return _SIDE_STREAMS[key]
+
+
+def resolution_launch(sted: torch.Tensor, lane=0):
+    """``resolution_device`` queued on a side stream (it then runs beside whatever the caller queues next on its own
     stream, e.g. ``objectives_kernel``); returns ``(res, done)``: wait for the event ``done`` before using ``res`` on
     another stream, and keep ``sted`` alive until then."""
     dev = sted.device
-    side = _SIDE_STREAMS.setdefault(str(dev), torch.cuda.Stream(dev))
-    side.wait_stream(torch.cuda.current_stream(dev))
+    side = side_stream(dev, lane)
+    cur = torch.cuda.current_stream(dev)
+    side.wait_stream(cur)
     with torch.cuda.stream(side):
         res = resolution_device(sted)
         done = torch.cuda.Event()
         done.record(side)
+    res.record_stream(cur)                    # read by the caller's stream after `done`
     return res, done
 
 
@@ -219,7 +232,7 @@ def detect_nanodomains_launch(sted: torch.Tensor, pixelsize=PIXELSIZE):
     """Enqueue candidates + Gaussian-fit validation of B device images on a side stream and return a handle for
     ``detect_nanodomains_collect``; the fits (few warps, long latency) then overlap whatever the caller runs next."""
     dev = sted.device
-    side = _SIDE_STREAMS.setdefault(str(dev), torch.cuda.Stream(dev))
+    side = side_stream(dev, 0)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
         sted32, peaks, npk, flags = _candidates_device(sted)

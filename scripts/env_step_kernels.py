@@ -27,3 +27,11 @@ for ev in prof.events():
 print(f"{'kernel':110s} launches   us")
 for name, (n, t) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
     print(f"{name[:110]:110s} {n:5d} {t:8.1f}")
+
+if os.environ.get("PROBE_TIMELINE"):
+    # start / end of every kernel and copy of the step relative to the first one, by stream (which ones overlap)
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    t0 = min(e.time_range.start for e in evs)
+    print(f"\n{'start us':>9s} {'end us':>9s} {'stream':>7s}  kernel")
+    for e in sorted(evs, key=lambda e: e.time_range.start):
+        print(f"{e.time_range.start - t0:9.1f} {e.time_range.end - t0:9.1f} {getattr(e, 'device_index', 0)!s:>3s}/{getattr(e, 'device_resource_id', '?')!s:>3s}  {e.name[:70]}")

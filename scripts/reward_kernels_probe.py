@@ -31,3 +31,18 @@ def timed(name, fn):
 timed("nanodomain candidates (device)", lambda: rewards._candidates_device(sted))
 timed("resolution chain (device)", lambda: rewards.resolution_device(sted))
 timed("foreground + objectives (device)", lambda: rewards.foreground_objectives_device(conf1, sted, conf2))
+
+# Gaussian-fit validation of the candidates of these images: device time, number of fits, and a digest of the fitted
+# parameters (two builds of the solver that differ only in inlining must print the same digest)
+import hashlib  # noqa: E402
+
+sted32, peaks, npk, _ = rewards._candidates_device(sted)
+timed("Gaussian fits (device)", lambda: rewards.gaussfit_validate(sted32, peaks, npk))
+valid, params = rewards.gaussfit_validate(sted32, peaks, npk, want_params=True)
+torch.cuda.synchronize()
+n = npk.cpu().numpy()
+v, p = valid.cpu().numpy(), params.cpu().numpy()
+h = hashlib.sha256()
+for b in range(B):
+    h.update(v[b, :n[b]].tobytes()); h.update(p[b, :n[b]].tobytes())
+print(f"fits {int(n.sum())} (max {int(n.max())} per image), kept {int(sum(v[b, :n[b]].sum() for b in range(B)))}, digest {h.hexdigest()[:16]}")

@@ -26,3 +26,9 @@ $NCU --set full --import-source on -k regex:'sweep2|presample|scatter_events|buc
 ENV1="python bench.py --workload env_step --size 256 --steps 1 --warmup 1 --no-cpu"
 $NCU --set full --import-source on -k regex:'gaussfit|nanodomain|decorr|objectives|synapse_cell|f1_match|apodize|spectrum_gather|pack_observation' -c 18 -f -o $OUT/${TAG}_env256 $ENV1 > $OUT/ncu6.log 2>&1
 ls -la $OUT | tail -20
+# summaries are extracted on the box (the reports together can exceed what gpurun merges back)
+for n in gather scan env256; do
+  python scripts/summarize_ncu.py $OUT/${TAG}_$n.ncu-rep $OUT/${TAG}_ncu_$n > /dev/null 2>> $OUT/ncu_sum.log
+done
+du -sh $OUT/*.ncu-rep
+rm -f $OUT/*.ncu-rep
