@@ -22,6 +22,11 @@
 #else
 #define LM_INL3 inline
 #endif
+#if defined(__CUDA_ARCH__) && defined(LMW_COMPACT) && LMW_COMPACT >= 4      // rolled loops over the 5 parameters
+#define LM_U1 _Pragma("unroll 1")
+#else
+#define LM_U1
+#endif
 
 namespace lm {
 
@@ -32,6 +37,7 @@ LM_HD LM_INL2 double lm_enorm(int n, const double* x) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
     const double agiant = rgiant / (double)n;
+    LM_U1
     for (int i = 0; i < n; ++i) {
         const double xabs = fabs(x[i]);
         if (xabs > rdwarf && xabs < agiant) {
@@ -59,6 +65,7 @@ struct GaussResiduals {
     LM_HD void operator()(const double* p, double* f) const {
         const double wx = p[3] + 1e-3, wy = p[4] + 1e-3;
         const double dx2 = 2.0 * (wx * wx), dy2 = 2.0 * (wy * wy);
+        LM_U1
         for (int i = 0; i < LM_M; ++i) {
             const double X = (double)(i / 7) - 3.0, Y = (double)(i % 7) - 3.0;
             const double a = (p[1] - X) * (p[1] - X) / dx2, b = (p[2] - Y) * (p[2] - Y) / dy2;
@@ -73,6 +80,7 @@ struct RationalResiduals {
     LM_HD void operator()(const double* p, double* f) const {
         const double wx = p[3] + 1e-3, wy = p[4] + 1e-3;
         const double dx2 = 2.0 * (wx * wx), dy2 = 2.0 * (wy * wy);
+        LM_U1
         for (int i = 0; i < LM_M; ++i) {
             const double X = (double)(i / 7) - 3.0, Y = (double)(i % 7) - 3.0;
             const double a = (p[1] - X) * (p[1] - X) / dx2, b = (p[2] - Y) * (p[2] - Y) / dy2;
@@ -86,17 +94,22 @@ template <int LD = LM_M>
 LM_HD LM_INL3 void lm_qrsolv(double* r /*[LD*LM_N], column major*/, const int* ipvt, const double* diag, const double* qtb,
                           double* x, double* sdiag, double* wa) {
     const int n = LM_N, ld = LD;
+    LM_U1
     for (int j = 0; j < n; ++j) {
+        LM_U1
         for (int i = j; i < n; ++i) r[i + ld * j] = r[j + ld * i];
         x[j] = r[j + ld * j];
         wa[j] = qtb[j];
     }
+    LM_U1
     for (int j = 0; j < n; ++j) {
         const int l = ipvt[j];
         if (diag[l] != 0.0) {
+            LM_U1
             for (int k = j; k < n; ++k) sdiag[k] = 0.0;
             sdiag[j] = diag[l];
             double qtbpj = 0.0;
+            LM_U1
             for (int k = j; k < n; ++k) {
                 if (sdiag[k] == 0.0) continue;
                 double c, s;
@@ -113,6 +126,7 @@ LM_HD LM_INL3 void lm_qrsolv(double* r /*[LD*LM_N], column major*/, const int* i
                 const double temp = c * wa[k] + s * qtbpj;
                 qtbpj = -s * wa[k] + c * qtbpj;
                 wa[k] = temp;
+                LM_U1
                 for (int i = k + 1; i < n; ++i) {
                     const double t2 = c * r[i + ld * k] + s * sdiag[i];
                     sdiag[i] = -s * r[i + ld * k] + c * sdiag[i];
@@ -124,16 +138,20 @@ LM_HD LM_INL3 void lm_qrsolv(double* r /*[LD*LM_N], column major*/, const int* i
         r[j + ld * j] = x[j];
     }
     int nsing = n;
+    LM_U1
     for (int j = 0; j < n; ++j) {
         if (sdiag[j] == 0.0 && nsing == n) nsing = j;
         if (nsing < n) wa[j] = 0.0;
     }
+    LM_U1
     for (int k = 0; k < nsing; ++k) {
         const int j = nsing - k - 1;
         double sum = 0.0;
+        LM_U1
         for (int i = j + 1; i < nsing; ++i) sum += r[i + ld * j] * wa[i];
         wa[j] = (wa[j] - sum) / sdiag[j];
     }
+    LM_U1
     for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
 }
 
@@ -142,36 +160,46 @@ LM_HD LM_INL3 void lm_lmpar(double* r, const int* ipvt, const double* diag, cons
                          double* sdiag, double* wa1, double* wa2) {
     const int n = LM_N, ld = LD;
     int nsing = n;
+    LM_U1
     for (int j = 0; j < n; ++j) {
         wa1[j] = qtb[j];
         if (r[j + ld * j] == 0.0 && nsing == n) nsing = j;
         if (nsing < n) wa1[j] = 0.0;
     }
+    LM_U1
     for (int k = 0; k < nsing; ++k) {
         const int j = nsing - k - 1;
         wa1[j] /= r[j + ld * j];
         const double temp = wa1[j];
+        LM_U1
         for (int i = 0; i < j; ++i) wa1[i] -= r[i + ld * j] * temp;
     }
+    LM_U1
     for (int j = 0; j < n; ++j) x[ipvt[j]] = wa1[j];
     int iter = 0;
+    LM_U1
     for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
     double dxnorm = lm_enorm(n, wa2);
     double fp = dxnorm - delta;
     if (fp <= 0.1 * delta) { *par = 0.0; return; }
     double parl = 0.0;
     if (nsing >= n) {
+        LM_U1
         for (int j = 0; j < n; ++j) { const int l = ipvt[j]; wa1[j] = diag[l] * (wa2[l] / dxnorm); }
+        LM_U1
         for (int j = 0; j < n; ++j) {
             double sum = 0.0;
+            LM_U1
             for (int i = 0; i < j; ++i) sum += r[i + ld * j] * wa1[i];
             wa1[j] = (wa1[j] - sum) / r[j + ld * j];
         }
         const double temp = lm_enorm(n, wa1);
         parl = ((fp / delta) / temp) / temp;
     }
+    LM_U1
     for (int j = 0; j < n; ++j) {
         double sum = 0.0;
+        LM_U1
         for (int i = 0; i <= j; ++i) sum += r[i + ld * j] * qtb[i];
         wa1[j] = sum / diag[ipvt[j]];
     }
@@ -185,17 +213,22 @@ LM_HD LM_INL3 void lm_lmpar(double* r, const int* ipvt, const double* diag, cons
         ++iter;
         if (*par == 0.0) *par = fmax(LM_DWARF, 0.001 * paru);
         double temp = sqrt(*par);
+        LM_U1
         for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
         lm_qrsolv<LD>(r, ipvt, wa1, qtb, x, sdiag, wa2);
+        LM_U1
         for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
         dxnorm = lm_enorm(n, wa2);
         temp = fp;
         fp = dxnorm - delta;
         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        LM_U1
         for (int j = 0; j < n; ++j) { const int l = ipvt[j]; wa1[j] = diag[l] * (wa2[l] / dxnorm); }
+        LM_U1
         for (int j = 0; j < n; ++j) {
             wa1[j] /= sdiag[j];
             const double t2 = wa1[j];
+            LM_U1
             for (int i = j + 1; i < n; ++i) wa1[i] -= r[i + ld * j] * t2;
         }
         temp = lm_enorm(n, wa1);

@@ -18,11 +18,14 @@
 #pragma once
 // Code size.  With everything inlined and unrolled the Gaussian-fit kernel is ~20 000 SASS instructions (320 KB): warps
 // of different fits sit in different parts of it and the kernel stalls on instruction fetch (`no_instruction` is the top
-// stall in profiles/r02d_ncu_env256.csv).  LMW_COMPACT keeps ONE copy of the residual evaluation, of ENORM and of QRFAC
-// (noinline, loops over the 5 parameters not unrolled); level 2 also keeps one copy of the scalar ENORM, level 3 of
-// LMPAR / QRSOLV.  The arithmetic - and so every result - is the same at every level.
+// stall in profiles/r02d_ncu_env256.csv; more resident warps change nothing).  LMW_COMPACT keeps ONE copy of the residual
+// evaluation, of ENORM and of QRFAC (noinline, loops over the 5 parameters not unrolled); level 2 also keeps one copy of
+// the scalar ENORM, level 3 of LMPAR / QRSOLV, level 4 rolls every loop over the 5 parameters.  The arithmetic - and so
+// every result - is the same at every level (same digest of 15 552 fitted parameter sets); measured for those fits of
+// 256 images of 256 x 256: 19 952 instructions 4.50 ms, level 1 13 808 / 4.25, level 2 7 392 / 3.99, level 3 6 344 / 3.86,
+// level 4 3 840 / 3.52 ms.
 #ifndef LMW_COMPACT
-#define LMW_COMPACT 3
+#define LMW_COMPACT 4
 #endif
 #if LMW_COMPACT >= 1
 #define LMW_NOINLINE __noinline__
@@ -124,6 +127,7 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
     const int m = LM_M, n = LM_N, lane = threadIdx.x & 31;
     double diag[LM_N], qtf[LM_N], wa1[LM_N], wa2[LM_N], wa3[LM_N], wa5[LM_N], r[LM_N * LM_N];
     int ipvt[LM_N];
+    LM_U1
     for (int i = 0; i < n * n; ++i) r[i] = 0.0;
     residuals(x, w.fvec);
     int nfev = 1, info = 0, iter = 1;
@@ -131,6 +135,7 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
     const double eps = sqrt(LM_EPS);
     while (info == 0) {
         LMW_UNROLL1
+        LM_U1
         for (int j = 0; j < n; ++j) {
             const double temp = x[j];
             double h = eps * fabs(temp);
@@ -144,7 +149,9 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
         nfev += n;
         lmw_qrfac(w, ipvt, wa1, wa2, wa3);
         if (iter == 1) {
+            LM_U1
             for (int j = 0; j < n; ++j) { diag[j] = wa2[j]; if (wa2[j] == 0.0) diag[j] = 1.0; }
+            LM_U1
             for (int j = 0; j < n; ++j) wa3[j] = diag[j] * x[j];
             xnorm = lm_enorm(n, wa3);
             delta = factor * xnorm;
@@ -153,6 +160,7 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
         for (int i = lane; i < m; i += 32) w.wa4[i] = w.fvec[i];
         __syncwarp();
         LMW_UNROLL1
+        LM_U1
         for (int j = 0; j < n; ++j) {
             const double ajj = w.fjac[j][j];
             if (ajj != 0.0) {
@@ -164,26 +172,31 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
                 for (int i = lane; i < m; i += 32) if (i >= j) w.wa4[i] += w.fjac[j][i] * temp;
                 __syncwarp();
             }
+            LM_U1
             for (int i = 0; i < j; ++i) r[i + n * j] = w.fjac[j][i];      // R, packed: column j above the diagonal ...
             r[j + n * j] = wa1[j];                                        // ... and its diagonal (rdiag)
             qtf[j] = w.wa4[j];
         }
         gnorm = 0.0;
         if (fnorm != 0.0) {
+            LM_U1
             for (int j = 0; j < n; ++j) {
                 const int l = ipvt[j];
                 if (wa2[l] != 0.0) {
                     double sum = 0.0;
+                    LM_U1
                     for (int i = 0; i <= j; ++i) sum += r[i + n * j] * (qtf[i] / fnorm);
                     gnorm = fmax(gnorm, fabs(sum / wa2[l]));
                 }
             }
         }
         if (gnorm <= gtol) { info = 4; break; }
+        LM_U1
         for (int j = 0; j < n; ++j) diag[j] = fmax(diag[j], wa2[j]);
         double ratio = 0.0;
         do {
             lm_lmpar<LM_N>(r, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wa5);
+            LM_U1
             for (int j = 0; j < n; ++j) { wa1[j] = -wa1[j]; wa2[j] = x[j] + wa1[j]; wa3[j] = diag[j] * wa1[j]; }
             const double pnorm = lm_enorm(n, wa3);
             if (iter == 1) delta = fmin(delta, pnorm);
@@ -192,9 +205,11 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
             const double fnorm1 = lmw_enorm(w, w.wa4, m);
             double actred = -1.0;
             if (0.1 * fnorm1 < fnorm) { const double t = fnorm1 / fnorm; actred = 1.0 - t * t; }
+            LM_U1
             for (int j = 0; j < n; ++j) {
                 wa3[j] = 0.0;
                 const double temp = wa1[ipvt[j]];
+                LM_U1
                 for (int i = 0; i <= j; ++i) wa3[i] += r[i + n * j] * temp;
             }
             const double temp1 = lm_enorm(n, wa3) / fnorm, temp2 = (sqrt(par) * pnorm) / fnorm;
@@ -213,6 +228,7 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
                 par *= 0.5;
             }
             if (ratio >= 1e-4) {
+                LM_U1
                 for (int j = 0; j < n; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; }
                 for (int i = lane; i < m; i += 32) w.fvec[i] = w.wa4[i];
                 __syncwarp();
