@@ -189,9 +189,16 @@ class VectorContextualMOSTED:
         self._conf_d = None
         self._obs_vec = None
         self.step_timing = bool(os.environ.get("STED_B200_STEP_TIMING"))   # info["timing"]: host seconds per phase of step()
-        # STED_B200_STEP_PRIORITY=0 keeps the step on the caller's stream (A/B measurements)
-        self._step_stream = (torch.cuda.Stream(self.device, priority=-2)
-                             if os.environ.get("STED_B200_STEP_PRIORITY", "1") != "0" else None)
+        # Two schedules of a step (same kernels, same results).  "wide": acquisitions on a high-priority stream, three
+        # side streams (next structures / candidates + fits / decorrelation) - pays when the kernels are long enough to
+        # fill the GPU (16.2 instead of 19.2 ms per 256-env step at 256 x 256).  "narrow": the acquisitions and the
+        # decorrelation chain on the caller's stream, the fits on one side stream - at 64 x 64 the step is bound by the
+        # host and the extra stream switches and event waits of the wide schedule cost 0.3 ms of 2.3.
+        layout = os.environ.get("STED_B200_STEP_LAYOUT", "auto")
+        if layout not in ("auto", "wide", "narrow"):
+            raise ValueError("STED_B200_STEP_LAYOUT must be auto, wide or narrow")
+        self.wide_step = layout == "wide" or (layout == "auto" and self.B * self.H * self.W >= (1 << 22))
+        self._step_stream = torch.cuda.Stream(self.device, priority=-2) if self.wide_step else None
 
     # ------------------------------------------------------------------ helpers
     def _pinned(self, name, shape, dtype):
@@ -324,15 +331,21 @@ class VectorContextualMOSTED:
         # ---- everything below only queues work.  Three side streams run beside the acquisitions: the next structures
         # (from the start), and - as soon as the STED image exists - candidates + Gaussian fits and the decorrelation
         # chain, both of which need nothing but that image and so overlap the second confocal and what follows it.
-        if self.prefetch_structures:
+        wide = self.wide_step
+        if wide and self.prefetch_structures:
             self._prefetch_structures()
         conf1, _ = bm.get_signal_and_bleach(*conf, bleach=False, tables_key="conf")
         sted, _ = bm.get_signal_and_bleach(d_act[0], d_act[1], d_act[2], bleach=True)
-        pending = rewards.detect_nanodomains_launch(sted) if self.compute_f1 else None
-        res_d, res_done = rewards.resolution_launch(sted, lane=1)
+        if wide:
+            pending = rewards.detect_nanodomains_launch(sted) if self.compute_f1 else None
+            res_d, res_done = rewards.resolution_launch(sted, lane=1)
         conf2, _ = bm.get_signal_and_bleach(*conf, bleach=False, tables_key="conf")
         bleached = bm.datamaps_roi().clone()
+        if not wide:
+            pending = rewards.detect_nanodomains_launch(sted) if self.compute_f1 else None
         fg_s, fg_c, objs_d, oflags_d = rewards.foreground_objectives_device(conf1, sted, conf2)
+        if not wide:
+            res_d, res_done = rewards.resolution_device(sted), None
         truths, coords = self._truths, self._coords_host
         exhausted = self._exhausted()
         state = self._next_state()
@@ -341,7 +354,8 @@ class VectorContextualMOSTED:
         img_slot = self._img_slot()
         host = {img_slot: self._pinned(img_slot, obs_img.shape, obs_img.dtype)}
         host[img_slot].copy_(obs_img, non_blocking=True)
-        torch.cuda.current_stream(dev).wait_event(res_done)
+        if res_done is not None:
+            torch.cuda.current_stream(dev).wait_event(res_done)
         pulls = [("res", res_d), ("objs", objs_d), ("oflags", oflags_d)]
         if self.compute_f1:
             f1_d, cnt_d, dfl_d, mfl_d = rewards.nanodomain_f1_launch(sted, truths, handle=pending)
