@@ -39,9 +39,19 @@
 namespace lm {
 
 constexpr int LMW_LD = 52;
+// LMW_LANES: independent reductions of QRFAC (the five column norms it starts with; the dot products of the pivot
+// column with every later column) are summed AT THE SAME TIME by different lanes - each still first term to last, so
+// every sum is the one MINPACK computes - and broadcast, instead of one after the other by all lanes: 16 dependent
+// 49-term chains per iteration of the fit instead of 26.
+#ifndef LMW_LANES
+#define LMW_LANES 1
+#endif
 struct LmWarpWork {
     double fvec[LMW_LD], wa4[LMW_LD], tmp[LMW_LD], data[LMW_LD];
     double fjac[LM_N][LMW_LD];
+#if LMW_LANES
+    double tmpn[LM_N][LMW_LD];       // the terms of up to five concurrent reductions
+#endif
 };
 
 __device__ __forceinline__ double lmw_seq_sum(const double* v, int from, int to) {
@@ -69,6 +79,31 @@ __device__ LMW_NOINLINE double lmw_enorm(LmWarpWork& w, const double* x, int n) 
 
 __device__ LMW_NOINLINE void lmw_qrfac(LmWarpWork& w, int* ipvt, double* rdiag, double* acnorm, double* wa) {
     const int m = LM_M, n = LM_N, lane = threadIdx.x & 31;
+#if LMW_LANES
+    {   // the five column norms at once: lane j sums column j (lmw_enorm's common case; anything else falls back to it)
+        const double rdwarf = 3.834e-20, agiant = 1.304e19 / (double)m;
+        bool mid = true;
+        LMW_UNROLL1
+        for (int j = 0; j < n; ++j)
+            for (int i = lane; i < m; i += 32) {
+                const double xabs = fabs(w.fjac[j][i]);
+                mid = mid && xabs > rdwarf && xabs < agiant;
+                w.tmpn[j][i] = xabs * xabs;
+            }
+        const bool all_mid = __all_sync(0xffffffffu, mid);
+        __syncwarp();
+        double mine = 0.0;
+        if (all_mid && lane < n) mine = sqrt(lmw_seq_sum(w.tmpn[lane], 0, m));
+        LMW_UNROLL1
+        for (int j = 0; j < n; ++j) {
+            acnorm[j] = all_mid ? __shfl_sync(0xffffffffu, mine, j) : lmw_enorm(w, w.fjac[j], m);
+            rdiag[j] = acnorm[j];
+            wa[j] = rdiag[j];
+            ipvt[j] = j;
+        }
+        __syncwarp();
+    }
+#else
     LMW_UNROLL1
     for (int j = 0; j < n; ++j) {
         acnorm[j] = lmw_enorm(w, w.fjac[j], m);
@@ -76,6 +111,7 @@ __device__ LMW_NOINLINE void lmw_qrfac(LmWarpWork& w, int* ipvt, double* rdiag, 
         wa[j] = rdiag[j];
         ipvt[j] = j;
     }
+#endif
     LMW_UNROLL1
     for (int j = 0; j < n; ++j) {
         int kmax = j;
@@ -95,8 +131,25 @@ __device__ LMW_NOINLINE void lmw_qrfac(LmWarpWork& w, int* ipvt, double* rdiag, 
             __syncwarp();
             if (lane == 0) w.fjac[j][j] += 1.0;
             __syncwarp();
+#if LMW_LANES
+            // the later columns are independent of one another: lane k sums the dot product of column k with the pivot
+            LMW_UNROLL1
+            for (int k = j + 1; k < n; ++k)
+                for (int i = lane; i < m; i += 32) if (i >= j) w.tmpn[k][i] = w.fjac[j][i] * w.fjac[k][i];
+            __syncwarp();
+            double mine = 0.0;
+            if (lane > j && lane < n) mine = lmw_seq_sum(w.tmpn[lane], j, m) / w.fjac[j][j];
+            __syncwarp();
             LMW_UNROLL1
             for (int k = j + 1; k < n; ++k) {
+                const double temp = __shfl_sync(0xffffffffu, mine, k);
+                for (int i = lane; i < m; i += 32) if (i >= j) w.fjac[k][i] -= temp * w.fjac[j][i];
+            }
+            __syncwarp();
+#endif
+            LMW_UNROLL1
+            for (int k = j + 1; k < n; ++k) {
+#if !LMW_LANES
                 for (int i = lane; i < m; i += 32) if (i >= j) w.tmp[i] = w.fjac[j][i] * w.fjac[k][i];
                 __syncwarp();
                 const double sum = lmw_seq_sum(w.tmp, j, m);
@@ -104,6 +157,7 @@ __device__ LMW_NOINLINE void lmw_qrfac(LmWarpWork& w, int* ipvt, double* rdiag, 
                 __syncwarp();
                 for (int i = lane; i < m; i += 32) if (i >= j) w.fjac[k][i] -= temp * w.fjac[j][i];
                 __syncwarp();
+#endif
                 if (rdiag[k] != 0.0) {
                     double t = w.fjac[k][j] / rdiag[k];
                     rdiag[k] *= sqrt(fmax(0.0, 1.0 - t * t));
