@@ -88,6 +88,7 @@ SIGNATURES = {
     "sted_sample_binomial": (_i, [_vp, _vp, _i64, _u64, _u64, _vp, _vp]),
     "sted_philox4x32_10": (None, [ctypes.POINTER(_u32), ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),
     "sted_foreground_objectives": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sted_objectives_masked": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sted_nanodomain_candidates": (_i, [_vp, _i, _i, _i, ctypes.POINTER(_d), _i64, _d, _vp, _vp, _vp, _vp, _vp]),
     "sted_decorrelation_resolution": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _d, _d, _d, _d, _d, _vp, _vp]),
     "sted_gaussfit_validate": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _d, _vp, _vp, _vp]),

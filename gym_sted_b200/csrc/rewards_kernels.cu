@@ -122,9 +122,9 @@ __device__ __forceinline__ double percentile75(long long n, const int* hist, int
 
 __global__ void __launch_bounds__(R_THREADS) objectives_kernel(const float* __restrict__ conf1, const float* __restrict__ sted,
                                                              const float* __restrict__ conf2, int HW,
-                                                             uint8_t* __restrict__ fg_c, uint8_t* __restrict__ fg_s,
+                                                             uint8_t* fg_c, uint8_t* fg_s,
                                                              double* __restrict__ objs, int* __restrict__ flags,
-                                                             int* __restrict__ hist_scratch) {
+                                                             int* __restrict__ hist_scratch, const int masks_given) {
     extern __shared__ int sh[];
     __shared__ long long red[R_THREADS / 32 + 1];
     __shared__ int redi[R_THREADS / 32 + 1];
@@ -170,10 +170,11 @@ __global__ void __launch_bounds__(R_THREADS) objectives_kernel(const float* __re
     sum_s = block_sum(sum_s, red);
     __syncthreads();
 
-    // ---- Otsu thresholds and masks
-    const int thr_c = otsu_threshold(hist_c, nb_c, c_lo, HW, sum_c, &s_tmp[0]);
+    // ---- Otsu thresholds and masks (masks_given: the caller's masks are read instead, objectives.py's evaluate()
+    // takes them as arguments)
+    const int thr_c = masks_given ? 0 : otsu_threshold(hist_c, nb_c, c_lo, HW, sum_c, &s_tmp[0]);
     const bool sted_any = (s_hi != 0 || s_lo != 0);       // numpy.any(sted_image)
-    const int thr_s = sted_any ? otsu_threshold(hist_s, nb_s, s_lo, HW, sum_s, &s_tmp[1]) : 0;
+    const int thr_s = (sted_any && !masks_given) ? otsu_threshold(hist_s, nb_s, s_lo, HW, sum_s, &s_tmp[1]) : 0;
     __syncthreads();
     clear(hist_c, nb_c); clear(hist_s, nb_s);
     __syncthreads();
@@ -181,9 +182,9 @@ __global__ void __launch_bounds__(R_THREADS) objectives_kernel(const float* __re
     long long n_c = 0, n_s = 0, sc1 = 0, sc2 = 0, sbg = 0;
     for (int i = tid; i < HW; i += R_THREADS) {
         const int a = __float2int_rn(c1[i]), s = __float2int_rn(st[i]);
-        const bool fc = a > thr_c;
-        const bool fs = (sted_any ? (s > thr_s) : true) && fc;
-        mc[i] = fc; ms[i] = fs;
+        const bool fc = masks_given ? mc[i] != 0 : a > thr_c;
+        const bool fs = masks_given ? ms[i] != 0 : (sted_any ? (s > thr_s) : true) && fc;
+        if (!masks_given) { mc[i] = fc; ms[i] = fs; }
         if (fc) { ++n_c; sc1 += a; sc2 += __float2int_rn(c2[i]); atomicAdd(&hist_c[a - c_lo], 1); }
         if (fs) { ++n_s; atomicAdd(&hist_s[s - s_lo], 1); } else sbg += s;
     }
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(R_THREADS) objectives_kernel(const float* __re
     if (n_s > 0) {
         const double fg = percentile75(n_s, hist_s, nb_s, s_lo, &s_tmp[2]);
         const double bg = (double)sbg / (double)((long long)HW - n_s);
-        const double den = percentile75(n_c, hist_c, nb_c, c_lo, &s_tmp[2]);
+        // numpy.percentile of an empty selection is NaN (only possible with caller-supplied masks; n_c is block-uniform)
+        const double den = n_c > 0 ? percentile75(n_c, hist_c, nb_c, c_lo, &s_tmp[2]) : __longlong_as_double(0x7ff8000000000000LL);
         snr = (fg - bg) / den;
         if (snr < 0.0) flag |= 1;                         // the reference returns None here
     }
@@ -219,7 +221,24 @@ extern "C" int sted_foreground_objectives(const float* conf1_dev, const float* s
     const size_t smem = 2 * R_SMEM_BINS * sizeof(int);
     CUDA_TRY(cudaFuncSetAttribute(objectives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     objectives_kernel<<<B, R_THREADS, smem, (cudaStream_t)stream>>>(conf1_dev, sted_dev, conf2_dev, H * W, fg_c_dev, fg_s_dev,
-                                                                    objs_dev, flags_dev, hist_scratch_dev);
+                                                                    objs_dev, flags_dev, hist_scratch_dev, 0);
+    CUDA_TRY(cudaGetLastError());
+    return STED_OK;
+}
+
+extern "C" int sted_objectives_masked(const float* conf1_dev, const float* sted_dev, const float* conf2_dev, int B, int H, int W,
+                                      const uint8_t* fg_c_dev, const uint8_t* fg_s_dev, double* objs_dev, int32_t* flags_dev,
+                                      int32_t* hist_scratch_dev, void* stream) {
+    if (!conf1_dev || !sted_dev || !conf2_dev || !fg_c_dev || !fg_s_dev || !objs_dev || !flags_dev)
+        return fail(STED_EINVAL, "null pointer argument");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(STED_EINVAL, "B, H, W must be positive");
+    int rc = check_device();
+    if (rc) return rc;
+    const size_t smem = 2 * R_SMEM_BINS * sizeof(int);
+    CUDA_TRY(cudaFuncSetAttribute(objectives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    objectives_kernel<<<B, R_THREADS, smem, (cudaStream_t)stream>>>(conf1_dev, sted_dev, conf2_dev, H * W,
+                                                                    const_cast<uint8_t*>(fg_c_dev), const_cast<uint8_t*>(fg_s_dev),
+                                                                    objs_dev, flags_dev, hist_scratch_dev, 1);
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }

@@ -315,6 +315,16 @@ int sted_foreground_objectives(const float* conf1_dev, const float* sted_dev, co
                                double* objs_dev, int32_t* flags_dev, int32_t* hist_scratch_dev,
                                void* stream);
 
+/* Bleach / SNR objectives of B acquisitions for masks the CALLER supplies - the form the reference's objective classes
+ * have: Bleach.evaluate and Signal_Ratio(75).evaluate take sted_fg / confocal_fg as arguments
+ * (gym_sted/rewards/objectives.py:76-111; called through MORewardCalculator.evaluate, gym_sted/rewards/rewards.py:52-67).
+ * Arguments as sted_foreground_objectives, except that fg_c_dev / fg_s_dev (uint8, non-zero = foreground) are inputs
+ * and fg_s is used as given (the environments multiply it by fg_c before the call, mosted_env.py:244).  Empty
+ * selections give NaN like numpy's mean / percentile of nothing; no STED foreground gives SNR = 0. */
+int sted_objectives_masked(const float* conf1_dev, const float* sted_dev, const float* conf2_dev,
+                           int B, int H, int W, const uint8_t* fg_c_dev, const uint8_t* fg_s_dev,
+                           double* objs_dev, int32_t* flags_dev, int32_t* hist_scratch_dev, void* stream);
+
 /* Nanodomain candidates of B STED images: the integer part of NumberNanodomains.evaluate
  * (gym_sted/rewards/objectives.py:416-422): gaussian(sigma 0.5) -> > quantile 0.99 -> remove_small_objects(4,
  * 8-connected) -> label -> peak_local_max(min_distance 2, per label, no border exclusion).
