@@ -44,16 +44,19 @@ def algorithmic_bytes(H, W, bleach):
     return 4 * hp * wp + 4 * H * W + (4 * hp * wp if bleach else 0)
 
 
-def gather_executed_fraction(maps, tile=64, rows_per_thread=4, warps=8):
+def gather_executed_fraction(maps, tile=64, rows_per_thread=4):
     """Share of gather_kernel's multiply-adds that are issued for these (n, H, W) molecule maps: a warp (two groups of
     `rows_per_thread` output rows, all `tile` columns) skips a band row when both datamap rows it would read hold no
-    molecule inside the tile's window (G_SKIP in csrc/sted_kernels.cu).  Same geometry as the kernel, counted on the host."""
+    molecule inside the tile's window (G_SKIP in csrc/sted_kernels.cu).  Same geometry as the kernel (32-row tiles when
+    H mod 64 is in 1..32, as launch_gather chooses), counted on the host."""
     maps = np.asarray(maps)
     n, H, W = maps.shape
+    tile_h = 32 if -(-H // 32) * 32 < -(-H // 64) * 64 else 64
+    warps = tile_h // (2 * rows_per_thread)
     p, kp = K // 2, ((K + 1) + 3) & ~3
-    span_r, span_c = tile + K - 1, tile + kp
-    ty, tx = -(-H // tile), -(-W // tile)
-    nz = np.zeros((n, ty * tile + span_r, tx * tile + span_c), dtype=bool)
+    span_r, span_c = tile_h + K - 1, tile + kp
+    ty, tx = -(-H // tile_h), -(-W // tile)
+    nz = np.zeros((n, ty * tile_h + span_r, tx * tile + span_c), dtype=bool)
     nz[:, p:p + H, p:p + W] = maps != 0
     issued = total = 0
     for cx in range(tx):
@@ -62,7 +65,7 @@ def gather_executed_fraction(maps, tile=64, rows_per_thread=4, warps=8):
             for w in range(warps):
                 for yy in range(rows_per_thread + K - 1):
                     pairs = sum(0 <= yy - 2 * q <= K for q in range(rows_per_thread // 2))   # live row pairs of this band row
-                    r = cy * tile + w * 2 * rows_per_thread + yy
+                    r = cy * tile_h + w * 2 * rows_per_thread + yy
                     live = row_any[:, r] | row_any[:, r + rows_per_thread]
                     issued += pairs * int(live.sum())
                     total += pairs * n
@@ -547,7 +550,7 @@ def run_ours(args, rank, local_rank, world):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
-        roofline = {"bound": "fp32", "kernel": "gather_kernel<59>", "achieved": achieved, "peak": pk.value,
+        roofline = {"bound": "fp32", "kernel": "gather_kernel<59, 64>" if -(-H // 32) * 32 >= -(-H // 64) * 64 else "gather_kernel<59, 32>", "achieved": achieved, "peak": pk.value,
                     "unit": "TFLOP/s", "frac": achieved / pk.value if pk.value else None,
                     "traffic": ncu_traffic("gather_kernel") if (H, B) == (256, 256) else None,
                     "peak_source": "FP32 FFMA micro-benchmark run in this process (sted_fma_peak); "

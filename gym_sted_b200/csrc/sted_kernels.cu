@@ -197,12 +197,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-template <int KT>
-__global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqParams P, const __grid_constant__ CUtensorMap tmap) {
+// TH: output rows of a tile.  64 everywhere except for image heights whose last 64-row tile would be at most half full
+// (config 4's 96 rows: three 32-row tiles instead of two 64-row ones, a quarter of the work less); a 32-row tile is a
+// 128-thread CTA, three of them per SM.
+template <int KT, int TH>
+__global__ void __launch_bounds__((TH / G_RT) * 16, TH >= 64 ? G_MINB : 3) gather_kernel(const AcqParams P, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int THREADS = (TH / G_RT) * 16;
     const int K = KT ? KT : P.K;
     const int KP = KT ? STED_KPITCH(KT) : P.KP;
     const int PITCH = G_TW + KP;
-    const int rows = G_TH + K - 1;
+    const int rows = TH + K - 1;
     extern __shared__ __align__(128) float smem[];
     float* sD = smem;
     // PSF rows interleaved in pairs for FFMA2: sE2[u][v] = (E[u][v], E[u-1][v]) for u = 0..K, E[-1] = E[K] = 0
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     const long long t_start = clock64();
 #endif
     const int b = blockIdx.z;
-    const int tr0 = blockIdx.y * G_TH, tc0 = blockIdx.x * G_TW;
+    const int tr0 = blockIdx.y * TH, tc0 = blockIdx.x * G_TW;
     const int tid = threadIdx.x;
     const float* gE2 = P.tables + ((size_t)b * STED_TABLES + STED_TAB_E2) * K * KP;      // written by make_effective_kernel
 
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     {
         const float* src = P.din + (size_t)b * P.Hp * P.Wpitch;
         const int q = PITCH / 4;
-        for (int i = tid; i < rows * q; i += G_THREADS) {
+        for (int i = tid; i < rows * q; i += THREADS) {
             const int ry = i / q, cx = (i - ry * q) * 4;
             const int y = tr0 + ry, x = tc0 + cx;
             float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
             *reinterpret_cast<float4*>(sD + ry * PITCH + cx) = val;
         }
         const float4* e4 = reinterpret_cast<const float4*>(gE2);
-        for (int i = tid; i < (K + 1) * KP / 2; i += G_THREADS) reinterpret_cast<float4*>(sE2)[i] = __ldg(e4 + i);
+        for (int i = tid; i < (K + 1) * KP / 2; i += THREADS) reinterpret_cast<float4*>(sE2)[i] = __ldg(e4 + i);
     }
     __syncthreads();
 #endif
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     __shared__ uint32_t zrow[128];
     {
         const int nseg = PITCH / 4;                       // <= 32
-        for (int ry = tid >> 5; ry < rows; ry += G_THREADS / 32) {
+        for (int ry = tid >> 5; ry < rows; ry += THREADS / 32) {
             bool nz = false;
             if ((tid & 31) < nseg) {
                 const float4 v = *reinterpret_cast<const float4*>(sD + ry * PITCH + 4 * (tid & 31));
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(G_THREADS, G_MINB) gather_kernel(const AcqPara
     }
     __syncthreads();
     // detected power goes to `signal`; detect_kernel turns it into photon counts in place
-    for (int idx = tid; idx < G_TH * G_TW; idx += G_THREADS) {
+    for (int idx = tid; idx < TH * G_TW; idx += THREADS) {
         const int r = tr0 + (idx / G_TW), c = tc0 + (idx % G_TW);
         if (r >= P.H || c >= P.W) continue;
         const float I = sOut[idx];
@@ -1975,7 +1979,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tile_map(const AcqParams& P, CUtensorMap* map) {
+int make_tile_map(const AcqParams& P, CUtensorMap* map, int tile_h) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -1986,7 +1990,7 @@ int make_tile_map(const AcqParams& P, CUtensorMap* map) {
     }
     const cuuint64_t dims[3] = {(cuuint64_t)P.Wpitch, (cuuint64_t)P.Hp, (cuuint64_t)P.B};
     const cuuint64_t strides[2] = {(cuuint64_t)P.Wpitch * sizeof(float), (cuuint64_t)P.Hp * P.Wpitch * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)(G_TW + P.KP), (cuuint32_t)(G_TH + P.K - 1), 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)(G_TW + P.KP), (cuuint32_t)(tile_h + P.K - 1), 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     if (((uintptr_t)P.din & 15u) != 0) return fail(STED_EINVAL, "dmap_in_dev must be 16-byte aligned");
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(P.din), dims, strides, box, estr,
@@ -1996,19 +2000,25 @@ int make_tile_map(const AcqParams& P, CUtensorMap* map) {
     return STED_OK;
 }
 
+template <int KT, int TH>
+int launch_gather_t(const AcqParams& P, const CUtensorMap& map, cudaStream_t st) {
+    const size_t smem = ((size_t)(TH + P.K - 1) * (G_TW + P.KP) + 2 * (size_t)(P.K + 1) * P.KP) * sizeof(float);
+    const dim3 grid((P.W + G_TW - 1) / G_TW, (P.H + TH - 1) / TH, P.B);
+    int rc;
+    if ((rc = set_smem(gather_kernel<KT, TH>, smem))) return rc;
+    gather_kernel<KT, TH><<<grid, (TH / G_RT) * 16, smem, st>>>(P, map);
+    return STED_OK;
+}
+
 int launch_gather(const AcqParams& P, cudaStream_t st) {
-    const size_t smem = ((size_t)(G_TH + P.K - 1) * (G_TW + P.KP) + 2 * (size_t)(P.K + 1) * P.KP) * sizeof(float);
-    dim3 grid((P.W + G_TW - 1) / G_TW, (P.H + G_TH - 1) / G_TH, P.B);
+    // 32-row tiles when they cover the image with fewer computed rows than 64-row tiles (H mod 64 in 1..32)
+    const bool half = G_TH == 64 && ((P.H + 31) / 32) * 32 < ((P.H + 63) / 64) * 64;
     CUtensorMap map;
     int rc;
-    if ((rc = make_tile_map(P, &map))) return rc;
-    if (P.K == 59) {
-        if ((rc = set_smem(gather_kernel<59>, smem))) return rc;
-        gather_kernel<59><<<grid, G_THREADS, smem, st>>>(P, map);
-    } else {
-        if ((rc = set_smem(gather_kernel<0>, smem))) return rc;
-        gather_kernel<0><<<grid, G_THREADS, smem, st>>>(P, map);
-    }
+    if ((rc = make_tile_map(P, &map, half ? 32 : G_TH))) return rc;
+    if (P.K == 59) rc = half ? launch_gather_t<59, 32>(P, map, st) : launch_gather_t<59, G_TH>(P, map, st);
+    else rc = half ? launch_gather_t<0, 32>(P, map, st) : launch_gather_t<0, G_TH>(P, map, st);
+    if (rc) return rc;
     CUDA_TRY(cudaGetLastError());
     return STED_OK;
 }
