@@ -224,6 +224,8 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "acquisitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["config"]["l2"] = "n/a: CPU arm (host caches; nothing runs on the GPU)"
+    line["config"]["parallelism"] = f"{cores} host threads, one environment each"
     print(json.dumps(line), flush=True)
 
 
