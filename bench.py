@@ -225,7 +225,6 @@ def run_reference(args, rank, world):
         "gpu_launches": 0,
     }
     line["config"]["l2"] = "n/a: CPU arm (host caches; nothing runs on the GPU)"
-    line["config"]["parallelism"] = f"{cores} host threads, one environment each"
     print(json.dumps(line), flush=True)
 
 
