@@ -37,6 +37,18 @@ LM_HD LM_INL2 double lm_enorm(int n, const double* x) {
     const double rdwarf = 3.834e-20, rgiant = 1.304e19;
     double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
     const double agiant = rgiant / (double)n;
+    {   // every component in (rdwarf, agiant) - the case of all but degenerate fits: the general code below then ends in
+        // sqrt(s2 * (1.0 + (0 / s2) * (0 * 0))) = sqrt(s2) with the same s2 (same additions, same order), so this
+        // shortcut returns the identical value without the scaled accumulators' branches and the division
+        double q = 0.0;
+        bool mid = n > 0;
+        for (int i = 0; i < n; ++i) {
+            const double xabs = fabs(x[i]);
+            mid = mid && xabs > rdwarf && xabs < agiant;
+            q += xabs * xabs;
+        }
+        if (mid) return sqrt(q);
+    }
     LM_U1
     for (int i = 0; i < n; ++i) {
         const double xabs = fabs(x[i]);

@@ -233,13 +233,16 @@ __device__ inline int lm_fit_warp(const WarpResiduals& residuals, LmWarpWork& w,
         }
         gnorm = 0.0;
         if (fnorm != 0.0) {
+            double qn[LM_N];                                  // qtf[i] / fnorm: the same five quotients MINPACK forms 15 times
+            LM_U1
+            for (int i = 0; i < n; ++i) qn[i] = qtf[i] / fnorm;
             LM_U1
             for (int j = 0; j < n; ++j) {
                 const int l = ipvt[j];
                 if (wa2[l] != 0.0) {
                     double sum = 0.0;
                     LM_U1
-                    for (int i = 0; i <= j; ++i) sum += r[i + n * j] * (qtf[i] / fnorm);
+                    for (int i = 0; i <= j; ++i) sum += r[i + n * j] * qn[i];
                     gnorm = fmax(gnorm, fabs(sum / wa2[l]));
                 }
             }
