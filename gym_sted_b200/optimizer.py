@@ -85,6 +85,13 @@ class FluorescenceOptimizer:
     def optimize_batch(self, criteria) -> np.ndarray:
         """``criteria``: sequence of criterion dicts / ``Criterion`` objects.  Returns a (B,5) float64 array:
         ``sigma_abs`` (m^2, at the excitation wavelength), ``k1``, ``b``, signal reached, bleach reached."""
+        return self.optimize_batch_device(criteria)[0].cpu().numpy()
+
+    def optimize_batch_device(self, criteria):
+        """``optimize_batch`` queued on the current stream with nothing read back: returns ``(out, keep)``, the (B,5)
+        device tensor and the input buffers the caller must keep alive until the stream has run.  A fit is one CTA per
+        criterion and takes tens of milliseconds whatever the batch, so callers with several independent batches (one per
+        correction factor, ``BleachSampler.sample_batch``) queue them on different streams and wait once."""
         import torch
         B = len(criteria)
         m = self.microscope
@@ -99,7 +106,7 @@ class FluorescenceOptimizer:
             _lib.check(self.lib.sted_fluo_optimize(self._cache.data_ptr(), blob.data_ptr(), self.K, radius, ctypes.byref(fl),
                                                    ctypes.byref(det), crit.data_ptr(), B, self.iterations, out.data_ptr(),
                                                    torch.cuda.current_stream(self.device).cuda_stream))
-        return out.cpu().numpy()
+        return out, (crit, blob)
 
     def optimize(self, criterions) -> dict:
         """The reference's call and result layout (``utils.py:517-597`` / ``aggregate``, ``:493-515``)."""
