@@ -24,7 +24,14 @@
 namespace {
 
 constexpr double kPlanckO = 6.62607015e-34, kLightO = 299792458.0;
-constexpr int OPT_THREADS = 128;
+#ifndef OPT_THREADS_N
+#define OPT_THREADS_N 512
+#endif
+// One fit is latency: the bleach objective evaluates pow(I, b) in float64 on all K x K = 3 481 taps, ~1 500 times per
+// environment, and nothing else of the CTA runs meanwhile.  512 threads = 7 taps each (128 threads, 27 taps each: 34 ms
+// per launch whatever the batch; the order of the partial sums - and with it the last bits of an objective value -
+// depends on this number, the path the optimiser follows does not: tests/test_gpu_optimizer.py).
+constexpr int OPT_THREADS = OPT_THREADS_N;
 
 // CTA-wide sum; every thread returns the same value (fixed reduction order: bit-reproducible)
 __device__ double cta_sum(double v, double* scratch) {
@@ -178,7 +185,7 @@ extern "C" int sted_fluo_optimize(const double* psf_cache_dev, const double* blo
     int rc = check_device();
     if (rc) return rc;
     const size_t nb = (size_t)(2 * blob_radius + 1) * (2 * blob_radius + 1);
-    const size_t smem = (4 * nb + (size_t)2 * K * K + 8) * sizeof(double);
+    const size_t smem = (4 * nb + (size_t)2 * K * K + OPT_THREADS / 32 + 8) * sizeof(double);
     CUDA_TRY(cudaFuncSetAttribute(fluo_optimize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fluo_optimize_kernel<<<B, OPT_THREADS, smem, (cudaStream_t)stream>>>(psf_cache_dev, blob_dev, *fluo_host, *det_host, criteria_dev, K,
                                                                        blob_radius, iterations, out_dev);
