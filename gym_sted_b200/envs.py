@@ -103,35 +103,44 @@ class BleachSampler:
         the device-side ``FluorescenceOptimizer`` (``optimizer.py``), which follows the reference's optimisation path.
         ``samples``: per environment the sample type whose correction factor sizes the test structure
         (``optimizer.set_correction_factor(self.group)``, ``preference_sted_env.py:154``); one launch per distinct factor."""
+        return self.sample_batch_collect(self.sample_batch_launch(n, microscope, samples))
+
+    def sample_batch_launch(self, n, microscope=None, samples=None):
+        """First half of ``sample_batch``: draws the ``n`` criteria (the sampler's RNG advances here) and QUEUES the fits -
+        one launch per distinct factor, each on its own stream (a launch lasts as long as ONE fit, 25 ms, however few
+        environments it holds: six of them one after the other were 200 ms of a 256-environment reset).  Nothing is
+        waited for: an environment queues the fits of its NEXT episode and steps through the current one meanwhile."""
         if self.mode == "constant":
-            return [self.value or defaults.FLUO] * n
+            return ("constant", n)
         from .optimizer import FluorescenceOptimizer
         if self._optimizer is None:
             self._optimizer = FluorescenceOptimizer(microscope or make_microscope())
         opt = self._optimizer
-        self.criteria = [self.draw_criteria() for _ in range(n)]
-        fits = np.empty((n, 5))
+        criteria = [self.draw_criteria() for _ in range(n)]
         names = ["clusters"] * n if samples is None else list(samples)
-        # one launch per distinct factor, each on its own stream (a launch lasts as long as ONE fit - 34 ms - however
-        # few environments it holds: six of them one after the other were 200 ms of a 256-environment reset), one wait
-        groups = sorted(set(names))
-        if len(groups) == 1:
-            opt.set_correction_factor(groups[0])
-            fits[:] = opt.optimize_batch(self.criteria)
-        else:
-            cur = torch.cuda.current_stream(opt.device)
-            pending = []
-            for g, name in enumerate(groups):
-                idx = [i for i, s_ in enumerate(names) if s_ == name]
-                opt.set_correction_factor(name)
-                side = rewards.side_stream(opt.device, 8 + g)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    out_d, keep = opt.optimize_batch_device([self.criteria[i] for i in idx])
-                pending.append((idx, out_d, keep, side))
-            for idx, out_d, keep, side in pending:
-                side.synchronize()
-                fits[idx] = out_d.cpu().numpy()
+        cur = torch.cuda.current_stream(opt.device)
+        pending = []
+        for g, name in enumerate(sorted(set(names))):
+            idx = [i for i, s_ in enumerate(names) if s_ == name]
+            opt.set_correction_factor(name)
+            side = rewards.side_stream(opt.device, 8 + g)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                out_d, keep = opt.optimize_batch_device([criteria[i] for i in idx])
+            pending.append((idx, out_d, keep, side))
+        return ("fits", n, criteria, pending)
+
+    def sample_batch_collect(self, handle):
+        """Second half of ``sample_batch``: waits for the queued fits and returns the ``n`` parameter dicts; ``criteria``
+        then holds the criteria they were fitted to."""
+        if handle[0] == "constant":
+            return [self.value or defaults.FLUO] * handle[1]
+        _, n, criteria, pending = handle
+        fits = np.empty((n, 5))
+        for idx, out_d, keep, side in pending:
+            side.synchronize()
+            fits[idx] = out_d.cpu().numpy()
+        self.criteria = criteria
         lam_ex = int(round(self._optimizer.microscope.excitation.lambda_ * 1e9))
         out = []
         for sigma, k1, b, _, _ in fits:
@@ -200,6 +209,8 @@ class VectorContextualMOSTED:
                                                           seed=int(self.np_rng.integers(0, 2 ** 62)))
         self._truths = None          # rewards.DeviceTruths of the structures being imaged
         self._prefetched = None      # ((frames, coords, counts), event) of structures generated ahead on a side stream
+        self._fluo_pending = None    # BleachSampler.sample_batch_launch handle: the next episode's fluorophore fits
+        self.prefetch_fluorophores = os.environ.get("STED_B200_PREFETCH_FLUO", "1") != "0"
         self._coords_host = None     # the same coordinates on the host (list of (n_i, 2) int64 arrays), read back lazily
         self._pin = {}               # pinned host buffers of the end-of-step transfer
         self._conf_d = None
@@ -314,8 +325,16 @@ class VectorContextualMOSTED:
             self.np_rng = np.random.default_rng(seed)
             self.bleach_sampler.rng.seed(int(self.np_rng.integers(0, 2 ** 31 - 1)))
             self.synapse_gen.seed, self.synapse_gen.offset = int(self.np_rng.integers(0, 2 ** 62)), 0
-        fluos = [base.Fluorescence(**f) for f in self.bleach_sampler.sample_batch(self.B, self.microscope)] \
-            if self.bleach_sampler.mode != "constant" else None
+        fluos = None
+        if self.bleach_sampler.mode != "constant":
+            # the fits of THIS episode were queued at the previous reset (they ran under that episode's steps) unless
+            # this reset reseeds the sampler; the criteria sequence is the one of fitting at reset time either way
+            handle, self._fluo_pending = self._fluo_pending, None
+            if handle is None or seed is not None:
+                handle = self.bleach_sampler.sample_batch_launch(self.B, self.microscope)
+            fluos = [base.Fluorescence(**f) for f in self.bleach_sampler.sample_batch_collect(handle)]
+            if self.prefetch_fluorophores:
+                self._fluo_pending = self.bleach_sampler.sample_batch_launch(self.B, self.microscope)
         if fluos is None:
             self.microscope = make_microscope(self.bleach_sampler.sample())
             self.bm.microscope = self.microscope

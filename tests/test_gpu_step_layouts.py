@@ -49,3 +49,28 @@ def test_layout_is_chosen_by_step_size(monkeypatch):
     monkeypatch.setenv("STED_B200_STEP_LAYOUT", "sideways")
     with pytest.raises(ValueError):
         envs.make_vec("ContextualMOSTED-easy-hslb-v0", 4, seed=0, image_size=64)
+
+
+def test_fluorophore_fits_queued_ahead_give_the_same_episodes(monkeypatch):
+    """``ContextualMOSTED-hard-v0``: the fits of the next episode are queued at a reset and run under the episode's
+    steps (``STED_B200_PREFETCH_FLUO``); criteria, fitted parameters and rewards are those of fitting at reset time."""
+    if not torch.cuda.is_available():
+        pytest.fail("these tests need a CUDA device (no CPU fallback exists)")
+    runs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("STED_B200_PREFETCH_FLUO", flag)
+        vec = envs.make_vec("ContextualMOSTED-hard-v0", 5, compute_f1=True, seed=21, image_size=64)
+        assert vec.prefetch_fluorophores == (flag == "1")
+        rng = np.random.default_rng(8)
+        out = []
+        for episode in range(3):
+            vec.reset(seed=4 if episode == 0 else None)           # unseeded resets consume the queued fits
+            out.append(np.array([c["signal"]["target"] for c in vec.bleach_sampler.criteria]))
+            out.append(vec.bm.d_fluo.cpu().numpy().copy())           # the fitted StedFluoParams of every environment
+            for _ in range(2):
+                a = rng.uniform(vec.action_space.low, vec.action_space.high, (5, 3)).astype(np.float32)
+                (img, v), reward, _, _, info = vec.step(a)
+                out += [img.copy(), reward.copy(), info["mo_objs"].copy()]
+        runs.append(out)
+    for i, (x, y) in enumerate(zip(*runs)):
+        np.testing.assert_array_equal(x, y, err_msg=f"item {i}")
