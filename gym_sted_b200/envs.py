@@ -409,9 +409,11 @@ class VectorContextualMOSTED:
             marks.append(("device_done", time.perf_counter()))
         host = {k: v.numpy() for k, v in host.items()}
         if coords is None:
-            coords = [host["tc"][b, :host["tn"][b]].astype(np.int64) for b in range(B)]
+            tc, tn = host["tc"].astype(np.int64), host["tn"]      # one conversion, then per-environment views of the copy
+            coords = [tc[b, :tn[b]] for b in range(B)]
         if self._truths is not truths:
-            self._coords_host = [host["nc"][b, :host["nn"][b]].astype(np.int64) for b in range(B)]
+            nc, nn = host["nc"].astype(np.int64), host["nn"].copy()   # the pinned buffers are rewritten by the next step
+            self._coords_host = [nc[b, :nn[b]] for b in range(B)]
         else:
             self._coords_host = coords
         snr = np.where((host["oflags"] & 1) != 0, np.nan, host["objs"][:, 1])
