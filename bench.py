@@ -659,7 +659,10 @@ def run_env_step(args, rank, local_rank, world):
 
     acts = rng.uniform(env.action_space.low, env.action_space.high, (args.steps + args.warmup, B, len(env.actions)))
     for i in range(args.warmup):
-        env.step(acts[i])
+        # results are held until the next step returns, as in the timed loop: the device tensors of `info` then keep
+        # their blocks one step longer and the allocator's pools reach their steady size HERE (dropping the results
+        # at once left that growth - cudaMalloc calls, 10-100 ms - to the second timed step)
+        (img, vec), reward, done, _, info = env.step(acts[i])
     sync_all()
     if sampler.nvml is not None:
         sampler.samples.clear()
