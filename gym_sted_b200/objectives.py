@@ -212,3 +212,19 @@ def default_objectives(pixelsize=defaults.PIXELSIZE, res_cap=None):
     from . import rewards
     return {"Resolution": Resolution(pixelsize, res_cap if res_cap is not None else rewards.RES_CAP),
             "Bleach": Bleach(), "SNR": Signal_Ratio(75)}
+
+
+def install_into_gym_sted():
+    """Zero-source-change form of the swap: ``gym_sted/defaults.py:114-120`` holds ONE dict of objective instances
+    (``obj_dict``) that every environment module imports by name, so replacing its entries in place puts the CUDA
+    objectives behind every environment constructed afterwards (the reference's own ``MORewardCalculator`` /
+    ``NanodomainsRewardCalculator`` then call ``evaluate`` on these objects).  ``Squirrel`` (not on the path of the
+    BASELINE environments) is left alone.  Returns the replaced entries so that a caller can put them back."""
+    import gym_sted.defaults as ref_defaults
+    table = ref_defaults.obj_dict
+    old = {k: table[k] for k in ("SNR", "Bleach", "Resolution", "NbNanodomains")}
+    table["SNR"] = Signal_Ratio(getattr(old["SNR"], "percentile", 75))
+    table["Bleach"] = Bleach()
+    table["Resolution"] = Resolution(old["Resolution"].pixelsize, old["Resolution"].res_cap)
+    table["NbNanodomains"] = NumberNanodomains(getattr(old["NbNanodomains"], "threshold", 2))
+    return old

@@ -121,3 +121,33 @@ def test_reference_env_with_the_calculators_swapped():
         np.testing.assert_allclose(info["mo_objs"][1:], want[1:], rtol=1e-12)
         np.testing.assert_allclose(info["mo_objs"][0], want[0], rtol=1e-9)
         assert abs(info["f1-score"] - ref_nb.evaluate(*args, synapse=synapse)) < 1e-12
+
+
+@pytest.mark.skipif(shims.reference_root() is None, reason="reference not installed (run baseline/install_ref.sh)")
+def test_install_into_gym_sted_runs_the_reference_env_on_the_cuda_objectives():
+    """``objectives.install_into_gym_sted()``: no source change, the reference's own calculators call the CUDA objectives."""
+    _gpu()
+    shims.install("product")
+    import gym
+    import gym_sted  # noqa: F401
+    import gym_sted.defaults as ref_defaults
+    old = objectives.install_into_gym_sted()
+    try:
+        env = gym.make("gym_sted:ContextualMOSTED-easy-v0")
+        assert type(env.mo_reward_calculator.objectives["Bleach"]) is objectives.Bleach
+        assert type(env.nb_reward_calculator.objectives["NbNanodomains"]) is objectives.NumberNanodomains
+        np.random.seed(3)
+        env.reset(seed=3)
+        for _ in range(2):
+            synapse = env.synapse
+            action = np.array([0.12, 8e-6, 30e-6], dtype=np.float32)
+            obs, reward, done, truncated, info = env.step(action)
+            args = ([info["sted_image"]], info["conf1"], info["conf2"], info["fg_s"], info["fg_c"])
+            want = [old["Resolution"].evaluate(*args), old["Bleach"].evaluate(*args), old["SNR"].evaluate(*args)]
+            np.testing.assert_allclose(info["mo_objs"][1:], want[1:], rtol=1e-12)
+            np.testing.assert_allclose(info["mo_objs"][0], want[0], rtol=1e-9)
+            f1_ref = old["NbNanodomains"].evaluate(info["sted_image"], info["conf1"], info["conf2"], info["fg_s"], info["fg_c"],
+                                                   synapse=synapse)
+            assert abs(info["f1-score"] - f1_ref) < 1e-12
+    finally:
+        ref_defaults.obj_dict.update(old)

@@ -62,3 +62,23 @@ def test_no_cpu_path_behind_the_objectives():
                  lambda: objectives.get_foreground(img)):
         with pytest.raises(_lib.StedError):
             call()
+
+
+@pytest.mark.skipif(shims.reference_root() is None, reason="reference not installed (run baseline/install_ref.sh)")
+def test_install_into_gym_sted_replaces_the_shared_objective_table():
+    shims.install("product")
+    import gym_sted  # noqa: F401
+    import gym_sted.defaults as ref_defaults
+    from gym_sted.envs import mosted_env
+    assert mosted_env.obj_dict is ref_defaults.obj_dict          # one dict, imported by name
+    old = objectives.install_into_gym_sted()
+    try:
+        table = mosted_env.obj_dict
+        assert type(table["SNR"]) is objectives.Signal_Ratio and type(table["Bleach"]) is objectives.Bleach
+        assert type(table["Resolution"]) is objectives.Resolution and table["Resolution"].res_cap == old["Resolution"].res_cap
+        assert table["Resolution"].pixelsize == old["Resolution"].pixelsize
+        assert type(table["NbNanodomains"]) is objectives.NumberNanodomains
+        assert type(table["Squirrel"]).__module__.startswith("gym_sted")     # untouched
+    finally:
+        ref_defaults.obj_dict.update(old)
+    assert type(ref_defaults.obj_dict["Bleach"]).__module__.startswith("gym_sted")
