@@ -155,8 +155,7 @@ __device__ __forceinline__ float detect(const AcqParams& P, float I, float gain,
 #ifndef G_ROWS_PER_THREAD
 #define G_ROWS_PER_THREAD 4   // measured on B200: 8 -> 2.46 ms, 4 -> 2.0 ms, 2 -> 2.05 ms per 256x256^2 launch
 #endif
-constexpr int G_TH = G_TILE_H, G_TW = 64, G_RT = G_ROWS_PER_THREAD, G_THREADS = (G_TILE_H / G_ROWS_PER_THREAD) * 16,
-              kGatherUnroll = G_UNROLL;
+constexpr int G_TH = G_TILE_H, G_TW = 64, G_RT = G_ROWS_PER_THREAD, kGatherUnroll = G_UNROLL;   // threads per CTA: (TH / G_RT) * 16
 constexpr int G_MINB = 2;       // tile (60.5 KB) + row-interleaved PSF (28.8 KB) per CTA
 
 #ifndef G_TRIM_COLS
