@@ -1,0 +1,59 @@
+"""Host-side helpers of the path against the reference's own classes, imported as they are (``baseline/_ref``; gym,
+skimage, metrics, pysted stood in by ``tests/shims.py``):
+
+* ``Normalizer`` (``gym_sted/utils.py:414-440``) - bit-equal float64 on random action / objective vectors;
+* ``PreferenceArticulator`` / ``PrefNet`` (``gym_sted/prefnet/articulation.py:51-75``, ``prefNet.py:11-27``) - the same
+  scores and the same ranking from the same weights;
+* ``UniformCriterion`` / ``ChoiceCriterion`` (``utils.py:718-769``) - ``BleachSampler.draw_criteria`` consumes the
+  Mersenne-Twister stream in the reference's order, so a given seed gives the reference's criteria.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from gym_sted_b200 import defaults, envs, rewards
+from tests import shims
+
+pytestmark = pytest.mark.skipif(shims.reference_root() is None, reason="reference not installed (run baseline/install_ref.sh)")
+
+
+@pytest.fixture(scope="module")
+def gu():
+    shims.install("product")
+    import gym_sted  # noqa: F401
+    import gym_sted.utils as ref_utils
+    return ref_utils
+
+
+def test_normalizer_equals_the_reference(gu):
+    rng = np.random.default_rng(0)
+    for names, scales in ((["p_sted", "p_ex", "pdt"], defaults.action_spaces), (envs.OBJ_NAMES, defaults.scales_dict)):
+        ref, ours = gu.Normalizer(names, scales), envs.Normalizer(names, scales)
+        for _ in range(50):
+            x = rng.uniform(-1.0, 400.0, len(names)) * rng.choice([1e-6, 1e-3, 1.0], len(names))
+            np.testing.assert_array_equal(ours(x), ref(x))
+        batch = rng.uniform(0.0, 1.0, (7, len(names)))
+        np.testing.assert_array_equal(ours(batch), np.stack([ref(row) for row in batch]))
+
+
+def test_preference_articulator_equals_the_reference(gu):
+    from gym_sted.prefnet import PreferenceArticulator as RefArticulator
+    ref, ours = RefArticulator(), rewards.PreferenceArticulator(device="cpu")
+    rng = np.random.default_rng(1)
+    thetas = np.stack([rng.uniform(40, 300, 9), rng.uniform(0, 1, 9), rng.uniform(0, 2, 9)], axis=1)
+    for use_sigmoid in (False, True):
+        s_ref, best_ref, order_ref = ref.articulate(thetas, use_sigmoid=use_sigmoid)
+        s_ours, best_ours, order_ours = ours.articulate(thetas, use_sigmoid=use_sigmoid)
+        np.testing.assert_allclose(np.asarray(s_ours).ravel(), np.asarray(s_ref).ravel(), rtol=1e-6, atol=1e-7)
+        assert int(best_ours) == int(best_ref) and list(order_ours) == list(order_ref)
+
+
+@pytest.mark.parametrize("mode,cls", [("uniform", "UniformCriterion"), ("choice", "ChoiceCriterion")])
+def test_criteria_follow_the_reference_random_stream(gu, mode, cls):
+    for seed in (0, 7, 123):
+        random.seed(seed)
+        want = [getattr(gu, cls)(gu.defaults.fluorescence_criterions).criterions for _ in range(4)]
+        sampler = envs.BleachSampler(mode, seed=seed)
+        got = [sampler.draw_criteria() for _ in range(4)]
+        assert got == want, (mode, seed)
