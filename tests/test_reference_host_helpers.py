@@ -57,3 +57,29 @@ def test_criteria_follow_the_reference_random_stream(gu, mode, cls):
         sampler = envs.BleachSampler(mode, seed=seed)
         got = [sampler.draw_criteria() for _ in range(4)]
         assert got == want, (mode, seed)
+
+
+def test_gaussian_validation_of_the_oracle_equals_the_reference_code(gu):
+    """``gym_sted/rewards/utils.py:6-49`` (``fitgaussian`` / ``validate_positions``: numpy + scipy only) run as it is on
+    the reference's recorded STED images: the oracle's restatement - the checker of ``gaussfit_kernel`` - returns the same
+    fitted parameters bit for bit and keeps the same candidates, also for windows that overlap the image border."""
+    from gym_sted.rewards import utils as ref_ru
+    from oracle import rewards_oracle as ro
+    from tests import helpers
+    demo = helpers.load_demonstrations()
+    fits = kept = 0
+    for i in range(0, 50, 2):
+        sted = demo["sted_image"][i].astype(np.int64)
+        cand = ro.candidate_peaks(sted)
+        extra = np.array([[0, 0], [0, 63], [63, 0], [63, 63], [1, 30]])          # windows padded with zeros
+        guesses = np.concatenate([cand.reshape(-1, 2), extra]) if len(cand) else extra
+        want = ref_ru.validate_positions(guesses, sted, 20e-9)
+        got = ro.validate_positions(guesses, sted, 20e-9)
+        assert np.array_equal(np.asarray(got).reshape(-1, 2), np.asarray(want).reshape(-1, 2)), i
+        kept += len(want)
+        padded = np.pad(sted, 3, constant_values=0)
+        for row, col in guesses[:6]:
+            data = padded[row:row + 7, col:col + 7]
+            np.testing.assert_array_equal(ro.fit_gaussian(data), ref_ru.fitgaussian(data))
+            fits += 1
+    assert fits >= 100 and kept >= 20
