@@ -83,3 +83,31 @@ def test_gaussian_validation_of_the_oracle_equals_the_reference_code(gu):
             np.testing.assert_array_equal(ro.fit_gaussian(data), ref_ru.fitgaussian(data))
             fits += 1
     assert fits >= 100 and kept >= 20
+
+
+def test_objective_oracle_equals_the_reference_classes_beyond_the_recorded_episodes(gu):
+    """``Resolution`` / ``Bleach`` / ``Signal_Ratio`` of ``gym_sted/rewards/objectives.py`` are numpy code: run as they are
+    on images the fixture does not hold (other sizes, noise only, bright background, arbitrary masks), they give what
+    ``oracle/rewards_oracle.py`` - the checker of ``objectives_kernel`` and ``decorr_kernel`` - gives, bit for bit."""
+    from gym_sted.rewards import objectives as ref_obj
+    from oracle import rewards_oracle as ro
+    rng = np.random.default_rng(11)
+    res_ref, snr_ref, bl_ref = ref_obj.Resolution(pixelsize=20e-9, res_cap=300), ref_obj.Signal_Ratio(75), ref_obj.Bleach()
+    for k, (H, W) in enumerate([(64, 64), (96, 96), (64, 80), (128, 128), (50, 50), (64, 64)]):
+        yy, xx = np.mgrid[:H, :W]
+        blobs = sum(rng.uniform(20, 120) * np.exp(-((yy - rng.uniform(8, H - 8)) ** 2 + (xx - rng.uniform(8, W - 8)) ** 2)
+                                                  / (2 * rng.uniform(1.2, 3.0) ** 2)) for _ in range(6))
+        sted = rng.poisson(blobs * (k != 5) + 0.4)                   # the last image is noise only
+        conf1 = rng.poisson(3 * blobs + 2.0)
+        conf2 = rng.poisson(2 * blobs + 2.0)
+        fg_c, fg_s = rng.random((H, W)) < 0.3, rng.random((H, W)) < 0.15
+        if k == 3:
+            sted = sted + 50 * (~fg_s)                               # background above foreground: negative ratio
+        args = ([sted], conf1, conf2, fg_s, fg_c)
+        assert ro.resolution(sted, 20e-9, 300) == res_ref.evaluate(*args), (k, H, W)
+        assert ro.bleach(conf1, conf2, fg_c) == bl_ref.evaluate(*args), k
+        want = snr_ref.evaluate(*args)
+        got = ro.signal_ratio(sted, conf1, fg_s, fg_c)
+        assert (got is None and want is None) or got == want, (k, got, want)
+        if k == 3:
+            assert want is None
